@@ -1,0 +1,201 @@
+/*
+ * tefem.h - C ABI of the B200-native thermoelastic FEM hot path (libtefem_b200.so).
+ *
+ * The reference (rcapillon/thermoelasticity_fem) is pure Python and has no FFI layer; its
+ * "plugin boundary" for this path is the set of numpy/scipy call sites listed in SURVEY.md 8(b).
+ * Every entry point below names the reference call site(s) it replaces (file:line relative to the
+ * reference repository).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (taken from torch tensors with .data_ptr()) unless the
+ *     parameter name starts with `h_` (host pointer);
+ *   - the library never allocates device memory for the caller's data: Python/torch owns every
+ *     buffer; the library owns only its constant tables and an opaque solver/communicator handle;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless documented;
+ *   - every function returns an int status: 0 = TEFEM_OK, negative = error class; the message of
+ *     the last error of the calling thread is returned by tefem_last_error();
+ *   - fp64 everywhere; node-level indices are int32, value offsets are computed in 64 bits.
+ *
+ * Storage formats
+ *   pattern   node-block CSR: rowptr[N+1] (int32), colidx[P] (int32, ascending inside a row);
+ *             P = number of touched node pairs.  Block p of row i couples node i with node colidx[p].
+ *   planes    operator values as structure-of-arrays planes: vals[plane*P + p].  Plane layouts:
+ *               K (13 planes): uu(i,j) -> 3*i+j (0..8), ut(i) -> 9+i, tt -> 12      (no tu block)
+ *               M ( 3 planes): uu(i,i) -> i                                          (component diagonal)
+ *               D (4 / 7 / 13 planes): tu(j) -> j, tt -> 3; then uu: none (alpha_M = alpha_K = 0),
+ *                 uu(i,i) -> 4+i (alpha_K = 0), uu(i,j) -> 4+3*i+j (alpha_K != 0)
+ *             so that the bytes written equal 8 * (touched non-zeros), SURVEY.md 8(d).
+ *   system    solver matrix as array-of-structures 4x4 blocks: sys[p*16 + 4*r + c], 128-byte aligned.
+ */
+#ifndef TEFEM_H
+#define TEFEM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEFEM_OK                 0
+#define TEFEM_ERR_INVALID       -1   /* bad argument                                             */
+#define TEFEM_ERR_CUDA          -2   /* CUDA runtime error (message has the CUDA string)         */
+#define TEFEM_ERR_NEG_JACOBIAN  -3   /* elements.py:207-208  'Element {n} has negative jacobian.' */
+#define TEFEM_ERR_ZERO_JACOBIAN -4   /* elements.py:209-210  'Element {n} has zero jacobian.'     */
+#define TEFEM_ERR_NO_CONVERGE   -5   /* Krylov solve did not reach the tolerance                 */
+#define TEFEM_ERR_BREAKDOWN     -6   /* Krylov breakdown that restarts could not cure            */
+#define TEFEM_ERR_NCCL          -7   /* NCCL error                                               */
+
+#define TEFEM_OP_M 1
+#define TEFEM_OP_K 2
+#define TEFEM_OP_D 4
+
+#define TEFEM_KIND_MUU 1
+#define TEFEM_KIND_DTU 2
+#define TEFEM_KIND_DTT 4
+#define TEFEM_KIND_KUU 8
+#define TEFEM_KIND_KUT 16
+#define TEFEM_KIND_KTT 32
+
+/* Message of the last error raised on the calling thread (NUL-terminated, truncated to n). */
+int tefem_last_error(char* h_buf, size_t n);
+
+/* Library / build information: writes "tefem_b200 <version> sm_100a cuda <ver>" into h_buf. */
+int tefem_version(char* h_buf, size_t n);
+
+/* Quadrature tables exactly as the reference builds them at import time
+ * (elements.py:65-69 truncated Gauss literals, :76-87 shape values, :165-172):
+ *   h_W4 = w+w+w+w, h_S[4] = sum_g w N_a(g), h_NN[16] = sum_g w N_a(g) N_b(g).                */
+int tefem_quadrature_tables(double* h_W4, double* h_S, double* h_NN);
+
+/* Per-element matrices for a list of elements (parity / Element.compute_mat_*_e):
+ * replaces Element.compute_mat_{Muu,Dtu,Dtt,Kuu,Kut,Ktt}_e, elements.py:220-286, including the
+ * Jacobian of elements.py:199-218.  elem_idx may be NULL (= 0..n-1).  Outputs (row-major, may be
+ * NULL when the kind is not requested): Muu[n,12,12] Dtu[n,4,12] Dtt[n,4,4] Kuu[n,12,12]
+ * Kut[n,12,4] Ktt[n,4,4].  mat_table[n_mat,8] = (rho, lambda, mu, k, c, beta, T0, pad),
+ * materials.py:18-29.  bad_elem[2] (device int32, initialised to INT32_MAX by the caller):
+ * smallest element index with det < 0 / det == 0.                                              */
+int tefem_element_matrices(const double* coords, const int32_t* conn, const int32_t* mat_id,
+                           const double* mat_table, int n_mat,
+                           const int64_t* elem_idx, int64_t n, int kinds,
+                           double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut, double* Ktt,
+                           int32_t* bad_elem, void* stream);
+
+/* Element quadrature + atomics-free scatter into the node-block pattern (kernel K1).
+ * Replaces Model.assemble_M / assemble_K / assemble_D, model.py:87-118 (the per-element
+ * compute_mat_*_e calls, the np.ix_ scatter into the dense matrix and csc_array(dense)).
+ *
+ * Owner-computes schedule built once per mesh by the symbolic phase (host side, symbolic.py):
+ *   CTA c owns the blocks item_block[cta_item_ptr[c] .. cta_item_ptr[c+1]) and first stages the
+ *   geometry of the elements cta_elems[cta_elem_ptr[c] .. cta_elem_ptr[c+1]) in shared memory;
+ *   block p sums the contributions inc[inc_ptr[p] .. inc_ptr[p+1]) IN ASCENDING ELEMENT ORDER
+ *   (the order of the reference's loop, model.py:89,96,107); an entry of inc packs
+ *   (local element index << 4) | (a << 2) | b with a, b the local node numbers of (row, column).
+ *   Every output value is written exactly once: no atomics, bitwise reproducible.
+ * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
+ * The D layout follows alpha_M / alpha_K (model.py:112-117).
+ * bad_elem[2] as above; the call itself does not synchronise - use tefem_check_jacobian().      */
+int tefem_assemble(const double* coords, const int32_t* conn, const int32_t* mat_id,
+                   const double* mat_table, int n_mat,
+                   int32_t n_cta, int32_t max_cta_elems,
+                   const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
+                   const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
+                   int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+                   double* vals_M, double* vals_K, double* vals_D,
+                   int32_t* bad_elem, void* stream);
+
+/* Synchronises the stream, reads bad_elem[2] and returns TEFEM_OK, TEFEM_ERR_NEG_JACOBIAN or
+ * TEFEM_ERR_ZERO_JACOBIAN for the FIRST offending element in element order (the one the
+ * reference's loop would have raised on); *h_elem receives its index.                          */
+int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, void* stream);
+
+/* y[4N] (+)= A x for an operator in plane storage (used for the Dirichlet lifting
+ * K[free, dir] @ x_dir of model.py:326-339 and the Newmark right-hand side D@(.) + K@(.) of
+ * solvers.py:167-170).  plane_map[16]: plane index of entry (r, c) of a block, or -1.
+ * y = beta_y * y + alpha * A x.                                                                */
+int tefem_planes_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, int64_t n_blocks,
+                      const double* vals, const int8_t* h_plane_map,
+                      const double* x, double alpha, double beta_y, double* y, void* stream);
+
+/* Dirichlet elimination + solver-matrix formation (kernel K2).  Replaces
+ * apply_dirichlet_matrices (model.py:296-302) and `M_ff + gamma dt D_ff + beta dt^2 K_ff`
+ * (solvers.py:159-161): sys = cM*M + cD*D + cK*K on the shared pattern, with every row and column
+ * of a constrained DOF (dir_mask[4N] != 0) replaced by the identity, which is the reduced system
+ * A[free,:][:,free] embedded in the uniform 4x4 block structure.  Any of the
+ * plane pointers may be NULL (coefficient ignored).  d_layout = number of D planes (4, 7, 13).   */
+int tefem_form_system(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, int64_t n_blocks,
+                      const double* vals_M, double cM, const double* vals_D, int d_layout, double cD,
+                      const double* vals_K, double cK, const uint8_t* dir_mask,
+                      double* sys, void* stream);
+
+/* Block-Jacobi setup (kernel K5): inverts the 4x4 diagonal block of every node row (partial
+ * pivoting) into dinv[N,16] and left-scales the system in place, sys <- blockdiag(dinv) * sys,
+ * so that the Krylov iteration needs no separate preconditioner application.
+ * diag_idx[N] = position of the diagonal block of each row.                                    */
+int tefem_block_jacobi_scale(const int32_t* rowptr, const int32_t* diag_idx, int32_t n_rows,
+                             double* sys, double* dinv, void* stream);
+
+/* z[4N] = blockdiag(dinv) * r   (applies the same scaling to a right-hand side).               */
+int tefem_block_jacobi_apply(const double* dinv, int32_t n_rows, const double* r, double* z, void* stream);
+
+/* y = sys * x on the 4x4 block format (kernel K3), 4 threads per node row.                     */
+int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows,
+               const double* sys, const double* x, double* y, void* stream);
+
+/* Opaque Krylov solver handle (kernel K4/K6 driver).  Work vectors are provided by the caller:
+ * work must hold tefem_solver_work_doubles(n_rows) doubles.                                    */
+typedef struct tefem_solver tefem_solver;
+int64_t tefem_solver_work_doubles(int32_t n_rows);
+int tefem_solver_create(tefem_solver** out, int32_t n_rows, double* work, void* comm /* tefem_comm* or NULL */);
+int tefem_solver_destroy(tefem_solver* s);
+
+/* Halo description for the row-partitioned multi-GPU solve (ignored when comm == NULL):
+ * x vectors have n_rows owned node rows followed by n_halo halo node rows;
+ * send: for each neighbour k, the owned node rows send_idx[send_ptr[k] .. send_ptr[k+1]) go to
+ * rank h_nbr[k]; recv: halo rows [recv_ptr[k], recv_ptr[k+1]) (relative to n_rows) arrive from it.
+ * n_interior_rows: rows [0, n_int) that reference no halo column are listed first in row_order
+ * (so the interior product overlaps the exchange); row_order may be NULL (identity).            */
+int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int32_t* h_nbr,
+                          const int32_t* h_send_ptr, const int32_t* send_idx,
+                          const int32_t* h_recv_ptr,
+                          const int32_t* boundary_rows, int32_t n_boundary_rows,
+                          const int32_t* interior_rows, int32_t n_interior_rows);
+
+/* Left-block-Jacobi-scaled BiCGSTAB (replaces spsolve at solvers.py:26 and :172).
+ * Solves sys x = b where sys and b have ALREADY been scaled by tefem_block_jacobi_scale/apply.
+ * Stops when ||b - sys x|| <= rtol * ||b|| (true residual, re-evaluated before returning;
+ * recursive-residual drift triggers a restart from the current x).  x holds the initial guess
+ * on entry.  h_info[4] = {iterations, restarts, final relative residual, ||b||}.                */
+int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx,
+                   const double* sys, const double* b, double* x,
+                   double rtol, int max_iter, int check_every, double* h_info, void* stream);
+
+/* Fused Newmark kernels (kernel K7), solvers.py:167-178.
+ * predictor: w1 = v + (1-gamma) dt a ; w2 = x + dt v + 0.5 dt^2 (1-2 beta) a   (zero on constrained DOFs)
+ * corrector: v <- v + (1-gamma) dt a + gamma dt a_new ; x <- x + dt v_old + 0.5 dt^2 ((1-2beta) a + 2 beta a_new);
+ *            a <- a_new, all masked to the free DOFs (constrained DOFs keep x, v = a = 0).       */
+int tefem_newmark_predict(int64_t n, const double* x, const double* v, const double* a,
+                          double dt, double gamma, double beta, const uint8_t* dir_mask,
+                          double* w1, double* w2, void* stream);
+int tefem_newmark_correct(int64_t n, double* x, double* v, double* a, const double* a_new,
+                          double dt, double gamma, double beta, const uint8_t* dir_mask, void* stream);
+
+/* F[4*node[i] + c] += w[i] * h_coef[c], c = 0..3: the load vector as geometric nodal weights x a
+ * time-dependent amplitude (model.py:120-286: area/3 and volume/4 lumping).  node[] unique.     */
+int tefem_load_axpy(int64_t n_entries, const int32_t* node, const double* w, const double* h_coef,
+                    double* F, void* stream);
+
+/* ---- multi-GPU communicator (NCCL over NVLink), one process per GPU ------------------------- */
+typedef struct tefem_comm tefem_comm;
+/* h_id: 128-byte ncclUniqueId buffer; created on rank 0, broadcast by the caller (torch.distributed). */
+int tefem_comm_unique_id(const char* h_nccl_lib_path, char* h_id);
+int tefem_comm_create(tefem_comm** out, const char* h_nccl_lib_path, const char* h_id, int n_ranks, int rank);
+int tefem_comm_destroy(tefem_comm* c);
+/* in-place sum all-reduce of n doubles (dot-product packets) */
+int tefem_comm_allreduce_sum(tefem_comm* c, double* buf, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEFEM_H */

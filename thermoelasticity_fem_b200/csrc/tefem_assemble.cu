@@ -1,0 +1,403 @@
+// K1: element quadrature + atomics-free owner-computes scatter into the node-block pattern.
+//
+// Replaces the reference's assembly loops (model.py:87-118): per element the six
+// Element.compute_mat_*_e (elements.py:220-286), the np.ix_ scatter into a dense n_dofs^2 array
+// and csc_array(dense).  Design (DESIGN.md "K1"):
+//
+//   * the symbolic phase groups node rows into CTAs; a CTA first stages, in shared memory, the
+//     geometry record (inverse Jacobian columns = shape-function gradients, det, material-scaled
+//     weights) of every element that touches one of its rows (phase 1: coalesced int4 connectivity
+//     loads, gathers of node coordinates through L2);
+//   * then one thread per node-pair block walks that block's precomputed incidence list
+//     (element, a, b) in ascending element order - the slot map - and accumulates the block's
+//     13 (K) / 1 (M) / 4 (D) values in registers (phase 2), writing every output exactly once,
+//     coalesced, into structure-of-arrays planes.  No atomics, bitwise reproducible, and the
+//     summation order per entry is the reference's element order.
+//
+// The same per-thread routines are compiled for the host when TEFEM_HOST_EMU is defined; that
+// build is used only by tests/host_emulation to check the schedule logic in a GPU-less container
+// and is never loaded by the package.
+#include "tefem_element.cuh"
+
+#include <limits.h>
+#include <vector>
+
+namespace tefem {
+
+struct AssembleArgs {
+    const double* coords;
+    const int32_t* conn;
+    const int32_t* mat_id;
+    const double* mat_table;
+    const int32_t* cta_item_ptr;
+    const int32_t* cta_elem_ptr;
+    const int32_t* cta_elems;
+    const int32_t* item_block;
+    const uint32_t* inc_ptr;
+    const uint16_t* inc;
+    int64_t n_blocks;
+    double alpha_M, alpha_K;
+    double* vals_M;
+    double* vals_K;
+    double* vals_D;
+    int32_t* bad_elem;
+};
+
+// ---- per-thread routines (host + device) -------------------------------------------------------
+
+// Phase 1 for one staged element: returns det so that the caller can flag bad Jacobians.
+TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double W4, double* rec) {
+    const int32_t n0 = A.conn[4 * (int64_t)e], n1 = A.conn[4 * (int64_t)e + 1];
+    const int32_t n2 = A.conn[4 * (int64_t)e + 2], n3 = A.conn[4 * (int64_t)e + 3];
+    const double* mat = A.mat_table + MAT_STRIDE * A.mat_id[e];
+    return element_record(A.coords + 3 * (int64_t)n0, A.coords + 3 * (int64_t)n1,
+                          A.coords + 3 * (int64_t)n2, A.coords + 3 * (int64_t)n3, mat, W4, rec);
+}
+
+// Phase 2 for one block: walk the incidence list and write the planes.
+// DUU: 0 = D has no uu part, 1 = alpha_M only (3 diagonal planes), 2 = alpha_K != 0 (9 planes).
+template <int OPS, int DUU>
+TEFEM_HD void assemble_block(const AssembleArgs& A, int32_t p, const double* recs,
+                             const double* S, const double* NN) {
+    constexpr bool WANT_M = (OPS & TEFEM_OP_M) != 0, WANT_K = (OPS & TEFEM_OP_K) != 0, WANT_D = (OPS & TEFEM_OP_D) != 0;
+    constexpr bool NEED_K = WANT_K || (WANT_D && DUU == 2);
+    constexpr bool NEED_M = WANT_M || (WANT_D && DUU >= 1);
+    BlockAcc<NEED_K, NEED_M, WANT_D> acc;
+    acc.clear();
+    const uint32_t s = A.inc_ptr[p], t = A.inc_ptr[p + 1];
+    for (uint32_t k = s; k < t; ++k) {
+        const uint32_t w = A.inc[k];
+        block_accumulate<NEED_K, NEED_M, WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
+    }
+    const int64_t P = A.n_blocks;
+    if (WANT_M) {
+        A.vals_M[p] = acc.m;
+        A.vals_M[P + p] = acc.m;
+        A.vals_M[2 * P + p] = acc.m;
+    }
+    if (WANT_K) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A.vals_K[i * P + p] = acc.kuu[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) A.vals_K[(9 + i) * P + p] = acc.kut[i];
+        A.vals_K[12 * P + p] = acc.ktt;
+    }
+    if (WANT_D) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) A.vals_D[i * P + p] = acc.dtu[i];
+        A.vals_D[3 * P + p] = acc.dtt;
+        if (DUU == 1) {
+            const double m = A.alpha_M * acc.m;
+            A.vals_D[4 * P + p] = m;
+            A.vals_D[5 * P + p] = m;
+            A.vals_D[6 * P + p] = m;
+        }
+        if (DUU == 2) {
+            const double m = A.alpha_M * acc.m;   // alpha_M may be 0 here: adds an exact 0
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    A.vals_D[(4 + 3 * i + j) * P + p] = (i == j ? m : 0.0) + A.alpha_K * acc.kuu[3 * i + j];
+        }
+    }
+}
+
+// Dense element matrices of one element (parity path; elements.py:220-286).
+TEFEM_HD void element_dense(const double* rec, const double* S, const double* NN, int kinds,
+                            double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut, double* Ktt) {
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            BlockAcc<true, true, true> acc;
+            acc.clear();
+            block_accumulate<true, true, true>(acc, rec, a, b, S, NN);
+            if (kinds & TEFEM_KIND_MUU)
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) Muu[(3 * a + i) * 12 + 3 * b + j] = (i == j) ? acc.m : 0.0;
+            if (kinds & TEFEM_KIND_KUU)
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) Kuu[(3 * a + i) * 12 + 3 * b + j] = acc.kuu[3 * i + j];
+            if (kinds & TEFEM_KIND_KUT)
+                for (int i = 0; i < 3; ++i) Kut[(3 * a + i) * 4 + b] = acc.kut[i];
+            if (kinds & TEFEM_KIND_KTT) Ktt[a * 4 + b] = acc.ktt;
+            if (kinds & TEFEM_KIND_DTU)
+                for (int c = 0; c < 3; ++c) Dtu[a * 12 + 3 * b + c] = acc.dtu[c];
+            if (kinds & TEFEM_KIND_DTT) Dtt[a * 4 + b] = acc.dtt;
+        }
+}
+
+// ---- host side: quadrature tables ----------------------------------------------------------------
+
+static QuadTables make_quad_tables() {
+    // elements.py:65-69: truncated 10-digit literals; :76-87: N_a = c0 + c1 x + c2 y + c3 z evaluated
+    // left to right with the coefficient table of :56-61 ([1,-1,-1,-1], [0,1,0,0], ...).
+    const double w = 0.0416666667, ga = 0.5854101966, gb = 0.1381966011;
+    const double pts[4][3] = {{ga, gb, gb}, {gb, ga, gb}, {gb, gb, ga}, {gb, gb, gb}};
+    const double coef[4][4] = {{1., 0., 0., 0.}, {-1., 1., 0., 0.}, {-1., 0., 1., 0.}, {-1., 0., 0., 1.}};  // [row][a]
+    QuadTables q;
+    memset(&q, 0, sizeof(q));
+    for (int g = 0; g < 4; ++g) {
+        volatile double N[4];  // volatile: keep the reference's rounding sequence (no contraction)
+        for (int a = 0; a < 4; ++a) {
+            volatile double v = coef[0][a];
+            volatile double t1 = coef[1][a] * pts[g][0];
+            v = v + t1;
+            volatile double t2 = coef[2][a] * pts[g][1];
+            v = v + t2;
+            volatile double t3 = coef[3][a] * pts[g][2];
+            v = v + t3;
+            N[a] = v;
+        }
+        q.W4 += w;
+        for (int a = 0; a < 4; ++a) {
+            volatile double wn = w * N[a];
+            q.S[a] += wn;
+            for (int b = 0; b < 4; ++b) {
+                volatile double nn = N[a] * N[b];
+                volatile double wnn = w * nn;
+                q.NN[4 * a + b] += wnn;
+            }
+        }
+    }
+    return q;
+}
+
+const QuadTables& quad_tables() {
+    static const QuadTables q = make_quad_tables();
+    return q;
+}
+
+}  // namespace tefem
+
+using namespace tefem;
+
+extern "C" int tefem_quadrature_tables(double* h_W4, double* h_S, double* h_NN) {
+    const QuadTables& q = quad_tables();
+    if (h_W4) *h_W4 = q.W4;
+    if (h_S) memcpy(h_S, q.S, sizeof(q.S));
+    if (h_NN) memcpy(h_NN, q.NN, sizeof(q.NN));
+    return TEFEM_OK;
+}
+
+#ifdef __CUDACC__
+// ================================================================================================
+// Device kernels
+// ================================================================================================
+namespace tefem {
+
+__constant__ QuadTables c_quad;
+
+static int upload_quad() {
+    static bool done = false;   // per process; constant memory is per device context of this module
+    static int dev_done = -1;
+    int dev = 0;
+    TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!done || dev_done != dev) {
+        TEFEM_CUDA_CHECK(cudaMemcpyToSymbol(c_quad, &quad_tables(), sizeof(QuadTables)));
+        done = true;
+        dev_done = dev;
+    }
+    return TEFEM_OK;
+}
+
+constexpr int ASM_THREADS = 256;
+
+template <int OPS, int DUU>
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A) {
+    extern __shared__ double recs[];
+    const int cta = blockIdx.x;
+    const int e0 = A.cta_elem_ptr[cta], ne = A.cta_elem_ptr[cta + 1] - e0;
+    const double W4 = c_quad.W4;
+    for (int le = threadIdx.x; le < ne; le += ASM_THREADS) {
+        const int32_t e = __ldg(A.cta_elems + e0 + le);
+        const double det = stage_element(A, e, W4, recs + (size_t)le * REC_STRIDE);
+        if (!(det > 0.0)) {  // error path only: elements.py:207-210
+            if (det < 0.0) atomicMin(A.bad_elem, e);
+            else atomicMin(A.bad_elem + 1, e);
+        }
+    }
+    __syncthreads();
+    const int i0 = A.cta_item_ptr[cta], i1 = A.cta_item_ptr[cta + 1];
+    for (int it = i0 + threadIdx.x; it < i1; it += ASM_THREADS) {
+        const int32_t p = __ldg(A.item_block + it);
+        assemble_block<OPS, DUU>(A, p, recs, c_quad.S, c_quad.NN);
+    }
+}
+
+__global__ void __launch_bounds__(128) element_matrices_kernel(
+    const double* __restrict__ coords, const int32_t* __restrict__ conn, const int32_t* __restrict__ mat_id,
+    const double* __restrict__ mat_table, const int64_t* __restrict__ elem_idx, int64_t n, int kinds,
+    double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut, double* Ktt, int32_t* bad_elem) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t e = elem_idx ? elem_idx[t] : t;
+    AssembleArgs A;
+    A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
+    double rec[REC_STRIDE];
+    const double det = stage_element(A, (int32_t)e, c_quad.W4, rec);
+    if (!(det > 0.0)) {
+        if (det < 0.0) atomicMin(bad_elem, (int32_t)e);
+        else atomicMin(bad_elem + 1, (int32_t)e);
+    }
+    element_dense(rec, c_quad.S, c_quad.NN, kinds,
+                  Muu ? Muu + t * 144 : nullptr, Dtu ? Dtu + t * 48 : nullptr, Dtt ? Dtt + t * 16 : nullptr,
+                  Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
+}
+
+template <int OPS, int DUU>
+static int launch_assemble(const AssembleArgs& A, int n_cta, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set || smem > 48 * 1024) {
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    assemble_kernel<OPS, DUU><<<n_cta, ASM_THREADS, smem, st>>>(A);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+template <int OPS>
+static int dispatch_duu(const AssembleArgs& A, int duu, int n_cta, size_t smem, cudaStream_t st) {
+    if (!(OPS & TEFEM_OP_D)) return launch_assemble<OPS, 0>(A, n_cta, smem, st);
+    switch (duu) {
+        case 0: return launch_assemble<OPS, 0>(A, n_cta, smem, st);
+        case 1: return launch_assemble<OPS, 1>(A, n_cta, smem, st);
+        default: return launch_assemble<OPS, 2>(A, n_cta, smem, st);
+    }
+}
+
+}  // namespace tefem
+
+extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn, const int32_t* mat_id,
+                                      const double* mat_table, int n_mat, const int64_t* elem_idx, int64_t n,
+                                      int kinds, double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut,
+                                      double* Ktt, int32_t* bad_elem, void* stream) {
+    TEFEM_REQUIRE(coords && conn && mat_id && mat_table && bad_elem, "null input");
+    TEFEM_REQUIRE(n_mat > 0 && n >= 0, "sizes");
+    if (n == 0) return TEFEM_OK;
+    int rc = upload_quad();
+    if (rc) return rc;
+    element_matrices_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(
+        coords, conn, mat_id, mat_table, elem_idx, n, kinds, Muu, Dtu, Dtt, Kuu, Kut, Ktt, bad_elem);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_assemble(const double* coords, const int32_t* conn, const int32_t* mat_id,
+                              const double* mat_table, int n_mat, int32_t n_cta, int32_t max_cta_elems,
+                              const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
+                              const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
+                              int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+                              double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem, void* stream) {
+    TEFEM_REQUIRE(coords && conn && mat_id && mat_table && bad_elem, "null mesh input");
+    TEFEM_REQUIRE(cta_item_ptr && cta_elem_ptr && cta_elems && item_block && inc_ptr && inc, "null schedule");
+    TEFEM_REQUIRE(ops > 0 && ops < 8, "ops mask");
+    TEFEM_REQUIRE(!(ops & TEFEM_OP_M) || vals_M, "vals_M");
+    TEFEM_REQUIRE(!(ops & TEFEM_OP_K) || vals_K, "vals_K");
+    TEFEM_REQUIRE(!(ops & TEFEM_OP_D) || vals_D, "vals_D");
+    TEFEM_REQUIRE(max_cta_elems > 0 && max_cta_elems <= 4096, "max_cta_elems must fit 12 bits");
+    TEFEM_REQUIRE(n_mat > 0, "n_mat");
+    if (n_cta == 0) return TEFEM_OK;
+    const size_t smem = (size_t)max_cta_elems * REC_STRIDE * sizeof(double);
+    TEFEM_REQUIRE(smem <= 200 * 1024, "max_cta_elems exceeds shared memory");
+    int rc = upload_quad();
+    if (rc) return rc;
+    AssembleArgs A;
+    A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
+    A.cta_item_ptr = cta_item_ptr; A.cta_elem_ptr = cta_elem_ptr; A.cta_elems = cta_elems;
+    A.item_block = item_block; A.inc_ptr = inc_ptr; A.inc = inc;
+    A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
+    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
+    const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
+    cudaStream_t st = as_stream(stream);
+    switch (ops) {
+        case 1: return dispatch_duu<1>(A, duu, n_cta, smem, st);
+        case 2: return dispatch_duu<2>(A, duu, n_cta, smem, st);
+        case 3: return dispatch_duu<3>(A, duu, n_cta, smem, st);
+        case 4: return dispatch_duu<4>(A, duu, n_cta, smem, st);
+        case 5: return dispatch_duu<5>(A, duu, n_cta, smem, st);
+        case 6: return dispatch_duu<6>(A, duu, n_cta, smem, st);
+        default: return dispatch_duu<7>(A, duu, n_cta, smem, st);
+    }
+}
+
+extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, void* stream) {
+    int32_t h[2];
+    TEFEM_CUDA_CHECK(cudaMemcpyAsync(h, bad_elem, sizeof(h), cudaMemcpyDeviceToHost, as_stream(stream)));
+    TEFEM_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+    if (h[0] == INT_MAX && h[1] == INT_MAX) return TEFEM_OK;
+    const bool neg_first = h[0] < h[1];
+    const int32_t e = neg_first ? h[0] : h[1];
+    if (h_elem) *h_elem = e;
+    set_error("Element %d has %s jacobian.", e, neg_first ? "negative" : "zero");
+    return neg_first ? TEFEM_ERR_NEG_JACOBIAN : TEFEM_ERR_ZERO_JACOBIAN;
+}
+
+#else  // ------------------------------------------------------------------------------------------
+// TEFEM_HOST_EMU: sequential execution of the SAME per-thread routines (tests/host_emulation only).
+// ================================================================================================
+extern "C" int tefem_emu_assemble(const double* coords, const int32_t* conn, const int32_t* mat_id,
+                                  const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
+                                  const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
+                                  const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
+                                  int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+                                  double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
+    AssembleArgs A;
+    A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
+    A.cta_item_ptr = cta_item_ptr; A.cta_elem_ptr = cta_elem_ptr; A.cta_elems = cta_elems;
+    A.item_block = item_block; A.inc_ptr = inc_ptr; A.inc = inc;
+    A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
+    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
+    const QuadTables& q = quad_tables();
+    const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
+    std::vector<double> recs((size_t)max_cta_elems * REC_STRIDE);
+    for (int cta = 0; cta < n_cta; ++cta) {
+        const int e0 = cta_elem_ptr[cta], ne = cta_elem_ptr[cta + 1] - e0;
+        if (ne > max_cta_elems) return TEFEM_ERR_INVALID;
+        for (int le = 0; le < ne; ++le) {
+            const int32_t e = cta_elems[e0 + le];
+            const double det = stage_element(A, e, q.W4, recs.data() + (size_t)le * REC_STRIDE);
+            if (!(det > 0.0)) {
+                int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
+                if (e < *slot) *slot = e;
+            }
+        }
+        for (int it = cta_item_ptr[cta]; it < cta_item_ptr[cta + 1]; ++it) {
+            const int32_t p = item_block[it];
+#define TEFEM_EMU_CASE(O)                                                                    \
+    case O:                                                                                  \
+        if (duu == 0 || !((O) & TEFEM_OP_D)) assemble_block<O, 0>(A, p, recs.data(), q.S, q.NN); \
+        else if (duu == 1) assemble_block<O, 1>(A, p, recs.data(), q.S, q.NN);               \
+        else assemble_block<O, 2>(A, p, recs.data(), q.S, q.NN);                             \
+        break;
+            switch (ops) {
+                TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)
+                TEFEM_EMU_CASE(5) TEFEM_EMU_CASE(6) TEFEM_EMU_CASE(7)
+                default: return TEFEM_ERR_INVALID;
+            }
+#undef TEFEM_EMU_CASE
+        }
+    }
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* conn, const int32_t* mat_id,
+                                          const double* mat_table, int64_t n, int kinds, double* Muu, double* Dtu,
+                                          double* Dtt, double* Kuu, double* Kut, double* Ktt, int32_t* bad_elem) {
+    AssembleArgs A;
+    A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
+    const QuadTables& q = quad_tables();
+    for (int64_t e = 0; e < n; ++e) {
+        double rec[REC_STRIDE];
+        const double det = stage_element(A, (int32_t)e, q.W4, rec);
+        if (!(det > 0.0)) {
+            int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
+            if (e < *slot) *slot = (int32_t)e;
+        }
+        element_dense(rec, q.S, q.NN, kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
+                      Dtt ? Dtt + e * 16 : nullptr, Kuu ? Kuu + e * 144 : nullptr, Kut ? Kut + e * 48 : nullptr,
+                      Ktt ? Ktt + e * 16 : nullptr);
+    }
+    return TEFEM_OK;
+}
+#endif

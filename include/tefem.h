@@ -136,18 +136,20 @@ int tefem_form_system(const int32_t* rowptr, const int32_t* colidx, int32_t n_ro
 int tefem_block_jacobi_scale(const int32_t* rowptr, const int32_t* diag_idx, int32_t n_rows,
                              double* sys, double* dinv, void* stream);
 
-/* z[4N] = blockdiag(dinv) * r   (applies the same scaling to a right-hand side).               */
-int tefem_block_jacobi_apply(const double* dinv, int32_t n_rows, const double* r, double* z, void* stream);
+/* z[4N] = blockdiag(dinv) * r   (applies the same scaling to a right-hand side); entries of the
+ * constrained DOFs (dir_mask != 0, may be NULL) are set to 0 (their unknown is eliminated).      */
+int tefem_block_jacobi_apply(const double* dinv, int32_t n_rows, const double* r, double* z,
+                             const uint8_t* dir_mask, void* stream);
 
 /* y = sys * x on the 4x4 block format (kernel K3), 4 threads per node row.                     */
 int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows,
                const double* sys, const double* x, double* y, void* stream);
 
 /* Opaque Krylov solver handle (kernel K4/K6 driver).  Work vectors are provided by the caller:
- * work must hold tefem_solver_work_doubles(n_rows) doubles.                                    */
+ * work must hold tefem_solver_work_doubles(n_rows, n_halo) doubles, 128-byte aligned.                                    */
 typedef struct tefem_solver tefem_solver;
-int64_t tefem_solver_work_doubles(int32_t n_rows);
-int tefem_solver_create(tefem_solver** out, int32_t n_rows, double* work, void* comm /* tefem_comm* or NULL */);
+int64_t tefem_solver_work_doubles(int32_t n_rows, int32_t n_halo);
+int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n_halo, double* work, void* comm /* tefem_comm* or NULL */);
 int tefem_solver_destroy(tefem_solver* s);
 
 /* Halo description for the row-partitioned multi-GPU solve (ignored when comm == NULL):

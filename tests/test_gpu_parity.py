@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed reference outputs."""
+import numpy as np
+import pytest
+
+from conftest import golden, csc_from
+import parity
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["Muu", "Dtu", "Dtt", "Kuu", "Kut", "Ktt"]
+MAT1 = (2300, 64e9, 0.1, 1., 750., 4e-6, 20.)
+MAT2 = (2300, 64e9, 0.1, 1., 1., 4e-6, 20.)
+KUHN_MATS = {1: (2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: (7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+             3: (2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+
+
+def make_mesh(pts, groups, mats):
+    from thermoelasticity_fem_b200 import LinearThermoElastic, Mesh
+    mesh = Mesh().from_arrays(pts, groups["tet"], groups["tri"], groups["nodes"])
+    mesh.set_materials({k: LinearThermoElastic(*v) for k, v in mats.items()})
+    mesh.make_elements()
+    return mesh
+
+
+@pytest.fixture(scope="module")
+def sandwich_mesh1(sandwich):
+    pts, blocks, groups = sandwich
+    return make_mesh(pts, groups, {1: MAT1, 2: MAT1, 3: MAT1})
+
+
+@pytest.fixture(scope="module")
+def sandwich_mesh2(sandwich):
+    pts, blocks, groups = sandwich
+    return make_mesh(pts, groups, {1: MAT2, 2: MAT2, 3: MAT2})
+
+
+def kuhn_case():
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(4, 2, 3, jitter=0.2, seed=0)
+    return pts, dict(tet=tets, tri=tris, nodes=nodes)
+
+
+def test_library_loaded():
+    from thermoelasticity_fem_b200 import _lib
+    assert "sm_100a" in _lib.version()
+
+
+def test_quadrature_tables_match_oracle():
+    import ctypes
+    from thermoelasticity_fem_b200 import _lib
+    from oracle import tefem_oracle as orc
+    W4 = ctypes.c_double()
+    S = (ctypes.c_double * 4)()
+    NN = (ctypes.c_double * 16)()
+    _lib.check(_lib.load().tefem_quadrature_tables(ctypes.byref(W4), S, NN))
+    oW4, oS, oNN = orc.quadrature_tables()
+    assert W4.value == oW4 and list(S) == list(oS) and list(NN) == list(oNN.reshape(-1))     # bit-exact
+
+
+def test_element_matrices_sandwich(sandwich_mesh1):
+    g = golden("sandwich_elements.npz")
+    sub = g["subset"]
+    em = sandwich_mesh1.element_matrices(NAMES, sub)
+    for nm in NAMES:
+        ref = g[nm]
+        scale = np.abs(ref).reshape(len(sub), -1).max(axis=1)[:, None, None]
+        assert np.max(np.abs(em[nm] - ref) / scale) < parity.VALUE_TOL, nm
+    # Element view API (reference elements.py:181-286)
+    el = sandwich_mesh1.elements[int(sub[3])]
+    assert np.max(np.abs(el.compute_mat_Kuu_e() - g["Kuu"][3])) < parity.VALUE_TOL * np.abs(g["Kuu"][3]).max()
+    assert el.dofs_nums_u[:3] == [4 * el.nodes_nums[0], 4 * el.nodes_nums[0] + 1, 4 * el.nodes_nums[0] + 2]
+    assert el.dofs_nums_t == [4 * n + 3 for n in el.nodes_nums]
+
+
+def test_element_matrices_kuhn_all():
+    g = golden("kuhn_small.npz")
+    pts, groups = kuhn_case()
+    mesh = make_mesh(pts, groups, KUHN_MATS)
+    em = mesh.element_matrices(NAMES)
+    for nm in NAMES:
+        assert np.max(np.abs(em[nm] - g[nm])) <= parity.VALUE_TOL * np.abs(g[nm]).max(), nm
+
+
+def test_assembly_sandwich_vs_reference(sandwich_mesh2, sandwich):
+    from thermoelasticity_fem_b200 import Model
+    from oracle import tefem_oracle as orc
+    pts, blocks, groups = sandwich
+    g = golden("sandwich_operators.npz")
+    model = Model(sandwich_mesh2, alpha_M=0.2, alpha_K=0.2)
+    model.assemble_M()
+    model.assemble_K()
+    model.assemble_D()
+    m = orc.Material(*MAT2)
+    conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
+    ops = orc.assemble(pts, conn, rows, mat_id, 0.2, 0.2)
+    ops["M"] = orc.drop_component_zeros_M(ops["M"])
+    for nm in "MDK":
+        A = model.touched(nm)
+        ref = csc_from(g, nm)
+        parity.check_pattern(A, ref, ops[nm])                       # touched pattern bit-exact; reference subset
+        assert parity.scaled_error(A, ref) < parity.VALUE_TOL, nm   # values vs the reference's own assembly
+        assert parity.scaled_error(A, ops[nm]) < parity.VALUE_TOL, nm
+    assert model.touched("K").nnz == 519805 and model.mat_M.nnz == 119955
+    # the exported attribute mimics csc_array(dense): int32 sorted indices, zeros dropped
+    K = model.mat_K
+    assert K.format == "csc" and K.shape == (12476, 12476) and K.has_sorted_indices
+    assert abs(K.nnz - 519725) < 200
+    # fused launch == three launches, bitwise; repeated assembly bitwise reproducible
+    model2 = Model(sandwich_mesh2, alpha_M=0.2, alpha_K=0.2)
+    model2.assemble_MDK()
+    for nm in "MDK":
+        assert np.array_equal(model2._planes[nm].cpu().numpy(), model._planes[nm].cpu().numpy()), nm
+    model2.assemble_MDK()
+    for nm in "MDK":
+        assert np.array_equal(model2._planes[nm].cpu().numpy(), model._planes[nm].cpu().numpy()), nm
+
+
+def test_assembly_kuhn_variants():
+    from thermoelasticity_fem_b200 import Model
+    g = golden("kuhn_small.npz")
+    pts, groups = kuhn_case()
+    mesh = make_mesh(pts, groups, KUHN_MATS)
+    for tag_, (aM, aK) in {"D": (0.3, 0.05), "D_noray": (0., 0.), "D_aM": (0.3, 0.)}.items():
+        model = Model(mesh, alpha_M=aM, alpha_K=aK)
+        model.assemble_D()
+        ref = csc_from(g, tag_)
+        A = model.touched("D")
+        parity.check_pattern(A, ref)
+        assert parity.scaled_error(A, ref) < parity.VALUE_TOL, tag_
+    model = Model(mesh, alpha_M=0.3, alpha_K=0.05)
+    model.assemble_K()
+    model.assemble_M()
+    assert parity.scaled_error(model.touched("K"), csc_from(g, "K")) < parity.VALUE_TOL
+    assert parity.scaled_error(model.touched("M"), csc_from(g, "M")) < parity.VALUE_TOL
+    assert np.array_equal(parity.keys(model.mat_M), parity.keys(csc_from(g, "M")))
+
+
+def test_dirichlet_maps_loads_lifting_kuhn():
+    from thermoelasticity_fem_b200 import Model
+    g = golden("kuhn_small.npz")
+    pts, groups = kuhn_case()
+    mesh = make_mesh(pts, groups, KUHN_MATS)
+    model = Model(mesh,
+                  dict_dirichlet_U={4: [('x', 0.), ('y', 1e-4), ('z', 0.)], 5: [('x', 2e-4)]},
+                  dict_dirichlet_theta={4: 3.0, 6: -1.5},
+                  dict_nodal_forces={8: np.array([1e3, -2e3, 5e2])},
+                  dict_surface_forces={7: np.array([0., 1e5, -1e6])},
+                  dict_volume_forces={1: np.array([0., 0., -2300 * 9.81]), 3: np.array([1., 2., 3.])},
+                  dict_heat_flux={7: -25.}, dict_heat_source={2: 1e3}, alpha_M=0.3, alpha_K=0.05)
+    model.create_free_dofs_lists()
+    for k in ("free_dofs", "free_dofs_U", "free_dofs_theta"):
+        assert np.array_equal(getattr(model, k), g[k]), k
+    assert np.array_equal(np.sort(model.dirichlet_dofs_U), g["dirichlet_dofs_U_sorted"])
+    assert np.array_equal(np.sort(model.dirichlet_dofs_theta), g["dirichlet_dofs_theta_sorted"])
+    model.assemble_K()
+    model.assemble_F()
+    model.apply_dirichlet_matrices()
+    model.apply_dirichlet_F()
+    assert np.max(np.abs(model.vec_F - g["F"])) <= 1e-13 * np.abs(g["F"]).max()
+    assert np.max(np.abs(model.vec_F_f - g["F_f"])) <= 1e-12 * np.abs(g["F_f"]).max()
+    Kff = model.mat_K_f_f
+    ref = csc_from(g, "Kff")
+    assert Kff.shape == ref.shape
+    assert np.isin(parity.keys(ref), parity.keys(Kff)).all() or (abs(Kff - ref)).max() < 1e-12 * abs(ref).max()
+    assert (abs(Kff - ref)).max() <= 1e-12 * abs(ref).max()
+    # time-indexed loads
+    n_t = 5
+    model2 = Model(mesh, dict_surface_forces={7: np.linspace(0, 1, 3 * n_t).reshape(3, n_t) * 1e5},
+                   dict_heat_flux={6: np.linspace(1, 2, n_t)}, dict_heat_source={2: 7.5},
+                   dict_nodal_forces={8: np.array([1., 2., 3.])})
+    model2.assemble_F(idx_t=3)
+    assert np.max(np.abs(model2.vec_F - g["F_t3"])) <= 1e-13 * np.abs(g["F_t3"]).max()
+    with pytest.raises(ValueError, match="1 or 2 dimensions"):
+        Model(mesh, dict_surface_forces={7: np.zeros((2, 2, 2))}).assemble_F(idx_t=0)
+    with pytest.raises(ValueError, match="Unrecognized DOF"):
+        Model(mesh, dict_dirichlet_U={4: [('w', 0.)]}).create_free_dofs_lists()
+
+
+def test_negative_jacobian_raises():
+    from thermoelasticity_fem_b200 import Model
+    pts, groups = kuhn_case()
+    tets = {k: v.copy() for k, v in groups["tet"].items()}
+    tets[2][5] = tets[2][5][[0, 2, 1, 3]]                 # flips the orientation of element 48 + 5
+    mesh = make_mesh(pts, dict(tet=tets, tri=groups["tri"], nodes=groups["nodes"]), KUHN_MATS)
+    with pytest.raises(ValueError, match="Element 53 has negative jacobian."):
+        Model(mesh).assemble_K()
+    tets[1][7][3] = tets[1][7][2]                          # degenerate element 7 comes first in element order
+    mesh = make_mesh(pts, dict(tet=tets, tri=groups["tri"], nodes=groups["nodes"]), KUHN_MATS)
+    with pytest.raises(ValueError, match="Element 7 has zero jacobian."):
+        Model(mesh).assemble_K()
+
+
+def test_spmv_and_system_against_scipy(sandwich_mesh2):
+    import torch
+    from thermoelasticity_fem_b200 import Model, layout
+    model = Model(sandwich_mesh2, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
+                  dict_dirichlet_theta={4: 0., 5: 0.}, alpha_M=0.2, alpha_K=0.2)
+    model.create_free_dofs_lists()
+    model.assemble_MDK()
+    dm = sandwich_mesh2.device_mesh()
+    n = sandwich_mesh2.n_dofs
+    rng = np.random.default_rng(0)
+    xh = rng.standard_normal(n)
+    x = torch.from_numpy(xh).cuda()
+    y = torch.zeros_like(x)
+    for nm in "MDK":
+        dm.planes_spmv(model._planes[nm], model.plane_map(nm), x, y)
+        ref = model.touched(nm) @ xh
+        assert np.max(np.abs(y.cpu().numpy() - ref)) <= 1e-13 * np.abs(ref).max(), nm
+    dt, gam, bet = 1.8, 0.5, 0.25
+    sys = dm.form_system(model._planes, 1.0, gam * dt, bet * dt * dt, 13, model._dir_mask)
+    free = model.free_dofs
+    Kdyn = (model.touched("M") + gam * dt * model.touched("D") + bet * dt * dt * model.touched("K")).tocsr()
+    dm.spmv(sys, x, y)
+    mask = model._mask_host
+    ref = np.where(mask, xh, 0.0)
+    ref[free] = Kdyn[free, :][:, free] @ xh[free]
+    assert np.max(np.abs(y.cpu().numpy() - ref)) <= 1e-13 * np.abs(ref).max()
+    # block-Jacobi scaling: dinv * A_ii = I
+    sys2 = sys.clone()
+    dinv = dm.block_jacobi_scale(sys2)
+    diag = sys2[dm.schedule.diag_idx.long()].reshape(-1, 4, 4).cpu().numpy()
+    assert np.max(np.abs(diag - np.eye(4))) < 1e-12
+
+
+def test_steady_state_sandwich(sandwich_mesh1, sandwich):
+    from thermoelasticity_fem_b200 import Model, LinearSteadyState
+    from oracle import tefem_oracle as orc
+    pts, blocks, groups = sandwich
+    g = golden("sandwich_steady.npz")
+    dU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('x', 0.), ('y', 0.), ('z', 0.)]}
+    dT = {4: 0., 5: 0.}
+    model = Model(sandwich_mesh1, dict_dirichlet_U=dU, dict_dirichlet_theta=dT,
+                  dict_surface_forces={7: np.array([0., 0., -1e9])}, dict_volume_forces=None,
+                  dict_heat_flux={6: -25.}, dict_heat_source=None)
+    solver = LinearSteadyState(model)
+    solver.solve()
+    for k in ("free_dofs", "free_dofs_U", "free_dofs_theta"):
+        assert np.array_equal(getattr(model, k), g[k]), k
+    assert np.max(np.abs(model.vec_F - g["F"])) <= 1e-13 * np.abs(g["F"]).max()
+    m = orc.Material(*MAT1)
+    X, info = orc.steady_state(pts, groups, {1: m, 2: m, 3: m}, dU, dT, dict(surface={7: np.array([0., 0., -1e9])}, flux={6: -25.}))
+    eu, et = parity.field_errors(solver.X, X)
+    assert eu < parity.SOLUTION_TOL and et < parity.SOLUTION_TOL, (eu, et)
+    ru, rt = orc.field_scaled_residual(info["Kff"], solver.X[model.free_dofs], info["Ff"], model.free_dofs)
+    assert ru < 1e-8 and rt < 1e-8
+    # informational distance to the reference's raw spsolve (theta limited by SuperLU on this scaling, H2)
+    eu_raw, et_raw = parity.field_errors(solver.X, g["X_raw_spsolve"])
+    assert eu_raw < 1e-7 and et_raw < 1e-4
+    assert abs(np.abs(solver.U).max() - 0.2111117771259024) < 1e-8
+    assert abs(solver.T.max() - 46.05154818198166) < 1e-3 and solver.T.min() == 20.0
+    assert solver.U.shape == (3 * 3119,) and solver.T.shape == (3119,)
+
+
+def test_steady_state_kuhn_nonzero_dirichlet():
+    import __graft_entry__
+    __graft_entry__.smoke()
+
+
+def test_transient_sandwich_first_steps(sandwich_mesh2, sandwich):
+    from thermoelasticity_fem_b200 import Model, LinearTransient
+    from oracle import tefem_oracle as orc
+    pts, blocks, groups = sandwich
+    g = golden("sandwich_transient2.npz") if __import__("os").path.exists(
+        __import__("os").path.join(__import__("conftest").GOLDEN, "sandwich_transient2.npz")) else None
+    t_end, n_t = 1800e0, 1000
+    vec_t = np.linspace(0., t_end, n_t)
+    arr = np.zeros((3, n_t))
+    arr[0, :] = np.sin(2 * np.pi * vec_t / 900.) * -1e9
+    dU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]}
+    dT = {4: 0., 5: 0.}
+    model = Model(sandwich_mesh2, dict_dirichlet_U=dU, dict_dirichlet_theta=dT, dict_surface_forces={5: arr},
+                  alpha_M=2e-1, alpha_K=2e-1)
+    n_steps = 10
+    N = sandwich_mesh2.n_nodes
+    solver = LinearTransient(model, np.zeros(3 * N), np.zeros(3 * N), np.zeros(N), np.zeros(N), t_end, n_t, 0.5, 0.25,
+                             progress=False)
+    solver.prepare()
+    states = {}
+    for i in range(1, n_steps + 1):
+        info = solver.step(i)
+        states[i] = tuple(t.cpu().numpy().copy() for t in (solver._x, solver._v, solver._a))
+    m = orc.Material(*MAT2)
+    ref = orc.transient(pts, groups, {1: m, 2: m, 3: m}, dU, dT, dict(surface={5: arr}), 0.2, 0.2, t_end, n_t,
+                        n_steps=n_steps, keep=[1, 2, 10])
+    free = model.free_dofs
+    assert free.shape[0] == 11874
+    for i in (1, 2, 10):
+        for k, name in enumerate(("x", "v", "a")):
+            full = np.zeros(4 * N)
+            full[free] = ref["hist"][i][k]
+            eu, et = parity.field_errors(states[i][k], full)
+            assert eu < parity.SOLUTION_TOL and et < 10 * parity.SOLUTION_TOL, (i, name, eu, et)
+    if g is not None:
+        # reference's own states (raw spsolve each step): u to ~1e-8, theta to ~1e-5 (H2)
+        for col, step in enumerate(g["steps"]):
+            if step <= n_steps:
+                eu, et = parity.field_errors(states[int(step)][0], g["X"][:, col])
+                assert eu < 1e-6 and et < 1e-3, (step, eu, et)

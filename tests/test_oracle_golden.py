@@ -1,0 +1,150 @@
+"""The CPU oracle against the fixtures produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden, csc_from
+from oracle import tefem_oracle as orc
+import parity
+
+NAMES = ["Muu", "Dtu", "Dtt", "Kuu", "Kut", "Ktt"]
+MAT1 = (2300, 64e9, 0.1, 1., 750., 4e-6, 20.)     # examples/example_steadystate.py:22
+MAT2 = (2300, 64e9, 0.1, 1., 1., 4e-6, 20.)       # examples/example_transient_2.py:29
+KUHN_MATS = {1: (2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: (7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+             3: (2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+
+
+def fingerprint_weights(n):
+    k = np.arange(n, dtype=np.float64)
+    return 1.0 + np.mod(k * 0.6180339887498949, 1.0)
+
+
+def test_quadrature_constants():
+    W4, S, NN = orc.quadrature_tables()
+    assert W4 == 0.1666666668
+    assert S[0] == pytest.approx(0.041666666712499995, rel=1e-15)
+    assert S[1] == pytest.approx(0.04166666669583334, rel=1e-15)
+    assert 120 * NN[0, 0] == pytest.approx(2.0000000023501414, rel=1e-14)
+    assert 120 * NN[1, 1] == pytest.approx(2.0000000013501413, rel=1e-14)
+
+
+def test_material():
+    m = orc.Material(*MAT1)
+    assert m.beta == 320000.0
+    assert m.mat_C[0, 0] == pytest.approx(6.545454545454545e10, rel=1e-15)
+    assert m.mat_C[0, 1] == pytest.approx(7.272727272727273e9, rel=1e-15)
+    assert m.mat_C[3, 3] == pytest.approx(5.818181818181818e10, rel=1e-15)
+
+
+def test_element_matrices_sandwich(sandwich):
+    pts, blocks, groups = sandwich
+    g = golden("sandwich_elements.npz")
+    m = orc.Material(*MAT1)
+    conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
+    em = orc.element_matrices_batch(pts, conn, rows, mat_id)
+    sub = g["subset"]
+    for nm in NAMES:
+        ref = g[nm]
+        scale = np.abs(ref).reshape(len(sub), -1).max(axis=1)[:, None, None]
+        assert np.max(np.abs(em[nm][sub] - ref) / scale) < 5e-15, nm
+    # per-call restatement is bit-identical to the reference on the subset
+    for k, e in enumerate(sub[:40]):
+        pc = orc.element_matrices_percall(pts[conn[e]], m)
+        for nm in NAMES:
+            assert np.array_equal(pc[nm], g[nm][k]), nm
+    # fingerprints of ALL 13 712 elements
+    fp = g["fingerprint"]
+    for j, nm in enumerate(NAMES):
+        v = em[nm].reshape(conn.shape[0], -1)
+        mine = v @ fingerprint_weights(v.shape[1])
+        scale = np.abs(v).max(axis=1) * v.shape[1]
+        assert np.max(np.abs(mine - fp[:, j]) / scale) < 1e-14, nm
+
+
+def test_kuhn_small_everything():
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    g = golden("kuhn_small.npz")
+    pts, tets, tris, nodes = kuhn_box(4, 2, 3, jitter=0.2, seed=0)
+    mats = {k: orc.Material(*v) for k, v in KUHN_MATS.items()}
+    conn, mat_id, rows = orc.element_table(tets, mats)
+    em = orc.element_matrices_batch(pts, conn, rows, mat_id)
+    for nm in NAMES:
+        assert np.max(np.abs(em[nm] - g[nm])) <= 5e-15 * np.abs(g[nm]).max(), nm
+    for e in range(0, conn.shape[0], 7):
+        pc = orc.element_matrices_percall(pts[conn[e]], mats[int(np.array(list(tets))[mat_id[e]])])
+        for nm in NAMES:
+            assert np.array_equal(pc[nm], g[nm][e]), nm
+    ops = orc.assemble(pts, conn, rows, mat_id, 0.3, 0.05)
+    for nm in "DK":
+        ref = csc_from(g, nm)
+        parity.check_pattern(ops[nm], ref)
+        assert parity.scaled_error(ops[nm], ref) < parity.VALUE_TOL, nm
+    M = orc.drop_component_zeros_M(ops["M"])
+    assert np.array_equal(parity.keys(M), parity.keys(csc_from(g, "M")))
+    assert parity.scaled_error(M, csc_from(g, "M")) < parity.VALUE_TOL
+    for tag_, (aM, aK) in {"D_noray": (0., 0.), "D_aM": (0.3, 0.)}.items():
+        D = orc.assemble(pts, conn, rows, mat_id, aM, aK, which="D")["D"]
+        ref = csc_from(g, tag_)
+        parity.check_pattern(D, ref)
+        assert parity.scaled_error(D, ref) < parity.VALUE_TOL, tag_
+    dU = {4: [('x', 0.), ('y', 1e-4), ('z', 0.)], 5: [('x', 2e-4)]}
+    dT = {4: 3.0, 6: -1.5}
+    maps = orc.free_dofs_lists(pts.shape[0], tris, dU, dT)
+    for k in ("free_dofs", "free_dofs_U", "free_dofs_theta"):
+        assert np.array_equal(maps[k], g[k]), k
+    assert np.array_equal(maps["dirichlet_dofs_U"], g["dirichlet_dofs_U_sorted"])
+    assert np.array_equal(maps["dirichlet_dofs_theta"], g["dirichlet_dofs_theta_sorted"])
+    groups = dict(nodes=nodes, tri=tris, tet=tets)
+    loads = dict(nodal={8: np.array([1e3, -2e3, 5e2])}, surface={7: np.array([0., 1e5, -1e6])},
+                 volume={1: np.array([0., 0., -2300 * 9.81]), 3: np.array([1., 2., 3.])}, flux={7: -25.}, source={2: 1e3})
+    F = orc.assemble_F(pts, groups, loads)
+    assert np.max(np.abs(F - g["F"])) <= 1e-14 * np.abs(g["F"]).max()
+    Ff = orc.lift_rhs(F, ops["K"], maps["free_dofs"], 4 * pts.shape[0], tris, dU, dT)
+    assert np.max(np.abs(Ff - g["F_f"])) <= 1e-13 * np.abs(g["F_f"]).max()
+    n_t = 5
+    loads_t = dict(surface={7: np.linspace(0, 1, 3 * n_t).reshape(3, n_t) * 1e5}, flux={6: np.linspace(1, 2, n_t)},
+                   source={2: 7.5}, nodal={8: np.array([1., 2., 3.])})
+    Ft = orc.assemble_F(pts, groups, loads_t, idx_t=3)
+    assert np.max(np.abs(Ft - g["F_t3"])) <= 1e-14 * np.abs(g["F_t3"]).max()
+    # refined oracle solve vs the reference's raw spsolve (theta of spsolve is only ~1e-6 accurate, H2)
+    X, _ = orc.steady_state(pts, groups, mats, dU, dT, dict(nodal=loads["nodal"], surface=loads["surface"],
+                                                             volume=loads["volume"], flux=loads["flux"], source=loads["source"]))
+    eu, et = parity.field_errors(X, g["X_raw_spsolve"])
+    assert eu < 1e-6 and et < 1e-4
+
+
+def test_sandwich_operators(sandwich):
+    pts, blocks, groups = sandwich
+    g = golden("sandwich_operators.npz")
+    m = orc.Material(*MAT2)
+    conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
+    ops = orc.assemble(pts, conn, rows, mat_id, 0.2, 0.2)
+    assert ops["K"].nnz == 519805 and ops["D"].nnz == 519805             # touched: 13 P, P = 39 985
+    for nm, stored in (("K", 519725), ("D", 518194)):
+        ref = csc_from(g, nm)
+        assert ref.nnz == stored
+        parity.check_pattern(ops[nm], ref)
+        assert parity.scaled_error(ops[nm], ref) < parity.VALUE_TOL, nm
+    M = orc.drop_component_zeros_M(ops["M"])
+    assert M.nnz == 119955 and np.array_equal(parity.keys(M), parity.keys(csc_from(g, "M")))
+    assert parity.scaled_error(M, csc_from(g, "M")) < parity.VALUE_TOL
+
+
+def test_sandwich_steady(sandwich):
+    pts, blocks, groups = sandwich
+    g = golden("sandwich_steady.npz")
+    m = orc.Material(*MAT1)
+    dU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('x', 0.), ('y', 0.), ('z', 0.)]}
+    dT = {4: 0., 5: 0.}
+    loads = dict(surface={7: np.array([0., 0., -1e9])}, flux={6: -25.})
+    X, info = orc.steady_state(pts, groups, {1: m, 2: m, 3: m}, dU, dT, loads)
+    for k in ("free_dofs", "free_dofs_U", "free_dofs_theta"):
+        assert np.array_equal(info["maps"][k], g[k]), k
+    assert np.max(np.abs(info["F"] - g["F"])) <= 1e-14 * np.abs(g["F"]).max()
+    assert np.max(np.abs(info["Ff"] - g["F_f"])) <= 1e-14 * np.abs(g["F_f"]).max()
+    eu, et = parity.field_errors(X, g["X_raw_spsolve"])
+    assert eu < 1e-7 and et < 1e-4          # raw spsolve: u 4e-9, theta 3.6e-6
+    ru, rt = orc.field_scaled_residual(info["Kff"], X[info["maps"]["free_dofs"]], info["Ff"], info["maps"]["free_dofs"])
+    assert ru < 1e-11 and rt < 1e-11
+    T0 = orc.reference_temperature(pts.shape[0], groups["tet"], {1: m, 2: m, 3: m})
+    assert np.array_equal(g["X_raw_spsolve"][3::4] + T0, g["T"])
+    assert np.abs(g["U"]).max() == 0.2111117771259024

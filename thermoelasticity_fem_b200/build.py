@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libtefem_b200.so")
 SOURCES = ["tefem_core.cu", "tefem_assemble.cu", "tefem_system.cu", "tefem_krylov.cu", "tefem_comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+              "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
 def _stale(target, deps):

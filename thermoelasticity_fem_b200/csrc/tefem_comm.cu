@@ -1,0 +1,126 @@
+// Multi-GPU plumbing: NCCL over NVLink 5 / NVSwitch, one process per GPU.
+// The reference has no distributed path; this implements SURVEY.md 8(e):
+// halo exchange of interface node values (ncclSend/ncclRecv in one group, <= 2 neighbours for slab
+// partitions) and packed dot-product all-reduces (<= 5 doubles).
+#include "tefem_common.cuh"
+#include "tefem_comm.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace tefem {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl(const char* path) {
+    if (g_nccl.handle) return TEFEM_OK;
+    void* h = nullptr;
+    if (path && path[0]) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy torch already loaded
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        set_error("cannot load NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+        return TEFEM_ERR_NCCL;
+    }
+#define TEFEM_SYM(field, name)                                            \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                            \
+    if (!g_nccl.field) { set_error("NCCL symbol %s missing", name); return TEFEM_ERR_NCCL; }
+    TEFEM_SYM(GetUniqueId, "ncclGetUniqueId")
+    TEFEM_SYM(CommInitRank, "ncclCommInitRank")
+    TEFEM_SYM(CommDestroy, "ncclCommDestroy")
+    TEFEM_SYM(AllReduce, "ncclAllReduce")
+    TEFEM_SYM(Send, "ncclSend")
+    TEFEM_SYM(Recv, "ncclRecv")
+    TEFEM_SYM(GroupStart, "ncclGroupStart")
+    TEFEM_SYM(GroupEnd, "ncclGroupEnd")
+    TEFEM_SYM(GetErrorString, "ncclGetErrorString")
+#undef TEFEM_SYM
+    g_nccl.handle = h;
+    return TEFEM_OK;
+}
+
+#define TEFEM_NCCL_CHECK(expr)                                                                   \
+    do {                                                                                         \
+        ncclResult_t _r = (expr);                                                                \
+        if (_r != ncclSuccess) {                                                                 \
+            tefem::set_error("%s failed: %s", #expr, tefem::g_nccl.GetErrorString(_r));          \
+            return TEFEM_ERR_NCCL;                                                               \
+        }                                                                                        \
+    } while (0)
+
+}  // namespace tefem
+
+using namespace tefem;
+
+struct tefem_comm {
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+extern "C" int tefem_comm_unique_id(const char* h_nccl_lib_path, char* h_id) {
+    TEFEM_REQUIRE(h_id, "null id buffer");
+    int rc = load_nccl(h_nccl_lib_path);
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    TEFEM_NCCL_CHECK(g_nccl.GetUniqueId(&id));
+    memcpy(h_id, &id, sizeof(id));
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_comm_create(tefem_comm** out, const char* h_nccl_lib_path, const char* h_id, int n_ranks, int rank) {
+    TEFEM_REQUIRE(out && h_id && n_ranks > 0 && rank >= 0 && rank < n_ranks, "arguments");
+    int rc = load_nccl(h_nccl_lib_path);
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, h_id, sizeof(id));
+    tefem_comm* c = new tefem_comm();
+    c->n_ranks = n_ranks; c->rank = rank;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        delete c;
+        return TEFEM_ERR_NCCL;
+    }
+    *out = c;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_comm_destroy(tefem_comm* c) {
+    if (!c) return TEFEM_OK;
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_comm_allreduce_sum(tefem_comm* c, double* buf, int n, void* stream) {
+    TEFEM_REQUIRE(c && buf && n > 0, "arguments");
+    TEFEM_NCCL_CHECK(g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, c->comm, as_stream(stream)));
+    return TEFEM_OK;
+}
+
+int tefem_comm_neighbor_exchange(tefem_comm* c, int n_nbr, const int32_t* nbr, const int32_t* send_ptr,
+                                 const double* send, const int32_t* recv_ptr, double* recv, cudaStream_t st) {
+    TEFEM_REQUIRE(c, "null communicator");
+    TEFEM_NCCL_CHECK(g_nccl.GroupStart());
+    for (int k = 0; k < n_nbr; ++k) {
+        const size_t ns = 4 * (size_t)(send_ptr[k + 1] - send_ptr[k]), nr = 4 * (size_t)(recv_ptr[k + 1] - recv_ptr[k]);
+        if (ns) TEFEM_NCCL_CHECK(g_nccl.Send(send + 4 * (size_t)send_ptr[k], ns, ncclDouble, nbr[k], c->comm, st));
+        if (nr) TEFEM_NCCL_CHECK(g_nccl.Recv(recv + 4 * (size_t)recv_ptr[k], nr, ncclDouble, nbr[k], c->comm, st));
+    }
+    TEFEM_NCCL_CHECK(g_nccl.GroupEnd());
+    return TEFEM_OK;
+}

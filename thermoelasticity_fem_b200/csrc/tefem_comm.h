@@ -1,0 +1,11 @@
+// Internal: communicator used by the Krylov driver (NCCL resolved at run time with dlopen so that
+// the library loads - and the single-GPU path runs - without NCCL on the link line).
+#pragma once
+#include "tefem.h"
+#include <cuda_runtime.h>
+
+// Packed point-to-point exchange with the neighbouring row blocks: for neighbour k, the doubles
+// send[4*send_ptr[k] .. 4*send_ptr[k+1]) go to rank nbr[k] and recv[4*recv_ptr[k] .. 4*recv_ptr[k+1])
+// arrive from it, all inside one ncclGroupStart/End.
+int tefem_comm_neighbor_exchange(tefem_comm* c, int n_nbr, const int32_t* nbr, const int32_t* send_ptr,
+                                 const double* send, const int32_t* recv_ptr, double* recv, cudaStream_t st);

@@ -1,0 +1,574 @@
+// K3 / K4 / K6 / K7: block SpMV, fused BLAS-1, the BiCGSTAB driver, and the Newmark vector kernels.
+//
+// Reference call sites replaced (rcapillon/thermoelasticity_fem):
+//   solvers.py:26, :172   spsolve(K_ff, F_f), spsolve(K_dyn, rhs)   -> tefem_bicgstab
+//   solvers.py:167-178    Newmark right-hand side and updates        -> tefem_newmark_predict / _correct
+//   model.py:120-286      lumped loads                               -> tefem_load_axpy
+//
+// BiCGSTAB is run on the block-Jacobi left-scaled system (tefem_block_jacobi_scale), so no
+// preconditioner application appears in the iteration.  One iteration is
+//     v = A p            + partial (rhat.v)                      [spmv<1>]
+//     alpha = rho / (rhat.v)                                      [reduce + scalars]
+//     s = r - alpha v                                             [axpy]
+//     t = A s            + partials (t.s, t.t, s.s per field, rhat.s, rhat.t)  [spmv<8>]
+//     omega = t.s / t.t ; rho' = rhat.s - omega rhat.t ; beta = (rho'/rho)(alpha/omega)
+//     |r_f|^2 = s.s_f - 2 omega t.s_f + omega^2 t.t_f  (f = u, theta)  [reduce + scalars]
+//     x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)   [fused update]
+// i.e. two reduction points per iteration (each one packed all-reduce in the multi-GPU case), all
+// scalars stay on the device, and the host only polls a stop flag every `check_every` iterations.
+// Dot products are reduced in a fixed order (per-CTA partials, then one CTA over the partials):
+// results are bitwise reproducible for a given grid.
+#include "tefem_common.cuh"
+#include "tefem_comm.h"
+
+#include <math.h>
+#include <vector>
+
+namespace tefem {
+
+constexpr int SPMV_THREADS = 256;
+constexpr int MAX_PARTIAL_CTAS = 148 * 8;   // grid of the reducing kernels: 8 CTAs of 256 threads per SM
+constexpr int NSCAL = 24;
+
+// device scalar block
+// (SC_RR / SC_BB hold max_f |r_f|^2 / thr_f and 1: the convergence measure is per field, see scalars_omega_kernel)
+enum { SC_RHO = 0, SC_ALPHA, SC_OMEGA, SC_BETA, SC_RR, SC_BB, SC_RHV, SC_THR_U = 7, SC_PKT = 8 /* 8 packet slots 8..15 */,
+       SC_THR_T = 16, SC_BNORM2 = 17 };
+// device int block
+enum { IN_STOP = 0, IN_STOP_ITER = 1, IN_ITERS = 2, IN_REASON = 3 };   // reason: 1 converged, 2 breakdown
+
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// x is rewritten between launches but never during one: the non-coherent path is safe inside a kernel.
+__device__ __forceinline__ void ld256_x(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// y = A x over node rows; 4 consecutive threads own the 4 scalar rows of a node.
+// DOTS = 0: none; 1: partial of (w . y); 8: partials of (y.s_u, y.s_t, y.y_u, y.y_t, s.s_u, s.s_t, w.s, w.y) with
+// s = x (owned part) and the first three split by field (u rows r < 3, theta rows r == 3).
+// rows: optional list of node rows (interior / boundary split), else rows [0, n_rows).
+template <int DOTS>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx,
+                                                            const int32_t* __restrict__ rows, int32_t n_rows,
+                                                            const double* __restrict__ sys, const double* __restrict__ x,
+                                                            double* __restrict__ y, const double* __restrict__ w,
+                                                            double* __restrict__ partials, const int* __restrict__ ictl) {
+    __shared__ double red[8 * 32];
+    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
+    if (active) {
+        const int64_t n = 4 * (int64_t)n_rows;
+        for (int64_t tid = (int64_t)blockIdx.x * SPMV_THREADS + threadIdx.x; tid < n;
+             tid += (int64_t)gridDim.x * SPMV_THREADS) {
+            const int32_t i = rows ? rows[tid >> 2] : (int32_t)(tid >> 2);
+            const int r = (int)(tid & 3);
+            const int32_t s = rowptr[i], t = rowptr[i + 1];
+            double acc0 = 0.0, acc1 = 0.0;
+            int32_t p = s;
+            for (; p + 1 < t; p += 2) {
+                double a0, a1, a2, a3, b0, b1, b2, b3, x0, x1, x2, x3, z0, z1, z2, z3;
+                const int32_t j0 = colidx[p], j1 = colidx[p + 1];
+                ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
+                ld256(sys + 16 * (int64_t)(p + 1) + 4 * r, b0, b1, b2, b3);
+                ld256_x(x + 4 * (int64_t)j0, x0, x1, x2, x3);
+                ld256_x(x + 4 * (int64_t)j1, z0, z1, z2, z3);
+                acc0 += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
+                acc1 += b0 * z0 + b1 * z1 + b2 * z2 + b3 * z3;
+            }
+            if (p < t) {
+                double a0, a1, a2, a3, x0, x1, x2, x3;
+                ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
+                ld256_x(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
+                acc0 += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
+            }
+            const double yv = acc0 + acc1;
+            const int64_t row = 4 * (int64_t)i + r;
+            y[row] = yv;
+            if (DOTS == 1) d[0] += w[row] * yv;
+            if (DOTS == 8) {
+                const double sv = x[row], wv = w[row];
+                d[0] += yv * sv; d[1] += yv * yv; d[2] += sv * sv; d[3] += wv * sv; d[4] += wv * yv;
+            }
+        }
+    }
+    if (DOTS == 1) {
+        double v1[1] = {d[0]};
+        block_reduce_sum<1>(v1, red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = v1[0];
+    }
+    if (DOTS == 8) {
+        // a thread always owns the same scalar row type (the grid stride is a multiple of 4)
+        const bool th = (threadIdx.x & 3) == 3;
+        double v8[8] = {th ? 0.0 : d[0], th ? d[0] : 0.0, th ? 0.0 : d[1], th ? d[1] : 0.0,
+                        th ? 0.0 : d[2], th ? d[2] : 0.0, d[3], d[4]};
+        block_reduce_sum<8>(v8, red);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) partials[(size_t)blockIdx.x * 8 + k] = v8[k];
+        }
+    }
+}
+
+// out[k] (+)= sum over CTAs of partials[cta*NV + k], fixed order; one CTA.
+template <int NV>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int n_cta,
+                                                              double* __restrict__ out, int accumulate) {
+    __shared__ double red[NV * 32];
+    double d[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) d[k] = 0.0;
+    for (int c = threadIdx.x; c < n_cta; c += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) d[k] += partials[(size_t)c * NV + k];
+    block_reduce_sum<NV>(d, red);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = (accumulate ? out[k] : 0.0) + d[k];
+}
+
+// r = b - y ; rhat = r ; p = r ; partials (r.r_u, r.r_t, b.b_u, b.b_t)
+__global__ void __launch_bounds__(256) init_residual_kernel(int64_t n, const double* __restrict__ b,
+                                                            const double* __restrict__ y, double* __restrict__ r,
+                                                            double* __restrict__ rhat, double* __restrict__ p,
+                                                            double* __restrict__ partials) {
+    __shared__ double red[4 * 32];
+    double rr = 0.0, bb = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double bv = b[k], rv = bv - y[k];
+        r[k] = rv; rhat[k] = rv; p[k] = rv;
+        rr += rv * rv; bb += bv * bv;
+    }
+    const bool th = (threadIdx.x & 3) == 3;
+    double d[4] = {th ? 0.0 : rr, th ? rr : 0.0, th ? 0.0 : bb, th ? bb : 0.0};
+    block_reduce_sum<4>(d, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) partials[4 * blockIdx.x + k] = d[k];
+    }
+}
+
+// Convergence is judged PER FIELD on the block-Jacobi-scaled residual: |r_u| <= rtol |b_u| and
+// |r_theta| <= rtol |b_theta| (a field whose right-hand side vanishes is measured against |b|).
+// The u rows (~1e10) and theta rows (~1) of the coupled operator make a single norm blind to one of the
+// fields; measured on data/sandwich.msh: one norm at 1e-10 leaves a 2e-7 error in u.
+__device__ __forceinline__ double field_measure(double rr_u, double rr_t, double thr_u, double thr_t) {
+    const double mu = thr_u > 0.0 ? rr_u / thr_u : (rr_u > 0.0 ? INFINITY : 0.0);
+    const double mt = thr_t > 0.0 ? rr_t / thr_t : (rr_t > 0.0 ? INFINITY : 0.0);
+    return fmax(mu, mt);
+}
+
+__global__ void scalars_init_kernel(double* sc, int* ictl, double rtol2) {
+    const double rr_u = sc[SC_PKT], rr_t = sc[SC_PKT + 1], bb_u = sc[SC_PKT + 2], bb_t = sc[SC_PKT + 3];
+    const double bb = bb_u + bb_t;
+    sc[SC_THR_U] = bb_u > 0.0 ? bb_u : bb;
+    sc[SC_THR_T] = bb_t > 0.0 ? bb_t : bb;
+    sc[SC_BNORM2] = bb;
+    sc[SC_RHO] = rr_u + rr_t;
+    sc[SC_RR] = field_measure(rr_u, rr_t, sc[SC_THR_U], sc[SC_THR_T]);
+    sc[SC_BB] = 1.0;
+    sc[SC_ALPHA] = 1.0; sc[SC_OMEGA] = 1.0; sc[SC_BETA] = 0.0;
+    ictl[IN_STOP] = 0; ictl[IN_STOP_ITER] = -1; ictl[IN_REASON] = 0;
+    if (sc[SC_RR] <= rtol2) { ictl[IN_STOP] = 1; ictl[IN_REASON] = 1; }
+}
+
+__global__ void scalars_alpha_kernel(double* sc, int* ictl, int iter) {
+    if (ictl[IN_STOP]) return;
+    const double rhv = sc[SC_PKT];
+    sc[SC_RHV] = rhv;
+    if (rhv == 0.0 || !isfinite(rhv)) { ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = -2; ictl[IN_REASON] = 2; return; }
+    sc[SC_ALPHA] = sc[SC_RHO] / rhv;
+}
+
+__global__ void scalars_omega_kernel(double* sc, int* ictl, int iter, double rtol2) {
+    if (ictl[IN_STOP]) return;
+    const double ts_u = sc[SC_PKT], ts_t = sc[SC_PKT + 1], tt_u = sc[SC_PKT + 2], tt_t = sc[SC_PKT + 3];
+    const double ss_u = sc[SC_PKT + 4], ss_t = sc[SC_PKT + 5], hs = sc[SC_PKT + 6], ht = sc[SC_PKT + 7];
+    const double ts = ts_u + ts_t, tt = tt_u + tt_t;
+    const double thr_u = sc[SC_THR_U], thr_t = sc[SC_THR_T];
+    ictl[IN_ITERS] += 1;
+    if (tt == 0.0 || !isfinite(tt)) {
+        // t = A s = 0: s = 0 (converged at the half step) or breakdown
+        sc[SC_OMEGA] = 0.0; sc[SC_BETA] = 0.0; sc[SC_RR] = field_measure(ss_u, ss_t, thr_u, thr_t);
+        ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = iter; ictl[IN_REASON] = (sc[SC_RR] <= rtol2) ? 1 : 2;
+        return;
+    }
+    const double omega = ts / tt;
+    const double rho_new = hs - omega * ht;
+    const double rr_u = fmax(ss_u - 2.0 * omega * ts_u + omega * omega * tt_u, 0.0);
+    const double rr_t = fmax(ss_t - 2.0 * omega * ts_t + omega * omega * tt_t, 0.0);
+    const double rr = field_measure(rr_u, rr_t, thr_u, thr_t);
+    sc[SC_OMEGA] = omega;
+    sc[SC_RR] = rr;
+    const double rho = sc[SC_RHO], alpha = sc[SC_ALPHA];
+    sc[SC_RHO] = rho_new;
+    if (rr <= rtol2) {
+        sc[SC_BETA] = 0.0;
+        ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = iter; ictl[IN_REASON] = 1;
+        return;
+    }
+    if (omega == 0.0 || rho_new == 0.0 || !isfinite(omega) || !isfinite(rho_new)) {
+        sc[SC_BETA] = 0.0;
+        ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = iter; ictl[IN_REASON] = 2;
+        return;
+    }
+    sc[SC_BETA] = (rho_new / rho) * (alpha / omega);
+}
+
+// s = r - alpha v
+__global__ void __launch_bounds__(256) update_s_kernel(int64_t n, const double* __restrict__ r,
+                                                       const double* __restrict__ v, double* __restrict__ s,
+                                                       const double* __restrict__ sc, const int* __restrict__ ictl) {
+    if (ictl[IN_STOP]) return;
+    const double alpha = sc[SC_ALPHA];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        s[k] = r[k] - alpha * v[k];
+}
+
+// x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)
+__global__ void __launch_bounds__(256) update_xrp_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
+                                                         double* __restrict__ p, const double* __restrict__ s,
+                                                         const double* __restrict__ t, const double* __restrict__ v,
+                                                         const double* __restrict__ sc, const int* __restrict__ ictl,
+                                                         int iter) {
+    if (ictl[IN_STOP] && ictl[IN_STOP_ITER] != iter) return;
+    const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA], beta = sc[SC_BETA];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double pv = p[k], sv = s[k];
+        x[k] += alpha * pv + omega * sv;
+        const double rv = sv - omega * t[k];
+        r[k] = rv;
+        p[k] = rv + beta * (pv - omega * v[k]);
+    }
+}
+
+// send[k*4 + c] = x[4*idx[k] + c]
+__global__ void __launch_bounds__(256) pack_halo_kernel(int64_t n_nodes, const int32_t* __restrict__ idx,
+                                                        const double* __restrict__ x, double* __restrict__ send,
+                                                        const int* __restrict__ ictl) {
+    if (ictl && ictl[IN_STOP]) return;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 4 * n_nodes) return;
+    send[k] = x[4 * (int64_t)idx[k >> 2] + (k & 3)];
+}
+
+__global__ void __launch_bounds__(256) newmark_predict_kernel(int64_t n, const double* __restrict__ x,
+                                                              const double* __restrict__ v, const double* __restrict__ a,
+                                                              double c_v, double c_xv, double c_xa,
+                                                              const uint8_t* __restrict__ mask, double* __restrict__ w1,
+                                                              double* __restrict__ w2) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (mask && mask[k]) { w1[k] = 0.0; w2[k] = 0.0; return; }
+    const double vv = v[k], av = a[k];
+    w1[k] = vv + c_v * av;
+    w2[k] = x[k] + c_xv * vv + c_xa * av;
+}
+
+__global__ void __launch_bounds__(256) newmark_correct_kernel(int64_t n, double* __restrict__ x, double* __restrict__ v,
+                                                              double* __restrict__ a, const double* __restrict__ an,
+                                                              double dt, double gamma, double beta,
+                                                              const uint8_t* __restrict__ mask) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (mask && mask[k]) { v[k] = 0.0; a[k] = 0.0; return; }
+    const double vv = v[k], av = a[k], nv = an[k];
+    // solvers.py:173-178, same association order
+    v[k] = vv + (1.0 - gamma) * dt * av + gamma * dt * nv;
+    x[k] = x[k] + dt * vv + 0.5 * (dt * dt) * ((1.0 - 2.0 * beta) * av + 2.0 * beta * nv);
+    a[k] = nv;
+}
+
+__global__ void __launch_bounds__(256) load_axpy_kernel(int64_t n, const int32_t* __restrict__ node,
+                                                        const double* __restrict__ w, double c0, double c1, double c2,
+                                                        double c3, double* __restrict__ F) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double wk = w[k];
+    double* f = F + 4 * (int64_t)node[k];
+    if (c0 != 0.0) f[0] += wk * c0;
+    if (c1 != 0.0) f[1] += wk * c1;
+    if (c2 != 0.0) f[2] += wk * c2;
+    if (c3 != 0.0) f[3] += wk * c3;
+}
+
+}  // namespace tefem
+
+using namespace tefem;
+
+struct tefem_solver {
+    int32_t n_rows = 0, n_halo = 0;
+    int64_t n_own = 0, n_loc = 0;   // scalar sizes: owned, owned + halo
+    double* work = nullptr;
+    double *r = nullptr, *rhat = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;
+    double *partials = nullptr, *sc = nullptr, *sendbuf = nullptr;
+    int* ictl = nullptr;
+    int* h_ictl = nullptr;      // pinned
+    double* h_sc = nullptr;     // pinned
+    tefem_comm* comm = nullptr;
+    // halo
+    int n_nbr = 0;
+    std::vector<int32_t> nbr, send_ptr, recv_ptr;
+    const int32_t* send_idx = nullptr;
+    const int32_t* boundary_rows = nullptr;
+    int32_t n_boundary_rows = 0;
+    const int32_t* interior_rows = nullptr;
+    int32_t n_interior_rows = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
+};
+
+static int64_t vec_len(int32_t n_rows, int32_t n_halo) { return 4 * ((int64_t)n_rows + n_halo); }
+
+static int64_t align16(int64_t n) { return (n + 15) / 16 * 16; }   // keep every vector 128-byte aligned
+
+extern "C" int64_t tefem_solver_work_doubles(int32_t n_rows, int32_t n_halo) {
+    const int64_t nl = align16(vec_len(n_rows, n_halo));
+    return 6 * nl + align16((int64_t)MAX_PARTIAL_CTAS * 2 * 8) + align16(NSCAL) + align16(16) + align16(4 * (int64_t)n_rows);
+}
+
+extern "C" int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n_halo, double* work, void* comm) {
+    TEFEM_REQUIRE(out && work, "null pointer");
+    TEFEM_REQUIRE((((uintptr_t)work) & 127) == 0, "work must be 128-byte aligned");
+    tefem_solver* s = new tefem_solver();
+    s->n_rows = n_rows; s->n_halo = n_halo;
+    s->n_own = 4 * (int64_t)n_rows; s->n_loc = vec_len(n_rows, n_halo);
+    s->work = work;
+    const int64_t nl = align16(s->n_loc);
+    double* w = work;
+    s->r = w; w += nl; s->rhat = w; w += nl; s->p = w; w += nl; s->v = w; w += nl; s->s = w; w += nl; s->t = w; w += nl;
+    s->partials = w; w += align16((int64_t)MAX_PARTIAL_CTAS * 2 * 8);
+    s->sc = w; w += align16(NSCAL);
+    s->ictl = reinterpret_cast<int*>(w); w += align16(16);
+    s->sendbuf = w;
+    s->comm = reinterpret_cast<tefem_comm*>(comm);
+    TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_ictl, 4 * sizeof(int)));
+    TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_sc, NSCAL * sizeof(double)));
+    if (s->comm) {
+        TEFEM_CUDA_CHECK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+        TEFEM_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming));
+        TEFEM_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
+    }
+    *out = s;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_solver_destroy(tefem_solver* s) {
+    if (!s) return TEFEM_OK;
+    if (s->h_ictl) cudaFreeHost(s->h_ictl);
+    if (s->h_sc) cudaFreeHost(s->h_sc);
+    if (s->ev_ready) cudaEventDestroy(s->ev_ready);
+    if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    delete s;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int32_t* h_nbr,
+                                     const int32_t* h_send_ptr, const int32_t* send_idx, const int32_t* h_recv_ptr,
+                                     const int32_t* boundary_rows, int32_t n_boundary_rows,
+                                     const int32_t* interior_rows, int32_t n_interior_rows) {
+    TEFEM_REQUIRE(s, "null solver");
+    TEFEM_REQUIRE(n_halo == s->n_halo, "n_halo differs from tefem_solver_create");
+    TEFEM_REQUIRE(n_nbr == 0 || (h_nbr && h_send_ptr && h_recv_ptr && send_idx), "null halo arrays");
+    TEFEM_REQUIRE(n_boundary_rows + n_interior_rows == s->n_rows, "interior + boundary rows must cover the owned rows");
+    s->n_nbr = n_nbr;
+    s->nbr.assign(h_nbr, h_nbr + n_nbr);
+    s->send_ptr.assign(h_send_ptr, h_send_ptr + n_nbr + 1);
+    s->recv_ptr.assign(h_recv_ptr, h_recv_ptr + n_nbr + 1);
+    TEFEM_REQUIRE(n_nbr == 0 || s->send_ptr[n_nbr] <= s->n_rows, "send list larger than the owned rows");
+    s->send_idx = send_idx;
+    s->boundary_rows = boundary_rows; s->n_boundary_rows = n_boundary_rows;
+    s->interior_rows = interior_rows; s->n_interior_rows = n_interior_rows;
+    return TEFEM_OK;
+}
+
+static int grid_for(int64_t n_threads, int per_cta) {
+    int64_t g = ceil_div(n_threads, per_cta);
+    if (g > MAX_PARTIAL_CTAS) g = MAX_PARTIAL_CTAS;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <int DOTS>
+static int launch_spmv(const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
+                       const double* sys, const double* x, double* y, const double* w, double* partials,
+                       const int* ictl, int* n_cta_out, cudaStream_t st) {
+    const int g = grid_for(4 * (int64_t)n_rows, SPMV_THREADS);
+    if (n_cta_out) *n_cta_out = g;
+    spmv_kernel<DOTS><<<g, SPMV_THREADS, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+// Exchange the halo part of x (owned rows listed in send_idx go out, halo rows come in).
+static int halo_exchange(tefem_solver* s, double* x, const int* ictl, cudaStream_t st) {
+    if (!s->comm || s->n_nbr == 0) return TEFEM_OK;
+    const int64_t n_send = s->send_ptr[s->n_nbr];
+    if (n_send > 0) {
+        pack_halo_kernel<<<(unsigned)ceil_div(4 * n_send, 256), 256, 0, st>>>(n_send, s->send_idx, x, s->sendbuf, ictl);
+        TEFEM_LAUNCH_CHECK();
+    }
+    return tefem_comm_neighbor_exchange(s->comm, s->n_nbr, s->nbr.data(), s->send_ptr.data(), s->sendbuf,
+                                        s->recv_ptr.data(), x + s->n_own, st);
+}
+
+// y = A x with the halo exchange of x overlapped with the interior rows; DOTS partials packed.
+template <int DOTS>
+static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys, double* x,
+                     double* y, const double* w, const int* ictl, int* n_part_ctas, cudaStream_t st) {
+    if (!s->comm || s->n_nbr == 0) return launch_spmv<DOTS>(rowptr, colidx, nullptr, s->n_rows, sys, x, y, w,
+                                                            s->partials, ictl, n_part_ctas, st);
+    // comm stream: pack + send/recv ; main stream: interior rows ; then boundary rows
+    TEFEM_CUDA_CHECK(cudaEventRecord(s->ev_ready, st));
+    TEFEM_CUDA_CHECK(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
+    int rc = halo_exchange(s, x, ictl, s->comm_stream);
+    if (rc) return rc;
+    TEFEM_CUDA_CHECK(cudaEventRecord(s->ev_halo, s->comm_stream));
+    int g0 = 0, g1 = 0;
+    if (s->n_interior_rows > 0) {
+        rc = launch_spmv<DOTS>(rowptr, colidx, s->interior_rows, s->n_interior_rows, sys, x, y, w, s->partials, ictl, &g0, st);
+        if (rc) return rc;
+    }
+    TEFEM_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_halo, 0));
+    if (s->n_boundary_rows > 0) {
+        rc = launch_spmv<DOTS>(rowptr, colidx, s->boundary_rows, s->n_boundary_rows, sys, x, y, w,
+                               s->partials + (size_t)g0 * (DOTS > 0 ? DOTS : 1), ictl, &g1, st);
+        if (rc) return rc;
+    }
+    if (n_part_ctas) *n_part_ctas = g0 + g1;
+    return TEFEM_OK;
+}
+
+template <int NV>
+static int reduce_to_packet(tefem_solver* s, int n_cta, cudaStream_t st) {
+    reduce_partials_kernel<NV><<<1, 256, 0, st>>>(s->partials, n_cta, s->sc + SC_PKT, 0);
+    TEFEM_LAUNCH_CHECK();
+    if (s->comm) return tefem_comm_allreduce_sum(s->comm, s->sc + SC_PKT, NV, st);
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, const double* sys,
+                          const double* x, double* y, void* stream) {
+    TEFEM_REQUIRE(rowptr && colidx && sys && x && y, "null pointer");
+    TEFEM_REQUIRE((((uintptr_t)sys) & 127) == 0 && (((uintptr_t)x) & 31) == 0, "sys / x alignment");
+    if (n_rows == 0) return TEFEM_OK;
+    return launch_spmv<0>(rowptr, colidx, nullptr, n_rows, sys, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys,
+                              const double* b, double* x, double rtol, int max_iter, int check_every, double* h_info,
+                              void* stream) {
+    TEFEM_REQUIRE(s && rowptr && colidx && sys && b && x, "null pointer");
+    TEFEM_REQUIRE((((uintptr_t)sys) & 127) == 0 && (((uintptr_t)x) & 31) == 0, "sys / x alignment");
+    TEFEM_REQUIRE(rtol > 0 && max_iter > 0, "rtol / max_iter");
+    if (check_every < 1) check_every = 1;
+    cudaStream_t st = as_stream(stream);
+    const int64_t n = s->n_own;
+    const int vgrid = grid_for(n, 256);
+    const double rtol2 = rtol * rtol;
+    const int max_restarts = 20;
+    int total_iters = 0, restarts = 0;
+    double relres = -1.0, bnorm = 0.0;
+    int status = TEFEM_ERR_NO_CONVERGE;
+    TEFEM_CUDA_CHECK(cudaMemsetAsync(s->ictl, 0, 16 * sizeof(int), st));
+    for (;;) {
+        // ---- (re)start: r = b - A x, rhat = p = r
+        int npc = 0;
+        int rc = dist_spmv<0>(s, rowptr, colidx, sys, x, s->t, nullptr, nullptr, &npc, st);
+        if (rc) return rc;
+        init_residual_kernel<<<vgrid, 256, 0, st>>>(n, b, s->t, s->r, s->rhat, s->p, s->partials);
+        TEFEM_LAUNCH_CHECK();
+        rc = reduce_to_packet<4>(s, vgrid, st);
+        if (rc) return rc;
+        scalars_init_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, rtol2);
+        TEFEM_LAUNCH_CHECK();
+        TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_sc, s->sc, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, st));
+        TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
+        bnorm = sqrt(s->h_sc[SC_BNORM2]);
+        relres = sqrt(s->h_sc[SC_RR]);   // max over the fields of |r_f| / |b_f|
+        if (bnorm == 0.0) {   // homogeneous system: the solution is 0
+            TEFEM_CUDA_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
+            relres = 0.0; status = TEFEM_OK; break;
+        }
+        if (!isfinite(relres)) { set_error("non-finite residual in BiCGSTAB"); status = TEFEM_ERR_BREAKDOWN; break; }
+        if (s->h_ictl[IN_STOP] && s->h_ictl[IN_REASON] == 1) { status = TEFEM_OK; break; }   // true residual converged
+        if (total_iters >= max_iter || restarts > max_restarts) break;
+        // ---- iterate
+        bool stopped = false;
+        int it = 0;
+        while (!stopped && total_iters + it < max_iter) {
+            const int batch_end = it + check_every;
+            for (; it < batch_end && total_iters + it < max_iter; ++it) {
+                rc = dist_spmv<1>(s, rowptr, colidx, sys, s->p, s->v, s->rhat, s->ictl, &npc, st);
+                if (rc) return rc;
+                rc = reduce_to_packet<1>(s, npc, st);
+                if (rc) return rc;
+                scalars_alpha_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, it);
+                update_s_kernel<<<vgrid, 256, 0, st>>>(n, s->r, s->v, s->s, s->sc, s->ictl);
+                TEFEM_LAUNCH_CHECK();
+                rc = dist_spmv<8>(s, rowptr, colidx, sys, s->s, s->t, s->rhat, s->ictl, &npc, st);
+                if (rc) return rc;
+                rc = reduce_to_packet<8>(s, npc, st);
+                if (rc) return rc;
+                scalars_omega_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, it, rtol2);
+                update_xrp_kernel<<<vgrid, 256, 0, st>>>(n, x, s->r, s->p, s->s, s->t, s->v, s->sc, s->ictl, it);
+                TEFEM_LAUNCH_CHECK();
+            }
+            TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
+            stopped = s->h_ictl[IN_STOP] != 0;
+        }
+        total_iters = s->h_ictl[IN_ITERS];
+        // loop back: the true residual is recomputed; converged -> exit, otherwise restart from x
+        if (!stopped && total_iters >= max_iter) {
+            // fall through to one last true-residual evaluation
+        }
+        ++restarts;
+    }
+    if (h_info) {
+        h_info[0] = (double)total_iters;
+        h_info[1] = (double)restarts;
+        h_info[2] = relres;
+        h_info[3] = bnorm;
+    }
+    if (status == TEFEM_ERR_NO_CONVERGE)
+        set_error("BiCGSTAB did not converge: %d iterations, %d restarts, relative residual %.3e (rtol %.3e)",
+                  total_iters, restarts, relres, rtol);
+    return status;
+}
+
+extern "C" int tefem_newmark_predict(int64_t n, const double* x, const double* v, const double* a, double dt,
+                                     double gamma, double beta, const uint8_t* dir_mask, double* w1, double* w2,
+                                     void* stream) {
+    TEFEM_REQUIRE(x && v && a && w1 && w2, "null pointer");
+    if (n == 0) return TEFEM_OK;
+    // solvers.py:168-170: v + (1-gamma) dt a ; x + dt v + 0.5 dt^2 (1-2 beta) a
+    newmark_predict_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+        n, x, v, a, (1.0 - gamma) * dt, dt, 0.5 * (dt * dt) * (1.0 - 2.0 * beta), dir_mask, w1, w2);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_newmark_correct(int64_t n, double* x, double* v, double* a, const double* a_new, double dt,
+                                     double gamma, double beta, const uint8_t* dir_mask, void* stream) {
+    TEFEM_REQUIRE(x && v && a && a_new, "null pointer");
+    if (n == 0) return TEFEM_OK;
+    newmark_correct_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(n, x, v, a, a_new, dt, gamma, beta,
+                                                                                       dir_mask);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_load_axpy(int64_t n_entries, const int32_t* node, const double* w, const double* h_coef, double* F,
+                               void* stream) {
+    TEFEM_REQUIRE(node && w && h_coef && F, "null pointer");
+    if (n_entries == 0) return TEFEM_OK;
+    load_axpy_kernel<<<(unsigned)ceil_div(n_entries, 256), 256, 0, as_stream(stream)>>>(n_entries, node, w, h_coef[0],
+                                                                                         h_coef[1], h_coef[2], h_coef[3], F);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}

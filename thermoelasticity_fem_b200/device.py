@@ -1,0 +1,222 @@
+"""Device-side engine: owns the torch tensors (device memory) and calls the CUDA library.
+
+This is the thin host layer between the reference-compatible classes (mesh / model / solvers) and
+the C ABI of ``include/tefem.h``.  Everything here requires a CUDA device; there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, layout
+from .symbolic import Schedule, build_schedule
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+class DeviceMesh:
+    """Mesh tables + symbolic schedule resident in HBM.
+
+    coords[N,3] f64, conn[E,4] int32 (reference element order, ``mesh.py:51-58``), mat_id[E] int32,
+    mat_table[n_mat,8] f64.  ``n_rows`` (< N) restricts assembly to the owned node rows of a
+    row-partitioned multi-GPU run (owned nodes are numbered first)."""
+
+    def __init__(self, coords, conn, mat_id, mat_table, n_rows=None, device=None, schedule=None):
+        self.device = device if device is not None else _lib.require_cuda()
+        self.lib = _lib.load()
+        dev = self.device
+        self.coords = torch.as_tensor(coords, dtype=torch.float64).to(dev).contiguous()
+        conn_t = torch.as_tensor(conn).to(dev)
+        self.n_nodes = int(self.coords.shape[0])
+        self.n_elems = int(conn_t.shape[0])
+        self.n_rows = self.n_nodes if n_rows is None else int(n_rows)
+        self.conn = _i32(conn_t)
+        self.mat_id = _i32(torch.as_tensor(mat_id).to(dev))
+        self.mat_table = torch.as_tensor(mat_table, dtype=torch.float64).to(dev).contiguous()
+        self.n_mat = int(self.mat_table.shape[0])
+        if schedule is None:
+            schedule = build_schedule(conn_t, self.n_nodes, self.n_rows)
+        self.schedule: Schedule = schedule.to(dev)
+        del conn_t
+        self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
+
+    # ---- K1 -------------------------------------------------------------------------------------
+    def alloc_planes(self, which, alpha_M=0., alpha_K=0.):
+        P = self.schedule.n_blocks
+        n = {"M": 3, "K": 13, "D": layout.n_planes(layout.plane_map_D(alpha_M, alpha_K))}[which]
+        return torch.empty((n, P), dtype=torch.float64, device=self.device)
+
+    def assemble(self, ops, alpha_M=0., alpha_K=0., out=None, check=True):
+        """ops: string subset of 'MKD'.  Returns dict name -> planes tensor [n_planes, P]."""
+        S = self.schedule
+        out = {} if out is None else out
+        for nm in ops:
+            if nm not in out or out[nm] is None:
+                out[nm] = self.alloc_planes(nm, alpha_M, alpha_K)
+        mask = sum({"M": _lib.OP_M, "K": _lib.OP_K, "D": _lib.OP_D}[nm] for nm in set(ops))
+        self.bad_elem.fill_(_lib.INT32_MAX)
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_assemble(
+            p(self.coords), p(self.conn), p(self.mat_id), p(self.mat_table), self.n_mat,
+            S.n_cta, S.max_cta_elems, p(S.cta_item_ptr), p(S.cta_elem_ptr), p(S.cta_elems),
+            p(S.item_block), p(S.inc_ptr), p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
+            p(out.get("M")) if "M" in ops else None, p(out.get("K")) if "K" in ops else None,
+            p(out.get("D")) if "D" in ops else None, p(self.bad_elem), _lib.stream_ptr()))
+        if check:
+            self.check_jacobian()
+        return out
+
+    def check_jacobian(self):
+        e = ctypes.c_int32(-1)
+        _lib.check(self.lib.tefem_check_jacobian(_lib.ptr(self.bad_elem), ctypes.byref(e), _lib.stream_ptr()))
+
+    def element_matrices(self, kinds=("Muu", "Dtu", "Dtt", "Kuu", "Kut", "Ktt"), elem_idx=None):
+        """Dense element matrices (parity path / Element.compute_mat_*_e), as device tensors."""
+        dev = self.device
+        if elem_idx is None:
+            n, idx = self.n_elems, None
+        else:
+            idx = torch.as_tensor(elem_idx, dtype=torch.int64, device=dev).contiguous()
+            n = int(idx.numel())
+        shapes = {"Muu": (12, 12), "Dtu": (4, 12), "Dtt": (4, 4), "Kuu": (12, 12), "Kut": (12, 4), "Ktt": (4, 4)}
+        out = {k: torch.empty((n,) + shapes[k], dtype=torch.float64, device=dev) for k in kinds}
+        mask = sum(_lib.KIND[k] for k in kinds)
+        self.bad_elem.fill_(_lib.INT32_MAX)
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_element_matrices(
+            p(self.coords), p(self.conn), p(self.mat_id), p(self.mat_table), self.n_mat, p(idx), n, mask,
+            p(out.get("Muu")), p(out.get("Dtu")), p(out.get("Dtt")), p(out.get("Kuu")), p(out.get("Kut")),
+            p(out.get("Ktt")), p(self.bad_elem), _lib.stream_ptr()))
+        self.check_jacobian()
+        return out
+
+    # ---- plane-storage operators -------------------------------------------------------------
+    def planes_spmv(self, vals, plane_map, x, y, alpha=1.0, beta_y=0.0):
+        S = self.schedule
+        pm = np.ascontiguousarray(plane_map, dtype=np.int8).reshape(16)
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_planes_spmv(p(S.rowptr), p(S.colidx), S.n_rows, S.n_blocks, p(vals), p(pm),
+                                              p(x), float(alpha), float(beta_y), p(y), _lib.stream_ptr()))
+        return y
+
+    def export_csc(self, vals, plane_map, drop_zeros=False):
+        """scipy CSC matrix of an operator in plane storage (host copy; for parity / API compatibility)."""
+        import scipy.sparse as sp
+        S = self.schedule
+        br = S.block_row.cpu().numpy().astype(np.int64)
+        bc = S.colidx.cpu().numpy().astype(np.int64)
+        v = vals.cpu().numpy()
+        rows, cols, data = [], [], []
+        for r in range(4):
+            for c in range(4):
+                pl = int(plane_map[r, c])
+                if pl >= 0:
+                    rows.append(4 * br + r)
+                    cols.append(4 * bc + c)
+                    data.append(v[pl])
+        n_r, n_c = 4 * S.n_rows, 4 * S.n_nodes
+        A = sp.csr_array((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(n_r, n_c)).tocsc()
+        A.sort_indices()
+        if drop_zeros:
+            A.eliminate_zeros()          # what csc_array(dense) does in the reference, model.py:92,103,118
+        return A
+
+    # ---- K2 / K5 -----------------------------------------------------------------------------
+    def form_system(self, planes, cM, cD, cK, d_layout, dir_mask, sys=None):
+        S = self.schedule
+        if sys is None:
+            sys = torch.empty((S.n_blocks, 16), dtype=torch.float64, device=self.device)
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_form_system(
+            p(S.rowptr), p(S.colidx), S.n_rows, S.n_blocks, p(planes.get("M")), float(cM),
+            p(planes.get("D")), int(d_layout), float(cD), p(planes.get("K")), float(cK),
+            p(dir_mask), p(sys), _lib.stream_ptr()))
+        return sys
+
+    def block_jacobi_scale(self, sys):
+        S = self.schedule
+        dinv = torch.empty((S.n_rows, 16), dtype=torch.float64, device=self.device)
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_block_jacobi_scale(p(S.rowptr), p(S.diag_idx), S.n_rows, p(sys), p(dinv),
+                                                     _lib.stream_ptr()))
+        return dinv
+
+    def block_jacobi_apply(self, dinv, r, z, dir_mask=None):
+        _lib.check(self.lib.tefem_block_jacobi_apply(_lib.ptr(dinv), self.schedule.n_rows, _lib.ptr(r), _lib.ptr(z),
+                                                     _lib.ptr(dir_mask), _lib.stream_ptr()))
+        return z
+
+    def spmv(self, sys, x, y):
+        S = self.schedule
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_spmv(p(S.rowptr), p(S.colidx), S.n_rows, p(sys), p(x), p(y), _lib.stream_ptr()))
+        return y
+
+
+class KrylovSolver:
+    """Handle of the BiCGSTAB driver (K6) with its torch-owned workspace."""
+
+    def __init__(self, dmesh: DeviceMesh, n_halo=0, comm=None):
+        self.dmesh = dmesh
+        self.lib = dmesh.lib
+        S = dmesh.schedule
+        n_work = int(self.lib.tefem_solver_work_doubles(S.n_rows, n_halo))
+        self.work = torch.zeros(n_work, dtype=torch.float64, device=dmesh.device)
+        self.handle = ctypes.c_void_p()
+        self.comm = comm
+        _lib.check(self.lib.tefem_solver_create(ctypes.byref(self.handle), S.n_rows, n_halo, _lib.ptr(self.work),
+                                                comm.handle if comm is not None else None))
+        self.n_halo = n_halo
+        self._keep = []
+
+    def set_halo(self, nbr, send_ptr, send_idx, recv_ptr, boundary_rows, interior_rows):
+        nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+        send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int32)
+        recv_ptr = np.ascontiguousarray(recv_ptr, dtype=np.int32)
+        self._keep = [send_idx, boundary_rows, interior_rows]
+        p = _lib.ptr
+        _lib.check(self.lib.tefem_solver_set_halo(
+            self.handle, self.n_halo, len(nbr), p(nbr), p(send_ptr), p(send_idx), p(recv_ptr),
+            p(boundary_rows), int(boundary_rows.numel()), p(interior_rows), int(interior_rows.numel())))
+
+    def bicgstab(self, sys, b, x, rtol=1e-10, max_iter=20000, check_every=16):
+        """Solves sys x = b (both already block-Jacobi scaled); x holds the initial guess and the result.
+        Returns dict(iterations, restarts, relres, bnorm).  Raises ConvergenceError when rtol is not met."""
+        S = self.dmesh.schedule
+        info = (ctypes.c_double * 4)()
+        p = _lib.ptr
+        rc = self.lib.tefem_bicgstab(self.handle, p(S.rowptr), p(S.colidx), p(sys), p(b), p(x), float(rtol),
+                                     int(max_iter), int(check_every), info, _lib.stream_ptr())
+        self.last_info = dict(iterations=int(info[0]), restarts=int(info[1]), relres=float(info[2]), bnorm=float(info[3]))
+        _lib.check(rc)
+        return self.last_info
+
+    def close(self):
+        if self.handle:
+            self.lib.tefem_solver_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def newmark_predict(lib, x, v, a, dt, gamma, beta, dir_mask, w1, w2):
+    p = _lib.ptr
+    _lib.check(lib.tefem_newmark_predict(x.numel(), p(x), p(v), p(a), float(dt), float(gamma), float(beta),
+                                         p(dir_mask), p(w1), p(w2), _lib.stream_ptr()))
+
+
+def newmark_correct(lib, x, v, a, a_new, dt, gamma, beta, dir_mask):
+    p = _lib.ptr
+    _lib.check(lib.tefem_newmark_correct(x.numel(), p(x), p(v), p(a), p(a_new), float(dt), float(gamma), float(beta),
+                                         p(dir_mask), _lib.stream_ptr()))
+
+
+def load_axpy(lib, node, w, coef, F):
+    c = (ctypes.c_double * 4)(*[float(v) for v in coef])
+    _lib.check(lib.tefem_load_axpy(node.numel(), _lib.ptr(node), _lib.ptr(w), c, _lib.ptr(F), _lib.stream_ptr()))

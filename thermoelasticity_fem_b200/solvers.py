@@ -1,0 +1,246 @@
+"""Steady-state and implicit transient solvers of the drop-in API (reference ``solvers.py:8-217``).
+
+Same classes, constructor signatures and result attributes as the reference; the linear algebra runs
+on the GPU: ``spsolve`` (``solvers.py:26,172``; SuperLU, re-factorised at every time step) is replaced by
+a block-Jacobi-scaled BiCGSTAB (kernels K3-K6) on the Dirichlet-eliminated operator embedded in the
+uniform 4x4 node-block layout (kernel K2), and the Newmark update (``solvers.py:167-178``) by fused
+vector kernels (K7).  Extra keyword arguments (``rtol``, ``max_iter``, ``history`` ...) have defaults,
+so reference scripts run unchanged.
+
+Out of scope: ``solve_ROM`` / ``solve_ROM_nonparametric`` (``solvers.py:219-668``).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, layout
+from .device import KrylovSolver, newmark_correct, newmark_predict, load_axpy
+
+try:                                    # the reference wraps its time loop in tqdm (solvers.py:163)
+    from tqdm import tqdm as _tqdm
+except ImportError:                     # pragma: no cover
+    def _tqdm(it, **kw):
+        return it
+
+
+def _deinterleave(X, n_nodes):
+    """reference solvers.py:62-66 / 188-202: X (4N[, n_t]) -> U (3N[, n_t]), theta (N[, n_t])."""
+    U = np.zeros((n_nodes * 3,) + X.shape[1:])
+    U[::3] = X[::4]
+    U[1::3] = X[1::4]
+    U[2::3] = X[2::4]
+    return U, X[3::4]
+
+
+class _SystemSolve:
+    """Shared by both solvers: forms the eliminated, block-Jacobi-scaled system and solves with it."""
+
+    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every):
+        self.model = model
+        self.dm = model.mesh.device_mesh()
+        self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
+        d_layout = layout.n_planes(layout.plane_map_D(*model._d_alpha)) if "D" in model._planes else 4
+        planes = {k: v for k, v in model._planes.items()
+                  if (k == "M" and cM != 0.) or (k == "D" and cD != 0.) or (k == "K" and cK != 0.)}
+        self.sys = self.dm.form_system(planes, cM, cD, cK, d_layout, model._dir_mask)
+        self.dinv = self.dm.block_jacobi_scale(self.sys)
+        self.krylov = KrylovSolver(self.dm)
+        self.b = torch.empty(model.mesh.n_dofs, dtype=torch.float64, device=self.dm.device)
+        self.info = []
+
+    def solve(self, rhs, x):
+        """x <- solution of A_ff x_f = rhs_f (constrained entries of x stay 0)."""
+        self.dm.block_jacobi_apply(self.dinv, rhs, self.b, self.model._dir_mask)
+        info = self.krylov.bicgstab(self.sys, self.b, x, self.rtol, self.max_iter, self.check_every)
+        self.info.append(info)
+        return info
+
+
+class LinearSteadyState:
+    """Steady-state solver for linear thermoelasticity (reference solvers.py:8-66)."""
+
+    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32):
+        self.model = model
+        self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
+        self.X = None
+        self.U = None
+        self.T = None
+        self.X_device = None
+        self.solve_info = None
+        self.timings = {}
+
+    def solve(self):
+        m = self.model
+        t0 = time.perf_counter()
+        m.create_free_dofs_lists()
+        m.assemble_K()
+        m.assemble_F()
+        m.apply_dirichlet_matrices()
+        m.apply_dirichlet_F()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every)
+        x = torch.zeros(m.mesh.n_dofs, dtype=torch.float64, device=ss.dm.device)
+        self.solve_info = ss.solve(m.rhs_device(), x)
+        x += m._g_fill                       # prescribed values on the constrained DOFs (solvers.py:27-49)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        self.X_device = x
+        self.X = x.cpu().numpy()
+        self.U, theta = _deinterleave(self.X, m.mesh.n_nodes)
+        self.T = theta + m.mesh.reference_temperature()       # solvers.py:51-66
+        self.timings = dict(assemble_s=t1 - t0, solve_s=t2 - t1, post_s=time.perf_counter() - t2)
+
+
+class LinearTransient:
+    """Transient solver (Newmark, acceleration form) for linear thermoelasticity (reference solvers.py:69-217).
+
+    history: 'full' keeps X, Xdot, Xdotdot of shape (n_dofs, n_t) like the reference (solvers.py:125-127);
+    'last' keeps only the final state (needed at 28 M DOF where one history array would be 45 GB);
+    an integer k keeps every k-th step.  `on_step(i, x, v, a)` is called with device tensors after each step."""
+
+    def __init__(self, model,
+                 initial_U, initial_Udot,
+                 initial_theta, initial_thetadot,
+                 t_end, n_t,
+                 gamma=0.5, beta=0.25,
+                 rtol=1e-10, max_iter=50000, check_every=32, history='full', warm_start=True, on_step=None,
+                 progress=True):
+        self.model = model
+        self.gamma = gamma
+        self.beta = beta
+        self.t_end = t_end
+        self.n_t = n_t
+        self.initial_U = initial_U
+        self.initial_Udot = initial_Udot
+        self.initial_theta = initial_theta
+        self.initial_thetadot = initial_thetadot
+
+        self.vec_t = np.linspace(0., t_end, n_t)
+        self.dt = t_end / (n_t - 1)                       # solvers.py:89
+
+        self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
+        self.history, self.warm_start, self.on_step, self.progress = history, warm_start, on_step, progress
+
+        self.X = None
+        self.Xdot = None
+        self.Xdotdot = None
+        self.q = None
+        self.qdot = None
+        self.qdotdot = None
+        self.U = None
+        self.Udot = None
+        self.Udotdot = None
+        self.T = None
+        self.Tdot = None
+        self.Tdotdot = None
+        self.solve_info = []
+        self.timings = {}
+        self.state_device = None
+
+    # -- pieces reused by bench.py ----------------------------------------------------------------
+    def prepare(self):
+        """Everything before the time loop (solvers.py:105-161)."""
+        m = self.model
+        m.create_free_dofs_lists()
+        m.assemble_MDK()                                  # assemble_M, assemble_K, assemble_D in one launch
+        m.apply_dirichlet_matrices()
+        dev = m._dir_mask.device
+        n_nodes, n = m.mesh.n_nodes, m.mesh.n_dofs
+
+        def interleave(u3, th):
+            X = np.zeros(n)
+            X[::4] = np.asarray(u3)[::3]
+            X[1::4] = np.asarray(u3)[1::3]
+            X[2::4] = np.asarray(u3)[2::3]
+            X[3::4] = th
+            return X
+
+        x0 = interleave(self.initial_U, self.initial_theta)
+        v0 = interleave(self.initial_Udot, self.initial_thetadot)
+        free_mask = ~m._mask_host
+        # the reference advances only the free DOFs (solvers.py:155-157); constrained DOFs stay at their
+        # prescribed value in X and at 0 in Xdot / Xdotdot
+        self._x = torch.from_numpy(x0 * free_mask).to(dev)
+        self._v = torch.from_numpy(v0 * free_mask).to(dev)
+        self._a = torch.zeros(n, dtype=torch.float64, device=dev)     # initial acceleration assumed zero (:131)
+        self._x0_full, self._v0_full = x0, v0
+        dt = self.dt
+        self._ss = _SystemSolve(m, 1.0, self.gamma * dt, self.beta * dt ** 2, self.rtol, self.max_iter, self.check_every)
+        self._w1 = torch.empty_like(self._x)
+        self._w2 = torch.empty_like(self._x)
+        self._rhs = torch.empty_like(self._x)
+        self._a_new = torch.zeros_like(self._x)
+        self._lift = m.lift_vector() if m._has_nonzero_dirichlet else None
+        self._mapD = layout.plane_map_D(*m._d_alpha)
+        self._mapK = layout.plane_map_K()
+        self._lib = _lib.load()
+
+    def step(self, i):
+        """One time step (solvers.py:164-186) entirely on the device."""
+        m, dm = self.model, self._ss.dm
+        rhs = self._rhs
+        rhs.zero_()
+        for node, w, coef in m.load_terms(idx_t=i):                        # F(i), model.py:120-286
+            load_axpy(self._lib, node, w, coef, rhs)
+        if self._lift is not None:                                         # F_f -= K_fd x_d, model.py:326-339
+            rhs -= self._lift
+        newmark_predict(self._lib, self._x, self._v, self._a, self.dt, self.gamma, self.beta, m._dir_mask,
+                        self._w1, self._w2)
+        dm.planes_spmv(m._planes["D"], self._mapD, self._w1, rhs, alpha=-1.0, beta_y=1.0)   # - D_ff @ (...)
+        dm.planes_spmv(m._planes["K"], self._mapK, self._w2, rhs, alpha=-1.0, beta_y=1.0)   # - K_ff @ (...)
+        if not self.warm_start:
+            self._a_new.zero_()
+        info = self._ss.solve(rhs, self._a_new)                            # spsolve(K_dyn, rhs), solvers.py:172
+        newmark_correct(self._lib, self._x, self._v, self._a, self._a_new, self.dt, self.gamma, self.beta, m._dir_mask)
+        return info
+
+    def solve(self):
+        m = self.model
+        t0 = time.perf_counter()
+        self.prepare()
+        n, n_t, n_nodes = m.mesh.n_dofs, self.n_t, m.mesh.n_nodes
+        keep_every = 1 if self.history == 'full' else (None if self.history == 'last' else int(self.history))
+        if keep_every is not None:
+            cols = list(range(0, n_t, keep_every))
+            col_of = {s: k for k, s in enumerate(cols)}
+            self.kept_steps = np.array(cols)
+            self.X = np.zeros((n, len(cols)))
+            self.Xdot = np.zeros((n, len(cols)))
+            self.Xdotdot = np.zeros((n, len(cols)))
+            self.X[:, 0] = self._x0_full
+            self.Xdot[:, 0] = self._v0_full
+            fill = m._g_fill_host
+            self.X[m._mask_host, :] = fill[m._mask_host][:, None]          # solvers.py:133-153
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        it = range(1, n_t)
+        for i in (_tqdm(it) if self.progress else it):
+            self.solve_info.append(self.step(i))
+            if self.on_step is not None:
+                self.on_step(i, self._x, self._v, self._a)
+            if keep_every is not None and i in col_of:
+                k = col_of[i]
+                free = m.free_dofs
+                self.X[free, k] = self._x.cpu().numpy()[free]
+                self.Xdot[free, k] = self._v.cpu().numpy()[free]
+                self.Xdotdot[free, k] = self._a.cpu().numpy()[free]
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        self.state_device = (self._x + m._g_fill, self._v, self._a)
+        if keep_every is None:
+            X = self.state_device[0].cpu().numpy()[:, None]
+            self.X, self.Xdot, self.Xdotdot = X, self._v.cpu().numpy()[:, None], self._a.cpu().numpy()[:, None]
+            self.kept_steps = np.array([n_t - 1])
+        self.U, theta = _deinterleave(self.X, n_nodes)
+        self.Udot, self.Tdot = _deinterleave(self.Xdot, n_nodes)
+        self.Udotdot, self.Tdotdot = _deinterleave(self.Xdotdot, n_nodes)
+        self.T = theta + m.mesh.reference_temperature()[:, None]          # solvers.py:204-215
+        self.timings = dict(prepare_s=t1 - t0, loop_s=t2 - t1, steps=n_t - 1, post_s=time.perf_counter() - t2)
+
+    def solve_ROM(self, *args, **kwargs):
+        raise NotImplementedError("reduced-order solve (reference solvers.py:219-354) is outside the B200 hot path")
+
+    def solve_ROM_nonparametric(self, *args, **kwargs):
+        raise NotImplementedError("non-parametric UQ solve (reference solvers.py:356-668) is outside the B200 hot path")

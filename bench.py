@@ -1,0 +1,394 @@
+"""Benchmark of the thermoelastic hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells C] [--impl tefem|reference]
+
+A "step" is ONE implicit transient time step (reference solvers.py:164-186) of BASELINE.json config 4: a
+unit box of C^3 cells x 6 Kuhn tets (default C = 190: 41 154 000 tets, 6 967 871 nodes, 27 871 484 DOF), single
+config-2 material, config-2 Dirichlet sets / time-varying surface load / Rayleigh damping, dt = 1800/999 s,
+Krylov tolerance 1e-10 on the per-field scaled true residual.  Every step = load vector, Newmark predictor,
+right-hand side (2 plane SpMVs), block-Jacobi-scaled BiCGSTAB solve (thousands of 4x4-block SpMVs), corrector.
+Assembly of M, D, K (kernel K1) is timed separately on the same mesh and reported under "assembly".
+
+One JSON line is printed by rank 0; see DESIGN.md for the definition of every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAT2 = dict(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.)     # examples/example_transient_2.py:29
+T_END, N_T = 1800e0, 1000                                                    # example_transient_2.py:20-21
+DU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]}       # example_transient_2.py:38-41
+DT = {4: 0., 5: 0.}
+ALPHA_M = ALPHA_K = 0.2
+RTOL = 1e-10
+
+
+def surface_load():
+    vec_t = np.linspace(0., T_END, N_T)
+    arr = np.zeros((3, N_T))
+    arr[0, :] = np.sin(2 * np.pi * vec_t / 900.) * -1e9                      # example_transient_2.py:53-59
+    return arr
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def build_case(cells, rank=0, world=1):
+    from thermoelasticity_fem_b200 import LinearThermoElastic, Mesh, Model, LinearTransient
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    if world > 1:
+        from thermoelasticity_fem_b200.distributed import build_distributed_case
+        return build_distributed_case(cells, rank, world, MAT2, DU, DT, surface_load(), ALPHA_M, ALPHA_K,
+                                      T_END, N_T, RTOL)
+    pts, tets, tris, nodes = kuhn_box(cells, cells, cells, 1.0, 1.0, 1.0, n_layers=1, index_dtype=np.int32)
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    mesh.set_materials({1: LinearThermoElastic(**MAT2)})
+    mesh.make_elements()
+    model = Model(mesh, dict_dirichlet_U=DU, dict_dirichlet_theta=DT, dict_surface_forces={5: surface_load()},
+                  alpha_M=ALPHA_M, alpha_K=ALPHA_K)
+    n = mesh.n_nodes
+    solver = LinearTransient(model, np.zeros(3 * n), np.zeros(3 * n), np.zeros(n), np.zeros(n), T_END, N_T, 0.5, 0.25,
+                             rtol=RTOL, history='last', progress=False, check_every=64)
+    return mesh, model, solver
+
+
+def run_tefem(args):
+    import torch
+    import torch.distributed as dist
+    from thermoelasticity_fem_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t0 = time.perf_counter()
+    mesh, model, solver = build_case(args.cells, rank, world)
+    dm = mesh.device_mesh()
+    S = dm.schedule
+    t_setup = time.perf_counter() - t0
+    E_loc, P_loc, N_own = dm.n_elems, S.n_blocks, S.n_rows
+    n_dofs_total = 4 * (args.cells + 1) ** 3
+    E_total = 6 * args.cells ** 3
+
+    # ---- assembly (K1): M + D + K in one launch, and K alone; CUDA events, outputs (>= L2) rewritten every launch
+    asm = {}
+    for ops, planes in (("MKD", 29), ("K", 13)):
+        out = dm.assemble(ops, ALPHA_M, ALPHA_K)
+        for _ in range(3):
+            dm.assemble(ops, ALPHA_M, ALPHA_K, out=out, check=False)
+        reps = 5
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            dm.assemble(ops, ALPHA_M, ALPHA_K, out=out, check=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(ev0.elapsed_time(ev1) / reps)
+        alg = 8 * planes * P_loc + 20 * E_loc + 24 * dm.n_nodes + 4 * 16 * E_loc
+        asm[ops] = {"ms": ms, "elements_per_s": E_total / (ms * 1e-3),
+                    "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / hbm_peak}
+        del out
+    dm.check_jacobian()
+
+    # ---- transient steps
+    solver.prepare()
+    kry = solver._ss.krylov
+    for i in range(1, args.warmup + 1):
+        solver.step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kry.profile(True)
+    launches0 = lib.tefem_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    infos = []
+    barrier()
+    ev0.record()
+    for i in range(args.warmup + 1, args.warmup + args.steps + 1):
+        infos.append(solver.step(i))
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = lib.tefem_launch_count() - launches0
+    spmv_ms, spmv_count = kry.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    iters = [inf["iterations"] for inf in infos]
+    ms_per_step = ms_total / args.steps
+    steps_per_s = 1e3 / ms_per_step
+
+    # ---- SpMV roofline (dominant kernel): algorithmic bytes, node-block accounting
+    n_halo = getattr(solver, "n_halo", 0)
+    spmv_bytes = 8 * 16 * P_loc + 4 * P_loc + 4 * (N_own + 1) + 16 * 4 * N_own
+    spmv_avg_ms = max_over_ranks(spmv_ms / max(spmv_count, 1))
+    spmv_gbs = spmv_bytes / spmv_avg_ms / 1e6
+    roofline = {"bound": "hbm", "kernel": "spmv_kernel (4x4-block SpMV of the Krylov iteration, fused dot partials)",
+                "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
+                "peak_source": peak_src, "traffic": None, "launches_timed": int(spmv_count),
+                "avg_launch_ms": spmv_avg_ms, "algorithmic_bytes_per_launch": spmv_bytes,
+                "share_of_step": spmv_ms / ms_total}
+
+    # ---- end to end through the public API: host-resident inputs and results every step
+    e2e = None
+    if args.e2e_steps > 0:
+        n_loc = 4 * dm.n_nodes if world == 1 else solver._x.numel()
+        host = [torch.empty(n_loc, dtype=torch.float64).pin_memory() for _ in range(3)]
+        load_host = torch.from_numpy(surface_load()).pin_memory()
+        coef_dev = torch.empty(3, dtype=torch.float64, device="cuda")
+        first = args.warmup + args.steps + 1
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(first, first + args.e2e_steps):
+            coef_dev.copy_(load_host[:, i], non_blocking=True)            # H2D: this step's load amplitudes
+            solver.step(i)
+            for h, d in zip(host, (solver._x, solver._v, solver._a)):      # D2H: X, Xdot, Xdotdot of this step
+                h.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt_e2e = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": args.e2e_steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 24,
+               "d2h_bytes_per_step": int(sum_over_ranks(3 * 8 * n_loc)), "steps": args.e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline(budget_s=args.cpu_budget) if (world == 1 and args.cpu_budget > 0) else None
+    n_free = int(n_dofs_total - (len(model.dirichlet_dofs_U) + len(model.dirichlet_dofs_theta))) if world == 1 else None
+    line = {
+        "metric": "transient steps/s (implicit Newmark step of the coupled thermoelastic model, 28M DOF box)",
+        "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 4: Kuhn box {args.cells}^3 cells = {E_total} tets, {n_dofs_total} DOF, "
+                               "transient (config-2 material/BCs/load/Rayleigh), BiCGSTAB rtol 1e-10 per field",
+                   "cells": args.cells, "n_tets": E_total, "n_dofs": n_dofs_total, "n_free_dofs": n_free,
+                   "partition": "single GPU" if world == 1 else f"x-slabs of node rows over {world} GPUs",
+                   "l2_policy": "operands larger than L2 (system matrix %.1f GB per GPU)" % (8 * 16 * P_loc / 1e9)},
+        "solver": {"iterations_per_step": float(np.mean(iters)), "iterations": iters,
+                   "dof_iterations_per_s": n_dofs_total * float(np.sum(iters)) / (ms_total * 1e-3),
+                   "ms_per_iteration": ms_total / max(float(np.sum(iters)), 1.0),
+                   "relres": [inf["relres"] for inf in infos], "restarts": [inf["restarts"] for inf in infos]},
+        "assembly": asm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "setup_s": t_setup,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_case(cells):
+    from oracle import tefem_oracle as orc
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(cells, cells, cells, 1.0, 1.0, 1.0, n_layers=1)
+    groups = dict(nodes=nodes, tri=tris, tet=tets)
+    mats = {1: orc.Material(**MAT2)}
+    return orc, pts, groups, mats
+
+
+def cpu_assembly_rate(n_elems=4000):
+    """elements/s of the per-element port (the reference's Python loop, model.py:87-118): M + K + D."""
+    orc, pts, groups, mats = cpu_case(10)
+    conn = groups["tet"][1][:n_elems]
+    t0 = time.perf_counter()
+    for e in range(conn.shape[0]):
+        orc.element_matrices_percall(pts[conn[e]], mats[1], e, which=("Muu",))                      # assemble_M
+        orc.element_matrices_percall(pts[conn[e]], mats[1], e, which=("Kuu", "Kut", "Ktt"))        # assemble_K
+        orc.element_matrices_percall(pts[conn[e]], mats[1], e, which=("Dtu", "Dtt", "Muu", "Kuu"))  # assemble_D (Rayleigh)
+    return conn.shape[0] / (time.perf_counter() - t0)
+
+
+class CpuTransient:
+    """Reference algorithm per step (solvers.py:164-186): F(i), lifting, 2 SpMV, spsolve(K_dyn, rhs), updates."""
+
+    def __init__(self, cells):
+        import scipy.sparse.linalg as spla
+        orc, pts, groups, mats = cpu_case(cells)
+        self.orc, self.pts, self.groups, self.spla = orc, pts, groups, spla
+        n_nodes = pts.shape[0]
+        conn, mat_id, rows = orc.element_table(groups["tet"], mats)
+        ops = orc.assemble(pts, conn, rows, mat_id, ALPHA_M, ALPHA_K)
+        maps = orc.free_dofs_lists(n_nodes, groups["tri"], DU, DT)
+        self.free = maps["free_dofs"]
+        self.K = ops["K"]
+        self.Mff, self.Dff, self.Kff = (orc.reduce_matrix(ops[k], self.free) for k in "MDK")
+        self.dt = T_END / (N_T - 1)
+        self.Kdyn = (self.Mff + 0.5 * self.dt * self.Dff + 0.25 * self.dt ** 2 * self.Kff).tocsc()
+        self.x = np.zeros(self.free.shape[0])
+        self.v = np.zeros_like(self.x)
+        self.a = np.zeros_like(self.x)
+        self.loads = dict(surface={5: surface_load()})
+        self.n_dofs = 4 * n_nodes
+        self.i = 0
+
+    def step(self):
+        self.i += 1
+        orc, dt = self.orc, self.dt
+        F = orc.assemble_F(self.pts, self.groups, self.loads, idx_t=self.i)
+        Ff = orc.lift_rhs(F, self.K, self.free, self.n_dofs, self.groups["tri"], DU, DT)
+        rhs = Ff - self.Dff @ (self.v + 0.5 * dt * self.a) - self.Kff @ (self.x + dt * self.v + 0.25 * dt ** 2 * self.a)
+        a_new = self.spla.spsolve(self.Kdyn, rhs)                         # re-factorised every step, like the reference
+        v_new = self.v + 0.5 * dt * self.a + 0.5 * dt * a_new
+        x_new = self.x + dt * self.v + 0.5 * dt ** 2 * (0.5 * self.a + 0.5 * a_new)
+        self.x, self.v, self.a = x_new, v_new, a_new
+
+
+def cpu_baseline(budget_s=20.0, cells=12):
+    t0 = time.perf_counter()
+    case = CpuTransient(cells)
+    t_setup = time.perf_counter() - t0
+    n, t1 = 0, time.perf_counter()
+    while n < 2 or (time.perf_counter() - t1 < budget_s * 0.6 and n < 50):
+        case.step()
+        n += 1
+    dt = time.perf_counter() - t1
+    return {"value": n / dt, "unit": "steps/s", "cores": 1, "kind": "port",
+            "sample": f"oracle port of the reference step (F, lifting, 2 SpMV, scipy spsolve re-factorised every step) on a "
+                      f"{cells}^3-cell Kuhn box = {case.n_dofs} DOF ({n} steps timed; SuperLU cannot factor the 28M-DOF "
+                      f"operator: 164 s at 86k DOF, BASELINE.md); assembly port = per-element Python loop",
+            "n_dofs": case.n_dofs, "assembly_elements_per_s": cpu_assembly_rate(), "setup_s": t_setup,
+            "host_cpu_count": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and is
+    not present on the GPU box) on the host cores, same metric / unit, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cells = args.ref_cells
+    case = CpuTransient(cells)
+    for _ in range(args.warmup):
+        case.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        case.step()
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    E_total = 6 * args.cells ** 3
+    n_dofs_total = 4 * (args.cells + 1) ** 3
+    sample = (f"bounded sample: the same transient step (config-2 physics) on a {cells}^3-cell Kuhn box = {case.n_dofs} DOF; "
+              "scipy spsolve re-factorised every step as in the reference (solvers.py:172); single-threaded")
+    line = {"impl": "reference", "metric": "transient steps/s (implicit Newmark step of the coupled thermoelastic model, 28M DOF box)",
+            "value": v, "unit": "steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4: Kuhn box {args.cells}^3 cells = {E_total} tets, {n_dofs_total} DOF, "
+                                   "transient (config-2 material/BCs/load/Rayleigh), BiCGSTAB rtol 1e-10 per field",
+                       "cells": args.cells, "n_tets": E_total, "n_dofs": n_dofs_total},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
+                             "n_dofs": case.n_dofs, "host_cpu_count": os.cpu_count()},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cells", type=int, default=190, help="cells per edge of the Kuhn box (190 = BASELINE config 4)")
+    ap.add_argument("--impl", default="tefem", choices=["tefem", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
+    ap.add_argument("--ref-cells", type=int, default=12)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_tefem(args)
+
+
+if __name__ == "__main__":
+    main()

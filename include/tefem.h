@@ -61,6 +61,9 @@ extern "C" {
 /* Message of the last error raised on the calling thread (NUL-terminated, truncated to n). */
 int tefem_last_error(char* h_buf, size_t n);
 
+/* Number of CUDA kernels this library has launched in the calling process (monotonic). */
+int64_t tefem_launch_count(void);
+
 /* Library / build information: writes "tefem_b200 <version> sm_100a cuda <ver>" into h_buf. */
 int tefem_version(char* h_buf, size_t n);
 
@@ -87,8 +90,12 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * compute_mat_*_e calls, the np.ix_ scatter into the dense matrix and csc_array(dense)).
  *
  * Owner-computes schedule built once per mesh by the symbolic phase (host side, symbolic.py):
- *   CTA c owns the blocks item_block[cta_item_ptr[c] .. cta_item_ptr[c+1]) and first stages the
- *   geometry of the elements cta_elems[cta_elem_ptr[c] .. cta_elem_ptr[c+1]) in shared memory;
+ *   CTA c owns the blocks item_block[cta_item_ptr[c] .. cta_item_ptr[c+1]) (a permutation of that same
+ *   contiguous block range) and first stages the geometry of the elements
+ *   cta_elems[cta_elem_ptr[c] .. cta_elem_ptr[c+1]) in shared memory, reading their connectivity and
+ *   material index from the per-CTA copies cta_conn[.,4] = conn[cta_elems], cta_mat = mat_id[cta_elems];
+ *   max_cta_elems / max_cta_inc = largest element list / incidence range of a CTA (shared-memory size);
+ *   inc must be 16-byte aligned and readable 8 entries past its end;
  *   block p sums the contributions inc[inc_ptr[p] .. inc_ptr[p+1]) IN ASCENDING ELEMENT ORDER
  *   (the order of the reference's loop, model.py:89,96,107); an entry of inc packs
  *   (local element index << 4) | (a << 2) | b with a, b the local node numbers of (row, column).
@@ -96,10 +103,10 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
  * The D layout follows alpha_M / alpha_K (model.py:112-117).
  * bad_elem[2] as above; the call itself does not synchronise - use tefem_check_jacobian().      */
-int tefem_assemble(const double* coords, const int32_t* conn, const int32_t* mat_id,
-                   const double* mat_table, int n_mat,
-                   int32_t n_cta, int32_t max_cta_elems,
+int tefem_assemble(const double* coords, const double* mat_table, int n_mat,
+                   int32_t n_cta, int32_t max_cta_elems, int32_t max_cta_inc,
                    const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
+                   const int32_t* cta_conn, const int32_t* cta_mat,
                    const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
                    int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                    double* vals_M, double* vals_K, double* vals_D,
@@ -151,6 +158,11 @@ typedef struct tefem_solver tefem_solver;
 int64_t tefem_solver_work_doubles(int32_t n_rows, int32_t n_halo);
 int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n_halo, double* work, void* comm /* tefem_comm* or NULL */);
 int tefem_solver_destroy(tefem_solver* s);
+/* SpMV timing for the roofline report: returns the accumulated device time (CUDA events on the launching
+ * stream around every SpMV of the Krylov iteration, halo exchange included in the multi-GPU case) and the
+ * number of SpMVs since profiling was enabled; enable = 1 / 0 switches it and clears the counters,
+ * enable < 0 only reads.                                                                            */
+int tefem_solver_profile(tefem_solver* s, int enable, double* h_spmv_ms, int64_t* h_spmv_count);
 
 /* Halo description for the row-partitioned multi-GPU solve (ignored when comm == NULL):
  * x vectors have n_rows owned node rows followed by n_halo halo node rows;
@@ -166,8 +178,10 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
 
 /* Left-block-Jacobi-scaled BiCGSTAB (replaces spsolve at solvers.py:26 and :172).
  * Solves sys x = b where sys and b have ALREADY been scaled by tefem_block_jacobi_scale/apply.
- * Stops when ||b - sys x|| <= rtol * ||b|| (true residual, re-evaluated before returning;
- * recursive-residual drift triggers a restart from the current x).  x holds the initial guess
+ * Stops when, for each field f in {u rows, theta rows}, ||(b - sys x)_f|| <= rtol * ||b_f|| (a field with
+ * b_f = 0 is measured against ||x_f||): the TRUE residual is re-evaluated before returning and
+ * recursive-residual drift triggers a restart from the current x; when two restarts in a row cannot
+ * improve the true residual (the eps*cond floor) the solve returns OK if it is within 100*rtol.  x holds the initial guess
  * on entry.  h_info[4] = {iterations, restarts, final relative residual, ||b||}.                */
 int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx,
                    const double* sys, const double* b, double* x,

@@ -1,0 +1,198 @@
+"""Symbolic phase (pattern, slot map, CTA schedule) and the K1 per-thread routines, on the CPU.
+
+The per-thread routines of the CUDA kernel are compiled for the host by tests/host_emulation/build_emu.py
+(test infrastructure, never loaded by the package) and executed sequentially; the result must match the oracle."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tefem_oracle as orc
+from thermoelasticity_fem_b200 import layout
+from thermoelasticity_fem_b200.symbolic import build_schedule
+from thermoelasticity_fem_b200.synthetic import kuhn_box
+import parity
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emulation"))
+
+MAT2 = (2300, 64e9, 0.1, 1., 1., 4e-6, 20.)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    return ctypes.CDLL(build_emu.build())
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def planes_to_csc(vals, pmap, S, n):
+    import scipy.sparse as sp
+    br = S.block_row.numpy().astype(np.int64)
+    bc = S.colidx.numpy().astype(np.int64)
+    r_, c_, v_ = [], [], []
+    for r in range(4):
+        for c in range(4):
+            pl = pmap[r, c]
+            if pl >= 0:
+                r_.append(4 * br + r)
+                c_.append(4 * bc + c)
+                v_.append(vals[pl])
+    A = sp.csr_array((np.concatenate(v_), (np.concatenate(r_), np.concatenate(c_))), shape=(4 * S.n_rows, n)).tocsc()
+    A.sort_indices()
+    return A
+
+
+def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
+    P = S.n_blocks
+    nD = layout.n_planes(layout.plane_map_D(aM, aK))
+    vM, vK, vD = np.zeros((3, P)), np.zeros((13, P)), np.zeros((nD, P))
+    bad = np.full(2, 2 ** 31 - 1, dtype=np.int32)
+    a = {k: getattr(S, k).numpy() for k in ("cta_item_ptr", "cta_elem_ptr", "cta_elems", "item_block", "inc_ptr", "inc")}
+    cta_conn = np.ascontiguousarray(conn.astype(np.int32)[a["cta_elems"]])
+    cta_mat = np.ascontiguousarray(mat_id.astype(np.int32)[a["cta_elems"]])
+    mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
+    rc = emu.tefem_emu_assemble(ptr(pts), ptr(rows), ctypes.c_int32(S.n_cta), ctypes.c_int32(S.max_cta_elems),
+                                ctypes.c_int32(S.max_cta_inc), ptr(a["cta_item_ptr"]), ptr(a["cta_elem_ptr"]),
+                                ptr(a["cta_elems"]), ptr(cta_conn), ptr(cta_mat), ptr(a["item_block"]), ptr(a["inc_ptr"]),
+                                ptr(a["inc"]), ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
+                                ptr(vM), ptr(vK), ptr(vD), ptr(bad))
+    assert rc == 0
+    return dict(M=vM, K=vK, D=vD), bad
+
+
+def check_schedule_invariants(S, conn, n_nodes):
+    E = conn.shape[0]
+    rowptr, colidx = S.rowptr.numpy(), S.colidx.numpy()
+    assert rowptr[0] == 0 and rowptr[-1] == S.n_blocks
+    for i in range(0, S.n_rows, max(1, S.n_rows // 50)):
+        cols = colidx[rowptr[i]:rowptr[i + 1]]
+        assert np.all(np.diff(cols) > 0)
+        assert colidx[S.diag_idx.numpy()[i]] == i
+    # each CTA's items are a permutation of its contiguous block range, longest incidence lists first
+    ip, ib, incp = S.cta_item_ptr.numpy(), S.item_block.numpy(), S.inc_ptr.numpy()
+    for c in range(S.n_cta):
+        blk = ib[ip[c]:ip[c + 1]]
+        assert np.array_equal(np.sort(blk), np.arange(ip[c], ip[c + 1]))
+        lens = incp[blk + 1] - incp[blk]
+        assert np.all(np.diff(lens) <= 0)
+        assert S.cta_elem_ptr.numpy()[c + 1] - S.cta_elem_ptr.numpy()[c] <= S.max_cta_elems
+        assert incp[ip[c + 1]] - incp[ip[c]] <= S.max_cta_inc
+    assert S.inc.numel() == incp[-1] + 8
+    # every incidence entry decodes to an element of the CTA's list that really contains (row, col)
+    inc = S.inc.numpy().astype(np.int64) & 0xFFFF
+    ce, cep = S.cta_elems.numpy(), S.cta_elem_ptr.numpy()
+    br = S.block_row.numpy()
+    cta_of_block = np.searchsorted(ip, np.arange(S.n_blocks), side="right") - 1
+    rng = np.random.default_rng(0)
+    for p in rng.integers(0, S.n_blocks, size=400):
+        c = cta_of_block[p]
+        last = -1
+        for k in range(incp[p], incp[p + 1]):
+            w = inc[k]
+            e = ce[cep[c] + (w >> 4)]
+            a, b = (w >> 2) & 3, w & 3
+            assert conn[e, a] == br[p] and conn[e, b] == colidx[p]
+            assert e > last                              # ascending element order = the reference's summation order
+            last = e
+    assert incp[-1] == 16 * E if S.n_rows == n_nodes else incp[-1] <= 16 * E
+
+
+@pytest.mark.parametrize("aM,aK", [(0.2, 0.2), (0.3, 0.0), (0.0, 0.0)])
+def test_sandwich_schedule_and_emulated_assembly(sandwich, emu, aM, aK):
+    pts, blocks, groups = sandwich
+    m = orc.Material(*MAT2)
+    conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
+    S = build_schedule(torch.from_numpy(conn), pts.shape[0])
+    assert S.n_blocks == 39985
+    if aM == 0.2:
+        check_schedule_invariants(S, conn, pts.shape[0])
+    vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", aM, aK)
+    assert bad[0] == 2 ** 31 - 1 and bad[1] == 2 ** 31 - 1
+    ops = orc.assemble(pts, conn, rows, mat_id, aM, aK)
+    ops["M"] = orc.drop_component_zeros_M(ops["M"])
+    if aK == 0. and aM != 0.:
+        ops["D"] = orc.drop_cross_component_uu(ops["D"])
+    n = 4 * pts.shape[0]
+    for nm, pm in (("M", layout.plane_map_M()), ("K", layout.plane_map_K()), ("D", layout.plane_map_D(aM, aK))):
+        A = planes_to_csc(vals[nm], pm, S, n)
+        parity.check_pattern(A, None, ops[nm])
+        assert parity.scaled_error(A, ops[nm]) < parity.VALUE_TOL, nm
+
+
+def test_single_operator_launches_match_fused(sandwich, emu):
+    pts, blocks, groups = sandwich
+    m = orc.Material(*MAT2)
+    conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
+    S = build_schedule(torch.from_numpy(conn), pts.shape[0])
+    fused, _ = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.2, 0.2)
+    for nm in "MKD":
+        single, _ = emu_assemble(emu, S, pts, conn, mat_id, rows, nm, 0.2, 0.2)
+        assert np.array_equal(single[nm], fused[nm]), nm
+
+
+def test_kuhn_multimaterial_and_bad_jacobian(emu):
+    pts, tets, tris, nodes = kuhn_box(5, 3, 4, jitter=0.2, seed=1)
+    mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+            3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    conn, mat_id, rows = orc.element_table(tets, mats)
+    for items in (256, 64):                       # small tiles: many CTAs, exercises the staging offsets
+        S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items))
+        check_schedule_invariants(S, conn, pts.shape[0])
+        vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
+        ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)
+        A = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * pts.shape[0])
+        parity.check_pattern(A, None, ops["K"])
+        assert parity.scaled_error(A, ops["K"]) < parity.VALUE_TOL
+        D = planes_to_csc(vals["D"], layout.plane_map_D(0.1, 0.4), S, 4 * pts.shape[0])
+        assert parity.scaled_error(D, ops["D"]) < parity.VALUE_TOL
+    bad_conn = conn.copy()
+    bad_conn[[17, 90]] = bad_conn[[17, 90]][:, [0, 2, 1, 3]]        # two inverted elements: the first one is reported
+    bad_conn[40, 3] = bad_conn[40, 2]                               # and a degenerate one in between
+    S = build_schedule(torch.from_numpy(bad_conn), pts.shape[0])
+    _, bad = emu_assemble(emu, S, pts, bad_conn, mat_id, rows, "K", 0., 0.)
+    assert bad[0] == 17 and bad[1] == 40
+
+
+def test_row_restricted_schedule_matches_global_rows():
+    """Row-partitioned assembly (multi-GPU): a schedule restricted to the first R rows has exactly the global
+    pattern's first R rows and the same incidence lists."""
+    pts, tets, tris, nodes = kuhn_box(6, 3, 3)
+    conn = np.concatenate(list(tets.values()))
+    N = pts.shape[0]
+    full = build_schedule(torch.from_numpy(conn), N)
+    R = N // 2
+    part = build_schedule(torch.from_numpy(conn), N, n_rows=R)
+    nb = int(full.rowptr[R])
+    assert part.n_blocks == nb and part.n_rows == R
+    assert torch.equal(part.rowptr, full.rowptr[:R + 1]) and torch.equal(part.colidx, full.colidx[:nb])
+    assert torch.equal(part.inc_ptr, full.inc_ptr[:nb + 1])
+
+
+def test_emulated_element_matrices_match_oracle(emu):
+    pts, tets, tris, nodes = kuhn_box(3, 2, 2, jitter=0.25, seed=3)
+    mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+            3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    conn, mat_id, rows = orc.element_table(tets, mats)
+    E = conn.shape[0]
+    out = {"Muu": np.zeros((E, 12, 12)), "Dtu": np.zeros((E, 4, 12)), "Dtt": np.zeros((E, 4, 4)),
+           "Kuu": np.zeros((E, 12, 12)), "Kut": np.zeros((E, 12, 4)), "Ktt": np.zeros((E, 4, 4))}
+    bad = np.full(2, 2 ** 31 - 1, dtype=np.int32)
+    conn32, mid32 = conn.astype(np.int32), mat_id.astype(np.int32)
+    rc = emu.tefem_emu_element_matrices(ptr(pts), ptr(conn32), ptr(mid32), ptr(rows), ctypes.c_int64(E), 63,
+                                        ptr(out["Muu"]), ptr(out["Dtu"]), ptr(out["Dtt"]), ptr(out["Kuu"]),
+                                        ptr(out["Kut"]), ptr(out["Ktt"]), ptr(bad))
+    assert rc == 0
+    em = orc.element_matrices_batch(pts, conn, rows, mat_id)
+    for nm in out:
+        assert np.max(np.abs(out[nm] - em[nm])) <= 1e-14 * np.abs(em[nm]).max(), nm
+    # and against the per-call restatement, which is bit-identical to the reference
+    for e in range(0, E, 5):
+        pc = orc.element_matrices_percall(pts[conn[e]], mats[int(list(tets)[mat_id[e]])])
+        for nm in out:
+            assert np.max(np.abs(out[nm][e] - pc[nm])) <= 1e-14 * np.abs(pc[nm]).max(), nm

@@ -25,7 +25,7 @@ _SIGNATURES = {
     "tefem_version": [c_char_p, c_size_t],
     "tefem_quadrature_tables": [P, P, P],
     "tefem_element_matrices": [P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P],
-    "tefem_assemble": [P, P, P, P, c_int, c_int32, c_int32, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
+    "tefem_assemble": [P, P, c_int, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
                        P, P, P, P, P],
     "tefem_check_jacobian": [P, P, P],
     "tefem_planes_spmv": [P, P, c_int32, c_int64, P, P, P, c_double, c_double, P, P],
@@ -35,6 +35,7 @@ _SIGNATURES = {
     "tefem_spmv": [P, P, c_int32, P, P, P, P],
     "tefem_solver_create": [P, c_int32, c_int32, P, P],
     "tefem_solver_destroy": [P],
+    "tefem_solver_profile": [P, c_int, P, P],
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
@@ -45,7 +46,7 @@ _SIGNATURES = {
     "tefem_comm_destroy": [P],
     "tefem_comm_allreduce_sum": [P, P, c_int, P],
 }
-_RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32])}
+_RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32]), "tefem_launch_count": (c_int64, [])}
 
 _lib = None
 

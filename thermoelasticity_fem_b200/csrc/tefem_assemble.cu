@@ -32,6 +32,8 @@ struct AssembleArgs {
     const int32_t* cta_item_ptr;
     const int32_t* cta_elem_ptr;
     const int32_t* cta_elems;
+    const int32_t* cta_conn;   // [n_staged, 4] connectivity of the staged elements (conn[cta_elems])
+    const int32_t* cta_mat;    // [n_staged]    material index of the staged elements
     const int32_t* item_block;
     const uint32_t* inc_ptr;
     const uint16_t* inc;
@@ -54,19 +56,26 @@ TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double W4, doubl
                           A.coords + 3 * (int64_t)n2, A.coords + 3 * (int64_t)n3, mat, W4, rec);
 }
 
+// Phase 1 from the per-CTA copies of connectivity / material index (one dependent-load level less than
+// going through the element number).
+TEFEM_HD double stage_element_direct(const AssembleArgs& A, int32_t n0, int32_t n1, int32_t n2, int32_t n3,
+                                     int32_t mat_idx, double W4, double* rec) {
+    return element_record(A.coords + 3 * (int64_t)n0, A.coords + 3 * (int64_t)n1, A.coords + 3 * (int64_t)n2,
+                          A.coords + 3 * (int64_t)n3, A.mat_table + MAT_STRIDE * mat_idx, W4, rec);
+}
+
 // Phase 2 for one block: walk the incidence list and write the planes.
 // DUU: 0 = D has no uu part, 1 = alpha_M only (3 diagonal planes), 2 = alpha_K != 0 (9 planes).
 template <int OPS, int DUU>
-TEFEM_HD void assemble_block(const AssembleArgs& A, int32_t p, const double* recs,
-                             const double* S, const double* NN) {
+TEFEM_HD void assemble_block(const AssembleArgs& A, int32_t p, const double* recs, const uint16_t* inc,
+                             uint32_t s, uint32_t t, const double* S, const double* NN) {
     constexpr bool WANT_M = (OPS & TEFEM_OP_M) != 0, WANT_K = (OPS & TEFEM_OP_K) != 0, WANT_D = (OPS & TEFEM_OP_D) != 0;
     constexpr bool NEED_K = WANT_K || (WANT_D && DUU == 2);
     constexpr bool NEED_M = WANT_M || (WANT_D && DUU >= 1);
     BlockAcc<NEED_K, NEED_M, WANT_D> acc;
     acc.clear();
-    const uint32_t s = A.inc_ptr[p], t = A.inc_ptr[p + 1];
     for (uint32_t k = s; k < t; ++k) {
-        const uint32_t w = A.inc[k];
+        const uint32_t w = inc[k];
         block_accumulate<NEED_K, NEED_M, WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
     }
     const int64_t P = A.n_blocks;
@@ -202,25 +211,53 @@ static int upload_quad() {
 
 constexpr int ASM_THREADS = 256;
 
+// Shared memory: [max_cta_elems * REC_STRIDE doubles of element records][incidence entries of the CTA].
+// The blocks of a CTA are a contiguous range of p, so its incidence entries are one contiguous range
+// of `inc`: they are copied with 16-byte loads while phase 1 waits on its gathers, and the phase-2 loop
+// then reads them from shared memory instead of chasing global loads (ncu, profiles/r1_assemble_v1.md:
+// 19 % of all stall samples sat on that one dependent load).
 template <int OPS, int DUU>
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A) {
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, int rec_doubles) {
     extern __shared__ double recs[];
+    uint16_t* inc_s = reinterpret_cast<uint16_t*>(recs + rec_doubles);
     const int cta = blockIdx.x;
     const int e0 = A.cta_elem_ptr[cta], ne = A.cta_elem_ptr[cta + 1] - e0;
+    const int i0 = A.cta_item_ptr[cta], i1 = A.cta_item_ptr[cta + 1];
+    // first item of this thread: issue its index loads now, they are consumed after the barrier
+    const int it0 = i0 + threadIdx.x;
+    int32_t p0 = 0;
+    uint32_t s0 = 0, t0 = 0;
+    if (it0 < i1) {
+        p0 = __ldg(A.item_block + it0);
+        s0 = __ldg(A.inc_ptr + p0);
+        t0 = __ldg(A.inc_ptr + p0 + 1);
+    }
+    // incidence entries [inc_lo, inc_hi) -> shared memory, from the 16-byte aligned address below inc_lo
+    const uint32_t inc_lo = __ldg(A.inc_ptr + i0), inc_hi = __ldg(A.inc_ptr + i1);
+    const uint32_t base = inc_lo & ~7u;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(A.inc + base);
+        uint4* dst = reinterpret_cast<uint4*>(inc_s);
+        const uint32_t n16 = (inc_hi - base + 7u) >> 3;
+        for (uint32_t k = threadIdx.x; k < n16; k += ASM_THREADS) dst[k] = __ldg(src + k);
+    }
     const double W4 = c_quad.W4;
     for (int le = threadIdx.x; le < ne; le += ASM_THREADS) {
-        const int32_t e = __ldg(A.cta_elems + e0 + le);
-        const double det = stage_element(A, e, W4, recs + (size_t)le * REC_STRIDE);
+        const int4 c = __ldg(reinterpret_cast<const int4*>(A.cta_conn) + e0 + le);
+        const int32_t m = __ldg(A.cta_mat + e0 + le);
+        const double det = stage_element_direct(A, c.x, c.y, c.z, c.w, m, W4, recs + (size_t)le * REC_STRIDE);
         if (!(det > 0.0)) {  // error path only: elements.py:207-210
+            const int32_t e = A.cta_elems[e0 + le];
             if (det < 0.0) atomicMin(A.bad_elem, e);
             else atomicMin(A.bad_elem + 1, e);
         }
     }
     __syncthreads();
-    const int i0 = A.cta_item_ptr[cta], i1 = A.cta_item_ptr[cta + 1];
-    for (int it = i0 + threadIdx.x; it < i1; it += ASM_THREADS) {
+    if (it0 < i1) assemble_block<OPS, DUU>(A, p0, recs, inc_s, s0 - base, t0 - base, c_quad.S, c_quad.NN);
+    for (int it = it0 + ASM_THREADS; it < i1; it += ASM_THREADS) {
         const int32_t p = __ldg(A.item_block + it);
-        assemble_block<OPS, DUU>(A, p, recs, c_quad.S, c_quad.NN);
+        assemble_block<OPS, DUU>(A, p, recs, inc_s, __ldg(A.inc_ptr + p) - base, __ldg(A.inc_ptr + p + 1) - base,
+                                 c_quad.S, c_quad.NN);
     }
 }
 
@@ -245,24 +282,24 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
 }
 
 template <int OPS, int DUU>
-static int launch_assemble(const AssembleArgs& A, int n_cta, size_t smem, cudaStream_t st) {
+static int launch_assemble(const AssembleArgs& A, int n_cta, int rec_doubles, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
-    if (!attr_set || smem > 48 * 1024) {
+    if (!attr_set) {
         TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    assemble_kernel<OPS, DUU><<<n_cta, ASM_THREADS, smem, st>>>(A);
+    assemble_kernel<OPS, DUU><<<n_cta, ASM_THREADS, smem, st>>>(A, rec_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
 
 template <int OPS>
-static int dispatch_duu(const AssembleArgs& A, int duu, int n_cta, size_t smem, cudaStream_t st) {
-    if (!(OPS & TEFEM_OP_D)) return launch_assemble<OPS, 0>(A, n_cta, smem, st);
+static int dispatch_duu(const AssembleArgs& A, int duu, int n_cta, int rec_doubles, size_t smem, cudaStream_t st) {
+    if (!(OPS & TEFEM_OP_D)) return launch_assemble<OPS, 0>(A, n_cta, rec_doubles, smem, st);
     switch (duu) {
-        case 0: return launch_assemble<OPS, 0>(A, n_cta, smem, st);
-        case 1: return launch_assemble<OPS, 1>(A, n_cta, smem, st);
-        default: return launch_assemble<OPS, 2>(A, n_cta, smem, st);
+        case 0: return launch_assemble<OPS, 0>(A, n_cta, rec_doubles, smem, st);
+        case 1: return launch_assemble<OPS, 1>(A, n_cta, rec_doubles, smem, st);
+        default: return launch_assemble<OPS, 2>(A, n_cta, rec_doubles, smem, st);
     }
 }
 
@@ -283,14 +320,18 @@ extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn,
     return TEFEM_OK;
 }
 
-extern "C" int tefem_assemble(const double* coords, const int32_t* conn, const int32_t* mat_id,
-                              const double* mat_table, int n_mat, int32_t n_cta, int32_t max_cta_elems,
+extern "C" int tefem_assemble(const double* coords, const double* mat_table, int n_mat, int32_t n_cta,
+                              int32_t max_cta_elems, int32_t max_cta_inc,
                               const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
+                              const int32_t* cta_conn, const int32_t* cta_mat,
                               const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
                               int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                               double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem, void* stream) {
-    TEFEM_REQUIRE(coords && conn && mat_id && mat_table && bad_elem, "null mesh input");
-    TEFEM_REQUIRE(cta_item_ptr && cta_elem_ptr && cta_elems && item_block && inc_ptr && inc, "null schedule");
+    TEFEM_REQUIRE(coords && mat_table && bad_elem, "null mesh input");
+    TEFEM_REQUIRE(cta_item_ptr && cta_elem_ptr && cta_elems && cta_conn && cta_mat && item_block && inc_ptr && inc,
+                  "null schedule");
+    TEFEM_REQUIRE((((uintptr_t)inc) & 15) == 0 && (((uintptr_t)cta_conn) & 15) == 0, "inc / cta_conn must be 16-byte aligned");
+    TEFEM_REQUIRE(max_cta_inc >= 0, "max_cta_inc");
     TEFEM_REQUIRE(ops > 0 && ops < 8, "ops mask");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_M) || vals_M, "vals_M");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_K) || vals_K, "vals_K");
@@ -298,26 +339,28 @@ extern "C" int tefem_assemble(const double* coords, const int32_t* conn, const i
     TEFEM_REQUIRE(max_cta_elems > 0 && max_cta_elems <= 4096, "max_cta_elems must fit 12 bits");
     TEFEM_REQUIRE(n_mat > 0, "n_mat");
     if (n_cta == 0) return TEFEM_OK;
-    const size_t smem = (size_t)max_cta_elems * REC_STRIDE * sizeof(double);
-    TEFEM_REQUIRE(smem <= 200 * 1024, "max_cta_elems exceeds shared memory");
+    const int rec_doubles = (max_cta_elems * REC_STRIDE + 1) & ~1;    // keep the incidence area 16-byte aligned
+    const size_t smem = (size_t)rec_doubles * sizeof(double) + ((size_t)max_cta_inc + 16) * sizeof(uint16_t);
+    TEFEM_REQUIRE(smem <= 200 * 1024, "CTA tile exceeds shared memory");
     int rc = upload_quad();
     if (rc) return rc;
     AssembleArgs A;
-    A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
+    A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
     A.cta_item_ptr = cta_item_ptr; A.cta_elem_ptr = cta_elem_ptr; A.cta_elems = cta_elems;
+    A.cta_conn = cta_conn; A.cta_mat = cta_mat;
     A.item_block = item_block; A.inc_ptr = inc_ptr; A.inc = inc;
     A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
     cudaStream_t st = as_stream(stream);
     switch (ops) {
-        case 1: return dispatch_duu<1>(A, duu, n_cta, smem, st);
-        case 2: return dispatch_duu<2>(A, duu, n_cta, smem, st);
-        case 3: return dispatch_duu<3>(A, duu, n_cta, smem, st);
-        case 4: return dispatch_duu<4>(A, duu, n_cta, smem, st);
-        case 5: return dispatch_duu<5>(A, duu, n_cta, smem, st);
-        case 6: return dispatch_duu<6>(A, duu, n_cta, smem, st);
-        default: return dispatch_duu<7>(A, duu, n_cta, smem, st);
+        case 1: return dispatch_duu<1>(A, duu, n_cta, rec_doubles, smem, st);
+        case 2: return dispatch_duu<2>(A, duu, n_cta, rec_doubles, smem, st);
+        case 3: return dispatch_duu<3>(A, duu, n_cta, rec_doubles, smem, st);
+        case 4: return dispatch_duu<4>(A, duu, n_cta, rec_doubles, smem, st);
+        case 5: return dispatch_duu<5>(A, duu, n_cta, rec_doubles, smem, st);
+        case 6: return dispatch_duu<6>(A, duu, n_cta, rec_doubles, smem, st);
+        default: return dispatch_duu<7>(A, duu, n_cta, rec_doubles, smem, st);
     }
 }
 
@@ -336,27 +379,39 @@ extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, vo
 #else  // ------------------------------------------------------------------------------------------
 // TEFEM_HOST_EMU: sequential execution of the SAME per-thread routines (tests/host_emulation only).
 // ================================================================================================
-extern "C" int tefem_emu_assemble(const double* coords, const int32_t* conn, const int32_t* mat_id,
-                                  const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
+extern "C" int tefem_emu_assemble(const double* coords, const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
+                                  int32_t max_cta_inc,
                                   const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
+                                  const int32_t* cta_conn, const int32_t* cta_mat,
                                   const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
                                   int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                                   double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
     AssembleArgs A;
-    A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
+    A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
     A.cta_item_ptr = cta_item_ptr; A.cta_elem_ptr = cta_elem_ptr; A.cta_elems = cta_elems;
+    A.cta_conn = cta_conn; A.cta_mat = cta_mat;
     A.item_block = item_block; A.inc_ptr = inc_ptr; A.inc = inc;
     A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const QuadTables& q = quad_tables();
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
     std::vector<double> recs((size_t)max_cta_elems * REC_STRIDE);
+    std::vector<uint16_t> inc_s((size_t)max_cta_inc + 16);
     for (int cta = 0; cta < n_cta; ++cta) {
         const int e0 = cta_elem_ptr[cta], ne = cta_elem_ptr[cta + 1] - e0;
         if (ne > max_cta_elems) return TEFEM_ERR_INVALID;
+        // same staging arithmetic as the kernel: aligned-down copy of the CTA's incidence range
+        const int i0 = cta_item_ptr[cta], i1 = cta_item_ptr[cta + 1];
+        const uint32_t inc_lo = inc_ptr[i0], inc_hi = inc_ptr[i1];
+        const uint32_t base = inc_lo & ~7u;
+        const uint32_t n16 = (inc_hi - base + 7u) >> 3;
+        if ((size_t)n16 * 8 > inc_s.size()) return TEFEM_ERR_INVALID;
+        for (uint32_t k = 0; k < n16 * 8; ++k) inc_s[k] = inc[base + k];
         for (int le = 0; le < ne; ++le) {
             const int32_t e = cta_elems[e0 + le];
-            const double det = stage_element(A, e, q.W4, recs.data() + (size_t)le * REC_STRIDE);
+            const int32_t* c = cta_conn + 4 * (size_t)(e0 + le);
+            const double det = stage_element_direct(A, c[0], c[1], c[2], c[3], cta_mat[e0 + le], q.W4,
+                                                    recs.data() + (size_t)le * REC_STRIDE);
             if (!(det > 0.0)) {
                 int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
                 if (e < *slot) *slot = e;
@@ -366,9 +421,9 @@ extern "C" int tefem_emu_assemble(const double* coords, const int32_t* conn, con
             const int32_t p = item_block[it];
 #define TEFEM_EMU_CASE(O)                                                                    \
     case O:                                                                                  \
-        if (duu == 0 || !((O) & TEFEM_OP_D)) assemble_block<O, 0>(A, p, recs.data(), q.S, q.NN); \
-        else if (duu == 1) assemble_block<O, 1>(A, p, recs.data(), q.S, q.NN);               \
-        else assemble_block<O, 2>(A, p, recs.data(), q.S, q.NN);                             \
+        if (duu == 0 || !((O) & TEFEM_OP_D)) assemble_block<O, 0>(A, p, recs.data(), inc_s.data(), inc_ptr[p] - base, inc_ptr[p + 1] - base, q.S, q.NN); \
+        else if (duu == 1) assemble_block<O, 1>(A, p, recs.data(), inc_s.data(), inc_ptr[p] - base, inc_ptr[p + 1] - base, q.S, q.NN); \
+        else assemble_block<O, 2>(A, p, recs.data(), inc_s.data(), inc_ptr[p] - base, inc_ptr[p + 1] - base, q.S, q.NN); \
         break;
             switch (ops) {
                 TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)

@@ -17,6 +17,7 @@
 namespace tefem {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define TEFEM_CUDA_CHECK(expr)                                                           \
     do {                                                                                 \
@@ -28,7 +29,13 @@ void set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
-#define TEFEM_LAUNCH_CHECK() TEFEM_CUDA_CHECK(cudaGetLastError())
+// every kernel launch of the library is followed by exactly one TEFEM_LAUNCH_CHECK(): it also feeds the
+// launch counter that bench.py reports as "gpu_launches".
+#define TEFEM_LAUNCH_CHECK()                      \
+    do {                                          \
+        tefem::count_launch();                    \
+        TEFEM_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 #define TEFEM_REQUIRE(cond, msg)                                                         \
     do {                                                                                 \

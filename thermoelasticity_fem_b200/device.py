@@ -40,6 +40,11 @@ class DeviceMesh:
             schedule = build_schedule(conn_t, self.n_nodes, self.n_rows)
         self.schedule: Schedule = schedule.to(dev)
         del conn_t
+        # per-CTA copies of the staged elements' connectivity / material index (one gather level less in K1)
+        ce = self.schedule.cta_elems.long()
+        self.cta_conn = self.conn[ce].contiguous()
+        self.cta_mat = self.mat_id[ce].contiguous()
+        del ce
         self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
 
     # ---- K1 -------------------------------------------------------------------------------------
@@ -59,8 +64,9 @@ class DeviceMesh:
         self.bad_elem.fill_(_lib.INT32_MAX)
         p = _lib.ptr
         _lib.check(self.lib.tefem_assemble(
-            p(self.coords), p(self.conn), p(self.mat_id), p(self.mat_table), self.n_mat,
-            S.n_cta, S.max_cta_elems, p(S.cta_item_ptr), p(S.cta_elem_ptr), p(S.cta_elems),
+            p(self.coords), p(self.mat_table), self.n_mat,
+            S.n_cta, S.max_cta_elems, S.max_cta_inc, p(S.cta_item_ptr), p(S.cta_elem_ptr), p(S.cta_elems),
+            p(self.cta_conn), p(self.cta_mat),
             p(S.item_block), p(S.inc_ptr), p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
             p(out.get("M")) if "M" in ops else None, p(out.get("K")) if "K" in ops else None,
             p(out.get("D")) if "D" in ops else None, p(self.bad_elem), _lib.stream_ptr()))
@@ -192,6 +198,13 @@ class KrylovSolver:
         self.last_info = dict(iterations=int(info[0]), restarts=int(info[1]), relres=float(info[2]), bnorm=float(info[3]))
         _lib.check(rc)
         return self.last_info
+
+    def profile(self, enable=None):
+        """SpMV device time accumulated by the driver: returns (ms, count); enable True/False resets."""
+        ms, cnt = ctypes.c_double(), ctypes.c_int64()
+        flag = -1 if enable is None else int(bool(enable))
+        _lib.check(self.lib.tefem_solver_profile(self.handle, flag, ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, cnt.value
 
     def close(self):
         if self.handle:

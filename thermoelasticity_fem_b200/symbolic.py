@@ -37,9 +37,10 @@ class Schedule:
     block_row: torch.Tensor  # int32 [P]
     diag_idx: torch.Tensor   # int32 [n_rows]
     inc_ptr: torch.Tensor    # int32 [P+1]  (read as uint32 by the kernels)
-    inc: torch.Tensor        # int16 [n_inc] (read as uint16 by the kernels)
+    inc: torch.Tensor        # int16 [n_inc + 8] (read as uint16 by the kernels; 8 entries of padding)
     n_cta: int
     max_cta_elems: int
+    max_cta_inc: int
     cta_item_ptr: torch.Tensor   # int32 [n_cta+1]
     item_block: torch.Tensor     # int32 [P]
     cta_elem_ptr: torch.Tensor   # int32 [n_cta+1]
@@ -130,6 +131,9 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     packed = (loc << 4) | ab
     del loc, ab
     packed = torch.where(packed >= 32768, packed - 65536, packed).to(torch.int16)
+    # the kernel copies a CTA's incidence range with 16-byte loads from the aligned address below it:
+    # keep the array readable 8 entries past its end
+    packed = torch.cat([packed, torch.zeros(8, dtype=torch.int16, device=dev)])
 
     # ---- items of each CTA, longest lists first (homogeneous warps), stable inside equal lengths
     maxlen = int(counts.max().item()) if P else 0
@@ -137,11 +141,14 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     item_block = torch.sort(k3, stable=True)[1]
     cta_item_ptr = torch.zeros(n_cta + 1, dtype=torch.int64, device=dev)
     torch.cumsum(torch.bincount(cta_of_block, minlength=n_cta), 0, out=cta_item_ptr[1:])
+    # incidence range of each CTA (its blocks are the contiguous range cta_item_ptr[c] .. cta_item_ptr[c+1])
+    cta_inc = inc_ptr[cta_item_ptr[1:]] - inc_ptr[cta_item_ptr[:-1]]
+    max_cta_inc = int(cta_inc.max().item()) if n_cta else 0
 
     i32 = torch.int32
     return Schedule(n_nodes=N, n_rows=R, n_blocks=P, n_elems=E,
                     rowptr=rowptr.to(i32), colidx=block_col.to(i32), block_row=block_row.to(i32),
                     diag_idx=diag_idx.to(i32), inc_ptr=inc_ptr.to(i32), inc=packed,
-                    n_cta=n_cta, max_cta_elems=max_cta_elems,
+                    n_cta=n_cta, max_cta_elems=max_cta_elems, max_cta_inc=max_cta_inc,
                     cta_item_ptr=cta_item_ptr.to(i32), item_block=item_block.to(i32),
                     cta_elem_ptr=cta_elem_ptr.to(i32), cta_elems=cta_elems.to(i32))

@@ -90,24 +90,30 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * compute_mat_*_e calls, the np.ix_ scatter into the dense matrix and csc_array(dense)).
  *
  * Owner-computes schedule built once per mesh by the symbolic phase (host side, symbolic.py):
- *   CTA c owns the blocks item_block[cta_item_ptr[c] .. cta_item_ptr[c+1]) (a permutation of that same
- *   contiguous block range) and first stages the geometry of the elements
- *   cta_elems[cta_elem_ptr[c] .. cta_elem_ptr[c+1]) in shared memory, reading their connectivity and
- *   material index from the per-CTA copies cta_conn[.,4] = conn[cta_elems], cta_mat = mat_id[cta_elems];
- *   max_cta_elems / max_cta_inc = largest element list / incidence range of a CTA (shared-memory size);
- *   inc must be 16-byte aligned and readable 8 entries past its end;
- *   block p sums the contributions inc[inc_ptr[p] .. inc_ptr[p+1]) IN ASCENDING ELEMENT ORDER
- *   (the order of the reference's loop, model.py:89,96,107); an entry of inc packs
- *   (local element index << 4) | (a << 2) | b with a, b the local node numbers of (row, column).
+ *   a CTA tile owns a contiguous range of node rows (hence of blocks p and of incidence entries);
+ *   cta_ptr[c][8] = {item0, item1, elem0, elem1, inc0, inc1, split0, split1};
+ *   it first stages, in shared memory, the geometry of the elements cta_elems[elem0 .. elem1), reading
+ *   their connectivity / material index from the per-tile copies cta_conn[.,4] = conn[cta_elems],
+ *   cta_mat = mat_id[cta_elems], and the incidence entries inc[inc0 .. inc1);
+ *   a WORK ITEM k in [item0, item1) is one block p = item_block[k], or one chunk of a block whose
+ *   incidence list is longer than the chunk limit (diagonal blocks): it sums the contributions
+ *   inc[item_inc[k] .. item_inc[k] + (item_meta[k] & 0xff)) IN ASCENDING ELEMENT ORDER (the order of the
+ *   reference's loop, model.py:89,96,107); an entry of inc packs (tile-local element << 4) | (a << 2) | b
+ *   with a, b the local node numbers of (row, column); (item_meta[k] >> 8) - 1 is the shared-memory slot
+ *   of a chunk's partial sums (-1: unsplit block, written directly);
+ *   split block j in [split0, split1): block split_block[j], partial slots (split_meta[j] & 0xffff) ..
+ *   + (split_meta[j] >> 16), added in chunk order by one thread;
+ *   max_cta_elems / max_cta_inc / max_cta_slots size the shared memory; inc must be 16-byte aligned and
+ *   readable 8 entries past its end.
  *   Every output value is written exactly once: no atomics, bitwise reproducible.
  * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
  * The D layout follows alpha_M / alpha_K (model.py:112-117).
  * bad_elem[2] as above; the call itself does not synchronise - use tefem_check_jacobian().      */
 int tefem_assemble(const double* coords, const double* mat_table, int n_mat,
-                   int32_t n_cta, int32_t max_cta_elems, int32_t max_cta_inc,
-                   const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
-                   const int32_t* cta_conn, const int32_t* cta_mat,
-                   const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
+                   int32_t n_cta, int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots,
+                   const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn, const int32_t* cta_mat,
+                   const int32_t* item_block, const uint32_t* item_inc, const int32_t* item_meta,
+                   const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
                    int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                    double* vals_M, double* vals_K, double* vals_D,
                    int32_t* bad_elem, void* stream);

@@ -53,20 +53,22 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     nD = layout.n_planes(layout.plane_map_D(aM, aK))
     vM, vK, vD = np.zeros((3, P)), np.zeros((13, P)), np.zeros((nD, P))
     bad = np.full(2, 2 ** 31 - 1, dtype=np.int32)
-    a = {k: getattr(S, k).numpy() for k in ("cta_item_ptr", "cta_elem_ptr", "cta_elems", "item_block", "inc_ptr", "inc")}
+    a = {k: getattr(S, k).numpy() for k in ("cta_ptr", "cta_elems", "item_block", "item_inc", "item_meta",
+                                            "split_block", "split_meta", "inc")}
     cta_conn = np.ascontiguousarray(conn.astype(np.int32)[a["cta_elems"]])
     cta_mat = np.ascontiguousarray(mat_id.astype(np.int32)[a["cta_elems"]])
     mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
     rc = emu.tefem_emu_assemble(ptr(pts), ptr(rows), ctypes.c_int32(S.n_cta), ctypes.c_int32(S.max_cta_elems),
-                                ctypes.c_int32(S.max_cta_inc), ptr(a["cta_item_ptr"]), ptr(a["cta_elem_ptr"]),
-                                ptr(a["cta_elems"]), ptr(cta_conn), ptr(cta_mat), ptr(a["item_block"]), ptr(a["inc_ptr"]),
+                                ctypes.c_int32(S.max_cta_inc), ctypes.c_int32(S.max_cta_slots), ptr(a["cta_ptr"]),
+                                ptr(a["cta_elems"]), ptr(cta_conn), ptr(cta_mat), ptr(a["item_block"]), ptr(a["item_inc"]),
+                                ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]),
                                 ptr(a["inc"]), ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
                                 ptr(vM), ptr(vK), ptr(vD), ptr(bad))
     assert rc == 0
     return dict(M=vM, K=vK, D=vD), bad
 
 
-def check_schedule_invariants(S, conn, n_nodes):
+def check_schedule_invariants(S, conn, n_nodes, max_chunk=6):
     E = conn.shape[0]
     rowptr, colidx = S.rowptr.numpy(), S.colidx.numpy()
     assert rowptr[0] == 0 and rowptr[-1] == S.n_blocks
@@ -74,32 +76,59 @@ def check_schedule_invariants(S, conn, n_nodes):
         cols = colidx[rowptr[i]:rowptr[i + 1]]
         assert np.all(np.diff(cols) > 0)
         assert colidx[S.diag_idx.numpy()[i]] == i
-    # each CTA's items are a permutation of its contiguous block range, longest incidence lists first
-    ip, ib, incp = S.cta_item_ptr.numpy(), S.item_block.numpy(), S.inc_ptr.numpy()
+    incp = S.inc_ptr.numpy().astype(np.int64)
+    cp = S.cta_ptr.numpy()
+    ib, ii, im = S.item_block.numpy(), S.item_inc.numpy().astype(np.int64), S.item_meta.numpy()
+    sb, sm = S.split_block.numpy(), S.split_meta.numpy()
+    assert cp[0, 0] == 0 and cp[-1, 1] == S.n_items and np.array_equal(cp[1:, 0], cp[:-1, 1])
+    assert np.array_equal(cp[1:, 4], cp[:-1, 5]) and cp[-1, 5] == incp[-1]
+    ilen = im & 0xff
+    assert ilen.max() <= max_chunk and ilen.min() >= 1
+    # the chunks of every block tile its incidence list exactly, in order
+    order = np.lexsort((ii, ib))
+    b_sorted, s_sorted, l_sorted = ib[order], ii[order], ilen[order]
+    first = np.r_[True, b_sorted[1:] != b_sorted[:-1]]
+    assert np.array_equal(s_sorted[first], incp[b_sorted[first]])
+    assert np.array_equal((s_sorted + l_sorted)[~np.r_[first[1:], True]], s_sorted[~first])
+    last = np.r_[first[1:], True]
+    assert np.array_equal((s_sorted + l_sorted)[last], incp[b_sorted[last] + 1])
+    assert np.array_equal(np.unique(ib), np.arange(S.n_blocks))
     for c in range(S.n_cta):
-        blk = ib[ip[c]:ip[c + 1]]
-        assert np.array_equal(np.sort(blk), np.arange(ip[c], ip[c + 1]))
-        lens = incp[blk + 1] - incp[blk]
-        assert np.all(np.diff(lens) <= 0)
-        assert S.cta_elem_ptr.numpy()[c + 1] - S.cta_elem_ptr.numpy()[c] <= S.max_cta_elems
-        assert incp[ip[c + 1]] - incp[ip[c]] <= S.max_cta_inc
+        i0, i1, e0, e1, n0, n1, s0, s1 = cp[c]
+        assert np.all(np.diff(ilen[i0:i1]) <= 0)                       # longest first
+        assert e1 - e0 <= S.max_cta_elems and n1 - n0 <= S.max_cta_inc
+        assert np.all(ii[i0:i1] >= n0) and np.all(ii[i0:i1] + ilen[i0:i1] <= n1)
+        slots = (im[i0:i1] >> 8) - 1
+        used = np.sort(slots[slots >= 0])
+        assert np.array_equal(used, np.arange(used.size)) and used.size <= S.max_cta_slots
+        # split lists: consecutive slots per block, covering exactly the split items of the tile
+        tot = 0
+        for k in range(s0, s1):
+            slot0, n = sm[k] & 0xffff, sm[k] >> 16
+            sel = (ib[i0:i1] == sb[k])
+            assert n >= 2 and sel.sum() == n
+            ss = slots[sel][np.argsort(ii[i0:i1][sel])]
+            assert np.array_equal(ss, np.arange(slot0, slot0 + n))      # chunk order = slot order
+            tot += n
+        assert tot == used.size
     assert S.inc.numel() == incp[-1] + 8
-    # every incidence entry decodes to an element of the CTA's list that really contains (row, col)
+    # every incidence entry decodes to an element of the tile's list that really contains (row, col)
     inc = S.inc.numpy().astype(np.int64) & 0xFFFF
-    ce, cep = S.cta_elems.numpy(), S.cta_elem_ptr.numpy()
+    ce = S.cta_elems.numpy()
     br = S.block_row.numpy()
-    cta_of_block = np.searchsorted(ip, np.arange(S.n_blocks), side="right") - 1
+    blk_ptr = np.searchsorted(incp, cp[:, 4])                         # first block of each tile
+    cta_of_block = np.searchsorted(blk_ptr, np.arange(S.n_blocks), side="right") - 1
     rng = np.random.default_rng(0)
     for p in rng.integers(0, S.n_blocks, size=400):
         c = cta_of_block[p]
-        last = -1
+        last_e = -1
         for k in range(incp[p], incp[p + 1]):
             w = inc[k]
-            e = ce[cep[c] + (w >> 4)]
+            e = ce[cp[c, 2] + (w >> 4)]
             a, b = (w >> 2) & 3, w & 3
             assert conn[e, a] == br[p] and conn[e, b] == colidx[p]
-            assert e > last                              # ascending element order = the reference's summation order
-            last = e
+            assert e > last_e                            # ascending element order = the reference's summation order
+            last_e = e
     assert incp[-1] == 16 * E if S.n_rows == n_nodes else incp[-1] <= 16 * E
 
 
@@ -142,8 +171,10 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
             3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
     conn, mat_id, rows = orc.element_table(tets, mats)
     for items in (256, 64):                       # small tiles: many CTAs, exercises the staging offsets
-        S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items))
-        check_schedule_invariants(S, conn, pts.shape[0])
+        chunk = 6 if items == 256 else 3
+        S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items),
+                           max_chunk=chunk)
+        check_schedule_invariants(S, conn, pts.shape[0], chunk)
         vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
         ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)
         A = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * pts.shape[0])

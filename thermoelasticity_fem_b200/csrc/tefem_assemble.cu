@@ -4,15 +4,19 @@
 // Element.compute_mat_*_e (elements.py:220-286), the np.ix_ scatter into a dense n_dofs^2 array
 // and csc_array(dense).  Design (DESIGN.md "K1"):
 //
-//   * the symbolic phase groups node rows into CTAs; a CTA first stages, in shared memory, the
+//   * the symbolic phase groups node rows into CTA tiles; a CTA first stages, in shared memory, the
 //     geometry record (inverse Jacobian columns = shape-function gradients, det, material-scaled
-//     weights) of every element that touches one of its rows (phase 1: coalesced int4 connectivity
-//     loads, gathers of node coordinates through L2);
-//   * then one thread per node-pair block walks that block's precomputed incidence list
-//     (element, a, b) in ascending element order - the slot map - and accumulates the block's
-//     13 (K) / 1 (M) / 4 (D) values in registers (phase 2), writing every output exactly once,
-//     coalesced, into structure-of-arrays planes.  No atomics, bitwise reproducible, and the
-//     summation order per entry is the reference's element order.
+//     weights) of every element that touches one of its rows (phase 1: coalesced int4 loads of the
+//     tile's connectivity copy, gathers of node coordinates through L2) and, with 16-byte loads, the
+//     tile's contiguous range of incidence entries;
+//   * then one thread per WORK ITEM - a node-pair block, or a chunk of <= max_chunk incidences of a
+//     block with a long incidence list (the diagonal blocks) - walks its precomputed incidence
+//     entries (element, a, b) in ascending element order - the slot map - and accumulates the block's
+//     13 (K) / 1 (M) / 4 (D) values in registers (phase 2).  Unsplit blocks are written straight to
+//     the structure-of-arrays planes; chunks park their partial sums in shared memory and one thread
+//     per split block adds them in chunk order (phase 3).  Every output value is written exactly
+//     once: no atomics, bitwise reproducible, summation in the reference's element order (chunked
+//     for the split blocks).
 //
 // The same per-thread routines are compiled for the host when TEFEM_HOST_EMU is defined; that
 // build is used only by tests/host_emulation to check the schedule logic in a GPU-less container
@@ -26,16 +30,18 @@ namespace tefem {
 
 struct AssembleArgs {
     const double* coords;
-    const int32_t* conn;
-    const int32_t* mat_id;
+    const int32_t* conn;       // element_matrices path only
+    const int32_t* mat_id;     // element_matrices path only
     const double* mat_table;
-    const int32_t* cta_item_ptr;
-    const int32_t* cta_elem_ptr;
-    const int32_t* cta_elems;
+    const int32_t* cta_ptr;    // [n_cta, 8]: item0, item1, elem0, elem1, inc0, inc1, split0, split1
+    const int32_t* cta_elems;  // staged element numbers (error reporting only)
     const int32_t* cta_conn;   // [n_staged, 4] connectivity of the staged elements (conn[cta_elems])
     const int32_t* cta_mat;    // [n_staged]    material index of the staged elements
-    const int32_t* item_block;
-    const uint32_t* inc_ptr;
+    const int32_t* item_block; // [n_items] block p of the work item
+    const uint32_t* item_inc;  // [n_items] first incidence entry of the work item (absolute index into inc)
+    const int32_t* item_meta;  // [n_items] length | (partial slot + 1) << 8   (slot + 1 == 0: unsplit block)
+    const int32_t* split_block;  // [n_split] block p of a split block
+    const int32_t* split_meta;   // [n_split] first partial slot | n_chunks << 16
     const uint16_t* inc;
     int64_t n_blocks;
     double alpha_M, alpha_K;
@@ -45,9 +51,11 @@ struct AssembleArgs {
     int32_t* bad_elem;
 };
 
+enum { CTA_ITEM0 = 0, CTA_ITEM1, CTA_ELEM0, CTA_ELEM1, CTA_INC0, CTA_INC1, CTA_SPLIT0, CTA_SPLIT1, CTA_STRIDE = 8 };
+
 // ---- per-thread routines (host + device) -------------------------------------------------------
 
-// Phase 1 for one staged element: returns det so that the caller can flag bad Jacobians.
+// Geometry record of element e read through the global connectivity (element_matrices path).
 TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double W4, double* rec) {
     const int32_t n0 = A.conn[4 * (int64_t)e], n1 = A.conn[4 * (int64_t)e + 1];
     const int32_t n2 = A.conn[4 * (int64_t)e + 2], n3 = A.conn[4 * (int64_t)e + 3];
@@ -64,34 +72,44 @@ TEFEM_HD double stage_element_direct(const AssembleArgs& A, int32_t n0, int32_t 
                           A.coords + 3 * (int64_t)n3, A.mat_table + MAT_STRIDE * mat_idx, W4, rec);
 }
 
-// Phase 2 for one block: walk the incidence list and write the planes.
-// DUU: 0 = D has no uu part, 1 = alpha_M only (3 diagonal planes), 2 = alpha_K != 0 (9 planes).
 template <int OPS, int DUU>
-TEFEM_HD void assemble_block(const AssembleArgs& A, int32_t p, const double* recs, const uint16_t* inc,
-                             uint32_t s, uint32_t t, const double* S, const double* NN) {
-    constexpr bool WANT_M = (OPS & TEFEM_OP_M) != 0, WANT_K = (OPS & TEFEM_OP_K) != 0, WANT_D = (OPS & TEFEM_OP_D) != 0;
-    constexpr bool NEED_K = WANT_K || (WANT_D && DUU == 2);
-    constexpr bool NEED_M = WANT_M || (WANT_D && DUU >= 1);
-    BlockAcc<NEED_K, NEED_M, WANT_D> acc;
-    acc.clear();
+struct AsmTraits {
+    static constexpr bool WANT_M = (OPS & TEFEM_OP_M) != 0, WANT_K = (OPS & TEFEM_OP_K) != 0, WANT_D = (OPS & TEFEM_OP_D) != 0;
+    static constexpr bool NEED_K = WANT_K || (WANT_D && DUU == 2);
+    static constexpr bool NEED_M = WANT_M || (WANT_D && DUU >= 1);
+    typedef BlockAcc<NEED_K, NEED_M, WANT_D> Acc;
+};
+
+// Phase 2: acc = sum over the incidence entries inc[s .. t) (ascending element order).
+template <int OPS, int DUU>
+TEFEM_HD void accumulate_list(typename AsmTraits<OPS, DUU>::Acc& acc, const double* recs, const uint16_t* inc,
+                              uint32_t s, uint32_t t, const double* S, const double* NN) {
+    typedef AsmTraits<OPS, DUU> T;
     for (uint32_t k = s; k < t; ++k) {
         const uint32_t w = inc[k];
-        block_accumulate<NEED_K, NEED_M, WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
+        block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
     }
+}
+
+// Write the planes of block p.  DUU: 0 = D has no uu part, 1 = alpha_M only (3 diagonal planes),
+// 2 = alpha_K != 0 (9 planes); model.py:112-117.
+template <int OPS, int DUU>
+TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTraits<OPS, DUU>::Acc& acc) {
+    typedef AsmTraits<OPS, DUU> T;
     const int64_t P = A.n_blocks;
-    if (WANT_M) {
+    if (T::WANT_M) {
         A.vals_M[p] = acc.m;
         A.vals_M[P + p] = acc.m;
         A.vals_M[2 * P + p] = acc.m;
     }
-    if (WANT_K) {
+    if (T::WANT_K) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) A.vals_K[i * P + p] = acc.kuu[i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) A.vals_K[(9 + i) * P + p] = acc.kut[i];
         A.vals_K[12 * P + p] = acc.ktt;
     }
-    if (WANT_D) {
+    if (T::WANT_D) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) A.vals_D[i * P + p] = acc.dtu[i];
         A.vals_D[3 * P + p] = acc.dtt;
@@ -110,6 +128,29 @@ TEFEM_HD void assemble_block(const AssembleArgs& A, int32_t p, const double* rec
                     A.vals_D[(4 + 3 * i + j) * P + p] = (i == j ? m : 0.0) + A.alpha_K * acc.kuu[3 * i + j];
         }
     }
+}
+
+// One work item: accumulate, then either write the block or park the partial sums.
+template <int OPS, int DUU>
+TEFEM_HD void process_item(const AssembleArgs& A, int32_t p, uint32_t s, int32_t meta, const double* recs,
+                           const uint16_t* inc_s, double* partials, const double* S, const double* NN) {
+    typename AsmTraits<OPS, DUU>::Acc acc;
+    acc.clear();
+    accumulate_list<OPS, DUU>(acc, recs, inc_s, s, s + (uint32_t)(meta & 0xff), S, NN);
+    const int slot = (meta >> 8) - 1;
+    if (slot < 0) store_block<OPS, DUU>(A, p, acc);
+    else acc.dump(partials + (size_t)slot * AsmTraits<OPS, DUU>::Acc::LIVE);
+}
+
+// Phase 3 for one split block: add the chunk partials in chunk order and write the block.
+template <int OPS, int DUU>
+TEFEM_HD void combine_split(const AssembleArgs& A, int32_t p, int32_t meta, const double* partials) {
+    typedef typename AsmTraits<OPS, DUU>::Acc Acc;
+    Acc acc;
+    acc.clear();
+    const int slot0 = meta & 0xffff, n = meta >> 16;
+    for (int c = 0; c < n; ++c) acc.add_from(partials + (size_t)(slot0 + c) * Acc::LIVE);
+    store_block<OPS, DUU>(A, p, acc);
 }
 
 // Dense element matrices of one element (parity path; elements.py:220-286).
@@ -176,6 +217,19 @@ const QuadTables& quad_tables() {
     return q;
 }
 
+static void fill_args(AssembleArgs& A, const double* coords, const double* mat_table, const int32_t* cta_ptr,
+                      const int32_t* cta_elems, const int32_t* cta_conn, const int32_t* cta_mat,
+                      const int32_t* item_block, const uint32_t* item_inc, const int32_t* item_meta,
+                      const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
+                      double alpha_M, double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
+    A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
+    A.cta_ptr = cta_ptr; A.cta_elems = cta_elems; A.cta_conn = cta_conn; A.cta_mat = cta_mat;
+    A.item_block = item_block; A.item_inc = item_inc; A.item_meta = item_meta;
+    A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
+    A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
+    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
+}
+
 }  // namespace tefem
 
 using namespace tefem;
@@ -211,29 +265,30 @@ static int upload_quad() {
 
 constexpr int ASM_THREADS = 256;
 
-// Shared memory: [max_cta_elems * REC_STRIDE doubles of element records][incidence entries of the CTA].
-// The blocks of a CTA are a contiguous range of p, so its incidence entries are one contiguous range
-// of `inc`: they are copied with 16-byte loads while phase 1 waits on its gathers, and the phase-2 loop
-// then reads them from shared memory instead of chasing global loads (ncu, profiles/r1_assemble_v1.md:
-// 19 % of all stall samples sat on that one dependent load).
+// Shared memory: [element records: rec_doubles][partial sums: part_doubles][incidence entries (uint16)].
+// A tile's incidence entries are one contiguous range of `inc`: they are copied with 16-byte loads while
+// phase 1 waits on its gathers, and the phase-2 loop reads them from shared memory instead of chasing a
+// global load per iteration (profiles/r1_assemble.md: 19 % of all stall samples sat on that load).
 template <int OPS, int DUU>
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, int rec_doubles) {
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, int rec_doubles, int part_doubles) {
     extern __shared__ double recs[];
-    uint16_t* inc_s = reinterpret_cast<uint16_t*>(recs + rec_doubles);
-    const int cta = blockIdx.x;
-    const int e0 = A.cta_elem_ptr[cta], ne = A.cta_elem_ptr[cta + 1] - e0;
-    const int i0 = A.cta_item_ptr[cta], i1 = A.cta_item_ptr[cta + 1];
-    // first item of this thread: issue its index loads now, they are consumed after the barrier
+    double* partials = recs + rec_doubles;
+    uint16_t* inc_s = reinterpret_cast<uint16_t*>(partials + part_doubles);
+    const int4 c0 = __ldg(reinterpret_cast<const int4*>(A.cta_ptr) + 2 * blockIdx.x);
+    const int4 c1 = __ldg(reinterpret_cast<const int4*>(A.cta_ptr) + 2 * blockIdx.x + 1);
+    const int i0 = c0.x, i1 = c0.y, e0 = c0.z, ne = c0.w - c0.z;
+    const uint32_t inc_lo = (uint32_t)c1.x, inc_hi = (uint32_t)c1.y;
+    const int sp0 = c1.z, sp1 = c1.w;
+    // first work item of this thread: issue its index loads now, they are consumed after the barrier
     const int it0 = i0 + threadIdx.x;
-    int32_t p0 = 0;
-    uint32_t s0 = 0, t0 = 0;
+    int32_t p0 = 0, m0 = 0;
+    uint32_t s0 = 0;
     if (it0 < i1) {
         p0 = __ldg(A.item_block + it0);
-        s0 = __ldg(A.inc_ptr + p0);
-        t0 = __ldg(A.inc_ptr + p0 + 1);
+        s0 = __ldg(A.item_inc + it0);
+        m0 = __ldg(A.item_meta + it0);
     }
     // incidence entries [inc_lo, inc_hi) -> shared memory, from the 16-byte aligned address below inc_lo
-    const uint32_t inc_lo = __ldg(A.inc_ptr + i0), inc_hi = __ldg(A.inc_ptr + i1);
     const uint32_t base = inc_lo & ~7u;
     {
         const uint4* src = reinterpret_cast<const uint4*>(A.inc + base);
@@ -253,11 +308,14 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const Assemble
         }
     }
     __syncthreads();
-    if (it0 < i1) assemble_block<OPS, DUU>(A, p0, recs, inc_s, s0 - base, t0 - base, c_quad.S, c_quad.NN);
-    for (int it = it0 + ASM_THREADS; it < i1; it += ASM_THREADS) {
-        const int32_t p = __ldg(A.item_block + it);
-        assemble_block<OPS, DUU>(A, p, recs, inc_s, __ldg(A.inc_ptr + p) - base, __ldg(A.inc_ptr + p + 1) - base,
-                                 c_quad.S, c_quad.NN);
+    if (it0 < i1) process_item<OPS, DUU>(A, p0, s0 - base, m0, recs, inc_s, partials, c_quad.S, c_quad.NN);
+    for (int it = it0 + ASM_THREADS; it < i1; it += ASM_THREADS)
+        process_item<OPS, DUU>(A, __ldg(A.item_block + it), __ldg(A.item_inc + it) - base, __ldg(A.item_meta + it), recs,
+                               inc_s, partials, c_quad.S, c_quad.NN);
+    if (sp1 > sp0) {   // uniform over the CTA
+        __syncthreads();
+        for (int k = sp0 + threadIdx.x; k < sp1; k += ASM_THREADS)
+            combine_split<OPS, DUU>(A, __ldg(A.split_block + k), __ldg(A.split_meta + k), partials);
     }
 }
 
@@ -281,25 +339,33 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
 
+struct LaunchDims {
+    int n_cta, max_cta_elems, max_cta_inc, max_cta_slots;
+};
+
 template <int OPS, int DUU>
-static int launch_assemble(const AssembleArgs& A, int n_cta, int rec_doubles, size_t smem, cudaStream_t st) {
+static int launch_assemble(const AssembleArgs& A, const LaunchDims& d, cudaStream_t st) {
+    const int rec_doubles = (d.max_cta_elems * REC_STRIDE + 1) & ~1;    // keep the areas behind it 16-byte aligned
+    const int part_doubles = (d.max_cta_slots * AsmTraits<OPS, DUU>::Acc::LIVE + 1) & ~1;
+    const size_t smem = ((size_t)rec_doubles + part_doubles) * sizeof(double) + ((size_t)d.max_cta_inc + 16) * sizeof(uint16_t);
+    TEFEM_REQUIRE(smem <= 200 * 1024, "CTA tile exceeds shared memory");
     static bool attr_set = false;
     if (!attr_set) {
         TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    assemble_kernel<OPS, DUU><<<n_cta, ASM_THREADS, smem, st>>>(A, rec_doubles);
+    assemble_kernel<OPS, DUU><<<d.n_cta, ASM_THREADS, smem, st>>>(A, rec_doubles, part_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
 
 template <int OPS>
-static int dispatch_duu(const AssembleArgs& A, int duu, int n_cta, int rec_doubles, size_t smem, cudaStream_t st) {
-    if (!(OPS & TEFEM_OP_D)) return launch_assemble<OPS, 0>(A, n_cta, rec_doubles, smem, st);
+static int dispatch_duu(const AssembleArgs& A, int duu, const LaunchDims& d, cudaStream_t st) {
+    if (!(OPS & TEFEM_OP_D)) return launch_assemble<OPS, 0>(A, d, st);
     switch (duu) {
-        case 0: return launch_assemble<OPS, 0>(A, n_cta, rec_doubles, smem, st);
-        case 1: return launch_assemble<OPS, 1>(A, n_cta, rec_doubles, smem, st);
-        default: return launch_assemble<OPS, 2>(A, n_cta, rec_doubles, smem, st);
+        case 0: return launch_assemble<OPS, 0>(A, d, st);
+        case 1: return launch_assemble<OPS, 1>(A, d, st);
+        default: return launch_assemble<OPS, 2>(A, d, st);
     }
 }
 
@@ -321,46 +387,41 @@ extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn,
 }
 
 extern "C" int tefem_assemble(const double* coords, const double* mat_table, int n_mat, int32_t n_cta,
-                              int32_t max_cta_elems, int32_t max_cta_inc,
-                              const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
-                              const int32_t* cta_conn, const int32_t* cta_mat,
-                              const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
-                              int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+                              int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots,
+                              const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn,
+                              const int32_t* cta_mat, const int32_t* item_block, const uint32_t* item_inc,
+                              const int32_t* item_meta, const int32_t* split_block, const int32_t* split_meta,
+                              const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                               double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem, void* stream) {
     TEFEM_REQUIRE(coords && mat_table && bad_elem, "null mesh input");
-    TEFEM_REQUIRE(cta_item_ptr && cta_elem_ptr && cta_elems && cta_conn && cta_mat && item_block && inc_ptr && inc,
-                  "null schedule");
-    TEFEM_REQUIRE((((uintptr_t)inc) & 15) == 0 && (((uintptr_t)cta_conn) & 15) == 0, "inc / cta_conn must be 16-byte aligned");
-    TEFEM_REQUIRE(max_cta_inc >= 0, "max_cta_inc");
+    TEFEM_REQUIRE(cta_ptr && cta_elems && cta_conn && cta_mat && item_block && item_inc && item_meta && inc, "null schedule");
+    TEFEM_REQUIRE(max_cta_slots == 0 || (split_block && split_meta), "null split lists");
+    TEFEM_REQUIRE((((uintptr_t)inc) & 15) == 0 && (((uintptr_t)cta_conn) & 15) == 0 && (((uintptr_t)cta_ptr) & 15) == 0,
+                  "inc / cta_conn / cta_ptr must be 16-byte aligned");
     TEFEM_REQUIRE(ops > 0 && ops < 8, "ops mask");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_M) || vals_M, "vals_M");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_K) || vals_K, "vals_K");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_D) || vals_D, "vals_D");
     TEFEM_REQUIRE(max_cta_elems > 0 && max_cta_elems <= 4096, "max_cta_elems must fit 12 bits");
+    TEFEM_REQUIRE(max_cta_inc >= 0 && max_cta_slots >= 0 && max_cta_slots < 65536, "max_cta_inc / max_cta_slots");
     TEFEM_REQUIRE(n_mat > 0, "n_mat");
     if (n_cta == 0) return TEFEM_OK;
-    const int rec_doubles = (max_cta_elems * REC_STRIDE + 1) & ~1;    // keep the incidence area 16-byte aligned
-    const size_t smem = (size_t)rec_doubles * sizeof(double) + ((size_t)max_cta_inc + 16) * sizeof(uint16_t);
-    TEFEM_REQUIRE(smem <= 200 * 1024, "CTA tile exceeds shared memory");
     int rc = upload_quad();
     if (rc) return rc;
     AssembleArgs A;
-    A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
-    A.cta_item_ptr = cta_item_ptr; A.cta_elem_ptr = cta_elem_ptr; A.cta_elems = cta_elems;
-    A.cta_conn = cta_conn; A.cta_mat = cta_mat;
-    A.item_block = item_block; A.inc_ptr = inc_ptr; A.inc = inc;
-    A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
-    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
+    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn, cta_mat, item_block, item_inc, item_meta, split_block,
+              split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
+    const LaunchDims d = {n_cta, max_cta_elems, max_cta_inc, max_cta_slots};
     cudaStream_t st = as_stream(stream);
     switch (ops) {
-        case 1: return dispatch_duu<1>(A, duu, n_cta, rec_doubles, smem, st);
-        case 2: return dispatch_duu<2>(A, duu, n_cta, rec_doubles, smem, st);
-        case 3: return dispatch_duu<3>(A, duu, n_cta, rec_doubles, smem, st);
-        case 4: return dispatch_duu<4>(A, duu, n_cta, rec_doubles, smem, st);
-        case 5: return dispatch_duu<5>(A, duu, n_cta, rec_doubles, smem, st);
-        case 6: return dispatch_duu<6>(A, duu, n_cta, rec_doubles, smem, st);
-        default: return dispatch_duu<7>(A, duu, n_cta, rec_doubles, smem, st);
+        case 1: return dispatch_duu<1>(A, duu, d, st);
+        case 2: return dispatch_duu<2>(A, duu, d, st);
+        case 3: return dispatch_duu<3>(A, duu, d, st);
+        case 4: return dispatch_duu<4>(A, duu, d, st);
+        case 5: return dispatch_duu<5>(A, duu, d, st);
+        case 6: return dispatch_duu<6>(A, duu, d, st);
+        default: return dispatch_duu<7>(A, duu, d, st);
     }
 }
 
@@ -379,61 +440,67 @@ extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, vo
 #else  // ------------------------------------------------------------------------------------------
 // TEFEM_HOST_EMU: sequential execution of the SAME per-thread routines (tests/host_emulation only).
 // ================================================================================================
-extern "C" int tefem_emu_assemble(const double* coords, const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
-                                  int32_t max_cta_inc,
-                                  const int32_t* cta_item_ptr, const int32_t* cta_elem_ptr, const int32_t* cta_elems,
-                                  const int32_t* cta_conn, const int32_t* cta_mat,
-                                  const int32_t* item_block, const uint32_t* inc_ptr, const uint16_t* inc,
-                                  int64_t n_blocks, int ops, double alpha_M, double alpha_K,
-                                  double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
-    AssembleArgs A;
-    A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
-    A.cta_item_ptr = cta_item_ptr; A.cta_elem_ptr = cta_elem_ptr; A.cta_elems = cta_elems;
-    A.cta_conn = cta_conn; A.cta_mat = cta_mat;
-    A.item_block = item_block; A.inc_ptr = inc_ptr; A.inc = inc;
-    A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
-    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
+template <int OPS, int DUU>
+static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_cta_inc, int max_cta_slots) {
+    typedef typename AsmTraits<OPS, DUU>::Acc Acc;
     const QuadTables& q = quad_tables();
-    const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
     std::vector<double> recs((size_t)max_cta_elems * REC_STRIDE);
+    std::vector<double> partials((size_t)max_cta_slots * Acc::LIVE + 1);
     std::vector<uint16_t> inc_s((size_t)max_cta_inc + 16);
     for (int cta = 0; cta < n_cta; ++cta) {
-        const int e0 = cta_elem_ptr[cta], ne = cta_elem_ptr[cta + 1] - e0;
+        const int32_t* c = A.cta_ptr + (size_t)CTA_STRIDE * cta;
+        const int e0 = c[CTA_ELEM0], ne = c[CTA_ELEM1] - e0;
         if (ne > max_cta_elems) return TEFEM_ERR_INVALID;
-        // same staging arithmetic as the kernel: aligned-down copy of the CTA's incidence range
-        const int i0 = cta_item_ptr[cta], i1 = cta_item_ptr[cta + 1];
-        const uint32_t inc_lo = inc_ptr[i0], inc_hi = inc_ptr[i1];
+        // same staging arithmetic as the kernel: aligned-down copy of the tile's incidence range
+        const uint32_t inc_lo = (uint32_t)c[CTA_INC0], inc_hi = (uint32_t)c[CTA_INC1];
         const uint32_t base = inc_lo & ~7u;
         const uint32_t n16 = (inc_hi - base + 7u) >> 3;
         if ((size_t)n16 * 8 > inc_s.size()) return TEFEM_ERR_INVALID;
-        for (uint32_t k = 0; k < n16 * 8; ++k) inc_s[k] = inc[base + k];
+        for (uint32_t k = 0; k < n16 * 8; ++k) inc_s[k] = A.inc[base + k];
         for (int le = 0; le < ne; ++le) {
-            const int32_t e = cta_elems[e0 + le];
-            const int32_t* c = cta_conn + 4 * (size_t)(e0 + le);
-            const double det = stage_element_direct(A, c[0], c[1], c[2], c[3], cta_mat[e0 + le], q.W4,
+            const int32_t* cn = A.cta_conn + 4 * (size_t)(e0 + le);
+            const double det = stage_element_direct(A, cn[0], cn[1], cn[2], cn[3], A.cta_mat[e0 + le], q.W4,
                                                     recs.data() + (size_t)le * REC_STRIDE);
             if (!(det > 0.0)) {
-                int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
+                const int32_t e = A.cta_elems[e0 + le];
+                int32_t* slot = A.bad_elem + (det < 0.0 ? 0 : 1);
                 if (e < *slot) *slot = e;
             }
         }
-        for (int it = cta_item_ptr[cta]; it < cta_item_ptr[cta + 1]; ++it) {
-            const int32_t p = item_block[it];
-#define TEFEM_EMU_CASE(O)                                                                    \
-    case O:                                                                                  \
-        if (duu == 0 || !((O) & TEFEM_OP_D)) assemble_block<O, 0>(A, p, recs.data(), inc_s.data(), inc_ptr[p] - base, inc_ptr[p + 1] - base, q.S, q.NN); \
-        else if (duu == 1) assemble_block<O, 1>(A, p, recs.data(), inc_s.data(), inc_ptr[p] - base, inc_ptr[p + 1] - base, q.S, q.NN); \
-        else assemble_block<O, 2>(A, p, recs.data(), inc_s.data(), inc_ptr[p] - base, inc_ptr[p + 1] - base, q.S, q.NN); \
-        break;
-            switch (ops) {
-                TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)
-                TEFEM_EMU_CASE(5) TEFEM_EMU_CASE(6) TEFEM_EMU_CASE(7)
-                default: return TEFEM_ERR_INVALID;
-            }
-#undef TEFEM_EMU_CASE
+        for (int it = c[CTA_ITEM0]; it < c[CTA_ITEM1]; ++it) {
+            const int slot = (A.item_meta[it] >> 8) - 1;
+            if (slot >= max_cta_slots) return TEFEM_ERR_INVALID;
+            process_item<OPS, DUU>(A, A.item_block[it], A.item_inc[it] - base, A.item_meta[it], recs.data(), inc_s.data(),
+                                   partials.data(), q.S, q.NN);
         }
+        for (int k = c[CTA_SPLIT0]; k < c[CTA_SPLIT1]; ++k)
+            combine_split<OPS, DUU>(A, A.split_block[k], A.split_meta[k], partials.data());
     }
     return TEFEM_OK;
+}
+
+extern "C" int tefem_emu_assemble(const double* coords, const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
+                                  int32_t max_cta_inc, int32_t max_cta_slots, const int32_t* cta_ptr,
+                                  const int32_t* cta_elems, const int32_t* cta_conn, const int32_t* cta_mat,
+                                  const int32_t* item_block, const uint32_t* item_inc, const int32_t* item_meta,
+                                  const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
+                                  int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+                                  double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
+    AssembleArgs A;
+    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn, cta_mat, item_block, item_inc, item_meta, split_block,
+              split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
+    const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
+#define TEFEM_EMU_CASE(O)                                                                                     \
+    case O:                                                                                                   \
+        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots); \
+        if (duu == 1) return emu_run<O, 1>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots);              \
+        return emu_run<O, 2>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots);
+    switch (ops) {
+        TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)
+        TEFEM_EMU_CASE(5) TEFEM_EMU_CASE(6) TEFEM_EMU_CASE(7)
+        default: return TEFEM_ERR_INVALID;
+    }
+#undef TEFEM_EMU_CASE
 }
 
 extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* conn, const int32_t* mat_id,

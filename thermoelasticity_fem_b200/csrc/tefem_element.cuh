@@ -96,6 +96,34 @@ struct BlockAcc {
         for (int i = 0; i < (WITH_D ? 3 : 1); ++i) dtu[i] = 0.0;
         ktt = 0.0; m = 0.0; dtt = 0.0;
     }
+    // number of live accumulators, and (de)serialisation for the partial sums of split incidence lists
+    static constexpr int LIVE = (WITH_K ? 13 : 0) + (WITH_M ? 1 : 0) + (WITH_D ? 4 : 0);
+    TEFEM_HD void dump(double* dst) const {
+        int k = 0;
+        if (WITH_K) {
+            for (int i = 0; i < 9; ++i) dst[k++] = kuu[i];
+            for (int i = 0; i < 3; ++i) dst[k++] = kut[i];
+            dst[k++] = ktt;
+        }
+        if (WITH_M) dst[k++] = m;
+        if (WITH_D) {
+            for (int i = 0; i < 3; ++i) dst[k++] = dtu[i];
+            dst[k++] = dtt;
+        }
+    }
+    TEFEM_HD void add_from(const double* src) {
+        int k = 0;
+        if (WITH_K) {
+            for (int i = 0; i < 9; ++i) kuu[i] += src[k++];
+            for (int i = 0; i < 3; ++i) kut[i] += src[k++];
+            ktt += src[k++];
+        }
+        if (WITH_M) m += src[k++];
+        if (WITH_D) {
+            for (int i = 0; i < 3; ++i) dtu[i] += src[k++];
+            dtt += src[k++];
+        }
+    }
 };
 
 // acc += contribution of block (a, b) of the element whose record is `rec`.

@@ -65,9 +65,9 @@ class DeviceMesh:
         p = _lib.ptr
         _lib.check(self.lib.tefem_assemble(
             p(self.coords), p(self.mat_table), self.n_mat,
-            S.n_cta, S.max_cta_elems, S.max_cta_inc, p(S.cta_item_ptr), p(S.cta_elem_ptr), p(S.cta_elems),
-            p(self.cta_conn), p(self.cta_mat),
-            p(S.item_block), p(S.inc_ptr), p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
+            S.n_cta, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, p(S.cta_ptr), p(S.cta_elems),
+            p(self.cta_conn), p(self.cta_mat), p(S.item_block), p(S.item_inc), p(S.item_meta),
+            p(S.split_block), p(S.split_meta), p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
             p(out.get("M")) if "M" in ops else None, p(out.get("K")) if "K" in ops else None,
             p(out.get("D")) if "D" in ops else None, p(self.bad_elem), _lib.stream_ptr()))
         if check:

@@ -11,18 +11,23 @@ connectivity and of which blocks an operator has - and the element order of thos
 touched pattern of each operator follows from the plane maps in ``layout.py``.
 
 Outputs (see include/tefem.h, tefem_assemble):
-  rowptr[N+1], colidx[P]            node-block CSR, columns ascending inside a row
-  diag_idx[N]                       position of block (i, i)
-  inc_ptr[P+1], inc[16E]            per block: contributing (local element, a, b), ascending element
-  cta_item_ptr, item_block          blocks owned by each CTA, longest incidence lists first
-  cta_elem_ptr, cta_elems           elements each CTA stages in shared memory
+  rowptr[R+1], colidx[P]     node-block CSR, columns ascending inside a row
+  diag_idx[R]                position of block (i, i)
+  inc_ptr[P+1], inc[...]     per block: contributing (tile-local element, a, b), ascending element
+  work items                 a block, or a chunk of <= max_chunk incidences of a block with a long list
+                             (the diagonal blocks): item_block, item_inc (first entry), item_meta
+                             (length | (partial slot + 1) << 8)
+  split_block, split_meta    blocks whose list was split: block, first slot | n_chunks << 16
+  cta_ptr[n_cta, 8]          per tile: item range, staged-element range, incidence range, split range
+  cta_elems                  elements each tile stages in shared memory
 """
 from dataclasses import dataclass
 
 import torch
 
 ITEMS_PER_CTA = 256          # = ASM_THREADS of tefem_assemble.cu
-ELEM_BUDGET_PER_CTA = 640    # bound on sum of node degrees per CTA (>= staged elements)
+ELEM_BUDGET_PER_CTA = 344    # bound on the sum of node degrees per tile (>= staged elements; ~256 on Kuhn meshes)
+MAX_CHUNK = 6                # longest incidence list handled by one thread
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 
 
@@ -32,19 +37,24 @@ class Schedule:
     n_rows: int              # number of owned node rows
     n_blocks: int
     n_elems: int
+    n_items: int
     rowptr: torch.Tensor     # int32 [n_rows+1]
     colidx: torch.Tensor     # int32 [P]
     block_row: torch.Tensor  # int32 [P]
     diag_idx: torch.Tensor   # int32 [n_rows]
-    inc_ptr: torch.Tensor    # int32 [P+1]  (read as uint32 by the kernels)
+    inc_ptr: torch.Tensor    # int32 [P+1]
     inc: torch.Tensor        # int16 [n_inc + 8] (read as uint16 by the kernels; 8 entries of padding)
     n_cta: int
     max_cta_elems: int
     max_cta_inc: int
-    cta_item_ptr: torch.Tensor   # int32 [n_cta+1]
-    item_block: torch.Tensor     # int32 [P]
-    cta_elem_ptr: torch.Tensor   # int32 [n_cta+1]
-    cta_elems: torch.Tensor      # int32 [sum]
+    max_cta_slots: int
+    cta_ptr: torch.Tensor        # int32 [n_cta, 8]: item0, item1, elem0, elem1, inc0, inc1, split0, split1
+    cta_elems: torch.Tensor      # int32 [n_staged]
+    item_block: torch.Tensor     # int32 [n_items]
+    item_inc: torch.Tensor       # int32 [n_items]
+    item_meta: torch.Tensor      # int32 [n_items]
+    split_block: torch.Tensor    # int32 [n_split]
+    split_meta: torch.Tensor     # int32 [n_split]
 
     def to(self, device):
         kw = {}
@@ -53,23 +63,30 @@ class Schedule:
         return Schedule(**kw)
 
     def schedule_bytes(self):
-        """Bytes of slot-map / schedule data one assembly launch reads."""
+        """Bytes of slot-map / schedule data one assembly launch reads (cta_conn / cta_mat are counted by DeviceMesh)."""
         return sum(t.numel() * t.element_size() for t in
-                   (self.inc_ptr, self.inc, self.cta_item_ptr, self.item_block, self.cta_elem_ptr, self.cta_elems))
+                   (self.inc, self.cta_ptr, self.item_block, self.item_inc, self.item_meta, self.split_block, self.split_meta))
+
+
+def _excl_cumsum(x):
+    return torch.cumsum(x, 0) - x
 
 
 def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
-                   items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA) -> Schedule:
+                   items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA,
+                   max_chunk: int = MAX_CHUNK) -> Schedule:
     """conn: integer tensor [E, 4] in the reference's element order; node numbers < n_nodes.
     n_rows: only rows of nodes < n_rows are assembled (row-partitioned multi-GPU: owned nodes
     are numbered first); default all."""
     assert conn.dim() == 2 and conn.shape[1] == 4
+    assert 1 <= max_chunk <= 255
     dev = conn.device
     E = int(conn.shape[0])
     N = int(n_nodes)
     R = N if n_rows is None else int(n_rows)
     conn = conn.to(torch.int64)
     assert 16 * E < 2 ** 31, "incidence count must fit 31 bits per rank"
+    i64 = dict(dtype=torch.int64, device=dev)
 
     # ---- all (row, col) incidences in (element, a, b) order, keyed by row*N + col
     key = (conn[:, :, None] * N + conn[:, None, :]).reshape(-1)
@@ -87,42 +104,42 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     block_row = torch.div(ukey, N, rounding_mode='floor')
     block_col = ukey - block_row * N
     del ukey
-    inc_ptr = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    inc_ptr = torch.zeros(P + 1, **i64)
     torch.cumsum(counts, 0, out=inc_ptr[1:])
     blocks_per_row = torch.bincount(block_row, minlength=R)
-    rowptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+    rowptr = torch.zeros(R + 1, **i64)
     torch.cumsum(blocks_per_row, 0, out=rowptr[1:])
-    is_diag = block_row == block_col
-    diag_idx = torch.nonzero(is_diag).reshape(-1)
+    diag_idx = torch.nonzero(block_row == block_col).reshape(-1)
     assert int(diag_idx.numel()) == R, "every owned node must belong to at least one element"
 
-    # ---- rows -> CTAs: cumulative cost, integer arithmetic (blocks vs. staged-element budget)
-    degree = torch.bincount(conn.reshape(-1), minlength=N)[:R]
-    cost = torch.maximum(blocks_per_row * elem_budget, degree * items_per_cta)
-    unit = items_per_cta * elem_budget
-    excl = torch.cumsum(cost, 0) - cost
-    cta_of_row = torch.div(excl, unit, rounding_mode='floor')
-    # compact CTA ids (a very heavy row can skip an id)
-    _, cta_of_row = torch.unique_consecutive(cta_of_row, return_inverse=True)
-    n_cta = int(cta_of_row[-1].item()) + 1 if R > 0 else 0
+    # ---- work items: split incidence lists longer than max_chunk into balanced chunks
+    n_chunks = torch.div(counts + (max_chunk - 1), max_chunk, rounding_mode='floor')
+    items_per_row = torch.zeros(R, **i64).index_add_(0, block_row, n_chunks)
 
-    # ---- per-CTA staged element lists: unique (cta, element) over the (element, node) incidences
+    # ---- rows -> tiles: cumulative cost, integer arithmetic (work items vs. staged-element budget)
+    degree = torch.bincount(conn.reshape(-1), minlength=N)[:R]
+    cost = torch.maximum(items_per_row * elem_budget, degree * items_per_cta)
+    unit = items_per_cta * elem_budget
+    cta_of_row = torch.div(_excl_cumsum(cost), unit, rounding_mode='floor')
+    _, cta_of_row = torch.unique_consecutive(cta_of_row, return_inverse=True)    # compact ids
+    n_cta = int(cta_of_row[-1].item()) + 1 if R > 0 else 0
+    cta_of_block = cta_of_row[block_row]
+
+    # ---- per-tile staged element lists: unique (tile, element) over the (element, node) incidences
     node = conn.reshape(-1)
-    elem_of = torch.arange(E, device=dev, dtype=torch.int64).repeat_interleave(4)
+    elem_of = torch.arange(E, **i64).repeat_interleave(4)
     owned = node < R
-    k2 = cta_of_row[node[owned]] * E + elem_of[owned]
+    k2 = torch.unique(cta_of_row[node[owned]] * E + elem_of[owned])             # sorted
     del node, elem_of, owned
-    k2 = torch.unique(k2)                             # sorted
     cta_of_k2 = torch.div(k2, E, rounding_mode='floor')
     cta_elems = k2 - cta_of_k2 * E
-    cta_elem_ptr = torch.zeros(n_cta + 1, dtype=torch.int64, device=dev)
+    cta_elem_ptr = torch.zeros(n_cta + 1, **i64)
     torch.cumsum(torch.bincount(cta_of_k2, minlength=n_cta), 0, out=cta_elem_ptr[1:])
     max_cta_elems = int((cta_elem_ptr[1:] - cta_elem_ptr[:-1]).max().item()) if n_cta else 0
-    assert max_cta_elems <= MAX_CTA_ELEMS, "CTA element list exceeds the 12-bit local index"
+    assert max_cta_elems <= MAX_CTA_ELEMS, "tile element list exceeds the 12-bit local index"
     del cta_of_k2
 
-    # ---- packed incidence entries: (local element << 4) | (a << 2) | b
-    cta_of_block = cta_of_row[block_row]
+    # ---- packed incidence entries: (tile-local element << 4) | (a << 2) | b
     e_src = torch.div(src, 16, rounding_mode='floor')
     ab = src - e_src * 16
     cta_of_inc = torch.repeat_interleave(cta_of_block, counts)
@@ -131,24 +148,55 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     packed = (loc << 4) | ab
     del loc, ab
     packed = torch.where(packed >= 32768, packed - 65536, packed).to(torch.int16)
-    # the kernel copies a CTA's incidence range with 16-byte loads from the aligned address below it:
+    # the kernel copies a tile's incidence range with 16-byte loads from the aligned address below it:
     # keep the array readable 8 entries past its end
     packed = torch.cat([packed, torch.zeros(8, dtype=torch.int16, device=dev)])
 
-    # ---- items of each CTA, longest lists first (homogeneous warps), stable inside equal lengths
-    maxlen = int(counts.max().item()) if P else 0
-    k3 = cta_of_block * (maxlen + 1) + (maxlen - counts)
-    item_block = torch.sort(k3, stable=True)[1]
-    cta_item_ptr = torch.zeros(n_cta + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(torch.bincount(cta_of_block, minlength=n_cta), 0, out=cta_item_ptr[1:])
-    # incidence range of each CTA (its blocks are the contiguous range cta_item_ptr[c] .. cta_item_ptr[c+1])
-    cta_inc = inc_ptr[cta_item_ptr[1:]] - inc_ptr[cta_item_ptr[:-1]]
-    max_cta_inc = int(cta_inc.max().item()) if n_cta else 0
+    # ---- item arrays in (block, chunk) order
+    n_items = int(n_chunks.sum().item())
+    item_blk = torch.repeat_interleave(torch.arange(P, **i64), n_chunks)
+    chunk = torch.arange(n_items, **i64) - _excl_cumsum(n_chunks)[item_blk]
+    base_len = torch.div(counts, n_chunks, rounding_mode='floor')[item_blk]
+    rem = (counts - torch.div(counts, n_chunks, rounding_mode='floor') * n_chunks)[item_blk]
+    item_len = base_len + (chunk < rem).to(torch.int64)
+    item_inc = inc_ptr[item_blk] + chunk * base_len + torch.minimum(chunk, rem)
+    is_split = n_chunks[item_blk] > 1
+    cta_of_item = cta_of_block[item_blk]
+    items_per_cta_t = torch.bincount(cta_of_item, minlength=n_cta)
+    cta_item_ptr = torch.zeros(n_cta + 1, **i64)
+    torch.cumsum(items_per_cta_t, 0, out=cta_item_ptr[1:])
+    split_run = _excl_cumsum(is_split.to(torch.int64))                           # global rank among split items
+    slot = split_run - split_run[cta_item_ptr[:-1].clamp(max=max(n_items - 1, 0))][cta_of_item]
+    item_meta = item_len | torch.where(is_split, (slot + 1) << 8, torch.zeros_like(slot))
+    # split blocks of each tile
+    blk_split = torch.nonzero(n_chunks > 1).reshape(-1)
+    first_item = _excl_cumsum(n_chunks)[blk_split]
+    split_meta = slot[first_item] | (n_chunks[blk_split] << 16)
+    cta_split_ptr = torch.zeros(n_cta + 1, **i64)
+    torch.cumsum(torch.bincount(cta_of_block[blk_split], minlength=n_cta), 0, out=cta_split_ptr[1:])
+    slots_per_cta = torch.zeros(n_cta, **i64).index_add_(0, cta_of_item, is_split.to(torch.int64))
+    max_cta_slots = int(slots_per_cta.max().item()) if n_cta else 0
+    assert max_cta_slots < 65536
+
+    # ---- order the items of each tile longest first (homogeneous warps), stable inside equal lengths
+    perm = torch.sort(cta_of_item * (max_chunk + 1) + (max_chunk - item_len), stable=True)[1]
+    item_blk, item_inc, item_meta = item_blk[perm], item_inc[perm], item_meta[perm]
+    del perm
+
+    # ---- per-tile ranges: items, staged elements, incidence entries (contiguous: a tile owns a block range), splits
+    blocks_per_cta = torch.bincount(cta_of_block, minlength=n_cta)
+    cta_blk_ptr = torch.zeros(n_cta + 1, **i64)
+    torch.cumsum(blocks_per_cta, 0, out=cta_blk_ptr[1:])
+    cta_inc_ptr = inc_ptr[cta_blk_ptr]
+    max_cta_inc = int((cta_inc_ptr[1:] - cta_inc_ptr[:-1]).max().item()) if n_cta else 0
+    cta_ptr = torch.stack([cta_item_ptr[:-1], cta_item_ptr[1:], cta_elem_ptr[:-1], cta_elem_ptr[1:],
+                           cta_inc_ptr[:-1], cta_inc_ptr[1:], cta_split_ptr[:-1], cta_split_ptr[1:]], dim=1)
 
     i32 = torch.int32
-    return Schedule(n_nodes=N, n_rows=R, n_blocks=P, n_elems=E,
+    return Schedule(n_nodes=N, n_rows=R, n_blocks=P, n_elems=E, n_items=n_items,
                     rowptr=rowptr.to(i32), colidx=block_col.to(i32), block_row=block_row.to(i32),
                     diag_idx=diag_idx.to(i32), inc_ptr=inc_ptr.to(i32), inc=packed,
-                    n_cta=n_cta, max_cta_elems=max_cta_elems, max_cta_inc=max_cta_inc,
-                    cta_item_ptr=cta_item_ptr.to(i32), item_block=item_block.to(i32),
-                    cta_elem_ptr=cta_elem_ptr.to(i32), cta_elems=cta_elems.to(i32))
+                    n_cta=n_cta, max_cta_elems=max_cta_elems, max_cta_inc=max_cta_inc, max_cta_slots=max_cta_slots,
+                    cta_ptr=cta_ptr.to(i32).contiguous(), cta_elems=cta_elems.to(i32),
+                    item_block=item_blk.to(i32), item_inc=item_inc.to(i32), item_meta=item_meta.to(i32),
+                    split_block=blk_split.to(i32), split_meta=split_meta.to(i32))

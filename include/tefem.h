@@ -182,6 +182,10 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
                           const int32_t* boundary_rows, int32_t n_boundary_rows,
                           const int32_t* interior_rows, int32_t n_interior_rows);
 
+/* Fills the halo part of x (rows n_rows .. n_rows + n_halo) with the owners' values: pack kernel +
+ * grouped ncclSend/ncclRecv on `stream`.  No-op without a communicator.                          */
+int tefem_solver_halo_exchange(tefem_solver* s, double* x, void* stream);
+
 /* Left-block-Jacobi-scaled BiCGSTAB (replaces spsolve at solvers.py:26 and :172).
  * Solves sys x = b where sys and b have ALREADY been scaled by tefem_block_jacobi_scale/apply.
  * Stops when, for each field f in {u rows, theta rows}, ||(b - sys x)_f|| <= rtol * ||b_f|| (a field with

@@ -1,0 +1,128 @@
+"""The N > 1 path on the CPU: world_size-2 (and 3) `gloo` processes run the partitioner, assemble their owned rows
+with the host emulation of kernel K1, exchange halos with the send / receive lists the CUDA driver uses and
+reproduce the single-process operator, SpMV and dot products."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, result_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, "host_emulation"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import build_emu
+        from oracle import tefem_oracle as orc
+        from thermoelasticity_fem_b200 import layout
+        from thermoelasticity_fem_b200.partition import localize, slab_ranges
+        from thermoelasticity_fem_b200.symbolic import build_schedule
+        from thermoelasticity_fem_b200.synthetic import kuhn_box
+        from test_symbolic_and_emulation import emu_assemble, planes_to_csc
+        emu = ctypes.CDLL(build_emu.build())
+        nx, ny, nz = 7, 3, 2
+        pts, tets, tris, nodes = kuhn_box(nx, ny, nz, jitter=0.15, seed=2)
+        mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+                3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+        conn, mat_id, rows = orc.element_table(tets, mats)
+        N = pts.shape[0]
+        bounds = slab_ranges(nx + 1, (ny + 1) * (nz + 1), world)
+        lp = localize(conn, np.arange(conn.shape[0]), bounds, rank)
+        # local assembly of the owned rows (no communication)
+        S = build_schedule(torch.from_numpy(lp.conn), lp.n_local, n_rows=lp.n_own)
+        vals, bad = emu_assemble(emu, S, pts[lp.local_nodes], lp.conn, mat_id[lp.elem_ids], rows, "MKD", 0.2, 0.1)
+        K_loc = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * lp.n_local).tocsr()
+        # reference: the global operator
+        Kg = orc.assemble(pts, conn, rows, mat_id, 0.2, 0.1, which="K")["K"].tocsr()
+        lo, hi = bounds[rank], bounds[rank + 1]
+        dof_loc = (4 * lp.local_nodes[:, None] + np.arange(4)[None, :]).reshape(-1)
+        K_ref = Kg[4 * lo:4 * hi, :][:, dof_loc]
+        assert abs(K_loc - K_ref).max() <= 1e-12 * abs(K_ref).max()
+        assert (K_loc != 0).nnz <= K_loc.nnz and K_loc.shape == K_ref.shape
+        # distributed SpMV: owned x, halo filled by the exchange lists
+        xg = np.random.default_rng(5).standard_normal(4 * N)
+        x = np.zeros(4 * lp.n_local)
+        x[:4 * lp.n_own] = xg[4 * lo:4 * hi]
+        reqs, recv_bufs = [], []
+        for k, q in enumerate(lp.nbr):
+            idx = lp.send_idx[lp.send_ptr[k]:lp.send_ptr[k + 1]]
+            send = torch.from_numpy(x.reshape(-1, 4)[idx].copy())
+            recv = torch.empty((int(lp.recv_ptr[k + 1] - lp.recv_ptr[k]), 4), dtype=torch.float64)
+            reqs.append(dist.isend(send, int(q)))
+            reqs.append(dist.irecv(recv, int(q)))
+            recv_bufs.append((k, recv))
+        for r in reqs:
+            r.wait()
+        for k, recv in recv_bufs:
+            x.reshape(-1, 4)[lp.n_own + lp.recv_ptr[k]: lp.n_own + lp.recv_ptr[k + 1]] = recv.numpy()
+        assert np.array_equal(x, xg[dof_loc])                           # halo values are the owners' values
+        y = K_loc @ x
+        y_ref = (Kg @ xg)[4 * lo:4 * hi]
+        assert np.max(np.abs(y - y_ref)) <= 1e-13 * np.abs(y_ref).max()
+        # interior rows do not touch the halo, boundary rows do
+        Kcsr = K_loc.tocsr()
+        for i in lp.interior_rows[:: max(1, len(lp.interior_rows) // 20)]:
+            cols = Kcsr[4 * i:4 * i + 4].indices
+            assert cols.size == 0 or cols.max() < 4 * lp.n_own
+        for i in lp.boundary_rows:
+            assert Kcsr[4 * i:4 * i + 4].indices.max() >= 4 * lp.n_own
+        assert len(lp.interior_rows) + len(lp.boundary_rows) == lp.n_own
+        # packed dot products: local partials + all-reduce == global
+        pkt = torch.tensor([float(y @ y), float(y @ x[:4 * lp.n_own])], dtype=torch.float64)
+        dist.all_reduce(pkt)
+        yg = Kg @ xg
+        assert abs(pkt[0].item() - yg @ yg) <= 1e-12 * abs(yg @ yg) and abs(pkt[1].item() - yg @ xg) <= 1e-12 * abs(yg @ yg)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_assembly_spmv_and_reductions(world, tmp_path):
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
+
+
+def test_dirichlet_and_load_restriction_to_local_nodes():
+    """Global boundary data -> local masks / weights (the distributed path never relies on local triangles)."""
+    sys.path.insert(0, ROOT)
+    from thermoelasticity_fem_b200.distributed import dirichlet_node_data, surface_node_weights
+    from thermoelasticity_fem_b200.partition import localize, slab_ranges
+    from thermoelasticity_fem_b200.synthetic import kuhn_box, kuhn_face_tris, kuhn_node_coords, kuhn_slab_tets
+    from oracle import tefem_oracle as orc
+    n = 5
+    pts, tets, tris, nodes = kuhn_box(n, n, n, 1.0, 1.0, 1.0, n_layers=1)
+    dU = {4: [('x', 0.), ('y', 0.5), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]}
+    dT = {4: 0., 5: 2.0}
+    dofs, fill, lift = dirichlet_node_data({4: tris[4], 5: tris[5]}, dU, dT)
+    maps = orc.free_dofs_lists(pts.shape[0], tris, dU, dT)
+    assert np.array_equal(dofs, np.sort(np.concatenate([maps["dirichlet_dofs_U"], maps["dirichlet_dofs_theta"]])))
+    X = np.zeros(4 * pts.shape[0])
+    orc.fill_dirichlet(X, tris, dU, dT)
+    assert np.array_equal(X[dofs], fill) and np.array_equal(fill, lift)
+    uniq, w = surface_node_weights(lambda ids: kuhn_node_coords(ids, n, n, n, 1., 1., 1.), tris[5])
+    F = orc.assemble_F(pts, dict(nodes=nodes, tri=tris, tet=tets), dict(surface={5: np.array([1.0, 0.0, 0.0])}))
+    assert np.allclose(F[4 * uniq], w, rtol=1e-14, atol=0)
+    # slab generation == global generation restricted to the rank
+    world = 3
+    bounds = slab_ranges(n + 1, (n + 1) ** 2, world)
+    conn = tets[1]
+    for rank in range(world):
+        p0, p1 = bounds[rank] // (n + 1) ** 2, bounds[rank + 1] // (n + 1) ** 2
+        cg, ids = kuhn_slab_tets(n, n, n, p0 - 1, p1)
+        a = localize(cg, ids, bounds, rank)
+        b = localize(conn, np.arange(conn.shape[0]), bounds, rank)
+        assert np.array_equal(a.conn, b.conn) and np.array_equal(a.elem_ids, b.elem_ids)
+        assert np.array_equal(a.local_nodes, b.local_nodes) and np.array_equal(a.send_idx, b.send_idx)

@@ -300,3 +300,18 @@ def test_transient_sandwich_first_steps(sandwich_mesh2, sandwich):
             if step <= n_steps:
                 eu, et = parity.field_errors(states[int(step)][0], g["X"][:, col])
                 assert eu < 1e-6 and et < 1e-3, (step, eu, et)
+
+
+def test_two_gpu_transient_matches_single_gpu():
+    """Row-partitioned solve (NCCL halo exchange + packed all-reduces) == single-GPU solve.  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(root, "tools", "dist_check.py"), "16", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "tefem_solver_create": [P, c_int32, c_int32, P, P],
     "tefem_solver_destroy": [P],
     "tefem_solver_profile": [P, c_int, P, P],
+    "tefem_solver_halo_exchange": [P, P, P],
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],

@@ -511,6 +511,11 @@ static int reduce_to_packet(tefem_solver* s, int n_cta, cudaStream_t st) {
     return TEFEM_OK;
 }
 
+extern "C" int tefem_solver_halo_exchange(tefem_solver* s, double* x, void* stream) {
+    TEFEM_REQUIRE(s && x, "null pointer");
+    return halo_exchange(s, x, nullptr, as_stream(stream));
+}
+
 extern "C" int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, const double* sys,
                           const double* x, double* y, void* stream) {
     TEFEM_REQUIRE(rowptr && colidx && sys && x && y, "null pointer");

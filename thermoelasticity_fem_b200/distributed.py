@@ -1,0 +1,241 @@
+"""Multi-GPU transient solve: row-partitioned assembly, halo exchange, packed all-reduces.
+
+One process per GPU (torchrun); ``torch.distributed`` provides the rendezvous (it broadcasts the NCCL unique
+id), the data path uses the library's own communicator (``tefem_comm_*``: NCCL over NVLink resolved with
+dlopen): one grouped send/recv of interface node values before each SpMV - overlapped with the interior
+rows - and two packed all-reduces (1 and 8 doubles) per BiCGSTAB iteration.  Assembly needs no
+communication (``partition.py``).
+
+The reference has no distributed path; this module is an extension next to the drop-in API, built from the
+same kernels.  Constrained DOFs and boundary loads are evaluated from the GLOBAL boundary description (a
+halo node can be constrained through a triangle that is not local), then restricted to the local nodes.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, layout
+from .device import DeviceMesh, KrylovSolver, load_axpy, newmark_correct, newmark_predict
+from .materials import LinearThermoElastic
+from .partition import LocalProblem, localize, slab_ranges
+
+_MODIF = {'x': 0, 'y': 1, 'z': 2}
+
+
+def _nccl_path():
+    try:
+        import nvidia.nccl
+        cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return ""
+
+
+class Comm:
+    """Library communicator over all ranks of the default torch.distributed group."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        path = _nccl_path().encode()
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            _lib.check(self.lib.tefem_comm_unique_id(path, raw))
+            buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        buf = buf.to(dev)
+        dist.broadcast(buf, src=0)
+        raw = ctypes.create_string_buffer(bytes(buf.cpu().numpy().tobytes()), 128)
+        self.handle = ctypes.c_void_p()
+        _lib.check(self.lib.tefem_comm_create(ctypes.byref(self.handle), path, raw, self.world, self.rank))
+
+    def allreduce_sum_(self, t):
+        _lib.check(self.lib.tefem_comm_allreduce_sum(self.handle, _lib.ptr(t), t.numel(), _lib.stream_ptr()))
+        return t
+
+    def close(self):
+        if self.handle:
+            self.lib.tefem_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+def dirichlet_node_data(tri_groups_global, dict_dirichlet_U, dict_dirichlet_theta):
+    """Global constrained DOFs with fill / lift values as sparse (dof, fill, lift) arrays
+    (same rules as Model.create_free_dofs_lists, reference model.py:51-85, 304-339)."""
+    fill, lift = {}, {}
+    if dict_dirichlet_U is not None:
+        for tag, lst in dict_dirichlet_U.items():
+            uniq = np.unique(np.asarray(tri_groups_global[tag]).reshape(-1))
+            last = {}
+            for letter, val in lst:
+                if letter not in _MODIF:
+                    raise ValueError('Unrecognized DOF.')
+                last[_MODIF[letter]] = val
+            for letter, _ in lst:
+                m = _MODIF[letter]
+                for d in 4 * uniq + m:
+                    lift[d] = lift.get(d, 0.0) + last[m]
+            for m, val in last.items():
+                for d in 4 * uniq + m:
+                    fill[d] = val
+    if dict_dirichlet_theta is not None:
+        for tag, theta in dict_dirichlet_theta.items():
+            uniq = np.unique(np.asarray(tri_groups_global[tag]).reshape(-1))
+            for d in 4 * uniq + 3:
+                lift[d] = lift.get(d, 0.0) + theta
+                fill[d] = theta
+    dofs = np.array(sorted(fill), dtype=np.int64)
+    return dofs, np.array([fill[d] for d in dofs]), np.array([lift[d] for d in dofs])
+
+
+def surface_node_weights(coords_of, tri_global):
+    """Lumped nodal weights area/3 with the reference's 'area' 0.5*|X12.X13| (model.py:153), summed per GLOBAL node
+    in triangle order.  coords_of(ids) -> [n, 3]."""
+    tri = np.asarray(tri_global, dtype=np.int64)
+    X1, X2, X3 = coords_of(tri[:, 0]), coords_of(tri[:, 1]), coords_of(tri[:, 2])
+    area = 0.5 * np.abs(np.einsum('ij,ij->i', X2 - X1, X3 - X1))
+    uniq, inv = np.unique(tri.reshape(-1), return_inverse=True)
+    w = np.bincount(inv, weights=np.repeat(area / 3, 3), minlength=uniq.shape[0])
+    return uniq, w
+
+
+class DistributedTransient:
+    """Newmark transient solve of one material / surface-load configuration on a row-partitioned mesh.
+
+    lp: LocalProblem; coords_local [n_local, 3]; mat_id_local [E_loc]; materials: list of LinearThermoElastic;
+    dirichlet = (global dofs, fill, lift); loads = list of (global node ids, weights, coef_fn(i) -> 4 amplitudes)."""
+
+    def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
+                 alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=64,
+                 comm=None):
+        self.lp, self.comm = lp, comm
+        self.alpha_M, self.alpha_K = alpha_M, alpha_K
+        self.gamma, self.beta = gamma, beta
+        self.t_end, self.n_t = t_end, n_t
+        self.dt = t_end / (n_t - 1)
+        self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
+        table = np.array([m.table_row() for m in materials])
+        self.dm = DeviceMesh(coords_local, lp.conn, mat_id_local, table, n_rows=lp.n_own)
+        self.n_halo = lp.n_halo
+        self.lib = self.dm.lib
+        dev = self.dm.device
+        n_loc = 4 * lp.n_local
+        # constrained DOFs of the LOCAL nodes (owned and halo)
+        dofs, fill, lift = dirichlet
+        loc = lp.to_local(dofs // 4)
+        keep = loc >= 0
+        ldof = 4 * loc[keep] + dofs[keep] % 4
+        mask = np.zeros(n_loc, dtype=np.uint8)
+        mask[ldof] = 1
+        g_fill = np.zeros(n_loc)
+        g_fill[ldof] = fill[keep]
+        g_lift = np.zeros(n_loc)
+        g_lift[ldof] = lift[keep]
+        self._mask_host = mask.astype(bool)
+        self.dir_mask = torch.from_numpy(mask).to(dev)
+        self.g_fill = torch.from_numpy(g_fill).to(dev)
+        self.g_lift = torch.from_numpy(g_lift).to(dev)
+        self.has_lift = bool(np.any(g_lift != 0.0))
+        # loads restricted to the OWNED nodes
+        self.loads = []
+        for nodes_g, w, coef_fn in loads:
+            l = lp.to_local(nodes_g)
+            own = (l >= 0) & (l < lp.n_own)
+            if own.any():
+                self.loads.append((torch.from_numpy(l[own].astype(np.int32)).to(dev),
+                                   torch.from_numpy(np.asarray(w)[own]).to(dev), coef_fn))
+        self.solve_info = []
+
+    def prepare(self):
+        lp, dm, dev = self.lp, self.dm, self.dm.device
+        dt = self.dt
+        self.planes = dm.assemble("MKD", self.alpha_M, self.alpha_K)
+        d_layout = layout.n_planes(layout.plane_map_D(self.alpha_M, self.alpha_K))
+        self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
+        self.dinv = dm.block_jacobi_scale(self.sys)
+        self.krylov = KrylovSolver(dm, lp.n_halo, self.comm)
+        i32 = torch.int32
+        self.krylov.set_halo(lp.nbr, lp.send_ptr, torch.from_numpy(lp.send_idx.astype(np.int32)).to(dev), lp.recv_ptr,
+                             torch.from_numpy(lp.boundary_rows.astype(np.int32)).to(dev),
+                             torch.from_numpy(lp.interior_rows.astype(np.int32)).to(dev))
+        n_loc = 4 * lp.n_local
+        z = lambda: torch.zeros(n_loc, dtype=torch.float64, device=dev)
+        self._x, self._v, self._a, self._a_new, self._w1, self._w2, self._rhs, self._b = (z() for _ in range(8))
+        self._mapD = layout.plane_map_D(self.alpha_M, self.alpha_K)
+        self._mapK = layout.plane_map_K()
+        self._lift = None
+        if self.has_lift:
+            self._lift = z()
+            dm.planes_spmv(self.planes["K"], self._mapK, self.g_lift, self._lift)
+
+    def step(self, i):
+        dm, lib = self.dm, self.lib
+        rhs = self._rhs
+        rhs.zero_()
+        for node, w, coef_fn in self.loads:
+            load_axpy(lib, node, w, coef_fn(i), rhs)
+        if self._lift is not None:
+            rhs -= self._lift
+        newmark_predict(lib, self._x, self._v, self._a, self.dt, self.gamma, self.beta, self.dir_mask, self._w1, self._w2)
+        dm.planes_spmv(self.planes["D"], self._mapD, self._w1, rhs, alpha=-1.0, beta_y=1.0)
+        dm.planes_spmv(self.planes["K"], self._mapK, self._w2, rhs, alpha=-1.0, beta_y=1.0)
+        dm.block_jacobi_apply(self.dinv, rhs, self._b, self.dir_mask)
+        info = self.krylov.bicgstab(self.sys, self._b, self._a_new, self.rtol, self.max_iter, self.check_every)
+        # x, v, a are advanced on the halo nodes as well (same arithmetic as on their owner): they need a_new there
+        _lib.check(lib.tefem_solver_halo_exchange(self.krylov.handle, _lib.ptr(self._a_new), _lib.stream_ptr()))
+        newmark_correct(lib, self._x, self._v, self._a, self._a_new, self.dt, self.gamma, self.beta, self.dir_mask)
+        self.solve_info.append(info)
+        return info
+
+    def owned_state(self):
+        n = 4 * self.lp.n_own
+        return (self._x + self.g_fill)[:n], self._v[:n], self._a[:n]
+
+
+class _MeshShim:
+    """What bench.py needs from a mesh in the distributed case."""
+
+    def __init__(self, dm, n_nodes_global):
+        self._dm, self.n_nodes, self.n_dofs = dm, n_nodes_global, 4 * n_nodes_global
+
+    def device_mesh(self):
+        return self._dm
+
+
+def build_distributed_case(cells, rank, world, mat_kwargs, dU, dT, surface_arr, alpha_M, alpha_K, t_end, n_t, rtol):
+    """BASELINE config 4 on `world` GPUs: unit box of cells^3 Kuhn cells, x-slabs of node planes, every rank
+    generates only the cells that touch its planes.  Returns (mesh shim, model shim, solver) for bench.py."""
+    from .synthetic import kuhn_face_tris, kuhn_node_coords, kuhn_slab_tets
+    n = cells
+    plane = (n + 1) * (n + 1)
+    bounds = slab_ranges(n + 1, plane, world)
+    p0, p1 = int(bounds[rank] // plane), int(bounds[rank + 1] // plane)         # owned node planes [p0, p1)
+    conn_g, elem_ids = kuhn_slab_tets(n, n, n, p0 - 1, p1)                        # cells touching those planes
+    lp = localize(conn_g, elem_ids, bounds, rank)
+    coords_of = lambda ids: kuhn_node_coords(ids, n, n, n, 1.0, 1.0, 1.0)
+    coords = coords_of(lp.local_nodes)
+    tri_g = {4: kuhn_face_tris(n, n, n, 0, False), 5: kuhn_face_tris(n, n, n, 0, True)}
+    dirichlet = dirichlet_node_data(tri_g, dU, dT)
+    nodes5, w5 = surface_node_weights(coords_of, tri_g[5])
+    loads = [(nodes5, w5, lambda i: (surface_arr[0, i], surface_arr[1, i], surface_arr[2, i], 0.0))]
+    comm = Comm() if world > 1 else None
+    solver = DistributedTransient(lp, coords, np.zeros(lp.conn.shape[0], dtype=np.int32),
+                                  [LinearThermoElastic(**mat_kwargs)], dirichlet, loads, alpha_M, alpha_K,
+                                  t_end, n_t, rtol=rtol, comm=comm)
+    solver._ss = type("S", (), {})()          # bench.py reads solver._ss.krylov after prepare()
+    orig_prepare = solver.prepare
+
+    def prepare():
+        orig_prepare()
+        solver._ss.krylov = solver.krylov
+    solver.prepare = prepare
+    model = type("M", (), {})()
+    model.dirichlet_dofs_U = dirichlet[0][dirichlet[0] % 4 != 3]
+    model.dirichlet_dofs_theta = dirichlet[0][dirichlet[0] % 4 == 3]
+    return _MeshShim(solver.dm, (n + 1) ** 3), model, solver

@@ -99,3 +99,48 @@ def kuhn_box(nx, ny, nz, lx=2.0, ly=0.5, lz=0.3, n_layers=3, jitter=0.0, seed=0,
     d = np.linalg.norm(pts[top] - target, axis=1)
     node_groups = {8: np.array([top[np.argmin(d)]], dtype=index_dtype)}
     return pts, tet_groups, tri_groups, node_groups
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pieces of the same box for the row-partitioned multi-GPU path: a rank generates only its slab
+# ---------------------------------------------------------------------------------------------------
+def kuhn_node_coords(ids, nx, ny, nz, lx=2.0, ly=0.5, lz=0.3):
+    """Coordinates of the (global) node ids of an un-jittered box: the same values kuhn_box() produces."""
+    ids = np.asarray(ids, dtype=np.int64)
+    k = ids % (nz + 1)
+    j = (ids // (nz + 1)) % (ny + 1)
+    i = ids // ((nz + 1) * (ny + 1))
+    return np.stack([i * (lx / nx), j * (ly / ny), k * (lz / nz)], axis=-1).astype(np.float64)
+
+
+def kuhn_slab_tets(nx, ny, nz, ci0, ci1, index_dtype=np.int64):
+    """Tets of the cells with x-index in [ci0, ci1) of a single-layer (n_layers = 1) box: GLOBAL node ids and
+    GLOBAL element numbers, in the element order of kuhn_box(..., n_layers=1)."""
+    ci0, ci1 = max(ci0, 0), min(ci1, nx)
+    if ci1 <= ci0:
+        return np.zeros((0, 4), dtype=index_dtype), np.zeros(0, dtype=np.int64)
+    ci, cj, ck = np.meshgrid(np.arange(ci0, ci1), np.arange(ny), np.arange(nz), indexing='ij')
+    ci, cj, ck = ci.reshape(-1, 1, 1), cj.reshape(-1, 1, 1), ck.reshape(-1, 1, 1)
+    off = CELL_TETS
+    conn = ((ci + off[None, :, :, 0]) * (ny + 1) + (cj + off[None, :, :, 1])) * (nz + 1) + (ck + off[None, :, :, 2])
+    first = 6 * ci0 * ny * nz
+    return conn.reshape(-1, 4).astype(index_dtype), np.arange(first, first + 6 * (ci1 - ci0) * ny * nz, dtype=np.int64)
+
+
+def kuhn_face_tris(nx, ny, nz, axis, at_max, index_dtype=np.int64):
+    """Boundary triangles (GLOBAL node ids) of one face, identical to the tri groups of kuhn_box()."""
+    a, b = [d for d in range(3) if d != axis]
+    n = [nx, ny, nz]
+    fixed = n[axis] if at_max else 0
+    ca, cb = np.meshgrid(np.arange(n[a]), np.arange(n[b]), indexing='ij')
+    ca, cb = ca.reshape(-1), cb.reshape(-1)
+
+    def node(da, db):
+        ijk = [None, None, None]
+        ijk[axis] = np.full_like(ca, fixed)
+        ijk[a] = ca + da
+        ijk[b] = cb + db
+        return (ijk[0] * (ny + 1) + ijk[1]) * (nz + 1) + ijk[2]
+    t1 = np.stack([node(0, 0), node(1, 0), node(1, 1)], axis=1)
+    t2 = np.stack([node(0, 0), node(0, 1), node(1, 1)], axis=1)
+    return np.stack([t1, t2], axis=1).reshape(-1, 3).astype(index_dtype)

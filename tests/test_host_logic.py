@@ -1,0 +1,124 @@
+"""Host-side logic that needs no GPU: Gmsh I/O, mesh container, materials, DOF maps, plane layouts, and that
+the C-ABI library loads and exports every symbol include/tefem.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from oracle import tefem_oracle as orc
+
+
+def test_gmsh_roundtrip_and_mesh_groups(sandwich, tmp_path):
+    from thermoelasticity_fem_b200 import gmsh
+    from thermoelasticity_fem_b200.mesh import Mesh
+    pts, blocks, groups = sandwich
+    path = str(tmp_path / "sandwich.msh")
+    gmsh.write_msh41(path, pts, blocks)
+    p2, b2 = gmsh.read_msh41(path)
+    assert np.array_equal(p2, pts) and len(b2) == len(blocks)
+    for (t1, g1, c1), (t2, g2, c2) in zip(blocks, b2):
+        assert t1 == t2 and g1 == g2 and np.array_equal(np.asarray(c1).reshape(c2.shape), c2)
+    mesh = Mesh()
+    mesh.load_mesh(path)
+    assert mesh.n_nodes == 3119 and mesh.n_dofs == 12476
+    assert list(mesh.dict_tet_groups) == [3, 2, 1]                    # tag first-appearance order (mesh.py:51)
+    assert [len(v) for v in mesh.dict_tet_groups.values()] == [4513, 4520, 4679]
+    assert list(mesh.dict_tri_groups) == [4, 6, 5, 7] and mesh.dict_nodes_groups[8].tolist() == [16]
+    from thermoelasticity_fem_b200 import LinearThermoElastic
+    m = LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=750., alpha=4e-6, T0=20.)
+    mesh.set_materials({1: m, 2: m, 3: m})
+    mesh.make_elements()
+    assert mesh.n_elements == 13712 and len(mesh.elements) == 13712
+    conn, mat_id, table = mesh.element_tables()
+    oconn, omid, orows = orc.element_table(groups["tet"], {k: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.) for k in (1, 2, 3)})
+    assert np.array_equal(conn, oconn) and np.array_equal(mat_id, omid) and np.array_equal(table, orows)
+    el = mesh.elements[100]
+    assert el.number == 100 and el.dofs_nums_t == [4 * n + 3 for n in conn[100]]
+    assert np.array_equal(mesh.reference_temperature(), np.full(3119, 20.0))
+    with pytest.raises(KeyError):
+        mesh.set_materials({1: m})
+        mesh.make_elements()
+
+
+def test_material_matches_reference_values():
+    from thermoelasticity_fem_b200 import LinearThermoElastic, glass_SG773
+    m = LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=750., alpha=4e-6, T0=20.)
+    o = orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.)
+    assert m.beta == o.beta == 320000.0 and np.array_equal(m.mat_C, o.mat_C) and np.array_equal(m.table_row(), o.row())
+    assert glass_SG773.beta == m.beta
+
+
+def test_dof_maps_match_reference_without_gpu(sandwich):
+    """Model.create_free_dofs_lists is pure host logic (device upload is lazy)."""
+    from thermoelasticity_fem_b200 import Mesh, Model
+    pts, blocks, groups = sandwich
+    mesh = Mesh()
+    mesh.from_blocks(pts, blocks)
+    for name, dU in (("sandwich_steady.npz", {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('x', 0.), ('y', 0.), ('z', 0.)]}),
+                     ("sandwich_transient2.npz", {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]})):
+        g = golden(name)
+        model = Model(mesh, dict_dirichlet_U=dU, dict_dirichlet_theta={4: 0., 5: 0.})
+        model.create_free_dofs_lists()
+        for k in ("free_dofs", "free_dofs_U", "free_dofs_theta"):
+            assert np.array_equal(getattr(model, k), g[k]), (name, k)          # bit-exact DOF maps
+        assert np.array_equal(model.dirichlet_dofs_U, g["dirichlet_dofs_U_sorted"])
+        assert np.array_equal(model.dirichlet_dofs_theta, g["dirichlet_dofs_theta_sorted"])
+    with pytest.raises(ValueError, match="Unrecognized DOF"):
+        Model(mesh, dict_dirichlet_U={4: [('q', 0.)]}).create_free_dofs_lists()
+
+
+def test_plane_maps_cover_exactly_the_touched_entries():
+    from thermoelasticity_fem_b200 import layout
+    K = layout.plane_map_K()
+    assert sorted(K[K >= 0].tolist()) == list(range(13)) and np.all(K[3, :3] == -1)       # no tu block in K
+    M = layout.plane_map_M()
+    assert sorted(M[M >= 0].tolist()) == [0, 1, 2] and M[3, 3] == -1                       # M has no theta rows
+    for (aM, aK), n in (((0., 0.), 4), ((0.2, 0.), 7), ((0., 0.3), 13), ((0.2, 0.2), 13)):
+        D = layout.plane_map_D(aM, aK)
+        assert layout.n_planes(D) == n and sorted(D[D >= 0].tolist()) == list(range(n)) and np.all(D[:3, 3] == -1)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from thermoelasticity_fem_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tefem.h")).read()
+    declared = sorted(set(re.findall(r"\b(tefem_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tefem.h but not exported"
+    assert sorted(_lib.declared_symbols()) == declared                 # the ctypes table binds exactly the header
+    # host-only entry points work without a GPU
+    W4 = ctypes.c_double()
+    S = (ctypes.c_double * 4)()
+    NN = (ctypes.c_double * 16)()
+    assert _lib.load().tefem_quadrature_tables(ctypes.byref(W4), S, NN) == 0
+    oW4, oS, oNN = orc.quadrature_tables()
+    assert W4.value == oW4 and list(S) == list(oS) and list(NN) == list(oNN.reshape(-1))   # bit-exact constants
+    assert "sm_100a" in _lib.version()
+    assert _lib.load().tefem_launch_count() == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from thermoelasticity_fem_b200 import Mesh, Model, LinearThermoElastic
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(2, 2, 2)
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    m = LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=750., alpha=4e-6, T0=20.)
+    mesh.set_materials({1: m, 2: m, 3: m})
+    mesh.make_elements()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Model(mesh).assemble_K()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "thermoelasticity_fem_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src and "host_emulation" not in src, fn

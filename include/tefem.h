@@ -90,29 +90,33 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * compute_mat_*_e calls, the np.ix_ scatter into the dense matrix and csc_array(dense)).
  *
  * Owner-computes schedule built once per mesh by the symbolic phase (host side, symbolic.py):
- *   a CTA tile owns a contiguous range of node rows (hence of blocks p and of incidence entries);
- *   cta_ptr[c][8] = {item0, item1, elem0, elem1, inc0, inc1, split0, split1};
- *   it first stages, in shared memory, the geometry of the elements cta_elems[elem0 .. elem1), reading
- *   their connectivity / material index from the per-tile copies cta_conn[.,4] = conn[cta_elems],
- *   cta_mat = mat_id[cta_elems], and the incidence entries inc[inc0 .. inc1);
- *   a WORK ITEM k in [item0, item1) is one block p = item_block[k], or one chunk of a block whose
- *   incidence list is longer than the chunk limit (diagonal blocks): it sums the contributions
- *   inc[item_inc[k] .. item_inc[k] + (item_meta[k] & 0xff)) IN ASCENDING ELEMENT ORDER (the order of the
- *   reference's loop, model.py:89,96,107); an entry of inc packs (tile-local element << 4) | (a << 2) | b
- *   with a, b the local node numbers of (row, column); (item_meta[k] >> 8) - 1 is the shared-memory slot
- *   of a chunk's partial sums (-1: unsplit block, written directly);
+ *   a CTA tile owns a contiguous range of node rows;
+ *   cta_ptr[c][12] = {item0, item1, elem0, elem1, inc0, inc1, split0, split1, node0, node1, 0, 0};
+ *   it first stages, in shared memory, the coordinates of the nodes cta_nodes[node0 .. node1), then the geometry
+ *   of the elements cta_elems[elem0 .. elem1) - connectivity from cta_conn8 (4 tile-local node numbers, one byte
+ *   each), material index from cta_mat - and the incidence entries inc[inc0 .. inc1);
+ *   only DIAGONAL and UPPER (row < column) blocks carry incidence lists: a WORK ITEM k in [item0, item1) is
+ *     - an upper block p = item_block[k] (item_meta bit 24 set): its thread sums the contributions
+ *       inc[item_inc[k] .. + (item_meta[k] & 0xff)) IN ASCENDING ELEMENT ORDER (the order of the reference's loop,
+ *       model.py:89,96,107) and also produces the mirror block item_blockT[k] = (column, row) from the same
+ *       elements with (a, b) swapped (Kuu, Ktt, Muu, Dtt are transposes / equal; Kut, Dtu are accumulated
+ *       separately); item_blockT = -1 when the mirror row is not owned;
+ *     - or one chunk of a diagonal block whose list is longer than the chunk limit; ((item_meta[k] >> 8) & 0xffff) - 1
+ *       is the shared-memory slot of the chunk's partial sums (-1: unsplit, written directly);
+ *   an entry of inc packs (tile-local element << 4) | (a << 2) | b with a, b the local node numbers of (row, column);
  *   split block j in [split0, split1): block split_block[j], partial slots (split_meta[j] & 0xffff) ..
  *   + (split_meta[j] >> 16), added in chunk order by one thread;
- *   max_cta_elems / max_cta_inc / max_cta_slots size the shared memory; inc must be 16-byte aligned and
- *   readable 8 entries past its end.
+ *   max_cta_elems / max_cta_inc / max_cta_slots / max_cta_nodes size the shared memory; inc must be 16-byte
+ *   aligned and readable 8 entries past its end.
  *   Every output value is written exactly once: no atomics, bitwise reproducible.
  * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
  * The D layout follows alpha_M / alpha_K (model.py:112-117).
  * bad_elem[2] as above; the call itself does not synchronise - use tefem_check_jacobian().      */
 int tefem_assemble(const double* coords, const double* mat_table, int n_mat,
-                   int32_t n_cta, int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots,
-                   const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn, const int32_t* cta_mat,
-                   const int32_t* item_block, const uint32_t* item_inc, const int32_t* item_meta,
+                   int32_t n_cta, int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots, int32_t max_cta_nodes,
+                   const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
+                   const int32_t* cta_nodes, const int32_t* item_block, const int32_t* item_blockT,
+                   const uint32_t* item_inc, const int32_t* item_meta,
                    const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
                    int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                    double* vals_M, double* vals_K, double* vals_D,
@@ -206,6 +210,12 @@ int tefem_newmark_predict(int64_t n, const double* x, const double* v, const dou
                           double* w1, double* w2, void* stream);
 int tefem_newmark_correct(int64_t n, double* x, double* v, double* a, const double* a_new,
                           double dt, double gamma, double beta, const uint8_t* dir_mask, void* stream);
+
+/* out = c0 x0 + c1 x1 + c2 x2 (x1, x2 may be NULL).  Used to extrapolate the previous accelerations into the
+ * initial guess of the next step's solve (3 a_n - 3 a_{n-1} + a_{n-2}); the reference has no counterpart
+ * (spsolve is direct, solvers.py:172).                                                            */
+int tefem_lincomb3(int64_t n, double c0, const double* x0, double c1, const double* x1, double c2,
+                   const double* x2, double* out, void* stream);
 
 /* F[4*node[i] + c] += w[i] * h_coef[c], c = 0..3: the load vector as geometric nodal weights x a
  * time-dependent amplitude (model.py:120-286: area/3 and volume/4 lumping).  node[] unique.     */

@@ -51,57 +51,71 @@ def planes_to_csc(vals, pmap, S, n):
 def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     P = S.n_blocks
     nD = layout.n_planes(layout.plane_map_D(aM, aK))
-    vM, vK, vD = np.zeros((3, P)), np.zeros((13, P)), np.zeros((nD, P))
+    vM, vK, vD = np.full((3, P), np.nan), np.full((13, P), np.nan), np.full((nD, P), np.nan)
     bad = np.full(2, 2 ** 31 - 1, dtype=np.int32)
-    a = {k: getattr(S, k).numpy() for k in ("cta_ptr", "cta_elems", "item_block", "item_inc", "item_meta",
-                                            "split_block", "split_meta", "inc")}
-    cta_conn = np.ascontiguousarray(conn.astype(np.int32)[a["cta_elems"]])
+    a = {k: getattr(S, k).numpy() for k in ("cta_ptr", "cta_elems", "cta_conn8", "cta_nodes", "item_block", "item_blockT",
+                                            "item_inc", "item_meta", "split_block", "split_meta", "inc")}
     cta_mat = np.ascontiguousarray(mat_id.astype(np.int32)[a["cta_elems"]])
     mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
     rc = emu.tefem_emu_assemble(ptr(pts), ptr(rows), ctypes.c_int32(S.n_cta), ctypes.c_int32(S.max_cta_elems),
-                                ctypes.c_int32(S.max_cta_inc), ctypes.c_int32(S.max_cta_slots), ptr(a["cta_ptr"]),
-                                ptr(a["cta_elems"]), ptr(cta_conn), ptr(cta_mat), ptr(a["item_block"]), ptr(a["item_inc"]),
+                                ctypes.c_int32(S.max_cta_inc), ctypes.c_int32(S.max_cta_slots), ctypes.c_int32(S.max_cta_nodes),
+                                ptr(a["cta_ptr"]), ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_mat), ptr(a["cta_nodes"]),
+                                ptr(a["item_block"]), ptr(a["item_blockT"]), ptr(a["item_inc"]),
                                 ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]),
                                 ptr(a["inc"]), ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
                                 ptr(vM), ptr(vK), ptr(vD), ptr(bad))
     assert rc == 0
+    for nm, v in (("M", vM), ("K", vK), ("D", vD)):
+        if nm in ops and bad.min() == 2 ** 31 - 1:                               # (a bad Jacobian yields inf / nan values)
+            assert not np.isnan(v).any(), f"{nm}: some block was never written"     # every value written (exactly once)
     return dict(M=vM, K=vK, D=vD), bad
 
 
 def check_schedule_invariants(S, conn, n_nodes, max_chunk=6):
     E = conn.shape[0]
-    rowptr, colidx = S.rowptr.numpy(), S.colidx.numpy()
+    rowptr, colidx, br = S.rowptr.numpy(), S.colidx.numpy(), S.block_row.numpy()
     assert rowptr[0] == 0 and rowptr[-1] == S.n_blocks
     for i in range(0, S.n_rows, max(1, S.n_rows // 50)):
         cols = colidx[rowptr[i]:rowptr[i + 1]]
         assert np.all(np.diff(cols) > 0)
         assert colidx[S.diag_idx.numpy()[i]] == i
     incp = S.inc_ptr.numpy().astype(np.int64)
+    lb = S.listed_block.numpy()
+    assert np.array_equal(lb, np.nonzero(colidx >= br)[0])               # diagonal + upper blocks carry the lists
     cp = S.cta_ptr.numpy()
-    ib, ii, im = S.item_block.numpy(), S.item_inc.numpy().astype(np.int64), S.item_meta.numpy()
+    ib, ibT, ii, im = S.item_block.numpy(), S.item_blockT.numpy(), S.item_inc.numpy().astype(np.int64), S.item_meta.numpy()
     sb, sm = S.split_block.numpy(), S.split_meta.numpy()
     assert cp[0, 0] == 0 and cp[-1, 1] == S.n_items and np.array_equal(cp[1:, 0], cp[:-1, 1])
     assert np.array_equal(cp[1:, 4], cp[:-1, 5]) and cp[-1, 5] == incp[-1]
     ilen = im & 0xff
-    assert ilen.max() <= max_chunk and ilen.min() >= 1
-    # the chunks of every block tile its incidence list exactly, in order
+    upper = (im >> 24) & 1
+    assert ilen.min() >= 1 and ilen[upper == 0].max() <= max_chunk
+    assert np.array_equal(upper == 1, colidx[ib] > br[ib])
+    # mirrors: block (j, i) of an upper block (i, j), or -1 when row j is not owned; every lower block is produced once
+    has = ibT >= 0
+    assert np.all(upper[has] == 1) and np.array_equal(br[ibT[has]], colidx[ib[has]]) and np.array_equal(colidx[ibT[has]], br[ib[has]])
+    assert np.all(colidx[ib[(upper == 1) & ~has]] >= S.n_rows)
+    assert np.array_equal(np.sort(ibT[has]), np.nonzero(colidx < br)[0])
+    # the chunks of every listed block tile its incidence list exactly, in order
+    pos_of_block = np.full(S.n_blocks, -1)
+    pos_of_block[lb] = np.arange(lb.size)
     order = np.lexsort((ii, ib))
     b_sorted, s_sorted, l_sorted = ib[order], ii[order], ilen[order]
     first = np.r_[True, b_sorted[1:] != b_sorted[:-1]]
-    assert np.array_equal(s_sorted[first], incp[b_sorted[first]])
+    assert np.array_equal(s_sorted[first], incp[pos_of_block[b_sorted[first]]])
     assert np.array_equal((s_sorted + l_sorted)[~np.r_[first[1:], True]], s_sorted[~first])
     last = np.r_[first[1:], True]
-    assert np.array_equal((s_sorted + l_sorted)[last], incp[b_sorted[last] + 1])
-    assert np.array_equal(np.unique(ib), np.arange(S.n_blocks))
+    assert np.array_equal((s_sorted + l_sorted)[last], incp[pos_of_block[b_sorted[last]] + 1])
+    assert np.array_equal(np.unique(ib), lb)
+    cn8 = S.cta_conn8.numpy().astype(np.int64) & 0xFFFFFFFF
+    ce, cnodes = S.cta_elems.numpy(), S.cta_nodes.numpy()
     for c in range(S.n_cta):
-        i0, i1, e0, e1, n0, n1, s0, s1 = cp[c]
-        assert np.all(np.diff(ilen[i0:i1]) <= 0)                       # longest first
-        assert e1 - e0 <= S.max_cta_elems and n1 - n0 <= S.max_cta_inc
+        i0, i1, e0, e1, n0, n1, s0, s1, k0, k1 = cp[c, :10]
+        assert e1 - e0 <= S.max_cta_elems and n1 - n0 <= S.max_cta_inc and k1 - k0 <= S.max_cta_nodes <= 256
         assert np.all(ii[i0:i1] >= n0) and np.all(ii[i0:i1] + ilen[i0:i1] <= n1)
-        slots = (im[i0:i1] >> 8) - 1
+        slots = ((im[i0:i1] >> 8) & 0xffff) - 1
         used = np.sort(slots[slots >= 0])
         assert np.array_equal(used, np.arange(used.size)) and used.size <= S.max_cta_slots
-        # split lists: consecutive slots per block, covering exactly the split items of the tile
         tot = 0
         for k in range(s0, s1):
             slot0, n = sm[k] & 0xffff, sm[k] >> 16
@@ -111,25 +125,27 @@ def check_schedule_invariants(S, conn, n_nodes, max_chunk=6):
             assert np.array_equal(ss, np.arange(slot0, slot0 + n))      # chunk order = slot order
             tot += n
         assert tot == used.size
+        # byte connectivity decodes to the global connectivity through the tile's node list
+        loc = np.stack([(cn8[e0:e1] >> (8 * a)) & 0xff for a in range(4)], axis=1)
+        assert loc.max() < k1 - k0 and np.array_equal(cnodes[k0:k1][loc], conn[ce[e0:e1]])
     assert S.inc.numel() == incp[-1] + 8
     # every incidence entry decodes to an element of the tile's list that really contains (row, col)
     inc = S.inc.numpy().astype(np.int64) & 0xFFFF
-    ce = S.cta_elems.numpy()
-    br = S.block_row.numpy()
-    blk_ptr = np.searchsorted(incp, cp[:, 4])                         # first block of each tile
-    cta_of_block = np.searchsorted(blk_ptr, np.arange(S.n_blocks), side="right") - 1
+    l_ptr = np.searchsorted(incp, cp[:, 4])                            # first listed block of each tile
+    cta_of_listed = np.searchsorted(l_ptr, np.arange(lb.size), side="right") - 1
     rng = np.random.default_rng(0)
-    for p in rng.integers(0, S.n_blocks, size=400):
-        c = cta_of_block[p]
+    for q in rng.integers(0, lb.size, size=400):
+        p, c = lb[q], cta_of_listed[q]
         last_e = -1
-        for k in range(incp[p], incp[p + 1]):
+        for k in range(incp[q], incp[q + 1]):
             w = inc[k]
             e = ce[cp[c, 2] + (w >> 4)]
             a, b = (w >> 2) & 3, w & 3
             assert conn[e, a] == br[p] and conn[e, b] == colidx[p]
             assert e > last_e                            # ascending element order = the reference's summation order
             last_e = e
-    assert incp[-1] == 16 * E if S.n_rows == n_nodes else incp[-1] <= 16 * E
+    if S.n_rows == n_nodes:
+        assert incp[-1] == 10 * E                        # 4 diagonal + 6 upper incidences per element
 
 
 @pytest.mark.parametrize("aM,aK", [(0.2, 0.2), (0.3, 0.0), (0.0, 0.0)])
@@ -202,7 +218,10 @@ def test_row_restricted_schedule_matches_global_rows():
     nb = int(full.rowptr[R])
     assert part.n_blocks == nb and part.n_rows == R
     assert torch.equal(part.rowptr, full.rowptr[:R + 1]) and torch.equal(part.colidx, full.colidx[:nb])
-    assert torch.equal(part.inc_ptr, full.inc_ptr[:nb + 1])
+    nl = int((full.listed_block < nb).sum())
+    assert torch.equal(part.listed_block, full.listed_block[:nl]) and torch.equal(part.inc_ptr, full.inc_ptr[:nl + 1])
+    # mirrors whose row is not owned are dropped, the others are identical
+    assert torch.equal(part.rowptr, full.rowptr[:R + 1])
 
 
 def test_emulated_element_matrices_match_oracle(emu):

@@ -25,7 +25,7 @@ _SIGNATURES = {
     "tefem_version": [c_char_p, c_size_t],
     "tefem_quadrature_tables": [P, P, P],
     "tefem_element_matrices": [P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P],
-    "tefem_assemble": [P, P, c_int, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P,
+    "tefem_assemble": [P, P, c_int, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, P,
                        c_int64, c_int, c_double, c_double, P, P, P, P, P],
     "tefem_check_jacobian": [P, P, P],
     "tefem_planes_spmv": [P, P, c_int32, c_int64, P, P, P, c_double, c_double, P, P],
@@ -42,6 +42,7 @@ _SIGNATURES = {
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
     "tefem_newmark_correct": [c_int64, P, P, P, P, c_double, c_double, c_double, P, P],
     "tefem_load_axpy": [c_int64, P, P, P, P, P],
+    "tefem_lincomb3": [c_int64, c_double, P, c_double, P, c_double, P, P, P],
     "tefem_comm_unique_id": [c_char_p, P],
     "tefem_comm_create": [P, c_char_p, P, c_int, c_int],
     "tefem_comm_destroy": [P],

@@ -33,13 +33,15 @@ struct AssembleArgs {
     const int32_t* conn;       // element_matrices path only
     const int32_t* mat_id;     // element_matrices path only
     const double* mat_table;
-    const int32_t* cta_ptr;    // [n_cta, 8]: item0, item1, elem0, elem1, inc0, inc1, split0, split1
+    const int32_t* cta_ptr;    // [n_cta, 12]: item0, item1, elem0, elem1, inc0, inc1, split0, split1, node0, node1, -, -
     const int32_t* cta_elems;  // staged element numbers (error reporting only)
-    const int32_t* cta_conn;   // [n_staged, 4] connectivity of the staged elements (conn[cta_elems])
-    const int32_t* cta_mat;    // [n_staged]    material index of the staged elements
+    const int32_t* cta_conn8;  // [n_staged] connectivity of the staged elements as 4 tile-local node bytes
+    const int32_t* cta_mat;    // [n_staged] material index of the staged elements
+    const int32_t* cta_nodes;  // [n_tile_nodes] nodes whose coordinates the tile stages
     const int32_t* item_block; // [n_items] block p of the work item
+    const int32_t* item_blockT;  // [n_items] mirror block (j, i) of an upper block (i, j), or -1
     const uint32_t* item_inc;  // [n_items] first incidence entry of the work item (absolute index into inc)
-    const int32_t* item_meta;  // [n_items] length | (partial slot + 1) << 8   (slot + 1 == 0: unsplit block)
+    const int32_t* item_meta;  // [n_items] length | (partial slot + 1) << 8 | upper << 24  (slot + 1 == 0: unsplit)
     const int32_t* split_block;  // [n_split] block p of a split block
     const int32_t* split_meta;   // [n_split] first partial slot | n_chunks << 16
     const uint16_t* inc;
@@ -51,7 +53,9 @@ struct AssembleArgs {
     int32_t* bad_elem;
 };
 
-enum { CTA_ITEM0 = 0, CTA_ITEM1, CTA_ELEM0, CTA_ELEM1, CTA_INC0, CTA_INC1, CTA_SPLIT0, CTA_SPLIT1, CTA_STRIDE = 8 };
+enum { CTA_ITEM0 = 0, CTA_ITEM1, CTA_ELEM0, CTA_ELEM1, CTA_INC0, CTA_INC1, CTA_SPLIT0, CTA_SPLIT1, CTA_NODE0, CTA_NODE1,
+       CTA_STRIDE = 12 };
+enum { ITEM_UPPER = 1 << 24 };
 
 // ---- per-thread routines (host + device) -------------------------------------------------------
 
@@ -64,12 +68,12 @@ TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double W4, doubl
                           A.coords + 3 * (int64_t)n2, A.coords + 3 * (int64_t)n3, mat, W4, rec);
 }
 
-// Phase 1 from the per-CTA copies of connectivity / material index (one dependent-load level less than
-// going through the element number).
-TEFEM_HD double stage_element_direct(const AssembleArgs& A, int32_t n0, int32_t n1, int32_t n2, int32_t n3,
-                                     int32_t mat_idx, double W4, double* rec) {
-    return element_record(A.coords + 3 * (int64_t)n0, A.coords + 3 * (int64_t)n1, A.coords + 3 * (int64_t)n2,
-                          A.coords + 3 * (int64_t)n3, A.mat_table + MAT_STRIDE * mat_idx, W4, rec);
+// Phase 1 from the tile's staged node coordinates xyz[tile-local node][3] and the byte-packed tile-local
+// connectivity (no gather from global memory per element).
+TEFEM_HD double stage_element_local(const AssembleArgs& A, const double* xyz, uint32_t conn8, int32_t mat_idx, double W4,
+                                    double* rec) {
+    return element_record(xyz + 3 * (conn8 & 0xff), xyz + 3 * ((conn8 >> 8) & 0xff), xyz + 3 * ((conn8 >> 16) & 0xff),
+                          xyz + 3 * (conn8 >> 24), A.mat_table + MAT_STRIDE * mat_idx, W4, rec);
 }
 
 template <int OPS, int DUU>
@@ -130,16 +134,42 @@ TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTr
     }
 }
 
-// One work item: accumulate, then either write the block or park the partial sums.
+// One work item.  Upper block (i, j): accumulate it together with the non-symmetric parts of its mirror (j, i)
+// and write both.  Diagonal chunk: accumulate, then write the block or park the partial sums.
 template <int OPS, int DUU>
-TEFEM_HD void process_item(const AssembleArgs& A, int32_t p, uint32_t s, int32_t meta, const double* recs,
+TEFEM_HD void process_item(const AssembleArgs& A, int32_t p, int32_t pT, uint32_t s, int32_t meta, const double* recs,
                            const uint16_t* inc_s, double* partials, const double* S, const double* NN) {
-    typename AsmTraits<OPS, DUU>::Acc acc;
+    typedef AsmTraits<OPS, DUU> T;
+    typename T::Acc acc;
     acc.clear();
-    accumulate_list<OPS, DUU>(acc, recs, inc_s, s, s + (uint32_t)(meta & 0xff), S, NN);
-    const int slot = (meta >> 8) - 1;
-    if (slot < 0) store_block<OPS, DUU>(A, p, acc);
-    else acc.dump(partials + (size_t)slot * AsmTraits<OPS, DUU>::Acc::LIVE);
+    const uint32_t t = s + (uint32_t)(meta & 0xff);
+    if (meta & ITEM_UPPER) {
+        MirrorAcc<T::NEED_K, T::WANT_D> mir;
+        mir.clear();
+        for (uint32_t k = s; k < t; ++k) {
+            const uint32_t w = inc_s[k];
+            pair_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(acc, mir, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3,
+                                                             w & 3, S, NN);
+        }
+        store_block<OPS, DUU>(A, p, acc);
+        if (pT >= 0) {
+            if (T::NEED_K) {   // Kuu_ji = Kuu_ij^T ; Kut_ji from the mirror accumulators
+                double tmp;
+                tmp = acc.kuu[1]; acc.kuu[1] = acc.kuu[3]; acc.kuu[3] = tmp;
+                tmp = acc.kuu[2]; acc.kuu[2] = acc.kuu[6]; acc.kuu[6] = tmp;
+                tmp = acc.kuu[5]; acc.kuu[5] = acc.kuu[7]; acc.kuu[7] = tmp;
+                for (int i = 0; i < 3; ++i) acc.kut[i] = mir.kut[i];
+            }
+            if (T::WANT_D)
+                for (int i = 0; i < 3; ++i) acc.dtu[i] = mir.dtu[i];
+            store_block<OPS, DUU>(A, pT, acc);
+        }
+    } else {
+        accumulate_list<OPS, DUU>(acc, recs, inc_s, s, t, S, NN);
+        const int slot = ((meta >> 8) & 0xffff) - 1;
+        if (slot < 0) store_block<OPS, DUU>(A, p, acc);
+        else acc.dump(partials + (size_t)slot * T::Acc::LIVE);
+    }
 }
 
 // Phase 3 for one split block: add the chunk partials in chunk order and write the block.
@@ -218,13 +248,13 @@ const QuadTables& quad_tables() {
 }
 
 static void fill_args(AssembleArgs& A, const double* coords, const double* mat_table, const int32_t* cta_ptr,
-                      const int32_t* cta_elems, const int32_t* cta_conn, const int32_t* cta_mat,
-                      const int32_t* item_block, const uint32_t* item_inc, const int32_t* item_meta,
+                      const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat, const int32_t* cta_nodes,
+                      const int32_t* item_block, const int32_t* item_blockT, const uint32_t* item_inc, const int32_t* item_meta,
                       const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
                       double alpha_M, double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
     A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
-    A.cta_ptr = cta_ptr; A.cta_elems = cta_elems; A.cta_conn = cta_conn; A.cta_mat = cta_mat;
-    A.item_block = item_block; A.item_inc = item_inc; A.item_meta = item_meta;
+    A.cta_ptr = cta_ptr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_mat = cta_mat; A.cta_nodes = cta_nodes;
+    A.item_block = item_block; A.item_blockT = item_blockT; A.item_inc = item_inc; A.item_meta = item_meta;
     A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
     A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
@@ -265,26 +295,37 @@ static int upload_quad() {
 
 constexpr int ASM_THREADS = 256;
 
-// Shared memory: [element records: rec_doubles][partial sums: part_doubles][incidence entries (uint16)].
-// A tile's incidence entries are one contiguous range of `inc`: they are copied with 16-byte loads while
-// phase 1 waits on its gathers, and the phase-2 loop reads them from shared memory instead of chasing a
-// global load per iteration (profiles/r1_assemble.md: 19 % of all stall samples sat on that load).
+// Shared memory: [element records: rec_doubles][partial sums: part_doubles][node coordinates: xyz_doubles]
+// [incidence entries (uint16)].
+// A tile's incidence entries are one contiguous range of `inc`: they are copied with 16-byte loads while phase 0
+// waits on the coordinates, and the phase-2 loop reads them from shared memory instead of chasing a global load
+// per iteration (profiles/README.md: 19 % of all stall samples sat on that load in v1).  Node coordinates are
+// staged once per tile (coalesced for consecutive node numbers) instead of 12 scattered 8-byte gathers per element.
 template <int OPS, int DUU>
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, int rec_doubles, int part_doubles) {
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, int rec_doubles, int part_doubles,
+                                                                  int xyz_doubles) {
     extern __shared__ double recs[];
     double* partials = recs + rec_doubles;
-    uint16_t* inc_s = reinterpret_cast<uint16_t*>(partials + part_doubles);
-    const int4 c0 = __ldg(reinterpret_cast<const int4*>(A.cta_ptr) + 2 * blockIdx.x);
-    const int4 c1 = __ldg(reinterpret_cast<const int4*>(A.cta_ptr) + 2 * blockIdx.x + 1);
+    double* xyz = partials + part_doubles;
+    uint16_t* inc_s = reinterpret_cast<uint16_t*>(xyz + xyz_doubles);
+    const int4* hdr = reinterpret_cast<const int4*>(A.cta_ptr) + 3 * blockIdx.x;
+    const int4 c0 = __ldg(hdr), c1 = __ldg(hdr + 1), c2 = __ldg(hdr + 2);
     const int i0 = c0.x, i1 = c0.y, e0 = c0.z, ne = c0.w - c0.z;
     const uint32_t inc_lo = (uint32_t)c1.x, inc_hi = (uint32_t)c1.y;
     const int sp0 = c1.z, sp1 = c1.w;
-    // first work item of this thread: issue its index loads now, they are consumed after the barrier
+    const int n0 = c2.x, nn = c2.y - c2.x;
+    // phase 0: node coordinates -> shared memory
+    for (int k = threadIdx.x; k < nn; k += ASM_THREADS) {
+        const double* X = A.coords + 3 * (int64_t)__ldg(A.cta_nodes + n0 + k);
+        xyz[3 * k] = X[0]; xyz[3 * k + 1] = X[1]; xyz[3 * k + 2] = X[2];
+    }
+    // first work item of this thread: issue its index loads now, they are consumed after the barriers
     const int it0 = i0 + threadIdx.x;
-    int32_t p0 = 0, m0 = 0;
+    int32_t p0 = 0, pT0 = -1, m0 = 0;
     uint32_t s0 = 0;
     if (it0 < i1) {
         p0 = __ldg(A.item_block + it0);
+        pT0 = __ldg(A.item_blockT + it0);
         s0 = __ldg(A.item_inc + it0);
         m0 = __ldg(A.item_meta + it0);
     }
@@ -296,11 +337,20 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const Assemble
         const uint32_t n16 = (inc_hi - base + 7u) >> 3;
         for (uint32_t k = threadIdx.x; k < n16; k += ASM_THREADS) dst[k] = __ldg(src + k);
     }
+    // connectivity / material of this thread's first staged element (consumed after the barrier)
+    uint32_t cn0 = 0;
+    int32_t mt0 = 0;
+    if ((int)threadIdx.x < ne) {
+        cn0 = (uint32_t)__ldg(A.cta_conn8 + e0 + threadIdx.x);
+        mt0 = __ldg(A.cta_mat + e0 + threadIdx.x);
+    }
+    __syncthreads();
+    // phase 1: geometry records of the staged elements
     const double W4 = c_quad.W4;
     for (int le = threadIdx.x; le < ne; le += ASM_THREADS) {
-        const int4 c = __ldg(reinterpret_cast<const int4*>(A.cta_conn) + e0 + le);
-        const int32_t m = __ldg(A.cta_mat + e0 + le);
-        const double det = stage_element_direct(A, c.x, c.y, c.z, c.w, m, W4, recs + (size_t)le * REC_STRIDE);
+        const uint32_t cn = (le == (int)threadIdx.x) ? cn0 : (uint32_t)__ldg(A.cta_conn8 + e0 + le);
+        const int32_t m = (le == (int)threadIdx.x) ? mt0 : __ldg(A.cta_mat + e0 + le);
+        const double det = stage_element_local(A, xyz, cn, m, W4, recs + (size_t)le * REC_STRIDE);
         if (!(det > 0.0)) {  // error path only: elements.py:207-210
             const int32_t e = A.cta_elems[e0 + le];
             if (det < 0.0) atomicMin(A.bad_elem, e);
@@ -308,10 +358,12 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const Assemble
         }
     }
     __syncthreads();
-    if (it0 < i1) process_item<OPS, DUU>(A, p0, s0 - base, m0, recs, inc_s, partials, c_quad.S, c_quad.NN);
+    // phase 2: work items
+    if (it0 < i1) process_item<OPS, DUU>(A, p0, pT0, s0 - base, m0, recs, inc_s, partials, c_quad.S, c_quad.NN);
     for (int it = it0 + ASM_THREADS; it < i1; it += ASM_THREADS)
-        process_item<OPS, DUU>(A, __ldg(A.item_block + it), __ldg(A.item_inc + it) - base, __ldg(A.item_meta + it), recs,
-                               inc_s, partials, c_quad.S, c_quad.NN);
+        process_item<OPS, DUU>(A, __ldg(A.item_block + it), __ldg(A.item_blockT + it), __ldg(A.item_inc + it) - base,
+                               __ldg(A.item_meta + it), recs, inc_s, partials, c_quad.S, c_quad.NN);
+    // phase 3: split (diagonal) blocks
     if (sp1 > sp0) {   // uniform over the CTA
         __syncthreads();
         for (int k = sp0 + threadIdx.x; k < sp1; k += ASM_THREADS)
@@ -340,21 +392,23 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
 }
 
 struct LaunchDims {
-    int n_cta, max_cta_elems, max_cta_inc, max_cta_slots;
+    int n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes;
 };
 
 template <int OPS, int DUU>
 static int launch_assemble(const AssembleArgs& A, const LaunchDims& d, cudaStream_t st) {
     const int rec_doubles = (d.max_cta_elems * REC_STRIDE + 1) & ~1;    // keep the areas behind it 16-byte aligned
     const int part_doubles = (d.max_cta_slots * AsmTraits<OPS, DUU>::Acc::LIVE + 1) & ~1;
-    const size_t smem = ((size_t)rec_doubles + part_doubles) * sizeof(double) + ((size_t)d.max_cta_inc + 16) * sizeof(uint16_t);
+    const int xyz_doubles = (3 * d.max_cta_nodes + 1) & ~1;
+    const size_t smem = ((size_t)rec_doubles + part_doubles + xyz_doubles) * sizeof(double) +
+                        ((size_t)d.max_cta_inc + 16) * sizeof(uint16_t);
     TEFEM_REQUIRE(smem <= 200 * 1024, "CTA tile exceeds shared memory");
     static bool attr_set = false;
     if (!attr_set) {
         TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    assemble_kernel<OPS, DUU><<<d.n_cta, ASM_THREADS, smem, st>>>(A, rec_doubles, part_doubles);
+    assemble_kernel<OPS, DUU><<<d.n_cta, ASM_THREADS, smem, st>>>(A, rec_doubles, part_doubles, xyz_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
@@ -387,17 +441,19 @@ extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn,
 }
 
 extern "C" int tefem_assemble(const double* coords, const double* mat_table, int n_mat, int32_t n_cta,
-                              int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots,
-                              const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn,
-                              const int32_t* cta_mat, const int32_t* item_block, const uint32_t* item_inc,
+                              int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots, int32_t max_cta_nodes,
+                              const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn8,
+                              const int32_t* cta_mat, const int32_t* cta_nodes, const int32_t* item_block,
+                              const int32_t* item_blockT, const uint32_t* item_inc,
                               const int32_t* item_meta, const int32_t* split_block, const int32_t* split_meta,
                               const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                               double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem, void* stream) {
     TEFEM_REQUIRE(coords && mat_table && bad_elem, "null mesh input");
-    TEFEM_REQUIRE(cta_ptr && cta_elems && cta_conn && cta_mat && item_block && item_inc && item_meta && inc, "null schedule");
+    TEFEM_REQUIRE(cta_ptr && cta_elems && cta_conn8 && cta_mat && cta_nodes && item_block && item_blockT && item_inc &&
+                      item_meta && inc, "null schedule");
     TEFEM_REQUIRE(max_cta_slots == 0 || (split_block && split_meta), "null split lists");
-    TEFEM_REQUIRE((((uintptr_t)inc) & 15) == 0 && (((uintptr_t)cta_conn) & 15) == 0 && (((uintptr_t)cta_ptr) & 15) == 0,
-                  "inc / cta_conn / cta_ptr must be 16-byte aligned");
+    TEFEM_REQUIRE((((uintptr_t)inc) & 15) == 0 && (((uintptr_t)cta_ptr) & 15) == 0, "inc / cta_ptr must be 16-byte aligned");
+    TEFEM_REQUIRE(max_cta_nodes > 0 && max_cta_nodes <= 256, "max_cta_nodes must fit a byte");
     TEFEM_REQUIRE(ops > 0 && ops < 8, "ops mask");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_M) || vals_M, "vals_M");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_K) || vals_K, "vals_K");
@@ -409,10 +465,10 @@ extern "C" int tefem_assemble(const double* coords, const double* mat_table, int
     int rc = upload_quad();
     if (rc) return rc;
     AssembleArgs A;
-    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn, cta_mat, item_block, item_inc, item_meta, split_block,
-              split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
+    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn8, cta_mat, cta_nodes, item_block, item_blockT, item_inc,
+              item_meta, split_block, split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
-    const LaunchDims d = {n_cta, max_cta_elems, max_cta_inc, max_cta_slots};
+    const LaunchDims d = {n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes};
     cudaStream_t st = as_stream(stream);
     switch (ops) {
         case 1: return dispatch_duu<1>(A, duu, d, st);
@@ -441,16 +497,22 @@ extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, vo
 // TEFEM_HOST_EMU: sequential execution of the SAME per-thread routines (tests/host_emulation only).
 // ================================================================================================
 template <int OPS, int DUU>
-static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_cta_inc, int max_cta_slots) {
+static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_cta_inc, int max_cta_slots,
+                   int max_cta_nodes) {
     typedef typename AsmTraits<OPS, DUU>::Acc Acc;
     const QuadTables& q = quad_tables();
     std::vector<double> recs((size_t)max_cta_elems * REC_STRIDE);
     std::vector<double> partials((size_t)max_cta_slots * Acc::LIVE + 1);
     std::vector<uint16_t> inc_s((size_t)max_cta_inc + 16);
+    std::vector<double> xyz((size_t)3 * max_cta_nodes + 1);
     for (int cta = 0; cta < n_cta; ++cta) {
         const int32_t* c = A.cta_ptr + (size_t)CTA_STRIDE * cta;
         const int e0 = c[CTA_ELEM0], ne = c[CTA_ELEM1] - e0;
         if (ne > max_cta_elems) return TEFEM_ERR_INVALID;
+        const int n0 = c[CTA_NODE0], nn = c[CTA_NODE1] - n0;
+        if (nn > max_cta_nodes) return TEFEM_ERR_INVALID;
+        for (int k = 0; k < nn; ++k)
+            for (int d = 0; d < 3; ++d) xyz[3 * k + d] = A.coords[3 * (size_t)A.cta_nodes[n0 + k] + d];
         // same staging arithmetic as the kernel: aligned-down copy of the tile's incidence range
         const uint32_t inc_lo = (uint32_t)c[CTA_INC0], inc_hi = (uint32_t)c[CTA_INC1];
         const uint32_t base = inc_lo & ~7u;
@@ -458,9 +520,8 @@ static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_
         if ((size_t)n16 * 8 > inc_s.size()) return TEFEM_ERR_INVALID;
         for (uint32_t k = 0; k < n16 * 8; ++k) inc_s[k] = A.inc[base + k];
         for (int le = 0; le < ne; ++le) {
-            const int32_t* cn = A.cta_conn + 4 * (size_t)(e0 + le);
-            const double det = stage_element_direct(A, cn[0], cn[1], cn[2], cn[3], A.cta_mat[e0 + le], q.W4,
-                                                    recs.data() + (size_t)le * REC_STRIDE);
+            const double det = stage_element_local(A, xyz.data(), (uint32_t)A.cta_conn8[e0 + le], A.cta_mat[e0 + le], q.W4,
+                                                   recs.data() + (size_t)le * REC_STRIDE);
             if (!(det > 0.0)) {
                 const int32_t e = A.cta_elems[e0 + le];
                 int32_t* slot = A.bad_elem + (det < 0.0 ? 0 : 1);
@@ -468,10 +529,10 @@ static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_
             }
         }
         for (int it = c[CTA_ITEM0]; it < c[CTA_ITEM1]; ++it) {
-            const int slot = (A.item_meta[it] >> 8) - 1;
+            const int slot = ((A.item_meta[it] >> 8) & 0xffff) - 1;
             if (slot >= max_cta_slots) return TEFEM_ERR_INVALID;
-            process_item<OPS, DUU>(A, A.item_block[it], A.item_inc[it] - base, A.item_meta[it], recs.data(), inc_s.data(),
-                                   partials.data(), q.S, q.NN);
+            process_item<OPS, DUU>(A, A.item_block[it], A.item_blockT[it], A.item_inc[it] - base, A.item_meta[it],
+                                   recs.data(), inc_s.data(), partials.data(), q.S, q.NN);
         }
         for (int k = c[CTA_SPLIT0]; k < c[CTA_SPLIT1]; ++k)
             combine_split<OPS, DUU>(A, A.split_block[k], A.split_meta[k], partials.data());
@@ -480,21 +541,22 @@ static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_
 }
 
 extern "C" int tefem_emu_assemble(const double* coords, const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
-                                  int32_t max_cta_inc, int32_t max_cta_slots, const int32_t* cta_ptr,
-                                  const int32_t* cta_elems, const int32_t* cta_conn, const int32_t* cta_mat,
-                                  const int32_t* item_block, const uint32_t* item_inc, const int32_t* item_meta,
+                                  int32_t max_cta_inc, int32_t max_cta_slots, int32_t max_cta_nodes, const int32_t* cta_ptr,
+                                  const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
+                                  const int32_t* cta_nodes, const int32_t* item_block, const int32_t* item_blockT,
+                                  const uint32_t* item_inc, const int32_t* item_meta,
                                   const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
                                   int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                                   double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
     AssembleArgs A;
-    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn, cta_mat, item_block, item_inc, item_meta, split_block,
-              split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
+    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn8, cta_mat, cta_nodes, item_block, item_blockT, item_inc,
+              item_meta, split_block, split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
 #define TEFEM_EMU_CASE(O)                                                                                     \
     case O:                                                                                                   \
-        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots); \
-        if (duu == 1) return emu_run<O, 1>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots);              \
-        return emu_run<O, 2>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots);
+        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes); \
+        if (duu == 1) return emu_run<O, 1>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes);              \
+        return emu_run<O, 2>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes);
     switch (ops) {
         TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)
         TEFEM_EMU_CASE(5) TEFEM_EMU_CASE(6) TEFEM_EMU_CASE(7)

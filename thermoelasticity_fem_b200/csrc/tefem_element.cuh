@@ -164,4 +164,64 @@ TEFEM_HD void block_accumulate(BlockAcc<WITH_K, WITH_M, WITH_D>& acc, const doub
     }
 }
 
+// The non-symmetric parts of the MIRROR block (j, i) of an upper block (i, j).  Its symmetric parts are those of
+// (i, j): Kuu_ji = Kuu_ij^T, Ktt, Muu, Dtt equal (NN and g_a.g_b are symmetric bit for bit); only
+//   Kut_ji[i] = -beta det S_b G[i][a]      and      Dtu_ji[c] = -beta T0 det S_b GT[c][a]
+// differ, and they need nothing beyond what (i, j) already loads except GT[:, a].
+template <bool WITH_K, bool WITH_D>
+struct MirrorAcc {
+    double kut[WITH_K ? 3 : 1];
+    double dtu[WITH_D ? 3 : 1];
+    TEFEM_HD void clear() {
+        for (int i = 0; i < (WITH_K ? 3 : 1); ++i) kut[i] = 0.0;
+        for (int i = 0; i < (WITH_D ? 3 : 1); ++i) dtu[i] = 0.0;
+    }
+};
+
+// acc += block (a, b) and mir += the non-symmetric parts of block (b, a) of the same element.
+template <bool WITH_K, bool WITH_M, bool WITH_D>
+TEFEM_HD void pair_accumulate(BlockAcc<WITH_K, WITH_M, WITH_D>& acc, MirrorAcc<WITH_K, WITH_D>& mir,
+                              const double* __restrict__ rec, int a, int b, const double* __restrict__ S,
+                              const double* __restrict__ NN) {
+    if (WITH_K) {
+        const double ga0 = rec[REC_G + 3 * a], ga1 = rec[REC_G + 3 * a + 1], ga2 = rec[REC_G + 3 * a + 2];
+        const double gb0 = rec[REC_G + 3 * b], gb1 = rec[REC_G + 3 * b + 1], gb2 = rec[REC_G + 3 * b + 2];
+        const double cl = rec[REC_CL], cm = rec[REC_CM];
+        const double dot = ga0 * gb0 + ga1 * gb1 + ga2 * gb2;
+        const double la0 = cl * ga0, la1 = cl * ga1, la2 = cl * ga2;
+        const double ma0 = cm * ga0, ma1 = cm * ga1, ma2 = cm * ga2;
+        const double md = cm * dot;
+        acc.kuu[0] += la0 * gb0 + ma0 * gb0 + md;
+        acc.kuu[1] += la0 * gb1 + ma1 * gb0;
+        acc.kuu[2] += la0 * gb2 + ma2 * gb0;
+        acc.kuu[3] += la1 * gb0 + ma0 * gb1;
+        acc.kuu[4] += la1 * gb1 + ma1 * gb1 + md;
+        acc.kuu[5] += la1 * gb2 + ma2 * gb1;
+        acc.kuu[6] += la2 * gb0 + ma0 * gb2;
+        acc.kuu[7] += la2 * gb1 + ma1 * gb2;
+        acc.kuu[8] += la2 * gb2 + ma2 * gb2 + md;
+        const double cb = rec[REC_CB];
+        const double t = cb * S[a], u = cb * S[b];
+        acc.kut[0] += t * gb0;
+        acc.kut[1] += t * gb1;
+        acc.kut[2] += t * gb2;
+        mir.kut[0] += u * ga0;
+        mir.kut[1] += u * ga1;
+        mir.kut[2] += u * ga2;
+        acc.ktt += rec[REC_CK] * dot;
+    }
+    if (WITH_M) acc.m += rec[REC_RM] * NN[4 * a + b];
+    if (WITH_D) {
+        const double cd = rec[REC_CD];
+        const double t = cd * S[a], u = cd * S[b];
+        acc.dtu[0] += t * rec_gt(rec, 0, b);
+        acc.dtu[1] += t * rec_gt(rec, 1, b);
+        acc.dtu[2] += t * rec_gt(rec, 2, b);
+        mir.dtu[0] += u * rec_gt(rec, 0, a);
+        mir.dtu[1] += u * rec_gt(rec, 1, a);
+        mir.dtu[2] += u * rec_gt(rec, 2, a);
+        acc.dtt += rec[REC_RC] * NN[4 * a + b];
+    }
+}
+
 }  // namespace tefem

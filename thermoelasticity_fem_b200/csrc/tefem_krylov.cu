@@ -285,6 +285,18 @@ __global__ void __launch_bounds__(256) newmark_correct_kernel(int64_t n, double*
     a[k] = nv;
 }
 
+// out = c0 x0 + c1 x1 + c2 x2 (x1 / x2 may be null): extrapolated initial guess for the next time step
+__global__ void __launch_bounds__(256) lincomb3_kernel(int64_t n, double c0, const double* __restrict__ x0, double c1,
+                                                       const double* __restrict__ x1, double c2,
+                                                       const double* __restrict__ x2, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double v = c0 * x0[k];
+    if (x1) v += c1 * x1[k];
+    if (x2) v += c2 * x2[k];
+    out[k] = v;
+}
+
 __global__ void __launch_bounds__(256) load_axpy_kernel(int64_t n, const int32_t* __restrict__ node,
                                                         const double* __restrict__ w, double c0, double c1, double c2,
                                                         double c3, double* __restrict__ F) {
@@ -646,6 +658,15 @@ extern "C" int tefem_load_axpy(int64_t n_entries, const int32_t* node, const dou
     if (n_entries == 0) return TEFEM_OK;
     load_axpy_kernel<<<(unsigned)ceil_div(n_entries, 256), 256, 0, as_stream(stream)>>>(n_entries, node, w, h_coef[0],
                                                                                          h_coef[1], h_coef[2], h_coef[3], F);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_lincomb3(int64_t n, double c0, const double* x0, double c1, const double* x1, double c2,
+                              const double* x2, double* out, void* stream) {
+    TEFEM_REQUIRE(x0 && out, "null pointer");
+    if (n == 0) return TEFEM_OK;
+    lincomb3_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(n, c0, x0, c1, x1, c2, x2, out);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }

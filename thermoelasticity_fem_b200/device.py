@@ -40,11 +40,8 @@ class DeviceMesh:
             schedule = build_schedule(conn_t, self.n_nodes, self.n_rows)
         self.schedule: Schedule = schedule.to(dev)
         del conn_t
-        # per-CTA copies of the staged elements' connectivity / material index (one gather level less in K1)
-        ce = self.schedule.cta_elems.long()
-        self.cta_conn = self.conn[ce].contiguous()
-        self.cta_mat = self.mat_id[ce].contiguous()
-        del ce
+        # per-tile copy of the staged elements' material index (the connectivity copy is part of the schedule)
+        self.cta_mat = self.mat_id[self.schedule.cta_elems.long()].contiguous()
         self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
 
     # ---- K1 -------------------------------------------------------------------------------------
@@ -65,8 +62,8 @@ class DeviceMesh:
         p = _lib.ptr
         _lib.check(self.lib.tefem_assemble(
             p(self.coords), p(self.mat_table), self.n_mat,
-            S.n_cta, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, p(S.cta_ptr), p(S.cta_elems),
-            p(self.cta_conn), p(self.cta_mat), p(S.item_block), p(S.item_inc), p(S.item_meta),
+            S.n_cta, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, S.max_cta_nodes, p(S.cta_ptr), p(S.cta_elems),
+            p(S.cta_conn8), p(self.cta_mat), p(S.cta_nodes), p(S.item_block), p(S.item_blockT), p(S.item_inc), p(S.item_meta),
             p(S.split_block), p(S.split_meta), p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
             p(out.get("M")) if "M" in ops else None, p(out.get("K")) if "K" in ops else None,
             p(out.get("D")) if "D" in ops else None, p(self.bad_elem), _lib.stream_ptr()))
@@ -233,3 +230,31 @@ def newmark_correct(lib, x, v, a, a_new, dt, gamma, beta, dir_mask):
 def load_axpy(lib, node, w, coef, F):
     c = (ctypes.c_double * 4)(*[float(v) for v in coef])
     _lib.check(lib.tefem_load_axpy(node.numel(), _lib.ptr(node), _lib.ptr(w), c, _lib.ptr(F), _lib.stream_ptr()))
+
+
+class GuessExtrapolator:
+    """Initial guess of the next step's solve from the previous accelerations: a_n, then 2 a_n - a_{n-1}, then
+    3 a_n - 3 a_{n-1} + a_{n-2} (the load is smooth in time, so the extrapolation error is O(dt^3) and the Krylov
+    solve starts several decades closer to its tolerance).  The reference has no counterpart (direct solve)."""
+
+    def __init__(self, lib, like, order=2):
+        self.lib, self.order = lib, order
+        self.h1 = torch.zeros_like(like)
+        self.h2 = torch.zeros_like(like)
+        self.n_hist = 0                   # number of valid older states behind `a`
+
+    def guess(self, a, out):
+        p = _lib.ptr
+        k = min(self.order, self.n_hist)
+        if k <= 0:
+            out.copy_(a)
+        elif k == 1:
+            _lib.check(self.lib.tefem_lincomb3(a.numel(), 2.0, p(a), -1.0, p(self.h1), 0.0, None, p(out), _lib.stream_ptr()))
+        else:
+            _lib.check(self.lib.tefem_lincomb3(a.numel(), 3.0, p(a), -3.0, p(self.h1), 1.0, p(self.h2), p(out), _lib.stream_ptr()))
+
+    def push(self, a_old):
+        """Call with a_n BEFORE the corrector overwrites it with a_{n+1}."""
+        self.h1, self.h2 = self.h2, self.h1
+        self.h1.copy_(a_old)
+        self.n_hist = min(self.n_hist + 1, 2)

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, layout
-from .device import DeviceMesh, KrylovSolver, load_axpy, newmark_correct, newmark_predict
+from .device import DeviceMesh, GuessExtrapolator, KrylovSolver, load_axpy, newmark_correct, newmark_predict
 from .materials import LinearThermoElastic
 from .partition import LocalProblem, localize, slab_ranges
 
@@ -169,6 +169,7 @@ class DistributedTransient:
         self._x, self._v, self._a, self._a_new, self._w1, self._w2, self._rhs, self._b = (z() for _ in range(8))
         self._mapD = layout.plane_map_D(self.alpha_M, self.alpha_K)
         self._mapK = layout.plane_map_K()
+        self._guess = GuessExtrapolator(self.lib, self._x, order=0)
         self._lift = None
         if self.has_lift:
             self._lift = z()
@@ -186,7 +187,9 @@ class DistributedTransient:
         dm.planes_spmv(self.planes["D"], self._mapD, self._w1, rhs, alpha=-1.0, beta_y=1.0)
         dm.planes_spmv(self.planes["K"], self._mapK, self._w2, rhs, alpha=-1.0, beta_y=1.0)
         dm.block_jacobi_apply(self.dinv, rhs, self._b, self.dir_mask)
+        self._guess.guess(self._a, self._a_new)
         info = self.krylov.bicgstab(self.sys, self._b, self._a_new, self.rtol, self.max_iter, self.check_every)
+        self._guess.push(self._a)
         # x, v, a are advanced on the halo nodes as well (same arithmetic as on their owner): they need a_new there
         _lib.check(lib.tefem_solver_halo_exchange(self.krylov.handle, _lib.ptr(self._a_new), _lib.stream_ptr()))
         newmark_correct(lib, self._x, self._v, self._a, self._a_new, self.dt, self.gamma, self.beta, self.dir_mask)

@@ -89,34 +89,29 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * Replaces Model.assemble_M / assemble_K / assemble_D, model.py:87-118 (the per-element
  * compute_mat_*_e calls, the np.ix_ scatter into the dense matrix and csc_array(dense)).
  *
- * Owner-computes schedule built once per mesh by the symbolic phase (host side, symbolic.py):
- *   a CTA tile owns a contiguous range of node rows;
- *   cta_ptr[c][12] = {item0, item1, elem0, elem1, inc0, inc1, split0, split1, node0, node1, 0, 0};
- *   it first stages, in shared memory, the coordinates of the nodes cta_nodes[node0 .. node1), then the geometry
- *   of the elements cta_elems[elem0 .. elem1) - connectivity from cta_conn8 (4 tile-local node numbers, one byte
- *   each), material index from cta_mat - and the incidence entries inc[inc0 .. inc1);
- *   only DIAGONAL and UPPER (row < column) blocks carry incidence lists: a WORK ITEM k in [item0, item1) is
- *     - an upper block p = item_block[k] (item_meta bit 24 set): its thread sums the contributions
- *       inc[item_inc[k] .. + (item_meta[k] & 0xff)) IN ASCENDING ELEMENT ORDER (the order of the reference's loop,
- *       model.py:89,96,107) and also produces the mirror block item_blockT[k] = (column, row) from the same
- *       elements with (a, b) swapped (Kuu, Ktt, Muu, Dtt are transposes / equal; Kut, Dtu are accumulated
- *       separately); item_blockT = -1 when the mirror row is not owned;
- *     - or one chunk of a diagonal block whose list is longer than the chunk limit; ((item_meta[k] >> 8) & 0xffff) - 1
- *       is the shared-memory slot of the chunk's partial sums (-1: unsplit, written directly);
- *   an entry of inc packs (tile-local element << 4) | (a << 2) | b with a, b the local node numbers of (row, column);
- *   split block j in [split0, split1): block split_block[j], partial slots (split_meta[j] & 0xffff) ..
- *   + (split_meta[j] >> 16), added in chunk order by one thread;
- *   max_cta_elems / max_cta_inc / max_cta_slots / max_cta_nodes size the shared memory; inc must be 16-byte
- *   aligned and readable 8 entries past its end.
+ * Owner-computes TILE schedule built once per mesh by the symbolic phase (host side, symbolic.py): a tile owns a
+ * contiguous range of node rows and everything it needs lives in per-tile segments that start on 16-byte
+ * boundaries, so that the persistent kernel can prefetch its next tile with TMA bulk copies while it computes:
+ *   cta_hdr[c][12] = {n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes, 0, 0};
+ *   cta_xyz[o_nodes ..][3]     coordinates of the tile's nodes (copy of coords[cta_nodes]);
+ *   cta_conn8 / cta_mat / cta_elems [o_elems ..]   staged elements: 4 tile-local node numbers (one byte each),
+ *                              material index, element number (error reporting);
+ *   inc[o_inc ..]              incidence entries (tile-local element << 4) | (a << 2) | b, a, b = local node numbers
+ *                              of (row, column), block after block, ASCENDING ELEMENT inside a block (the order of
+ *                              the reference's loop, model.py:89,96,107);
+ *   item_block / item_inc / item_meta [o_items ..]   work items: one block p, or one chunk of a block whose list is
+ *                              long (diagonal blocks); the thread sums inc[item_inc .. + (item_meta & 0xff)) (tile-
+ *                              relative) and either writes the block or, when (item_meta >> 8) - 1 >= 0, parks the
+ *                              partial sums in that shared-memory slot;
+ *   split_block / split_meta [o_split ..]   split blocks: block, first slot | n_chunks << 16 (added in chunk order);
+ *   h_max[6] = largest n_items, n_elems, n_inc, partial slots, n_split, n_nodes of a tile (shared-memory sizes).
  *   Every output value is written exactly once: no atomics, bitwise reproducible.
  * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
  * The D layout follows alpha_M / alpha_K (model.py:112-117).
  * bad_elem[2] as above; the call itself does not synchronise - use tefem_check_jacobian().      */
-int tefem_assemble(const double* coords, const double* mat_table, int n_mat,
-                   int32_t n_cta, int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots, int32_t max_cta_nodes,
-                   const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
-                   const int32_t* cta_nodes, const int32_t* item_block, const int32_t* item_blockT,
-                   const uint32_t* item_inc, const int32_t* item_meta,
+int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
+                   const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
+                   const double* cta_xyz, const int32_t* item_block, const int32_t* item_inc, const int32_t* item_meta,
                    const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
                    int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                    double* vals_M, double* vals_K, double* vals_D,

@@ -53,16 +53,17 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     nD = layout.n_planes(layout.plane_map_D(aM, aK))
     vM, vK, vD = np.full((3, P), np.nan), np.full((13, P), np.nan), np.full((nD, P), np.nan)
     bad = np.full(2, 2 ** 31 - 1, dtype=np.int32)
-    a = {k: getattr(S, k).numpy() for k in ("cta_ptr", "cta_elems", "cta_conn8", "cta_nodes", "item_block", "item_blockT",
-                                            "item_inc", "item_meta", "split_block", "split_meta", "inc")}
-    cta_mat = np.ascontiguousarray(mat_id.astype(np.int32)[a["cta_elems"]])
+    a = {k: getattr(S, k).numpy() for k in ("cta_hdr", "cta_elems", "cta_conn8", "cta_nodes", "item_block", "item_inc",
+                                            "item_meta", "split_block", "split_meta", "inc")}
+    cta_mat = np.ascontiguousarray(mat_id.astype(np.int32)[np.maximum(a["cta_elems"], 0)])
+    cta_xyz = np.ascontiguousarray(pts[a["cta_nodes"]])
+    h_max = np.array([S.max_cta_items, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, S.max_cta_split, S.max_cta_nodes],
+                     dtype=np.int32)
     mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
-    rc = emu.tefem_emu_assemble(ptr(pts), ptr(rows), ctypes.c_int32(S.n_cta), ctypes.c_int32(S.max_cta_elems),
-                                ctypes.c_int32(S.max_cta_inc), ctypes.c_int32(S.max_cta_slots), ctypes.c_int32(S.max_cta_nodes),
-                                ptr(a["cta_ptr"]), ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_mat), ptr(a["cta_nodes"]),
-                                ptr(a["item_block"]), ptr(a["item_blockT"]), ptr(a["item_inc"]),
-                                ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]),
-                                ptr(a["inc"]), ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
+    rc = emu.tefem_emu_assemble(ptr(rows), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]), ptr(a["cta_elems"]),
+                                ptr(a["cta_conn8"]), ptr(cta_mat), ptr(cta_xyz), ptr(a["item_block"]), ptr(a["item_inc"]),
+                                ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]), ptr(a["inc"]),
+                                ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
                                 ptr(vM), ptr(vK), ptr(vD), ptr(bad))
     assert rc == 0
     for nm, v in (("M", vM), ("K", vK), ("D", vD)):
@@ -79,73 +80,59 @@ def check_schedule_invariants(S, conn, n_nodes, max_chunk=6):
         cols = colidx[rowptr[i]:rowptr[i + 1]]
         assert np.all(np.diff(cols) > 0)
         assert colidx[S.diag_idx.numpy()[i]] == i
-    incp = S.inc_ptr.numpy().astype(np.int64)
-    lb = S.listed_block.numpy()
-    assert np.array_equal(lb, np.nonzero(colidx >= br)[0])               # diagonal + upper blocks carry the lists
-    cp = S.cta_ptr.numpy()
-    ib, ibT, ii, im = S.item_block.numpy(), S.item_blockT.numpy(), S.item_inc.numpy().astype(np.int64), S.item_meta.numpy()
+    H = S.cta_hdr.numpy().astype(np.int64)
+    binc, blen = S.block_inc.numpy().astype(np.int64), S.block_len.numpy().astype(np.int64)
+    ib, ii, im = S.item_block.numpy(), S.item_inc.numpy().astype(np.int64), S.item_meta.numpy()
     sb, sm = S.split_block.numpy(), S.split_meta.numpy()
-    assert cp[0, 0] == 0 and cp[-1, 1] == S.n_items and np.array_equal(cp[1:, 0], cp[:-1, 1])
-    assert np.array_equal(cp[1:, 4], cp[:-1, 5]) and cp[-1, 5] == incp[-1]
-    ilen = im & 0xff
-    upper = (im >> 24) & 1
-    assert ilen.min() >= 1 and ilen[upper == 0].max() <= max_chunk
-    assert np.array_equal(upper == 1, colidx[ib] > br[ib])
-    # mirrors: block (j, i) of an upper block (i, j), or -1 when row j is not owned; every lower block is produced once
-    has = ibT >= 0
-    assert np.all(upper[has] == 1) and np.array_equal(br[ibT[has]], colidx[ib[has]]) and np.array_equal(colidx[ibT[has]], br[ib[has]])
-    assert np.all(colidx[ib[(upper == 1) & ~has]] >= S.n_rows)
-    assert np.array_equal(np.sort(ibT[has]), np.nonzero(colidx < br)[0])
-    # the chunks of every listed block tile its incidence list exactly, in order
-    pos_of_block = np.full(S.n_blocks, -1)
-    pos_of_block[lb] = np.arange(lb.size)
-    order = np.lexsort((ii, ib))
-    b_sorted, s_sorted, l_sorted = ib[order], ii[order], ilen[order]
-    first = np.r_[True, b_sorted[1:] != b_sorted[:-1]]
-    assert np.array_equal(s_sorted[first], incp[pos_of_block[b_sorted[first]]])
-    assert np.array_equal((s_sorted + l_sorted)[~np.r_[first[1:], True]], s_sorted[~first])
-    last = np.r_[first[1:], True]
-    assert np.array_equal((s_sorted + l_sorted)[last], incp[pos_of_block[b_sorted[last]] + 1])
-    assert np.array_equal(np.unique(ib), lb)
+    inc = S.inc.numpy().astype(np.int64) & 0xFFFF
     cn8 = S.cta_conn8.numpy().astype(np.int64) & 0xFFFFFFFF
     ce, cnodes = S.cta_elems.numpy(), S.cta_nodes.numpy()
+    assert H[:, 0].sum() == S.n_items and blen.sum() == (16 * E if S.n_rows == n_nodes else blen.sum())
+    seen_blocks = []
     for c in range(S.n_cta):
-        i0, i1, e0, e1, n0, n1, s0, s1, k0, k1 = cp[c, :10]
-        assert e1 - e0 <= S.max_cta_elems and n1 - n0 <= S.max_cta_inc and k1 - k0 <= S.max_cta_nodes <= 256
-        assert np.all(ii[i0:i1] >= n0) and np.all(ii[i0:i1] + ilen[i0:i1] <= n1)
-        slots = ((im[i0:i1] >> 8) & 0xffff) - 1
+        n_it, n_el, n_inc, n_sp, n_nd, o_it, o_el, o_inc, o_sp, o_nd = H[c, :10]
+        # 16-byte aligned segment starts, sizes within the declared maxima
+        assert o_it % 4 == 0 and o_el % 4 == 0 and o_inc % 8 == 0 and o_sp % 4 == 0 and o_nd % 2 == 0
+        assert n_it <= S.max_cta_items and n_el <= S.max_cta_elems and n_inc <= S.max_cta_inc
+        assert n_sp <= S.max_cta_split and n_nd <= S.max_cta_nodes <= 256
+        blk, start, meta = ib[o_it:o_it + n_it], ii[o_it:o_it + n_it], im[o_it:o_it + n_it]
+        ilen = meta & 0xff
+        slots = (meta >> 8) - 1
+        assert ilen.min() >= 1 and np.all(np.diff(ilen) <= 0)             # longest first
+        assert np.all(start >= 0) and np.all(start + ilen <= n_inc)
+        assert np.all(ilen[slots >= 0] <= max_chunk) and np.all(ilen[slots < 0] <= 2 * max_chunk)
         used = np.sort(slots[slots >= 0])
         assert np.array_equal(used, np.arange(used.size)) and used.size <= S.max_cta_slots
+        # the chunks of every block tile its incidence list exactly, in order
+        order = np.lexsort((start, blk))
+        b_s, s_s, l_s = blk[order], start[order], ilen[order]
+        first = np.r_[True, b_s[1:] != b_s[:-1]]
+        last = np.r_[first[1:], True]
+        assert np.array_equal(s_s[first] + o_inc, binc[b_s[first]])
+        assert np.array_equal((s_s + l_s)[~last], s_s[~first])
+        assert np.array_equal((s_s + l_s)[last] + o_inc, binc[b_s[last]] + blen[b_s[last]])
+        seen_blocks.append(np.unique(blk))
         tot = 0
-        for k in range(s0, s1):
+        for k in range(o_sp, o_sp + n_sp):
             slot0, n = sm[k] & 0xffff, sm[k] >> 16
-            sel = (ib[i0:i1] == sb[k])
+            sel = blk == sb[k]
             assert n >= 2 and sel.sum() == n
-            ss = slots[sel][np.argsort(ii[i0:i1][sel])]
-            assert np.array_equal(ss, np.arange(slot0, slot0 + n))      # chunk order = slot order
+            assert np.array_equal(slots[sel][np.argsort(start[sel])], np.arange(slot0, slot0 + n))   # chunk order = slot order
             tot += n
         assert tot == used.size
         # byte connectivity decodes to the global connectivity through the tile's node list
-        loc = np.stack([(cn8[e0:e1] >> (8 * a)) & 0xff for a in range(4)], axis=1)
-        assert loc.max() < k1 - k0 and np.array_equal(cnodes[k0:k1][loc], conn[ce[e0:e1]])
-    assert S.inc.numel() == incp[-1] + 8
-    # every incidence entry decodes to an element of the tile's list that really contains (row, col)
-    inc = S.inc.numpy().astype(np.int64) & 0xFFFF
-    l_ptr = np.searchsorted(incp, cp[:, 4])                            # first listed block of each tile
-    cta_of_listed = np.searchsorted(l_ptr, np.arange(lb.size), side="right") - 1
-    rng = np.random.default_rng(0)
-    for q in rng.integers(0, lb.size, size=400):
-        p, c = lb[q], cta_of_listed[q]
-        last_e = -1
-        for k in range(incp[q], incp[q + 1]):
-            w = inc[k]
-            e = ce[cp[c, 2] + (w >> 4)]
-            a, b = (w >> 2) & 3, w & 3
-            assert conn[e, a] == br[p] and conn[e, b] == colidx[p]
-            assert e > last_e                            # ascending element order = the reference's summation order
-            last_e = e
-    if S.n_rows == n_nodes:
-        assert incp[-1] == 10 * E                        # 4 diagonal + 6 upper incidences per element
+        loc = np.stack([(cn8[o_el:o_el + n_el] >> (8 * a)) & 0xff for a in range(4)], axis=1)
+        assert loc.max() < n_nd and np.array_equal(cnodes[o_nd:o_nd + n_nd][loc], conn[ce[o_el:o_el + n_el]])
+        # incidence entries decode to elements of the tile that really contain (row, col), ascending element
+        for p in np.unique(blk)[:: max(1, len(np.unique(blk)) // 6)]:
+            last_e = -1
+            for k in range(binc[p], binc[p] + blen[p]):
+                w = inc[k]
+                e = ce[o_el + (w >> 4)]
+                assert conn[e, (w >> 2) & 3] == br[p] and conn[e, w & 3] == colidx[p]
+                assert e > last_e                        # = the reference's summation order
+                last_e = e
+    assert np.array_equal(np.concatenate(seen_blocks), np.arange(S.n_blocks))       # tiles own contiguous block ranges
 
 
 @pytest.mark.parametrize("aM,aK", [(0.2, 0.2), (0.3, 0.0), (0.0, 0.0)])
@@ -186,7 +173,7 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
     mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
             3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
     conn, mat_id, rows = orc.element_table(tets, mats)
-    for items in (256, 64):                       # small tiles: many CTAs, exercises the staging offsets
+    for items in (256, 64):                       # small tiles: many CTAs, exercises the segment offsets
         chunk = 6 if items == 256 else 3
         S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items),
                            max_chunk=chunk)
@@ -218,10 +205,7 @@ def test_row_restricted_schedule_matches_global_rows():
     nb = int(full.rowptr[R])
     assert part.n_blocks == nb and part.n_rows == R
     assert torch.equal(part.rowptr, full.rowptr[:R + 1]) and torch.equal(part.colidx, full.colidx[:nb])
-    nl = int((full.listed_block < nb).sum())
-    assert torch.equal(part.listed_block, full.listed_block[:nl]) and torch.equal(part.inc_ptr, full.inc_ptr[:nl + 1])
-    # mirrors whose row is not owned are dropped, the others are identical
-    assert torch.equal(part.rowptr, full.rowptr[:R + 1])
+    assert torch.equal(part.block_len, full.block_len[:nb])
 
 
 def test_emulated_element_matrices_match_oracle(emu):

@@ -4,19 +4,23 @@
 // Element.compute_mat_*_e (elements.py:220-286), the np.ix_ scatter into a dense n_dofs^2 array
 // and csc_array(dense).  Design (DESIGN.md "K1"):
 //
-//   * the symbolic phase groups node rows into CTA tiles; a CTA first stages, in shared memory, the
-//     geometry record (inverse Jacobian columns = shape-function gradients, det, material-scaled
-//     weights) of every element that touches one of its rows (phase 1: coalesced int4 loads of the
-//     tile's connectivity copy, gathers of node coordinates through L2) and, with 16-byte loads, the
-//     tile's contiguous range of incidence entries;
-//   * then one thread per WORK ITEM - a node-pair block, or a chunk of <= max_chunk incidences of a
-//     block with a long incidence list (the diagonal blocks) - walks its precomputed incidence
-//     entries (element, a, b) in ascending element order - the slot map - and accumulates the block's
-//     13 (K) / 1 (M) / 4 (D) values in registers (phase 2).  Unsplit blocks are written straight to
-//     the structure-of-arrays planes; chunks park their partial sums in shared memory and one thread
-//     per split block adds them in chunk order (phase 3).  Every output value is written exactly
-//     once: no atomics, bitwise reproducible, summation in the reference's element order (chunked
-//     for the split blocks).
+//   * the symbolic phase groups node rows into TILES and stores everything a tile needs in per-tile
+//     segments (16-byte aligned): node coordinates, byte-packed tile-local connectivity, material
+//     index, incidence entries (the slot map), work items, split lists;
+//   * the kernel is PERSISTENT (grid = CTAs that fit on the 148 SMs): while a CTA computes tile t it
+//     prefetches the segments of its next tile into the other half of a double buffer with TMA bulk
+//     copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier, so no global-memory latency sits
+//     on the critical path of a tile (v1-v3 were latency bound: 3.4 warps per scheduler, 81 % of the
+//     cycles without an eligible warp, profiles/README.md);
+//   * per tile: phase 1 builds the geometry record (inverse Jacobian columns = shape-function
+//     gradients, det, material-scaled weights) of every staged element in shared memory; phase 2: one
+//     thread per WORK ITEM - a node-pair block, or a chunk of a block with a long incidence list (the
+//     diagonal blocks) - walks its incidence entries (element, a, b) in ascending element order and
+//     accumulates the block's 13 (K) / 1 (M) / 4 (D) values in registers; unsplit blocks are written
+//     straight to the structure-of-arrays planes, chunks park partial sums in shared memory and one
+//     thread per split block adds them in chunk order (phase 3).  Every output value is written
+//     exactly once: no atomics, bitwise reproducible, summation in the reference's element order
+//     (chunked for the split blocks).
 //
 // The same per-thread routines are compiled for the host when TEFEM_HOST_EMU is defined; that
 // build is used only by tests/host_emulation to check the schedule logic in a GPU-less container
@@ -29,22 +33,22 @@
 namespace tefem {
 
 struct AssembleArgs {
-    const double* coords;
+    const double* coords;      // element_matrices path only
     const int32_t* conn;       // element_matrices path only
     const int32_t* mat_id;     // element_matrices path only
     const double* mat_table;
-    const int32_t* cta_ptr;    // [n_cta, 12]: item0, item1, elem0, elem1, inc0, inc1, split0, split1, node0, node1, -, -
+    const int32_t* cta_hdr;    // [n_cta, 12]: n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes
     const int32_t* cta_elems;  // staged element numbers (error reporting only)
-    const int32_t* cta_conn8;  // [n_staged] connectivity of the staged elements as 4 tile-local node bytes
-    const int32_t* cta_mat;    // [n_staged] material index of the staged elements
-    const int32_t* cta_nodes;  // [n_tile_nodes] nodes whose coordinates the tile stages
-    const int32_t* item_block; // [n_items] block p of the work item
-    const int32_t* item_blockT;  // [n_items] mirror block (j, i) of an upper block (i, j), or -1
-    const uint32_t* item_inc;  // [n_items] first incidence entry of the work item (absolute index into inc)
-    const int32_t* item_meta;  // [n_items] length | (partial slot + 1) << 8 | upper << 24  (slot + 1 == 0: unsplit)
-    const int32_t* split_block;  // [n_split] block p of a split block
-    const int32_t* split_meta;   // [n_split] first partial slot | n_chunks << 16
+    const int32_t* cta_conn8;  // connectivity of the staged elements as 4 tile-local node bytes
+    const int32_t* cta_mat;    // material index of the staged elements
+    const double* cta_xyz;     // coordinates of the tile's nodes, [.., 3]
+    const int32_t* item_block; // block p of the work item
+    const int32_t* item_inc;   // first incidence entry of the work item (relative to the tile's segment)
+    const int32_t* item_meta;  // length | (partial slot + 1) << 8   (slot + 1 == 0: unsplit block)
+    const int32_t* split_block;  // block p of a split block
+    const int32_t* split_meta;   // first partial slot | n_chunks << 16
     const uint16_t* inc;
+    int32_t n_cta;
     int64_t n_blocks;
     double alpha_M, alpha_K;
     double* vals_M;
@@ -53,9 +57,7 @@ struct AssembleArgs {
     int32_t* bad_elem;
 };
 
-enum { CTA_ITEM0 = 0, CTA_ITEM1, CTA_ELEM0, CTA_ELEM1, CTA_INC0, CTA_INC1, CTA_SPLIT0, CTA_SPLIT1, CTA_NODE0, CTA_NODE1,
-       CTA_STRIDE = 12 };
-enum { ITEM_UPPER = 1 << 24 };
+enum { H_NITEMS = 0, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, HDR_STRIDE = 12 };
 
 // ---- per-thread routines (host + device) -------------------------------------------------------
 
@@ -70,10 +72,10 @@ TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double W4, doubl
 
 // Phase 1 from the tile's staged node coordinates xyz[tile-local node][3] and the byte-packed tile-local
 // connectivity (no gather from global memory per element).
-TEFEM_HD double stage_element_local(const AssembleArgs& A, const double* xyz, uint32_t conn8, int32_t mat_idx, double W4,
+TEFEM_HD double stage_element_local(const double* mat_table, const double* xyz, uint32_t conn8, int32_t mat_idx, double W4,
                                     double* rec) {
     return element_record(xyz + 3 * (conn8 & 0xff), xyz + 3 * ((conn8 >> 8) & 0xff), xyz + 3 * ((conn8 >> 16) & 0xff),
-                          xyz + 3 * (conn8 >> 24), A.mat_table + MAT_STRIDE * mat_idx, W4, rec);
+                          xyz + 3 * (conn8 >> 24), mat_table + MAT_STRIDE * mat_idx, W4, rec);
 }
 
 template <int OPS, int DUU>
@@ -83,17 +85,6 @@ struct AsmTraits {
     static constexpr bool NEED_M = WANT_M || (WANT_D && DUU >= 1);
     typedef BlockAcc<NEED_K, NEED_M, WANT_D> Acc;
 };
-
-// Phase 2: acc = sum over the incidence entries inc[s .. t) (ascending element order).
-template <int OPS, int DUU>
-TEFEM_HD void accumulate_list(typename AsmTraits<OPS, DUU>::Acc& acc, const double* recs, const uint16_t* inc,
-                              uint32_t s, uint32_t t, const double* S, const double* NN) {
-    typedef AsmTraits<OPS, DUU> T;
-    for (uint32_t k = s; k < t; ++k) {
-        const uint32_t w = inc[k];
-        block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
-    }
-}
 
 // Write the planes of block p.  DUU: 0 = D has no uu part, 1 = alpha_M only (3 diagonal planes),
 // 2 = alpha_K != 0 (9 planes); model.py:112-117.
@@ -134,42 +125,22 @@ TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTr
     }
 }
 
-// One work item.  Upper block (i, j): accumulate it together with the non-symmetric parts of its mirror (j, i)
-// and write both.  Diagonal chunk: accumulate, then write the block or park the partial sums.
+// One work item: acc = sum over the incidence entries inc[s .. s + len) (ascending element order), then either
+// write the block or park the partial sums of a chunk.
 template <int OPS, int DUU>
-TEFEM_HD void process_item(const AssembleArgs& A, int32_t p, int32_t pT, uint32_t s, int32_t meta, const double* recs,
+TEFEM_HD void process_item(const AssembleArgs& A, int32_t p, uint32_t s, int32_t meta, const double* recs,
                            const uint16_t* inc_s, double* partials, const double* S, const double* NN) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Acc acc;
     acc.clear();
     const uint32_t t = s + (uint32_t)(meta & 0xff);
-    if (meta & ITEM_UPPER) {
-        MirrorAcc<T::NEED_K, T::WANT_D> mir;
-        mir.clear();
-        for (uint32_t k = s; k < t; ++k) {
-            const uint32_t w = inc_s[k];
-            pair_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(acc, mir, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3,
-                                                             w & 3, S, NN);
-        }
-        store_block<OPS, DUU>(A, p, acc);
-        if (pT >= 0) {
-            if (T::NEED_K) {   // Kuu_ji = Kuu_ij^T ; Kut_ji from the mirror accumulators
-                double tmp;
-                tmp = acc.kuu[1]; acc.kuu[1] = acc.kuu[3]; acc.kuu[3] = tmp;
-                tmp = acc.kuu[2]; acc.kuu[2] = acc.kuu[6]; acc.kuu[6] = tmp;
-                tmp = acc.kuu[5]; acc.kuu[5] = acc.kuu[7]; acc.kuu[7] = tmp;
-                for (int i = 0; i < 3; ++i) acc.kut[i] = mir.kut[i];
-            }
-            if (T::WANT_D)
-                for (int i = 0; i < 3; ++i) acc.dtu[i] = mir.dtu[i];
-            store_block<OPS, DUU>(A, pT, acc);
-        }
-    } else {
-        accumulate_list<OPS, DUU>(acc, recs, inc_s, s, t, S, NN);
-        const int slot = ((meta >> 8) & 0xffff) - 1;
-        if (slot < 0) store_block<OPS, DUU>(A, p, acc);
-        else acc.dump(partials + (size_t)slot * T::Acc::LIVE);
+    for (uint32_t k = s; k < t; ++k) {
+        const uint32_t w = inc_s[k];
+        block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
     }
+    const int slot = (meta >> 8) - 1;
+    if (slot < 0) store_block<OPS, DUU>(A, p, acc);
+    else acc.dump(partials + (size_t)slot * T::Acc::LIVE);
 }
 
 // Phase 3 for one split block: add the chunk partials in chunk order and write the block.
@@ -247,18 +218,9 @@ const QuadTables& quad_tables() {
     return q;
 }
 
-static void fill_args(AssembleArgs& A, const double* coords, const double* mat_table, const int32_t* cta_ptr,
-                      const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat, const int32_t* cta_nodes,
-                      const int32_t* item_block, const int32_t* item_blockT, const uint32_t* item_inc, const int32_t* item_meta,
-                      const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
-                      double alpha_M, double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
-    A.coords = coords; A.conn = nullptr; A.mat_id = nullptr; A.mat_table = mat_table;
-    A.cta_ptr = cta_ptr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_mat = cta_mat; A.cta_nodes = cta_nodes;
-    A.item_block = item_block; A.item_blockT = item_blockT; A.item_inc = item_inc; A.item_meta = item_meta;
-    A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
-    A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
-    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
-}
+struct TileDims {
+    int n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes;
+};
 
 }  // namespace tefem
 
@@ -295,79 +257,158 @@ static int upload_quad() {
 
 constexpr int ASM_THREADS = 256;
 
-// Shared memory: [element records: rec_doubles][partial sums: part_doubles][node coordinates: xyz_doubles]
-// [incidence entries (uint16)].
-// A tile's incidence entries are one contiguous range of `inc`: they are copied with 16-byte loads while phase 0
-// waits on the coordinates, and the phase-2 loop reads them from shared memory instead of chasing a global load
-// per iteration (profiles/README.md: 19 % of all stall samples sat on that load in v1).  Node coordinates are
-// staged once per tile (coalesced for consecutive node numbers) instead of 12 scattered 8-byte gathers per element.
+// ---- TMA bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ inline uint32_t up16(uint32_t bytes) { return (bytes + 15u) & ~15u; }
+
+// Shared-memory layout of one prefetch stage (byte offsets, all multiples of 16).
+struct StageLayout {
+    uint32_t hdr, xyz, conn8, mat, it_block, it_inc, it_meta, sp_block, sp_meta, inc, bytes;
+};
+__host__ __device__ inline StageLayout stage_layout(int max_items, int max_elems, int max_inc, int max_split, int max_nodes) {
+    StageLayout L;
+    uint32_t o = 0;
+    L.hdr = o; o += 64;
+    L.xyz = o; o += up16(24u * (uint32_t)((max_nodes + 1) & ~1));
+    L.conn8 = o; o += up16(4u * (uint32_t)(max_elems + 3));
+    L.mat = o; o += up16(4u * (uint32_t)(max_elems + 3));
+    L.it_block = o; o += up16(4u * (uint32_t)(max_items + 3));
+    L.it_inc = o; o += up16(4u * (uint32_t)(max_items + 3));
+    L.it_meta = o; o += up16(4u * (uint32_t)(max_items + 3));
+    L.sp_block = o; o += up16(4u * (uint32_t)(max_split + 3));
+    L.sp_meta = o; o += up16(4u * (uint32_t)(max_split + 3));
+    L.inc = o; o += up16(2u * (uint32_t)(max_inc + 7));
+    L.bytes = o;
+    return L;
+}
+
+// Thread 0: issue the bulk copies of tile `t`, whose header (h0, h1, h2) was loaded one iteration earlier, into
+// stage buffer `st` (completing on `bar`).
+__device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, const int4& h0, const int4& h1, const int4& h2,
+                                              char* st, const StageLayout& L, uint64_t* bar) {
+    const int4* hg = reinterpret_cast<const int4*>(A.cta_hdr) + 3 * (size_t)t;
+    const int n_items = h0.x, n_elems = h0.y, n_inc = h0.z, n_split = h0.w, n_nodes = h1.x;
+    const int o_items = h1.y, o_elems = h1.z, o_inc = h1.w, o_split = h2.x, o_nodes = h2.y;
+    const uint32_t b_items = up16(4u * n_items), b_elems = up16(4u * n_elems), b_inc = up16(2u * n_inc);
+    const uint32_t b_split = up16(4u * n_split), b_xyz = up16(24u * n_nodes);
+    const uint32_t total = 48u + b_xyz + 2u * b_elems + 3u * b_items + 2u * b_split + b_inc;
+    mbar_expect_tx(bar, total);
+    bulk_g2s(st + L.hdr, hg, 48u, bar);
+    if (b_xyz) bulk_g2s(st + L.xyz, A.cta_xyz + 3 * (size_t)o_nodes, b_xyz, bar);
+    if (b_elems) {
+        bulk_g2s(st + L.conn8, A.cta_conn8 + o_elems, b_elems, bar);
+        bulk_g2s(st + L.mat, A.cta_mat + o_elems, b_elems, bar);
+    }
+    if (b_items) {
+        bulk_g2s(st + L.it_block, A.item_block + o_items, b_items, bar);
+        bulk_g2s(st + L.it_inc, A.item_inc + o_items, b_items, bar);
+        bulk_g2s(st + L.it_meta, A.item_meta + o_items, b_items, bar);
+    }
+    if (b_split) {
+        bulk_g2s(st + L.sp_block, A.split_block + o_split, b_split, bar);
+        bulk_g2s(st + L.sp_meta, A.split_meta + o_split, b_split, bar);
+    }
+    if (b_inc) bulk_g2s(st + L.inc, A.inc + o_inc, b_inc, bar);
+}
+
+// Shared memory: [element records][partial sums][stage 0][stage 1][2 mbarriers].
 template <int OPS, int DUU>
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, int rec_doubles, int part_doubles,
-                                                                  int xyz_doubles) {
-    extern __shared__ double recs[];
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
+                                                                  int part_doubles) {
+    extern __shared__ __align__(128) double smem[];
+    double* recs = smem;
     double* partials = recs + rec_doubles;
-    double* xyz = partials + part_doubles;
-    uint16_t* inc_s = reinterpret_cast<uint16_t*>(xyz + xyz_doubles);
-    const int4* hdr = reinterpret_cast<const int4*>(A.cta_ptr) + 3 * blockIdx.x;
-    const int4 c0 = __ldg(hdr), c1 = __ldg(hdr + 1), c2 = __ldg(hdr + 2);
-    const int i0 = c0.x, i1 = c0.y, e0 = c0.z, ne = c0.w - c0.z;
-    const uint32_t inc_lo = (uint32_t)c1.x, inc_hi = (uint32_t)c1.y;
-    const int sp0 = c1.z, sp1 = c1.w;
-    const int n0 = c2.x, nn = c2.y - c2.x;
-    // phase 0: node coordinates -> shared memory
-    for (int k = threadIdx.x; k < nn; k += ASM_THREADS) {
-        const double* X = A.coords + 3 * (int64_t)__ldg(A.cta_nodes + n0 + k);
-        xyz[3 * k] = X[0]; xyz[3 * k + 1] = X[1]; xyz[3 * k + 2] = X[2];
-    }
-    // first work item of this thread: issue its index loads now, they are consumed after the barriers
-    const int it0 = i0 + threadIdx.x;
-    int32_t p0 = 0, pT0 = -1, m0 = 0;
-    uint32_t s0 = 0;
-    if (it0 < i1) {
-        p0 = __ldg(A.item_block + it0);
-        pT0 = __ldg(A.item_blockT + it0);
-        s0 = __ldg(A.item_inc + it0);
-        m0 = __ldg(A.item_meta + it0);
-    }
-    // incidence entries [inc_lo, inc_hi) -> shared memory, from the 16-byte aligned address below inc_lo
-    const uint32_t base = inc_lo & ~7u;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(A.inc + base);
-        uint4* dst = reinterpret_cast<uint4*>(inc_s);
-        const uint32_t n16 = (inc_hi - base + 7u) >> 3;
-        for (uint32_t k = threadIdx.x; k < n16; k += ASM_THREADS) dst[k] = __ldg(src + k);
-    }
-    // connectivity / material of this thread's first staged element (consumed after the barrier)
-    uint32_t cn0 = 0;
-    int32_t mt0 = 0;
-    if ((int)threadIdx.x < ne) {
-        cn0 = (uint32_t)__ldg(A.cta_conn8 + e0 + threadIdx.x);
-        mt0 = __ldg(A.cta_mat + e0 + threadIdx.x);
+    const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
+    char* stage0 = reinterpret_cast<char*>(partials + part_doubles);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
+    const int G = gridDim.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_proxy_async();
     }
     __syncthreads();
-    // phase 1: geometry records of the staged elements
-    const double W4 = c_quad.W4;
-    for (int le = threadIdx.x; le < ne; le += ASM_THREADS) {
-        const uint32_t cn = (le == (int)threadIdx.x) ? cn0 : (uint32_t)__ldg(A.cta_conn8 + e0 + le);
-        const int32_t m = (le == (int)threadIdx.x) ? mt0 : __ldg(A.cta_mat + e0 + le);
-        const double det = stage_element_local(A, xyz, cn, m, W4, recs + (size_t)le * REC_STRIDE);
-        if (!(det > 0.0)) {  // error path only: elements.py:207-210
-            const int32_t e = A.cta_elems[e0 + le];
-            if (det < 0.0) atomicMin(A.bad_elem, e);
-            else atomicMin(A.bad_elem + 1, e);
+    // thread 0 keeps the header of the next tile to prefetch in registers, loaded one iteration ahead
+    const int4* hdr_g = reinterpret_cast<const int4*>(A.cta_hdr);
+    int4 nh0 = make_int4(0, 0, 0, 0), nh1 = nh0, nh2 = nh0;
+    if (threadIdx.x == 0 && (int)blockIdx.x < A.n_cta) {
+        const int4* hg = hdr_g + 3 * (size_t)blockIdx.x;
+        prefetch_tile(A, blockIdx.x, __ldg(hg), __ldg(hg + 1), __ldg(hg + 2), stage0, L, &bars[0]);
+        if ((int)blockIdx.x + G < A.n_cta) {
+            const int4* hn = hdr_g + 3 * (size_t)(blockIdx.x + G);
+            nh0 = __ldg(hn); nh1 = __ldg(hn + 1); nh2 = __ldg(hn + 2);
         }
     }
-    __syncthreads();
-    // phase 2: work items
-    if (it0 < i1) process_item<OPS, DUU>(A, p0, pT0, s0 - base, m0, recs, inc_s, partials, c_quad.S, c_quad.NN);
-    for (int it = it0 + ASM_THREADS; it < i1; it += ASM_THREADS)
-        process_item<OPS, DUU>(A, __ldg(A.item_block + it), __ldg(A.item_blockT + it), __ldg(A.item_inc + it) - base,
-                               __ldg(A.item_meta + it), recs, inc_s, partials, c_quad.S, c_quad.NN);
-    // phase 3: split (diagonal) blocks
-    if (sp1 > sp0) {   // uniform over the CTA
+    const double W4 = c_quad.W4;
+    int k = 0;
+    for (int t = blockIdx.x; t < A.n_cta; t += G, ++k) {
+        const int s = k & 1;
+        char* st = stage0 + (size_t)s * L.bytes;
+        // prefetch the next tile of this CTA into the other stage (its last readers passed the barrier that
+        // ends the previous iteration; the proxy fence orders their generic reads before the async writes)
+        if (threadIdx.x == 0 && t + G < A.n_cta) {
+            fence_proxy_async();
+            prefetch_tile(A, t + G, nh0, nh1, nh2, stage0 + (size_t)(s ^ 1) * L.bytes, L, &bars[s ^ 1]);
+            if (t + 2 * G < A.n_cta) {
+                const int4* hn = hdr_g + 3 * (size_t)(t + 2 * G);
+                nh0 = __ldg(hn); nh1 = __ldg(hn + 1); nh2 = __ldg(hn + 2);
+            }
+        }
+        // wait for this tile's segments
+        const uint32_t parity = (uint32_t)(k >> 1) & 1u;
+        while (!mbar_try_wait(&bars[s], parity)) {}
+        const int32_t* hdr = reinterpret_cast<const int32_t*>(st + L.hdr);
+        const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], n_split = hdr[H_NSPLIT], o_elems = hdr[H_OELEMS];
+        const double* xyz = reinterpret_cast<const double*>(st + L.xyz);
+        const uint32_t* conn8 = reinterpret_cast<const uint32_t*>(st + L.conn8);
+        const int32_t* mat = reinterpret_cast<const int32_t*>(st + L.mat);
+        const int32_t* it_block = reinterpret_cast<const int32_t*>(st + L.it_block);
+        const int32_t* it_inc = reinterpret_cast<const int32_t*>(st + L.it_inc);
+        const int32_t* it_meta = reinterpret_cast<const int32_t*>(st + L.it_meta);
+        const uint16_t* inc_s = reinterpret_cast<const uint16_t*>(st + L.inc);
+        // phase 1: geometry records of the staged elements
+        for (int le = threadIdx.x; le < n_elems; le += ASM_THREADS) {
+            const double det = stage_element_local(A.mat_table, xyz, conn8[le], mat[le], W4, recs + (size_t)le * REC_STRIDE);
+            if (!(det > 0.0)) {  // error path only: elements.py:207-210
+                const int32_t e = A.cta_elems[o_elems + le];
+                if (det < 0.0) atomicMin(A.bad_elem, e);
+                else atomicMin(A.bad_elem + 1, e);
+            }
+        }
         __syncthreads();
-        for (int k = sp0 + threadIdx.x; k < sp1; k += ASM_THREADS)
-            combine_split<OPS, DUU>(A, __ldg(A.split_block + k), __ldg(A.split_meta + k), partials);
+        // phase 2: work items
+        for (int it = threadIdx.x; it < n_items; it += ASM_THREADS)
+            process_item<OPS, DUU>(A, it_block[it], (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, c_quad.S, c_quad.NN);
+        // phase 3: split (diagonal) blocks
+        if (n_split > 0) {   // uniform over the CTA
+            __syncthreads();
+            const int32_t* sp_block = reinterpret_cast<const int32_t*>(st + L.sp_block);
+            const int32_t* sp_meta = reinterpret_cast<const int32_t*>(st + L.sp_meta);
+            for (int q = threadIdx.x; q < n_split; q += ASM_THREADS) combine_split<OPS, DUU>(A, sp_block[q], sp_meta[q], partials);
+        }
+        __syncthreads();   // records, partials and this stage are free again
     }
 }
 
@@ -391,30 +432,34 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
 
-struct LaunchDims {
-    int n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes;
-};
-
 template <int OPS, int DUU>
-static int launch_assemble(const AssembleArgs& A, const LaunchDims& d, cudaStream_t st) {
-    const int rec_doubles = (d.max_cta_elems * REC_STRIDE + 1) & ~1;    // keep the areas behind it 16-byte aligned
-    const int part_doubles = (d.max_cta_slots * AsmTraits<OPS, DUU>::Acc::LIVE + 1) & ~1;
-    const int xyz_doubles = (3 * d.max_cta_nodes + 1) & ~1;
-    const size_t smem = ((size_t)rec_doubles + part_doubles + xyz_doubles) * sizeof(double) +
-                        ((size_t)d.max_cta_inc + 16) * sizeof(uint16_t);
-    TEFEM_REQUIRE(smem <= 200 * 1024, "CTA tile exceeds shared memory");
+static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
+    const int rec_doubles = (d.max_elems * REC_STRIDE + 15) & ~15;          // keep what follows 128-byte aligned
+    const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::Acc::LIVE + 15) & ~15;
+    const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
+    const size_t smem = ((size_t)rec_doubles + part_doubles) * sizeof(double) + 2 * (size_t)L.bytes + 16;
+    TEFEM_REQUIRE(smem <= 220 * 1024, "tile exceeds shared memory");
+    static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        int dev = 0;
+        TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
+        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
-    assemble_kernel<OPS, DUU><<<d.n_cta, ASM_THREADS, smem, st>>>(A, rec_doubles, part_doubles, xyz_doubles);
+    int per_sm = 0;
+    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU>, ASM_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count * per_sm;
+    if (grid > d.n_cta) grid = d.n_cta;
+    assemble_kernel<OPS, DUU><<<grid, ASM_THREADS, smem, st>>>(A, d, rec_doubles, part_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
 
 template <int OPS>
-static int dispatch_duu(const AssembleArgs& A, int duu, const LaunchDims& d, cudaStream_t st) {
+static int dispatch_duu(const AssembleArgs& A, int duu, const TileDims& d, cudaStream_t st) {
     if (!(OPS & TEFEM_OP_D)) return launch_assemble<OPS, 0>(A, d, st);
     switch (duu) {
         case 0: return launch_assemble<OPS, 0>(A, d, st);
@@ -440,35 +485,44 @@ extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn,
     return TEFEM_OK;
 }
 
-extern "C" int tefem_assemble(const double* coords, const double* mat_table, int n_mat, int32_t n_cta,
-                              int32_t max_cta_elems, int32_t max_cta_inc, int32_t max_cta_slots, int32_t max_cta_nodes,
-                              const int32_t* cta_ptr, const int32_t* cta_elems, const int32_t* cta_conn8,
-                              const int32_t* cta_mat, const int32_t* cta_nodes, const int32_t* item_block,
-                              const int32_t* item_blockT, const uint32_t* item_inc,
-                              const int32_t* item_meta, const int32_t* split_block, const int32_t* split_meta,
-                              const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M, double alpha_K,
-                              double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem, void* stream) {
-    TEFEM_REQUIRE(coords && mat_table && bad_elem, "null mesh input");
-    TEFEM_REQUIRE(cta_ptr && cta_elems && cta_conn8 && cta_mat && cta_nodes && item_block && item_blockT && item_inc &&
-                      item_meta && inc, "null schedule");
-    TEFEM_REQUIRE(max_cta_slots == 0 || (split_block && split_meta), "null split lists");
-    TEFEM_REQUIRE((((uintptr_t)inc) & 15) == 0 && (((uintptr_t)cta_ptr) & 15) == 0, "inc / cta_ptr must be 16-byte aligned");
-    TEFEM_REQUIRE(max_cta_nodes > 0 && max_cta_nodes <= 256, "max_cta_nodes must fit a byte");
+extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
+                              const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
+                              const int32_t* cta_mat, const double* cta_xyz, const int32_t* item_block,
+                              const int32_t* item_inc, const int32_t* item_meta, const int32_t* split_block,
+                              const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M,
+                              double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem,
+                              void* stream) {
+    TEFEM_REQUIRE(mat_table && bad_elem && h_max, "null input");
+    TEFEM_REQUIRE(cta_hdr && cta_elems && cta_conn8 && cta_mat && cta_xyz && item_block && item_inc && item_meta && inc,
+                  "null schedule");
+    const int max_items = h_max[0], max_elems = h_max[1], max_inc = h_max[2], max_slots = h_max[3], max_split = h_max[4],
+              max_nodes = h_max[5];
+    TEFEM_REQUIRE(max_split == 0 || (split_block && split_meta), "null split lists");
+    const uintptr_t align_or = (uintptr_t)cta_hdr | (uintptr_t)cta_conn8 | (uintptr_t)cta_mat | (uintptr_t)cta_xyz |
+                               (uintptr_t)item_block | (uintptr_t)item_inc | (uintptr_t)item_meta | (uintptr_t)split_block |
+                               (uintptr_t)split_meta | (uintptr_t)inc;
+    TEFEM_REQUIRE((align_or & 15) == 0, "schedule arrays must be 16-byte aligned");
     TEFEM_REQUIRE(ops > 0 && ops < 8, "ops mask");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_M) || vals_M, "vals_M");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_K) || vals_K, "vals_K");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_D) || vals_D, "vals_D");
-    TEFEM_REQUIRE(max_cta_elems > 0 && max_cta_elems <= 4096, "max_cta_elems must fit 12 bits");
-    TEFEM_REQUIRE(max_cta_inc >= 0 && max_cta_slots >= 0 && max_cta_slots < 65536, "max_cta_inc / max_cta_slots");
+    TEFEM_REQUIRE(max_elems > 0 && max_elems <= 4096, "max elements per tile must fit 12 bits");
+    TEFEM_REQUIRE(max_nodes > 0 && max_nodes <= 256, "max nodes per tile must fit a byte");
+    TEFEM_REQUIRE(max_items > 0 && max_inc >= 0 && max_slots >= 0 && max_slots < 65536 && max_split >= 0, "tile limits");
     TEFEM_REQUIRE(n_mat > 0, "n_mat");
     if (n_cta == 0) return TEFEM_OK;
     int rc = upload_quad();
     if (rc) return rc;
     AssembleArgs A;
-    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn8, cta_mat, cta_nodes, item_block, item_blockT, item_inc,
-              item_meta, split_block, split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
+    memset(&A, 0, sizeof(A));
+    A.mat_table = mat_table;
+    A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_mat = cta_mat; A.cta_xyz = cta_xyz;
+    A.item_block = item_block; A.item_inc = item_inc; A.item_meta = item_meta;
+    A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
+    A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
+    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
-    const LaunchDims d = {n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes};
+    const TileDims d = {n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes};
     cudaStream_t st = as_stream(stream);
     switch (ops) {
         case 1: return dispatch_duu<1>(A, duu, d, st);
@@ -497,66 +551,67 @@ extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, vo
 // TEFEM_HOST_EMU: sequential execution of the SAME per-thread routines (tests/host_emulation only).
 // ================================================================================================
 template <int OPS, int DUU>
-static int emu_run(const AssembleArgs& A, int n_cta, int max_cta_elems, int max_cta_inc, int max_cta_slots,
-                   int max_cta_nodes) {
+static int emu_run(const AssembleArgs& A, const TileDims& d) {
     typedef typename AsmTraits<OPS, DUU>::Acc Acc;
     const QuadTables& q = quad_tables();
-    std::vector<double> recs((size_t)max_cta_elems * REC_STRIDE);
-    std::vector<double> partials((size_t)max_cta_slots * Acc::LIVE + 1);
-    std::vector<uint16_t> inc_s((size_t)max_cta_inc + 16);
-    std::vector<double> xyz((size_t)3 * max_cta_nodes + 1);
-    for (int cta = 0; cta < n_cta; ++cta) {
-        const int32_t* c = A.cta_ptr + (size_t)CTA_STRIDE * cta;
-        const int e0 = c[CTA_ELEM0], ne = c[CTA_ELEM1] - e0;
-        if (ne > max_cta_elems) return TEFEM_ERR_INVALID;
-        const int n0 = c[CTA_NODE0], nn = c[CTA_NODE1] - n0;
-        if (nn > max_cta_nodes) return TEFEM_ERR_INVALID;
-        for (int k = 0; k < nn; ++k)
-            for (int d = 0; d < 3; ++d) xyz[3 * k + d] = A.coords[3 * (size_t)A.cta_nodes[n0 + k] + d];
-        // same staging arithmetic as the kernel: aligned-down copy of the tile's incidence range
-        const uint32_t inc_lo = (uint32_t)c[CTA_INC0], inc_hi = (uint32_t)c[CTA_INC1];
-        const uint32_t base = inc_lo & ~7u;
-        const uint32_t n16 = (inc_hi - base + 7u) >> 3;
-        if ((size_t)n16 * 8 > inc_s.size()) return TEFEM_ERR_INVALID;
-        for (uint32_t k = 0; k < n16 * 8; ++k) inc_s[k] = A.inc[base + k];
-        for (int le = 0; le < ne; ++le) {
-            const double det = stage_element_local(A, xyz.data(), (uint32_t)A.cta_conn8[e0 + le], A.cta_mat[e0 + le], q.W4,
+    std::vector<double> recs((size_t)d.max_elems * REC_STRIDE);
+    std::vector<double> partials((size_t)d.max_slots * Acc::LIVE + 1);
+    for (int cta = 0; cta < d.n_cta; ++cta) {
+        const int32_t* h = A.cta_hdr + (size_t)HDR_STRIDE * cta;
+        if (h[H_NELEMS] > d.max_elems || h[H_NITEMS] > d.max_items || h[H_NINC] > d.max_inc || h[H_NSPLIT] > d.max_split ||
+            h[H_NNODES] > d.max_nodes)
+            return TEFEM_ERR_INVALID;
+        // every segment must start on a 16-byte boundary (bulk copies)
+        if ((h[H_OITEMS] & 3) || (h[H_OELEMS] & 3) || (h[H_OINC] & 7) || (h[H_OSPLIT] & 3) || (h[H_ONODES] & 1)) return TEFEM_ERR_INVALID;
+        const double* xyz = A.cta_xyz + 3 * (size_t)h[H_ONODES];
+        const uint16_t* inc_s = A.inc + h[H_OINC];
+        for (int le = 0; le < h[H_NELEMS]; ++le) {
+            const uint32_t cn = (uint32_t)A.cta_conn8[h[H_OELEMS] + le];
+            for (int a = 0; a < 4; ++a)
+                if ((int)((cn >> (8 * a)) & 0xff) >= h[H_NNODES]) return TEFEM_ERR_INVALID;
+            const double det = stage_element_local(A.mat_table, xyz, cn, A.cta_mat[h[H_OELEMS] + le], q.W4,
                                                    recs.data() + (size_t)le * REC_STRIDE);
             if (!(det > 0.0)) {
-                const int32_t e = A.cta_elems[e0 + le];
+                const int32_t e = A.cta_elems[h[H_OELEMS] + le];
                 int32_t* slot = A.bad_elem + (det < 0.0 ? 0 : 1);
                 if (e < *slot) *slot = e;
             }
         }
-        for (int it = c[CTA_ITEM0]; it < c[CTA_ITEM1]; ++it) {
-            const int slot = ((A.item_meta[it] >> 8) & 0xffff) - 1;
-            if (slot >= max_cta_slots) return TEFEM_ERR_INVALID;
-            process_item<OPS, DUU>(A, A.item_block[it], A.item_blockT[it], A.item_inc[it] - base, A.item_meta[it],
-                                   recs.data(), inc_s.data(), partials.data(), q.S, q.NN);
+        for (int it = 0; it < h[H_NITEMS]; ++it) {
+            const int32_t meta = A.item_meta[h[H_OITEMS] + it];
+            const int slot = (meta >> 8) - 1;
+            const int32_t s = A.item_inc[h[H_OITEMS] + it];
+            if (slot >= d.max_slots || s < 0 || s + (meta & 0xff) > h[H_NINC]) return TEFEM_ERR_INVALID;
+            process_item<OPS, DUU>(A, A.item_block[h[H_OITEMS] + it], (uint32_t)s, meta, recs.data(), inc_s, partials.data(),
+                                   q.S, q.NN);
         }
-        for (int k = c[CTA_SPLIT0]; k < c[CTA_SPLIT1]; ++k)
-            combine_split<OPS, DUU>(A, A.split_block[k], A.split_meta[k], partials.data());
+        for (int k = 0; k < h[H_NSPLIT]; ++k)
+            combine_split<OPS, DUU>(A, A.split_block[h[H_OSPLIT] + k], A.split_meta[h[H_OSPLIT] + k], partials.data());
     }
     return TEFEM_OK;
 }
 
-extern "C" int tefem_emu_assemble(const double* coords, const double* mat_table, int32_t n_cta, int32_t max_cta_elems,
-                                  int32_t max_cta_inc, int32_t max_cta_slots, int32_t max_cta_nodes, const int32_t* cta_ptr,
+extern "C" int tefem_emu_assemble(const double* mat_table, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
                                   const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
-                                  const int32_t* cta_nodes, const int32_t* item_block, const int32_t* item_blockT,
-                                  const uint32_t* item_inc, const int32_t* item_meta,
-                                  const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
-                                  int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+                                  const double* cta_xyz, const int32_t* item_block, const int32_t* item_inc,
+                                  const int32_t* item_meta, const int32_t* split_block, const int32_t* split_meta,
+                                  const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                                   double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
     AssembleArgs A;
-    fill_args(A, coords, mat_table, cta_ptr, cta_elems, cta_conn8, cta_mat, cta_nodes, item_block, item_blockT, item_inc,
-              item_meta, split_block, split_meta, inc, n_blocks, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
+    memset(&A, 0, sizeof(A));
+    A.mat_table = mat_table;
+    A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_mat = cta_mat; A.cta_xyz = cta_xyz;
+    A.item_block = item_block; A.item_inc = item_inc; A.item_meta = item_meta;
+    A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
+    A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
+    A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
+    const TileDims d = {n_cta, h_max[0], h_max[1], h_max[2], h_max[3], h_max[4], h_max[5]};
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
-#define TEFEM_EMU_CASE(O)                                                                                     \
-    case O:                                                                                                   \
-        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes); \
-        if (duu == 1) return emu_run<O, 1>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes);              \
-        return emu_run<O, 2>(A, n_cta, max_cta_elems, max_cta_inc, max_cta_slots, max_cta_nodes);
+#define TEFEM_EMU_CASE(O)                                                     \
+    case O:                                                                   \
+        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, d);      \
+        if (duu == 1) return emu_run<O, 1>(A, d);                             \
+        return emu_run<O, 2>(A, d);
     switch (ops) {
         TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)
         TEFEM_EMU_CASE(5) TEFEM_EMU_CASE(6) TEFEM_EMU_CASE(7)
@@ -569,6 +624,7 @@ extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* c
                                           const double* mat_table, int64_t n, int kinds, double* Muu, double* Dtu,
                                           double* Dtt, double* Kuu, double* Kut, double* Ktt, int32_t* bad_elem) {
     AssembleArgs A;
+    memset(&A, 0, sizeof(A));
     A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
     const QuadTables& q = quad_tables();
     for (int64_t e = 0; e < n; ++e) {

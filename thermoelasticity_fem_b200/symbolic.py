@@ -1,4 +1,4 @@
-"""Symbolic phase: node-block sparsity pattern, slot map and owner-computes schedule.
+"""Symbolic phase: node-block sparsity pattern, slot map and owner-computes tile schedule.
 
 Runs once per mesh (not on the repeatable path) with plain torch integer ops on whatever
 device the connectivity lives on, so the same code is exercised on CPU tensors by the
@@ -13,16 +13,18 @@ touched pattern of each operator follows from the plane maps in ``layout.py``.
 Outputs (see include/tefem.h, tefem_assemble):
   rowptr[R+1], colidx[P]     node-block CSR, columns ascending inside a row
   diag_idx[R]                position of block (i, i)
-  inc[...]                   incidence entries (tile-local element << 4) | (a << 2) | b of the DIAGONAL and
-                             UPPER (row < col) blocks, block after block, ascending element inside a block
-  work items                 an upper block (i, j) - its thread also produces the mirrored block (j, i), whose
-                             contributions come from the same elements with (a, b) swapped - or a chunk of
-                             <= max_chunk incidences of a diagonal block: item_block, item_blockT (mirror block
-                             or -1), item_inc (first entry), item_meta (length | (partial slot + 1) << 8)
-  split_block, split_meta    diagonal blocks whose list was split: block, first slot | n_chunks << 16
-  cta_ptr[n_cta, 12]         per tile: item, staged-element, incidence, split and node ranges
-  cta_elems, cta_conn8       elements each tile stages, and their connectivity as 4 tile-local node bytes
-  cta_nodes                  nodes whose coordinates each tile stages
+  tile-packed schedule       a tile owns a contiguous range of node rows; everything it needs is stored in
+                             per-tile segments that start on 16-byte boundaries (each segment is fetched with
+                             one bulk copy into shared memory):
+    cta_hdr[n_cta, 12]         n_items, n_elems, n_inc, n_split, n_nodes, then the five segment offsets
+    item_block/inc/meta        work items: a block, or a chunk of a block whose incidence list is long (the
+                               diagonal blocks); item_inc = first incidence entry (tile-relative),
+                               item_meta = length | (partial slot + 1) << 8
+    inc                        incidence entries (tile-local element << 4) | (a << 2) | b, block after block,
+                               ascending element inside a block (the reference's summation order)
+    split_block/meta           blocks whose list was split: block, first slot | n_chunks << 16
+    cta_elems, cta_conn8       elements the tile stages, and their connectivity as 4 tile-local node bytes
+    cta_nodes                  nodes whose coordinates the tile stages
 """
 from dataclasses import dataclass
 
@@ -30,10 +32,11 @@ import torch
 
 ITEMS_PER_CTA = 256          # = ASM_THREADS of tefem_assemble.cu
 ELEM_BUDGET_PER_CTA = 600    # bound on the sum of node degrees per tile (>= staged elements)
-MAX_CHUNK = 6                # longest incidence list handled by one thread
+MAX_CHUNK = 6                # lists longer than 2 * MAX_CHUNK are split into chunks of <= MAX_CHUNK
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
-CTA_STRIDE = 12
+HDR_STRIDE = 12
+H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES = range(10)
 
 
 @dataclass
@@ -47,24 +50,25 @@ class Schedule:
     colidx: torch.Tensor     # int32 [P]
     block_row: torch.Tensor  # int32 [P]
     diag_idx: torch.Tensor   # int32 [n_rows]
-    inc_ptr: torch.Tensor    # int32 [n_listed+1]  offsets of the listed (diagonal + upper) blocks into inc
-    listed_block: torch.Tensor   # int32 [n_listed] block number of each listed block
-    inc: torch.Tensor        # int16 [n_inc + 8] (read as uint16 by the kernels; 8 entries of padding)
+    block_inc: torch.Tensor  # int32 [P] absolute position of each block's incidence list in `inc`
+    block_len: torch.Tensor  # int32 [P] its length
+    inc: torch.Tensor        # int16 [padded] (read as uint16 by the kernels)
     n_cta: int
+    max_cta_items: int
     max_cta_elems: int
     max_cta_inc: int
     max_cta_slots: int
+    max_cta_split: int
     max_cta_nodes: int
-    cta_ptr: torch.Tensor        # int32 [n_cta, 12]: item0, item1, elem0, elem1, inc0, inc1, split0, split1, node0, node1, 0, 0
-    cta_elems: torch.Tensor      # int32 [n_staged]
-    cta_conn8: torch.Tensor      # int32 [n_staged] 4 tile-local node numbers, byte a = node a
-    cta_nodes: torch.Tensor      # int32 [n_tile_nodes]
-    item_block: torch.Tensor     # int32 [n_items]
-    item_blockT: torch.Tensor    # int32 [n_items]
-    item_inc: torch.Tensor       # int32 [n_items]
-    item_meta: torch.Tensor      # int32 [n_items]
-    split_block: torch.Tensor    # int32 [n_split]
-    split_meta: torch.Tensor     # int32 [n_split]
+    cta_hdr: torch.Tensor        # int32 [n_cta, 12]
+    cta_elems: torch.Tensor      # int32 [padded] (-1 in the padding)
+    cta_conn8: torch.Tensor      # int32 [padded] 4 tile-local node numbers, byte a = node a
+    cta_nodes: torch.Tensor      # int32 [padded] (padding repeats node 0 of the tile)
+    item_block: torch.Tensor     # int32 [padded]
+    item_inc: torch.Tensor       # int32 [padded] tile-relative
+    item_meta: torch.Tensor      # int32 [padded]
+    split_block: torch.Tensor    # int32 [padded]
+    split_meta: torch.Tensor     # int32 [padded]
 
     def to(self, device):
         kw = {}
@@ -73,10 +77,10 @@ class Schedule:
         return Schedule(**kw)
 
     def schedule_bytes(self):
-        """Bytes of slot-map / schedule data one assembly launch reads (cta_mat is counted by DeviceMesh)."""
+        """Bytes of slot-map / schedule data one assembly launch reads (cta_mat / cta_xyz are counted by DeviceMesh)."""
         return sum(t.numel() * t.element_size() for t in
-                   (self.inc, self.cta_ptr, self.cta_conn8, self.cta_nodes, self.item_block, self.item_blockT,
-                    self.item_inc, self.item_meta, self.split_block, self.split_meta))
+                   (self.inc, self.cta_hdr, self.cta_conn8, self.item_block, self.item_inc, self.item_meta,
+                    self.split_block, self.split_meta))
 
 
 def _excl_cumsum(x):
@@ -87,6 +91,18 @@ def _ptr_from_counts(counts, n, dev):
     ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=ptr[1:])
     return ptr
+
+
+def _pad_segments(values, seg_of, seg_ptr, n_seg, align, fill):
+    """values are grouped by segment (seg_of ascending, seg_ptr their unpadded offsets); returns the array with
+    every segment start aligned to `align` entries, the padded offsets [n_seg + 1] and the padded positions."""
+    counts = seg_ptr[1:] - seg_ptr[:-1]
+    padded = torch.div(counts + (align - 1), align, rounding_mode='floor') * align
+    pptr = _ptr_from_counts(padded, n_seg, values.device)
+    pos = pptr[seg_of] + (torch.arange(values.numel(), device=values.device, dtype=torch.int64) - seg_ptr[seg_of])
+    out = torch.full((int(pptr[-1].item()),), fill, dtype=values.dtype, device=values.device)
+    out[pos] = values
+    return out, pptr, pos
 
 
 class _TileTooLarge(Exception):
@@ -113,7 +129,7 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
 
 def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk):
     assert conn.dim() == 2 and conn.shape[1] == 4
-    assert 1 <= max_chunk <= 255
+    assert 1 <= max_chunk <= 127
     dev = conn.device
     E = int(conn.shape[0])
     N = int(n_nodes)
@@ -137,37 +153,17 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
     P = int(ukey.numel())
     block_row = torch.div(ukey, N, rounding_mode='floor')
     block_col = ukey - block_row * N
+    del ukey
+    inc_ptr = _ptr_from_counts(counts, P, dev)
     blocks_per_row = torch.bincount(block_row, minlength=R)
     rowptr = _ptr_from_counts(blocks_per_row, R, dev)
     diag_idx = torch.nonzero(block_row == block_col).reshape(-1)
     assert int(diag_idx.numel()) == R, "every owned node must belong to at least one element"
 
-    # ---- listed blocks: diagonal and upper; the mirror (j, i) of an upper block is produced by the same thread
-    listed = block_col >= block_row
-    listed_block = torch.nonzero(listed).reshape(-1)
-    L = int(listed_block.numel())
-    lcounts = counts[listed_block]
-    is_upper = (block_col > block_row)[listed_block]
-    mirror = torch.full((L,), -1, **i64)
-    up = listed_block[is_upper]
-    # the mirror block exists in this rank's pattern only when its row (= col of the upper block) is owned
-    mkey = block_col[up] * N + block_row[up]
-    pos = torch.searchsorted(ukey, mkey).clamp(max=max(P - 1, 0))
-    found = ukey[pos] == mkey
-    mirror[is_upper] = torch.where(found, pos, torch.full_like(pos, -1))
-    assert bool((found | (block_col[up] >= R)).all()), "pattern must be structurally symmetric on the owned rows"
-    del ukey, mkey, pos, found, up
-    # incidence entries of the listed blocks only
-    inc_keep = torch.repeat_interleave(listed, counts)
-    src = src[inc_keep]
-    del inc_keep
-    inc_ptr = _ptr_from_counts(lcounts, L, dev)
-
-    # ---- work items: upper blocks are single items, diagonal blocks are split into balanced chunks
-    n_chunks = torch.where(is_upper, torch.ones_like(lcounts),
-                           torch.div(lcounts + (max_chunk - 1), max_chunk, rounding_mode='floor'))
-    lrow = block_row[listed_block]
-    items_per_row = torch.zeros(R, **i64).index_add_(0, lrow, n_chunks)
+    # ---- work items: lists longer than 2 * max_chunk (the diagonal blocks) are split into balanced chunks
+    n_chunks = torch.where(counts > 2 * max_chunk, torch.div(counts + (max_chunk - 1), max_chunk, rounding_mode='floor'),
+                           torch.ones_like(counts))
+    items_per_row = torch.zeros(R, **i64).index_add_(0, block_row, n_chunks)
 
     # ---- rows -> tiles: cumulative cost, integer arithmetic (work items vs. staged-element budget)
     degree = torch.bincount(conn.reshape(-1), minlength=N)[:R]
@@ -176,7 +172,7 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
     cta_of_row = torch.div(_excl_cumsum(cost), unit, rounding_mode='floor')
     _, cta_of_row = torch.unique_consecutive(cta_of_row, return_inverse=True)    # compact ids
     n_cta = int(cta_of_row[-1].item()) + 1 if R > 0 else 0
-    cta_of_listed = cta_of_row[lrow]
+    cta_of_block = cta_of_row[block_row]
 
     # ---- per-tile staged element lists: unique (tile, element) over the (element, node) incidences
     node = conn.reshape(-1)
@@ -205,74 +201,89 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
     lnode = torch.searchsorted(unodes, k4.reshape(-1)).reshape(n_staged, 4) - cta_node_ptr[cta_of_k2][:, None]
     conn8 = lnode[:, 0] | (lnode[:, 1] << 8) | (lnode[:, 2] << 16) | (lnode[:, 3] << 24)
     conn8 = torch.where(conn8 >= 2 ** 31, conn8 - 2 ** 32, conn8)
-    del sconn, k4, unodes, cta_of_un, lnode, cta_of_k2
+    del sconn, k4, unodes, lnode
 
     # ---- packed incidence entries: (tile-local element << 4) | (a << 2) | b
     e_src = torch.div(src, 16, rounding_mode='floor')
     ab = src - e_src * 16
-    cta_of_inc = torch.repeat_interleave(cta_of_listed, lcounts)
+    cta_of_inc = torch.repeat_interleave(cta_of_block, counts)
     loc = torch.searchsorted(k2, cta_of_inc * E + e_src) - cta_elem_ptr[cta_of_inc]
-    del k2, e_src, cta_of_inc, src
+    del k2, e_src, src
     packed = (loc << 4) | ab
     del loc, ab
     packed = torch.where(packed >= 32768, packed - 65536, packed).to(torch.int16)
-    # the kernel copies a tile's incidence range with 16-byte loads from the aligned address below it:
-    # keep the array readable 8 entries past its end
-    packed = torch.cat([packed, torch.zeros(8, dtype=torch.int16, device=dev)])
 
-    # ---- item arrays in (listed block, chunk) order
+    # ---- tile-packed segments (16-byte aligned starts)
+    blocks_per_cta = torch.bincount(cta_of_block, minlength=n_cta)
+    cta_blk_ptr = _ptr_from_counts(blocks_per_cta, n_cta, dev)
+    cta_inc_ptr = inc_ptr[cta_blk_ptr]                                           # unpadded incidence range of each tile
+    inc_p, inc_pptr, inc_pos = _pad_segments(packed, cta_of_inc, cta_inc_ptr, n_cta, 8, 0)
+    del packed, cta_of_inc
+    block_inc_abs = inc_pos[inc_ptr[:-1]]                                        # every block has >= 1 incidence
+    del inc_pos
+    max_cta_inc = int((cta_inc_ptr[1:] - cta_inc_ptr[:-1]).max().item()) if n_cta else 0
+
+    # ---- item arrays in (block, chunk) order
     n_items = int(n_chunks.sum().item())
-    item_l = torch.repeat_interleave(torch.arange(L, **i64), n_chunks)
-    chunk = torch.arange(n_items, **i64) - _excl_cumsum(n_chunks)[item_l]
-    base_len = torch.div(lcounts, n_chunks, rounding_mode='floor')[item_l]
-    rem = (lcounts - torch.div(lcounts, n_chunks, rounding_mode='floor') * n_chunks)[item_l]
+    item_blk = torch.repeat_interleave(torch.arange(P, **i64), n_chunks)
+    chunk = torch.arange(n_items, **i64) - _excl_cumsum(n_chunks)[item_blk]
+    base_len = torch.div(counts, n_chunks, rounding_mode='floor')[item_blk]
+    rem = (counts - torch.div(counts, n_chunks, rounding_mode='floor') * n_chunks)[item_blk]
     item_len = base_len + (chunk < rem).to(torch.int64)
-    item_inc = inc_ptr[item_l] + chunk * base_len + torch.minimum(chunk, rem)
-    is_split = n_chunks[item_l] > 1
-    cta_of_item = cta_of_listed[item_l]
+    if n_items and int(item_len.max().item()) > 255:
+        raise _TileTooLarge()
+    cta_of_item = cta_of_block[item_blk]
+    # first entry relative to the tile's (padded) incidence segment
+    item_inc = block_inc_abs[item_blk] - inc_pptr[cta_of_item] + chunk * base_len + torch.minimum(chunk, rem)
+    is_split = n_chunks[item_blk] > 1
     cta_item_ptr = _ptr_from_counts(torch.bincount(cta_of_item, minlength=n_cta), n_cta, dev)
+    max_cta_items = int((cta_item_ptr[1:] - cta_item_ptr[:-1]).max().item()) if n_cta else 0
     split_run = _excl_cumsum(is_split.to(torch.int64))                           # global rank among split items
     slot = split_run - split_run[cta_item_ptr[:-1].clamp(max=max(n_items - 1, 0))][cta_of_item]
     item_meta = item_len | torch.where(is_split, (slot + 1) << 8, torch.zeros_like(slot))
-    item_block = listed_block[item_l]
-    item_blockT = mirror[item_l]
-    item_upper = is_upper[item_l]
-    item_meta = item_meta | (item_upper.to(torch.int64) << 24)
     # split blocks of each tile
-    l_split = torch.nonzero(n_chunks > 1).reshape(-1)
-    first_item = _excl_cumsum(n_chunks)[l_split]
-    split_meta = slot[first_item] | (n_chunks[l_split] << 16)
-    split_block = listed_block[l_split]
-    cta_split_ptr = _ptr_from_counts(torch.bincount(cta_of_listed[l_split], minlength=n_cta), n_cta, dev)
+    blk_split = torch.nonzero(n_chunks > 1).reshape(-1)
+    first_item = _excl_cumsum(n_chunks)[blk_split]
+    split_meta = slot[first_item] | (n_chunks[blk_split] << 16)
+    cta_of_split = cta_of_block[blk_split]
+    cta_split_ptr = _ptr_from_counts(torch.bincount(cta_of_split, minlength=n_cta), n_cta, dev)
+    max_cta_split = int((cta_split_ptr[1:] - cta_split_ptr[:-1]).max().item()) if n_cta else 0
     slots_per_cta = torch.zeros(n_cta, **i64).index_add_(0, cta_of_item, is_split.to(torch.int64))
     max_cta_slots = int(slots_per_cta.max().item()) if n_cta else 0
     assert max_cta_slots < 65536
+    # order the items of each tile longest first (homogeneous warps), stable inside equal lengths
+    maxlen = int(item_len.max().item()) if n_items else 0
+    perm = torch.sort(cta_of_item * (maxlen + 1) + (maxlen - item_len), stable=True)[1]
+    item_blk, item_inc, item_meta = item_blk[perm], item_inc[perm], item_meta[perm]
+    del perm                                                                     # cta_of_item is unchanged by the permutation
 
-    # ---- order the items of each tile: upper blocks first (their threads do more work), then longest first
-    # (homogeneous warps); stable inside equal keys
-    kind = torch.where(item_upper, torch.zeros_like(item_len), torch.ones_like(item_len))
-    perm = torch.sort((cta_of_item * 2 + kind) * (max(max_chunk, int(lcounts.max().item()) if L else 1) + 1)
-                      + (max(max_chunk, int(lcounts.max().item()) if L else 1) - item_len), stable=True)[1]
-    item_block, item_blockT, item_inc, item_meta = item_block[perm], item_blockT[perm], item_inc[perm], item_meta[perm]
-    del perm
+    item_block_p, item_pptr, _ = _pad_segments(item_blk, cta_of_item, cta_item_ptr, n_cta, 4, 0)
+    item_inc_p, _, _ = _pad_segments(item_inc, cta_of_item, cta_item_ptr, n_cta, 4, 0)
+    item_meta_p, _, _ = _pad_segments(item_meta, cta_of_item, cta_item_ptr, n_cta, 4, 0)      # padding: length 0
+    split_block_p, split_pptr, _ = _pad_segments(blk_split, cta_of_split, cta_split_ptr, n_cta, 4, 0)
+    split_meta_p, _, _ = _pad_segments(split_meta, cta_of_split, cta_split_ptr, n_cta, 4, 0)
+    elems_p, elem_pptr, _ = _pad_segments(cta_elems, cta_of_k2, cta_elem_ptr, n_cta, 4, -1)
+    conn8_p, _, _ = _pad_segments(conn8, cta_of_k2, cta_elem_ptr, n_cta, 4, 0)
+    nodes_p, node_pptr, _ = _pad_segments(cta_nodes, cta_of_un, cta_node_ptr, n_cta, 2, -1)
+    # padding entries of the node list repeat the tile's first node (a valid address for the coordinate copy)
+    if nodes_p.numel():
+        first_node = cta_nodes[cta_node_ptr[:-1]]
+        tile_of_slot = torch.searchsorted(node_pptr[1:], torch.arange(nodes_p.numel(), **i64), right=True)
+        nodes_p = torch.where(nodes_p < 0, first_node[tile_of_slot.clamp(max=max(n_cta - 1, 0))], nodes_p)
 
-    # ---- per-tile ranges
-    listed_per_cta = torch.bincount(cta_of_listed, minlength=n_cta)
-    cta_l_ptr = _ptr_from_counts(listed_per_cta, n_cta, dev)
-    cta_inc_ptr = inc_ptr[cta_l_ptr]
-    max_cta_inc = int((cta_inc_ptr[1:] - cta_inc_ptr[:-1]).max().item()) if n_cta else 0
+    def cnt(ptr):
+        return ptr[1:] - ptr[:-1]
     zero = torch.zeros(n_cta, **i64)
-    cta_ptr = torch.stack([cta_item_ptr[:-1], cta_item_ptr[1:], cta_elem_ptr[:-1], cta_elem_ptr[1:],
-                           cta_inc_ptr[:-1], cta_inc_ptr[1:], cta_split_ptr[:-1], cta_split_ptr[1:],
-                           cta_node_ptr[:-1], cta_node_ptr[1:], zero, zero], dim=1)
+    cta_hdr = torch.stack([cnt(cta_item_ptr), cnt(cta_elem_ptr), cnt(cta_inc_ptr), cnt(cta_split_ptr), cnt(cta_node_ptr),
+                           item_pptr[:-1], elem_pptr[:-1], inc_pptr[:-1], split_pptr[:-1], node_pptr[:-1], zero, zero], dim=1)
+    assert int(inc_pptr[-1].item()) < 2 ** 31
 
     i32 = torch.int32
     return Schedule(n_nodes=N, n_rows=R, n_blocks=P, n_elems=E, n_items=n_items,
                     rowptr=rowptr.to(i32), colidx=block_col.to(i32), block_row=block_row.to(i32),
-                    diag_idx=diag_idx.to(i32), inc_ptr=inc_ptr.to(i32), listed_block=listed_block.to(i32), inc=packed,
-                    n_cta=n_cta, max_cta_elems=max_cta_elems, max_cta_inc=max_cta_inc, max_cta_slots=max_cta_slots,
-                    max_cta_nodes=max_cta_nodes,
-                    cta_ptr=cta_ptr.to(i32).contiguous(), cta_elems=cta_elems.to(i32), cta_conn8=conn8.to(i32),
-                    cta_nodes=cta_nodes.to(i32),
-                    item_block=item_block.to(i32), item_blockT=item_blockT.to(i32), item_inc=item_inc.to(i32),
-                    item_meta=item_meta.to(i32), split_block=split_block.to(i32), split_meta=split_meta.to(i32))
+                    diag_idx=diag_idx.to(i32), block_inc=block_inc_abs.to(i32), block_len=counts.to(i32), inc=inc_p,
+                    n_cta=n_cta, max_cta_items=max_cta_items, max_cta_elems=max_cta_elems, max_cta_inc=max_cta_inc,
+                    max_cta_slots=max_cta_slots, max_cta_split=max_cta_split, max_cta_nodes=max_cta_nodes,
+                    cta_hdr=cta_hdr.to(i32).contiguous(), cta_elems=elems_p.to(i32), cta_conn8=conn8_p.to(i32),
+                    cta_nodes=nodes_p.to(i32), item_block=item_block_p.to(i32), item_inc=item_inc_p.to(i32),
+                    item_meta=item_meta_p.to(i32), split_block=split_block_p.to(i32), split_meta=split_meta_p.to(i32))

@@ -72,7 +72,7 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     return dict(M=vM, K=vK, D=vD), bad
 
 
-def check_schedule_invariants(S, conn, n_nodes, max_chunk=6):
+def check_schedule_invariants(S, conn, n_nodes, max_chunk=8):
     E = conn.shape[0]
     rowptr, colidx, br = S.rowptr.numpy(), S.colidx.numpy(), S.block_row.numpy()
     assert rowptr[0] == 0 and rowptr[-1] == S.n_blocks

@@ -22,6 +22,7 @@
 #include "tefem_comm.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace tefem {
@@ -49,7 +50,7 @@ __device__ __forceinline__ void ld256_x(const double* p, double& a, double& b, d
 // DOTS = 0: none; 1: partial of (w . y); 8: partials of (y.s_u, y.s_t, y.y_u, y.y_t, s.s_u, s.s_t, w.s, w.y) with
 // s = x (owned part) and the first three split by field (u rows r < 3, theta rows r == 3).
 // rows: optional list of node rows (interior / boundary split), else rows [0, n_rows).
-template <int DOTS>
+template <int DOTS, int UNROLL>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ colidx,
                                                             const int32_t* __restrict__ rows, int32_t n_rows,
@@ -61,24 +62,30 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const int32_t* __res
     const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
     if (active) {
         const int64_t n = 4 * (int64_t)n_rows;
-        for (int64_t tid = (int64_t)blockIdx.x * SPMV_THREADS + threadIdx.x; tid < n;
-             tid += (int64_t)gridDim.x * SPMV_THREADS) {
+        for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n;
+             tid += (int64_t)gridDim.x * blockDim.x) {
             const int32_t i = rows ? rows[tid >> 2] : (int32_t)(tid >> 2);
             const int r = (int)(tid & 3);
             const int32_t s = rowptr[i], t = rowptr[i + 1];
             double acc0 = 0.0, acc1 = 0.0;
             int32_t p = s;
-            for (; p + 1 < t; p += 2) {
-                double a0, a1, a2, a3, b0, b1, b2, b3, x0, x1, x2, x3, z0, z1, z2, z3;
-                const int32_t j0 = colidx[p], j1 = colidx[p + 1];
-                ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
-                ld256(sys + 16 * (int64_t)(p + 1) + 4 * r, b0, b1, b2, b3);
-                ld256_x(x + 4 * (int64_t)j0, x0, x1, x2, x3);
-                ld256_x(x + 4 * (int64_t)j1, z0, z1, z2, z3);
-                acc0 += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
-                acc1 += b0 * z0 + b1 * z1 + b2 * z2 + b3 * z3;
+            // UNROLL blocks per trip: all their 256-bit loads are issued before the first use
+            for (; p + UNROLL <= t; p += UNROLL) {
+                double a[UNROLL][4], v[UNROLL][4];
+                int32_t j[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) j[u] = colidx[p + u];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) ld256(sys + 16 * (int64_t)(p + u) + 4 * r, a[u][0], a[u][1], a[u][2], a[u][3]);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) ld256_x(x + 4 * (int64_t)j[u], v[u][0], v[u][1], v[u][2], v[u][3]);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const double c = a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2] + a[u][3] * v[u][3];
+                    if (u & 1) acc1 += c; else acc0 += c;
+                }
             }
-            if (p < t) {
+            for (; p < t; ++p) {
                 double a0, a1, a2, a3, x0, x1, x2, x3;
                 ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
                 ld256_x(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
@@ -458,13 +465,37 @@ static int grid_for(int64_t n_threads, int per_cta) {
     return (int)g;
 }
 
+// Launch configuration of the SpMV (threads per CTA, CTAs per SM of the grid-stride grid, blocks per trip):
+// tuned on the B200 at config B (profiles/README.md); TEFEM_SPMV_CFG="threads,ctas_per_sm,unroll" overrides it
+// for experiments.
+struct SpmvCfg {
+    int threads = 256, ctas_per_sm = 8, unroll = 2;
+};
+static const SpmvCfg& spmv_cfg() {
+    static SpmvCfg cfg = [] {
+        SpmvCfg c;
+        const char* e = getenv("TEFEM_SPMV_CFG");
+        if (e) sscanf(e, "%d,%d,%d", &c.threads, &c.ctas_per_sm, &c.unroll);
+        if (c.threads < 32 || c.threads > 256 || (c.threads & 31)) c.threads = 256;
+        if (c.ctas_per_sm < 1 || c.ctas_per_sm > 8) c.ctas_per_sm = 8;   // partial buffers hold 148 * 8 CTAs
+        if (c.unroll != 1 && c.unroll != 2 && c.unroll != 4) c.unroll = 2;
+        return c;
+    }();
+    return cfg;
+}
+
 template <int DOTS>
 static int launch_spmv(const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
                        const double* sys, const double* x, double* y, const double* w, double* partials,
                        const int* ictl, int* n_cta_out, cudaStream_t st) {
-    const int g = grid_for(4 * (int64_t)n_rows, SPMV_THREADS);
+    const SpmvCfg& c = spmv_cfg();
+    int64_t g64 = ceil_div(4 * (int64_t)n_rows, c.threads);
+    if (g64 > 148 * c.ctas_per_sm) g64 = 148 * c.ctas_per_sm;
+    const int g = g64 < 1 ? 1 : (int)g64;
     if (n_cta_out) *n_cta_out = g;
-    spmv_kernel<DOTS><<<g, SPMV_THREADS, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
+    if (c.unroll == 4) spmv_kernel<DOTS, 4><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
+    else if (c.unroll == 1) spmv_kernel<DOTS, 1><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
+    else spmv_kernel<DOTS, 2><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }

@@ -31,8 +31,8 @@ from dataclasses import dataclass
 import torch
 
 ITEMS_PER_CTA = 256          # = ASM_THREADS of tefem_assemble.cu
-ELEM_BUDGET_PER_CTA = 600    # bound on the sum of node degrees per tile (>= staged elements)
-MAX_CHUNK = 6                # lists longer than 2 * MAX_CHUNK are split into chunks of <= MAX_CHUNK
+ELEM_BUDGET_PER_CTA = 330    # bound on the sum of node degrees per tile (>= staged elements; ~256 on Kuhn meshes)
+MAX_CHUNK = 8                # lists longer than 2 * MAX_CHUNK are split into chunks of <= MAX_CHUNK
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
 HDR_STRIDE = 12

@@ -315,3 +315,58 @@ def test_two_gpu_transient_matches_single_gpu():
            "--master-port", "29617", os.path.join(root, "tools", "dist_check.py"), "16", "2"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_steady_state_synthetic_sandwich_vs_refined_oracle():
+    """BASELINE config 3 in miniature: Kuhn sandwich (three different layer materials), config-1 boundary conditions,
+    against the oracle's LU + iterative refinement."""
+    from thermoelasticity_fem_b200 import Model, LinearSteadyState
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    from oracle import tefem_oracle as orc
+    pts, tets, tris, nodes = kuhn_box(24, 6, 6)
+    groups = dict(tet=tets, tri=tris, nodes=nodes)
+    mesh = make_mesh(pts, groups, KUHN_MATS)
+    dU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('x', 0.), ('y', 0.), ('z', 0.)]}
+    dT = {4: 0., 5: 0.}
+    model = Model(mesh, dict_dirichlet_U=dU, dict_dirichlet_theta=dT, dict_surface_forces={7: np.array([0., 0., -1e9])},
+                  dict_heat_flux={6: -25.})
+    solver = LinearSteadyState(model)
+    solver.solve()
+    X, info = orc.steady_state(pts, groups, {k: orc.Material(*v) for k, v in KUHN_MATS.items()}, dU, dT,
+                               dict(surface={7: np.array([0., 0., -1e9])}, flux={6: -25.}))
+    K = model.touched("K")
+    parity.check_pattern(K, None, info["K"])
+    assert parity.scaled_error(K, info["K"]) < parity.VALUE_TOL
+    eu, et = parity.field_errors(solver.X, X)
+    assert eu < parity.SOLUTION_TOL and et < parity.SOLUTION_TOL, (eu, et)
+    # reference temperature = mean of T0 over the materials touching a node (solvers.py:51-60)
+    T0 = orc.reference_temperature(pts.shape[0], tets, {k: orc.Material(*v) for k, v in KUHN_MATS.items()})
+    assert np.allclose(solver.T, X[3::4] + T0, rtol=0, atol=1e-6 * np.abs(X[3::4]).max())
+
+
+def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
+    """BASELINE config 2 end to end (999 steps, public API, full histories) against the states the UNMODIFIED reference
+    produced (tests/golden/sandwich_transient2.npz).  The reference re-solves with raw spsolve every step: its own theta
+    carries ~5e-7 of error per solve, so the comparison is at 1e-6 (u) / 1e-4 (theta) after 999 steps."""
+    from thermoelasticity_fem_b200 import Model, LinearTransient
+    g = golden("sandwich_transient2.npz")
+    t_end, n_t = 1800e0, 1000
+    vec_t = np.linspace(0., t_end, n_t)
+    arr = np.zeros((3, n_t))
+    arr[0, :] = np.sin(2 * np.pi * vec_t / 900.) * -1e9
+    model = Model(sandwich_mesh2, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
+                  dict_dirichlet_theta={4: 0., 5: 0.}, dict_surface_forces={5: arr}, alpha_M=2e-1, alpha_K=2e-1)
+    N = sandwich_mesh2.n_nodes
+    solver = LinearTransient(model, np.zeros(3 * N), np.zeros(3 * N), np.zeros(N), np.zeros(N), t_end, n_t, 0.5, 0.25,
+                             progress=False)
+    solver.solve()
+    assert solver.X.shape == (4 * N, n_t) and solver.U.shape == (3 * N, n_t) and solver.T.shape == (N, n_t)
+    assert solver.dt == float(g["dt"])
+    for col, step in enumerate(g["steps"]):
+        eu, et = parity.field_errors(solver.X[:, int(step)], g["X"][:, col])
+        assert eu < 1e-6 and et < 1e-4, (int(step), eu, et)
+        ev, _ = parity.field_errors(solver.Xdot[:, int(step)], g["Xdot"][:, col])
+        assert ev < 1e-5, (int(step), ev)
+        assert np.max(np.abs(solver.T[:, int(step)] - g["T"][:, col])) < 1e-4 * np.abs(g["T"][:, col]).max()
+    assert abs(np.abs(solver.U).max() - float(g["maxU"])) < 1e-8 * float(g["maxU"])
+    assert abs(np.abs(solver.X[3::4]).max() - float(g["maxTheta"])) < 1e-6 * float(g["maxTheta"])

@@ -25,6 +25,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("TEFEM_NVCC_EXTRA", "").split()      # experiments only (e.g. -DTEFEM_EXP_...)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "tefem.h"))
     objs = []
@@ -33,7 +34,7 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(PKG, "build", src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.run(cmd, check=True)
         objs.append(o)
     if force or _stale(LIB, objs):

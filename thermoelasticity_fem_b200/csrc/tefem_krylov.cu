@@ -28,6 +28,13 @@
 namespace tefem {
 
 constexpr int SPMV_THREADS = 256;
+// 4 resident CTAs per SM (<= 64 registers) and a grid of exactly one resident wave: ncu showed spmv<1> at 66
+// registers -> 3 CTAs per SM, 2.67 waves of the old 1184-CTA grid and a 13 % longer launch than spmv<8> (64
+// registers).  5 CTAs per SM (48 registers) spills and is slower: live 2.61 ms vs 2.43 ms at config B
+// (profiles/README.md).
+#ifndef SPMV_MIN_CTAS
+#define SPMV_MIN_CTAS 4
+#endif
 constexpr int MAX_PARTIAL_CTAS = 148 * 8;   // grid of the reducing kernels: 8 CTAs of 256 threads per SM
 constexpr int NSCAL = 24;
 
@@ -51,7 +58,7 @@ __device__ __forceinline__ void ld256_x(const double* p, double& a, double& b, d
 // s = x (owned part) and the first three split by field (u rows r < 3, theta rows r == 3).
 // rows: optional list of node rows (interior / boundary split), else rows [0, n_rows).
 template <int DOTS, int UNROLL>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ colidx,
                                                             const int32_t* __restrict__ rows, int32_t n_rows,
                                                             const double* __restrict__ sys, const double* __restrict__ x,
@@ -484,20 +491,48 @@ static const SpmvCfg& spmv_cfg() {
     return cfg;
 }
 
+template <int DOTS, int UNROLL>
+static int spmv_resident_ctas(int threads, int* out) {
+    static int cached_threads = 0, cached = 0;
+    if (cached_threads != threads) {
+        int occ = 0, dev = 0, sms = 0;
+        TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_kernel<DOTS, UNROLL>, threads, 0));
+        TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
+        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cached = (occ < 1 ? 1 : occ) * sms;
+        cached_threads = threads;
+    }
+    *out = cached;
+    return TEFEM_OK;
+}
+
+template <int DOTS, int UNROLL>
+static int launch_spmv_u(const SpmvCfg& c, const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
+                         const double* sys, const double* x, double* y, const double* w, double* partials,
+                         const int* ictl, int* n_cta_out, cudaStream_t st) {
+    // one resident wave of grid-striding CTAs (no tail), capped by the partial-sum buffers
+    int resident = 0;
+    int rc = spmv_resident_ctas<DOTS, UNROLL>(c.threads, &resident);
+    if (rc) return rc;
+    if (c.ctas_per_sm > 0 && resident > 148 * c.ctas_per_sm) resident = 148 * c.ctas_per_sm;
+    if (resident > MAX_PARTIAL_CTAS) resident = MAX_PARTIAL_CTAS;
+    int64_t g64 = ceil_div(4 * (int64_t)n_rows, c.threads);
+    if (g64 > resident) g64 = resident;
+    const int g = g64 < 1 ? 1 : (int)g64;
+    if (n_cta_out) *n_cta_out = g;
+    spmv_kernel<DOTS, UNROLL><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
 template <int DOTS>
 static int launch_spmv(const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
                        const double* sys, const double* x, double* y, const double* w, double* partials,
                        const int* ictl, int* n_cta_out, cudaStream_t st) {
     const SpmvCfg& c = spmv_cfg();
-    int64_t g64 = ceil_div(4 * (int64_t)n_rows, c.threads);
-    if (g64 > 148 * c.ctas_per_sm) g64 = 148 * c.ctas_per_sm;
-    const int g = g64 < 1 ? 1 : (int)g64;
-    if (n_cta_out) *n_cta_out = g;
-    if (c.unroll == 4) spmv_kernel<DOTS, 4><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
-    else if (c.unroll == 1) spmv_kernel<DOTS, 1><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
-    else spmv_kernel<DOTS, 2><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
-    TEFEM_LAUNCH_CHECK();
-    return TEFEM_OK;
+    if (c.unroll == 4) return launch_spmv_u<DOTS, 4>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl, n_cta_out, st);
+    if (c.unroll == 1) return launch_spmv_u<DOTS, 1>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl, n_cta_out, st);
+    return launch_spmv_u<DOTS, 2>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl, n_cta_out, st);
 }
 
 // Exchange the halo part of x (owned rows listed in send_idx go out, halo rows come in).

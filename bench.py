@@ -209,9 +209,16 @@ def run_tefem(args):
     spmv_bytes = 8 * 16 * P_loc + 4 * P_loc + 4 * (N_own + 1) + 16 * 4 * N_own
     spmv_avg_ms = max_over_ranks(spmv_ms / max(spmv_count, 1))
     spmv_gbs = spmv_bytes / spmv_avg_ms / 1e6
+    traffic = None      # DRAM bytes per launch from the committed ncu --set full capture of this very command
+    tpath = os.path.join(ROOT, "profiles", "r1_spmv_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if tj["workload"] == {"cells": args.cells, "n_gpus": world}:
+            traffic = tj["traffic_bytes_per_launch_mean"]
     roofline = {"bound": "hbm", "kernel": "spmv_kernel (4x4-block SpMV of the Krylov iteration, fused dot partials)",
                 "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
-                "peak_source": peak_src, "traffic": None, "launches_timed": int(spmv_count),
+                "peak_source": peak_src, "traffic": traffic, "launches_timed": int(spmv_count),
                 "avg_launch_ms": spmv_avg_ms, "algorithmic_bytes_per_launch": spmv_bytes,
                 "share_of_step": spmv_ms / ms_total}
 

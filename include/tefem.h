@@ -181,6 +181,28 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
                           const int32_t* boundary_rows, int32_t n_boundary_rows,
                           const int32_t* interior_rows, int32_t n_interior_rows);
 
+/* Aggregation-based coarse correction, used as the right preconditioner of tefem_bicgstab on top of the block-Jacobi
+ * scaling: z = omega r + P1 M1(P1^T r) on the scaled system, with a replicated 4x4-block level 1 (one V-cycle with
+ * damped Jacobi) and a dense level 2 (csrc/tefem_precond.cu).  The reference has no counterpart (spsolve is a direct
+ * solve, solvers.py:26,172).  All arrays are built by the host side (multilevel.py) and owned by the caller:
+ *   agg_ptr[n_coarse+1], agg_nodes[n_rows]: owned fine node rows grouped by aggregate; node_agg[n_rows]: aggregate of
+ *   each owned fine node; rowptr1 / colidx1 / sys1 / dinv1: block-Jacobi-scaled Galerkin operator of level 1 and the
+ *   inverses of its diagonal blocks; agg2_* / node_agg2: aggregation of the level-1 nodes; inv2: dense row-major
+ *   inverse [4 n_coarse2, 4 n_coarse2] of the level-2 Galerkin operator (n_coarse2 = 0: two levels only);
+ *   work: tefem_precond_work_doubles(n_coarse, n_coarse2) doubles, 128-byte aligned; comm: tefem_comm* or NULL
+ *   (the restricted residual is all-reduced, levels 1 and 2 are replicated on every rank).                      */
+typedef struct tefem_precond tefem_precond;
+int64_t tefem_precond_work_doubles(int32_t n_coarse, int32_t n_coarse2);
+int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_coarse, const int32_t* agg_ptr,
+                         const int32_t* agg_nodes, const int32_t* node_agg, double omega,
+                         const int32_t* rowptr1, const int32_t* colidx1, const double* sys1, const double* dinv1,
+                         double omega_c, int32_t n_coarse2, const int32_t* agg2_ptr, const int32_t* agg2_nodes,
+                         const int32_t* node_agg2, const double* inv2, double* work, void* comm);
+int tefem_precond_destroy(tefem_precond* pc);
+int tefem_precond_apply(tefem_precond* pc, const double* r, double* z, void* stream);
+/* Attach (or detach with NULL) a preconditioner to the Krylov driver. */
+int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc);
+
 /* Fills the halo part of x (rows n_rows .. n_rows + n_halo) with the owners' values: pack kernel +
  * grouped ncclSend/ncclRecv on `stream`.  No-op without a communicator.                          */
 int tefem_solver_halo_exchange(tefem_solver* s, double* x, void* stream);

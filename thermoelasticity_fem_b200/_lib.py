@@ -37,6 +37,10 @@ _SIGNATURES = {
     "tefem_solver_destroy": [P],
     "tefem_solver_profile": [P, c_int, P, P],
     "tefem_solver_halo_exchange": [P, P, P],
+    "tefem_solver_set_precond": [P, P],
+    "tefem_precond_create": [P, c_int32, c_int32, P, P, P, c_double, P, P, P, P, c_double, c_int32, P, P, P, P, P, P],
+    "tefem_precond_destroy": [P],
+    "tefem_precond_apply": [P, P, P, P],
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
@@ -48,7 +52,8 @@ _SIGNATURES = {
     "tefem_comm_destroy": [P],
     "tefem_comm_allreduce_sum": [P, P, c_int, P],
 }
-_RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32]), "tefem_launch_count": (c_int64, [])}
+_RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32]), "tefem_launch_count": (c_int64, []),
+             "tefem_precond_work_doubles": (c_int64, [c_int32, c_int32])}
 
 _lib = None
 

@@ -20,6 +20,7 @@
 // results are bitwise reproducible for a given grid.
 #include "tefem_common.cuh"
 #include "tefem_comm.h"
+#include "tefem_precond.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -55,7 +56,8 @@ __device__ __forceinline__ void ld256_x(const double* p, double& a, double& b, d
 
 // y = A x over node rows; 4 consecutive threads own the 4 scalar rows of a node.
 // DOTS = 0: none; 1: partial of (w . y); 8: partials of (y.s_u, y.s_t, y.y_u, y.y_t, s.s_u, s.s_t, w.s, w.y) with
-// s = x (owned part) and the first three split by field (u rows r < 3, theta rows r == 3).
+// s = sd (the un-preconditioned vector whose image y is; sd == x without a preconditioner) and the first three
+// split by field (u rows r < 3, theta rows r == 3).
 // rows: optional list of node rows (interior / boundary split), else rows [0, n_rows).
 template <int DOTS, int UNROLL>
 __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const int32_t* __restrict__ rowptr,
@@ -63,7 +65,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const
                                                             const int32_t* __restrict__ rows, int32_t n_rows,
                                                             const double* __restrict__ sys, const double* __restrict__ x,
                                                             double* __restrict__ y, const double* __restrict__ w,
-                                                            double* __restrict__ partials, const int* __restrict__ ictl) {
+                                                            const double* __restrict__ sd, double* __restrict__ partials,
+                                                            const int* __restrict__ ictl) {
     __shared__ double red[8 * 32];
     double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const
             y[row] = yv;
             if (DOTS == 1) d[0] += w[row] * yv;
             if (DOTS == 8) {
-                const double sv = x[row], wv = w[row];
+                const double sv = sd[row], wv = w[row];
                 d[0] += yv * sv; d[1] += yv * yv; d[2] += sv * sv; d[3] += wv * sv; d[4] += wv * yv;
             }
         }
@@ -245,17 +248,19 @@ __global__ void __launch_bounds__(256) update_s_kernel(int64_t n, const double* 
         s[k] = r[k] - alpha * v[k];
 }
 
-// x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)
+// x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v)
+// (ph = N p, sh = N s: the right-preconditioned directions; ph == p, sh == s without a preconditioner)
 __global__ void __launch_bounds__(256) update_xrp_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
                                                          double* __restrict__ p, const double* __restrict__ s,
                                                          const double* __restrict__ t, const double* __restrict__ v,
+                                                         const double* __restrict__ ph, const double* __restrict__ sh,
                                                          const double* __restrict__ sc, const int* __restrict__ ictl,
                                                          int iter) {
     if (ictl[IN_STOP] && ictl[IN_STOP_ITER] != iter) return;
     const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA], beta = sc[SC_BETA];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const double pv = p[k], sv = s[k];
-        x[k] += alpha * pv + omega * sv;
+        x[k] += alpha * ph[k] + omega * sh[k];
         const double rv = sv - omega * t[k];
         r[k] = rv;
         p[k] = rv + beta * (pv - omega * v[k]);
@@ -333,6 +338,8 @@ struct tefem_solver {
     int64_t n_own = 0, n_loc = 0;   // scalar sizes: owned, owned + halo
     double* work = nullptr;
     double *r = nullptr, *rhat = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;
+    double *ph = nullptr, *sh = nullptr;   // preconditioned directions (used only with a preconditioner)
+    tefem_precond* pc = nullptr;
     double *partials = nullptr, *sc = nullptr, *sendbuf = nullptr;
     int* ictl = nullptr;
     int* h_ictl = nullptr;      // pinned
@@ -393,7 +400,7 @@ static int64_t align16(int64_t n) { return (n + 15) / 16 * 16; }   // keep every
 
 extern "C" int64_t tefem_solver_work_doubles(int32_t n_rows, int32_t n_halo) {
     const int64_t nl = align16(vec_len(n_rows, n_halo));
-    return 6 * nl + align16((int64_t)MAX_PARTIAL_CTAS * 2 * 8) + align16(NSCAL) + align16(16) + align16(4 * (int64_t)n_rows);
+    return 8 * nl + align16((int64_t)MAX_PARTIAL_CTAS * 2 * 8) + align16(NSCAL) + align16(16) + align16(4 * (int64_t)n_rows);
 }
 
 extern "C" int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n_halo, double* work, void* comm) {
@@ -406,6 +413,7 @@ extern "C" int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n
     const int64_t nl = align16(s->n_loc);
     double* w = work;
     s->r = w; w += nl; s->rhat = w; w += nl; s->p = w; w += nl; s->v = w; w += nl; s->s = w; w += nl; s->t = w; w += nl;
+    s->ph = w; w += nl; s->sh = w; w += nl;
     s->partials = w; w += align16((int64_t)MAX_PARTIAL_CTAS * 2 * 8);
     s->sc = w; w += align16(NSCAL);
     s->ictl = reinterpret_cast<int*>(w); w += align16(16);
@@ -508,7 +516,7 @@ static int spmv_resident_ctas(int threads, int* out) {
 
 template <int DOTS, int UNROLL>
 static int launch_spmv_u(const SpmvCfg& c, const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
-                         const double* sys, const double* x, double* y, const double* w, double* partials,
+                         const double* sys, const double* x, double* y, const double* w, const double* sd, double* partials,
                          const int* ictl, int* n_cta_out, cudaStream_t st) {
     // one resident wave of grid-striding CTAs (no tail), capped by the partial-sum buffers
     int resident = 0;
@@ -520,19 +528,19 @@ static int launch_spmv_u(const SpmvCfg& c, const int32_t* rowptr, const int32_t*
     if (g64 > resident) g64 = resident;
     const int g = g64 < 1 ? 1 : (int)g64;
     if (n_cta_out) *n_cta_out = g;
-    spmv_kernel<DOTS, UNROLL><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl);
+    spmv_kernel<DOTS, UNROLL><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, sd ? sd : x, partials, ictl);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
 
 template <int DOTS>
 static int launch_spmv(const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
-                       const double* sys, const double* x, double* y, const double* w, double* partials,
+                       const double* sys, const double* x, double* y, const double* w, const double* sd, double* partials,
                        const int* ictl, int* n_cta_out, cudaStream_t st) {
     const SpmvCfg& c = spmv_cfg();
-    if (c.unroll == 4) return launch_spmv_u<DOTS, 4>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl, n_cta_out, st);
-    if (c.unroll == 1) return launch_spmv_u<DOTS, 1>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl, n_cta_out, st);
-    return launch_spmv_u<DOTS, 2>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, partials, ictl, n_cta_out, st);
+    if (c.unroll == 4) return launch_spmv_u<DOTS, 4>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, st);
+    if (c.unroll == 1) return launch_spmv_u<DOTS, 1>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, st);
+    return launch_spmv_u<DOTS, 2>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, st);
 }
 
 // Exchange the halo part of x (owned rows listed in send_idx go out, halo rows come in).
@@ -550,11 +558,11 @@ static int halo_exchange(tefem_solver* s, double* x, const int* ictl, cudaStream
 // y = A x with the halo exchange of x overlapped with the interior rows; DOTS partials packed.
 template <int DOTS>
 static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys, double* x,
-                     double* y, const double* w, const int* ictl, int* n_part_ctas, cudaStream_t st) {
+                     double* y, const double* w, const double* sd, const int* ictl, int* n_part_ctas, cudaStream_t st) {
     if (!s->comm || s->n_nbr == 0) {
         int rc0 = prof_begin(s, st);
         if (rc0) return rc0;
-        rc0 = launch_spmv<DOTS>(rowptr, colidx, nullptr, s->n_rows, sys, x, y, w, s->partials, ictl, n_part_ctas, st);
+        rc0 = launch_spmv<DOTS>(rowptr, colidx, nullptr, s->n_rows, sys, x, y, w, sd, s->partials, ictl, n_part_ctas, st);
         if (rc0) return rc0;
         return prof_end(s, st);
     }
@@ -568,12 +576,12 @@ static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* coli
     TEFEM_CUDA_CHECK(cudaEventRecord(s->ev_halo, s->comm_stream));
     int g0 = 0, g1 = 0;
     if (s->n_interior_rows > 0) {
-        rc = launch_spmv<DOTS>(rowptr, colidx, s->interior_rows, s->n_interior_rows, sys, x, y, w, s->partials, ictl, &g0, st);
+        rc = launch_spmv<DOTS>(rowptr, colidx, s->interior_rows, s->n_interior_rows, sys, x, y, w, sd, s->partials, ictl, &g0, st);
         if (rc) return rc;
     }
     TEFEM_CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_halo, 0));
     if (s->n_boundary_rows > 0) {
-        rc = launch_spmv<DOTS>(rowptr, colidx, s->boundary_rows, s->n_boundary_rows, sys, x, y, w,
+        rc = launch_spmv<DOTS>(rowptr, colidx, s->boundary_rows, s->n_boundary_rows, sys, x, y, w, sd,
                                s->partials + (size_t)g0 * (DOTS > 0 ? DOTS : 1), ictl, &g1, st);
         if (rc) return rc;
     }
@@ -589,6 +597,12 @@ static int reduce_to_packet(tefem_solver* s, int n_cta, cudaStream_t st) {
     return TEFEM_OK;
 }
 
+extern "C" int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc) {
+    TEFEM_REQUIRE(s, "null solver");
+    s->pc = pc;
+    return TEFEM_OK;
+}
+
 extern "C" int tefem_solver_halo_exchange(tefem_solver* s, double* x, void* stream) {
     TEFEM_REQUIRE(s && x, "null pointer");
     return halo_exchange(s, x, nullptr, as_stream(stream));
@@ -599,7 +613,7 @@ extern "C" int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t 
     TEFEM_REQUIRE(rowptr && colidx && sys && x && y, "null pointer");
     TEFEM_REQUIRE((((uintptr_t)sys) & 127) == 0 && (((uintptr_t)x) & 31) == 0, "sys / x alignment");
     if (n_rows == 0) return TEFEM_OK;
-    return launch_spmv<0>(rowptr, colidx, nullptr, n_rows, sys, x, y, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
+    return launch_spmv<0>(rowptr, colidx, nullptr, n_rows, sys, x, y, nullptr, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
 }
 
 extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys,
@@ -621,7 +635,7 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
     for (;;) {
         // ---- (re)start: r = b - A x, rhat = p = r
         int npc = 0;
-        int rc = dist_spmv<0>(s, rowptr, colidx, sys, x, s->t, nullptr, nullptr, &npc, st);
+        int rc = dist_spmv<0>(s, rowptr, colidx, sys, x, s->t, nullptr, nullptr, nullptr, &npc, st);
         if (rc) return rc;
         init_residual_kernel<<<vgrid, 256, 0, st>>>(n, b, s->t, x, s->r, s->rhat, s->p, s->partials);
         TEFEM_LAUNCH_CHECK();
@@ -655,7 +669,13 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         while (!stopped && total_iters + it < max_iter) {
             const int batch_end = it + check_every;
             for (; it < batch_end && total_iters + it < max_iter; ++it) {
-                rc = dist_spmv<1>(s, rowptr, colidx, sys, s->p, s->v, s->rhat, s->ictl, &npc, st);
+                double* pdir = s->p;      // direction fed to the operator: p, or N p with a preconditioner
+                if (s->pc) {
+                    rc = tefem_precond_apply_stream(s->pc, s->p, s->ph, st);
+                    if (rc) return rc;
+                    pdir = s->ph;
+                }
+                rc = dist_spmv<1>(s, rowptr, colidx, sys, pdir, s->v, s->rhat, nullptr, s->ictl, &npc, st);
                 if (rc) return rc;
                 rc = reduce_to_packet<1>(s, npc, st);
                 if (rc) return rc;
@@ -663,13 +683,19 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
                 TEFEM_LAUNCH_CHECK();
                 update_s_kernel<<<vgrid, 256, 0, st>>>(n, s->r, s->v, s->s, s->sc, s->ictl);
                 TEFEM_LAUNCH_CHECK();
-                rc = dist_spmv<8>(s, rowptr, colidx, sys, s->s, s->t, s->rhat, s->ictl, &npc, st);
+                double* sdir = s->s;
+                if (s->pc) {
+                    rc = tefem_precond_apply_stream(s->pc, s->s, s->sh, st);
+                    if (rc) return rc;
+                    sdir = s->sh;
+                }
+                rc = dist_spmv<8>(s, rowptr, colidx, sys, sdir, s->t, s->rhat, s->s, s->ictl, &npc, st);
                 if (rc) return rc;
                 rc = reduce_to_packet<8>(s, npc, st);
                 if (rc) return rc;
                 scalars_omega_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, it, rtol2);
                 TEFEM_LAUNCH_CHECK();
-                update_xrp_kernel<<<vgrid, 256, 0, st>>>(n, x, s->r, s->p, s->s, s->t, s->v, s->sc, s->ictl, it);
+                update_xrp_kernel<<<vgrid, 256, 0, st>>>(n, x, s->r, s->p, s->s, s->t, s->v, pdir, sdir, s->sc, s->ictl, it);
                 TEFEM_LAUNCH_CHECK();
             }
             TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -200,6 +200,11 @@ class KrylovSolver:
         _lib.check(rc)
         return self.last_info
 
+    def set_precond(self, pc):
+        """Attach a TwoLevelPreconditioner (multilevel.py) as right preconditioner, or detach with None."""
+        self._pc = pc
+        _lib.check(self.lib.tefem_solver_set_precond(self.handle, pc.handle if pc is not None else None))
+
     def profile(self, enable=None):
         """SpMV device time accumulated by the driver: returns (ms, count); enable True/False resets."""
         ms, cnt = ctypes.c_double(), ctypes.c_int64()

@@ -113,13 +113,13 @@ class DistributedTransient:
 
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
                  alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=64,
-                 comm=None):
+                 comm=None, precond="multilevel"):
         self.lp, self.comm = lp, comm
         self.alpha_M, self.alpha_K = alpha_M, alpha_K
         self.gamma, self.beta = gamma, beta
         self.t_end, self.n_t = t_end, n_t
         self.dt = t_end / (n_t - 1)
-        self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
+        self.rtol, self.max_iter, self.check_every, self.precond_kind = rtol, max_iter, check_every, precond
         table = np.array([m.table_row() for m in materials])
         self.dm = DeviceMesh(coords_local, lp.conn, mat_id_local, table, n_rows=lp.n_own)
         self.n_halo = lp.n_halo
@@ -160,6 +160,11 @@ class DistributedTransient:
         self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
         self.dinv = dm.block_jacobi_scale(self.sys)
         self.krylov = KrylovSolver(dm, lp.n_halo, self.comm)
+        self.precond = None
+        if self.precond_kind == "multilevel":
+            from .multilevel import TwoLevelPreconditioner
+            self.precond = TwoLevelPreconditioner(dm, self.sys, comm=self.comm)
+            self.krylov.set_precond(self.precond)
         i32 = torch.int32
         self.krylov.set_halo(lp.nbr, lp.send_ptr, torch.from_numpy(lp.send_idx.astype(np.int32)).to(dev), lp.recv_ptr,
                              torch.from_numpy(lp.boundary_rows.astype(np.int32)).to(dev),

@@ -36,7 +36,7 @@ def _deinterleave(X, n_nodes):
 class _SystemSolve:
     """Shared by both solvers: forms the eliminated, block-Jacobi-scaled system and solves with it."""
 
-    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every):
+    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="multilevel"):
         self.model = model
         self.dm = model.mesh.device_mesh()
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
@@ -46,6 +46,15 @@ class _SystemSolve:
         self.sys = self.dm.form_system(planes, cM, cD, cK, d_layout, model._dir_mask)
         self.dinv = self.dm.block_jacobi_scale(self.sys)
         self.krylov = KrylovSolver(self.dm)
+        # right preconditioner on top of the block-Jacobi scaling: aggregation coarse correction (multilevel.py);
+        # precond="block_jacobi" keeps the scaling alone
+        self.precond = None
+        if precond == "multilevel":
+            from .multilevel import TwoLevelPreconditioner
+            self.precond = TwoLevelPreconditioner(self.dm, self.sys)
+            self.krylov.set_precond(self.precond)
+        elif precond != "block_jacobi":
+            raise ValueError("precond must be 'multilevel' or 'block_jacobi'")
         self.b = torch.empty(model.mesh.n_dofs, dtype=torch.float64, device=self.dm.device)
         self.info = []
 
@@ -60,9 +69,9 @@ class _SystemSolve:
 class LinearSteadyState:
     """Steady-state solver for linear thermoelasticity (reference solvers.py:8-66)."""
 
-    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32):
+    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="multilevel"):
         self.model = model
-        self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
+        self.rtol, self.max_iter, self.check_every, self.precond = rtol, max_iter, check_every, precond
         self.X = None
         self.U = None
         self.T = None
@@ -80,9 +89,10 @@ class LinearSteadyState:
         m.apply_dirichlet_F()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every)
+        ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every, self.precond)
         x = torch.zeros(m.mesh.n_dofs, dtype=torch.float64, device=ss.dm.device)
         self.solve_info = ss.solve(m.rhs_device(), x)
+        x.masked_fill_(m._dir_mask.bool(), 0.0)   # eliminated unknowns (a coarse correction may leave round-off there)
         x += m._g_fill                       # prescribed values on the constrained DOFs (solvers.py:27-49)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
@@ -106,7 +116,7 @@ class LinearTransient:
                  t_end, n_t,
                  gamma=0.5, beta=0.25,
                  rtol=1e-10, max_iter=50000, check_every=32, history='full', warm_start=True, guess_order=0,
-                 on_step=None, progress=True):
+                 on_step=None, progress=True, precond="multilevel"):
         self.model = model
         self.gamma = gamma
         self.beta = beta
@@ -122,6 +132,7 @@ class LinearTransient:
 
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
         self.history, self.warm_start, self.on_step, self.progress = history, warm_start, on_step, progress
+        self.precond = precond
         # initial guess of each solve: 0 (warm_start=False) or the previous accelerations extrapolated in time
         # with a polynomial of degree guess_order (0 = previous acceleration, 1 = linear, 2 = quadratic).
         # Measured on the B200 (sandwich mesh and the 100^3 box): the iteration count of block-Jacobi BiCGSTAB
@@ -173,7 +184,8 @@ class LinearTransient:
         self._a = torch.zeros(n, dtype=torch.float64, device=dev)     # initial acceleration assumed zero (:131)
         self._x0_full, self._v0_full = x0, v0
         dt = self.dt
-        self._ss = _SystemSolve(m, 1.0, self.gamma * dt, self.beta * dt ** 2, self.rtol, self.max_iter, self.check_every)
+        self._ss = _SystemSolve(m, 1.0, self.gamma * dt, self.beta * dt ** 2, self.rtol, self.max_iter, self.check_every,
+                                self.precond)
         self._w1 = torch.empty_like(self._x)
         self._w2 = torch.empty_like(self._x)
         self._rhs = torch.empty_like(self._x)

@@ -24,6 +24,9 @@ except ImportError:                     # pragma: no cover
         return it
 
 
+MULTILEVEL_MIN_NODES = 20000     # below this the iteration is launch-latency bound and block-Jacobi alone is faster
+
+
 def _deinterleave(X, n_nodes):
     """reference solvers.py:62-66 / 188-202: X (4N[, n_t]) -> U (3N[, n_t]), theta (N[, n_t])."""
     U = np.zeros((n_nodes * 3,) + X.shape[1:])
@@ -36,7 +39,7 @@ def _deinterleave(X, n_nodes):
 class _SystemSolve:
     """Shared by both solvers: forms the eliminated, block-Jacobi-scaled system and solves with it."""
 
-    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="multilevel"):
+    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="auto"):
         self.model = model
         self.dm = model.mesh.device_mesh()
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
@@ -49,12 +52,14 @@ class _SystemSolve:
         # right preconditioner on top of the block-Jacobi scaling: aggregation coarse correction (multilevel.py);
         # precond="block_jacobi" keeps the scaling alone
         self.precond = None
+        if precond == "auto":      # the coarse correction pays off once the iteration is bandwidth- not launch-bound
+            precond = "multilevel" if self.dm.n_nodes >= MULTILEVEL_MIN_NODES else "block_jacobi"
         if precond == "multilevel":
             from .multilevel import TwoLevelPreconditioner
             self.precond = TwoLevelPreconditioner(self.dm, self.sys)
             self.krylov.set_precond(self.precond)
         elif precond != "block_jacobi":
-            raise ValueError("precond must be 'multilevel' or 'block_jacobi'")
+            raise ValueError("precond must be 'auto', 'multilevel' or 'block_jacobi'")
         self.b = torch.empty(model.mesh.n_dofs, dtype=torch.float64, device=self.dm.device)
         self.info = []
 
@@ -69,7 +74,7 @@ class _SystemSolve:
 class LinearSteadyState:
     """Steady-state solver for linear thermoelasticity (reference solvers.py:8-66)."""
 
-    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="multilevel"):
+    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="auto"):
         self.model = model
         self.rtol, self.max_iter, self.check_every, self.precond = rtol, max_iter, check_every, precond
         self.X = None
@@ -116,7 +121,7 @@ class LinearTransient:
                  t_end, n_t,
                  gamma=0.5, beta=0.25,
                  rtol=1e-10, max_iter=50000, check_every=32, history='full', warm_start=True, guess_order=0,
-                 on_step=None, progress=True, precond="multilevel"):
+                 on_step=None, progress=True, precond="auto"):
         self.model = model
         self.gamma = gamma
         self.beta = beta

@@ -109,6 +109,9 @@ class TwoLevelPreconditioner:
         else:
             k = uniq
             ijk = np.stack([k // (int(dims1[1]) * int(dims1[2])), (k // int(dims1[2])) % int(dims1[1]), k % int(dims1[2])], axis=1)
+            if factor2 <= 0:      # automatic: keep the dense level-2 operator at a few hundred nodes
+                factor2 = max(3.0, float(np.ceil((n1 / 450.0) ** (1.0 / 3.0))))
+            self.factor2 = factor2
             c = np.floor(ijk / factor2 + 1e-9).astype(np.int64)
             d2 = c.max(axis=0) + 1
             key2 = (c[:, 0] * d2[1] + c[:, 1]) * d2[2] + c[:, 2]

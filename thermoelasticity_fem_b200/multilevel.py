@@ -47,7 +47,7 @@ def _grid_keys(xyz, lo, H, dims):
 class TwoLevelPreconditioner:
     """Owns the device arrays of one preconditioner and its C handle (attach with KrylovSolver.set_precond)."""
 
-    def __init__(self, dm, sys, comm=None, factor1=8.0, factor2=4.0, omega=0.7, omega_c=0.6, dense_limit=300):
+    def __init__(self, dm, sys, comm=None, factor1=4.0, factor2=0.0, omega=1.0, omega_c=0.8, dense_limit=300):
         import os
         if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c"
             factor1, factor2, omega, omega_c = (float(v) for v in os.environ["TEFEM_ML"].split(","))

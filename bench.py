@@ -110,7 +110,7 @@ def build_case(cells, rank=0, world=1):
                   alpha_M=ALPHA_M, alpha_K=ALPHA_K)
     n = mesh.n_nodes
     solver = LinearTransient(model, np.zeros(3 * n), np.zeros(3 * n), np.zeros(n), np.zeros(n), T_END, N_T, 0.5, 0.25,
-                             rtol=RTOL, history='last', progress=False, check_every=64)
+                             rtol=RTOL, history='last', progress=False, check_every=16)
     return mesh, model, solver
 
 

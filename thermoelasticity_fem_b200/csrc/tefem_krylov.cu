@@ -382,9 +382,10 @@ static int prof_end(tefem_solver* s, cudaStream_t st) {
     s->ev_used += 2;
     return TEFEM_OK;
 }
-// call only after the stream has been synchronised
-static int prof_harvest(tefem_solver* s) {
-    for (size_t k = 0; k + 1 < s->ev_used; k += 2) {
+// call only after the stream has been synchronised; only the first n_valid SpMVs of the batch did real work (the
+// launches queued after the stop flag was raised return immediately and must not dilute the average)
+static int prof_harvest(tefem_solver* s, size_t n_valid) {
+    for (size_t k = 0; k + 1 < s->ev_used && k / 2 < n_valid; k += 2) {
         float ms = 0.f;
         TEFEM_CUDA_CHECK(cudaEventElapsedTime(&ms, s->ev_pool[k], s->ev_pool[k + 1]));
         s->spmv_ms += ms;
@@ -666,6 +667,8 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         // ---- iterate
         bool stopped = false;
         int it = 0;
+        if (s->profile) s->ev_used = 0;          // drop the (re)start SpMV from the timing
+        int iters_seen = total_iters;
         while (!stopped && total_iters + it < max_iter) {
             const int batch_end = it + check_every;
             for (; it < batch_end && total_iters + it < max_iter; ++it) {
@@ -700,7 +703,12 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
             }
             TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
-            if (s->profile) { rc = prof_harvest(s); if (rc) return rc; }
+            if (s->profile) {
+                const int done_now = s->h_ictl[IN_ITERS] - iters_seen;      // iterations that really ran in this batch
+                rc = prof_harvest(s, 2 * (size_t)(done_now > 0 ? done_now : 0));
+                if (rc) return rc;
+            }
+            iters_seen = s->h_ictl[IN_ITERS];
             stopped = s->h_ictl[IN_STOP] != 0;
         }
         total_iters = s->h_ictl[IN_ITERS];

@@ -112,7 +112,7 @@ class DistributedTransient:
     dirichlet = (global dofs, fill, lift); loads = list of (global node ids, weights, coef_fn(i) -> 4 amplitudes)."""
 
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
-                 alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=64,
+                 alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=16,
                  comm=None, precond="multilevel"):
         self.lp, self.comm = lp, comm
         self.alpha_M, self.alpha_K = alpha_M, alpha_K

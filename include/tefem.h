@@ -189,15 +189,16 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
  *   each owned fine node; rowptr1 / colidx1 / sys1 / dinv1: block-Jacobi-scaled Galerkin operator of level 1 and the
  *   inverses of its diagonal blocks; agg2_* / node_agg2: aggregation of the level-1 nodes; inv2: dense row-major
  *   inverse [4 n_coarse2, 4 n_coarse2] of the level-2 Galerkin operator (n_coarse2 = 0: two levels only);
+ *   sys1 and inv2 are SINGLE precision (preconditioner data only; all vectors and the fine operator are fp64);
  *   work: tefem_precond_work_doubles(n_coarse, n_coarse2) doubles, 128-byte aligned; comm: tefem_comm* or NULL
  *   (the restricted residual is all-reduced, levels 1 and 2 are replicated on every rank).                      */
 typedef struct tefem_precond tefem_precond;
 int64_t tefem_precond_work_doubles(int32_t n_coarse, int32_t n_coarse2);
 int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_coarse, const int32_t* agg_ptr,
                          const int32_t* agg_nodes, const int32_t* node_agg, double omega,
-                         const int32_t* rowptr1, const int32_t* colidx1, const double* sys1, const double* dinv1,
+                         const int32_t* rowptr1, const int32_t* colidx1, const float* sys1, const double* dinv1,
                          double omega_c, int32_t n_coarse2, const int32_t* agg2_ptr, const int32_t* agg2_nodes,
-                         const int32_t* node_agg2, const double* inv2, double* work, void* comm);
+                         const int32_t* node_agg2, const float* inv2, double* work, void* comm);
 int tefem_precond_destroy(tefem_precond* pc);
 int tefem_precond_apply(tefem_precond* pc, const double* r, double* z, void* stream);
 /* Attach (or detach with NULL) a preconditioner to the Krylov driver. */

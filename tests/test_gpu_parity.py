@@ -344,6 +344,82 @@ def test_steady_state_synthetic_sandwich_vs_refined_oracle():
     assert np.allclose(solver.T, X[3::4] + T0, rtol=0, atol=1e-6 * np.abs(X[3::4]).max())
 
 
+def _kuhn_steady_model(nx, ny, nz):
+    from thermoelasticity_fem_b200 import Model
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(nx, ny, nz)
+    groups = dict(tet=tets, tri=tris, nodes=nodes)
+    mesh = make_mesh(pts, groups, KUHN_MATS)
+    dU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('x', 0.), ('y', 0.), ('z', 0.)]}
+    dT = {4: 0., 5: 0.}
+    loads = dict(surface={7: np.array([0., 0., -1e9])}, flux={6: -25.})
+    model = Model(mesh, dict_dirichlet_U=dU, dict_dirichlet_theta=dT, dict_surface_forces=loads["surface"],
+                  dict_heat_flux=loads["flux"])
+    return pts, groups, mesh, model, dU, dT, loads
+
+
+def test_aggregation_preconditioner_apply_matches_host_restatement():
+    """z = omega r + P1 V(P1^T r) of csrc/tefem_precond.cu against the same operator written with scipy from the arrays
+    the preconditioner holds, and the level-1 operator against the Galerkin product P1^T A^ P1 of the fine system."""
+    import scipy.sparse as sp
+    import torch
+    from thermoelasticity_fem_b200.solvers import _SystemSolve
+    pts, groups, mesh, model, *_ = _kuhn_steady_model(16, 9, 6)
+    model.create_free_dofs_lists()
+    model.assemble_K()
+    model.assemble_F()
+    model.apply_dirichlet_matrices()
+    from thermoelasticity_fem_b200.multilevel import TwoLevelPreconditioner
+    ss = _SystemSolve(model, 0., 0., 1., 1e-10, 1000, 16, precond="block_jacobi")
+    pc, S = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, dense_limit=10), ss.dm.schedule
+    n, n1, n2 = mesh.n_nodes, pc.n1, pc.n2
+    assert 1 < n2 < n1 < n
+    A = sp.bsr_array((ss.sys.cpu().numpy().reshape(-1, 4, 4), S.colidx.cpu().numpy(), S.rowptr.cpu().numpy()),
+                     shape=(4 * n, 4 * n)).tocsr()
+    agg = pc.node_agg.cpu().numpy().astype(np.int64)
+
+    def prolongation(a, nc):
+        rows = (4 * np.arange(a.shape[0])[:, None] + np.arange(4)).ravel()
+        cols = (4 * a[:, None] + np.arange(4)).ravel()
+        return sp.csr_array((np.ones(rows.shape[0]), (rows, cols)), shape=(4 * a.shape[0], 4 * nc))
+
+    P1 = prolongation(agg, n1)
+    P2 = prolongation(pc.node_agg2.cpu().numpy().astype(np.int64), n2)
+    A1 = sp.bsr_array((pc.sys1.double().cpu().numpy().reshape(-1, 4, 4), pc.colidx1.cpu().numpy(), pc.rowptr1.cpu().numpy()),
+                      shape=(4 * n1, 4 * n1)).tocsr()
+    D1inv = sp.block_diag(list(pc.dinv1.cpu().numpy().reshape(-1, 4, 4)), format="csr")
+    G = (D1inv @ (P1.T @ A @ P1)).tocsr()
+    assert abs(G - A1).max() <= 2e-7 * abs(G).max()          # stored in single precision
+    inv2 = pc.inv2.double().cpu().numpy()
+    assert np.abs(inv2 @ (P2.T @ A1 @ P2).toarray() - np.eye(4 * n2)).max() < 1e-3
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(4 * n)
+    bc = D1inv @ (P1.T @ r)
+    xc = pc.omega_c * bc
+    xc = xc + P2 @ (inv2 @ (P2.T @ (bc - A1 @ xc)))
+    xc = xc + pc.omega_c * (bc - A1 @ xc)
+    z_host = pc.omega * r + P1 @ xc
+    z = torch.empty(4 * n, dtype=torch.float64, device="cuda")
+    pc.apply(torch.from_numpy(r).cuda(), z)
+    assert np.abs(z.cpu().numpy() - z_host).max() <= 1e-11 * np.abs(z_host).max()
+
+
+def test_steady_state_multilevel_matches_block_jacobi_and_oracle():
+    from thermoelasticity_fem_b200 import LinearSteadyState
+    from oracle import tefem_oracle as orc
+    pts, groups, mesh, model, dU, dT, loads = _kuhn_steady_model(30, 10, 8)
+    sols, its = {}, {}
+    for kind in ("block_jacobi", "multilevel"):
+        solver = LinearSteadyState(model, precond=kind)
+        solver.solve()
+        sols[kind], its[kind] = solver.X.copy(), solver.solve_info["iterations"]
+    X, info = orc.steady_state(pts, groups, {k: orc.Material(*v) for k, v in KUHN_MATS.items()}, dU, dT, loads)
+    for kind in sols:
+        eu, et = parity.field_errors(sols[kind], X)
+        assert eu < parity.SOLUTION_TOL and et < parity.SOLUTION_TOL, (kind, eu, et)
+    assert its["multilevel"] < its["block_jacobi"], its
+
+
 def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
     """BASELINE config 2 end to end (999 steps, public API, full histories) against the states the UNMODIFIED reference
     produced (tests/golden/sandwich_transient2.npz).  The reference re-solves with raw spsolve every step: its own theta

@@ -9,7 +9,8 @@
 // on the ALREADY block-Jacobi-scaled fine operator A^ = D^-1 A, where
 //   * P1 is the piecewise-constant prolongation of a geometric aggregation of the nodes (one coarse node per
 //     aggregate, the 4 DOFs u_x, u_y, u_z, theta kept separate), A1 = P1^T A^ P1 (Galerkin, built on the host
-//     side with torch, 4x4-block CSR like the fine level) and A1^ = D1^-1 A1 its block-Jacobi-scaled form;
+//     side with torch, 4x4-block CSR like the fine level) and A1^ = D1^-1 A1 its block-Jacobi-scaled form, stored
+//     in single precision (preconditioner data only; every vector and the fine operator stay fp64);
 //   * M1 is one V-cycle on level 1: damped Jacobi on A1^ (= a scaling by omega_c, the diagonal blocks are the
 //     identity), a level-2 correction P2 * inv(P2^T A1^ P2) * P2^T with a DENSE inverse (a few hundred nodes), and
 //     a post-smoothing step;
@@ -51,13 +52,18 @@ __global__ void __launch_bounds__(256) restrict_kernel(int32_t n_agg, const int3
     }
 }
 
-// z[4i + c] = omega * r[4i + c] + xc[4 * node_agg[i] + c]
-__global__ void __launch_bounds__(256) prolong_combine_kernel(int64_t n, const int32_t* __restrict__ node_agg, double omega,
+// z[4i + c] = omega * r[4i + c] + xc[4 * node_agg[i] + c]; one thread per node, 256-bit accesses
+__global__ void __launch_bounds__(256) prolong_combine_kernel(int64_t n_nodes, const int32_t* __restrict__ node_agg, double omega,
                                                               const double* __restrict__ r, const double* __restrict__ xc,
                                                               double* __restrict__ z) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    z[k] = omega * r[k] + xc[4 * (int64_t)node_agg[k >> 2] + (k & 3)];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double r0, r1, r2, r3, c0, c1, c2, c3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(r + 4 * i));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3)
+                 : "l"(xc + 4 * (int64_t)node_agg[i]));
+    r0 = omega * r0 + c0; r1 = omega * r1 + c1; r2 = omega * r2 + c2; r3 = omega * r3 + c3;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(z + 4 * i), "d"(r0), "d"(r1), "d"(r2), "d"(r3) : "memory");
 }
 
 // x[4i + c] += x2[4 * node_agg[i] + c]
@@ -68,28 +74,64 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(int64_t n, const int32
     x[k] += x2[4 * (int64_t)node_agg[k >> 2] + (k & 3)];
 }
 
-// out = a * x + b * (y - z)   (y, z may be null: treated as 0)
-__global__ void __launch_bounds__(256) lin_kernel(int64_t n, double a, const double* __restrict__ x, double b,
-                                                  const double* __restrict__ y, const double* __restrict__ z,
-                                                  double* __restrict__ out) {
+// bc = D1^-1 rc (4x4 block per coarse node, row-major) ; xc = wc * bc.   One thread per scalar row.
+__global__ void __launch_bounds__(256) coarse_start_kernel(int64_t n, const double* __restrict__ dinv,
+                                                           const double* __restrict__ rc, double wc,
+                                                           double* __restrict__ bc, double* __restrict__ xc) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    double v = a * x[k];
-    if (y) v += b * (y[k] - (z ? z[k] : 0.0));
-    out[k] = v;
+    const double* d = dinv + 4 * k;                    // row (k & 3) of block (k >> 2)
+    const double* v = rc + (k & ~(int64_t)3);
+    const double b = d[0] * v[0] + d[1] * v[1] + d[2] * v[2] + d[3] * v[3];
+    bc[k] = b;
+    xc[k] = wc * b;
 }
 
-// y = M x for a dense row-major n x n matrix; one warp per row, fixed shuffle tree.
-__global__ void __launch_bounds__(256) dense_matvec_kernel(int32_t n, const double* __restrict__ M,
+// out = c0 * xin + c1 * (b - A1^ x) on level 1.  The level-1 operator is stored in SINGLE precision: it only
+// shapes the preconditioner (a fixed linear operator either way), the Krylov vectors and the fine operator stay
+// fp64; half the bytes keep the whole level in L2.  4 threads per coarse node, one 128-bit load per block row.
+__global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restrict__ rowptr,
+                                                          const int32_t* __restrict__ colidx, int32_t n_rows,
+                                                          const float* __restrict__ sys, const double* __restrict__ x,
+                                                          const double* __restrict__ b, const double* __restrict__ xin,
+                                                          double c0, double c1, double* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 4 * (int64_t)n_rows) return;
+    const int32_t i = (int32_t)(tid >> 2);
+    const int r = (int)(tid & 3);
+    const int32_t s = rowptr[i], t = rowptr[i + 1];
+    double acc0 = 0.0, acc1 = 0.0;
+    int32_t p = s;
+    for (; p + 2 <= t; p += 2) {
+        const int32_t j0 = colidx[p], j1 = colidx[p + 1];
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sys + 16 * (int64_t)p + 4 * r));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(sys + 16 * (int64_t)(p + 1) + 4 * r));
+        const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0);
+        const double2 u1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0 + 2);
+        const double2 w0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j1);
+        const double2 w1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j1 + 2);
+        acc0 += (double)a0.x * u0.x + (double)a0.y * u0.y + (double)a0.z * u1.x + (double)a0.w * u1.y;
+        acc1 += (double)a1.x * w0.x + (double)a1.y * w0.y + (double)a1.z * w1.x + (double)a1.w * w1.y;
+    }
+    if (p < t) {
+        const int32_t j0 = colidx[p];
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sys + 16 * (int64_t)p + 4 * r));
+        const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0);
+        const double2 u1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0 + 2);
+        acc0 += (double)a0.x * u0.x + (double)a0.y * u0.y + (double)a0.z * u1.x + (double)a0.w * u1.y;
+    }
+    out[tid] = (c0 != 0.0 ? c0 * xin[tid] : 0.0) + c1 * (b[tid] - (acc0 + acc1));
+}
+
+// y = M x for a dense row-major n x n single-precision matrix; one CTA of 128 threads per row, fixed reduction tree.
+__global__ void __launch_bounds__(128) dense_matvec_kernel(int32_t n, const float* __restrict__ M,
                                                            const double* __restrict__ x, double* __restrict__ y) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= n) return;
-    const double* m = M + (int64_t)row * n;
-    double a = 0.0;
-    for (int k = lane; k < n; k += 32) a += m[k] * x[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
-    if (lane == 0) y[row] = a;
+    __shared__ double red[32];
+    const float* m = M + (int64_t)blockIdx.x * n;
+    double a[1] = {0.0};
+    for (int k = threadIdx.x; k < n; k += 128) a[0] += (double)m[k] * x[k];
+    block_reduce_sum<1>(a, red);
+    if (threadIdx.x == 0) y[blockIdx.x] = a[0];
 }
 
 }  // namespace tefem
@@ -100,9 +142,10 @@ struct tefem_precond {
     int32_t n_rows = 0, n1 = 0, n2 = 0;
     const int32_t *agg_ptr = nullptr, *agg_nodes = nullptr, *node_agg = nullptr;
     const int32_t *rowptr1 = nullptr, *colidx1 = nullptr;
-    const double *sys1 = nullptr, *dinv1 = nullptr;
+    const float* sys1 = nullptr;
+    const double* dinv1 = nullptr;
     const int32_t *agg2_ptr = nullptr, *agg2_nodes = nullptr, *node_agg2 = nullptr;
-    const double* inv2 = nullptr;
+    const float* inv2 = nullptr;
     double omega = 0.7, omega_c = 0.6;
     double *rc = nullptr, *bc = nullptr, *xc = nullptr, *tc = nullptr, *r2 = nullptr, *x2 = nullptr;
     tefem_comm* comm = nullptr;
@@ -116,14 +159,14 @@ extern "C" int64_t tefem_precond_work_doubles(int32_t n_coarse, int32_t n_coarse
 
 extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_coarse, const int32_t* agg_ptr,
                                     const int32_t* agg_nodes, const int32_t* node_agg, double omega,
-                                    const int32_t* rowptr1, const int32_t* colidx1, const double* sys1,
+                                    const int32_t* rowptr1, const int32_t* colidx1, const float* sys1,
                                     const double* dinv1, double omega_c, int32_t n_coarse2, const int32_t* agg2_ptr,
-                                    const int32_t* agg2_nodes, const int32_t* node_agg2, const double* inv2, double* work,
+                                    const int32_t* agg2_nodes, const int32_t* node_agg2, const float* inv2, double* work,
                                     void* comm) {
     TEFEM_REQUIRE(out && agg_ptr && agg_nodes && node_agg && rowptr1 && colidx1 && sys1 && dinv1 && work, "null pointer");
     TEFEM_REQUIRE(n_coarse > 0 && n_rows >= 0, "sizes");
     TEFEM_REQUIRE(n_coarse2 == 0 || (agg2_ptr && agg2_nodes && node_agg2 && inv2), "null level-2 arrays");
-    TEFEM_REQUIRE((((uintptr_t)work) & 127) == 0 && (((uintptr_t)sys1) & 127) == 0, "work / sys1 must be 128-byte aligned");
+    TEFEM_REQUIRE((((uintptr_t)work) & 127) == 0 && (((uintptr_t)sys1) & 63) == 0, "work must be 128-byte, sys1 64-byte aligned");
     tefem_precond* p = new tefem_precond();
     p->n_rows = n_rows; p->n1 = n_coarse; p->n2 = n_coarse2;
     p->agg_ptr = agg_ptr; p->agg_nodes = agg_nodes; p->node_agg = node_agg;
@@ -156,30 +199,27 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
         if (rc) return rc;
     }
     // level 1 V-cycle on A1^ = D1^-1 A1:  bc = D1^-1 rc ; xc = wc bc ; correction from level 2 ; xc += wc (bc - A1^ xc)
-    int rc = tefem_block_jacobi_apply(p->dinv1, p->n1, p->rc, p->bc, nullptr, s);
-    if (rc) return rc;
     const unsigned g1 = (unsigned)ceil_div(n1, 256);
-    lin_kernel<<<g1, 256, 0, st>>>(n1, p->omega_c, p->bc, 0.0, nullptr, nullptr, p->xc);
+    coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
     TEFEM_LAUNCH_CHECK();
+    const double* xcur = p->xc;
     if (p->n2 > 0) {
-        rc = tefem_spmv(p->rowptr1, p->colidx1, p->n1, p->sys1, p->xc, p->tc, s);
-        if (rc) return rc;
-        lin_kernel<<<g1, 256, 0, st>>>(n1, 1.0, p->bc, -1.0, p->tc, nullptr, p->tc);            // tc = bc - A1^ xc
-        TEFEM_LAUNCH_CHECK();
+        coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, p->n1, p->sys1, p->xc, p->bc, nullptr, 0.0, 1.0, p->tc);
+        TEFEM_LAUNCH_CHECK();                                                                   // tc = bc - A1^ xc
         restrict_kernel<<<(unsigned)ceil_div(32 * (int64_t)p->n2, 256), 256, 0, st>>>(p->n2, p->agg2_ptr, p->agg2_nodes, p->tc, p->r2);
         TEFEM_LAUNCH_CHECK();
-        dense_matvec_kernel<<<(unsigned)ceil_div(32 * 4 * (int64_t)p->n2, 256), 256, 0, st>>>(4 * p->n2, p->inv2, p->r2, p->x2);
+        dense_matvec_kernel<<<(unsigned)(4 * p->n2), 128, 0, st>>>(4 * p->n2, p->inv2, p->r2, p->x2);
         TEFEM_LAUNCH_CHECK();
         prolong_add_kernel<<<g1, 256, 0, st>>>(n1, p->node_agg2, p->x2, p->xc);
         TEFEM_LAUNCH_CHECK();
     }
-    rc = tefem_spmv(p->rowptr1, p->colidx1, p->n1, p->sys1, p->xc, p->tc, s);
-    if (rc) return rc;
-    lin_kernel<<<g1, 256, 0, st>>>(n1, 1.0, p->xc, p->omega_c, p->bc, p->tc, p->xc);              // xc += wc (bc - A1^ xc)
+    // post-smoothing into a second buffer (the SpMV reads all of xc): rc <- xc + wc (bc - A1^ xc)
+    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, p->n1, p->sys1, p->xc, p->bc, p->xc, 1.0, p->omega_c, p->rc);
     TEFEM_LAUNCH_CHECK();
+    xcur = p->rc;
     // level 1 -> 0
     if (nf > 0) {
-        prolong_combine_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(nf, p->node_agg, p->omega, r, p->xc, z);
+        prolong_combine_kernel<<<(unsigned)ceil_div((int64_t)p->n_rows, 256), 256, 0, st>>>(p->n_rows, p->node_agg, p->omega, r, xcur, z);
         TEFEM_LAUNCH_CHECK();
     }
     return TEFEM_OK;

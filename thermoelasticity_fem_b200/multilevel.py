@@ -47,7 +47,7 @@ def _grid_keys(xyz, lo, H, dims):
 class TwoLevelPreconditioner:
     """Owns the device arrays of one preconditioner and its C handle (attach with KrylovSolver.set_precond)."""
 
-    def __init__(self, dm, sys, comm=None, factor1=4.0, factor2=0.0, omega=1.0, omega_c=0.8, dense_limit=300):
+    def __init__(self, dm, sys, comm=None, factor1=6.0, factor2=0.0, omega=1.0, omega_c=0.8, dense_limit=300):
         import os
         if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c"
             factor1, factor2, omega, omega_c = (float(v) for v in os.environ["TEFEM_ML"].split(","))
@@ -111,12 +111,12 @@ class TwoLevelPreconditioner:
             ijk = np.stack([k // (int(dims1[1]) * int(dims1[2])), (k // int(dims1[2])) % int(dims1[1]), k % int(dims1[2])], axis=1)
             if factor2 <= 0:      # automatic: keep the dense level-2 operator at a few hundred nodes
                 factor2 = max(3.0, float(np.ceil((n1 / 450.0) ** (1.0 / 3.0))))
-            self.factor2 = factor2
             c = np.floor(ijk / factor2 + 1e-9).astype(np.int64)
             d2 = c.max(axis=0) + 1
             key2 = (c[:, 0] * d2[1] + c[:, 1]) * d2[2] + c[:, 2]
             _, agg2 = np.unique(key2, return_inverse=True)
             n2 = int(agg2.max()) + 1
+        self.factor2 = factor2
         import scipy.sparse as sp
         A1 = sp.bsr_array((self.sys1.cpu().numpy().reshape(-1, 4, 4), self.colidx1.cpu().numpy(), self.rowptr1.cpu().numpy()),
                           shape=(4 * n1, 4 * n1)).tocsr()
@@ -124,7 +124,9 @@ class TwoLevelPreconditioner:
         cols = (4 * agg2[:, None] + np.arange(4)).ravel()
         P2 = sp.csr_array((np.ones(4 * n1), (rows, cols)), shape=(4 * n1, 4 * n2))
         A2 = (P2.T @ A1 @ P2).toarray()
-        self.inv2 = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(A2))).to(dev)
+        # preconditioner data of the coarse levels is kept in single precision (half the bytes, L2-resident)
+        self.inv2 = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(A2)).astype(np.float32)).to(dev)
+        self.sys1 = self.sys1.to(torch.float32).contiguous()
         order2 = np.argsort(agg2, kind="stable")
         agg2_ptr = np.zeros(n2 + 1, dtype=np.int64)
         np.cumsum(np.bincount(agg2, minlength=n2), out=agg2_ptr[1:])
@@ -133,6 +135,7 @@ class TwoLevelPreconditioner:
         self.agg2_nodes = torch.from_numpy(order2.astype(np.int32)).to(dev)
         self.node_agg2 = torch.from_numpy(agg2.astype(np.int32)).to(dev)
         self.n1, self.n2, self.h, self.H1 = n1, n2, h, H1
+        self.factor1, self.omega, self.omega_c = factor1, omega, omega_c
         self.work = torch.zeros(int(lib.tefem_precond_work_doubles(n1, n2)), **f64)
         self.handle = ctypes.c_void_p()
         self.lib = lib

@@ -387,7 +387,8 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
     P2 = prolongation(pc.node_agg2.cpu().numpy().astype(np.int64), n2)
     A1 = sp.bsr_array((pc.sys1.double().cpu().numpy().reshape(-1, 4, 4), pc.colidx1.cpu().numpy(), pc.rowptr1.cpu().numpy()),
                       shape=(4 * n1, 4 * n1)).tocsr()
-    D1inv = sp.block_diag(list(pc.dinv1.cpu().numpy().reshape(-1, 4, 4)), format="csr")
+    D1inv = sp.bsr_array((pc.dinv1.cpu().numpy().reshape(-1, 4, 4), np.arange(n1), np.arange(n1 + 1)),
+                         shape=(4 * n1, 4 * n1)).tocsr()
     G = (D1inv @ (P1.T @ A @ P1)).tocsr()
     assert abs(G - A1).max() <= 2e-7 * abs(G).max()          # stored in single precision
     inv2 = pc.inv2.double().cpu().numpy()

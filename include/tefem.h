@@ -92,26 +92,32 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * Owner-computes TILE schedule built once per mesh by the symbolic phase (host side, symbolic.py): a tile owns a
  * contiguous range of node rows and everything it needs lives in per-tile segments that start on 16-byte
  * boundaries, so that the persistent kernel can prefetch its next tile with TMA bulk copies while it computes:
- *   cta_hdr[c][12] = {n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes, 0, 0};
+ *   cta_hdr[c][12] = {n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes,
+ *                     first block, 0}   (a tile owns a contiguous block range starting at `first block`);
  *   cta_xyz[o_nodes ..][3]     coordinates of the tile's nodes (copy of coords[cta_nodes]);
- *   cta_conn8 / cta_mat / cta_elems [o_elems ..]   staged elements: 4 tile-local node numbers (one byte each),
- *                              material index, element number (error reporting);
+ *   cta_conn8 / cta_elems [o_elems ..]   staged elements: 4 tile-local node numbers (one byte each), element
+ *                              number (error reporting);
  *   inc[o_inc ..]              incidence entries (tile-local element << 4) | (a << 2) | b, a, b = local node numbers
  *                              of (row, column), block after block, ASCENDING ELEMENT inside a block (the order of
  *                              the reference's loop, model.py:89,96,107);
- *   item_block / item_inc / item_meta [o_items ..]   work items: one block p, or one chunk of a block whose list is
- *                              long (diagonal blocks); the thread sums inc[item_inc .. + (item_meta & 0xff)) (tile-
- *                              relative) and either writes the block or, when (item_meta >> 8) - 1 >= 0, parks the
- *                              partial sums in that shared-memory slot;
- *   split_block / split_meta [o_split ..]   split blocks: block, first slot | n_chunks << 16 (added in chunk order);
+ *   item_inc / item_meta [o_items ..]   work items: one block, or one piece of a block's list (lists are cut where
+ *                              the element material changes, and long runs - the diagonal blocks - into chunks):
+ *                              ALL ELEMENTS OF AN ITEM SHARE ONE MATERIAL, row (item_meta >> 24) & 0xff of mat_table,
+ *                              whose constants multiply the item's geometric sums once; the thread sums
+ *                              inc[(item_inc & 0xffff) .. + (item_meta & 0xff)) (tile-relative) and either writes
+ *                              block `first block + (item_inc >> 16)` (items are in block order: the plane stores
+ *                              of a warp are contiguous) or, when ((item_meta >> 8) & 0xffff) - 1 >= 0, parks the
+ *                              values in that shared-memory slot;
+ *   split_block / split_meta [o_split ..]   blocks with several items: tile-local block, first slot | n_items << 16
+ *                              (added in list order = ascending element);
  *   h_max[6] = largest n_items, n_elems, n_inc, partial slots, n_split, n_nodes of a tile (shared-memory sizes).
  *   Every output value is written exactly once: no atomics, bitwise reproducible.
  * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
  * The D layout follows alpha_M / alpha_K (model.py:112-117).
  * bad_elem[2] as above; the call itself does not synchronise - use tefem_check_jacobian().      */
 int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
-                   const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
-                   const double* cta_xyz, const int32_t* item_block, const int32_t* item_inc, const int32_t* item_meta,
+                   const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
+                   const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
                    const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc,
                    int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                    double* vals_M, double* vals_K, double* vals_D,

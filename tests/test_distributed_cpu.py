@@ -40,7 +40,8 @@ def _worker(rank, world, port, result_dir):
         bounds = slab_ranges(nx + 1, (ny + 1) * (nz + 1), world)
         lp = localize(conn, np.arange(conn.shape[0]), bounds, rank)
         # local assembly of the owned rows (no communication)
-        S = build_schedule(torch.from_numpy(lp.conn), lp.n_local, n_rows=lp.n_own)
+        S = build_schedule(torch.from_numpy(lp.conn), lp.n_local, n_rows=lp.n_own,
+                           mat_id=torch.from_numpy(mat_id[lp.elem_ids]))
         vals, bad = emu_assemble(emu, S, pts[lp.local_nodes], lp.conn, mat_id[lp.elem_ids], rows, "MKD", 0.2, 0.1)
         K_loc = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * lp.n_local).tocsr()
         # reference: the global operator

@@ -53,15 +53,14 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     nD = layout.n_planes(layout.plane_map_D(aM, aK))
     vM, vK, vD = np.full((3, P), np.nan), np.full((13, P), np.nan), np.full((nD, P), np.nan)
     bad = np.full(2, 2 ** 31 - 1, dtype=np.int32)
-    a = {k: getattr(S, k).numpy() for k in ("cta_hdr", "cta_elems", "cta_conn8", "cta_nodes", "item_block", "item_inc",
-                                            "item_meta", "split_block", "split_meta", "inc")}
-    cta_mat = np.ascontiguousarray(mat_id.astype(np.int32)[np.maximum(a["cta_elems"], 0)])
+    a = {k: getattr(S, k).numpy() for k in ("cta_hdr", "cta_elems", "cta_conn8", "cta_nodes", "item_inc", "item_meta",
+                                            "split_block", "split_meta", "inc")}
     cta_xyz = np.ascontiguousarray(pts[a["cta_nodes"]])
     h_max = np.array([S.max_cta_items, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, S.max_cta_split, S.max_cta_nodes],
                      dtype=np.int32)
     mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
-    rc = emu.tefem_emu_assemble(ptr(rows), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]), ptr(a["cta_elems"]),
-                                ptr(a["cta_conn8"]), ptr(cta_mat), ptr(cta_xyz), ptr(a["item_block"]), ptr(a["item_inc"]),
+    rc = emu.tefem_emu_assemble(ptr(rows), ctypes.c_int(rows.shape[0]), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]),
+                                ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_xyz), ptr(a["item_inc"]),
                                 ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]), ptr(a["inc"]),
                                 ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
                                 ptr(vM), ptr(vK), ptr(vD), ptr(bad))
@@ -72,7 +71,7 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     return dict(M=vM, K=vK, D=vD), bad
 
 
-def check_schedule_invariants(S, conn, n_nodes, max_chunk=8):
+def check_schedule_invariants(S, conn, n_nodes, max_chunk=8, mat_id=None):
     E = conn.shape[0]
     rowptr, colidx, br = S.rowptr.numpy(), S.colidx.numpy(), S.block_row.numpy()
     assert rowptr[0] == 0 and rowptr[-1] == S.n_blocks
@@ -83,24 +82,31 @@ def check_schedule_invariants(S, conn, n_nodes, max_chunk=8):
     H = S.cta_hdr.numpy().astype(np.int64)
     binc, blen = S.block_inc.numpy().astype(np.int64), S.block_len.numpy().astype(np.int64)
     ib, ii, im = S.item_block.numpy(), S.item_inc.numpy().astype(np.int64), S.item_meta.numpy()
-    sb, sm = S.split_block.numpy(), S.split_meta.numpy()
+    sb, sm = S.split_block.numpy(), S.split_meta.numpy().astype(np.int64) & 0xFFFFFFFF
     inc = S.inc.numpy().astype(np.int64) & 0xFFFF
     cn8 = S.cta_conn8.numpy().astype(np.int64) & 0xFFFFFFFF
     ce, cnodes = S.cta_elems.numpy(), S.cta_nodes.numpy()
     assert H[:, 0].sum() == S.n_items and blen.sum() == (16 * E if S.n_rows == n_nodes else blen.sum())
     seen_blocks = []
     for c in range(S.n_cta):
-        n_it, n_el, n_inc, n_sp, n_nd, o_it, o_el, o_inc, o_sp, o_nd = H[c, :10]
+        n_it, n_el, n_inc, n_sp, n_nd, o_it, o_el, o_inc, o_sp, o_nd, p0 = H[c, :11]
         # 16-byte aligned segment starts, sizes within the declared maxima
         assert o_it % 4 == 0 and o_el % 4 == 0 and o_inc % 8 == 0 and o_sp % 4 == 0 and o_nd % 2 == 0
         assert n_it <= S.max_cta_items and n_el <= S.max_cta_elems and n_inc <= S.max_cta_inc
         assert n_sp <= S.max_cta_split and n_nd <= S.max_cta_nodes <= 256
-        blk, start, meta = ib[o_it:o_it + n_it], ii[o_it:o_it + n_it], im[o_it:o_it + n_it]
+        blk, start, meta = ib[o_it:o_it + n_it], ii[o_it:o_it + n_it] & 0xffff, im[o_it:o_it + n_it]
+        assert np.array_equal(ii[o_it:o_it + n_it] >> 16, blk - p0) and np.all(np.diff(blk) >= 0)      # block order
         ilen = meta & 0xff
-        slots = (meta >> 8) - 1
-        assert ilen.min() >= 1 and np.all(np.diff(ilen) <= 0)             # longest first
+        slots = ((meta >> 8) & 0xffff) - 1
+        imat = (meta.astype(np.int64) >> 24) & 0xff
+        assert ilen.min() >= 1
         assert np.all(start >= 0) and np.all(start + ilen <= n_inc)
-        assert np.all(ilen[slots >= 0] <= max_chunk) and np.all(ilen[slots < 0] <= 2 * max_chunk)
+        assert np.all(ilen <= 2 * max_chunk)
+        # every item is material-uniform and carries that material
+        for k in range(0, n_it, max(1, n_it // 40)):
+            els = ce[o_el + (inc[o_inc + start[k]:o_inc + start[k] + ilen[k]] >> 4)]
+            want = 0 if mat_id is None else mat_id[els]
+            assert np.all(want == imat[k])
         used = np.sort(slots[slots >= 0])
         assert np.array_equal(used, np.arange(used.size)) and used.size <= S.max_cta_slots
         # the chunks of every block tile its incidence list exactly, in order
@@ -115,9 +121,9 @@ def check_schedule_invariants(S, conn, n_nodes, max_chunk=8):
         tot = 0
         for k in range(o_sp, o_sp + n_sp):
             slot0, n = sm[k] & 0xffff, sm[k] >> 16
-            sel = blk == sb[k]
+            sel = blk == p0 + sb[k]
             assert n >= 2 and sel.sum() == n
-            assert np.array_equal(slots[sel][np.argsort(start[sel])], np.arange(slot0, slot0 + n))   # chunk order = slot order
+            assert np.array_equal(slots[sel][np.argsort(start[sel])], np.arange(slot0, slot0 + n))   # list order = slot order
             tot += n
         assert tot == used.size
         # byte connectivity decodes to the global connectivity through the tile's node list
@@ -140,10 +146,10 @@ def test_sandwich_schedule_and_emulated_assembly(sandwich, emu, aM, aK):
     pts, blocks, groups = sandwich
     m = orc.Material(*MAT2)
     conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
-    S = build_schedule(torch.from_numpy(conn), pts.shape[0])
+    S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id))
     assert S.n_blocks == 39985
     if aM == 0.2:
-        check_schedule_invariants(S, conn, pts.shape[0])
+        check_schedule_invariants(S, conn, pts.shape[0], mat_id=mat_id)
     vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", aM, aK)
     assert bad[0] == 2 ** 31 - 1 and bad[1] == 2 ** 31 - 1
     ops = orc.assemble(pts, conn, rows, mat_id, aM, aK)
@@ -161,7 +167,7 @@ def test_single_operator_launches_match_fused(sandwich, emu):
     pts, blocks, groups = sandwich
     m = orc.Material(*MAT2)
     conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
-    S = build_schedule(torch.from_numpy(conn), pts.shape[0])
+    S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id))
     fused, _ = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.2, 0.2)
     for nm in "MKD":
         single, _ = emu_assemble(emu, S, pts, conn, mat_id, rows, nm, 0.2, 0.2)
@@ -176,8 +182,8 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
     for items in (256, 64):                       # small tiles: many CTAs, exercises the segment offsets
         chunk = 6 if items == 256 else 3
         S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items),
-                           max_chunk=chunk)
-        check_schedule_invariants(S, conn, pts.shape[0], chunk)
+                           max_chunk=chunk, mat_id=torch.from_numpy(mat_id))
+        check_schedule_invariants(S, conn, pts.shape[0], chunk, mat_id=mat_id)
         vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
         ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)
         A = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * pts.shape[0])
@@ -188,7 +194,7 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
     bad_conn = conn.copy()
     bad_conn[[17, 90]] = bad_conn[[17, 90]][:, [0, 2, 1, 3]]        # two inverted elements: the first one is reported
     bad_conn[40, 3] = bad_conn[40, 2]                               # and a degenerate one in between
-    S = build_schedule(torch.from_numpy(bad_conn), pts.shape[0])
+    S = build_schedule(torch.from_numpy(bad_conn), pts.shape[0], mat_id=torch.from_numpy(mat_id))
     _, bad = emu_assemble(emu, S, pts, bad_conn, mat_id, rows, "K", 0., 0.)
     assert bad[0] == 17 and bad[1] == 40
 

@@ -25,7 +25,7 @@ _SIGNATURES = {
     "tefem_version": [c_char_p, c_size_t],
     "tefem_quadrature_tables": [P, P, P],
     "tefem_element_matrices": [P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P],
-    "tefem_assemble": [P, c_int, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
+    "tefem_assemble": [P, c_int, c_int32, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
                        P, P, P, P, P],
     "tefem_check_jacobian": [P, P, P],
     "tefem_planes_spmv": [P, P, c_int32, c_int64, P, P, P, c_double, c_double, P, P],

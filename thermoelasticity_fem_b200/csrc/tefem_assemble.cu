@@ -5,22 +5,24 @@
 // and csc_array(dense).  Design (DESIGN.md "K1"):
 //
 //   * the symbolic phase groups node rows into TILES and stores everything a tile needs in per-tile
-//     segments (16-byte aligned): node coordinates, byte-packed tile-local connectivity, material
-//     index, incidence entries (the slot map), work items, split lists;
-//   * the kernel is PERSISTENT (grid = CTAs that fit on the 148 SMs): while a CTA computes tile t it
-//     prefetches the segments of its next tile into the other half of a double buffer with TMA bulk
-//     copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier, so no global-memory latency sits
-//     on the critical path of a tile (v1-v3 were latency bound: 3.4 warps per scheduler, 81 % of the
-//     cycles without an eligible warp, profiles/README.md);
-//   * per tile: phase 1 builds the geometry record (inverse Jacobian columns = shape-function
-//     gradients, det, material-scaled weights) of every staged element in shared memory; phase 2: one
-//     thread per WORK ITEM - a node-pair block, or a chunk of a block with a long incidence list (the
-//     diagonal blocks) - walks its incidence entries (element, a, b) in ascending element order and
-//     accumulates the block's 13 (K) / 1 (M) / 4 (D) values in registers; unsplit blocks are written
-//     straight to the structure-of-arrays planes, chunks park partial sums in shared memory and one
-//     thread per split block adds them in chunk order (phase 3).  Every output value is written
-//     exactly once: no atomics, bitwise reproducible, summation in the reference's element order
-//     (chunked for the split blocks).
+//     segments (16-byte aligned): node coordinates, byte-packed tile-local connectivity, incidence
+//     entries (the slot map), work items, split lists;
+//   * the kernel is PERSISTENT (grid = CTAs that fit on the 148 SMs, 3 per SM): while a CTA computes
+//     tile t it prefetches the segments of its next tile into the other half of a double buffer with
+//     TMA bulk copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier, so no global-memory
+//     latency sits on the critical path of a tile (v1-v3 were latency bound, profiles/README.md);
+//   * per tile: phase 1 builds the GEOMETRY record (inverse Jacobian columns = shape-function
+//     gradients, det; no material) of every staged element in shared memory; phase 2: one thread per
+//     WORK ITEM - a node-pair block, or a piece of a block whose incidence list is long (the diagonal
+//     blocks) or crosses a material interface - walks its incidence entries (element, a, b) in
+//     ascending element order and accumulates the MATERIAL-FREE geometric sums (9 + 3 + 1 + 3 values)
+//     in registers; all elements of an item share one material, whose constants are applied once per
+//     item (7 / 10 shared-memory loads per incidence instead of 11 / 17: the kernel is bound by the
+//     shared-memory pipe).  Items are in block order, so the structure-of-arrays plane stores of a
+//     warp are contiguous; pieces of split blocks park their values in shared memory and one thread
+//     per split block adds them in list order (phase 3).  Every output value is written exactly once:
+//     no atomics, bitwise reproducible, summation in the reference's element order (piecewise for the
+//     split blocks).
 //
 // The same per-thread routines are compiled for the host when TEFEM_HOST_EMU is defined; that
 // build is used only by tests/host_emulation to check the schedule logic in a GPU-less container
@@ -37,16 +39,14 @@ struct AssembleArgs {
     const int32_t* conn;       // element_matrices path only
     const int32_t* mat_id;     // element_matrices path only
     const double* mat_table;
-    const int32_t* cta_hdr;    // [n_cta, 12]: n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes
+    const int32_t* cta_hdr;    // [n_cta, 12]: n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes, block0
     const int32_t* cta_elems;  // staged element numbers (error reporting only)
     const int32_t* cta_conn8;  // connectivity of the staged elements as 4 tile-local node bytes
-    const int32_t* cta_mat;    // material index of the staged elements
     const double* cta_xyz;     // coordinates of the tile's nodes, [.., 3]
-    const int32_t* item_block; // block p of the work item
-    const int32_t* item_inc;   // first incidence entry of the work item (relative to the tile's segment)
-    const int32_t* item_meta;  // length | (partial slot + 1) << 8   (slot + 1 == 0: unsplit block)
-    const int32_t* split_block;  // block p of a split block
-    const int32_t* split_meta;   // first partial slot | n_chunks << 16
+    const int32_t* item_inc;   // first incidence entry of the work item (relative to the tile's segment) | tile-local block << 16
+    const int32_t* item_meta;  // length | (partial slot + 1) << 8 | material << 24   (slot + 1 == 0: the block's only item)
+    const int32_t* split_block;  // tile-local block with several items
+    const int32_t* split_meta;   // first partial slot | n_items << 16
     const uint16_t* inc;
     int32_t n_cta;
     int64_t n_blocks;
@@ -57,25 +57,24 @@ struct AssembleArgs {
     int32_t* bad_elem;
 };
 
-enum { H_NITEMS = 0, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, HDR_STRIDE = 12 };
+enum { H_NITEMS = 0, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, HDR_STRIDE = 12 };
 
 // ---- per-thread routines (host + device) -------------------------------------------------------
 
 // Geometry record of element e read through the global connectivity (element_matrices path).
-TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double W4, double* rec) {
+TEFEM_HD double stage_element(const AssembleArgs& A, int32_t e, double* rec) {
     const int32_t n0 = A.conn[4 * (int64_t)e], n1 = A.conn[4 * (int64_t)e + 1];
     const int32_t n2 = A.conn[4 * (int64_t)e + 2], n3 = A.conn[4 * (int64_t)e + 3];
-    const double* mat = A.mat_table + MAT_STRIDE * A.mat_id[e];
-    return element_record(A.coords + 3 * (int64_t)n0, A.coords + 3 * (int64_t)n1,
-                          A.coords + 3 * (int64_t)n2, A.coords + 3 * (int64_t)n3, mat, W4, rec);
+    return element_record<true>(A.coords + 3 * (int64_t)n0, A.coords + 3 * (int64_t)n1, A.coords + 3 * (int64_t)n2,
+                                A.coords + 3 * (int64_t)n3, rec);
 }
 
 // Phase 1 from the tile's staged node coordinates xyz[tile-local node][3] and the byte-packed tile-local
 // connectivity (no gather from global memory per element).
-TEFEM_HD double stage_element_local(const double* mat_table, const double* xyz, uint32_t conn8, int32_t mat_idx, double W4,
-                                    double* rec) {
-    return element_record(xyz + 3 * (conn8 & 0xff), xyz + 3 * ((conn8 >> 8) & 0xff), xyz + 3 * ((conn8 >> 16) & 0xff),
-                          xyz + 3 * (conn8 >> 24), mat_table + MAT_STRIDE * mat_idx, W4, rec);
+template <bool WITH_GT>
+TEFEM_HD double stage_element_local(const double* xyz, uint32_t conn8, double* rec) {
+    return element_record<WITH_GT>(xyz + 3 * (conn8 & 0xff), xyz + 3 * ((conn8 >> 8) & 0xff), xyz + 3 * ((conn8 >> 16) & 0xff),
+                                   xyz + 3 * (conn8 >> 24), rec);
 }
 
 template <int OPS, int DUU>
@@ -84,7 +83,15 @@ struct AsmTraits {
     static constexpr bool NEED_K = WANT_K || (WANT_D && DUU == 2);
     static constexpr bool NEED_M = WANT_M || (WANT_D && DUU >= 1);
     typedef BlockAcc<NEED_K, NEED_M, WANT_D> Acc;
+    typedef GeomAcc<NEED_K, NEED_M, WANT_D> Geom;
+    static constexpr int REC = WANT_D ? REC_STRIDE_D : REC_STRIDE_K;     // record stride (doubles)
+    static constexpr int SLOT = Acc::LIVE | 1;                           // slot stride (doubles), odd
 };
+
+// item_meta fields
+TEFEM_HD int meta_len(int32_t meta) { return meta & 0xff; }
+TEFEM_HD int meta_slot(int32_t meta) { return ((meta >> 8) & 0xffff) - 1; }
+TEFEM_HD int meta_mat(int32_t meta) { return (int)((uint32_t)meta >> 24); }
 
 // Write the planes of block p.  DUU: 0 = D has no uu part, 1 = alpha_M only (3 diagonal planes),
 // 2 = alpha_K != 0 (9 planes); model.py:112-117.
@@ -125,43 +132,49 @@ TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTr
     }
 }
 
-// One work item: acc = sum over the incidence entries inc[s .. s + len) (ascending element order), then either
-// write the block or park the partial sums of a chunk.
+// One work item (all its elements share one material): geometric sums over the incidence entries
+// inc[s .. s + len) (ascending element order), material constants applied once; then either write the block (items
+// are in block order: consecutive threads write consecutive addresses of every plane) or park the values of a
+// piece of a split block in its shared-memory slot.
 template <int OPS, int DUU>
-TEFEM_HD void process_item(const AssembleArgs& A, int32_t p, uint32_t s, int32_t meta, const double* recs,
-                           const uint16_t* inc_s, double* partials, const double* S, const double* NN) {
+TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_word, int32_t meta, const double* recs,
+                           const uint16_t* inc_s, double* slots, double W4, const double* S, const double* NN) {
+    typedef AsmTraits<OPS, DUU> T;
+    typename T::Geom g;
+    g.clear();
+    const uint32_t s = inc_word & 0xffffu, t = s + (uint32_t)meta_len(meta);
+    for (uint32_t k = s; k < t; ++k) {
+        const uint32_t w = inc_s[k];
+        block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(g, recs + (size_t)(w >> 4) * T::REC, (w >> 2) & 3, w & 3, W4, S, NN);
+    }
+    typename T::Acc acc;
+    block_finalize<T::NEED_K, T::NEED_M, T::WANT_D>(g, A.mat_table + MAT_STRIDE * meta_mat(meta), acc);
+    const int slot = meta_slot(meta);
+    if (slot < 0) store_block<OPS, DUU>(A, block0 + (int32_t)(inc_word >> 16), acc);
+    else acc.dump(slots + (size_t)slot * T::SLOT);
+}
+
+// Phase 3 for one split block: add the values of its items in list order (= ascending element) and write the block.
+template <int OPS, int DUU>
+TEFEM_HD void combine_split(const AssembleArgs& A, int32_t p, int32_t meta, const double* slots) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Acc acc;
     acc.clear();
-    const uint32_t t = s + (uint32_t)(meta & 0xff);
-    for (uint32_t k = s; k < t; ++k) {
-        const uint32_t w = inc_s[k];
-        block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(acc, recs + (size_t)(w >> 4) * REC_STRIDE, (w >> 2) & 3, w & 3, S, NN);
-    }
-    const int slot = (meta >> 8) - 1;
-    if (slot < 0) store_block<OPS, DUU>(A, p, acc);
-    else acc.dump(partials + (size_t)slot * T::Acc::LIVE);
-}
-
-// Phase 3 for one split block: add the chunk partials in chunk order and write the block.
-template <int OPS, int DUU>
-TEFEM_HD void combine_split(const AssembleArgs& A, int32_t p, int32_t meta, const double* partials) {
-    typedef typename AsmTraits<OPS, DUU>::Acc Acc;
-    Acc acc;
-    acc.clear();
-    const int slot0 = meta & 0xffff, n = meta >> 16;
-    for (int c = 0; c < n; ++c) acc.add_from(partials + (size_t)(slot0 + c) * Acc::LIVE);
+    const int slot0 = meta & 0xffff, n = (int)((uint32_t)meta >> 16);
+    for (int c = 0; c < n; ++c) acc.add_from(slots + (size_t)(slot0 + c) * T::SLOT);
     store_block<OPS, DUU>(A, p, acc);
 }
 
 // Dense element matrices of one element (parity path; elements.py:220-286).
-TEFEM_HD void element_dense(const double* rec, const double* S, const double* NN, int kinds,
+TEFEM_HD void element_dense(const double* rec, const double* mat, double W4, const double* S, const double* NN, int kinds,
                             double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut, double* Ktt) {
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
+            GeomAcc<true, true, true> g;
+            g.clear();
+            block_accumulate<true, true, true>(g, rec, a, b, W4, S, NN);
             BlockAcc<true, true, true> acc;
-            acc.clear();
-            block_accumulate<true, true, true>(acc, rec, a, b, S, NN);
+            block_finalize<true, true, true>(g, mat, acc);
             if (kinds & TEFEM_KIND_MUU)
                 for (int i = 0; i < 3; ++i)
                     for (int j = 0; j < 3; ++j) Muu[(3 * a + i) * 12 + 3 * b + j] = (i == j) ? acc.m : 0.0;
@@ -256,6 +269,9 @@ static int upload_quad() {
 }
 
 constexpr int ASM_THREADS = 256;
+#ifndef ASM_MIN_CTAS
+#define ASM_MIN_CTAS 3
+#endif
 
 // ---- TMA bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -285,7 +301,7 @@ __host__ __device__ inline uint32_t up16(uint32_t bytes) { return (bytes + 15u) 
 
 // Shared-memory layout of one prefetch stage (byte offsets, all multiples of 16).
 struct StageLayout {
-    uint32_t hdr, xyz, conn8, mat, it_block, it_inc, it_meta, sp_block, sp_meta, inc, bytes;
+    uint32_t hdr, xyz, conn8, it_inc, it_meta, sp_block, sp_meta, inc, bytes;
 };
 __host__ __device__ inline StageLayout stage_layout(int max_items, int max_elems, int max_inc, int max_split, int max_nodes) {
     StageLayout L;
@@ -293,8 +309,6 @@ __host__ __device__ inline StageLayout stage_layout(int max_items, int max_elems
     L.hdr = o; o += 64;
     L.xyz = o; o += up16(24u * (uint32_t)((max_nodes + 1) & ~1));
     L.conn8 = o; o += up16(4u * (uint32_t)(max_elems + 3));
-    L.mat = o; o += up16(4u * (uint32_t)(max_elems + 3));
-    L.it_block = o; o += up16(4u * (uint32_t)(max_items + 3));
     L.it_inc = o; o += up16(4u * (uint32_t)(max_items + 3));
     L.it_meta = o; o += up16(4u * (uint32_t)(max_items + 3));
     L.sp_block = o; o += up16(4u * (uint32_t)(max_split + 3));
@@ -313,16 +327,12 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
     const int o_items = h1.y, o_elems = h1.z, o_inc = h1.w, o_split = h2.x, o_nodes = h2.y;
     const uint32_t b_items = up16(4u * n_items), b_elems = up16(4u * n_elems), b_inc = up16(2u * n_inc);
     const uint32_t b_split = up16(4u * n_split), b_xyz = up16(24u * n_nodes);
-    const uint32_t total = 48u + b_xyz + 2u * b_elems + 3u * b_items + 2u * b_split + b_inc;
+    const uint32_t total = 48u + b_xyz + b_elems + 2u * b_items + 2u * b_split + b_inc;
     mbar_expect_tx(bar, total);
     bulk_g2s(st + L.hdr, hg, 48u, bar);
     if (b_xyz) bulk_g2s(st + L.xyz, A.cta_xyz + 3 * (size_t)o_nodes, b_xyz, bar);
-    if (b_elems) {
-        bulk_g2s(st + L.conn8, A.cta_conn8 + o_elems, b_elems, bar);
-        bulk_g2s(st + L.mat, A.cta_mat + o_elems, b_elems, bar);
-    }
+    if (b_elems) bulk_g2s(st + L.conn8, A.cta_conn8 + o_elems, b_elems, bar);
     if (b_items) {
-        bulk_g2s(st + L.it_block, A.item_block + o_items, b_items, bar);
         bulk_g2s(st + L.it_inc, A.item_inc + o_items, b_items, bar);
         bulk_g2s(st + L.it_meta, A.item_meta + o_items, b_items, bar);
     }
@@ -333,9 +343,11 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
     if (b_inc) bulk_g2s(st + L.inc, A.inc + o_inc, b_inc, bar);
 }
 
-// Shared memory: [element records][partial sums][stage 0][stage 1][2 mbarriers].
+// Shared memory: [element records][partial-sum slots][stage 0][stage 1][2 mbarriers][S, NN tables].
+// The quadrature tables are indexed by the per-incidence local node numbers: from shared memory (20 distinct
+// banks, broadcast) instead of constant memory, where a warp's divergent indices would be serialised.
 template <int OPS, int DUU>
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
+__global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
                                                                   int part_doubles) {
     extern __shared__ __align__(128) double smem[];
     double* recs = smem;
@@ -343,6 +355,11 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const Assemble
     const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
     char* stage0 = reinterpret_cast<char*>(partials + part_doubles);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
+    double* tabS = reinterpret_cast<double*>(bars + 2);
+    double* tabNN = tabS + 4;
+    if (threadIdx.x < 4) tabS[threadIdx.x] = c_quad.S[threadIdx.x];
+    if (threadIdx.x < 16) tabNN[threadIdx.x] = c_quad.NN[threadIdx.x];
+    typedef AsmTraits<OPS, DUU> T;
     const int G = gridDim.x;
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -381,16 +398,15 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const Assemble
         while (!mbar_try_wait(&bars[s], parity)) {}
         const int32_t* hdr = reinterpret_cast<const int32_t*>(st + L.hdr);
         const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], n_split = hdr[H_NSPLIT], o_elems = hdr[H_OELEMS];
+        const int32_t block0 = hdr[H_BLOCK0];
         const double* xyz = reinterpret_cast<const double*>(st + L.xyz);
         const uint32_t* conn8 = reinterpret_cast<const uint32_t*>(st + L.conn8);
-        const int32_t* mat = reinterpret_cast<const int32_t*>(st + L.mat);
-        const int32_t* it_block = reinterpret_cast<const int32_t*>(st + L.it_block);
         const int32_t* it_inc = reinterpret_cast<const int32_t*>(st + L.it_inc);
         const int32_t* it_meta = reinterpret_cast<const int32_t*>(st + L.it_meta);
         const uint16_t* inc_s = reinterpret_cast<const uint16_t*>(st + L.inc);
         // phase 1: geometry records of the staged elements
         for (int le = threadIdx.x; le < n_elems; le += ASM_THREADS) {
-            const double det = stage_element_local(A.mat_table, xyz, conn8[le], mat[le], W4, recs + (size_t)le * REC_STRIDE);
+            const double det = stage_element_local<T::WANT_D>(xyz, conn8[le], recs + (size_t)le * T::REC);
             if (!(det > 0.0)) {  // error path only: elements.py:207-210
                 const int32_t e = A.cta_elems[o_elems + le];
                 if (det < 0.0) atomicMin(A.bad_elem, e);
@@ -398,15 +414,16 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const Assemble
             }
         }
         __syncthreads();
-        // phase 2: work items
+        // phase 2: work items in block order
         for (int it = threadIdx.x; it < n_items; it += ASM_THREADS)
-            process_item<OPS, DUU>(A, it_block[it], (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, c_quad.S, c_quad.NN);
-        // phase 3: split (diagonal) blocks
+            process_item<OPS, DUU>(A, block0, (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, W4, tabS, tabNN);
+        // phase 3: blocks with several items (the diagonal blocks, material interfaces)
         if (n_split > 0) {   // uniform over the CTA
             __syncthreads();
             const int32_t* sp_block = reinterpret_cast<const int32_t*>(st + L.sp_block);
             const int32_t* sp_meta = reinterpret_cast<const int32_t*>(st + L.sp_meta);
-            for (int q = threadIdx.x; q < n_split; q += ASM_THREADS) combine_split<OPS, DUU>(A, sp_block[q], sp_meta[q], partials);
+            for (int q = threadIdx.x; q < n_split; q += ASM_THREADS)
+                combine_split<OPS, DUU>(A, block0 + sp_block[q], sp_meta[q], partials);
         }
         __syncthreads();   // records, partials and this stage are free again
     }
@@ -421,23 +438,23 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
     const int64_t e = elem_idx ? elem_idx[t] : t;
     AssembleArgs A;
     A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
-    double rec[REC_STRIDE];
-    const double det = stage_element(A, (int32_t)e, c_quad.W4, rec);
+    double rec[REC_STRIDE_MAX];
+    const double det = stage_element(A, (int32_t)e, rec);
     if (!(det > 0.0)) {
         if (det < 0.0) atomicMin(bad_elem, (int32_t)e);
         else atomicMin(bad_elem + 1, (int32_t)e);
     }
-    element_dense(rec, c_quad.S, c_quad.NN, kinds,
+    element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], c_quad.W4, c_quad.S, c_quad.NN, kinds,
                   Muu ? Muu + t * 144 : nullptr, Dtu ? Dtu + t * 48 : nullptr, Dtt ? Dtt + t * 16 : nullptr,
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
 
 template <int OPS, int DUU>
 static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
-    const int rec_doubles = (d.max_elems * REC_STRIDE + 15) & ~15;          // keep what follows 128-byte aligned
-    const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::Acc::LIVE + 15) & ~15;
+    const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
+    const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
     const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
-    const size_t smem = ((size_t)rec_doubles + part_doubles) * sizeof(double) + 2 * (size_t)L.bytes + 16;
+    const size_t smem = ((size_t)rec_doubles + part_doubles) * sizeof(double) + 2 * (size_t)L.bytes + 16 + 20 * sizeof(double);
     TEFEM_REQUIRE(smem <= 220 * 1024, "tile exceeds shared memory");
     static int sm_count = 0;
     static bool attr_set = false;
@@ -487,20 +504,18 @@ extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn,
 
 extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
                               const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
-                              const int32_t* cta_mat, const double* cta_xyz, const int32_t* item_block,
-                              const int32_t* item_inc, const int32_t* item_meta, const int32_t* split_block,
-                              const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M,
+                              const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
+                              const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
+                              int ops, double alpha_M,
                               double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem,
                               void* stream) {
     TEFEM_REQUIRE(mat_table && bad_elem && h_max, "null input");
-    TEFEM_REQUIRE(cta_hdr && cta_elems && cta_conn8 && cta_mat && cta_xyz && item_block && item_inc && item_meta && inc,
-                  "null schedule");
+    TEFEM_REQUIRE(cta_hdr && cta_elems && cta_conn8 && cta_xyz && item_inc && item_meta && inc, "null schedule");
     const int max_items = h_max[0], max_elems = h_max[1], max_inc = h_max[2], max_slots = h_max[3], max_split = h_max[4],
               max_nodes = h_max[5];
     TEFEM_REQUIRE(max_split == 0 || (split_block && split_meta), "null split lists");
-    const uintptr_t align_or = (uintptr_t)cta_hdr | (uintptr_t)cta_conn8 | (uintptr_t)cta_mat | (uintptr_t)cta_xyz |
-                               (uintptr_t)item_block | (uintptr_t)item_inc | (uintptr_t)item_meta | (uintptr_t)split_block |
-                               (uintptr_t)split_meta | (uintptr_t)inc;
+    const uintptr_t align_or = (uintptr_t)cta_hdr | (uintptr_t)cta_conn8 | (uintptr_t)cta_xyz | (uintptr_t)item_inc |
+                               (uintptr_t)item_meta | (uintptr_t)split_block | (uintptr_t)split_meta | (uintptr_t)inc;
     TEFEM_REQUIRE((align_or & 15) == 0, "schedule arrays must be 16-byte aligned");
     TEFEM_REQUIRE(ops > 0 && ops < 8, "ops mask");
     TEFEM_REQUIRE(!(ops & TEFEM_OP_M) || vals_M, "vals_M");
@@ -508,17 +523,17 @@ extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta,
     TEFEM_REQUIRE(!(ops & TEFEM_OP_D) || vals_D, "vals_D");
     TEFEM_REQUIRE(max_elems > 0 && max_elems <= 4096, "max elements per tile must fit 12 bits");
     TEFEM_REQUIRE(max_nodes > 0 && max_nodes <= 256, "max nodes per tile must fit a byte");
-    TEFEM_REQUIRE(max_items > 0 && max_inc >= 0 && max_slots >= 0 && max_slots < 65536 && max_split >= 0, "tile limits");
-    TEFEM_REQUIRE(n_mat > 0, "n_mat");
+    TEFEM_REQUIRE(max_items > 0 && max_inc >= 0 && max_inc < 65536 && max_slots >= 0 && max_slots < 65536 && max_split >= 0,
+                  "tile limits");
+    TEFEM_REQUIRE(n_mat > 0 && n_mat <= 256, "1 .. 256 materials (the work items carry the material index in 8 bits)");
     if (n_cta == 0) return TEFEM_OK;
     int rc = upload_quad();
     if (rc) return rc;
     AssembleArgs A;
     memset(&A, 0, sizeof(A));
     A.mat_table = mat_table;
-    A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_mat = cta_mat; A.cta_xyz = cta_xyz;
-    A.item_block = item_block; A.item_inc = item_inc; A.item_meta = item_meta;
-    A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
+    A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_xyz = cta_xyz;
+    A.item_inc = item_inc; A.item_meta = item_meta; A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
     A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
@@ -551,11 +566,12 @@ extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, vo
 // TEFEM_HOST_EMU: sequential execution of the SAME per-thread routines (tests/host_emulation only).
 // ================================================================================================
 template <int OPS, int DUU>
-static int emu_run(const AssembleArgs& A, const TileDims& d) {
+static int emu_run(const AssembleArgs& A, const TileDims& d, int n_mat) {
     typedef typename AsmTraits<OPS, DUU>::Acc Acc;
     const QuadTables& q = quad_tables();
-    std::vector<double> recs((size_t)d.max_elems * REC_STRIDE);
-    std::vector<double> partials((size_t)d.max_slots * Acc::LIVE + 1);
+    typedef AsmTraits<OPS, DUU> T;
+    std::vector<double> recs((size_t)d.max_elems * T::REC);
+    std::vector<double> partials((size_t)d.max_slots * T::SLOT + 1);
     for (int cta = 0; cta < d.n_cta; ++cta) {
         const int32_t* h = A.cta_hdr + (size_t)HDR_STRIDE * cta;
         if (h[H_NELEMS] > d.max_elems || h[H_NITEMS] > d.max_items || h[H_NINC] > d.max_inc || h[H_NSPLIT] > d.max_split ||
@@ -569,8 +585,7 @@ static int emu_run(const AssembleArgs& A, const TileDims& d) {
             const uint32_t cn = (uint32_t)A.cta_conn8[h[H_OELEMS] + le];
             for (int a = 0; a < 4; ++a)
                 if ((int)((cn >> (8 * a)) & 0xff) >= h[H_NNODES]) return TEFEM_ERR_INVALID;
-            const double det = stage_element_local(A.mat_table, xyz, cn, A.cta_mat[h[H_OELEMS] + le], q.W4,
-                                                   recs.data() + (size_t)le * REC_STRIDE);
+            const double det = stage_element_local<T::WANT_D>(xyz, cn, recs.data() + (size_t)le * T::REC);
             if (!(det > 0.0)) {
                 const int32_t e = A.cta_elems[h[H_OELEMS] + le];
                 int32_t* slot = A.bad_elem + (det < 0.0 ? 0 : 1);
@@ -579,39 +594,41 @@ static int emu_run(const AssembleArgs& A, const TileDims& d) {
         }
         for (int it = 0; it < h[H_NITEMS]; ++it) {
             const int32_t meta = A.item_meta[h[H_OITEMS] + it];
-            const int slot = (meta >> 8) - 1;
-            const int32_t s = A.item_inc[h[H_OITEMS] + it];
-            if (slot >= d.max_slots || s < 0 || s + (meta & 0xff) > h[H_NINC]) return TEFEM_ERR_INVALID;
-            process_item<OPS, DUU>(A, A.item_block[h[H_OITEMS] + it], (uint32_t)s, meta, recs.data(), inc_s, partials.data(),
-                                   q.S, q.NN);
+            const int slot = meta_slot(meta);
+            const uint32_t iw = (uint32_t)A.item_inc[h[H_OITEMS] + it];
+            const int32_t s = (int32_t)(iw & 0xffffu);
+            if (slot >= d.max_slots || s + meta_len(meta) > h[H_NINC] || meta_mat(meta) >= n_mat) return TEFEM_ERR_INVALID;
+            process_item<OPS, DUU>(A, h[H_BLOCK0], iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
         }
-        for (int k = 0; k < h[H_NSPLIT]; ++k)
-            combine_split<OPS, DUU>(A, A.split_block[h[H_OSPLIT] + k], A.split_meta[h[H_OSPLIT] + k], partials.data());
+        for (int k = 0; k < h[H_NSPLIT]; ++k) {
+            const int32_t sm = A.split_meta[h[H_OSPLIT] + k];
+            if ((sm & 0xffff) + (int)((uint32_t)sm >> 16) > d.max_slots) return TEFEM_ERR_INVALID;
+            combine_split<OPS, DUU>(A, h[H_BLOCK0] + A.split_block[h[H_OSPLIT] + k], sm, partials.data());
+        }
     }
     return TEFEM_OK;
 }
 
-extern "C" int tefem_emu_assemble(const double* mat_table, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
-                                  const int32_t* cta_elems, const int32_t* cta_conn8, const int32_t* cta_mat,
-                                  const double* cta_xyz, const int32_t* item_block, const int32_t* item_inc,
-                                  const int32_t* item_meta, const int32_t* split_block, const int32_t* split_meta,
-                                  const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M, double alpha_K,
+extern "C" int tefem_emu_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
+                                  const int32_t* cta_elems, const int32_t* cta_conn8,
+                                  const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
+                                  const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
+                                  int ops, double alpha_M, double alpha_K,
                                   double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
     AssembleArgs A;
     memset(&A, 0, sizeof(A));
     A.mat_table = mat_table;
-    A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_mat = cta_mat; A.cta_xyz = cta_xyz;
-    A.item_block = item_block; A.item_inc = item_inc; A.item_meta = item_meta;
-    A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
+    A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_xyz = cta_xyz;
+    A.item_inc = item_inc; A.item_meta = item_meta; A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
     A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const TileDims d = {n_cta, h_max[0], h_max[1], h_max[2], h_max[3], h_max[4], h_max[5]};
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
 #define TEFEM_EMU_CASE(O)                                                     \
     case O:                                                                   \
-        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, d);      \
-        if (duu == 1) return emu_run<O, 1>(A, d);                             \
-        return emu_run<O, 2>(A, d);
+        if (duu == 0 || !((O) & TEFEM_OP_D)) return emu_run<O, 0>(A, d, n_mat);      \
+        if (duu == 1) return emu_run<O, 1>(A, d, n_mat);                             \
+        return emu_run<O, 2>(A, d, n_mat);
     switch (ops) {
         TEFEM_EMU_CASE(1) TEFEM_EMU_CASE(2) TEFEM_EMU_CASE(3) TEFEM_EMU_CASE(4)
         TEFEM_EMU_CASE(5) TEFEM_EMU_CASE(6) TEFEM_EMU_CASE(7)
@@ -628,13 +645,13 @@ extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* c
     A.coords = coords; A.conn = conn; A.mat_id = mat_id; A.mat_table = mat_table;
     const QuadTables& q = quad_tables();
     for (int64_t e = 0; e < n; ++e) {
-        double rec[REC_STRIDE];
-        const double det = stage_element(A, (int32_t)e, q.W4, rec);
+        double rec[REC_STRIDE_MAX];
+        const double det = stage_element(A, (int32_t)e, rec);
         if (!(det > 0.0)) {
             int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
             if (e < *slot) *slot = (int32_t)e;
         }
-        element_dense(rec, q.S, q.NN, kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
+        element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], q.W4, q.S, q.NN, kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
                       Dtt ? Dtt + e * 16 : nullptr, Kuu ? Kuu + e * 144 : nullptr, Kut ? Kut + e * 48 : nullptr,
                       Ktt ? Ktt + e * 16 : nullptr);
     }

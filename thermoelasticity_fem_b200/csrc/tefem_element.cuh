@@ -13,33 +13,33 @@
 //   Muu[3a+i,3b+j] = rho det NN[a][b] d_ij                                                  :220-229
 //   Dtt[a,b]       = rho c det NN[a][b]                                                     :243-252
 //   Dtu[a,3b+c]    = -beta T0 det S_a GT[c][b]                                              :231-241
+// Every form is (material constant) x (geometric factor): the geometric factors are summed per work item and the
+// constants applied once (block_finalize).
 #pragma once
 #include "tefem_common.cuh"
 
 namespace tefem {
 
-// Staged per-element record (doubles).  The odd stride keeps 8-byte shared-memory accesses of
-// consecutive records on distinct banks.
+// Staged per-element record (doubles): geometry only.  Work items are material-uniform (the symbolic phase cuts
+// a block's incidence list where the material changes), so the material constants multiply the accumulated
+// geometric sums ONCE per item instead of once per incidence: 7 (K) / 10 (M + D + K) shared-memory loads per
+// incidence instead of 11 / 17.  The odd strides keep 8-byte accesses of consecutive records on distinct banks.
 enum {
-    REC_G = 0,     // 12: G column-major, G[i][a] at REC_G + 3*a + i
-    REC_GT0 = 12,  //  3: GT[c][0]
-    REC_CL = 15,   // W4 det lambda
-    REC_CM = 16,   // W4 det mu
-    REC_CK = 17,   // W4 det k
-    REC_CB = 18,   // -beta det
-    REC_RM = 19,   // rho det
-    REC_RC = 20,   // rho c det
-    REC_CD = 21,   // -beta T0 det
-    REC_STRIDE = 23
+    REC_G = 0,      // 12: G column-major, G[i][a] at REC_G + 3*a + i
+    REC_DET = 12,   // det(Jt)
+    REC_GT0 = 13,   //  3: GT[c][0] (D only)
+    REC_STRIDE_K = 13,
+    REC_STRIDE_D = 17,
+    REC_STRIDE_MAX = 17
 };
 
 // Material table row (materials.py:5-29): rho, lambda, mu, k, c, beta, T0, pad.
 enum { MAT_RHO = 0, MAT_LAM = 1, MAT_MU = 2, MAT_K = 3, MAT_C = 4, MAT_BETA = 5, MAT_T0 = 6, MAT_STRIDE = 8 };
 
-// Geometry + material scalars of one element.  Returns det(Jt).
+// Geometry of one element.  Returns det(Jt).
+template <bool WITH_GT>
 TEFEM_HD double element_record(const double* __restrict__ X0, const double* __restrict__ X1,
-                               const double* __restrict__ X2, const double* __restrict__ X3,
-                               const double* __restrict__ mat, double W4, double* __restrict__ rec) {
+                               const double* __restrict__ X2, const double* __restrict__ X3, double* __restrict__ rec) {
     // Jt[a][b] = d x_b / d xi_a
     const double j00 = X1[0] - X0[0], j01 = X1[1] - X0[1], j02 = X1[2] - X0[2];
     const double j10 = X2[0] - X0[0], j11 = X2[1] - X0[1], j12 = X2[2] - X0[2];
@@ -60,18 +60,12 @@ TEFEM_HD double element_record(const double* __restrict__ X0, const double* __re
     rec[REC_G + 3] = i00; rec[REC_G + 4] = i10; rec[REC_G + 5] = i20;
     rec[REC_G + 6] = i01; rec[REC_G + 7] = i11; rec[REC_G + 8] = i21;
     rec[REC_G + 9] = i02; rec[REC_G + 10] = i12; rec[REC_G + 11] = i22;
-    // GT[c][0] = -(inv[0][c] + inv[1][c] + inv[2][c])
-    rec[REC_GT0 + 0] = -(i00 + i10 + i20);
-    rec[REC_GT0 + 1] = -(i01 + i11 + i21);
-    rec[REC_GT0 + 2] = -(i02 + i12 + i22);
-    const double wd = W4 * det;
-    rec[REC_CL] = wd * mat[MAT_LAM];
-    rec[REC_CM] = wd * mat[MAT_MU];
-    rec[REC_CK] = wd * mat[MAT_K];
-    rec[REC_CB] = -(mat[MAT_BETA] * det);
-    rec[REC_RM] = mat[MAT_RHO] * det;
-    rec[REC_RC] = mat[MAT_RHO] * mat[MAT_C] * det;
-    rec[REC_CD] = -(mat[MAT_BETA] * mat[MAT_T0] * det);
+    rec[REC_DET] = det;
+    if (WITH_GT) {   // GT[c][0] = -(inv[0][c] + inv[1][c] + inv[2][c])
+        rec[REC_GT0 + 0] = -(i00 + i10 + i20);
+        rec[REC_GT0 + 1] = -(i01 + i11 + i21);
+        rec[REC_GT0 + 2] = -(i02 + i12 + i22);
+    }
     return det;
 }
 
@@ -80,8 +74,8 @@ TEFEM_HD double rec_gt(const double* rec, int c, int b) {
     return b == 0 ? rec[REC_GT0 + c] : rec[REC_G + 3 * (c + 1) + (b - 1)];
 }
 
-// Accumulators of one node-pair block.  WITH_KUU/… select which parts are live so that the
-// compiler drops the dead ones per kernel instantiation.
+// Values of one node-pair block.  WITH_K/... select which parts are live so that the compiler drops the dead
+// ones per kernel instantiation.
 template <bool WITH_K, bool WITH_M, bool WITH_D>
 struct BlockAcc {
     double kuu[WITH_K ? 9 : 1];
@@ -96,7 +90,7 @@ struct BlockAcc {
         for (int i = 0; i < (WITH_D ? 3 : 1); ++i) dtu[i] = 0.0;
         ktt = 0.0; m = 0.0; dtt = 0.0;
     }
-    // number of live accumulators, and (de)serialisation for the partial sums of split incidence lists
+    // number of live values, and (de)serialisation for the partial sums of split incidence lists
     static constexpr int LIVE = (WITH_K ? 13 : 0) + (WITH_M ? 1 : 0) + (WITH_D ? 4 : 0);
     TEFEM_HD void dump(double* dst) const {
         int k = 0;
@@ -126,101 +120,73 @@ struct BlockAcc {
     }
 };
 
-// acc += contribution of block (a, b) of the element whose record is `rec`.
+// Material-free sums of one work item over its incidence entries (element e, local nodes a, b):
+//   P[3i+j] = sum W4 det G[i][a] G[j][b]      q[i] = sum det S_a G[i][b]
+//   nn      = sum det NN[a][b]                r[c] = sum det S_a GT[c][b]
 template <bool WITH_K, bool WITH_M, bool WITH_D>
-TEFEM_HD void block_accumulate(BlockAcc<WITH_K, WITH_M, WITH_D>& acc, const double* __restrict__ rec,
-                               int a, int b, const double* __restrict__ S, const double* __restrict__ NN) {
-    if (WITH_K) {
-        const double ga0 = rec[REC_G + 3 * a], ga1 = rec[REC_G + 3 * a + 1], ga2 = rec[REC_G + 3 * a + 2];
-        const double gb0 = rec[REC_G + 3 * b], gb1 = rec[REC_G + 3 * b + 1], gb2 = rec[REC_G + 3 * b + 2];
-        const double cl = rec[REC_CL], cm = rec[REC_CM];
-        const double dot = ga0 * gb0 + ga1 * gb1 + ga2 * gb2;
-        const double la0 = cl * ga0, la1 = cl * ga1, la2 = cl * ga2;
-        const double ma0 = cm * ga0, ma1 = cm * ga1, ma2 = cm * ga2;
-        const double md = cm * dot;
-        // kuu[i][j] += lam ga_i gb_j + mu ga_j gb_i (+ mu dot on the diagonal)
-        acc.kuu[0] += la0 * gb0 + ma0 * gb0 + md;
-        acc.kuu[1] += la0 * gb1 + ma1 * gb0;
-        acc.kuu[2] += la0 * gb2 + ma2 * gb0;
-        acc.kuu[3] += la1 * gb0 + ma0 * gb1;
-        acc.kuu[4] += la1 * gb1 + ma1 * gb1 + md;
-        acc.kuu[5] += la1 * gb2 + ma2 * gb1;
-        acc.kuu[6] += la2 * gb0 + ma0 * gb2;
-        acc.kuu[7] += la2 * gb1 + ma1 * gb2;
-        acc.kuu[8] += la2 * gb2 + ma2 * gb2 + md;
-        const double t = rec[REC_CB] * S[a];
-        acc.kut[0] += t * gb0;
-        acc.kut[1] += t * gb1;
-        acc.kut[2] += t * gb2;
-        acc.ktt += rec[REC_CK] * dot;
-    }
-    if (WITH_M) acc.m += rec[REC_RM] * NN[4 * a + b];
-    if (WITH_D) {
-        const double t = rec[REC_CD] * S[a];
-        acc.dtu[0] += t * rec_gt(rec, 0, b);
-        acc.dtu[1] += t * rec_gt(rec, 1, b);
-        acc.dtu[2] += t * rec_gt(rec, 2, b);
-        acc.dtt += rec[REC_RC] * NN[4 * a + b];
-    }
-}
-
-// The non-symmetric parts of the MIRROR block (j, i) of an upper block (i, j).  Its symmetric parts are those of
-// (i, j): Kuu_ji = Kuu_ij^T, Ktt, Muu, Dtt equal (NN and g_a.g_b are symmetric bit for bit); only
-//   Kut_ji[i] = -beta det S_b G[i][a]      and      Dtu_ji[c] = -beta T0 det S_b GT[c][a]
-// differ, and they need nothing beyond what (i, j) already loads except GT[:, a].
-template <bool WITH_K, bool WITH_D>
-struct MirrorAcc {
-    double kut[WITH_K ? 3 : 1];
-    double dtu[WITH_D ? 3 : 1];
+struct GeomAcc {
+    double P[WITH_K ? 9 : 1];
+    double q[WITH_K ? 3 : 1];
+    double nn;
+    double r[WITH_D ? 3 : 1];
     TEFEM_HD void clear() {
-        for (int i = 0; i < (WITH_K ? 3 : 1); ++i) kut[i] = 0.0;
-        for (int i = 0; i < (WITH_D ? 3 : 1); ++i) dtu[i] = 0.0;
+        for (int i = 0; i < (WITH_K ? 9 : 1); ++i) P[i] = 0.0;
+        for (int i = 0; i < (WITH_K ? 3 : 1); ++i) q[i] = 0.0;
+        for (int i = 0; i < (WITH_D ? 3 : 1); ++i) r[i] = 0.0;
+        nn = 0.0;
     }
 };
 
-// acc += block (a, b) and mir += the non-symmetric parts of block (b, a) of the same element.
+// acc += geometric contribution of block (a, b) of the element whose record is `rec`.
 template <bool WITH_K, bool WITH_M, bool WITH_D>
-TEFEM_HD void pair_accumulate(BlockAcc<WITH_K, WITH_M, WITH_D>& acc, MirrorAcc<WITH_K, WITH_D>& mir,
-                              const double* __restrict__ rec, int a, int b, const double* __restrict__ S,
-                              const double* __restrict__ NN) {
+TEFEM_HD void block_accumulate(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, const double* __restrict__ rec, int a, int b,
+                               double W4, const double* __restrict__ S, const double* __restrict__ NN) {
+    const double det = rec[REC_DET];
+    double ds = 0.0;
+    if (WITH_K || WITH_D) ds = det * S[a];
     if (WITH_K) {
         const double ga0 = rec[REC_G + 3 * a], ga1 = rec[REC_G + 3 * a + 1], ga2 = rec[REC_G + 3 * a + 2];
         const double gb0 = rec[REC_G + 3 * b], gb1 = rec[REC_G + 3 * b + 1], gb2 = rec[REC_G + 3 * b + 2];
-        const double cl = rec[REC_CL], cm = rec[REC_CM];
-        const double dot = ga0 * gb0 + ga1 * gb1 + ga2 * gb2;
-        const double la0 = cl * ga0, la1 = cl * ga1, la2 = cl * ga2;
-        const double ma0 = cm * ga0, ma1 = cm * ga1, ma2 = cm * ga2;
-        const double md = cm * dot;
-        acc.kuu[0] += la0 * gb0 + ma0 * gb0 + md;
-        acc.kuu[1] += la0 * gb1 + ma1 * gb0;
-        acc.kuu[2] += la0 * gb2 + ma2 * gb0;
-        acc.kuu[3] += la1 * gb0 + ma0 * gb1;
-        acc.kuu[4] += la1 * gb1 + ma1 * gb1 + md;
-        acc.kuu[5] += la1 * gb2 + ma2 * gb1;
-        acc.kuu[6] += la2 * gb0 + ma0 * gb2;
-        acc.kuu[7] += la2 * gb1 + ma1 * gb2;
-        acc.kuu[8] += la2 * gb2 + ma2 * gb2 + md;
-        const double cb = rec[REC_CB];
-        const double t = cb * S[a], u = cb * S[b];
-        acc.kut[0] += t * gb0;
-        acc.kut[1] += t * gb1;
-        acc.kut[2] += t * gb2;
-        mir.kut[0] += u * ga0;
-        mir.kut[1] += u * ga1;
-        mir.kut[2] += u * ga2;
-        acc.ktt += rec[REC_CK] * dot;
+        const double wd = W4 * det;
+        const double w0 = wd * ga0, w1 = wd * ga1, w2 = wd * ga2;
+        acc.P[0] += w0 * gb0; acc.P[1] += w0 * gb1; acc.P[2] += w0 * gb2;
+        acc.P[3] += w1 * gb0; acc.P[4] += w1 * gb1; acc.P[5] += w1 * gb2;
+        acc.P[6] += w2 * gb0; acc.P[7] += w2 * gb1; acc.P[8] += w2 * gb2;
+        acc.q[0] += ds * gb0;
+        acc.q[1] += ds * gb1;
+        acc.q[2] += ds * gb2;
     }
-    if (WITH_M) acc.m += rec[REC_RM] * NN[4 * a + b];
+    if (WITH_M || WITH_D) acc.nn += det * NN[4 * a + b];
     if (WITH_D) {
-        const double cd = rec[REC_CD];
-        const double t = cd * S[a], u = cd * S[b];
-        acc.dtu[0] += t * rec_gt(rec, 0, b);
-        acc.dtu[1] += t * rec_gt(rec, 1, b);
-        acc.dtu[2] += t * rec_gt(rec, 2, b);
-        mir.dtu[0] += u * rec_gt(rec, 0, a);
-        mir.dtu[1] += u * rec_gt(rec, 1, a);
-        mir.dtu[2] += u * rec_gt(rec, 2, a);
-        acc.dtt += rec[REC_RC] * NN[4 * a + b];
+        acc.r[0] += ds * rec_gt(rec, 0, b);
+        acc.r[1] += ds * rec_gt(rec, 1, b);
+        acc.r[2] += ds * rec_gt(rec, 2, b);
+    }
+}
+
+// The block values of a material-uniform item: out = material constants x geometric sums
+// (Kuu/Kut/Ktt elements.py:254-286, Muu :220-229, Dtu :231-241, Dtt :243-252).
+template <bool WITH_K, bool WITH_M, bool WITH_D>
+TEFEM_HD void block_finalize(const GeomAcc<WITH_K, WITH_M, WITH_D>& g, const double* __restrict__ mat,
+                             BlockAcc<WITH_K, WITH_M, WITH_D>& out) {
+    out.clear();
+    if (WITH_K) {
+        const double lam = mat[MAT_LAM], mu = mat[MAT_MU];
+        const double md = mu * (g.P[0] + g.P[4] + g.P[8]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                out.kuu[3 * i + j] = lam * g.P[3 * i + j] + mu * g.P[3 * j + i] + (i == j ? md : 0.0);
+        const double nb = -mat[MAT_BETA];
+        out.kut[0] = nb * g.q[0]; out.kut[1] = nb * g.q[1]; out.kut[2] = nb * g.q[2];
+        out.ktt = mat[MAT_K] * (g.P[0] + g.P[4] + g.P[8]);
+    }
+    if (WITH_M || WITH_D) out.m = mat[MAT_RHO] * g.nn;
+    if (WITH_D) {
+        const double nbt = -(mat[MAT_BETA] * mat[MAT_T0]);
+        out.dtu[0] = nbt * g.r[0]; out.dtu[1] = nbt * g.r[1]; out.dtu[2] = nbt * g.r[2];
+        out.dtt = mat[MAT_RHO] * mat[MAT_C] * g.nn;
     }
 }
 

@@ -37,13 +37,12 @@ class DeviceMesh:
         self.mat_table = torch.as_tensor(mat_table, dtype=torch.float64).to(dev).contiguous()
         self.n_mat = int(self.mat_table.shape[0])
         if schedule is None:
-            schedule = build_schedule(conn_t, self.n_nodes, self.n_rows)
+            schedule = build_schedule(conn_t, self.n_nodes, self.n_rows, mat_id=self.mat_id)
         self.schedule: Schedule = schedule.to(dev)
         del conn_t
-        # per-tile copies of the staged elements' material index and of the tile nodes' coordinates (the
-        # byte-packed connectivity is part of the schedule): every tile segment is one bulk copy for K1
+        # per-tile copy of the tile nodes' coordinates (the byte-packed connectivity and the material of every
+        # work item are part of the schedule): every tile segment is one bulk copy for K1
         S = self.schedule
-        self.cta_mat = self.mat_id[S.cta_elems.long().clamp(min=0)].contiguous()
         self.cta_xyz = self.coords[S.cta_nodes.long()].contiguous()
         self._h_max = np.array([S.max_cta_items, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, S.max_cta_split,
                                 S.max_cta_nodes], dtype=np.int32)
@@ -67,8 +66,8 @@ class DeviceMesh:
         p = _lib.ptr
         _lib.check(self.lib.tefem_assemble(
             p(self.mat_table), self.n_mat, S.n_cta, p(self._h_max), p(S.cta_hdr), p(S.cta_elems),
-            p(S.cta_conn8), p(self.cta_mat), p(self.cta_xyz), p(S.item_block), p(S.item_inc), p(S.item_meta),
-            p(S.split_block), p(S.split_meta), p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
+            p(S.cta_conn8), p(self.cta_xyz), p(S.item_inc), p(S.item_meta), p(S.split_block), p(S.split_meta),
+            p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
             p(out.get("M")) if "M" in ops else None, p(out.get("K")) if "K" in ops else None,
             p(out.get("D")) if "D" in ops else None, p(self.bad_elem), _lib.stream_ptr()))
         if check:

@@ -16,13 +16,17 @@ Outputs (see include/tefem.h, tefem_assemble):
   tile-packed schedule       a tile owns a contiguous range of node rows; everything it needs is stored in
                              per-tile segments that start on 16-byte boundaries (each segment is fetched with
                              one bulk copy into shared memory):
-    cta_hdr[n_cta, 12]         n_items, n_elems, n_inc, n_split, n_nodes, then the five segment offsets
-    item_block/inc/meta        work items: a block, or a chunk of a block whose incidence list is long (the
-                               diagonal blocks); item_inc = first incidence entry (tile-relative),
-                               item_meta = length | (partial slot + 1) << 8
+    cta_hdr[n_cta, 12]         n_items, n_elems, n_inc, n_split, n_nodes, the five segment offsets, first block
+    item_block/inc/meta        work items: a block, or a piece of a block's incidence list - lists are cut where
+                               the material of the elements changes (every item is material-uniform, the kernel
+                               applies the material constants once per item) and long uniform runs (the diagonal
+                               blocks) into chunks; items are stored in block order, so consecutive threads
+                               write consecutive addresses of every plane (coalesced stores);
+                               item_inc = first incidence entry (tile-relative) | tile-local block << 16,
+                               item_meta = length | (partial slot + 1) << 8 | material << 24
     inc                        incidence entries (tile-local element << 4) | (a << 2) | b, block after block,
                                ascending element inside a block (the reference's summation order)
-    split_block/meta           blocks whose list was split: block, first slot | n_chunks << 16
+    split_block/meta           blocks with more than one item: tile-local block, first slot | n_items << 16
     cta_elems, cta_conn8       elements the tile stages, and their connectivity as 4 tile-local node bytes
     cta_nodes                  nodes whose coordinates the tile stages
 """
@@ -31,12 +35,12 @@ from dataclasses import dataclass
 import torch
 
 ITEMS_PER_CTA = 256          # = ASM_THREADS of tefem_assemble.cu
-ELEM_BUDGET_PER_CTA = 330    # bound on the sum of node degrees per tile (>= staged elements; ~256 on Kuhn meshes)
+ELEM_BUDGET_PER_CTA = 310    # bound on the sum of node degrees per tile (>= staged elements; ~246 on Kuhn meshes)
 MAX_CHUNK = 8                # lists longer than 2 * MAX_CHUNK are split into chunks of <= MAX_CHUNK
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
 HDR_STRIDE = 12
-H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES = range(10)
+H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0 = range(11)
 
 
 @dataclass
@@ -67,7 +71,7 @@ class Schedule:
     item_block: torch.Tensor     # int32 [padded]
     item_inc: torch.Tensor       # int32 [padded] tile-relative
     item_meta: torch.Tensor      # int32 [padded]
-    split_block: torch.Tensor    # int32 [padded]
+    split_block: torch.Tensor    # int32 [padded] tile-local block
     split_meta: torch.Tensor     # int32 [padded]
 
     def to(self, device):
@@ -77,10 +81,9 @@ class Schedule:
         return Schedule(**kw)
 
     def schedule_bytes(self):
-        """Bytes of slot-map / schedule data one assembly launch reads (cta_mat / cta_xyz are counted by DeviceMesh)."""
+        """Bytes of slot-map / schedule data one assembly launch reads (cta_xyz is counted by DeviceMesh)."""
         return sum(t.numel() * t.element_size() for t in
-                   (self.inc, self.cta_hdr, self.cta_conn8, self.item_block, self.item_inc, self.item_meta,
-                    self.split_block, self.split_meta))
+                   (self.inc, self.cta_hdr, self.cta_conn8, self.item_inc, self.item_meta, self.split_block, self.split_meta))
 
 
 def _excl_cumsum(x):
@@ -111,23 +114,24 @@ class _TileTooLarge(Exception):
 
 def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                    items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA,
-                   max_chunk: int = MAX_CHUNK) -> Schedule:
+                   max_chunk: int = MAX_CHUNK, mat_id: torch.Tensor = None) -> Schedule:
     """conn: integer tensor [E, 4] in the reference's element order; node numbers < n_nodes.
     n_rows: only rows of nodes < n_rows are assembled (row-partitioned multi-GPU: owned nodes
     are numbered first); default all.
+    mat_id: material row of every element (< 256); default: one material (row 0).
 
     A tile must not reference more than 256 nodes / 4096 elements (byte / 12-bit local numbers); meshes whose
     node numbering has little locality (e.g. the Gmsh numbering of data/sandwich.msh) get smaller tiles."""
     for _ in range(12):
         try:
-            return _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk)
+            return _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id)
         except _TileTooLarge:
             items_per_cta = max(16, (3 * items_per_cta) // 4)
             elem_budget = max(32, (3 * elem_budget) // 4)
     raise RuntimeError("could not build a tile schedule within the shared-memory index limits")
 
 
-def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk):
+def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id=None):
     assert conn.dim() == 2 and conn.shape[1] == 4
     assert 1 <= max_chunk <= 127
     dev = conn.device
@@ -155,15 +159,32 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
     block_col = ukey - block_row * N
     del ukey
     inc_ptr = _ptr_from_counts(counts, P, dev)
+    n_inc = int(src.numel())
+    # ---- material-uniform runs of every block's incidence list ("sub-blocks", in list order)
+    blk_of_inc = torch.repeat_interleave(torch.arange(P, **i64), counts)
+    new_run = torch.zeros(n_inc, dtype=torch.bool, device=dev)
+    new_run[inc_ptr[:-1]] = True
+    if mat_id is not None:
+        mat_id = mat_id.to(device=dev, dtype=torch.int64)
+        assert int(mat_id.numel()) == E and (E == 0 or (int(mat_id.min()) >= 0 and int(mat_id.max()) < 256))
+        mat_of_inc = mat_id[torch.div(src, 16, rounding_mode='floor')]
+        new_run[1:] |= mat_of_inc[1:] != mat_of_inc[:-1]
+    run_start = torch.nonzero(new_run).reshape(-1)                               # unpadded absolute position
+    n_runs = int(run_start.numel())
+    run_block = blk_of_inc[run_start]
+    run_len = torch.diff(run_start, append=torch.tensor([n_inc], **i64))
+    run_mat = mat_of_inc[run_start] if mat_id is not None else torch.zeros(n_runs, **i64)
+    del blk_of_inc, new_run
     blocks_per_row = torch.bincount(block_row, minlength=R)
     rowptr = _ptr_from_counts(blocks_per_row, R, dev)
     diag_idx = torch.nonzero(block_row == block_col).reshape(-1)
     assert int(diag_idx.numel()) == R, "every owned node must belong to at least one element"
 
     # ---- work items: lists longer than 2 * max_chunk (the diagonal blocks) are split into balanced chunks
-    n_chunks = torch.where(counts > 2 * max_chunk, torch.div(counts + (max_chunk - 1), max_chunk, rounding_mode='floor'),
-                           torch.ones_like(counts))
-    items_per_row = torch.zeros(R, **i64).index_add_(0, block_row, n_chunks)
+    n_chunks = torch.where(run_len > 2 * max_chunk, torch.div(run_len + (max_chunk - 1), max_chunk, rounding_mode='floor'),
+                           torch.ones_like(run_len))                             # per run
+    items_per_block = torch.zeros(P, **i64).index_add_(0, run_block, n_chunks)
+    items_per_row = torch.zeros(R, **i64).index_add_(0, block_row, items_per_block)
 
     # ---- rows -> tiles: cumulative cost, integer arithmetic (work items vs. staged-element budget)
     degree = torch.bincount(conn.reshape(-1), minlength=N)[:R]
@@ -220,47 +241,51 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
     inc_p, inc_pptr, inc_pos = _pad_segments(packed, cta_of_inc, cta_inc_ptr, n_cta, 8, 0)
     del packed, cta_of_inc
     block_inc_abs = inc_pos[inc_ptr[:-1]]                                        # every block has >= 1 incidence
+    run_inc_abs = inc_pos[run_start]
     del inc_pos
     max_cta_inc = int((cta_inc_ptr[1:] - cta_inc_ptr[:-1]).max().item()) if n_cta else 0
 
     # ---- item arrays in (block, chunk) order
     n_items = int(n_chunks.sum().item())
-    item_blk = torch.repeat_interleave(torch.arange(P, **i64), n_chunks)
-    chunk = torch.arange(n_items, **i64) - _excl_cumsum(n_chunks)[item_blk]
-    base_len = torch.div(counts, n_chunks, rounding_mode='floor')[item_blk]
-    rem = (counts - torch.div(counts, n_chunks, rounding_mode='floor') * n_chunks)[item_blk]
+    item_run = torch.repeat_interleave(torch.arange(n_runs, **i64), n_chunks)
+    item_blk = run_block[item_run]                                               # ascending: runs are in block order
+    chunk = torch.arange(n_items, **i64) - _excl_cumsum(n_chunks)[item_run]
+    base_len = torch.div(run_len, n_chunks, rounding_mode='floor')[item_run]
+    rem = (run_len - torch.div(run_len, n_chunks, rounding_mode='floor') * n_chunks)[item_run]
     item_len = base_len + (chunk < rem).to(torch.int64)
     if n_items and int(item_len.max().item()) > 255:
         raise _TileTooLarge()
     cta_of_item = cta_of_block[item_blk]
     # first entry relative to the tile's (padded) incidence segment
-    item_inc = block_inc_abs[item_blk] - inc_pptr[cta_of_item] + chunk * base_len + torch.minimum(chunk, rem)
-    is_split = n_chunks[item_blk] > 1
+    item_inc = run_inc_abs[item_run] - inc_pptr[cta_of_item] + chunk * base_len + torch.minimum(chunk, rem)
     cta_item_ptr = _ptr_from_counts(torch.bincount(cta_of_item, minlength=n_cta), n_cta, dev)
     max_cta_items = int((cta_item_ptr[1:] - cta_item_ptr[:-1]).max().item()) if n_cta else 0
+    blocks_per_cta = torch.bincount(cta_of_block, minlength=n_cta)
+    if max_cta_inc >= 65536 or (n_cta and int(blocks_per_cta.max().item()) >= 65536):
+        raise _TileTooLarge()
+    # blocks with several items park partial sums in shared-memory slots (rank among the tile's split items)
+    is_split = items_per_block[item_blk] > 1
     split_run = _excl_cumsum(is_split.to(torch.int64))                           # global rank among split items
     slot = split_run - split_run[cta_item_ptr[:-1].clamp(max=max(n_items - 1, 0))][cta_of_item]
-    item_meta = item_len | torch.where(is_split, (slot + 1) << 8, torch.zeros_like(slot))
-    # split blocks of each tile
-    blk_split = torch.nonzero(n_chunks > 1).reshape(-1)
-    first_item = _excl_cumsum(n_chunks)[blk_split]
-    split_meta = slot[first_item] | (n_chunks[blk_split] << 16)
+    item_meta = item_len | torch.where(is_split, (slot + 1) << 8, torch.zeros_like(slot)) | (run_mat[item_run] << 24)
+    item_meta = torch.where(item_meta >= 2 ** 31, item_meta - 2 ** 32, item_meta)            # int32 bit pattern
+    local_blk = item_blk - cta_blk_ptr[cta_of_item]                              # tiles own contiguous block ranges
+    item_inc = item_inc | (local_blk << 16)
+    blk_split = torch.nonzero(items_per_block > 1).reshape(-1)
+    first_item = _excl_cumsum(items_per_block)[blk_split]
+    split_meta = slot[first_item] | (items_per_block[blk_split] << 16)
     cta_of_split = cta_of_block[blk_split]
+    split_local = blk_split - cta_blk_ptr[cta_of_split]
     cta_split_ptr = _ptr_from_counts(torch.bincount(cta_of_split, minlength=n_cta), n_cta, dev)
     max_cta_split = int((cta_split_ptr[1:] - cta_split_ptr[:-1]).max().item()) if n_cta else 0
     slots_per_cta = torch.zeros(n_cta, **i64).index_add_(0, cta_of_item, is_split.to(torch.int64))
     max_cta_slots = int(slots_per_cta.max().item()) if n_cta else 0
     assert max_cta_slots < 65536
-    # order the items of each tile longest first (homogeneous warps), stable inside equal lengths
-    maxlen = int(item_len.max().item()) if n_items else 0
-    perm = torch.sort(cta_of_item * (maxlen + 1) + (maxlen - item_len), stable=True)[1]
-    item_blk, item_inc, item_meta = item_blk[perm], item_inc[perm], item_meta[perm]
-    del perm                                                                     # cta_of_item is unchanged by the permutation
 
     item_block_p, item_pptr, _ = _pad_segments(item_blk, cta_of_item, cta_item_ptr, n_cta, 4, 0)
     item_inc_p, _, _ = _pad_segments(item_inc, cta_of_item, cta_item_ptr, n_cta, 4, 0)
     item_meta_p, _, _ = _pad_segments(item_meta, cta_of_item, cta_item_ptr, n_cta, 4, 0)      # padding: length 0
-    split_block_p, split_pptr, _ = _pad_segments(blk_split, cta_of_split, cta_split_ptr, n_cta, 4, 0)
+    split_block_p, split_pptr, _ = _pad_segments(split_local, cta_of_split, cta_split_ptr, n_cta, 4, 0)
     split_meta_p, _, _ = _pad_segments(split_meta, cta_of_split, cta_split_ptr, n_cta, 4, 0)
     elems_p, elem_pptr, _ = _pad_segments(cta_elems, cta_of_k2, cta_elem_ptr, n_cta, 4, -1)
     conn8_p, _, _ = _pad_segments(conn8, cta_of_k2, cta_elem_ptr, n_cta, 4, 0)
@@ -275,7 +300,8 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
         return ptr[1:] - ptr[:-1]
     zero = torch.zeros(n_cta, **i64)
     cta_hdr = torch.stack([cnt(cta_item_ptr), cnt(cta_elem_ptr), cnt(cta_inc_ptr), cnt(cta_split_ptr), cnt(cta_node_ptr),
-                           item_pptr[:-1], elem_pptr[:-1], inc_pptr[:-1], split_pptr[:-1], node_pptr[:-1], zero, zero], dim=1)
+                           item_pptr[:-1], elem_pptr[:-1], inc_pptr[:-1], split_pptr[:-1], node_pptr[:-1], cta_blk_ptr[:-1],
+                           zero], dim=1)
     assert int(inc_pptr[-1].item()) < 2 ** 31
 
     i32 = torch.int32

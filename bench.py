@@ -24,6 +24,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"      # stdout carries exactly one JSON line (NCCL prints its version banner there)
 
 MAT2 = dict(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.)     # examples/example_transient_2.py:29
 T_END, N_T = 1800e0, 1000                                                    # example_transient_2.py:20-21

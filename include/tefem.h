@@ -252,8 +252,18 @@ typedef struct tefem_comm tefem_comm;
 int tefem_comm_unique_id(const char* h_nccl_lib_path, char* h_id);
 int tefem_comm_create(tefem_comm** out, const char* h_nccl_lib_path, const char* h_id, int n_ranks, int rank);
 int tefem_comm_destroy(tefem_comm* c);
-/* in-place sum all-reduce of n doubles (dot-product packets) */
+/* in-place sum all-reduce of n doubles with NCCL (set-up paths) */
 int tefem_comm_allreduce_sum(tefem_comm* c, double* buf, int n, void* stream);
+/* Peer-memory region for the reductions of the solve (csrc/tefem_peer.cuh): the dot-product packets of BiCGSTAB and
+ * the restricted residual of the coarse correction are all-reduced INSIDE the kernels that consume them, by direct
+ * loads from the other GPUs' memory over NVLink / NVSwitch (no NCCL call, no extra launch).  Every rank allocates
+ * its region (big_cap_doubles >= 4 * n_coarse of the preconditioner, 0 without one) and receives a 64-byte CUDA IPC
+ * handle in h_handle; the caller gathers the handles of all ranks (rank order, n_ranks * 64 bytes) and passes them
+ * to tefem_comm_shm_open on every rank.  One node, at most 8 ranks.  tefem_comm_check reports a time-out of a
+ * peer wait (call after a stream synchronisation; tefem_bicgstab does).                                          */
+int tefem_comm_shm_alloc(tefem_comm* c, int64_t big_cap_doubles, char* h_handle);
+int tefem_comm_shm_open(tefem_comm* c, const char* h_handles);
+int tefem_comm_check(tefem_comm* c);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,9 @@ _SIGNATURES = {
     "tefem_comm_create": [P, c_char_p, P, c_int, c_int],
     "tefem_comm_destroy": [P],
     "tefem_comm_allreduce_sum": [P, P, c_int, P],
+    "tefem_comm_shm_alloc": [P, c_int64, P],
+    "tefem_comm_shm_open": [P, P],
+    "tefem_comm_check": [P],
 }
 _RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32]), "tefem_launch_count": (c_int64, []),
              "tefem_precond_work_doubles": (c_int64, [c_int32, c_int32])}

@@ -4,6 +4,7 @@
 // partitions) and packed dot-product all-reduces (<= 5 doubles).
 #include "tefem_common.cuh"
 #include "tefem_comm.h"
+#include "tefem_peer.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -68,6 +69,12 @@ using namespace tefem;
 struct tefem_comm {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
+    // peer-memory region (tefem_peer.cuh): local allocation, the mapped regions of all ranks, epochs per channel
+    char* shm_local = nullptr;
+    char* shm_base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t shm_cap = 0;
+    uint32_t epoch[2] = {0, 0};
+    int* d_err = nullptr;
 };
 
 extern "C" int tefem_comm_unique_id(const char* h_nccl_lib_path, char* h_id) {
@@ -101,6 +108,10 @@ extern "C" int tefem_comm_create(tefem_comm** out, const char* h_nccl_lib_path, 
 
 extern "C" int tefem_comm_destroy(tefem_comm* c) {
     if (!c) return TEFEM_OK;
+    for (int r = 0; r < c->n_ranks && r < PEER_MAX_RANKS; ++r)
+        if (r != c->rank && c->shm_base[r]) cudaIpcCloseMemHandle(c->shm_base[r]);
+    if (c->shm_local) cudaFree(c->shm_local);
+    if (c->d_err) cudaFree(c->d_err);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     delete c;
     return TEFEM_OK;
@@ -122,5 +133,63 @@ int tefem_comm_neighbor_exchange(tefem_comm* c, int n_nbr, const int32_t* nbr, c
         if (nr) TEFEM_NCCL_CHECK(g_nccl.Recv(recv + 4 * (size_t)recv_ptr[k], nr, ncclDouble, nbr[k], c->comm, st));
     }
     TEFEM_NCCL_CHECK(g_nccl.GroupEnd());
+    return TEFEM_OK;
+}
+
+// ---- peer-memory region --------------------------------------------------------------------------
+
+extern "C" int tefem_comm_shm_alloc(tefem_comm* c, int64_t big_cap_doubles, char* h_handle) {
+    TEFEM_REQUIRE(c && h_handle && big_cap_doubles >= 0, "arguments");
+    TEFEM_REQUIRE(c->n_ranks <= PEER_MAX_RANKS, "peer-memory reductions support up to 8 ranks (one node)");
+    TEFEM_REQUIRE(!c->shm_local, "peer-memory region already allocated");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    const int64_t cap = (big_cap_doubles + 15) / 16 * 16;
+    const size_t bytes = (size_t)PEER_BIG_OFFSET + 2 * (size_t)cap * sizeof(double);
+    TEFEM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->shm_local), bytes));
+    TEFEM_CUDA_CHECK(cudaMemset(c->shm_local, 0, bytes));
+    TEFEM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_err), sizeof(int)));
+    TEFEM_CUDA_CHECK(cudaMemset(c->d_err, 0, sizeof(int)));
+    TEFEM_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    TEFEM_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->shm_local));
+    memcpy(h_handle, &h, sizeof(h));
+    c->shm_cap = cap;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_comm_shm_open(tefem_comm* c, const char* h_handles) {
+    TEFEM_REQUIRE(c && h_handles && c->shm_local, "allocate the local region first");
+    for (int r = 0; r < c->n_ranks; ++r) {
+        if (r == c->rank) { c->shm_base[r] = c->shm_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_handles + 64 * (size_t)r, sizeof(h));
+        void* p = nullptr;
+        TEFEM_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->shm_base[r] = reinterpret_cast<char*>(p);
+    }
+    return TEFEM_OK;
+}
+
+bool tefem_comm_has_peer(const tefem_comm* c) { return c && c->shm_base[c->n_ranks - 1] != nullptr && c->shm_base[0] != nullptr; }
+int64_t tefem_comm_peer_cap(const tefem_comm* c) { return c ? c->shm_cap : 0; }
+
+PeerCtx tefem_comm_peer_ctx(tefem_comm* c, int channel) {
+    PeerCtx ctx;
+    ctx.world = c->n_ranks; ctx.rank = c->rank; ctx.channel = channel; ctx.cap = c->shm_cap;
+    ctx.epoch = ++c->epoch[channel];
+    for (int r = 0; r < c->n_ranks; ++r) ctx.base[r] = c->shm_base[r];
+    ctx.err = c->d_err;
+    return ctx;
+}
+
+// Call after a stream synchronisation: reports a time-out recorded by a peer wait.
+extern "C" int tefem_comm_check(tefem_comm* c) {
+    if (!c || !c->d_err) return TEFEM_OK;
+    int e = 0;
+    TEFEM_CUDA_CHECK(cudaMemcpy(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) {
+        set_error("peer-memory reduction timed out waiting for another rank");
+        return TEFEM_ERR_NCCL;
+    }
     return TEFEM_OK;
 }

@@ -3,6 +3,12 @@
 #pragma once
 #include "tefem.h"
 #include <cuda_runtime.h>
+#include "tefem_peer.cuh"
+
+// Peer-memory reductions (tefem_peer.cuh): available once tefem_comm_shm_alloc / _open have run on every rank.
+bool tefem_comm_has_peer(const tefem_comm* c);
+int64_t tefem_comm_peer_cap(const tefem_comm* c);
+tefem::PeerCtx tefem_comm_peer_ctx(tefem_comm* c, int channel);      // next epoch of that channel
 
 // Packed point-to-point exchange with the neighbouring row blocks: for neighbour k, the doubles
 // send[4*send_ptr[k] .. 4*send_ptr[k+1]) go to rank nbr[k] and recv[4*recv_ptr[k] .. 4*recv_ptr[k+1])

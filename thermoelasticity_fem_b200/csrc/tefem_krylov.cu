@@ -180,7 +180,7 @@ __device__ __forceinline__ double field_measure(double rr_u, double rr_t, double
     return fmax(mu, mt);
 }
 
-__global__ void scalars_init_kernel(double* sc, int* ictl, double rtol2) {
+__device__ __forceinline__ void scalars_init(double* sc, int* ictl, double rtol2) {
     const double rr_u = sc[SC_PKT], rr_t = sc[SC_PKT + 1], bb_u = sc[SC_PKT + 2], bb_t = sc[SC_PKT + 3];
     const double xx_u = sc[SC_PKT + 4], xx_t = sc[SC_PKT + 5];
     const double bb = bb_u + bb_t;
@@ -195,7 +195,7 @@ __global__ void scalars_init_kernel(double* sc, int* ictl, double rtol2) {
     if (sc[SC_RR] <= rtol2) { ictl[IN_STOP] = 1; ictl[IN_REASON] = 1; }
 }
 
-__global__ void scalars_alpha_kernel(double* sc, int* ictl, int iter) {
+__device__ __forceinline__ void scalars_alpha(double* sc, int* ictl, int iter) {
     if (ictl[IN_STOP]) return;
     const double rhv = sc[SC_PKT];
     sc[SC_RHV] = rhv;
@@ -203,7 +203,7 @@ __global__ void scalars_alpha_kernel(double* sc, int* ictl, int iter) {
     sc[SC_ALPHA] = sc[SC_RHO] / rhv;
 }
 
-__global__ void scalars_omega_kernel(double* sc, int* ictl, int iter, double rtol2) {
+__device__ __forceinline__ void scalars_omega(double* sc, int* ictl, int iter, double rtol2) {
     if (ictl[IN_STOP]) return;
     const double ts_u = sc[SC_PKT], ts_t = sc[SC_PKT + 1], tt_u = sc[SC_PKT + 2], tt_t = sc[SC_PKT + 3];
     const double ss_u = sc[SC_PKT + 4], ss_t = sc[SC_PKT + 5], hs = sc[SC_PKT + 6], ht = sc[SC_PKT + 7];
@@ -236,6 +236,59 @@ __global__ void scalars_omega_kernel(double* sc, int* ictl, int iter, double rto
         return;
     }
     sc[SC_BETA] = (rho_new / rho) * (alpha / omega);
+}
+
+// One reduction point of the iteration in ONE kernel (one CTA): fixed-order sum of the per-CTA partials, the
+// all-reduce over the ranks through NVLink peer memory (tefem_peer.cuh: every rank adds the packets of all ranks
+// in rank order, so the scalars - and the stop decision - are bitwise identical everywhere), and the BiCGSTAB
+// scalar update.  MODE 0: (re)start, 1: alpha, 2: omega / beta / convergence.  The exchange is executed even after
+// the stop flag is set: the epochs of all ranks must advance together.
+template <int NV, int MODE>
+__global__ void __launch_bounds__(256) reduce_scalars_kernel(const double* __restrict__ partials, int n_cta, double* sc,
+                                                             int* ictl, int iter, double rtol2, const PeerCtx pc) {
+    __shared__ double red[NV * 32];
+    __shared__ double pk[PEER_MAX_RANKS][NV];
+    double d[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) d[k] = 0.0;
+    for (int c = threadIdx.x; c < n_cta; c += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) d[k] += partials[(size_t)c * NV + k];
+    block_reduce_sum<NV>(d, red);
+    if (pc.world > 1) {
+        if (threadIdx.x == 0) {
+            double* mine = peer_small(pc, pc.rank);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) mine[k] = d[k];
+            __threadfence_system();
+        }
+        __syncthreads();
+        peer_signal(pc, threadIdx.x);
+        peer_wait(pc, threadIdx.x);
+        if ((int)threadIdx.x < pc.world) {
+            const double* src = peer_small(pc, threadIdx.x);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) pk[threadIdx.x][k] = ld_volatile_f64(src + k);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double a = 0.0;
+                for (int r = 0; r < pc.world; ++r) a += pk[r][k];
+                d[k] = a;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (MODE == 0 || !ictl[IN_STOP]) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) sc[SC_PKT + k] = d[k];
+        }
+        if (MODE == 0) scalars_init(sc, ictl, rtol2);
+        if (MODE == 1) scalars_alpha(sc, ictl, iter);
+        if (MODE == 2) scalars_omega(sc, ictl, iter, rtol2);
+    }
 }
 
 // s = r - alpha v
@@ -590,11 +643,15 @@ static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* coli
     return prof_end(s, st);
 }
 
-template <int NV>
-static int reduce_to_packet(tefem_solver* s, int n_cta, cudaStream_t st) {
-    reduce_partials_kernel<NV><<<1, 256, 0, st>>>(s->partials, n_cta, s->sc + SC_PKT, 0);
+template <int NV, int MODE>
+static int reduce_scalars(tefem_solver* s, int n_cta, int iter, double rtol2, cudaStream_t st) {
+    PeerCtx pc;                                           // world = 1: no exchange
+    if (s->comm) {
+        TEFEM_REQUIRE(tefem_comm_has_peer(s->comm), "multi-GPU solves need the peer-memory region (tefem_comm_shm_alloc / _open)");
+        pc = tefem_comm_peer_ctx(s->comm, PEER_CH_DOTS);
+    }
+    reduce_scalars_kernel<NV, MODE><<<1, 256, 0, st>>>(s->partials, n_cta, s->sc, s->ictl, iter, rtol2, pc);
     TEFEM_LAUNCH_CHECK();
-    if (s->comm) return tefem_comm_allreduce_sum(s->comm, s->sc + SC_PKT, NV, st);
     return TEFEM_OK;
 }
 
@@ -640,10 +697,8 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         if (rc) return rc;
         init_residual_kernel<<<vgrid, 256, 0, st>>>(n, b, s->t, x, s->r, s->rhat, s->p, s->partials);
         TEFEM_LAUNCH_CHECK();
-        rc = reduce_to_packet<6>(s, vgrid, st);
+        rc = reduce_scalars<6, 0>(s, vgrid, 0, rtol2, st);
         if (rc) return rc;
-        scalars_init_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, rtol2);
-        TEFEM_LAUNCH_CHECK();
         TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_sc, s->sc, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, st));
         TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -680,10 +735,8 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
                 }
                 rc = dist_spmv<1>(s, rowptr, colidx, sys, pdir, s->v, s->rhat, nullptr, s->ictl, &npc, st);
                 if (rc) return rc;
-                rc = reduce_to_packet<1>(s, npc, st);
+                rc = reduce_scalars<1, 1>(s, npc, it, rtol2, st);
                 if (rc) return rc;
-                scalars_alpha_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, it);
-                TEFEM_LAUNCH_CHECK();
                 update_s_kernel<<<vgrid, 256, 0, st>>>(n, s->r, s->v, s->s, s->sc, s->ictl);
                 TEFEM_LAUNCH_CHECK();
                 double* sdir = s->s;
@@ -694,15 +747,14 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
                 }
                 rc = dist_spmv<8>(s, rowptr, colidx, sys, sdir, s->t, s->rhat, s->s, s->ictl, &npc, st);
                 if (rc) return rc;
-                rc = reduce_to_packet<8>(s, npc, st);
+                rc = reduce_scalars<8, 2>(s, npc, it, rtol2, st);
                 if (rc) return rc;
-                scalars_omega_kernel<<<1, 1, 0, st>>>(s->sc, s->ictl, it, rtol2);
-                TEFEM_LAUNCH_CHECK();
                 update_xrp_kernel<<<vgrid, 256, 0, st>>>(n, x, s->r, s->p, s->s, s->t, s->v, pdir, sdir, s->sc, s->ictl, it);
                 TEFEM_LAUNCH_CHECK();
             }
             TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (s->comm) { rc = tefem_comm_check(s->comm); if (rc) return rc; }
             if (s->profile) {
                 const int done_now = s->h_ictl[IN_ITERS] - iters_seen;      // iterations that really ran in this batch
                 rc = prof_harvest(s, 2 * (size_t)(done_now > 0 ? done_now : 0));

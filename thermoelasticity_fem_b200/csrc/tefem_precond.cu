@@ -87,6 +87,39 @@ __global__ void __launch_bounds__(256) coarse_start_kernel(int64_t n, const doub
     xc[k] = wc * b;
 }
 
+// Multi-GPU form of coarse_start_kernel, fused with the all-reduce of the restricted residual over NVLink peer
+// memory (tefem_peer.cuh): every rank's restriction kernel wrote its partial P1^T r into its own peer buffer; this
+// kernel raises the flags, waits for all ranks, adds the partial vectors of all ranks in rank order (bitwise
+// identical on every rank: level 1 and 2 stay consistent replicas) and applies D1^-1 and the first damped-Jacobi
+// step.  One thread per coarse node (4 doubles, two 128-bit volatile loads per rank).
+__global__ void __launch_bounds__(256) peer_coarse_start_kernel(const PeerCtx pc, int32_t n_nodes,
+                                                                const double* __restrict__ dinv, double wc,
+                                                                double* __restrict__ bc, double* __restrict__ xc) {
+    if (blockIdx.x == 0) {
+        __threadfence_system();
+        peer_signal(pc, threadIdx.x);
+    }
+    peer_wait(pc, threadIdx.x);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int r = 0; r < pc.world; ++r) {
+        const double* src = peer_big(pc, r) + 4 * i;
+        double a, b, c, d;
+        ld_volatile_v2(src, a, b);
+        ld_volatile_v2(src + 2, c, d);
+        s0 += a; s1 += b; s2 += c; s3 += d;
+    }
+    const double* D = dinv + 16 * i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double b = D[4 * k] * s0 + D[4 * k + 1] * s1 + D[4 * k + 2] * s2 + D[4 * k + 3] * s3;
+        bc[4 * i + k] = b;
+        xc[4 * i + k] = wc * b;
+    }
+}
+
 // out = c0 * xin + c1 * (b - A1^ x) on level 1.  The level-1 operator is stored in SINGLE precision: it only
 // shapes the preconditioner (a fixed linear operator either way), the Krylov vectors and the fine operator stay
 // fp64; half the bytes keep the whole level in L2.  4 threads per coarse node, one 128-bit load per block row.
@@ -190,18 +223,25 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
 int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cudaStream_t st) {
     TEFEM_REQUIRE(p && r && z, "null pointer");
     const int64_t nf = 4 * (int64_t)p->n_rows, n1 = 4 * (int64_t)p->n1;
-    void* s = reinterpret_cast<void*>(st);
-    // level 0 -> 1: rc = P1^T r  (all-reduced over the ranks: levels 1 and 2 are replicated)
-    restrict_kernel<<<(unsigned)ceil_div(32 * (int64_t)p->n1, 256), 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, r, p->rc);
-    TEFEM_LAUNCH_CHECK();
+    // level 0 -> 1: rc = P1^T r, summed over the ranks (levels 1 and 2 are replicated): the restriction writes
+    // into this rank's peer buffer and the next kernel does all-reduce + D1^-1 + first smoothing step in one
+    const unsigned g1 = (unsigned)ceil_div(n1, 256);
     if (p->comm) {
-        int rc = tefem_comm_allreduce_sum(p->comm, p->rc, (int)n1, s);
-        if (rc) return rc;
+        TEFEM_REQUIRE(tefem_comm_has_peer(p->comm) && tefem_comm_peer_cap(p->comm) >= n1,
+                      "the peer-memory region must hold 4 * n_coarse doubles (tefem_comm_shm_alloc)");
+        const PeerCtx pc = tefem_comm_peer_ctx(p->comm, PEER_CH_COARSE);
+        double* mine = reinterpret_cast<double*>(pc.base[pc.rank] + PEER_BIG_OFFSET) + (int64_t)(pc.epoch & 1u) * pc.cap;
+        restrict_kernel<<<(unsigned)ceil_div(32 * (int64_t)p->n1, 256), 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, r, mine);
+        TEFEM_LAUNCH_CHECK();
+        peer_coarse_start_kernel<<<(unsigned)ceil_div((int64_t)p->n1, 256), 256, 0, st>>>(pc, p->n1, p->dinv1, p->omega_c, p->bc, p->xc);
+        TEFEM_LAUNCH_CHECK();
+    } else {
+        restrict_kernel<<<(unsigned)ceil_div(32 * (int64_t)p->n1, 256), 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, r, p->rc);
+        TEFEM_LAUNCH_CHECK();
+        coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
+        TEFEM_LAUNCH_CHECK();
     }
     // level 1 V-cycle on A1^ = D1^-1 A1:  bc = D1^-1 rc ; xc = wc bc ; correction from level 2 ; xc += wc (bc - A1^ xc)
-    const unsigned g1 = (unsigned)ceil_div(n1, 256);
-    coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
-    TEFEM_LAUNCH_CHECK();
     const double* xcur = p->xc;
     if (p->n2 > 0) {
         coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, p->n1, p->sys1, p->xc, p->bc, nullptr, 0.0, 1.0, p->tc);

@@ -55,6 +55,24 @@ class Comm:
         self.handle = ctypes.c_void_p()
         _lib.check(self.lib.tefem_comm_create(ctypes.byref(self.handle), path, raw, self.world, self.rank))
 
+        self.peer_cap = -1
+
+    def setup_peer(self, big_cap_doubles=0):
+        """Allocate and exchange the peer-memory region of the in-kernel reductions (include/tefem.h,
+        tefem_comm_shm_alloc): once per communicator, before the first solve."""
+        import torch.distributed as dist
+        if self.peer_cap >= 0:
+            if big_cap_doubles > self.peer_cap:
+                raise RuntimeError("peer-memory region already allocated with a smaller capacity")
+            return
+        raw = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.tefem_comm_shm_alloc(self.handle, int(big_cap_doubles), raw))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(raw.raw))
+        _lib.check(self.lib.tefem_comm_shm_open(self.handle, ctypes.create_string_buffer(b"".join(handles), 64 * self.world)))
+        dist.barrier()
+        self.peer_cap = int(big_cap_doubles)
+
     def allreduce_sum_(self, t):
         _lib.check(self.lib.tefem_comm_allreduce_sum(self.handle, _lib.ptr(t), t.numel(), _lib.stream_ptr()))
         return t
@@ -160,6 +178,8 @@ class DistributedTransient:
         self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
         self.dinv = dm.block_jacobi_scale(self.sys)
         self.krylov = KrylovSolver(dm, lp.n_halo, self.comm)
+        if self.comm is not None and self.precond_kind != "multilevel":
+            self.comm.setup_peer(0)
         self.precond = None
         if self.precond_kind == "multilevel":
             from .multilevel import TwoLevelPreconditioner

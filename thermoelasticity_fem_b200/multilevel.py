@@ -136,6 +136,8 @@ class TwoLevelPreconditioner:
         self.node_agg2 = torch.from_numpy(agg2.astype(np.int32)).to(dev)
         self.n1, self.n2, self.h, self.H1 = n1, n2, h, H1
         self.factor1, self.omega, self.omega_c = factor1, omega, omega_c
+        if comm is not None:
+            comm.setup_peer(4 * n1)               # the restricted residual is all-reduced through peer memory
         self.work = torch.zeros(int(lib.tefem_precond_work_doubles(n1, n2)), **f64)
         self.handle = ctypes.c_void_p()
         self.lib = lib

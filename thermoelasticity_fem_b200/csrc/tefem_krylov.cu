@@ -412,13 +412,20 @@ struct tefem_solver {
     // host polls of the stop flag
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_cat;      // category of every event pair (PROF_*)
     size_t ev_used = 0;
     double spmv_ms = 0.0;
     long long spmv_count = 0;
+    bool profile_all = false;     // TEFEM_PROFILE_ALL=1: also time the other parts of an iteration (diagnostics, stderr)
+    double cat_ms[4] = {0.0, 0.0, 0.0, 0.0};
+    long long cat_count[4] = {0, 0, 0, 0};
 };
 
-static int prof_begin(tefem_solver* s, cudaStream_t st) {
-    if (!s->profile) return TEFEM_OK;
+enum { PROF_SPMV = 0, PROF_PRECOND = 1, PROF_REDUCE = 2, PROF_UPDATE = 3 };
+static int prof_begin(tefem_solver* s, cudaStream_t st, int cat = PROF_SPMV) {
+    if (!s->profile || (cat != PROF_SPMV && !s->profile_all)) return TEFEM_OK;
+    if (s->ev_cat.size() < s->ev_used / 2 + 1) s->ev_cat.resize(s->ev_used / 2 + 1);
+    s->ev_cat[s->ev_used / 2] = cat;
     if (s->ev_used + 2 > s->ev_pool.size()) {
         for (int k = 0; k < 2; ++k) {
             cudaEvent_t e;
@@ -429,8 +436,8 @@ static int prof_begin(tefem_solver* s, cudaStream_t st) {
     TEFEM_CUDA_CHECK(cudaEventRecord(s->ev_pool[s->ev_used], st));
     return TEFEM_OK;
 }
-static int prof_end(tefem_solver* s, cudaStream_t st) {
-    if (!s->profile) return TEFEM_OK;
+static int prof_end(tefem_solver* s, cudaStream_t st, int cat = PROF_SPMV) {
+    if (!s->profile || (cat != PROF_SPMV && !s->profile_all)) return TEFEM_OK;
     TEFEM_CUDA_CHECK(cudaEventRecord(s->ev_pool[s->ev_used + 1], st));
     s->ev_used += 2;
     return TEFEM_OK;
@@ -438,11 +445,15 @@ static int prof_end(tefem_solver* s, cudaStream_t st) {
 // call only after the stream has been synchronised; only the first n_valid SpMVs of the batch did real work (the
 // launches queued after the stop flag was raised return immediately and must not dilute the average)
 static int prof_harvest(tefem_solver* s, size_t n_valid) {
-    for (size_t k = 0; k + 1 < s->ev_used && k / 2 < n_valid; k += 2) {
+    size_t seen[4] = {0, 0, 0, 0};      // every category has two pairs per iteration
+    for (size_t k = 0; k + 1 < s->ev_used; k += 2) {
+        const int cat = s->ev_cat[k / 2];
+        if (seen[cat]++ >= n_valid) continue;
         float ms = 0.f;
         TEFEM_CUDA_CHECK(cudaEventElapsedTime(&ms, s->ev_pool[k], s->ev_pool[k + 1]));
-        s->spmv_ms += ms;
-        s->spmv_count += 1;
+        s->cat_ms[cat] += ms;
+        s->cat_count[cat] += 1;
+        if (cat == PROF_SPMV) { s->spmv_ms += ms; s->spmv_count += 1; }
     }
     s->ev_used = 0;
     return TEFEM_OK;
@@ -486,12 +497,21 @@ extern "C" int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n
 
 extern "C" int tefem_solver_profile(tefem_solver* s, int enable, double* h_spmv_ms, int64_t* h_spmv_count) {
     TEFEM_REQUIRE(s, "null solver");
+    if (s->profile_all && s->cat_count[0] > 0)
+        fprintf(stderr, "tefem profile (ms per call): spmv %.4f x %lld | precond %.4f x %lld | reduce+scalars %.4f x %lld | "
+                        "vector updates %.4f x %lld\n",
+                s->cat_ms[0] / s->cat_count[0], s->cat_count[0], s->cat_ms[1] / (s->cat_count[1] ? s->cat_count[1] : 1),
+                s->cat_count[1], s->cat_ms[2] / (s->cat_count[2] ? s->cat_count[2] : 1), s->cat_count[2],
+                s->cat_ms[3] / (s->cat_count[3] ? s->cat_count[3] : 1), s->cat_count[3]);
     if (h_spmv_ms) *h_spmv_ms = s->spmv_ms;
     if (h_spmv_count) *h_spmv_count = s->spmv_count;
     if (enable >= 0) {
         s->profile = enable != 0;
         s->spmv_ms = 0.0;
         s->spmv_count = 0;
+        for (int k = 0; k < 4; ++k) { s->cat_ms[k] = 0.0; s->cat_count[k] = 0; }
+        const char* pa = getenv("TEFEM_PROFILE_ALL");
+        s->profile_all = pa && pa[0] == '1';
     }
     return TEFEM_OK;
 }
@@ -729,28 +749,40 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
             for (; it < batch_end && total_iters + it < max_iter; ++it) {
                 double* pdir = s->p;      // direction fed to the operator: p, or N p with a preconditioner
                 if (s->pc) {
+                    prof_begin(s, st, PROF_PRECOND);
                     rc = tefem_precond_apply_stream(s->pc, s->p, s->ph, st);
                     if (rc) return rc;
+                    prof_end(s, st, PROF_PRECOND);
                     pdir = s->ph;
                 }
                 rc = dist_spmv<1>(s, rowptr, colidx, sys, pdir, s->v, s->rhat, nullptr, s->ictl, &npc, st);
                 if (rc) return rc;
+                prof_begin(s, st, PROF_REDUCE);
                 rc = reduce_scalars<1, 1>(s, npc, it, rtol2, st);
                 if (rc) return rc;
+                prof_end(s, st, PROF_REDUCE);
+                prof_begin(s, st, PROF_UPDATE);
                 update_s_kernel<<<vgrid, 256, 0, st>>>(n, s->r, s->v, s->s, s->sc, s->ictl);
                 TEFEM_LAUNCH_CHECK();
+                prof_end(s, st, PROF_UPDATE);
                 double* sdir = s->s;
                 if (s->pc) {
+                    prof_begin(s, st, PROF_PRECOND);
                     rc = tefem_precond_apply_stream(s->pc, s->s, s->sh, st);
                     if (rc) return rc;
+                    prof_end(s, st, PROF_PRECOND);
                     sdir = s->sh;
                 }
                 rc = dist_spmv<8>(s, rowptr, colidx, sys, sdir, s->t, s->rhat, s->s, s->ictl, &npc, st);
                 if (rc) return rc;
+                prof_begin(s, st, PROF_REDUCE);
                 rc = reduce_scalars<8, 2>(s, npc, it, rtol2, st);
                 if (rc) return rc;
+                prof_end(s, st, PROF_REDUCE);
+                prof_begin(s, st, PROF_UPDATE);
                 update_xrp_kernel<<<vgrid, 256, 0, st>>>(n, x, s->r, s->p, s->s, s->t, s->v, pdir, sdir, s->sc, s->ictl, it);
                 TEFEM_LAUNCH_CHECK();
+                prof_end(s, st, PROF_UPDATE);
             }
             TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -22,9 +22,12 @@
 #include "tefem_comm.h"
 #include "tefem_precond.h"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace tefem {
 
@@ -59,58 +62,55 @@ __device__ __forceinline__ void ld256_x(const double* p, double& a, double& b, d
 // s = sd (the un-preconditioned vector whose image y is; sd == x without a preconditioner) and the first three
 // split by field (u rows r < 3, theta rows r == 3).
 // rows: optional list of node rows (interior / boundary split), else rows [0, n_rows).
+// The grid-stride row loop of the SpMV; d[] receives this thread's dot-product contributions.
 template <int DOTS, int UNROLL>
-__global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const int32_t* __restrict__ rowptr,
-                                                            const int32_t* __restrict__ colidx,
-                                                            const int32_t* __restrict__ rows, int32_t n_rows,
-                                                            const double* __restrict__ sys, const double* __restrict__ x,
-                                                            double* __restrict__ y, const double* __restrict__ w,
-                                                            const double* __restrict__ sd, double* __restrict__ partials,
-                                                            const int* __restrict__ ictl) {
-    __shared__ double red[8 * 32];
-    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
-    if (active) {
-        const int64_t n = 4 * (int64_t)n_rows;
-        for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n;
-             tid += (int64_t)gridDim.x * blockDim.x) {
-            const int32_t i = rows ? rows[tid >> 2] : (int32_t)(tid >> 2);
-            const int r = (int)(tid & 3);
-            const int32_t s = rowptr[i], t = rowptr[i + 1];
-            double acc0 = 0.0, acc1 = 0.0;
-            int32_t p = s;
-            // UNROLL blocks per trip: all their 256-bit loads are issued before the first use
-            for (; p + UNROLL <= t; p += UNROLL) {
-                double a[UNROLL][4], v[UNROLL][4];
-                int32_t j[UNROLL];
+__device__ __forceinline__ void spmv_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                          const int32_t* __restrict__ rows, int32_t n_rows, const double* __restrict__ sys,
+                                          const double* __restrict__ x, double* __restrict__ y,
+                                          const double* __restrict__ w, const double* __restrict__ sd, double (&d)[5]) {
+    const int64_t n = 4 * (int64_t)n_rows;
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = rows ? rows[tid >> 2] : (int32_t)(tid >> 2);
+        const int r = (int)(tid & 3);
+        const int32_t s = rowptr[i], t = rowptr[i + 1];
+        double acc0 = 0.0, acc1 = 0.0;
+        int32_t p = s;
+        // UNROLL blocks per trip: all their 256-bit loads are issued before the first use
+        for (; p + UNROLL <= t; p += UNROLL) {
+            double a[UNROLL][4], v[UNROLL][4];
+            int32_t j[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) j[u] = colidx[p + u];
+            for (int u = 0; u < UNROLL; ++u) j[u] = colidx[p + u];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) ld256(sys + 16 * (int64_t)(p + u) + 4 * r, a[u][0], a[u][1], a[u][2], a[u][3]);
+            for (int u = 0; u < UNROLL; ++u) ld256(sys + 16 * (int64_t)(p + u) + 4 * r, a[u][0], a[u][1], a[u][2], a[u][3]);
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) ld256_x(x + 4 * (int64_t)j[u], v[u][0], v[u][1], v[u][2], v[u][3]);
+            for (int u = 0; u < UNROLL; ++u) ld256_x(x + 4 * (int64_t)j[u], v[u][0], v[u][1], v[u][2], v[u][3]);
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const double c = a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2] + a[u][3] * v[u][3];
-                    if (u & 1) acc1 += c; else acc0 += c;
-                }
-            }
-            for (; p < t; ++p) {
-                double a0, a1, a2, a3, x0, x1, x2, x3;
-                ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
-                ld256_x(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
-                acc0 += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
-            }
-            const double yv = acc0 + acc1;
-            const int64_t row = 4 * (int64_t)i + r;
-            y[row] = yv;
-            if (DOTS == 1) d[0] += w[row] * yv;
-            if (DOTS == 8) {
-                const double sv = sd[row], wv = w[row];
-                d[0] += yv * sv; d[1] += yv * yv; d[2] += sv * sv; d[3] += wv * sv; d[4] += wv * yv;
+            for (int u = 0; u < UNROLL; ++u) {
+                const double c = a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2] + a[u][3] * v[u][3];
+                if (u & 1) acc1 += c; else acc0 += c;
             }
         }
+        for (; p < t; ++p) {
+            double a0, a1, a2, a3, x0, x1, x2, x3;
+            ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
+            ld256_x(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
+            acc0 += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
+        }
+        const double yv = acc0 + acc1;
+        const int64_t row = 4 * (int64_t)i + r;
+        y[row] = yv;
+        if (DOTS == 1) d[0] += w[row] * yv;
+        if (DOTS == 8) {
+            const double sv = sd[row], wv = w[row];
+            d[0] += yv * sv; d[1] += yv * yv; d[2] += sv * sv; d[3] += wv * sv; d[4] += wv * yv;
+        }
     }
+}
+
+// CTA sums of the dot-product contributions -> partials[blockIdx.x * DOTS + k] (fixed reduction tree).
+template <int DOTS>
+__device__ __forceinline__ void spmv_store_partials(const double (&d)[5], double* red, double* __restrict__ partials) {
     if (DOTS == 1) {
         double v1[1] = {d[0]};
         block_reduce_sum<1>(v1, red);
@@ -127,6 +127,21 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const
             for (int k = 0; k < 8; ++k) partials[(size_t)blockIdx.x * 8 + k] = v8[k];
         }
     }
+}
+
+template <int DOTS, int UNROLL>
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx,
+                                                            const int32_t* __restrict__ rows, int32_t n_rows,
+                                                            const double* __restrict__ sys, const double* __restrict__ x,
+                                                            double* __restrict__ y, const double* __restrict__ w,
+                                                            const double* __restrict__ sd, double* __restrict__ partials,
+                                                            const int* __restrict__ ictl) {
+    __shared__ double red[8 * 32];
+    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
+    if (active) spmv_rows<DOTS, UNROLL>(rowptr, colidx, rows, n_rows, sys, x, y, w, sd, d);
+    spmv_store_partials<DOTS>(d, red, partials);
 }
 
 // out[k] (+)= sum over CTAs of partials[cta*NV + k], fixed order; one CTA.
@@ -317,6 +332,93 @@ __global__ void __launch_bounds__(256) update_xrp_kernel(int64_t n, double* __re
         const double rv = sv - omega * t[k];
         r[k] = rv;
         p[k] = rv + beta * (pv - omega * v[k]);
+    }
+}
+
+// ---- persistent cooperative iteration for SMALL single-GPU systems ---------------------------------------------
+// Below ~1e5 rows an iteration of the launch-per-operation driver is bound by launch latency (10 launches of 2-4 us
+// around microsecond kernels: the reference's own example_transient_2 runs 458 iterations per step).  Here ONE
+// cooperative kernel runs a whole batch of iterations: the grid stays resident, the phases are separated by
+// grid.sync() (4 per iteration), every CTA reduces the per-CTA partials itself in the same fixed order, so all
+// CTAs hold bitwise identical copies of the scalars and take the same (uniform) stop decision without a broadcast.
+// Same arithmetic per row and per reduction as the multi-kernel path.
+struct CoopArgs {
+    const int32_t* rowptr; const int32_t* colidx; const double* sys;
+    int32_t n_rows;
+    double *x, *r, *rhat, *p, *v, *s, *t, *partials, *sc;
+    int* ictl;
+    int it0, it1;
+    double rtol2;
+};
+
+template <int NV>
+__device__ __forceinline__ void coop_reduce(const double* partials, int n_cta, double* red, double* out /* shared */) {
+    double d[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) d[k] = 0.0;
+    for (int c = threadIdx.x; c < n_cta; c += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) d[k] += __ldcg(partials + (size_t)c * NV + k);
+    block_reduce_sum<NV>(d, red);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = d[k];
+}
+
+__global__ void __launch_bounds__(SPMV_THREADS, 2) coop_bicgstab_kernel(const CoopArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[8 * 32];
+    __shared__ double sc[NSCAL];
+    __shared__ int ictl[4];
+    if (threadIdx.x < NSCAL) sc[threadIdx.x] = a.sc[threadIdx.x];
+    if (threadIdx.x < 4) ictl[threadIdx.x] = a.ictl[threadIdx.x];
+    __syncthreads();
+    const int64_t n = 4 * (int64_t)a.n_rows;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    double* part1 = a.partials;
+    double* part8 = a.partials + MAX_PARTIAL_CTAS;
+    for (int it = a.it0; it < a.it1; ++it) {
+        if (ictl[IN_STOP]) break;                       // identical in every CTA
+        {   // v = A p, (rhat . v)
+            double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            spmv_rows<1, 2>(a.rowptr, a.colidx, nullptr, a.n_rows, a.sys, a.p, a.v, a.rhat, nullptr, d);
+            spmv_store_partials<1>(d, red, part1);
+        }
+        grid.sync();
+        coop_reduce<1>(part1, gridDim.x, red, sc + SC_PKT);
+        if (threadIdx.x == 0) scalars_alpha(sc, ictl, it);
+        __syncthreads();
+        if (ictl[IN_STOP]) break;
+        {   // s = r - alpha v
+            const double alpha = sc[SC_ALPHA];
+            for (int64_t k = t0; k < n; k += stride) a.s[k] = a.r[k] - alpha * a.v[k];
+        }
+        grid.sync();
+        {   // t = A s and the 8 packed dots
+            double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            spmv_rows<8, 2>(a.rowptr, a.colidx, nullptr, a.n_rows, a.sys, a.s, a.t, a.rhat, a.s, d);
+            spmv_store_partials<8>(d, red, part8);
+        }
+        grid.sync();
+        coop_reduce<8>(part8, gridDim.x, red, sc + SC_PKT);
+        if (threadIdx.x == 0) scalars_omega(sc, ictl, it, a.rtol2);
+        __syncthreads();
+        {   // x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)   (also in the stopping iteration)
+            const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA], beta = sc[SC_BETA];
+            for (int64_t k = t0; k < n; k += stride) {
+                const double pv = a.p[k], sv = a.s[k];
+                a.x[k] += alpha * pv + omega * sv;
+                const double rv = sv - omega * a.t[k];
+                a.r[k] = rv;
+                a.p[k] = rv + beta * (pv - omega * a.v[k]);
+            }
+        }
+        grid.sync();
+    }
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x < NSCAL) a.sc[threadIdx.x] = sc[threadIdx.x];
+        if (threadIdx.x < 4) a.ictl[threadIdx.x] = ictl[threadIdx.x];
     }
 }
 
@@ -694,6 +796,25 @@ extern "C" int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t 
     return launch_spmv<0>(rowptr, colidx, nullptr, n_rows, sys, x, y, nullptr, nullptr, nullptr, nullptr, nullptr, as_stream(stream));
 }
 
+// Persistent cooperative path: systems small enough that an iteration is launch-latency bound.
+constexpr int32_t COOP_MAX_ROWS = 65536;
+static int coop_grid(int32_t n_rows) {
+    static int resident = -1;
+    if (resident < 0) {
+        int dev = 0, sms = 0, per_sm = 0, coop_ok = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_bicgstab_kernel, SPMV_THREADS, 0) != cudaSuccess)
+            resident = 0;
+        else
+            resident = coop_ok ? sms * per_sm : 0;
+        if (resident > MAX_PARTIAL_CTAS) resident = MAX_PARTIAL_CTAS;
+    }
+    int64_t g = ceil_div(4 * (int64_t)n_rows, SPMV_THREADS);
+    if (g > resident) g = resident;
+    return (int)g;
+}
+
 extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys,
                               const double* b, double* x, double rtol, int max_iter, int check_every, double* h_info,
                               void* stream) {
@@ -742,11 +863,23 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         // ---- iterate
         bool stopped = false;
         int it = 0;
+        const bool coop = !s->comm && !s->pc && !s->profile && s->n_rows <= COOP_MAX_ROWS && coop_grid(s->n_rows) > 0;
         if (s->profile) s->ev_used = 0;          // drop the (re)start SpMV from the timing
         int iters_seen = total_iters;
         while (!stopped && total_iters + it < max_iter) {
             const int batch_end = it + check_every;
-            for (; it < batch_end && total_iters + it < max_iter; ++it) {
+            if (coop) {   // one cooperative launch runs the whole batch (small systems)
+                int it1 = batch_end;
+                if (total_iters + it1 > max_iter) it1 = max_iter - total_iters;
+                CoopArgs ca = {rowptr, colidx, sys, s->n_rows, x, s->r, s->rhat, s->p, s->v, s->s, s->t, s->partials, s->sc,
+                               s->ictl, it, it1, rtol2};
+                void* kargs[] = {&ca};
+                TEFEM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)coop_bicgstab_kernel, dim3(coop_grid(s->n_rows)),
+                                                             dim3(SPMV_THREADS), kargs, 0, st));
+                count_launch();
+                it = it1;
+            }
+            for (; !coop && it < batch_end && total_iters + it < max_iter; ++it) {
                 double* pdir = s->p;      // direction fed to the operator: p, or N p with a preconditioner
                 if (s->pc) {
                     prof_begin(s, st, PROF_PRECOND);

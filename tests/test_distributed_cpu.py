@@ -84,6 +84,37 @@ def _worker(rank, world, port, result_dir):
         dist.all_reduce(pkt)
         yg = Kg @ xg
         assert abs(pkt[0].item() - yg @ yg) <= 1e-12 * abs(yg @ yg) and abs(pkt[1].item() - yg @ xg) <= 1e-12 * abs(yg @ yg)
+        # coarse level of the aggregation preconditioner: aggregates may straddle ranks; the gathered Galerkin
+        # operator equals P1^T K P1 of the global operator on every rank
+        import scipy.sparse as sp
+        from thermoelasticity_fem_b200 import multilevel as ml
+        br, ci = S.block_row.numpy().astype(np.int64), S.colidx.numpy().astype(np.int64)
+        Kd = K_loc.toarray()
+        blocks = np.stack([Kd[4 * r:4 * r + 4, 4 * c:4 * c + 4].reshape(16) for r, c in zip(br, ci)])
+        A = ml.build_aggregation(torch.from_numpy(pts[lp.local_nodes]), lp.n_own, 2.0)
+        rowptr1, col1, diag1, part = ml.galerkin_level1(A["agg"], S.block_row, S.colidx, torch.from_numpy(blocks), A["n1"])
+        n1 = A["n1"]
+        # the same aggregation computed from the global coordinates
+        ptg = torch.from_numpy(pts)
+        lo_g, hi_g = ptg.min(dim=0).values, ptg.max(dim=0).values
+        ext = hi_g - lo_g
+        H1 = 2.0 * float(ext.prod().item() / N) ** (1.0 / 3.0)
+        dims1 = torch.ceil(ext / H1 + 1e-9).to(torch.int64).clamp(min=1)
+        keys = ml._grid_keys(ptg, lo_g, H1, dims1).numpy()
+        uniq_g, agg_g = np.unique(keys, return_inverse=True)
+        assert np.array_equal(uniq_g, A["uniq"]) and np.array_equal(agg_g[lp.local_nodes], A["agg"].numpy())
+        assert abs(A["H1"] - H1) < 1e-12 and 1 < n1 < N
+        rows_ = (4 * np.arange(N)[:, None] + np.arange(4)).ravel()
+        cols_ = (4 * agg_g[:, None] + np.arange(4)).ravel()
+        P1 = sp.csr_array((np.ones(4 * N), (rows_, cols_)), shape=(4 * N, 4 * n1))
+        A1_ref = (P1.T @ Kg @ P1).toarray()
+        A1 = sp.bsr_array((part.numpy().reshape(-1, 4, 4), col1.numpy(), rowptr1.numpy()), shape=(4 * n1, 4 * n1)).toarray()
+        assert np.abs(A1 - A1_ref).max() <= 1e-12 * np.abs(A1_ref).max()
+        assert np.array_equal(col1.numpy()[diag1.numpy()], np.arange(n1))
+        # owned nodes grouped by aggregate
+        ptr, order = A["agg_ptr"].numpy(), A["order"].numpy()
+        assert ptr[-1] == lp.n_own and np.array_equal(np.sort(order), np.arange(lp.n_own))
+        assert np.all(np.repeat(np.arange(n1), np.diff(ptr)) == A["node_agg"].numpy()[order])
         open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

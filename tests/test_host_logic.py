@@ -122,3 +122,31 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src and "host_emulation" not in src, fn
+
+
+def test_preconditioner_hierarchy_host_logic():
+    """Aggregation / level-2 set-up of multilevel.py (pure torch + numpy, no device code)."""
+    import torch
+    from thermoelasticity_fem_b200 import multilevel as ml
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(12, 8, 6, 3.0, 2.0, 1.5)
+    N = pts.shape[0]
+    A = ml.build_aggregation(torch.from_numpy(pts), N, 3.0)
+    n1 = A["n1"]
+    assert abs(A["h"] - (3.0 * 2.0 * 1.5 / N) ** (1 / 3)) < 1e-12
+    agg = A["agg"].numpy()
+    assert agg.min() == 0 and agg.max() == n1 - 1 and np.unique(agg).size == n1
+    # every aggregate is a box of edge <= H1 (cubes of the anchored grid)
+    for a in range(0, n1, max(1, n1 // 12)):
+        box = pts[agg == a]
+        assert np.all(box.max(axis=0) - box.min(axis=0) <= A["H1"] + 1e-9)
+    # level 2: identity below the dense limit, else cubes of factor2 level-1 cells with a few hundred nodes at most
+    agg2, n2, f2 = ml.build_level2(A["uniq"], A["dims1"], 0.0, dense_limit=10 ** 6)
+    assert n2 == n1 and np.array_equal(agg2, np.arange(n1))
+    agg2, n2, f2 = ml.build_level2(A["uniq"], A["dims1"], 0.0, dense_limit=8)
+    assert f2 >= 3.0 and 1 <= n2 < n1 and agg2.min() == 0 and agg2.max() == n2 - 1 and np.unique(agg2).size == n2
+    d1, d2 = int(A["dims1"][1]), int(A["dims1"][2])
+    ijk = np.stack([A["uniq"] // (d1 * d2), (A["uniq"] // d2) % d1, A["uniq"] % d2], axis=1)
+    for a in range(n2):
+        cells = ijk[agg2 == a]
+        assert np.all(cells.max(axis=0) - cells.min(axis=0) < f2)

@@ -95,7 +95,14 @@ def check_schedule_invariants(S, conn, n_nodes, max_chunk=8, mat_id=None):
         assert n_it <= S.max_cta_items and n_el <= S.max_cta_elems and n_inc <= S.max_cta_inc
         assert n_sp <= S.max_cta_split and n_nd <= S.max_cta_nodes <= 256
         blk, start, meta = ib[o_it:o_it + n_it], ii[o_it:o_it + n_it] & 0xffff, im[o_it:o_it + n_it]
-        assert np.array_equal(ii[o_it:o_it + n_it] >> 16, blk - p0) and np.all(np.diff(blk) >= 0)      # block order
+        ilen_all = meta & 0xff
+        assert np.array_equal(ii[o_it:o_it + n_it] >> 16, blk - p0)
+        # block order up to the longest-first ordering inside windows of consecutive items
+        from thermoelasticity_fem_b200.symbolic import ITEM_SORT_WINDOW as W
+        for w0 in range(0, n_it, W):
+            assert np.all(np.diff(ilen_all[w0:w0 + W]) <= 0)
+            if w0 + W < n_it:
+                assert blk[w0:w0 + W].max() <= blk[w0 + W:].min()
         ilen = meta & 0xff
         slots = ((meta >> 8) & 0xffff) - 1
         imat = (meta.astype(np.int64) >> 24) & 0xff

@@ -23,7 +23,8 @@ E, N = conn.shape[0], pts.shape[0]
 conn_d = torch.from_numpy(conn).cuda()
 for v in variants:
     items, budget, chunk = [int(x) for x in v.split(",")][:3]
-    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk)
+    window = int(v.split(",")[3]) if len(v.split(",")) > 3 else None
+    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk, item_sort_window=window)
     dm = DeviceMesh(pts, conn, np.zeros(E, dtype=np.int32), table, schedule=S)
     P = S.n_blocks
     line = f"{v:16s} n_cta={S.n_cta} items={S.n_items} max_el={S.max_cta_elems} max_nodes={S.max_cta_nodes} slots={S.max_cta_slots} sched={S.schedule_bytes() / E:.0f} B/elem |"

@@ -188,23 +188,30 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
                           const int32_t* interior_rows, int32_t n_interior_rows);
 
 /* Aggregation-based coarse correction, used as the right preconditioner of tefem_bicgstab on top of the block-Jacobi
- * scaling: z = omega r + P1 M1(P1^T r) on the scaled system, with a replicated 4x4-block level 1 (one V-cycle with
- * damped Jacobi) and a dense level 2 (csrc/tefem_precond.cu).  The reference has no counterpart (spsolve is a direct
- * solve, solvers.py:26,172).  All arrays are built by the host side (multilevel.py) and owned by the caller:
- *   agg_ptr[n_coarse+1], agg_nodes[n_rows]: owned fine node rows grouped by aggregate; node_agg[n_rows]: aggregate of
- *   each owned fine node; rowptr1 / colidx1 / sys1 / dinv1: block-Jacobi-scaled Galerkin operator of level 1 and the
- *   inverses of its diagonal blocks; agg2_* / node_agg2: aggregation of the level-1 nodes; inv2: dense row-major
- *   inverse [4 n_coarse2, 4 n_coarse2] of the level-2 Galerkin operator (n_coarse2 = 0: two levels only);
- *   sys1 and inv2 are SINGLE precision (preconditioner data only; all vectors and the fine operator are fp64);
- *   work: tefem_precond_work_doubles(n_coarse, n_coarse2) doubles, 128-byte aligned; comm: tefem_comm* or NULL
- *   (the restricted residual is all-reduced, levels 1 and 2 are replicated on every rank).                      */
+ * scaling: z = omega r + P1 M1(P1^T r) on the scaled system, with a replicated level 1 (one V-cycle with damped
+ * Jacobi) and a dense level 2 (csrc/tefem_precond.cu).  The coarse space of an aggregate holds its rigid-body modes
+ * (3 translations, 3 rotations about its centre) and a constant theta, stored as two 4-DOF pseudo nodes
+ * (t_x, t_y, t_z, theta), (w_x, w_y, w_z, 0).  The reference has no counterpart (spsolve is a direct solve,
+ * solvers.py:26,172).  All arrays are built by the host side (multilevel.py) and owned by the caller:
+ *   agg_ptr[n_agg+1], agg_nodes[n_rows]: owned fine node rows grouped by aggregate; node_agg[n_rows]: aggregate of
+ *   each owned fine node; node_off[n_rows][4] (float): offset of the node from its aggregate's centre (x, y, z, 0);
+ *   rowptr1 / colidx1 / sys1: 4x4-block CSR over the 2 n_agg pseudo nodes of A1^ = D1^-1 P1^T A^ P1 (D1 = its 8x8
+ *   diagonal blocks); dinv1[n_agg][64]: D1^-1, row-major 8x8;
+ *   r2_* / p2_*: the transfer operators P2^T (2 n_agg2 block rows) and P2 (2 n_agg block rows) between the pseudo
+ *   nodes of levels 1 and 2 as 4x4-block CSR; inv2: dense row-major inverse [8 n_agg2, 8 n_agg2] of P2^T A1^ P2;
+ *   sys1, r2_vals, p2_vals and inv2 are SINGLE precision (preconditioner data only; all vectors and the fine
+ *   operator are fp64);
+ *   work: tefem_precond_work_doubles(n_agg, n_agg2) doubles, 128-byte aligned; comm: tefem_comm* or NULL (the
+ *   restricted residual, 8 n_agg doubles, is summed over the ranks through peer memory; levels 1 and 2 are
+ *   replicated on every rank).                                                                                  */
 typedef struct tefem_precond tefem_precond;
-int64_t tefem_precond_work_doubles(int32_t n_coarse, int32_t n_coarse2);
-int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_coarse, const int32_t* agg_ptr,
-                         const int32_t* agg_nodes, const int32_t* node_agg, double omega,
+int64_t tefem_precond_work_doubles(int32_t n_agg, int32_t n_agg2);
+int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, const int32_t* agg_ptr,
+                         const int32_t* agg_nodes, const int32_t* node_agg, const float* node_off, double omega,
                          const int32_t* rowptr1, const int32_t* colidx1, const float* sys1, const double* dinv1,
-                         double omega_c, int32_t n_coarse2, const int32_t* agg2_ptr, const int32_t* agg2_nodes,
-                         const int32_t* node_agg2, const float* inv2, double* work, void* comm);
+                         double omega_c, int32_t n_agg2, const int32_t* r2_rowptr, const int32_t* r2_colidx,
+                         const float* r2_vals, const int32_t* p2_rowptr, const int32_t* p2_colidx, const float* p2_vals,
+                         const float* inv2, double* work, void* comm);
 int tefem_precond_destroy(tefem_precond* pc);
 int tefem_precond_apply(tefem_precond* pc, const double* r, double* z, void* stream);
 /* Attach (or detach with NULL) a preconditioner to the Krylov driver. */

@@ -92,7 +92,7 @@ def _worker(rank, world, port, result_dir):
         Kd = K_loc.toarray()
         blocks = np.stack([Kd[4 * r:4 * r + 4, 4 * c:4 * c + 4].reshape(16) for r, c in zip(br, ci)])
         A = ml.build_aggregation(torch.from_numpy(pts[lp.local_nodes]), lp.n_own, 2.0)
-        rowptr1, col1, diag1, part = ml.galerkin_level1(A["agg"], S.block_row, S.colidx, torch.from_numpy(blocks), A["n1"])
+        row1, col1, blocks8 = ml.galerkin_level1(A["agg"], A["off"], S.block_row, S.colidx, torch.from_numpy(blocks), A["n1"])
         n1 = A["n1"]
         # the same aggregation computed from the global coordinates
         ptg = torch.from_numpy(pts)
@@ -104,13 +104,38 @@ def _worker(rank, world, port, result_dir):
         uniq_g, agg_g = np.unique(keys, return_inverse=True)
         assert np.array_equal(uniq_g, A["uniq"]) and np.array_equal(agg_g[lp.local_nodes], A["agg"].numpy())
         assert abs(A["H1"] - H1) < 1e-12 and 1 < n1 < N
-        rows_ = (4 * np.arange(N)[:, None] + np.arange(4)).ravel()
-        cols_ = (4 * agg_g[:, None] + np.arange(4)).ravel()
-        P1 = sp.csr_array((np.ones(4 * N), (rows_, cols_)), shape=(4 * N, 4 * n1))
+        cen_g = np.stack([np.bincount(agg_g, weights=pts[:, k], minlength=n1) / np.bincount(agg_g, minlength=n1)
+                          for k in range(3)], axis=1)
+        assert np.abs(A["centres"].numpy() - cen_g).max() < 1e-13
+        off_g = pts - cen_g[agg_g]
+        assert np.abs(A["off"].numpy() - off_g[lp.local_nodes]).max() < 1e-13
+        # rigid-body prolongation: u_i = t + w x d_i, theta_i = theta (8 coarse values per aggregate)
+        ar = np.arange(N)
+        rows_, cols_, vals_ = [], [], []
+        for c in range(4):
+            rows_.append(4 * ar + c); cols_.append(8 * agg_g + c); vals_.append(np.ones(N))
+        dx, dy, dz = off_g[:, 0], off_g[:, 1], off_g[:, 2]
+        for (c, k, v) in [(0, 1, dz), (0, 2, -dy), (1, 2, dx), (1, 0, -dz), (2, 0, dy), (2, 1, -dx)]:
+            rows_.append(4 * ar + c); cols_.append(8 * agg_g + 4 + k); vals_.append(v)
+        P1 = sp.csr_array((np.concatenate(vals_), (np.concatenate(rows_), np.concatenate(cols_))), shape=(4 * N, 8 * n1))
         A1_ref = (P1.T @ Kg @ P1).toarray()
-        A1 = sp.bsr_array((part.numpy().reshape(-1, 4, 4), col1.numpy(), rowptr1.numpy()), shape=(4 * n1, 4 * n1)).toarray()
+        A1 = np.zeros((8 * n1, 8 * n1))
+        for r_, c_, b_ in zip(row1.numpy(), col1.numpy(), blocks8.numpy()):
+            A1[8 * r_:8 * r_ + 8, 8 * c_:8 * c_ + 8] = b_
         assert np.abs(A1 - A1_ref).max() <= 1e-12 * np.abs(A1_ref).max()
-        assert np.array_equal(col1.numpy()[diag1.numpy()], np.arange(n1))
+        # scaling with the 8x8 diagonal blocks and the pseudo-node block CSR hold the same operator
+        rowptr1, Dinv, scaled = ml.scale_level1(row1, col1, blocks8, n1)
+        rp, ci, vv = ml.pseudo_node_csr(rowptr1, col1, scaled)
+        A1s = sp.bsr_array((vv.numpy().reshape(-1, 4, 4), ci.numpy(), rp.numpy()), shape=(8 * n1, 8 * n1)).toarray()
+        ref = np.zeros_like(A1s)
+        for r_, c_, b_ in zip(row1.numpy(), col1.numpy(), scaled.numpy()):
+            ref[8 * r_:8 * r_ + 8, 8 * c_:8 * c_ + 8] = b_
+        assert np.array_equal(A1s, ref)
+        for I in range(n1):
+            assert np.abs(A1s[8 * I:8 * I + 8, 8 * I:8 * I + 8] - np.eye(8)).max() < 1e-6       # unscaled K: cond ~ 1e10
+        live = np.ones(8 * n1, bool); live[7::8] = False
+        Dfull = sp.block_diag([np.linalg.inv(d) for d in Dinv.numpy()]).toarray()
+        assert np.abs((Dfull @ A1s - A1)[np.ix_(live, live)]).max() <= 1e-7 * np.abs(A1).max()
         # owned nodes grouped by aggregate
         ptr, order = A["agg_ptr"].numpy(), A["order"].numpy()
         assert ptr[-1] == lp.n_own and np.array_equal(np.sort(order), np.arange(lp.n_own))

@@ -360,16 +360,17 @@ def _kuhn_steady_model(nx, ny, nz):
 
 def test_aggregation_preconditioner_apply_matches_host_restatement():
     """z = omega r + P1 V(P1^T r) of csrc/tefem_precond.cu against the same operator written with scipy from the arrays
-    the preconditioner holds, and the level-1 operator against the Galerkin product P1^T A^ P1 of the fine system."""
+    the preconditioner holds, and the level-1 operator against the Galerkin product P1^T A^ P1 of the fine system for
+    the rigid-body prolongation (translations + rotations about the aggregate centres, constant theta)."""
     import scipy.sparse as sp
     import torch
     from thermoelasticity_fem_b200.solvers import _SystemSolve
+    from thermoelasticity_fem_b200.multilevel import TwoLevelPreconditioner
     pts, groups, mesh, model, *_ = _kuhn_steady_model(16, 9, 6)
     model.create_free_dofs_lists()
     model.assemble_K()
     model.assemble_F()
     model.apply_dirichlet_matrices()
-    from thermoelasticity_fem_b200.multilevel import TwoLevelPreconditioner
     ss = _SystemSolve(model, 0., 0., 1., 1e-10, 1000, 16, precond="block_jacobi")
     pc, S = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, dense_limit=10), ss.dm.schedule
     n, n1, n2 = mesh.n_nodes, pc.n1, pc.n2
@@ -377,22 +378,39 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
     A = sp.bsr_array((ss.sys.cpu().numpy().reshape(-1, 4, 4), S.colidx.cpu().numpy(), S.rowptr.cpu().numpy()),
                      shape=(4 * n, 4 * n)).tocsr()
     agg = pc.node_agg.cpu().numpy().astype(np.int64)
+    off = pc.node_off.double().cpu().numpy()[:, :3]
+    # offsets are relative to the aggregate centres (mean of the member nodes)
+    cen = np.stack([np.bincount(agg, weights=pts[:, k], minlength=n1) / np.bincount(agg, minlength=n1) for k in range(3)], axis=1)
+    assert np.abs(off - (pts - cen[agg])).max() <= 1e-6 * np.abs(pts).max()
+    ar = np.arange(n)
+    rows, cols, vals = [], [], []
+    for c in range(4):
+        rows.append(4 * ar + c); cols.append(8 * agg + c); vals.append(np.ones(n))
+    dx, dy, dz = off[:, 0], off[:, 1], off[:, 2]
+    for (c, k, v) in [(0, 1, dz), (0, 2, -dy), (1, 2, dx), (1, 0, -dz), (2, 0, dy), (2, 1, -dx)]:
+        rows.append(4 * ar + c); cols.append(8 * agg + 4 + k); vals.append(v)
+    P1 = sp.csr_array((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(4 * n, 8 * n1))
 
-    def prolongation(a, nc):
-        rows = (4 * np.arange(a.shape[0])[:, None] + np.arange(4)).ravel()
-        cols = (4 * a[:, None] + np.arange(4)).ravel()
-        return sp.csr_array((np.ones(rows.shape[0]), (rows, cols)), shape=(4 * a.shape[0], 4 * nc))
+    def bsr(rowptr, colidx, data, shape):
+        return sp.bsr_array((data.double().cpu().numpy().reshape(-1, 4, 4), colidx.cpu().numpy(), rowptr.cpu().numpy()),
+                            shape=shape).tocsr()
 
-    P1 = prolongation(agg, n1)
-    P2 = prolongation(pc.node_agg2.cpu().numpy().astype(np.int64), n2)
-    A1 = sp.bsr_array((pc.sys1.double().cpu().numpy().reshape(-1, 4, 4), pc.colidx1.cpu().numpy(), pc.rowptr1.cpu().numpy()),
-                      shape=(4 * n1, 4 * n1)).tocsr()
-    D1inv = sp.bsr_array((pc.dinv1.cpu().numpy().reshape(-1, 4, 4), np.arange(n1), np.arange(n1 + 1)),
-                         shape=(4 * n1, 4 * n1)).tocsr()
+    A1 = bsr(pc.rowptr1, pc.colidx1, pc.sys1, (8 * n1, 8 * n1))
+    D1inv = sp.bsr_array((pc.dinv1.cpu().numpy().reshape(-1, 8, 8), np.arange(n1), np.arange(n1 + 1)),
+                         shape=(8 * n1, 8 * n1)).tocsr()
     G = (D1inv @ (P1.T @ A @ P1)).tocsr()
-    assert abs(G - A1).max() <= 2e-7 * abs(G).max()          # stored in single precision
+    Gd, A1d = G.toarray(), A1.toarray()
+    off_diag = ~np.kron(np.eye(n1, dtype=bool), np.ones((8, 8), dtype=bool))
+    assert np.abs(Gd - A1d)[off_diag].max() <= 2e-7 * np.abs(Gd).max()          # stored in single precision
+    blk = np.abs(A1d[~off_diag].reshape(n1, 8, 8) - np.eye(8)).max()
+    assert blk <= 1e-6                                                           # scaled diagonal blocks = identity
+    P2 = bsr(pc.p2_rowptr, pc.p2_colidx, pc.p2_vals, (8 * n1, 8 * n2))
+    R2 = bsr(pc.r2_rowptr, pc.r2_colidx, pc.r2_vals, (8 * n2, 8 * n1))
+    assert abs(R2 - P2.T).max() == 0.0
     inv2 = pc.inv2.double().cpu().numpy()
-    assert np.abs(inv2 @ (P2.T @ A1 @ P2).toarray() - np.eye(4 * n2)).max() < 1e-3
+    A2 = (P2.T @ A1 @ P2).toarray()
+    live = np.abs(A2).sum(axis=1) > 0
+    assert np.abs((inv2 @ A2)[np.ix_(live, live)] - np.eye(int(live.sum()))).max() < 1e-3
     rng = np.random.default_rng(5)
     r = rng.standard_normal(4 * n)
     bc = D1inv @ (P1.T @ r)

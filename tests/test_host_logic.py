@@ -140,6 +140,19 @@ def test_preconditioner_hierarchy_host_logic():
     for a in range(0, n1, max(1, n1 // 12)):
         box = pts[agg == a]
         assert np.all(box.max(axis=0) - box.min(axis=0) <= A["H1"] + 1e-9)
+    cen = A["centres"].numpy()
+    assert np.abs(cen - np.stack([np.bincount(agg, weights=pts[:, k], minlength=n1) / np.bincount(agg, minlength=n1)
+                                  for k in range(3)], axis=1)).max() < 1e-13
+    assert np.abs(A["off"].numpy() - (pts - cen[agg])).max() < 1e-13
+    # rigid-body transfer between the levels: a rigid motion of the level-2 aggregates is reproduced at the centres
+    agg2s, n2s, _ = ml.build_level2(A["uniq"], A["dims1"], 0.0, dense_limit=8)
+    P2 = ml.transfer_level2(cen, agg2s, n2s)
+    T, W = np.array([0.3, -0.2, 0.5]), np.array([0.1, 0.4, -0.7])
+    C2 = np.stack([np.bincount(agg2s, weights=cen[:, k], minlength=n2s) / np.bincount(agg2s, minlength=n2s) for k in range(3)], axis=1)
+    x2 = np.zeros((n2s, 8)); x2[:, :3] = T + np.cross(W, C2); x2[:, 3] = 2.0; x2[:, 4:7] = W      # global rigid motion
+    x1 = (P2 @ x2.ravel()).reshape(n1, 8)
+    assert np.abs(x1[:, :3] - (T + np.cross(W, cen))).max() < 1e-12 and np.abs(x1[:, 4:7] - W).max() == 0
+    assert np.all(x1[:, 3] == 2.0) and np.all(x1[:, 7] == 0.0)
     # level 2: identity below the dense limit, else cubes of factor2 level-1 cells with a few hundred nodes at most
     agg2, n2, f2 = ml.build_level2(A["uniq"], A["dims1"], 0.0, dense_limit=10 ** 6)
     assert n2 == n1 and np.array_equal(agg2, np.arange(n1))

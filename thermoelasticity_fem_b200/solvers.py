@@ -9,6 +9,7 @@ so reference scripts run unchanged.
 
 Out of scope: ``solve_ROM`` / ``solve_ROM_nonparametric`` (``solvers.py:219-668``).
 """
+import os
 import time
 
 import numpy as np
@@ -143,7 +144,7 @@ class LinearTransient:
         # Measured on the B200 (sandwich mesh and the 100^3 box): the iteration count of block-Jacobi BiCGSTAB
         # is insensitive to the initial guess (420 +- 30 iterations for orders 0, 1, 2 alike - the Krylov space
         # has to be rebuilt to resolve the low modes whatever the starting residual), so the default stays 0.
-        self.guess_order = guess_order
+        self.guess_order = int(os.environ.get("TEFEM_GUESS_ORDER", guess_order))      # env: experiments
 
         self.X = None
         self.Xdot = None

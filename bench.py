@@ -207,9 +207,9 @@ def run_tefem(args):
     pc = getattr(solver._ss, "precond", None) or getattr(solver, "precond", None)
     pc = pc if hasattr(pc, "n1") else None
     precond_desc = "block-Jacobi scaling only" if pc is None else (
-        f"block-Jacobi scaling + additive aggregation correction: level 1 = {pc.n1} aggregates (cubes of "
-        f"{pc.factor1:g} h, Galerkin, damped Jacobi {pc.omega_c:g}), level 2 = {pc.n2} aggregates (dense inverse), "
-        f"fine weight {pc.omega:g}")
+        f"block-Jacobi scaling + additive aggregation correction with rigid-body coarse spaces: level 1 = {pc.n1} "
+        f"aggregates (cubes of {pc.factor1:g} h, Galerkin, {pc.n_pre}+{pc.n_post} damped-Jacobi sweeps {pc.omega_c:g}), "
+        f"level 2 = {pc.n2} aggregates (dense inverse), fine weight {pc.omega:g}")
     ms_per_step = ms_total / args.steps
     steps_per_s = 1e3 / ms_per_step
 

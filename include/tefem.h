@@ -196,7 +196,8 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
  *   agg_ptr[n_agg+1], agg_nodes[n_rows]: owned fine node rows grouped by aggregate; node_agg[n_rows]: aggregate of
  *   each owned fine node; node_off[n_rows][4] (float): offset of the node from its aggregate's centre (x, y, z, 0);
  *   rowptr1 / colidx1 / sys1: 4x4-block CSR over the 2 n_agg pseudo nodes of A1^ = D1^-1 P1^T A^ P1 (D1 = its 8x8
- *   diagonal blocks); dinv1[n_agg][64]: D1^-1, row-major 8x8;
+ *   diagonal blocks); dinv1[n_agg][64]: D1^-1, row-major 8x8; omega_c, n_pre >= 1, n_post >= 0: damping and number
+ *   of the Jacobi sweeps on level 1 before / after the level-2 correction;
  *   r2_* / p2_*: the transfer operators P2^T (2 n_agg2 block rows) and P2 (2 n_agg block rows) between the pseudo
  *   nodes of levels 1 and 2 as 4x4-block CSR; inv2: dense row-major inverse [8 n_agg2, 8 n_agg2] of P2^T A1^ P2;
  *   sys1, r2_vals, p2_vals and inv2 are SINGLE precision (preconditioner data only; all vectors and the fine
@@ -209,7 +210,8 @@ int64_t tefem_precond_work_doubles(int32_t n_agg, int32_t n_agg2);
 int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, const int32_t* agg_ptr,
                          const int32_t* agg_nodes, const int32_t* node_agg, const float* node_off, double omega,
                          const int32_t* rowptr1, const int32_t* colidx1, const float* sys1, const double* dinv1,
-                         double omega_c, int32_t n_agg2, const int32_t* r2_rowptr, const int32_t* r2_colidx,
+                         double omega_c, int n_pre, int n_post, int32_t n_agg2, const int32_t* r2_rowptr,
+                         const int32_t* r2_colidx,
                          const float* r2_vals, const int32_t* p2_rowptr, const int32_t* p2_colidx, const float* p2_vals,
                          const float* inv2, double* work, void* comm);
 int tefem_precond_destroy(tefem_precond* pc);

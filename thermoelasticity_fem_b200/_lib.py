@@ -38,7 +38,7 @@ _SIGNATURES = {
     "tefem_solver_profile": [P, c_int, P, P],
     "tefem_solver_halo_exchange": [P, P, P],
     "tefem_solver_set_precond": [P, P],
-    "tefem_precond_create": [P, c_int32, c_int32, P, P, P, P, c_double, P, P, P, P, c_double, c_int32, P, P, P, P, P, P,
+    "tefem_precond_create": [P, c_int32, c_int32, P, P, P, P, c_double, P, P, P, P, c_double, c_int, c_int, c_int32, P, P, P, P, P, P,
                              P, P, P],
     "tefem_precond_destroy": [P],
     "tefem_precond_apply": [P, P, P, P],

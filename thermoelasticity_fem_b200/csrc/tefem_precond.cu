@@ -198,6 +198,7 @@ struct tefem_precond {
     const float *r2_vals = nullptr, *p2_vals = nullptr;
     const float* inv2 = nullptr;
     double omega = 1.0, omega_c = 0.8;
+    int n_pre = 1, n_post = 1;                   // damped-Jacobi sweeps on level 1 before / after the level-2 correction
     double *rc = nullptr, *bc = nullptr, *xc = nullptr, *tc = nullptr, *r2 = nullptr, *x2 = nullptr;
     tefem_comm* comm = nullptr;
 };
@@ -211,13 +212,15 @@ extern "C" int64_t tefem_precond_work_doubles(int32_t n_agg, int32_t n_agg2) {
 extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, const int32_t* agg_ptr,
                                     const int32_t* agg_nodes, const int32_t* node_agg, const float* node_off, double omega,
                                     const int32_t* rowptr1, const int32_t* colidx1, const float* sys1,
-                                    const double* dinv1, double omega_c, int32_t n_agg2, const int32_t* r2_rowptr,
+                                    const double* dinv1, double omega_c, int n_pre, int n_post, int32_t n_agg2,
+                                    const int32_t* r2_rowptr,
                                     const int32_t* r2_colidx, const float* r2_vals, const int32_t* p2_rowptr,
                                     const int32_t* p2_colidx, const float* p2_vals, const float* inv2, double* work,
                                     void* comm) {
     TEFEM_REQUIRE(out && agg_ptr && agg_nodes && node_agg && node_off && rowptr1 && colidx1 && sys1 && dinv1 && work,
                   "null pointer");
     TEFEM_REQUIRE(n_agg > 0 && n_rows >= 0 && n_agg2 > 0, "sizes");
+    TEFEM_REQUIRE(n_pre >= 1 && n_pre <= 8 && n_post >= 0 && n_post <= 8, "1 .. 8 pre- and 0 .. 8 post-smoothing sweeps");
     TEFEM_REQUIRE(r2_rowptr && r2_colidx && r2_vals && p2_rowptr && p2_colidx && p2_vals && inv2, "null level-2 arrays");
     TEFEM_REQUIRE((((uintptr_t)work) & 127) == 0 && (((uintptr_t)sys1) & 63) == 0 && (((uintptr_t)node_off) & 15) == 0 &&
                       (((uintptr_t)r2_vals) & 63) == 0 && (((uintptr_t)p2_vals) & 63) == 0,
@@ -229,7 +232,7 @@ extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t
     p->rowptr1 = rowptr1; p->colidx1 = colidx1; p->sys1 = sys1; p->dinv1 = dinv1;
     p->r2_rowptr = r2_rowptr; p->r2_colidx = r2_colidx; p->r2_vals = r2_vals;
     p->p2_rowptr = p2_rowptr; p->p2_colidx = p2_colidx; p->p2_vals = p2_vals; p->inv2 = inv2;
-    p->omega = omega; p->omega_c = omega_c;
+    p->omega = omega; p->omega_c = omega_c; p->n_pre = n_pre; p->n_post = n_post;
     const int64_t a1 = pc_align(8 * (int64_t)n_agg), a2 = pc_align(8 * (int64_t)n_agg2);
     double* w = work;
     p->rc = w; w += a1; p->bc = w; w += a1; p->xc = w; w += a1; p->tc = w; w += a1;
@@ -267,22 +270,32 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
         coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();
     }
-    // level 1 V-cycle on A1^ = D1^-1 A1 (bc = D1^-1 rc, xc = wc bc so far): correction from level 2, post-smoothing
-    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, p->xc, p->bc, nullptr, 0.0, 1.0, p->tc);
-    TEFEM_LAUNCH_CHECK();                                                                       // tc = bc - A1^ xc
+    // level 1 V-cycle on A1^ = D1^-1 A1 (bc = D1^-1 rc, x = wc bc so far = the first damped-Jacobi sweep from 0):
+    // further pre-smoothing sweeps, correction from level 2, post-smoothing.  A sweep reads all of x, so it writes
+    // into the other buffer: x' = x + wc (bc - A1^ x).
+    double *cur = p->xc, *alt = p->rc;
+    for (int k = 1; k < p->n_pre; ++k) {
+        coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
+        TEFEM_LAUNCH_CHECK();
+        double* t = cur; cur = alt; alt = t;
+    }
+    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, nullptr, 0.0, 1.0, p->tc);
+    TEFEM_LAUNCH_CHECK();                                                                       // tc = bc - A1^ x
     coarse_spmv_kernel<<<g2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, p->r2);
     TEFEM_LAUNCH_CHECK();                                                                       // r2 = P2^T tc
     dense_matvec_kernel<<<(unsigned)(4 * np2), 128, 0, st>>>(4 * np2, p->inv2, p->r2, p->x2);
     TEFEM_LAUNCH_CHECK();                                                                       // x2 = A2^-1 r2
-    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, p->xc, 1.0, -1.0, p->xc);
-    TEFEM_LAUNCH_CHECK();                                                                       // xc += P2 x2
-    // post-smoothing into a second buffer (the SpMV reads all of xc): rc <- xc + wc (bc - A1^ xc)
-    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, p->xc, p->bc, p->xc, 1.0, p->omega_c, p->rc);
-    TEFEM_LAUNCH_CHECK();
+    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, cur);
+    TEFEM_LAUNCH_CHECK();                                                                       // x += P2 x2
+    for (int k = 0; k < p->n_post; ++k) {
+        coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
+        TEFEM_LAUNCH_CHECK();
+        double* t = cur; cur = alt; alt = t;
+    }
     // level 1 -> 0
     if (p->n_rows > 0) {
         prolong_combine_kernel<<<(unsigned)ceil_div((int64_t)p->n_rows, 256), 256, 0, st>>>(p->n_rows, p->node_agg, p->node_off,
-                                                                                            p->omega, r, p->rc, z);
+                                                                                            p->omega, r, cur, z);
         TEFEM_LAUNCH_CHECK();
     }
     return TEFEM_OK;

@@ -239,11 +239,15 @@ def _bsr_arrays(M, dev):
 class TwoLevelPreconditioner:
     """Owns the device arrays of one preconditioner and its C handle (attach with KrylovSolver.set_precond)."""
 
-    def __init__(self, dm, sys, comm=None, factor1=6.0, factor2=0.0, omega=1.0, omega_c=0.8, dense_limit=200):
+    def __init__(self, dm, sys, comm=None, factor1=8.0, factor2=3.0, omega=1.0, omega_c=0.7, n_pre=3, n_post=3,
+                 dense_limit=200):
         import os
         import scipy.sparse as sp
-        if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c"
-            factor1, factor2, omega, omega_c = (float(v) for v in os.environ["TEFEM_ML"].split(","))
+        if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c[,n_pre,n_post]"
+            v = [float(x) for x in os.environ["TEFEM_ML"].split(",")]
+            factor1, factor2, omega, omega_c = v[:4]
+            if len(v) >= 6:
+                n_pre, n_post = int(v[4]), int(v[5])
         lib, dev = dm.lib, dm.device
         S = dm.schedule
         n_own = S.n_rows
@@ -280,7 +284,7 @@ class TwoLevelPreconditioner:
         self.agg_ptr, self.agg_nodes, self.node_agg = agg_ptr.to(i32), order.to(i32), node_agg.to(i32)
         self.agg2 = agg2
         self.n1, self.n2, self.h, self.H1 = n1, n2, h, H1
-        self.factor1, self.omega, self.omega_c = factor1, omega, omega_c
+        self.factor1, self.omega, self.omega_c, self.n_pre, self.n_post = factor1, omega, omega_c, n_pre, n_post
         if comm is not None:
             comm.setup_peer(8 * n1)               # the restricted residual is all-reduced through peer memory
         self.work = torch.zeros(int(lib.tefem_precond_work_doubles(n1, n2)), **f64)
@@ -288,7 +292,8 @@ class TwoLevelPreconditioner:
         self.lib = lib
         _lib.check(lib.tefem_precond_create(
             ctypes.byref(self.handle), n_own, n1, p(self.agg_ptr), p(self.agg_nodes), p(self.node_agg), p(self.node_off),
-            float(omega), p(self.rowptr1), p(self.colidx1), p(self.sys1), p(self.dinv1), float(omega_c), n2,
+            float(omega), p(self.rowptr1), p(self.colidx1), p(self.sys1), p(self.dinv1), float(omega_c), int(n_pre),
+            int(n_post), n2,
             p(self.r2_rowptr), p(self.r2_colidx), p(self.r2_vals), p(self.p2_rowptr), p(self.p2_colidx), p(self.p2_vals),
             p(self.inv2), p(self.work), comm.handle if comm is not None else None))
 

@@ -144,23 +144,6 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const
     spmv_store_partials<DOTS>(d, red, partials);
 }
 
-// out[k] (+)= sum over CTAs of partials[cta*NV + k], fixed order; one CTA.
-template <int NV>
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int n_cta,
-                                                              double* __restrict__ out, int accumulate) {
-    __shared__ double red[NV * 32];
-    double d[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) d[k] = 0.0;
-    for (int c = threadIdx.x; c < n_cta; c += blockDim.x)
-#pragma unroll
-        for (int k = 0; k < NV; ++k) d[k] += partials[(size_t)c * NV + k];
-    block_reduce_sum<NV>(d, red);
-    if (threadIdx.x == 0)
-#pragma unroll
-        for (int k = 0; k < NV; ++k) out[k] = (accumulate ? out[k] : 0.0) + d[k];
-}
-
 // r = b - y ; rhat = r ; p = r ; partials (r.r_u, r.r_t, b.b_u, b.b_t, x.x_u, x.x_t)
 __global__ void __launch_bounds__(256) init_residual_kernel(int64_t n, const double* __restrict__ b,
                                                             const double* __restrict__ y, const double* __restrict__ x,

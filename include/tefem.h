@@ -93,7 +93,7 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  * contiguous range of node rows and everything it needs lives in per-tile segments that start on 16-byte
  * boundaries, so that the persistent kernel can prefetch its next tile with TMA bulk copies while it computes:
  *   cta_hdr[c][12] = {n_items, n_elems, n_inc, n_split, n_nodes, o_items, o_elems, o_inc, o_split, o_nodes,
- *                     first block, 0}   (a tile owns a contiguous block range starting at `first block`);
+ *                     first block, n_pieces}   (a tile owns a contiguous block range starting at `first block`);
  *   cta_xyz[o_nodes ..][3]     coordinates of the tile's nodes (copy of coords[cta_nodes]);
  *   cta_conn8 / cta_elems [o_elems ..]   staged elements: 4 tile-local node numbers (one byte each), element
  *                              number (error reporting);
@@ -110,7 +110,14 @@ int tefem_element_matrices(const double* coords, const int32_t* conn, const int3
  *                              values in that shared-memory slot;
  *   split_block / split_meta [o_split ..]   blocks with several items: tile-local block, first slot | n_items << 16
  *                              (added in list order = ascending element);
- *   h_max[6] = largest n_items, n_elems, n_inc, partial slots, n_split, n_nodes of a tile (shared-memory sizes).
+ *   h_max[7] = largest n_items, n_elems, n_inc, partial slots, n_split, n_nodes of a tile (shared-memory sizes), and
+ *              the ITEM LAYOUT of the tiles: 0 = inline (above), 1 = pieces first: cta_hdr[c][11] = n_pieces; the item
+ *              list of a tile starts with all pieces of its split blocks (piece k parks its values in slot k) and
+ *              continues with exactly ONE item per block in block order - a plain block, or a combine item
+ *              (item_meta = n_pieces | (first slot + 1) << 8) that adds the parked pieces in list order; the kernel
+ *              runs the pieces, synchronises, then the block items, so that warps hold lists of similar length and
+ *              every block is stored at its block-order position (no split lists: n_split = 0).  Same chunks, same
+ *              summation order, bitwise the same values as layout 0.
  *   Every output value is written exactly once: no atomics, bitwise reproducible.
  * ops = bit mask of TEFEM_OP_*; vals_* are planes (see above) and may be NULL when not requested.
  * The D layout follows alpha_M / alpha_K (model.py:112-117).

@@ -56,8 +56,7 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     a = {k: getattr(S, k).numpy() for k in ("cta_hdr", "cta_elems", "cta_conn8", "cta_nodes", "item_inc", "item_meta",
                                             "split_block", "split_meta", "inc")}
     cta_xyz = np.ascontiguousarray(pts[a["cta_nodes"]])
-    h_max = np.array([S.max_cta_items, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, S.max_cta_split, S.max_cta_nodes],
-                     dtype=np.int32)
+    h_max = S.h_max()
     mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
     rc = emu.tefem_emu_assemble(ptr(rows), ctypes.c_int(rows.shape[0]), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]),
                                 ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_xyz), ptr(a["item_inc"]),
@@ -156,7 +155,9 @@ def test_sandwich_schedule_and_emulated_assembly(sandwich, emu, aM, aK):
     S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id))
     assert S.n_blocks == 39985
     if aM == 0.2:
-        check_schedule_invariants(S, conn, pts.shape[0], mat_id=mat_id)
+        S_inline = S if not S.pieces_first else build_schedule(torch.from_numpy(conn), pts.shape[0],
+                                                               mat_id=torch.from_numpy(mat_id), pieces_first=False)
+        check_schedule_invariants(S_inline, conn, pts.shape[0], mat_id=mat_id)
     vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", aM, aK)
     assert bad[0] == 2 ** 31 - 1 and bad[1] == 2 ** 31 - 1
     ops = orc.assemble(pts, conn, rows, mat_id, aM, aK)
@@ -190,7 +191,8 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
         chunk = 6 if items == 256 else 3
         S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items),
                            max_chunk=chunk, mat_id=torch.from_numpy(mat_id))
-        check_schedule_invariants(S, conn, pts.shape[0], chunk, mat_id=mat_id)
+        if not S.pieces_first:
+            check_schedule_invariants(S, conn, pts.shape[0], chunk, mat_id=mat_id)
         vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
         ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)
         A = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * pts.shape[0])
@@ -243,3 +245,69 @@ def test_emulated_element_matrices_match_oracle(emu):
         pc = orc.element_matrices_percall(pts[conn[e]], mats[int(list(tets)[mat_id[e]])])
         for nm in out:
             assert np.max(np.abs(out[nm][e] - pc[nm])) <= 1e-14 * np.abs(pc[nm]).max(), nm
+
+
+def check_pieces_first_invariants(S, S0):
+    """Pieces-first layout against the inline layout S0 of the same mesh / parameters: same tiles, same pieces (in the
+    same order, piece k -> slot k), exactly one item per block in block order, combine items cover their pieces."""
+    assert S.pieces_first and not S0.pieces_first
+    assert S.n_cta == S0.n_cta and S.max_cta_split == 0 and S.max_cta_slots == S0.max_cta_slots
+    H, H0 = S.cta_hdr.numpy().astype(np.int64), S0.cta_hdr.numpy().astype(np.int64)
+    assert np.array_equal(H[:, [1, 2, 4, 6, 7, 9, 10]], H0[:, [1, 2, 4, 6, 7, 9, 10]]) and np.all(H[:, 3] == 0)
+    assert torch.equal(S.inc, S0.inc) and torch.equal(S.cta_conn8, S0.cta_conn8)
+    ii, im, ib = S.item_inc.numpy().astype(np.int64), S.item_meta.numpy().astype(np.int64), S.item_block.numpy()
+    ii0, im0, ib0 = S0.item_inc.numpy().astype(np.int64), S0.item_meta.numpy().astype(np.int64), S0.item_block.numpy()
+    for c in range(S.n_cta):
+        n_it, o_it, p0, n_pc = H[c, 0], H[c, 5], H[c, 10], H[c, 11]
+        n0, o0 = H0[c, 0], H0[c, 5]
+        slot0 = ((im0[o0:o0 + n0] >> 8) & 0xffff) - 1
+        pieces0 = np.nonzero(slot0 >= 0)[0]
+        assert n_pc == pieces0.size
+        # the pieces are the inline layout's split items, unchanged and in the same order; piece k parks in slot k
+        assert np.array_equal(ii[o_it:o_it + n_pc], ii0[o0 + pieces0]) and np.array_equal(im[o_it:o_it + n_pc], im0[o0 + pieces0])
+        assert np.array_equal(((im[o_it:o_it + n_pc] >> 8) & 0xffff) - 1, np.arange(n_pc))
+        # one item per block, in block order
+        nb = n_it - n_pc
+        nxt = H[c + 1, 10] if c + 1 < S.n_cta else S.n_blocks
+        assert nb == nxt - p0
+        bi, bm = ii[o_it + n_pc:o_it + n_it], im[o_it + n_pc:o_it + n_it]
+        assert np.array_equal(ib[o_it + n_pc:o_it + n_it], p0 + np.arange(nb)) and np.array_equal(bi >> 16, np.arange(nb))
+        bslot = ((bm >> 8) & 0xffff) - 1
+        plain = bslot < 0
+        # plain blocks: the inline layout's single item of that block
+        single0 = np.nonzero(slot0 < 0)[0]
+        assert np.array_equal(ib0[o0 + single0], p0 + np.nonzero(plain)[0])
+        assert np.array_equal(bi[plain], ii0[o0 + single0]) and np.array_equal(bm[plain], im0[o0 + single0])
+        # combine items: consecutive, disjoint slot ranges that tile [0, n_pieces) and belong to that block
+        cs, cn = bslot[~plain], bm[~plain] & 0xff
+        assert np.array_equal(cs, np.cumsum(cn) - cn) and cn.sum() == n_pc and (cn.size == 0 or cn.min() >= 2)
+        assert np.array_equal(np.repeat(p0 + np.nonzero(~plain)[0], cn), ib[o_it:o_it + n_pc])
+
+
+@pytest.mark.parametrize("mesh_kind", ["sandwich", "kuhn3"])
+def test_pieces_first_layout_is_bitwise_the_inline_layout(sandwich, emu, mesh_kind):
+    if mesh_kind == "sandwich":
+        pts, blocks, groups = sandwich
+        m = orc.Material(*MAT2)
+        conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
+        variants = [dict()]
+    else:
+        pts, tets, tris, nodes = kuhn_box(5, 4, 4, jitter=0.2, seed=2)
+        mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+                3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+        conn, mat_id, rows = orc.element_table(tets, mats)
+        variants = [dict(), dict(items_per_cta=64, elem_budget=160, max_chunk=3), dict(items_per_cta=700, elem_budget=800, max_chunk=6)]
+    for kw in variants:
+        S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=False, **kw)
+        S1 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=True,
+                            tile_cost='items', **kw)
+        check_pieces_first_invariants(S1, S0)
+        S2 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=True, **kw)
+        assert S2.n_cta <= S1.n_cta            # default tile cost of this layout: blocks per tile (the block-order pass)
+        for ops, aM, aK in (("MKD", 0.2, 0.3), ("K", 0., 0.), ("MD", 0.3, 0.)):
+            v0, bad0 = emu_assemble(emu, S0, pts, conn, mat_id, rows, ops, aM, aK)
+            for S in (S1, S2):                 # the values depend on the chunks only, not on the tiles
+                v1, bad1 = emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK)
+                for nm in ops:
+                    assert np.array_equal(v0[nm], v1[nm]), (kw, ops, nm)
+                assert np.array_equal(bad0, bad1)

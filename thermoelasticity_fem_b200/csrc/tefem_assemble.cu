@@ -57,7 +57,7 @@ struct AssembleArgs {
     int32_t* bad_elem;
 };
 
-enum { H_NITEMS = 0, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, HDR_STRIDE = 12 };
+enum { H_NITEMS = 0, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE, HDR_STRIDE = 12 };
 
 // ---- per-thread routines (host + device) -------------------------------------------------------
 
@@ -132,13 +132,11 @@ TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTr
     }
 }
 
-// One work item (all its elements share one material): geometric sums over the incidence entries
-// inc[s .. s + len) (ascending element order), material constants applied once; then either write the block (items
-// are in block order: consecutive threads write consecutive addresses of every plane) or park the values of a
-// piece of a split block in its shared-memory slot.
+// Geometric sums of one material-uniform list inc[s .. s + len) (ascending element order) with the material
+// constants applied once.
 template <int OPS, int DUU>
-TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_word, int32_t meta, const double* recs,
-                           const uint16_t* inc_s, double* slots, double W4, const double* S, const double* NN) {
+TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta, const double* recs, const uint16_t* inc_s,
+                          double W4, const double* S, const double* NN, typename AsmTraits<OPS, DUU>::Acc& acc) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Geom g;
     g.clear();
@@ -147,11 +145,41 @@ TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_w
         const uint32_t w = inc_s[k];
         block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(g, recs + (size_t)(w >> 4) * T::REC, (w >> 2) & 3, w & 3, W4, S, NN);
     }
-    typename T::Acc acc;
     block_finalize<T::NEED_K, T::NEED_M, T::WANT_D>(g, A.mat_table + MAT_STRIDE * meta_mat(meta), acc);
+}
+
+// One work item of the inline layout: either write the block (items are in block order: consecutive threads write
+// consecutive addresses of every plane) or park the values of a piece of a split block in its shared-memory slot.
+template <int OPS, int DUU>
+TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_word, int32_t meta, const double* recs,
+                           const uint16_t* inc_s, double* slots, double W4, const double* S, const double* NN) {
+    typedef AsmTraits<OPS, DUU> T;
+    typename T::Acc acc;
+    gather_item<OPS, DUU>(A, inc_word, meta, recs, inc_s, W4, S, NN, acc);
     const int slot = meta_slot(meta);
     if (slot < 0) store_block<OPS, DUU>(A, block0 + (int32_t)(inc_word >> 16), acc);
     else acc.dump(slots + (size_t)slot * T::SLOT);
+}
+
+// Pieces-first layout.  First pass (p < 0): a piece of a split block sums its list and parks the values in its slot.
+// Second pass (p = the block, one thread per block in block order): a plain block sums its whole list; a combine item
+// (slot field set) adds its meta_len(meta) parked pieces in list order.  Either way the block is stored by the thread
+// at its block-order position: the plane stores of a warp are contiguous.
+template <int OPS, int DUU>
+TEFEM_HD void process_pf_item(const AssembleArgs& A, int32_t p, uint32_t inc_word, int32_t meta, const double* recs,
+                              const uint16_t* inc_s, double* slots, double W4, const double* S, const double* NN) {
+    typedef AsmTraits<OPS, DUU> T;
+    typename T::Acc acc;
+    const int slot = meta_slot(meta);
+    if (p < 0 || slot < 0) {
+        gather_item<OPS, DUU>(A, inc_word, meta, recs, inc_s, W4, S, NN, acc);
+    } else {
+        acc.clear();
+        const int n = meta_len(meta);
+        for (int c = 0; c < n; ++c) acc.add_from(slots + (size_t)(slot + c) * T::SLOT);
+    }
+    if (p < 0) acc.dump(slots + (size_t)slot * T::SLOT);
+    else store_block<OPS, DUU>(A, p, acc);
 }
 
 // Phase 3 for one split block: add the values of its items in list order (= ascending element) and write the block.
@@ -233,6 +261,7 @@ const QuadTables& quad_tables() {
 
 struct TileDims {
     int n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes;
+    int pieces_first;   // item layout of every tile: 0 = inline (split lists), 1 = pieces first + one item per block
 };
 
 }  // namespace tefem
@@ -346,7 +375,7 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
 // Shared memory: [element records][partial-sum slots][stage 0][stage 1][2 mbarriers][S, NN tables].
 // The quadrature tables are indexed by the per-incidence local node numbers: from shared memory (20 distinct
 // banks, broadcast) instead of constant memory, where a warp's divergent indices would be serialised.
-template <int OPS, int DUU>
+template <int OPS, int DUU, bool PF>
 __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
                                                                   int part_doubles) {
     extern __shared__ __align__(128) double smem[];
@@ -397,7 +426,7 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(con
         const uint32_t parity = (uint32_t)(k >> 1) & 1u;
         while (!mbar_try_wait(&bars[s], parity)) {}
         const int32_t* hdr = reinterpret_cast<const int32_t*>(st + L.hdr);
-        const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], n_split = hdr[H_NSPLIT], o_elems = hdr[H_OELEMS];
+        const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], o_elems = hdr[H_OELEMS];
         const int32_t block0 = hdr[H_BLOCK0];
         const double* xyz = reinterpret_cast<const double*>(st + L.xyz);
         const uint32_t* conn8 = reinterpret_cast<const uint32_t*>(st + L.conn8);
@@ -414,16 +443,31 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(con
             }
         }
         __syncthreads();
-        // phase 2: work items in block order
-        for (int it = threadIdx.x; it < n_items; it += ASM_THREADS)
-            process_item<OPS, DUU>(A, block0, (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, W4, tabS, tabNN);
-        // phase 3: blocks with several items (the diagonal blocks, material interfaces)
-        if (n_split > 0) {   // uniform over the CTA
-            __syncthreads();
-            const int32_t* sp_block = reinterpret_cast<const int32_t*>(st + L.sp_block);
-            const int32_t* sp_meta = reinterpret_cast<const int32_t*>(st + L.sp_meta);
-            for (int q = threadIdx.x; q < n_split; q += ASM_THREADS)
-                combine_split<OPS, DUU>(A, block0 + sp_block[q], sp_meta[q], partials);
+        if (PF) {   // pieces-first layout
+            const int n_piece = hdr[H_NPIECE];
+            // phase 2a: the pieces of the split blocks (diagonal chunks, material interfaces; lists of similar length)
+            // park their values; phase 2b: one thread per block, in block order (one copy of the incidence loop)
+#pragma unroll 1
+            for (int ph = (n_piece > 0 ? 0 : 1); ph < 2; ++ph) {
+                const int lo = ph ? n_piece : 0, hi = ph ? n_items : n_piece;
+                for (int it = lo + threadIdx.x; it < hi; it += ASM_THREADS)
+                    process_pf_item<OPS, DUU>(A, ph ? block0 + (it - lo) : -1, (uint32_t)it_inc[it], it_meta[it], recs, inc_s,
+                                              partials, W4, tabS, tabNN);
+                if (ph == 0) __syncthreads();
+            }
+        } else {
+            // phase 2: work items in block order
+            for (int it = threadIdx.x; it < n_items; it += ASM_THREADS)
+                process_item<OPS, DUU>(A, block0, (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, W4, tabS, tabNN);
+            // phase 3: blocks with several items (the diagonal blocks, material interfaces)
+            const int n_split = hdr[H_NSPLIT];
+            if (n_split > 0) {   // uniform over the CTA
+                __syncthreads();
+                const int32_t* sp_block = reinterpret_cast<const int32_t*>(st + L.sp_block);
+                const int32_t* sp_meta = reinterpret_cast<const int32_t*>(st + L.sp_meta);
+                for (int q = threadIdx.x; q < n_split; q += ASM_THREADS)
+                    combine_split<OPS, DUU>(A, block0 + sp_block[q], sp_meta[q], partials);
+            }
         }
         __syncthreads();   // records, partials and this stage are free again
     }
@@ -449,8 +493,8 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
 
-template <int OPS, int DUU>
-static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
+template <int OPS, int DUU, bool PF>
+static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
     const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
     const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
     const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
@@ -459,20 +503,25 @@ static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_
     static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         int dev = 0;
         TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
         TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
     int per_sm = 0;
-    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU>, ASM_THREADS, smem));
+    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU, PF>, ASM_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count * per_sm;
     if (grid > d.n_cta) grid = d.n_cta;
-    assemble_kernel<OPS, DUU><<<grid, ASM_THREADS, smem, st>>>(A, d, rec_doubles, part_doubles);
+    assemble_kernel<OPS, DUU, PF><<<grid, ASM_THREADS, smem, st>>>(A, d, rec_doubles, part_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
+}
+
+template <int OPS, int DUU>
+static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
+    return d.pieces_first ? launch_assemble_pf<OPS, DUU, true>(A, d, st) : launch_assemble_pf<OPS, DUU, false>(A, d, st);
 }
 
 template <int OPS>
@@ -512,7 +561,8 @@ extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta,
     TEFEM_REQUIRE(mat_table && bad_elem && h_max, "null input");
     TEFEM_REQUIRE(cta_hdr && cta_elems && cta_conn8 && cta_xyz && item_inc && item_meta && inc, "null schedule");
     const int max_items = h_max[0], max_elems = h_max[1], max_inc = h_max[2], max_slots = h_max[3], max_split = h_max[4],
-              max_nodes = h_max[5];
+              max_nodes = h_max[5], pieces_first = h_max[6];
+    TEFEM_REQUIRE(pieces_first == 0 || (pieces_first == 1 && max_split == 0), "item layout flag");
     TEFEM_REQUIRE(max_split == 0 || (split_block && split_meta), "null split lists");
     const uintptr_t align_or = (uintptr_t)cta_hdr | (uintptr_t)cta_conn8 | (uintptr_t)cta_xyz | (uintptr_t)item_inc |
                                (uintptr_t)item_meta | (uintptr_t)split_block | (uintptr_t)split_meta | (uintptr_t)inc;
@@ -537,7 +587,7 @@ extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta,
     A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
-    const TileDims d = {n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes};
+    const TileDims d = {n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes, pieces_first};
     cudaStream_t st = as_stream(stream);
     switch (ops) {
         case 1: return dispatch_duu<1>(A, duu, d, st);
@@ -592,12 +642,28 @@ static int emu_run(const AssembleArgs& A, const TileDims& d, int n_mat) {
                 if (e < *slot) *slot = e;
             }
         }
+        const int n_piece = h[H_NPIECE];
+        if (n_piece < 0 || n_piece > h[H_NITEMS] || n_piece > d.max_slots || (n_piece > 0 && h[H_NSPLIT] != 0)) return TEFEM_ERR_INVALID;
+        if (!d.pieces_first && n_piece != 0) return TEFEM_ERR_INVALID;
         for (int it = 0; it < h[H_NITEMS]; ++it) {
             const int32_t meta = A.item_meta[h[H_OITEMS] + it];
             const int slot = meta_slot(meta);
             const uint32_t iw = (uint32_t)A.item_inc[h[H_OITEMS] + it];
             const int32_t s = (int32_t)(iw & 0xffffu);
-            if (slot >= d.max_slots || s + meta_len(meta) > h[H_NINC] || meta_mat(meta) >= n_mat) return TEFEM_ERR_INVALID;
+            if (meta_mat(meta) >= n_mat) return TEFEM_ERR_INVALID;
+            if (d.pieces_first) {
+                if (it < n_piece) {   // piece k parks in slot k
+                    if (slot != it || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
+                    process_pf_item<OPS, DUU>(A, -1, iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
+                } else {              // block items: all pieces were processed before (the kernel synchronises)
+                    const int b = it - n_piece;
+                    if ((int)(iw >> 16) != b) return TEFEM_ERR_INVALID;
+                    if (slot < 0 ? s + meta_len(meta) > h[H_NINC] : slot + meta_len(meta) > n_piece) return TEFEM_ERR_INVALID;
+                    process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
+                }
+                continue;
+            }
+            if (slot >= d.max_slots || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
             process_item<OPS, DUU>(A, h[H_BLOCK0], iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
         }
         for (int k = 0; k < h[H_NSPLIT]; ++k) {
@@ -622,7 +688,7 @@ extern "C" int tefem_emu_assemble(const double* mat_table, int n_mat, int32_t n_
     A.item_inc = item_inc; A.item_meta = item_meta; A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
     A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
-    const TileDims d = {n_cta, h_max[0], h_max[1], h_max[2], h_max[3], h_max[4], h_max[5]};
+    const TileDims d = {n_cta, h_max[0], h_max[1], h_max[2], h_max[3], h_max[4], h_max[5], h_max[6]};
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
 #define TEFEM_EMU_CASE(O)                                                     \
     case O:                                                                   \

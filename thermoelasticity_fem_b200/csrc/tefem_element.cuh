@@ -146,7 +146,10 @@ TEFEM_HD void block_accumulate(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, const doubl
     if (WITH_K || WITH_D) ds = det * S[a];
     if (WITH_K) {
         const double ga0 = rec[REC_G + 3 * a], ga1 = rec[REC_G + 3 * a + 1], ga2 = rec[REC_G + 3 * a + 2];
-        const double gb0 = rec[REC_G + 3 * b], gb1 = rec[REC_G + 3 * b + 1], gb2 = rec[REC_G + 3 * b + 2];
+        double gb0 = ga0, gb1 = ga1, gb2 = ga2;
+        if (a != b) {   // diagonal incidences (all lanes of a warp of diagonal chunks) skip three shared-memory loads
+            gb0 = rec[REC_G + 3 * b]; gb1 = rec[REC_G + 3 * b + 1]; gb2 = rec[REC_G + 3 * b + 2];
+        }
         const double wd = W4 * det;
         const double w0 = wd * ga0, w1 = wd * ga1, w2 = wd * ga2;
         acc.P[0] += w0 * gb0; acc.P[1] += w0 * gb1; acc.P[2] += w0 * gb2;

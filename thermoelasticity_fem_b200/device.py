@@ -44,8 +44,7 @@ class DeviceMesh:
         # work item are part of the schedule): every tile segment is one bulk copy for K1
         S = self.schedule
         self.cta_xyz = self.coords[S.cta_nodes.long()].contiguous()
-        self._h_max = np.array([S.max_cta_items, S.max_cta_elems, S.max_cta_inc, S.max_cta_slots, S.max_cta_split,
-                                S.max_cta_nodes], dtype=np.int32)
+        self._h_max = S.h_max()
         self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
 
     # ---- K1 -------------------------------------------------------------------------------------

@@ -16,7 +16,8 @@ Outputs (see include/tefem.h, tefem_assemble):
   tile-packed schedule       a tile owns a contiguous range of node rows; everything it needs is stored in
                              per-tile segments that start on 16-byte boundaries (each segment is fetched with
                              one bulk copy into shared memory):
-    cta_hdr[n_cta, 12]         n_items, n_elems, n_inc, n_split, n_nodes, the five segment offsets, first block
+    cta_hdr[n_cta, 12]         n_items, n_elems, n_inc, n_split, n_nodes, the five segment offsets, first block,
+                               n_pieces (pieces-first layout, see build_schedule; 0 = inline layout)
     item_block/inc/meta        work items: a block, or a piece of a block's incidence list - lists are cut where
                                the material of the elements changes (every item is material-uniform, the kernel
                                applies the material constants once per item) and long uniform runs (the diagonal
@@ -30,6 +31,7 @@ Outputs (see include/tefem.h, tefem_assemble):
     cta_elems, cta_conn8       elements the tile stages, and their connectivity as 4 tile-local node bytes
     cta_nodes                  nodes whose coordinates the tile stages
 """
+import os
 from dataclasses import dataclass
 
 import torch
@@ -41,8 +43,11 @@ ITEM_SORT_WINDOW = 1         # > 1: items ordered longest-first inside windows o
                              # helps the K-only launch by <= 12 %, scatters the 29 plane stores of M + D + K: off)
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
+# True: the pieces of split blocks come first in a tile's item list and every block has one item in block order behind
+# them (see build_schedule); False: pieces inline + split lists.  TEFEM_PIECES_FIRST=0/1 overrides (A/B measurements).
+PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "0") == "1"
 HDR_STRIDE = 12
-H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0 = range(11)
+H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)
 
 
 @dataclass
@@ -75,12 +80,19 @@ class Schedule:
     item_meta: torch.Tensor      # int32 [padded]
     split_block: torch.Tensor    # int32 [padded] tile-local block
     split_meta: torch.Tensor     # int32 [padded]
+    pieces_first: bool = False   # item layout of the tiles (build_schedule)
 
     def to(self, device):
         kw = {}
         for k, v in self.__dict__.items():
             kw[k] = v.to(device) if isinstance(v, torch.Tensor) else v
         return Schedule(**kw)
+
+    def h_max(self):
+        """The h_max[7] argument of tefem_assemble (shared-memory sizes of the largest tile, item layout)."""
+        import numpy as np
+        return np.array([self.max_cta_items, self.max_cta_elems, self.max_cta_inc, self.max_cta_slots, self.max_cta_split,
+                         self.max_cta_nodes, int(self.pieces_first)], dtype=np.int32)
 
     def schedule_bytes(self):
         """Bytes of slot-map / schedule data one assembly launch reads (cta_xyz is counted by DeviceMesh)."""
@@ -117,25 +129,41 @@ class _TileTooLarge(Exception):
 def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                    items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA,
                    max_chunk: int = MAX_CHUNK, mat_id: torch.Tensor = None,
-                   item_sort_window: int = None) -> Schedule:
+                   item_sort_window: int = None, pieces_first: bool = None, tile_cost: str = None) -> Schedule:
     """conn: integer tensor [E, 4] in the reference's element order; node numbers < n_nodes.
     n_rows: only rows of nodes < n_rows are assembled (row-partitioned multi-GPU: owned nodes
     are numbered first); default all.
     mat_id: material row of every element (< 256); default: one material (row 0).
+    pieces_first: item layout of a tile.  False: items in (block, chunk) order, the pieces of split blocks park
+    their values in slots and the split lists name the blocks to combine afterwards.  True: the tile's item list
+    starts with ALL pieces of its split blocks (cta_hdr[11] = their number; piece k parks in slot k), followed by
+    exactly one item per block in block order - a plain block (its whole list), or a "combine" item
+    (item_meta = n_pieces | (first slot + 1) << 8) that adds the parked pieces in list order.  The kernel runs the
+    pieces, synchronises, then the block items: warps hold lists of similar length (the diagonal chunks no longer
+    sit between the short off-diagonal lists) and EVERY block is stored by the thread at its block-order position
+    (no scattered stores of the combined blocks).  Same chunks, same summation order: bitwise the same values.
+    tile_cost: what `items_per_cta` bounds - 'items' (all work items of the tile's rows; default of the inline layout)
+    or 'blocks' (its blocks = the threads of the block-order pass; default of the pieces-first layout).
 
     A tile must not reference more than 256 nodes / 4096 elements (byte / 12-bit local numbers); meshes whose
     node numbering has little locality (e.g. the Gmsh numbering of data/sandwich.msh) get smaller tiles."""
+    pieces_first = PIECES_FIRST if pieces_first is None else bool(pieces_first)
+    if tile_cost is None:
+        tile_cost = 'blocks' if pieces_first else 'items'
+    assert tile_cost in ('items', 'blocks')
     for _ in range(12):
         try:
             return _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id,
-                                   ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window)
+                                   ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
+                                   pieces_first, tile_cost)
         except _TileTooLarge:
             items_per_cta = max(16, (3 * items_per_cta) // 4)
             elem_budget = max(32, (3 * elem_budget) // 4)
     raise RuntimeError("could not build a tile schedule within the shared-memory index limits")
 
 
-def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id=None, item_sort_window=1):
+def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id=None, item_sort_window=1,
+                    pieces_first=False, tile_cost='items'):
     assert conn.dim() == 2 and conn.shape[1] == 4
     assert 1 <= max_chunk <= 127
     dev = conn.device
@@ -192,7 +220,7 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
 
     # ---- rows -> tiles: cumulative cost, integer arithmetic (work items vs. staged-element budget)
     degree = torch.bincount(conn.reshape(-1), minlength=N)[:R]
-    cost = torch.maximum(items_per_row * elem_budget, degree * items_per_cta)
+    cost = torch.maximum((items_per_row if tile_cost == 'items' else blocks_per_row) * elem_budget, degree * items_per_cta)
     unit = items_per_cta * elem_budget
     cta_of_row = torch.div(_excl_cumsum(cost), unit, rounding_mode='floor')
     _, cta_of_row = torch.unique_consecutive(cta_of_row, return_inverse=True)    # compact ids
@@ -296,11 +324,46 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
         item_blk, item_inc, item_meta = item_blk[perm], item_inc[perm], item_meta[perm]
         del perm, rank_in_cta, win                                               # cta_of_item is unchanged by the permutation
 
+    n_piece_cta = torch.zeros(n_cta, **i64)
+    if pieces_first and n_items:
+        assert item_sort_window <= 1, "the windowed item order applies to the inline layout only"
+        # pieces of split blocks (already in (tile, block, chunk) order; piece k of a tile parks in slot k) ...
+        pc = torch.nonzero(is_split).reshape(-1)
+        n_piece_cta = slots_per_cta
+        # ... then one item per block, in block order
+        first_item_all = _excl_cumsum(items_per_block)
+        blk_split_mask = items_per_block > 1
+        if int(items_per_block.max().item()) > 255:
+            raise RuntimeError("a block has more than 255 pieces (material changes x chunks)")
+        b_inc = torch.where(blk_split_mask, torch.zeros(P, **i64), item_inc[first_item_all] & 0xffff)
+        b_inc = b_inc | ((torch.arange(P, **i64) - cta_blk_ptr[cta_of_block]) << 16)
+        b_meta = torch.where(blk_split_mask, items_per_block | ((slot[first_item_all] + 1) << 8) | (run_mat[item_run[first_item_all]] << 24),
+                             item_meta[first_item_all])
+        b_meta = torch.where(b_meta >= 2 ** 31, b_meta - 2 ** 32, b_meta)
+        cat_cta = torch.cat([cta_of_item[pc], cta_of_block])
+        perm = torch.sort(cat_cta * 2 + torch.cat([torch.zeros_like(pc), torch.ones(P, **i64)]), stable=True)[1]
+        item_blk = torch.cat([item_blk[pc], torch.arange(P, **i64)])[perm]
+        item_inc = torch.cat([item_inc[pc], b_inc])[perm]
+        item_meta = torch.cat([item_meta[pc], b_meta])[perm]
+        cta_of_item = cat_cta[perm]
+        n_items = int(item_blk.numel())
+        cta_item_ptr = _ptr_from_counts(torch.bincount(cta_of_item, minlength=n_cta), n_cta, dev)
+        max_cta_items = int((cta_item_ptr[1:] - cta_item_ptr[:-1]).max().item())
+        # no split lists in this layout
+        split_local = split_local[:0]
+        split_meta = split_meta[:0]
+        cta_of_split = cta_of_split[:0]
+        cta_split_ptr = torch.zeros(n_cta + 1, **i64)
+        max_cta_split = 0
+        del pc, perm, cat_cta, b_inc, b_meta
     item_block_p, item_pptr, _ = _pad_segments(item_blk, cta_of_item, cta_item_ptr, n_cta, 4, 0)
     item_inc_p, _, _ = _pad_segments(item_inc, cta_of_item, cta_item_ptr, n_cta, 4, 0)
     item_meta_p, _, _ = _pad_segments(item_meta, cta_of_item, cta_item_ptr, n_cta, 4, 0)      # padding: length 0
     split_block_p, split_pptr, _ = _pad_segments(split_local, cta_of_split, cta_split_ptr, n_cta, 4, 0)
     split_meta_p, _, _ = _pad_segments(split_meta, cta_of_split, cta_split_ptr, n_cta, 4, 0)
+    if split_block_p.numel() == 0:                                               # keep the pointers valid (16-byte aligned)
+        split_block_p = torch.zeros(4, **i64)
+        split_meta_p = torch.zeros(4, **i64)
     elems_p, elem_pptr, _ = _pad_segments(cta_elems, cta_of_k2, cta_elem_ptr, n_cta, 4, -1)
     conn8_p, _, _ = _pad_segments(conn8, cta_of_k2, cta_elem_ptr, n_cta, 4, 0)
     nodes_p, node_pptr, _ = _pad_segments(cta_nodes, cta_of_un, cta_node_ptr, n_cta, 2, -1)
@@ -312,10 +375,9 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
 
     def cnt(ptr):
         return ptr[1:] - ptr[:-1]
-    zero = torch.zeros(n_cta, **i64)
     cta_hdr = torch.stack([cnt(cta_item_ptr), cnt(cta_elem_ptr), cnt(cta_inc_ptr), cnt(cta_split_ptr), cnt(cta_node_ptr),
                            item_pptr[:-1], elem_pptr[:-1], inc_pptr[:-1], split_pptr[:-1], node_pptr[:-1], cta_blk_ptr[:-1],
-                           zero], dim=1)
+                           n_piece_cta], dim=1)
     assert int(inc_pptr[-1].item()) < 2 ** 31
 
     i32 = torch.int32
@@ -326,4 +388,5 @@ def _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk
                     max_cta_slots=max_cta_slots, max_cta_split=max_cta_split, max_cta_nodes=max_cta_nodes,
                     cta_hdr=cta_hdr.to(i32).contiguous(), cta_elems=elems_p.to(i32), cta_conn8=conn8_p.to(i32),
                     cta_nodes=nodes_p.to(i32), item_block=item_block_p.to(i32), item_inc=item_inc_p.to(i32),
-                    item_meta=item_meta_p.to(i32), split_block=split_block_p.to(i32), split_meta=split_meta_p.to(i32))
+                    item_meta=item_meta_p.to(i32), split_block=split_block_p.to(i32), split_meta=split_meta_p.to(i32),
+                    pieces_first=bool(pieces_first))

@@ -1,0 +1,56 @@
+"""A/B of K1 item layouts on the GPU box: inline (split lists) vs pieces-first, same mesh, same chunks.
+Checks that the planes are BITWISE identical (same chunks => same summation order) and times both.
+usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first" ...]   (first variant = reference)"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from thermoelasticity_fem_b200 import LinearThermoElastic  # noqa: E402
+from thermoelasticity_fem_b200.device import DeviceMesh  # noqa: E402
+from thermoelasticity_fem_b200.symbolic import build_schedule  # noqa: E402
+from thermoelasticity_fem_b200.synthetic import kuhn_box  # noqa: E402
+
+cells = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+variants = sys.argv[2:] or ["256,310,8,0", "256,310,8,1", "272,330,8,1", "256,310,6,1", "512,620,8,1"]
+pts, tets, tris, nodes = kuhn_box(cells, cells, cells, 1.0, 1.0, 1.0, n_layers=1, index_dtype=np.int32)
+conn = tets[1]
+mat = LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.)
+table = np.array([mat.table_row()])
+E, N = conn.shape[0], pts.shape[0]
+conn_d = torch.from_numpy(conn).cuda()
+ref = {}
+for v in variants:
+    items, budget, chunk, pf = [int(x) for x in v.split(",")]
+    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk, pieces_first=bool(pf))
+    dm = DeviceMesh(pts, conn, np.zeros(E, dtype=np.int32), table, schedule=S)
+    P = S.n_blocks
+    line = f"{v:14s} n_cta={S.n_cta} items={S.n_items} max_items={S.max_cta_items} max_el={S.max_cta_elems} slots={S.max_cta_slots} |"
+    for ops, nnz in (("K", 13), ("MKD", 29)):
+        out = dm.assemble(ops, 0.2, 0.2)
+        for _ in range(3):
+            dm.assemble(ops, 0.2, 0.2, out=out, check=False)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(10):
+            dm.assemble(ops, 0.2, 0.2, out=out, check=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 10
+        alg = 8 * nnz * P + 20 * E + 24 * N + 64 * E
+        line += f" {ops}: {ms:.3f} ms {E / ms / 1e6:.2f} Gel/s {alg / ms / 1e6 / 6554.9 * 100:.1f}% |"
+        key = (ops, chunk)
+        if key not in ref:
+            ref[key] = {k: t.clone() for k, t in out.items()}
+            line += " (ref)"
+        else:
+            same = all(torch.equal(ref[key][k], out[k]) for k in out)
+            worst = max(float(((ref[key][k] - out[k]).abs().max() / ref[key][k].abs().max()).item()) for k in out)
+            line += f" bitwise={'YES' if same else 'NO'} maxrel={worst:.1e}"
+        del out
+    print(line, flush=True)
+    del dm, S

@@ -13,6 +13,9 @@ Fixtures written (all produced by the reference's own classes, nothing from the 
 * sandwich_steady.npz      config 1 (examples/example_steadystate.py): DOF maps, F, F_f, raw spsolve X, U, T
 * sandwich_transient2.npz  config 2 (examples/example_transient_2.py): DOF maps, F(idx), states at chosen steps
 * kuhn_small.npz           4x2x3 Kuhn box with three different materials: all element matrices, M, D, K, maps, F
+* sandwich_rom3.npz        config of examples/example_transient_3.py (LinearTransient.solve_ROM, reduced-order bases from
+                           eigs): Rayleigh quotients of the bases, basis-independent fingerprints of the two subspaces,
+                           U / T / their rates at chosen steps  (--only rom [--rom-modes 30,30])
 """
 import argparse
 import os
@@ -181,6 +184,37 @@ def run_transient(ref, n_steps, keep):
           % (n_steps, time.time() - t, d["maxU"], d["maxTheta"]))
 
 
+def run_rom(ref, n_u, n_t_modes, keep):
+    """examples/example_transient_3.py: config 2 solved with solve_ROM (solvers.py:219-354, model.py:341-440).
+    The bases returned by eigs are unique only up to sign / rotation inside an eigenspace, so the fixture stores
+    basis-independent data: Rayleigh quotients, the M- (D-) orthogonal projection of a fixed vector onto each
+    subspace, and the physical histories U, T at chosen steps."""
+    t = time.time()
+    mesh, model, t_end, n_t = config2(ref)
+    solver = ref.solvers.LinearTransient(model, np.zeros(mesh.n_nodes * 3), np.zeros(mesh.n_nodes * 3),
+                                         np.zeros(mesh.n_nodes), np.zeros(mesh.n_nodes), t_end, n_t, 1 / 2, 1 / 4)
+    solver.solve_ROM(n_modes_u=n_u, n_modes_theta=n_t_modes)
+    print("reference solve_ROM done in %.1f s" % (time.time() - t))
+    d = maps_of(model)
+    fu, ft = np.array(model.free_dofs_U), np.array(model.free_dofs_theta)
+    Muu, Kuu = model.mat_M[fu, :][:, fu], model.mat_K[fu, :][:, fu]
+    Dtt, Ktt = model.mat_D[ft, :][:, ft], model.mat_K[ft, :][:, ft]
+    for nm, phi, A, B, n in (("u", model.mat_phi_u, Kuu, Muu, fu.size), ("t", model.mat_phi_t, Ktt, Dtt, ft.size)):
+        G = phi.T @ (B @ phi)
+        d["lam_" + nm] = np.sort(np.linalg.eigvals(np.linalg.solve(G, phi.T @ (A @ phi))).real)
+        w = fingerprint_weights(n)
+        d["proj_" + nm] = phi @ np.linalg.solve(G, phi.T @ (B @ w))      # B-orthogonal projection of w onto span(phi)
+        d["resid_" + nm] = np.array(max(np.linalg.norm(A @ phi[:, j] - ((phi[:, j] @ (A @ phi[:, j])) / (phi[:, j] @ (B @ phi[:, j])))
+                                                       * (B @ phi[:, j])) / np.linalg.norm(A @ phi[:, j]) for j in range(phi.shape[1])))
+    keep = [k for k in keep if k < n_t]
+    d.update(steps=np.array(keep), n_modes=np.array([n_u, n_t_modes]), U=solver.U[:, keep], T=solver.T[:, keep],
+             Udot=solver.Udot[:, keep], Tdot=solver.Tdot[:, keep],
+             maxU=np.array(np.abs(solver.U).max()), maxT=np.array(np.abs(solver.T).max()))
+    np.savez_compressed(os.path.join(OUT, "sandwich_rom3.npz"), **d)
+    print("rom (%d + %d modes) done in %.1f s; max|U| = %.16g, max|T| = %.16g, eig residuals %.2e / %.2e, lam_u[:3] = %s, lam_t[:3] = %s"
+          % (n_u, n_t_modes, time.time() - t, d["maxU"], d["maxT"], d["resid_u"], d["resid_t"], d["lam_u"][:3], d["lam_t"][:3]))
+
+
 def run_kuhn(ref):
     """Small structured box with three DIFFERENT materials, non-zero Dirichlet values, all load kinds."""
     from thermoelasticity_fem_b200.synthetic import kuhn_box
@@ -247,6 +281,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--transient-steps", type=int, default=999)
     ap.add_argument("--only", default="")
+    ap.add_argument("--rom-modes", default="30,30")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     ref = rs.load_reference()
@@ -262,6 +297,9 @@ def main():
         run_operators(ref, K)
     if only is None or "transient" in only:
         run_transient(ref, args.transient_steps, [1, 2, 10, 100, 500, 999])
+    if only is None or "rom" in only:
+        n_u, n_th = [int(v) for v in args.rom_modes.split(",")]
+        run_rom(ref, n_u, n_th, [1, 2, 10, 100, 500, 999])
 
 
 if __name__ == "__main__":

@@ -1,0 +1,156 @@
+"""Reduced-order path (reference model.py:341-440, solvers.py:219-354).
+
+CPU: the block shift-invert Lanczos iteration of rom.py against dense eigen-decompositions (scipy-backed operators).
+GPU: bases / reduced solve on data/sandwich.msh against the committed outputs of the reference's own solve_ROM
+(tests/golden/sandwich_rom3.npz, the configuration of examples/example_transient_3.py).  The reference's bases are
+unique only up to sign (rotation inside a multiple eigenvalue), so the comparison uses basis-independent quantities:
+eigenvalues, the B-orthogonal projection of a fixed vector onto each subspace, and the physical histories U, T."""
+import numpy as np
+import pytest
+import scipy.linalg
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+import torch
+
+from conftest import golden
+from thermoelasticity_fem_b200.rom import block_lanczos_smallest
+
+MAT2 = (2300, 64e9, 0.1, 1., 1., 4e-6, 20.)
+
+
+def laplacian3(m, neumann=False):
+    T = sp.diags([-np.ones(m - 1), 2 * np.ones(m), -np.ones(m - 1)], [-1, 0, 1]).tolil()
+    if neumann:
+        T[0, 0] = T[m - 1, m - 1] = 1.0
+    T = T.tocsc()
+    eye = sp.identity(m, format="csc")
+    return (sp.kron(sp.kron(T, eye), eye) + sp.kron(sp.kron(eye, T), eye) + sp.kron(sp.kron(eye, eye), T)).tocsc()
+
+
+def scipy_ops(A, B, shift):
+    lu = spl.splu((A + shift * B).tocsc())
+    return (lambda X: torch.from_numpy((B @ X.numpy().T).T.copy()),
+            lambda R, X0=None: torch.from_numpy(lu.solve(R.numpy().T.copy()).T.copy()))
+
+
+@pytest.mark.parametrize("neumann", [False, True])
+def test_block_lanczos_matches_dense_eigh(neumann):
+    m, k = 9, 14
+    A = laplacian3(m, neumann)                     # triple eigenvalues (cube symmetry); singular when neumann
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    B = sp.diags(1.0 + rng.random(n)).tocsc()
+    shift = 0.05 if neumann else 0.0
+    apply_B, solve_A = scipy_ops(A, B, shift)
+    x0 = torch.from_numpy(rng.random((6, n)) - 0.5)
+    lam, X, info = block_lanczos_smallest(apply_B, solve_A, x0, k, tol=1e-10, shift=shift)
+    assert info["converged"]
+    ref, vec = scipy.linalg.eigh(A.toarray(), B.toarray())
+    assert np.max(np.abs(lam - ref[:k])) <= 1e-9 * ref[k]
+    Xn = X.numpy()
+    assert np.allclose(Xn @ (B @ Xn.T), np.eye(k), atol=1e-9)                     # B-orthonormal rows
+    # same invariant subspace wherever the cut does not split a cluster
+    cut = k
+    while cut > 0 and ref[cut] - ref[cut - 1] < 1e-8 * ref[k]:
+        cut -= 1
+    P_ref = vec[:, :cut] @ (vec[:, :cut].T @ B.toarray())
+    lead = Xn[:cut].T
+    assert np.max(np.abs(P_ref @ lead - lead)) < 1e-7
+    res = np.linalg.norm(A @ Xn.T - (B @ Xn.T) * lam, axis=0) / np.maximum(np.linalg.norm(A @ Xn.T, axis=0), 1e-300)
+    assert res[1 if neumann else 0:].max() < 1e-7
+
+
+def test_block_lanczos_needs_enough_vectors():
+    A = laplacian3(4)
+    B = sp.identity(A.shape[0], format="csc")
+    apply_B, solve_A = scipy_ops(A, B, 0.0)
+    x0 = torch.from_numpy(np.random.default_rng(0).random((2, A.shape[0])) - 0.5)
+    with pytest.raises(RuntimeError):
+        block_lanczos_smallest(apply_B, solve_A, x0, 10, max_vectors=4)
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------------
+
+def rom_model(sandwich):
+    from thermoelasticity_fem_b200 import LinearThermoElastic, Mesh, Model
+    pts, blocks, groups = sandwich
+    mesh = Mesh().from_arrays(pts, groups["tet"], groups["tri"], groups["nodes"])
+    mesh.set_materials({k: LinearThermoElastic(*MAT2) for k in (1, 2, 3)})
+    mesh.make_elements()
+    t_end, n_t = 1800e0, 1000
+    vec_t = np.linspace(0., t_end, n_t)
+    arr = np.zeros((3, n_t))
+    arr[0, :] = np.sin(2 * np.pi * vec_t / 900.) * -1e9
+    model = Model(mesh, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
+                  dict_dirichlet_theta={4: 0., 5: 0.}, dict_surface_forces={5: arr}, alpha_M=2e-1, alpha_K=2e-1)
+    return mesh, model, t_end, n_t
+
+
+def fingerprint_weights(n):                         # = oracle/make_golden.py
+    k = np.arange(n, dtype=np.float64)
+    return 1.0 + np.mod(k * 0.6180339887498949, 1.0)
+
+
+@pytest.mark.gpu
+def test_reduced_bases_span_the_reference_subspaces(sandwich):
+    g = golden("sandwich_rom3.npz")
+    mesh, model, t_end, n_t = rom_model(sandwich)
+    model.create_free_dofs_lists()
+    model.assemble_MDK()
+    n_u, n_th = [int(v) for v in g["n_modes"]]
+    model.compute_ROB_u(n_u)
+    model.compute_ROB_theta(n_th)
+    assert model.rob_info_u["converged"] and model.rob_info_t["converged"]
+    assert model.rob_info_u["residual"] < 1e-7 and model.rob_info_t["residual"] < 1e-7
+    assert np.max(np.abs(model.eig_u / g["lam_u"] - 1)) < 1e-7
+    assert np.max(np.abs(model.eig_t / g["lam_t"] - 1)) < 1e-7
+    assert np.array_equal(model.free_dofs_U, g["free_dofs_U"]) and np.array_equal(model.free_dofs_theta, g["free_dofs_theta"])
+    for nm, phi, op, free in (("u", model.mat_phi_u, "M", model.free_dofs_U), ("t", model.mat_phi_t, "D", model.free_dofs_theta)):
+        assert phi.shape == (free.size, n_u if nm == "u" else n_th)
+        assert np.allclose(np.linalg.norm(phi, axis=0), 1.0, atol=1e-12)           # unit columns like eigs
+        B = model.touched(op).tocsr()[free, :].tocsc()[:, free]
+        w = fingerprint_weights(free.size)
+        proj = phi @ np.linalg.solve(phi.T @ (B @ phi), phi.T @ (B @ w))
+        assert np.linalg.norm(proj - g["proj_" + nm]) <= 1e-6 * np.linalg.norm(g["proj_" + nm]), nm
+
+
+@pytest.mark.gpu
+def test_solve_ROM_matches_reference_histories(sandwich):
+    from thermoelasticity_fem_b200 import LinearTransient
+    g = golden("sandwich_rom3.npz")
+    mesh, model, t_end, n_t = rom_model(sandwich)
+    N = mesh.n_nodes
+    solver = LinearTransient(model, np.zeros(3 * N), np.zeros(3 * N), np.zeros(N), np.zeros(N), t_end, n_t, 0.5, 0.25,
+                             progress=False)
+    n_u, n_th = [int(v) for v in g["n_modes"]]
+    solver.solve_ROM(n_modes_u=n_u, n_modes_theta=n_th)
+    assert solver.U.shape == (3 * N, n_t) and solver.T.shape == (N, n_t) and solver.q.shape == (n_u + n_th, n_t)
+    assert abs(np.abs(solver.U).max() / float(g["maxU"]) - 1) < 1e-6
+    steps = g["steps"]
+    for nm in ("U", "T", "Udot", "Tdot"):
+        got, ref = getattr(solver, nm)[:, steps], g[nm]
+        ref_shift = 20.0 if nm == "T" else 0.0                                      # T carries the reference temperature
+        err = np.abs(got - ref).max(axis=0) / np.maximum(np.abs(ref - ref_shift).max(axis=0), 1e-300)
+        assert err.max() < 1e-5, (nm, err)
+    # the reduced matrices reproduce the pencils' eigenvalues: Krom_uu / Mrom_uu and Krom_tt / Drom_tt
+    m = solver.model
+    lu = np.sort(scipy.linalg.eigvals(m.mat_Krom[:n_u, :n_u], m.mat_Mrom[:n_u, :n_u]).real)
+    lt = np.sort(scipy.linalg.eigvals(m.mat_Krom[n_u:, n_u:], m.mat_Drom[n_u:, n_u:]).real)
+    assert np.max(np.abs(lu / g["lam_u"] - 1)) < 1e-6 and np.max(np.abs(lt / g["lam_t"] - 1)) < 1e-6
+
+
+@pytest.mark.gpu
+def test_rom_forces_equal_projected_load_vector(sandwich):
+    mesh, model, t_end, n_t = rom_model(sandwich)
+    model.create_free_dofs_lists()
+    model.assemble_MDK()
+    model.compute_ROB_u(5, tol=1e-7)
+    model.compute_ROB_theta(4, tol=1e-7)
+    for idx in (1, 250):
+        model.assemble_F(idx_t=idx)
+        model.compute_ROM_forces()                                                   # model.py:395-440 from vec_F
+        fast = model.rom_forces(idx)                                                 # cached projected weights
+        assert np.max(np.abs(fast - model.vec_From)) <= 1e-12 * np.abs(model.vec_From).max()
+        F = model.vec_F
+        want = np.r_[model.mat_phi_u.T @ F[model.free_dofs_U], model.mat_phi_t.T @ F[model.free_dofs_theta]]
+        assert np.max(np.abs(model.vec_From - want)) <= 1e-12 * np.abs(want).max()

@@ -187,11 +187,11 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
     mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
             3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
     conn, mat_id, rows = orc.element_table(tets, mats)
-    for items in (256, 64):                       # small tiles: many CTAs, exercises the segment offsets
+    for items, pf in ((256, False), (256, True), (64, False), (64, True)):     # small tiles: many CTAs, exercises the offsets
         chunk = 6 if items == 256 else 3
         S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items),
-                           max_chunk=chunk, mat_id=torch.from_numpy(mat_id))
-        if not S.pieces_first:
+                           max_chunk=chunk, mat_id=torch.from_numpy(mat_id), pieces_first=pf)
+        if not pf:
             check_schedule_invariants(S, conn, pts.shape[0], chunk, mat_id=mat_id)
         vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
         ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)

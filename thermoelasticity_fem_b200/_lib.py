@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtefem_b200.so")
+LIB_PATH = os.environ.get("TEFEM_LIB") or os.path.join(_PKG, "libtefem_b200.so")    # TEFEM_LIB: build variants (experiments)
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NEG_JACOBIAN, ERR_ZERO_JACOBIAN, ERR_NO_CONVERGE, ERR_BREAKDOWN, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7

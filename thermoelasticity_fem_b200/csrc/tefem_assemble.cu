@@ -297,7 +297,10 @@ static int upload_quad() {
     return TEFEM_OK;
 }
 
-constexpr int ASM_THREADS = 256;
+#ifndef ASM_THREADS_N
+#define ASM_THREADS_N 256
+#endif
+constexpr int ASM_THREADS = ASM_THREADS_N;
 #ifndef ASM_MIN_CTAS
 #define ASM_MIN_CTAS 3
 #endif

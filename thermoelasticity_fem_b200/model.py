@@ -11,7 +11,8 @@ Deliberate deviations (documented in DESIGN.md):
   ``dirichlet_dofs_U`` is sorted (the reference's ``list(set(...))`` order is CPython-specific).
 * the exported matrices carry the reference's STORED pattern approximately (exact zeros dropped like
   ``csc_array(dense)``, ``model.py:92``); ``touched(name)`` gives the reproducible touched pattern.
-* the reduced-order-model helpers (``model.py:341-440``) are out of scope.
+* the reduced-order bases (``model.py:341-363``) come from a block shift-invert Lanczos iteration on the GPU operators
+  (``rom.py``) instead of ARPACK: same subspaces, arbitrary signs / rotations inside multiple eigenvalues.
 """
 import numpy as np
 import torch
@@ -69,6 +70,10 @@ class Model:
         self._lift = None            # device [4N]: K @ g_lift (cached)
         self._has_nonzero_dirichlet = False
         self._load_cache = {}
+        self._rom_force_cache = {}
+        self._phi_u_dev = self._phi_t_dev = None
+        self.n_q_u = self.n_q_t = None
+        self.mat_Mrom = self.mat_Drom = self.mat_Krom = self.vec_From = None
 
     # ------------------------------------------------------------------------------------------
     # DOF maps (reference model.py:51-85)
@@ -389,11 +394,107 @@ class Model:
         return self._export["vec_F_f"]
 
     # ------------------------------------------------------------------------------------------
-    # reduced-order model (reference model.py:341-440): out of scope of the B200 hot path
+    # reduced-order model (reference model.py:341-440) - rom.py: block shift-invert Lanczos on the GPU operators
     # ------------------------------------------------------------------------------------------
-    def _rom_out_of_scope(self, *args, **kwargs):
-        raise NotImplementedError("the reduced-order-model path (reference model.py:341-440) is outside the "
-                                  "B200 hot path; the assembled operators are available as scipy matrices "
-                                  "through mat_M / mat_D / mat_K for use with the reference's ROM code")
+    def _compute_ROB(self, field, n_q, tol, **kw):
+        from .rom import FieldEigenProblem
+        if self._mask_host is None:
+            raise RuntimeError("create_free_dofs_lists() must be called first")            # model.py:342,354
+        prob = FieldEigenProblem(self, field, **kw)
+        lam, Phi, info = prob.smallest(int(n_q), tol=tol)
+        return lam, Phi, info
 
-    compute_ROB_u = compute_ROB_theta = compute_ROM_matrices = compute_ROM_forces = _rom_out_of_scope
+    def compute_ROB_u(self, n_q_u, tol=1e-9, **kw):
+        """eigs(K_uu, k=n_q_u, M=M_uu, which='SM') on free_dofs_U (model.py:341-351).  mat_phi_u has unit 2-norm
+        columns like ARPACK's; signs (and rotations inside a multiple eigenvalue) are arbitrary there and here."""
+        self.n_q_u = int(n_q_u)
+        self.eig_u, self._phi_u_dev, self.rob_info_u = self._compute_ROB("u", n_q_u, tol, **kw)
+        self._export.pop("mat_phi_u", None)
+        self._rom_force_cache = {}
+
+    def compute_ROB_theta(self, n_q_t, tol=1e-9, **kw):
+        """eigs(K_tt, k=n_q_t, M=D_tt, which='SM') on free_dofs_theta (model.py:353-363)."""
+        self.n_q_t = int(n_q_t)
+        self.eig_t, self._phi_t_dev, self.rob_info_t = self._compute_ROB("theta", n_q_t, tol, **kw)
+        self._export.pop("mat_phi_t", None)
+        self._rom_force_cache = {}
+
+    @property
+    def mat_phi_u(self):
+        """(len(free_dofs_U), n_q_u) numpy array in the reference's row order (host copy, lazy)."""
+        if getattr(self, "_phi_u_dev", None) is None:
+            return None
+        if "mat_phi_u" not in self._export:
+            self._export["mat_phi_u"] = self._phi_u_dev.cpu().numpy()[:, self.free_dofs_U].T.copy()
+        return self._export["mat_phi_u"]
+
+    @property
+    def mat_phi_t(self):
+        if getattr(self, "_phi_t_dev", None) is None:
+            return None
+        if "mat_phi_t" not in self._export:
+            self._export["mat_phi_t"] = self._phi_t_dev.cpu().numpy()[:, self.free_dofs_theta].T.copy()
+        return self._export["mat_phi_t"]
+
+    def compute_ROM_matrices(self):
+        """Phi^T M Phi, Phi^T D Phi, Phi^T K Phi block by block (model.py:365-393): one plane SpMV per basis vector and
+        operator; the bases vanish on the constrained DOFs, so the [free, free] restriction is implicit."""
+        from .rom import project
+        dm = self.mesh.device_mesh()
+        Pu, Pt = self._phi_u_dev, self._phi_t_dev
+        nu, nt = self.n_q_u, self.n_q_t
+        (Muu,) = project(dm, self._planes["M"], self.plane_map("M"), Pu, [Pu])
+        Duu, Dtu = project(dm, self._planes["D"], self.plane_map("D"), Pu, [Pu, Pt])
+        (Dtt,) = project(dm, self._planes["D"], self.plane_map("D"), Pt, [Pt])
+        (Kuu,) = project(dm, self._planes["K"], self.plane_map("K"), Pu, [Pu])
+        Kut, Ktt = project(dm, self._planes["K"], self.plane_map("K"), Pt, [Pu, Pt])
+        self.mat_Mrom = np.zeros((nu + nt, nu + nt))
+        self.mat_Mrom[:nu, :nu] = Muu
+        self.mat_Drom = np.zeros((nu + nt, nu + nt))
+        self.mat_Drom[:nu, :nu] = Duu
+        self.mat_Drom[nu:, :nu] = Dtu
+        self.mat_Drom[nu:, nu:] = Dtt
+        self.mat_Krom = np.zeros((nu + nt, nu + nt))
+        self.mat_Krom[:nu, :nu] = Kuu
+        self.mat_Krom[:nu, nu:] = Kut
+        self.mat_Krom[nu:, nu:] = Ktt
+
+    def _rom_lift(self):
+        """Phi^T (K_uu g_u) and Phi^T (K_tt g_theta): compute_ROM_forces lifts every field through its OWN diagonal block
+        of K only (model.py:399-418 use K[free_U, dir_U], :420-433 K[free_theta, dir_theta]), unlike apply_dirichlet_F."""
+        if "lift" not in self._rom_force_cache:
+            out = np.zeros(self.n_q_u + self.n_q_t)
+            if self._has_nonzero_dirichlet and "K" in self._planes:
+                dm = self.mesh.device_mesh()
+                full = layout.plane_map_K()
+                for sl, Phi, off in ((slice(0, 3), self._phi_u_dev, 0), (slice(3, 4), self._phi_t_dev, self.n_q_u)):
+                    pm = np.full((4, 4), -1, dtype=np.int8)
+                    pm[sl, sl] = full[sl, sl]
+                    y = torch.zeros(self.mesh.n_dofs, dtype=torch.float64, device=dm.device)
+                    dm.planes_spmv(self._planes["K"], pm, self._g_lift, y)
+                    out[off:off + Phi.shape[0]] = (Phi @ y).cpu().numpy()
+            self._rom_force_cache["lift"] = out
+        return self._rom_force_cache["lift"]
+
+    def rom_forces(self, idx_t=None):
+        """Reduced load vector of time index idx_t without forming F: the loads are lumped nodal weights times an
+        amplitude (load_terms), so Phi^T F = sum_terms (Phi[:, 4 node + c] @ w) coef[c]; the projections of the weight
+        vectors are cached, which leaves an (n_q x 4) product per load and step."""
+        Phi = None
+        out = -self._rom_lift().copy()
+        for node, w, coef in self.load_terms(idx_t):
+            key = (node.data_ptr(), w.data_ptr())
+            if key not in self._rom_force_cache:
+                if Phi is None:
+                    Phi = torch.cat([self._phi_u_dev, self._phi_t_dev])
+                idx = 4 * node.long()
+                self._rom_force_cache[key] = torch.stack([Phi[:, idx + c] @ w for c in range(4)], dim=1).cpu().numpy()
+            out += self._rom_force_cache[key] @ np.asarray(coef, dtype=np.float64)
+        return out
+
+    def compute_ROM_forces(self):
+        """vec_From from the assembled vec_F (model.py:395-440); assemble_F must have been called."""
+        if self._F is None:
+            raise RuntimeError("assemble_F() must be called first")
+        Phi = torch.cat([self._phi_u_dev, self._phi_t_dev])
+        self.vec_From = (Phi @ self._F).cpu().numpy() - self._rom_lift()

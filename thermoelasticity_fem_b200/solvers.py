@@ -7,7 +7,8 @@ uniform 4x4 node-block layout (kernel K2), and the Newmark update (``solvers.py:
 vector kernels (K7).  Extra keyword arguments (``rtol``, ``max_iter``, ``history`` ...) have defaults,
 so reference scripts run unchanged.
 
-Out of scope: ``solve_ROM`` / ``solve_ROM_nonparametric`` (``solvers.py:219-668``).
+``solve_ROM`` (``solvers.py:219-354``) runs on reduced-order bases computed on the GPU (``rom.py``); the
+non-parametric UQ solver ``solve_ROM_nonparametric`` (``solvers.py:356-668``) is out of scope.
 """
 import os
 import time
@@ -40,14 +41,17 @@ def _deinterleave(X, n_nodes):
 class _SystemSolve:
     """Shared by both solvers: forms the eliminated, block-Jacobi-scaled system and solves with it."""
 
-    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="auto"):
+    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="auto", dir_mask=None):
+        """dir_mask (uint8 [4N], default: the model's Dirichlet DOFs): DOFs eliminated from the system (identity rows
+        and columns); the reduced-order bases pass the complement of one field's free DOFs (rom.py)."""
         self.model = model
         self.dm = model.mesh.device_mesh()
+        self.dir_mask = model._dir_mask if dir_mask is None else dir_mask
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
         d_layout = layout.n_planes(layout.plane_map_D(*model._d_alpha)) if "D" in model._planes else 4
         planes = {k: v for k, v in model._planes.items()
                   if (k == "M" and cM != 0.) or (k == "D" and cD != 0.) or (k == "K" and cK != 0.)}
-        self.sys = self.dm.form_system(planes, cM, cD, cK, d_layout, model._dir_mask)
+        self.sys = self.dm.form_system(planes, cM, cD, cK, d_layout, self.dir_mask)
         self.dinv = self.dm.block_jacobi_scale(self.sys)
         self.krylov = KrylovSolver(self.dm)
         # right preconditioner on top of the block-Jacobi scaling: aggregation coarse correction (multilevel.py);
@@ -66,7 +70,7 @@ class _SystemSolve:
 
     def solve(self, rhs, x):
         """x <- solution of A_ff x_f = rhs_f (constrained entries of x stay 0)."""
-        self.dm.block_jacobi_apply(self.dinv, rhs, self.b, self.model._dir_mask)
+        self.dm.block_jacobi_apply(self.dinv, rhs, self.b, self.dir_mask)
         info = self.krylov.bicgstab(self.sys, self.b, x, self.rtol, self.max_iter, self.check_every)
         self.info.append(info)
         return info
@@ -268,8 +272,76 @@ class LinearTransient:
         self.T = theta + m.mesh.reference_temperature()[:, None]          # solvers.py:204-215
         self.timings = dict(prepare_s=t1 - t0, loop_s=t2 - t1, steps=n_t - 1, post_s=time.perf_counter() - t2)
 
-    def solve_ROM(self, *args, **kwargs):
-        raise NotImplementedError("reduced-order solve (reference solvers.py:219-354) is outside the B200 hot path")
+    def solve_ROM(self, n_modes_u, n_modes_theta, history='full', eig_tol=1e-9):
+        """Newmark integration of the Galerkin-reduced model (reference solvers.py:219-354).
+
+        The bases (model.compute_ROB_u / compute_ROB_theta), the reduced matrices and the reduced load vectors are
+        computed on the GPU; the (n_q x n_q) time loop runs on the host exactly like the reference's
+        (solvers.py:273-297) and the histories are expanded with one GEMM per quantity.  history: 'full' like the
+        reference (arrays of shape (., n_t)), 'last', or an integer stride."""
+        m = self.model
+        t0 = time.perf_counter()
+        m.create_free_dofs_lists()
+        m.assemble_MDK()                                   # assemble_M, assemble_K, assemble_D (solvers.py:221-223)
+        m.compute_ROB_u(n_modes_u, tol=eig_tol)
+        m.compute_ROB_theta(n_modes_theta, tol=eig_tol)
+        m.compute_ROM_matrices()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        nu, nt, n_t, n = m.n_q_u, m.n_q_t, self.n_t, m.mesh.n_dofs
+        dev = m._phi_u_dev.device
+        Phi = torch.cat([m._phi_u_dev, m._phi_t_dev])       # [nu + nt, 4N], rows vanish outside their field's free DOFs
+
+        def interleave_rom(u3, th):                         # solvers.py:237-241 / 246-250: y and z are initialised
+            X = np.zeros(n)                                 # from the X components, as in the reference
+            X[::4] = np.asarray(u3)[::3]
+            X[1::4] = np.asarray(u3)[::3]
+            X[2::4] = np.asarray(u3)[::3]
+            X[3::4] = th
+            return torch.from_numpy(X).to(dev)
+
+        prev_q = (Phi @ interleave_rom(self.initial_U, self.initial_theta)).cpu().numpy()          # solvers.py:243-244
+        prev_qdot = (Phi @ interleave_rom(self.initial_Udot, self.initial_thetadot)).cpu().numpy()   # :252-253
+        prev_qdotdot = np.zeros(nu + nt)
+        self.q = np.zeros((nu + nt, n_t))
+        self.qdot = np.zeros((nu + nt, n_t))
+        self.qdotdot = np.zeros((nu + nt, n_t))
+        self.q[:, 0] = prev_q
+        self.qdot[:, 0] = prev_qdot
+        dt, gamma, beta = self.dt, self.gamma, self.beta
+        Kdyn = m.mat_Mrom + gamma * dt * m.mat_Drom + beta * dt ** 2 * m.mat_Krom                 # solvers.py:264-266
+        import scipy.linalg
+        lu = scipy.linalg.lu_factor(Kdyn)                   # the reference calls np.linalg.solve every step (:277)
+        it = range(1, n_t)
+        for i in (_tqdm(it) if self.progress else it):
+            From = m.rom_forces(i)                          # assemble_F(idx_t=i) + compute_ROM_forces (:269-270)
+            rhs = (From - m.mat_Drom @ (prev_qdot + (1 - gamma) * dt * prev_qdotdot)
+                   - m.mat_Krom @ (prev_q + dt * prev_qdot + 0.5 * dt ** 2 * (1 - 2 * beta) * prev_qdotdot))
+            new_qdotdot = scipy.linalg.lu_solve(lu, rhs)
+            new_qdot = prev_qdot + (1 - gamma) * dt * prev_qdotdot + gamma * dt * new_qdotdot
+            new_q = prev_q + dt * prev_qdot + 0.5 * dt ** 2 * ((1 - 2 * beta) * prev_qdotdot + 2 * beta * new_qdotdot)
+            self.q[:, i], self.qdot[:, i], self.qdotdot[:, i] = new_q, new_qdot, new_qdotdot
+            prev_q, prev_qdot, prev_qdotdot = new_q, new_qdot, new_qdotdot
+        t2 = time.perf_counter()
+        # expansion to the physical DOFs (solvers.py:299-326) and prescribed values (:328-341)
+        cols = (np.arange(n_t) if history == 'full' else np.array([n_t - 1]) if history == 'last'
+                else np.arange(0, n_t, int(history)))
+        self.kept_steps = cols
+        PhiT = Phi.T.contiguous()
+
+        def expand(q, with_dirichlet):
+            X = (PhiT @ torch.from_numpy(np.ascontiguousarray(q[:, cols])).to(dev)).cpu().numpy()
+            if with_dirichlet:
+                X[m._mask_host, :] = m._g_fill_host[m._mask_host][:, None]
+            return X
+
+        self.X, self.Xdot, self.Xdotdot = expand(self.q, True), expand(self.qdot, False), expand(self.qdotdot, False)
+        n_nodes = m.mesh.n_nodes
+        self.U, theta = _deinterleave(self.X, n_nodes)
+        self.Udot, self.Tdot = _deinterleave(self.Xdot, n_nodes)
+        self.Udotdot, self.Tdotdot = _deinterleave(self.Xdotdot, n_nodes)
+        self.T = theta + m.mesh.reference_temperature()[:, None]             # solvers.py:343-354
+        self.timings = dict(prepare_s=t1 - t0, loop_s=t2 - t1, steps=n_t - 1, post_s=time.perf_counter() - t2)
 
     def solve_ROM_nonparametric(self, *args, **kwargs):
         raise NotImplementedError("non-parametric UQ solve (reference solvers.py:356-668) is outside the B200 hot path")

@@ -36,8 +36,8 @@ from dataclasses import dataclass
 
 import torch
 
-ITEMS_PER_CTA = 256          # = ASM_THREADS of tefem_assemble.cu
-ELEM_BUDGET_PER_CTA = 310    # bound on the sum of node degrees per tile (>= staged elements; ~246 on Kuhn meshes)
+ITEMS_PER_CTA = 512          # blocks per tile = two passes of the 256 threads of tefem_assemble.cu (B200 sweep, profiles/README.md)
+ELEM_BUDGET_PER_CTA = 620    # bound on the sum of node degrees per tile (>= staged elements; ~480 on Kuhn meshes)
 MAX_CHUNK = 8                # lists longer than 2 * MAX_CHUNK are split into chunks of <= MAX_CHUNK
 ITEM_SORT_WINDOW = 1         # > 1: items ordered longest-first inside windows of this many consecutive items (measured:
                              # helps the K-only launch by <= 12 %, scatters the 29 plane stores of M + D + K: off)
@@ -45,7 +45,7 @@ MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
 # True: the pieces of split blocks come first in a tile's item list and every block has one item in block order behind
 # them (see build_schedule); False: pieces inline + split lists.  TEFEM_PIECES_FIRST=0/1 overrides (A/B measurements).
-PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "0") == "1"
+PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "1") == "1"
 HDR_STRIDE = 12
 H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)
 

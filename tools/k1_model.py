@@ -96,6 +96,29 @@ def model(S, rec_stride=13, with_d=False, skip_equal_ab=False, tiles=None):
     return dict(wavefronts=tot_w, ideal=tot_ideal / 16.0, lane_steps=lane_steps, warp_steps=warp_steps, blocks=n_blocks)
 
 
+def model_phase1(S, rec_stride=13, tiles=None):
+    """Shared-memory wavefronts of phase 1 (thread le -> staged element le): 12 coordinate loads gathered by tile-local
+    node (xyz[3 * node + c]) and rec_stride record stores at le * rec_stride + k."""
+    H = S.cta_hdr.numpy().astype(np.int64)
+    cn8 = S.cta_conn8.numpy().astype(np.int64) & 0xFFFFFFFF
+    tot = staged = 0
+    for c in (range(S.n_cta) if tiles is None else tiles):
+        n_el, o_el = H[c, 1], H[c, 6]
+        npad = -(-n_el // 16) * 16
+        act = np.arange(npad) < n_el
+        w = np.zeros(npad, dtype=np.int64)
+        w[:n_el] = cn8[o_el:o_el + n_el]
+        le = np.arange(npad)
+        for a in range(4):
+            node = (w >> (8 * a)) & 0xff
+            for cc in range(3):
+                tot += int(_max_bank_load((3 * node + cc).reshape(-1, 16), act.reshape(-1, 16)).sum())
+        for k in range(rec_stride):
+            tot += int(_max_bank_load((le * rec_stride + k).reshape(-1, 16), act.reshape(-1, 16)).sum())
+        staged += n_el
+    return dict(wavefronts=tot, staged=staged)
+
+
 if __name__ == "__main__":
     cells = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     variants = sys.argv[2:] or ["256,310,8"]
@@ -109,6 +132,12 @@ if __name__ == "__main__":
             kw["pieces_first"] = bool(f[3])
         S = build_schedule(conn, N, **kw)
         staged = int(S.cta_hdr[:, 1].sum())
+        tiles = range(S.n_cta // 2, min(S.n_cta, S.n_cta // 2 + 40))
+        for rs in (13, 17):
+            r1 = model_phase1(S, rs, tiles)
+            nb = sum(int((S.cta_hdr[c + 1, 10] if c + 1 < S.n_cta else S.n_blocks) - S.cta_hdr[c, 10]) for c in tiles)
+            print(f"{v:14s} phase 1 (record stride {rs}): {r1['wavefronts'] / (nb / 2.5):.2f} wavefronts/elem, "
+                  f"{r1['wavefronts'] / r1['staged']:.2f} per staged element, staged/elem={r1['staged'] / (nb / 2.5):.2f}", flush=True)
         for with_d in (False, True):
             for skip in (False, True):
                 # a sample of tiles from the middle of the mesh (interior rows: 15 blocks per row = 2.5 per element)

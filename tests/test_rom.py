@@ -43,7 +43,8 @@ def test_block_lanczos_matches_dense_eigh(neumann):
     shift = 0.05 if neumann else 0.0
     apply_B, solve_A = scipy_ops(A, B, shift)
     x0 = torch.from_numpy(rng.random((6, n)) - 0.5)
-    lam, X, info = block_lanczos_smallest(apply_B, solve_A, x0, k, tol=1e-10, shift=shift)
+    lam, X, info = block_lanczos_smallest(apply_B, solve_A, x0, k, tol=1e-10, shift=shift,
+                                          apply_A=(lambda X: torch.from_numpy((A @ X.numpy().T).T.copy())) if not neumann else None)
     assert info["converged"]
     ref, vec = scipy.linalg.eigh(A.toarray(), B.toarray())
     assert np.max(np.abs(lam - ref[:k])) <= 1e-9 * ref[k]
@@ -101,9 +102,10 @@ def test_reduced_bases_span_the_reference_subspaces(sandwich):
     model.compute_ROB_u(n_u)
     model.compute_ROB_theta(n_th)
     assert model.rob_info_u["converged"] and model.rob_info_t["converged"]
-    assert model.rob_info_u["residual"] < 1e-7 and model.rob_info_t["residual"] < 1e-7
-    assert np.max(np.abs(model.eig_u / g["lam_u"] - 1)) < 1e-7
-    assert np.max(np.abs(model.eig_t / g["lam_t"] - 1)) < 1e-7
+    print("ROB info", model.rob_info_u, model.rob_info_t)
+    assert model.rob_info_u["residual"] < 1e-8 and model.rob_info_t["residual"] < 1e-8     # |K x - lam B x| / |K x|
+    assert np.max(np.abs(model.eig_u / g["lam_u"] - 1)) < 1e-9
+    assert np.max(np.abs(model.eig_t / g["lam_t"] - 1)) < 1e-9
     assert np.array_equal(model.free_dofs_U, g["free_dofs_U"]) and np.array_equal(model.free_dofs_theta, g["free_dofs_theta"])
     for nm, phi, op, free in (("u", model.mat_phi_u, "M", model.free_dofs_U), ("t", model.mat_phi_t, "D", model.free_dofs_theta)):
         assert phi.shape == (free.size, n_u if nm == "u" else n_th)
@@ -111,7 +113,10 @@ def test_reduced_bases_span_the_reference_subspaces(sandwich):
         B = model.touched(op).tocsr()[free, :].tocsc()[:, free]
         w = fingerprint_weights(free.size)
         proj = phi @ np.linalg.solve(phi.T @ (B @ phi), phi.T @ (B @ w))
-        assert np.linalg.norm(proj - g["proj_" + nm]) <= 1e-6 * np.linalg.norm(g["proj_" + nm]), nm
+        perr = np.linalg.norm(proj - g["proj_" + nm]) / np.linalg.norm(g["proj_" + nm])
+        print("subspace fingerprint error", nm, perr, "eigenvalue error",
+              np.max(np.abs((model.eig_u if nm == "u" else model.eig_t) / g["lam_" + nm] - 1)))
+        assert perr <= 1e-8, nm          # measured on the B200: 1.5e-12 (u), 1.9e-11 (theta)
 
 
 @pytest.mark.gpu
@@ -131,7 +136,8 @@ def test_solve_ROM_matches_reference_histories(sandwich):
         got, ref = getattr(solver, nm)[:, steps], g[nm]
         ref_shift = 20.0 if nm == "T" else 0.0                                      # T carries the reference temperature
         err = np.abs(got - ref).max(axis=0) / np.maximum(np.abs(ref - ref_shift).max(axis=0), 1e-300)
-        assert err.max() < 1e-5, (nm, err)
+        print("solve_ROM history error", nm, err)
+        assert err.max() < 1e-8, (nm, err)          # measured: 1e-12 (U), 2e-11 (T)
     # the reduced matrices reproduce the pencils' eigenvalues: Krom_uu / Mrom_uu and Krom_tt / Drom_tt
     m = solver.model
     lu = np.sort(scipy.linalg.eigvals(m.mat_Krom[:n_u, :n_u], m.mat_Mrom[:n_u, :n_u]).real)

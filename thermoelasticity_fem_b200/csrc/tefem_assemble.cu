@@ -141,6 +141,7 @@ TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta
     typename T::Geom g;
     g.clear();
     const uint32_t s = inc_word & 0xffffu, t = s + (uint32_t)meta_len(meta);
+#pragma unroll 2
     for (uint32_t k = s; k < t; ++k) {
         const uint32_t w = inc_s[k];
         block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(g, recs + (size_t)(w >> 4) * T::REC, (w >> 2) & 3, w & 3, W4, S, NN);
@@ -302,7 +303,7 @@ static int upload_quad() {
 #endif
 constexpr int ASM_THREADS = ASM_THREADS_N;
 #ifndef ASM_MIN_CTAS
-#define ASM_MIN_CTAS 3
+#define ASM_MIN_CTAS 2   // the default 512-block tiles leave room for two CTAs per SM (shared memory): no 80-register cap
 #endif
 
 // ---- TMA bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------

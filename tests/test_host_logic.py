@@ -116,6 +116,35 @@ def test_no_cpu_fallback_without_gpu():
         Model(mesh).assemble_K()
 
 
+def test_reduced_order_api_order_of_calls_and_no_fallback():
+    """compute_ROB_* mirror the reference's preconditions (model.py:342,354: DOF lists and assembled matrices first) and,
+    like every numerical entry point, have no CPU path."""
+    import torch
+    from thermoelasticity_fem_b200 import Mesh, Model, LinearThermoElastic, LinearTransient
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(2, 2, 2)
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    m = LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=750., alpha=4e-6, T0=20.)
+    mesh.set_materials({1: m, 2: m, 3: m})
+    mesh.make_elements()
+    model = Model(mesh, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)]}, dict_dirichlet_theta={4: 0.})
+    assert model.mat_phi_u is None and model.mat_phi_t is None and model.mat_Mrom is None and model.vec_From is None
+    with pytest.raises(RuntimeError, match="create_free_dofs_lists"):
+        model.compute_ROB_u(3)
+    with pytest.raises(RuntimeError, match="assemble_F"):
+        model.compute_ROM_forces()
+    if not torch.cuda.is_available():
+        model.create_free_dofs_lists()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model.compute_ROB_theta(3)
+        N = mesh.n_nodes
+        solver = LinearTransient(model, np.zeros(3 * N), np.zeros(3 * N), np.zeros(N), np.zeros(N), 1.0, 5)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            solver.solve_ROM(2, 2)
+        with pytest.raises(NotImplementedError):
+            solver.solve_ROM_nonparametric(2, 2, {}, 1, [], [])
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "thermoelasticity_fem_b200")
     for fn in os.listdir(pkg):

@@ -70,7 +70,44 @@ def test_block_lanczos_needs_enough_vectors():
         block_lanczos_smallest(apply_B, solve_A, x0, 10, max_vectors=4)
 
 
+def test_oracle_reduced_order_restatement_matches_reference_fixture(sandwich):
+    """Pins oracle.reduced_order_transient (numpy / scipy restatement of model.py:341-440 + solvers.py:219-354) to the
+    outputs of the reference's own solve_ROM: eigenvalues, subspaces, histories."""
+    from oracle import tefem_oracle as orc
+    g = golden("sandwich_rom3.npz")
+    pts, blocks, groups = sandwich
+    m = orc.Material(*MAT2)
+    t_end, n_t = 1800e0, 1000
+    vec_t = np.linspace(0., t_end, n_t)
+    arr = np.zeros((3, n_t))
+    arr[0, :] = np.sin(2 * np.pi * vec_t / 900.) * -1e9
+    n_u, n_th = [int(v) for v in g["n_modes"]]
+    steps = [int(v) for v in g["steps"]]
+    r = orc.reduced_order_transient(pts, groups, {1: m, 2: m, 3: m}, {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
+                                    {4: 0., 5: 0.}, dict(surface={5: arr}), 0.2, 0.2, t_end, n_t, n_u, n_th, keep=steps)
+    assert np.array_equal(r["maps"]["free_dofs_U"], g["free_dofs_U"]) and np.array_equal(r["maps"]["free_dofs_theta"], g["free_dofs_theta"])
+    assert np.max(np.abs(r["lam_u"] / g["lam_u"] - 1)) < 1e-9 and np.max(np.abs(r["lam_t"] / g["lam_t"] - 1)) < 1e-9
+    for nm, phi, op, free in (("u", r["phi_u"], "M", g["free_dofs_U"]), ("t", r["phi_t"], "D", g["free_dofs_theta"])):
+        B = r["ops"][op].tocsr()[free, :].tocsc()[:, free]
+        w = fingerprint_weights(free.size)
+        proj = phi @ np.linalg.solve(phi.T @ (B @ phi), phi.T @ (B @ w))
+        assert np.linalg.norm(proj - g["proj_" + nm]) <= 1e-8 * np.linalg.norm(g["proj_" + nm]), nm
+    N = pts.shape[0]
+    for X, U_ref, T_ref, shift in ((r["X"], g["U"], g["T"], 20.0), (r["Xdot"], g["Udot"], g["Tdot"], 0.0)):
+        U = np.zeros((3 * N, len(steps)))
+        for c in range(3):
+            U[c::3] = X[c::4]
+        T = X[3::4] + shift                                                         # reference temperature: T0 = 20 everywhere
+        assert np.abs(U - U_ref).max() <= 1e-8 * np.abs(U_ref).max()
+        assert np.abs(T - T_ref).max() <= 1e-8 * np.abs(T_ref - shift).max()
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------------------
+
+def fingerprint_weights(n):                         # = oracle/make_golden.py
+    k = np.arange(n, dtype=np.float64)
+    return 1.0 + np.mod(k * 0.6180339887498949, 1.0)
+
 
 def rom_model(sandwich):
     from thermoelasticity_fem_b200 import LinearThermoElastic, Mesh, Model
@@ -85,11 +122,6 @@ def rom_model(sandwich):
     model = Model(mesh, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
                   dict_dirichlet_theta={4: 0., 5: 0.}, dict_surface_forces={5: arr}, alpha_M=2e-1, alpha_K=2e-1)
     return mesh, model, t_end, n_t
-
-
-def fingerprint_weights(n):                         # = oracle/make_golden.py
-    k = np.arange(n, dtype=np.float64)
-    return 1.0 + np.mod(k * 0.6180339887498949, 1.0)
 
 
 @pytest.mark.gpu

@@ -298,12 +298,17 @@ static int upload_quad() {
     return TEFEM_OK;
 }
 
+// Threads per CTA: 256 (default; the 512-block tiles of symbolic.py are two passes).  The pieces-first kernel is also
+// instantiated for 128 and 64 threads - more, smaller CTAs per SM, i.e. more independent barrier domains (a third of the
+// stall samples of the 256-thread kernel wait at one of the three barriers of a tile, profiles/README.md) - selected
+// with the environment variable TEFEM_ASM_THREADS (measurement knob; pair it with items_per_cta = 2 x threads).
+// 512 threads per SM in every case, so that no instantiation is capped below 128 registers.
 #ifndef ASM_THREADS_N
 #define ASM_THREADS_N 256
 #endif
 constexpr int ASM_THREADS = ASM_THREADS_N;
-#ifndef ASM_MIN_CTAS
-#define ASM_MIN_CTAS 2   // the default 512-block tiles leave room for two CTAs per SM (shared memory): no 80-register cap
+#ifndef ASM_THREADS_PER_SM
+#define ASM_THREADS_PER_SM 512
 #endif
 
 // ---- TMA bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------
@@ -379,8 +384,8 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
 // Shared memory: [element records][partial-sum slots][stage 0][stage 1][2 mbarriers][S, NN tables].
 // The quadrature tables are indexed by the per-incidence local node numbers: from shared memory (20 distinct
 // banks, broadcast) instead of constant memory, where a warp's divergent indices would be serialised.
-template <int OPS, int DUU, bool PF>
-__global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
+template <int OPS, int DUU, bool PF, int NT>
+__global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
                                                                   int part_doubles) {
     extern __shared__ __align__(128) double smem[];
     double* recs = smem;
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(con
         const int32_t* it_meta = reinterpret_cast<const int32_t*>(st + L.it_meta);
         const uint16_t* inc_s = reinterpret_cast<const uint16_t*>(st + L.inc);
         // phase 1: geometry records of the staged elements
-        for (int le = threadIdx.x; le < n_elems; le += ASM_THREADS) {
+        for (int le = threadIdx.x; le < n_elems; le += NT) {
             const double det = stage_element_local<T::WANT_D>(xyz, conn8[le], recs + (size_t)le * T::REC);
             if (!(det > 0.0)) {  // error path only: elements.py:207-210
                 const int32_t e = A.cta_elems[o_elems + le];
@@ -454,14 +459,14 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(con
 #pragma unroll 1
             for (int ph = (n_piece > 0 ? 0 : 1); ph < 2; ++ph) {
                 const int lo = ph ? n_piece : 0, hi = ph ? n_items : n_piece;
-                for (int it = lo + threadIdx.x; it < hi; it += ASM_THREADS)
+                for (int it = lo + threadIdx.x; it < hi; it += NT)
                     process_pf_item<OPS, DUU>(A, ph ? block0 + (it - lo) : -1, (uint32_t)it_inc[it], it_meta[it], recs, inc_s,
                                               partials, W4, tabS, tabNN);
                 if (ph == 0) __syncthreads();
             }
         } else {
             // phase 2: work items in block order
-            for (int it = threadIdx.x; it < n_items; it += ASM_THREADS)
+            for (int it = threadIdx.x; it < n_items; it += NT)
                 process_item<OPS, DUU>(A, block0, (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, W4, tabS, tabNN);
             // phase 3: blocks with several items (the diagonal blocks, material interfaces)
             const int n_split = hdr[H_NSPLIT];
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_CTAS) assemble_kernel(con
                 __syncthreads();
                 const int32_t* sp_block = reinterpret_cast<const int32_t*>(st + L.sp_block);
                 const int32_t* sp_meta = reinterpret_cast<const int32_t*>(st + L.sp_meta);
-                for (int q = threadIdx.x; q < n_split; q += ASM_THREADS)
+                for (int q = threadIdx.x; q < n_split; q += NT)
                     combine_split<OPS, DUU>(A, block0 + sp_block[q], sp_meta[q], partials);
             }
         }
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
 
-template <int OPS, int DUU, bool PF>
+template <int OPS, int DUU, bool PF, int NT>
 static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
     const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
     const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
@@ -507,25 +512,49 @@ static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStre
     static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU, PF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         int dev = 0;
         TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
         TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
     int per_sm = 0;
-    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU, PF>, ASM_THREADS, smem));
+    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU, PF, NT>, NT, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count * per_sm;
     if (grid > d.n_cta) grid = d.n_cta;
-    assemble_kernel<OPS, DUU, PF><<<grid, ASM_THREADS, smem, st>>>(A, d, rec_doubles, part_doubles);
+    assemble_kernel<OPS, DUU, PF, NT><<<grid, NT, smem, st>>>(A, d, rec_doubles, part_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
 
+// TEFEM_ASM_THREADS = 64 | 128 | 256 (read once per process)
+static int asm_threads() {
+    static int nt = 0;
+    if (nt == 0) {
+        const char* e = getenv("TEFEM_ASM_THREADS");
+        nt = e ? atoi(e) : ASM_THREADS;
+    }
+    return nt;
+}
+
 template <int OPS, int DUU>
 static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
-    return d.pieces_first ? launch_assemble_pf<OPS, DUU, true>(A, d, st) : launch_assemble_pf<OPS, DUU, false>(A, d, st);
+    const int nt = asm_threads();
+    if (!d.pieces_first) {
+        TEFEM_REQUIRE(nt == ASM_THREADS, "TEFEM_ASM_THREADS applies to the pieces-first item layout only");
+        return launch_assemble_pf<OPS, DUU, false, ASM_THREADS>(A, d, st);
+    }
+    switch (nt) {
+        case ASM_THREADS: return launch_assemble_pf<OPS, DUU, true, ASM_THREADS>(A, d, st);
+#if ASM_THREADS_N == 256
+        case 128: return launch_assemble_pf<OPS, DUU, true, 128>(A, d, st);
+        case 64: return launch_assemble_pf<OPS, DUU, true, 64>(A, d, st);
+#endif
+        default: break;
+    }
+    set_error("TEFEM_ASM_THREADS must be 64, 128 or 256");
+    return TEFEM_ERR_INVALID;
 }
 
 template <int OPS>

@@ -1,6 +1,8 @@
 """A/B of K1 item layouts on the GPU box: inline (split lists) vs pieces-first, same mesh, same chunks.
 Checks that the planes are BITWISE identical (same chunks => same summation order) and times both.
-usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first" ...]   (first variant = reference)"""
+usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first" ...]   (first variant = reference)
+Threads per CTA are a per-process knob of the library: TEFEM_ASM_THREADS=64|128 python tools/asm_ab.py 100 128,160,8,1 256,310,8,1
+(pair with items = 2 x threads; build variants: TEFEM_LIB=/path/to/lib.so)."""
 import os
 import sys
 

@@ -30,6 +30,7 @@
 #include "tefem_element.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace tefem {

@@ -28,6 +28,8 @@
 #include "tefem_comm.h"
 #include "tefem_precond.h"
 
+#include <stdlib.h>
+
 namespace tefem {
 
 // rc[8I + 0..3] = sum_i r_i ; rc[8I + 4..6] = sum_i d_i x r_u,i ; rc[8I + 7] = 0 over the nodes i of aggregate I
@@ -201,6 +203,13 @@ struct tefem_precond {
     int n_pre = 1, n_post = 1;                   // damped-Jacobi sweeps on level 1 before / after the level-2 correction
     double *rc = nullptr, *bc = nullptr, *xc = nullptr, *tc = nullptr, *r2 = nullptr, *x2 = nullptr;
     tefem_comm* comm = nullptr;
+    // TEFEM_PROFILE_PRECOND=1 (diagnostics, stderr at destroy): device time of the three parts of an application -
+    // restriction + all-reduce over the ranks + first sweep (includes waiting for the slowest rank), the level-1 / level-2
+    // cycle (replicated work), the prolongation.  Synchronises the stream after every application: not for timed runs.
+    bool profile = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double part_ms[3] = {0.0, 0.0, 0.0};
+    int64_t n_apply = 0;
 };
 
 static int64_t pc_align(int64_t n) { return (n + 15) / 16 * 16; }
@@ -238,11 +247,26 @@ extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t
     p->rc = w; w += a1; p->bc = w; w += a1; p->xc = w; w += a1; p->tc = w; w += a1;
     p->r2 = w; w += a2; p->x2 = w;
     p->comm = reinterpret_cast<tefem_comm*>(comm);
+    const char* pe = getenv("TEFEM_PROFILE_PRECOND");
+    if (pe && pe[0] == '1') {
+        p->profile = true;
+        for (int k = 0; k < 4; ++k) {
+            if (cudaEventCreate(&p->ev[k]) != cudaSuccess) { p->profile = false; break; }
+        }
+    }
     *out = p;
     return TEFEM_OK;
 }
 
 extern "C" int tefem_precond_destroy(tefem_precond* p) {
+    if (p && p->profile) {
+        if (p->n_apply > 0)
+            fprintf(stderr, "[tefem precond profile] %lld applications: restrict + all-reduce + first sweep %.4f ms, level-1/2 cycle %.4f ms, "
+                            "prolongation %.4f ms per application\n", (long long)p->n_apply, p->part_ms[0] / p->n_apply,
+                    p->part_ms[1] / p->n_apply, p->part_ms[2] / p->n_apply);
+        for (int k = 0; k < 4; ++k)
+            if (p->ev[k]) cudaEventDestroy(p->ev[k]);
+    }
     delete p;
     return TEFEM_OK;
 }
@@ -253,6 +277,7 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
     const int32_t np1 = 2 * p->n1, np2 = 2 * p->n2;           // pseudo nodes (4-DOF block rows) of levels 1 and 2
     const unsigned g1 = (unsigned)ceil_div(n1, 256), g2 = (unsigned)ceil_div(4 * (int64_t)np2, 256);
     const unsigned gr = (unsigned)ceil_div(32 * (int64_t)p->n1, 256);
+    if (p->profile) cudaEventRecord(p->ev[0], st);
     // level 0 -> 1: rc = P1^T r, summed over the ranks (levels 1 and 2 are replicated): the restriction writes
     // into this rank's peer buffer and the next kernel does all-reduce + D1^-1 + first smoothing step in one
     if (p->comm) {
@@ -270,6 +295,7 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
         coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();
     }
+    if (p->profile) cudaEventRecord(p->ev[1], st);
     // level 1 V-cycle on A1^ = D1^-1 A1 (bc = D1^-1 rc, x = wc bc so far = the first damped-Jacobi sweep from 0):
     // further pre-smoothing sweeps, correction from level 2, post-smoothing.  A sweep reads all of x, so it writes
     // into the other buffer: x' = x + wc (bc - A1^ x).
@@ -292,11 +318,22 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
         TEFEM_LAUNCH_CHECK();
         double* t = cur; cur = alt; alt = t;
     }
+    if (p->profile) cudaEventRecord(p->ev[2], st);
     // level 1 -> 0
     if (p->n_rows > 0) {
         prolong_combine_kernel<<<(unsigned)ceil_div((int64_t)p->n_rows, 256), 256, 0, st>>>(p->n_rows, p->node_agg, p->node_off,
                                                                                             p->omega, r, cur, z);
         TEFEM_LAUNCH_CHECK();
+    }
+    if (p->profile) {
+        cudaEventRecord(p->ev[3], st);
+        if (cudaEventSynchronize(p->ev[3]) == cudaSuccess) {
+            for (int k = 0; k < 3; ++k) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]) == cudaSuccess) p->part_ms[k] += ms;
+            }
+            p->n_apply += 1;
+        }
     }
     return TEFEM_OK;
 }

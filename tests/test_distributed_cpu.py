@@ -157,7 +157,7 @@ def test_dirichlet_and_load_restriction_to_local_nodes():
     sys.path.insert(0, ROOT)
     from thermoelasticity_fem_b200.distributed import dirichlet_node_data, surface_node_weights
     from thermoelasticity_fem_b200.partition import localize, slab_ranges
-    from thermoelasticity_fem_b200.synthetic import kuhn_box, kuhn_face_tris, kuhn_node_coords, kuhn_slab_tets
+    from thermoelasticity_fem_b200.synthetic import kuhn_box, kuhn_node_coords, kuhn_slab_tets
     from oracle import tefem_oracle as orc
     n = 5
     pts, tets, tris, nodes = kuhn_box(n, n, n, 1.0, 1.0, 1.0, n_layers=1)

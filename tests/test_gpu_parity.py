@@ -192,7 +192,7 @@ def test_negative_jacobian_raises():
 
 def test_spmv_and_system_against_scipy(sandwich_mesh2):
     import torch
-    from thermoelasticity_fem_b200 import Model, layout
+    from thermoelasticity_fem_b200 import Model
     model = Model(sandwich_mesh2, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
                   dict_dirichlet_theta={4: 0., 5: 0.}, alpha_M=0.2, alpha_K=0.2)
     model.create_free_dofs_lists()

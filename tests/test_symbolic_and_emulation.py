@@ -311,3 +311,24 @@ def test_pieces_first_layout_is_bitwise_the_inline_layout(sandwich, emu, mesh_ki
                 for nm in ops:
                     assert np.array_equal(v0[nm], v1[nm]), (kw, ops, nm)
                 assert np.array_equal(bad0, bad1)
+
+
+def test_bank_conflict_model_of_the_incidence_loop():
+    """tools/k1_model.py (the CPU model behind the K1 analysis in profiles/README.md): every incidence of the schedule is
+    replayed exactly once, the conflict-free bound is loads / 16 and the modelled wavefronts lie between that bound and one
+    wavefront per active lane."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import k1_model
+    pts, tets, tris, nodes = kuhn_box(6, 5, 4)
+    conn = np.concatenate(list(tets.values()))
+    for pf in (False, True):
+        S = build_schedule(torch.from_numpy(conn), pts.shape[0], pieces_first=pf)
+        for with_d, loads in ((False, 7), (True, 10)):
+            r = k1_model.model(S, 17 if with_d else 13, with_d)
+            assert r["lane_steps"] == 16 * conn.shape[0]                    # one lane-step per (element, a, b)
+            assert abs(r["ideal"] - loads * r["lane_steps"] / 16.0) < 1e-9
+            assert r["ideal"] <= r["wavefronts"] <= loads * r["lane_steps"]
+            skip = k1_model.model(S, 17 if with_d else 13, with_d, skip_equal_ab=True)
+            assert abs(skip["ideal"] - (loads * r["lane_steps"] - 3 * 4 * conn.shape[0]) / 16.0) < 1e-9    # a == b: 4 per element
+        p1 = k1_model.model_phase1(S)
+        assert p1["staged"] == int(S.cta_hdr[:, 1].sum()) and p1["wavefronts"] >= 25 * p1["staged"] / 16.0

@@ -10,7 +10,6 @@ so reference scripts run unchanged.
 ``solve_ROM`` (``solvers.py:219-354``) runs on reduced-order bases computed on the GPU (``rom.py``); the
 non-parametric UQ solver ``solve_ROM_nonparametric`` (``solvers.py:356-668``) is out of scope.
 """
-import os
 import time
 
 import numpy as np

@@ -137,7 +137,7 @@ TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTr
 // constants applied once.
 template <int OPS, int DUU>
 TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta, const double* recs, const uint16_t* inc_s,
-                          double W4, const double* S, const double* NN, typename AsmTraits<OPS, DUU>::Acc& acc) {
+                          double W4, const QuadS& S, const double* NN, typename AsmTraits<OPS, DUU>::Acc& acc) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Geom g;
     g.clear();
@@ -154,7 +154,7 @@ TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta
 // consecutive addresses of every plane) or park the values of a piece of a split block in its shared-memory slot.
 template <int OPS, int DUU>
 TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_word, int32_t meta, const double* recs,
-                           const uint16_t* inc_s, double* slots, double W4, const double* S, const double* NN) {
+                           const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const double* NN) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Acc acc;
     gather_item<OPS, DUU>(A, inc_word, meta, recs, inc_s, W4, S, NN, acc);
@@ -169,7 +169,7 @@ TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_w
 // at its block-order position: the plane stores of a warp are contiguous.
 template <int OPS, int DUU>
 TEFEM_HD void process_pf_item(const AssembleArgs& A, int32_t p, uint32_t inc_word, int32_t meta, const double* recs,
-                              const uint16_t* inc_s, double* slots, double W4, const double* S, const double* NN) {
+                              const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const double* NN) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Acc acc;
     const int slot = meta_slot(meta);
@@ -196,7 +196,7 @@ TEFEM_HD void combine_split(const AssembleArgs& A, int32_t p, int32_t meta, cons
 }
 
 // Dense element matrices of one element (parity path; elements.py:220-286).
-TEFEM_HD void element_dense(const double* rec, const double* mat, double W4, const double* S, const double* NN, int kinds,
+TEFEM_HD void element_dense(const double* rec, const double* mat, double W4, const QuadS& S, const double* NN, int kinds,
                             double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut, double* Ktt) {
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
@@ -394,10 +394,15 @@ __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(c
     const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
     char* stage0 = reinterpret_cast<char*>(partials + part_doubles);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
-    double* tabS = reinterpret_cast<double*>(bars + 2);
-    double* tabNN = tabS + 4;
-    if (threadIdx.x < 4) tabS[threadIdx.x] = c_quad.S[threadIdx.x];
+    double* tabS_s = reinterpret_cast<double*>(bars + 2);
+    double* tabNN = tabS_s + 4;
+    if (threadIdx.x < 4) tabS_s[threadIdx.x] = c_quad.S[threadIdx.x];
     if (threadIdx.x < 16) tabNN[threadIdx.x] = c_quad.NN[threadIdx.x];
+#ifdef ASM_S_SELECT
+    const QuadS tabS = make_quad_s(c_quad.S);
+#else
+    const QuadS tabS = make_quad_s(tabS_s);
+#endif
     typedef AsmTraits<OPS, DUU> T;
     const int G = gridDim.x;
     if (threadIdx.x == 0) {
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
         if (det < 0.0) atomicMin(bad_elem, (int32_t)e);
         else atomicMin(bad_elem + 1, (int32_t)e);
     }
-    element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], c_quad.W4, c_quad.S, c_quad.NN, kinds,
+    element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], c_quad.W4, make_quad_s(c_quad.S), c_quad.NN, kinds,
                   Muu ? Muu + t * 144 : nullptr, Dtu ? Dtu + t * 48 : nullptr, Dtt ? Dtt + t * 16 : nullptr,
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
@@ -688,17 +693,17 @@ static int emu_run(const AssembleArgs& A, const TileDims& d, int n_mat) {
             if (d.pieces_first) {
                 if (it < n_piece) {   // piece k parks in slot k
                     if (slot != it || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
-                    process_pf_item<OPS, DUU>(A, -1, iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
+                    process_pf_item<OPS, DUU>(A, -1, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), q.NN);
                 } else {              // block items: all pieces were processed before (the kernel synchronises)
                     const int b = it - n_piece;
                     if ((int)(iw >> 16) != b) return TEFEM_ERR_INVALID;
                     if (slot < 0 ? s + meta_len(meta) > h[H_NINC] : slot + meta_len(meta) > n_piece) return TEFEM_ERR_INVALID;
-                    process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
+                    process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), q.NN);
                 }
                 continue;
             }
             if (slot >= d.max_slots || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
-            process_item<OPS, DUU>(A, h[H_BLOCK0], iw, meta, recs.data(), inc_s, partials.data(), q.W4, q.S, q.NN);
+            process_item<OPS, DUU>(A, h[H_BLOCK0], iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), q.NN);
         }
         for (int k = 0; k < h[H_NSPLIT]; ++k) {
             const int32_t sm = A.split_meta[h[H_OSPLIT] + k];
@@ -751,7 +756,7 @@ extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* c
             int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
             if (e < *slot) *slot = (int32_t)e;
         }
-        element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], q.W4, q.S, q.NN, kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
+        element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], q.W4, make_quad_s(q.S), q.NN, kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
                       Dtt ? Dtt + e * 16 : nullptr, Kuu ? Kuu + e * 144 : nullptr, Kut ? Kut + e * 48 : nullptr,
                       Ktt ? Ktt + e * 16 : nullptr);
     }

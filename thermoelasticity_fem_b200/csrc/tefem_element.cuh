@@ -74,6 +74,29 @@ TEFEM_HD double rec_gt(const double* rec, int c, int b) {
     return b == 0 ? rec[REC_GT0 + c] : rec[REC_G + 3 * (c + 1) + (b - 1)];
 }
 
+// S_a = sum_g w N_a(g) of the four local nodes.  Default: an indexed load from the table (shared memory in K1: one
+// conflict-free wavefront per half-warp on the pipe that bounds the kernel, profiles/README.md).  -DASM_S_SELECT
+// (measurement variant, same values): the four values are held by value and selected with compares; ptxas re-reads them
+// from the constant bank inside the loop (LDCU / LDC), whether that beats the shared-memory load is not measured yet.
+struct QuadS {
+#ifdef ASM_S_SELECT
+    double s0, s1, s2, s3;
+    TEFEM_HD double at(int a) const { return a == 0 ? s0 : (a == 1 ? s1 : (a == 2 ? s2 : s3)); }
+#else
+    const double* s;
+    TEFEM_HD double at(int a) const { return s[a]; }
+#endif
+};
+TEFEM_HD QuadS make_quad_s(const double* S) {
+    QuadS q;
+#ifdef ASM_S_SELECT
+    q.s0 = S[0]; q.s1 = S[1]; q.s2 = S[2]; q.s3 = S[3];
+#else
+    q.s = S;
+#endif
+    return q;
+}
+
 // Values of one node-pair block.  WITH_K/... select which parts are live so that the compiler drops the dead
 // ones per kernel instantiation.
 template <bool WITH_K, bool WITH_M, bool WITH_D>
@@ -140,10 +163,10 @@ struct GeomAcc {
 // acc += geometric contribution of block (a, b) of the element whose record is `rec`.
 template <bool WITH_K, bool WITH_M, bool WITH_D>
 TEFEM_HD void block_accumulate(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, const double* __restrict__ rec, int a, int b,
-                               double W4, const double* __restrict__ S, const double* __restrict__ NN) {
+                               double W4, const QuadS& S, const double* __restrict__ NN) {
     const double det = rec[REC_DET];
     double ds = 0.0;
-    if (WITH_K || WITH_D) ds = det * S[a];
+    if (WITH_K || WITH_D) ds = det * S.at(a);
     if (WITH_K) {
         const double ga0 = rec[REC_G + 3 * a], ga1 = rec[REC_G + 3 * a + 1], ga2 = rec[REC_G + 3 * a + 2];
         double gb0 = ga0, gb1 = ga1, gb2 = ga2;

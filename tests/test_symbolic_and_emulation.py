@@ -332,3 +332,26 @@ def test_bank_conflict_model_of_the_incidence_loop():
             assert abs(skip["ideal"] - (loads * r["lane_steps"] - 3 * 4 * conn.shape[0]) / 16.0) < 1e-9    # a == b: 4 per element
         p1 = k1_model.model_phase1(S)
         assert p1["staged"] == int(S.cta_hdr[:, 1].sum()) and p1["wavefronts"] >= 25 * p1["staged"] / 16.0
+
+
+@pytest.mark.parametrize("pf", [False, True])
+def test_edge_meshes_single_tet_and_fan(emu, pf):
+    """A mesh of one tetrahedron (no split block at all) and a fan of 40 tets around one edge (two nodes of valence 40:
+    long lists cut into many pieces, also with a tiny chunk length) in both item layouts."""
+    m = orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.)
+    single = (np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.]]), {1: np.array([[0, 1, 2, 3]])})
+    n = 40
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    ring = np.stack([np.cos(ang), np.sin(ang), np.zeros(n)], 1)
+    fan = (np.vstack([[0, 0, -1.], [0, 0, 1.], ring]), {1: np.array([[0, 2 + k, 2 + (k + 1) % n, 1] for k in range(n)])})
+    for pts, tg in (single, fan):
+        conn, mat_id, rows = orc.element_table(tg, {1: m})
+        ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.2)
+        for chunk in (8, 2):
+            S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=pf, max_chunk=chunk)
+            vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.2)
+            assert bad.min() == 2 ** 31 - 1
+            for nm, pm in (("K", layout.plane_map_K()), ("D", layout.plane_map_D(0.1, 0.2))):
+                A = planes_to_csc(vals[nm], pm, S, 4 * pts.shape[0])
+                parity.check_pattern(A, None, ops[nm])
+                assert parity.scaled_error(A, ops[nm]) < parity.VALUE_TOL

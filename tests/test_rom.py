@@ -70,6 +70,31 @@ def test_block_lanczos_needs_enough_vectors():
         block_lanczos_smallest(apply_B, solve_A, x0, 10, max_vectors=4)
 
 
+def test_reduced_newmark_loop_against_the_reference_recurrence():
+    """solvers.reduced_newmark (host loop of solve_ROM) against the recurrence written exactly as reference solvers.py:268-291."""
+    from thermoelasticity_fem_b200.solvers import reduced_newmark
+    rng = np.random.default_rng(11)
+    nq, n_t, dt, gamma, beta = 7, 40, 0.37, 0.5, 0.25
+    B = rng.standard_normal((nq, nq))
+    Mr, Kr = B @ B.T + nq * np.eye(nq), rng.standard_normal((nq, nq)) + 5 * nq * np.eye(nq)
+    Dr = 0.2 * Mr + 0.1 * Kr + rng.standard_normal((nq, nq))              # non-symmetric like the coupled Drom
+    F = rng.standard_normal((nq, n_t))
+    q0, v0 = rng.standard_normal(nq), rng.standard_normal(nq)
+    q, qd, qdd = reduced_newmark(Mr, Dr, Kr, lambda i: F[:, i], q0, v0, dt, gamma, beta, n_t)
+    Kdyn = Mr + gamma * dt * Dr + beta * dt ** 2 * Kr
+    prev_q, prev_qdot, prev_qdotdot = q0.copy(), v0.copy(), np.zeros(nq)
+    for i in range(1, n_t):
+        rhs = (F[:, i] - Dr @ (prev_qdot + (1 - gamma) * dt * prev_qdotdot)
+               - Kr @ (prev_q + dt * prev_qdot + 0.5 * (dt ** 2) * (1 - 2 * beta) * prev_qdotdot))
+        new_qdotdot = np.linalg.solve(Kdyn, rhs)
+        new_qdot = prev_qdot + (1 - gamma) * dt * prev_qdotdot + gamma * dt * new_qdotdot
+        new_q = prev_q + dt * prev_qdot + 0.5 * (dt ** 2) * ((1 - 2 * beta) * prev_qdotdot + 2 * beta * new_qdotdot)
+        for got, want in ((q[:, i], new_q), (qd[:, i], new_qdot), (qdd[:, i], new_qdotdot)):
+            assert np.abs(got - want).max() <= 1e-11 * max(np.abs(want).max(), 1.0)
+        prev_q, prev_qdot, prev_qdotdot = new_q, new_qdot, new_qdotdot
+    assert np.array_equal(q[:, 0], q0) and np.array_equal(qd[:, 0], v0) and not qdd[:, 0].any()
+
+
 def test_oracle_reduced_order_restatement_matches_reference_fixture(sandwich):
     """Pins oracle.reduced_order_transient (numpy / scipy restatement of model.py:341-440 + solvers.py:219-354) to the
     outputs of the reference's own solve_ROM: eigenvalues, subspaces, histories."""

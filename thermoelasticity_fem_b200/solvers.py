@@ -37,6 +37,27 @@ def _deinterleave(X, n_nodes):
     return U, X[3::4]
 
 
+def reduced_newmark(Mr, Dr, Kr, forces, q_init, v_init, dt, gamma, beta, n_t, steps=None):
+    """Newmark integration (acceleration form, zero initial acceleration) of the dense reduced system
+    Mr q'' + Dr q' + Kr q = forces(i), i = 1 .. n_t - 1 (reference solvers.py:255-297).  Host-side: the matrices are
+    (n_q x n_q) with n_q ~ 10 - 100; Mr + gamma dt Dr + beta dt^2 Kr is factorised once (the reference calls
+    np.linalg.solve every step).  Returns q, q', q'' of shape (n_q, n_t)."""
+    import scipy.linalg
+    nq = Mr.shape[0]
+    Q = np.zeros((3, nq, n_t))
+    Q[0, :, 0], Q[1, :, 0] = q_init, v_init
+    lu = scipy.linalg.lu_factor(Mr + gamma * dt * Dr + beta * dt ** 2 * Kr)                  # solvers.py:264-266
+    for i in (range(1, n_t) if steps is None else steps):
+        q0, q1, q2 = Q[0, :, i - 1], Q[1, :, i - 1], Q[2, :, i - 1]
+        v_pred = q1 + (1 - gamma) * dt * q2                                                  # predictors, solvers.py:271-275
+        x_pred = q0 + dt * q1 + 0.5 * dt ** 2 * (1 - 2 * beta) * q2
+        acc = scipy.linalg.lu_solve(lu, forces(i) - Dr @ v_pred - Kr @ x_pred)               # solvers.py:269-277
+        Q[2, :, i] = acc
+        Q[1, :, i] = v_pred + gamma * dt * acc                                               # solvers.py:278-283
+        Q[0, :, i] = x_pred + beta * dt ** 2 * acc
+    return Q[0], Q[1], Q[2]
+
+
 class _SystemSolve:
     """Shared by both solvers: forms the eliminated, block-Jacobi-scaled system and solves with it."""
 
@@ -299,28 +320,12 @@ class LinearTransient:
             X[3::4] = th
             return torch.from_numpy(X).to(dev)
 
-        prev_q = (Phi @ interleave_rom(self.initial_U, self.initial_theta)).cpu().numpy()          # solvers.py:243-244
-        prev_qdot = (Phi @ interleave_rom(self.initial_Udot, self.initial_thetadot)).cpu().numpy()   # :252-253
-        prev_qdotdot = np.zeros(nu + nt)
-        self.q = np.zeros((nu + nt, n_t))
-        self.qdot = np.zeros((nu + nt, n_t))
-        self.qdotdot = np.zeros((nu + nt, n_t))
-        self.q[:, 0] = prev_q
-        self.qdot[:, 0] = prev_qdot
-        dt, gamma, beta = self.dt, self.gamma, self.beta
-        Kdyn = m.mat_Mrom + gamma * dt * m.mat_Drom + beta * dt ** 2 * m.mat_Krom                 # solvers.py:264-266
-        import scipy.linalg
-        lu = scipy.linalg.lu_factor(Kdyn)                   # the reference calls np.linalg.solve every step (:277)
+        q_init = (Phi @ interleave_rom(self.initial_U, self.initial_theta)).cpu().numpy()          # solvers.py:243-244
+        v_init = (Phi @ interleave_rom(self.initial_Udot, self.initial_thetadot)).cpu().numpy()    # solvers.py:252-253
         it = range(1, n_t)
-        for i in (_tqdm(it) if self.progress else it):
-            From = m.rom_forces(i)                          # assemble_F(idx_t=i) + compute_ROM_forces (:269-270)
-            rhs = (From - m.mat_Drom @ (prev_qdot + (1 - gamma) * dt * prev_qdotdot)
-                   - m.mat_Krom @ (prev_q + dt * prev_qdot + 0.5 * dt ** 2 * (1 - 2 * beta) * prev_qdotdot))
-            new_qdotdot = scipy.linalg.lu_solve(lu, rhs)
-            new_qdot = prev_qdot + (1 - gamma) * dt * prev_qdotdot + gamma * dt * new_qdotdot
-            new_q = prev_q + dt * prev_qdot + 0.5 * dt ** 2 * ((1 - 2 * beta) * prev_qdotdot + 2 * beta * new_qdotdot)
-            self.q[:, i], self.qdot[:, i], self.qdotdot[:, i] = new_q, new_qdot, new_qdotdot
-            prev_q, prev_qdot, prev_qdotdot = new_q, new_qdot, new_qdotdot
+        self.q, self.qdot, self.qdotdot = reduced_newmark(m.mat_Mrom, m.mat_Drom, m.mat_Krom, m.rom_forces, q_init, v_init,
+                                                          self.dt, self.gamma, self.beta, n_t,
+                                                          steps=_tqdm(it) if self.progress else it)
         t2 = time.perf_counter()
         # expansion to the physical DOFs (solvers.py:299-326) and prescribed values (:328-341)
         cols = (np.arange(n_t) if history == 'full' else np.array([n_t - 1]) if history == 'last'

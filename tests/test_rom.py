@@ -217,3 +217,74 @@ def test_rom_forces_equal_projected_load_vector(sandwich):
         F = model.vec_F
         want = np.r_[model.mat_phi_u.T @ F[model.free_dofs_U], model.mat_phi_t.T @ F[model.free_dofs_theta]]
         assert np.max(np.abs(model.vec_From - want)) <= 1e-12 * np.abs(want).max()
+
+
+def test_solve_ROM_host_flow_with_stubbed_device_steps(monkeypatch):
+    """The host side of LinearTransient.solve_ROM (initial projection, reduced loop, expansion, prescribed values, reference
+    temperature, history option) with the device steps replaced by CPU stand-ins: bases = random vectors supported on the free
+    DOFs of their field, reduced matrices = their exact projections of random operators."""
+    from thermoelasticity_fem_b200 import Mesh, Model, LinearThermoElastic, LinearTransient
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(3, 2, 3)
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    mats = {1: LinearThermoElastic(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: LinearThermoElastic(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+            3: LinearThermoElastic(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    mesh.set_materials(mats)
+    mesh.make_elements()
+    model = Model(mesh, dict_dirichlet_U={4: [('x', 1e-3), ('y', 0.), ('z', 0.)]}, dict_dirichlet_theta={4: 2.5})
+    N, n = mesh.n_nodes, mesh.n_dofs
+    n_t, nu, nt = 9, 3, 2
+    rng = np.random.default_rng(2)
+
+    def fake_rob(field, k):
+        model.create_free_dofs_lists()
+        comp = np.arange(n) % 4
+        free = ((comp < 3) if field == "u" else (comp == 3)) & ~model._mask_host
+        return torch.from_numpy(rng.standard_normal((k, n)) * free)
+
+    def compute_u(k, tol=None):
+        model.n_q_u, model._phi_u_dev = k, fake_rob("u", k)
+
+    def compute_t(k, tol=None):
+        model.n_q_t, model._phi_t_dev = k, fake_rob("theta", k)
+
+    def matrices():
+        nq = model.n_q_u + model.n_q_t
+        B = rng.standard_normal((nq, nq))
+        model.mat_Mrom, model.mat_Krom = B @ B.T + nq * np.eye(nq), 3.0 * np.eye(nq) + 0.1 * rng.standard_normal((nq, nq))
+        model.mat_Drom = 0.2 * model.mat_Mrom
+
+    forces = rng.standard_normal((nu + nt, n_t))
+    monkeypatch.setattr(model, "assemble_MDK", lambda: None)
+    monkeypatch.setattr(model, "compute_ROB_u", compute_u)
+    monkeypatch.setattr(model, "compute_ROB_theta", compute_t)
+    monkeypatch.setattr(model, "compute_ROM_matrices", matrices)
+    monkeypatch.setattr(model, "rom_forces", lambda i: forces[:, i])
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    U0 = rng.standard_normal(3 * N)
+    th0 = rng.standard_normal(N)
+    solver = LinearTransient(model, U0, np.zeros(3 * N), th0, np.zeros(N), 2.0, n_t, progress=False)
+    solver.solve_ROM(nu, nt)
+    Phi = np.vstack([model._phi_u_dev.numpy(), model._phi_t_dev.numpy()])
+    X0 = np.zeros(n)
+    X0[0::4] = X0[1::4] = X0[2::4] = U0[::3]                                   # reference quirk, solvers.py:237-239
+    X0[3::4] = th0
+    assert np.allclose(solver.q[:, 0], Phi @ X0, rtol=1e-13, atol=1e-13)
+    assert solver.q.shape == (nu + nt, n_t) and solver.X.shape == (n, n_t) and solver.U.shape == (3 * N, n_t) and solver.T.shape == (N, n_t)
+    X = Phi.T @ solver.q
+    mask = model._mask_host
+    X[mask, :] = model._g_fill_host[mask][:, None]
+    assert np.allclose(solver.X, X, rtol=1e-12, atol=1e-12)
+    assert np.allclose(solver.Xdot, Phi.T @ solver.qdot, rtol=1e-12, atol=1e-12)
+    for c in range(3):
+        assert np.array_equal(solver.U[c::3], solver.X[c::4])
+    assert np.allclose(solver.T, solver.X[3::4] + mesh.reference_temperature()[:, None])
+    dir_nodes = np.unique(np.asarray(mesh.dict_tri_groups[4]).reshape(-1))
+    assert np.all(solver.U[3 * dir_nodes, :] == 1e-3) and np.allclose(solver.T[dir_nodes, :], 2.5 + mesh.reference_temperature()[dir_nodes][:, None])
+    q_full = solver.q.copy()
+    solver2 = LinearTransient(model, U0, np.zeros(3 * N), th0, np.zeros(N), 2.0, n_t, progress=False)
+    monkeypatch.setattr(model, "compute_ROB_u", lambda k, tol=None: None)      # keep the same bases
+    monkeypatch.setattr(model, "compute_ROB_theta", lambda k, tol=None: None)
+    monkeypatch.setattr(model, "compute_ROM_matrices", lambda: None)
+    solver2.solve_ROM(nu, nt, history='last')
+    assert np.allclose(solver2.q, q_full) and solver2.X.shape == (n, 1) and np.allclose(solver2.X[:, 0], solver.X[:, -1])

@@ -288,3 +288,111 @@ def test_solve_ROM_host_flow_with_stubbed_device_steps(monkeypatch):
     monkeypatch.setattr(model, "compute_ROM_matrices", lambda: None)
     solver2.solve_ROM(nu, nt, history='last')
     assert np.allclose(solver2.q, q_full) and solver2.X.shape == (n, 1) and np.allclose(solver2.X[:, 0], solver.X[:, -1])
+
+
+class _ScipyPlanes:
+    """Stand-in for an operator in plane storage (CPU tests of the host logic only): a scipy matrix."""
+
+    def __init__(self, A):
+        self.A = A.tocsr()
+
+
+class _ScipyDeviceMesh:
+    """Stand-in for DeviceMesh with the one call the ROM host logic makes: y = beta_y y + alpha Op_masked x, where the plane
+    map selects which (row component, column component) entries of the 4x4 node blocks the operator has."""
+    device = torch.device("cpu")
+
+    def planes_spmv(self, vals, plane_map, x, y, alpha=1.0, beta_y=0.0):
+        n = vals.A.shape[0]
+        comp = np.arange(n) % 4
+        out = np.zeros(n)
+        xv = x.numpy()
+        for r in range(4):
+            for c in range(4):
+                if plane_map[r, c] >= 0:
+                    out[comp == r] += (vals.A[comp == r, :][:, comp == c] @ xv[comp == c])
+        y.copy_(torch.from_numpy(beta_y * y.numpy() + alpha * out))
+        return y
+
+
+def test_reduced_matrices_and_forces_host_logic_against_the_oracle(monkeypatch):
+    """Model.compute_ROM_matrices / rom_forces / compute_ROM_forces (projection block structure, per-field lifting with NON-ZERO
+    prescribed values, cached load projections) with the plane SpMV replaced by scipy, against direct projections of the
+    oracle's operators (reference model.py:365-440)."""
+    from oracle import tefem_oracle as orc
+    from thermoelasticity_fem_b200 import Mesh, Model, LinearThermoElastic, _lib, layout
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    monkeypatch.setattr(_lib, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(_lib, "load", lambda: None)
+    pts, tets, tris, nodes = kuhn_box(3, 2, 3, jitter=0.15, seed=4)
+    props = {1: (2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: (7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.), 3: (2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    mesh.set_materials({k: LinearThermoElastic(*v) for k, v in props.items()})
+    mesh.make_elements()
+    n_t = 6
+    amp = np.linspace(0.0, 1.0, n_t)
+    surf = np.outer(np.array([0., 1e5, -1e6]), amp)
+    flux = -25.0 * amp
+    dU = {4: [('x', 2e-4), ('y', 1e-4), ('z', 0.)], 5: [('x', -1e-4)]}
+    dT = {4: 3.0, 6: -1.5}
+    aM, aK = 0.3, 0.05
+    model = Model(mesh, dict_dirichlet_U=dU, dict_dirichlet_theta=dT, dict_surface_forces={7: surf}, dict_heat_flux={7: flux},
+                  alpha_M=aM, alpha_K=aK)
+    model.create_free_dofs_lists()
+    groups = dict(tet=tets, tri=tris, nodes=nodes)
+    omats = {k: orc.Material(*v) for k, v in props.items()}
+    conn, mat_id, rows = orc.element_table(tets, omats)
+    ops = orc.assemble(pts, conn, rows, mat_id, aM, aK, which="MKD")
+    monkeypatch.setattr(type(mesh), "device_mesh", lambda self: _ScipyDeviceMesh())
+    model._planes = {k: _ScipyPlanes(ops[k]) for k in "MDK"}
+    model._d_alpha = (aM, aK)
+    n = mesh.n_dofs
+    fu, ft = model.free_dofs_U, model.free_dofs_theta
+    rng = np.random.default_rng(9)
+    nu, nt = 4, 3
+    phi_u, phi_t = rng.standard_normal((fu.size, nu)), rng.standard_normal((ft.size, nt))
+    Pu, Pt = np.zeros((nu, n)), np.zeros((nt, n))
+    Pu[:, fu], Pt[:, ft] = phi_u.T, phi_t.T
+    model.n_q_u, model.n_q_t = nu, nt
+    model._phi_u_dev, model._phi_t_dev = torch.from_numpy(Pu), torch.from_numpy(Pt)
+    assert np.array_equal(model.mat_phi_u, phi_u) and np.array_equal(model.mat_phi_t, phi_t)
+
+    def sub(A, r, c):
+        return A.tocsr()[r, :].tocsc()[:, c]
+
+    model.compute_ROM_matrices()
+    M, D, K = ops["M"], ops["D"], ops["K"]
+    want_M = np.zeros((nu + nt, nu + nt)); want_D = np.zeros_like(want_M); want_K = np.zeros_like(want_M)
+    want_M[:nu, :nu] = phi_u.T @ (sub(M, fu, fu) @ phi_u)
+    want_D[:nu, :nu] = phi_u.T @ (sub(D, fu, fu) @ phi_u)
+    want_D[nu:, :nu] = phi_t.T @ (sub(D, ft, fu) @ phi_u)
+    want_D[nu:, nu:] = phi_t.T @ (sub(D, ft, ft) @ phi_t)
+    want_K[:nu, :nu] = phi_u.T @ (sub(K, fu, fu) @ phi_u)
+    want_K[:nu, nu:] = phi_u.T @ (sub(K, fu, ft) @ phi_t)
+    want_K[nu:, nu:] = phi_t.T @ (sub(K, ft, ft) @ phi_t)
+    for got, want in ((model.mat_Mrom, want_M), (model.mat_Drom, want_D), (model.mat_Krom, want_K)):
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    # reduced loads exactly as reference model.py:395-440: per-tag lifting through K[free_U, dir_U] and K[free_theta, dir_theta]
+    Kcsr = K.tocsr()
+    for idx in (1, 3, 5):
+        F = orc.assemble_F(pts, groups, dict(surface={7: surf}, flux={7: flux}), idx_t=idx)
+        Fu, Ft = F[fu].copy(), F[ft].copy()
+        for tag, lst in dU.items():
+            nodes_t = np.unique(np.asarray(tris[tag]).reshape(-1))
+            vec = np.zeros(n)
+            dofs = []
+            for node in nodes_t:
+                for letter, val in lst:
+                    dofs.append(4 * node + "xyz".index(letter))
+                    vec[4 * node + "xyz".index(letter)] = val
+            Fu -= Kcsr[fu, :][:, dofs] @ vec[dofs]
+        for tag, theta in dT.items():
+            nodes_t = np.unique(np.asarray(tris[tag]).reshape(-1))
+            dofs = [4 * node + 3 for node in nodes_t]
+            Ft -= Kcsr[ft, :][:, dofs] @ np.full(len(dofs), theta)
+        want = np.r_[phi_u.T @ Fu, phi_t.T @ Ft]
+        got = model.rom_forces(idx)
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), idx
+        model._F = torch.from_numpy(F)                        # what assemble_F(idx_t) leaves on the device
+        model.compute_ROM_forces()
+        assert np.abs(model.vec_From - want).max() <= 1e-12 * np.abs(want).max(), idx

@@ -396,3 +396,66 @@ def test_reduced_matrices_and_forces_host_logic_against_the_oracle(monkeypatch):
         model._F = torch.from_numpy(F)                        # what assemble_F(idx_t) leaves on the device
         model.compute_ROM_forces()
         assert np.abs(model.vec_From - want).max() <= 1e-12 * np.abs(want).max(), idx
+
+
+@pytest.mark.parametrize("theta_dirichlet", [True, False])
+def test_field_eigenproblem_host_logic_with_scipy_solves(monkeypatch, theta_dirichlet):
+    """rom.FieldEigenProblem (field masks, field-restricted plane maps, shift for a field without Dirichlet DOFs, Lanczos +
+    polish, unit-norm vectors) with the plane SpMV and the Krylov solves replaced by scipy, against dense eigh of the oracle's
+    K_uu / M_uu and K_tt / D_tt on the free DOFs (reference model.py:341-363)."""
+    from oracle import tefem_oracle as orc
+    from thermoelasticity_fem_b200 import Mesh, Model, LinearThermoElastic, _lib, rom, solvers
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    monkeypatch.setattr(_lib, "require_cuda", lambda: torch.device("cpu"))
+    pts, tets, tris, nodes = kuhn_box(4, 3, 3, jitter=0.1, seed=7)
+    props = {1: (2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: (7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.), 3: (2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    mesh.set_materials({k: LinearThermoElastic(*v) for k, v in props.items()})
+    mesh.make_elements()
+    model = Model(mesh, dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)]},
+                  dict_dirichlet_theta={4: 0.} if theta_dirichlet else None, alpha_M=0.1, alpha_K=0.0)
+    model.create_free_dofs_lists()
+    conn, mat_id, rows = orc.element_table(tets, {k: orc.Material(*v) for k, v in props.items()})
+    ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.0, which="MKD")
+    monkeypatch.setattr(type(mesh), "device_mesh", lambda self: _ScipyDeviceMesh())
+    model._planes = {k: _ScipyPlanes(ops[k]) for k in "MDK"}
+    model._d_alpha = (0.1, 0.0)
+    n = mesh.n_dofs
+    seen = {}
+
+    class ScipySystemSolve:                                   # stand-in for solvers._SystemSolve (form_system + BiCGSTAB)
+        def __init__(self, model_, cM, cD, cK, rtol, max_iter, check_every, precond="auto", dir_mask=None):
+            elim = dir_mask.numpy().astype(bool)
+            A = (cM * ops["M"] + cD * ops["D"] + cK * ops["K"]).tocsr()
+            keep = sp.diags((~elim).astype(float))
+            self.elim = elim
+            self.lu = spl.splu((keep @ A @ keep + sp.diags(elim.astype(float))).tocsc())
+            seen["coef"] = (cM, cD, cK)
+
+        def solve(self, rhs, x):
+            b = rhs.numpy().copy()
+            b[self.elim] = 0.0
+            x.copy_(torch.from_numpy(self.lu.solve(b)))
+
+    monkeypatch.setattr(solvers, "_SystemSolve", ScipySystemSolve)
+    for field, k, free, A_name, B_name in (("u", 6, model.free_dofs_U, "K", "M"), ("theta", 5, model.free_dofs_theta, "K", "D")):
+        prob = rom.FieldEigenProblem(model, field)
+        singular = field == "theta" and not theta_dirichlet
+        assert (prob.shift > 0.0) == singular                                       # pure-Neumann theta field: shifted solves
+        assert seen["coef"] == ((prob.shift, 0.0, 1.0) if field == "u" else (0.0, prob.shift, 1.0))
+        lam, Phi, info = prob.smallest(k, tol=1e-10)
+        A = ops[A_name].tocsr()[free, :].tocsc()[:, free].toarray()
+        B = ops[B_name].tocsr()[free, :].tocsc()[:, free].toarray()
+        ref = scipy.linalg.eigh(0.5 * (A + A.T), 0.5 * (B + B.T), eigvals_only=True)[:k]
+        scale = np.abs(ref).max()
+        assert np.abs(lam - ref).max() <= 1e-8 * scale, (field, lam, ref)
+        if singular:
+            assert abs(ref[0]) <= 1e-9 * scale                                       # the constant mode
+        assert info["converged"]
+        P = Phi.numpy()
+        outside = np.ones(n, dtype=bool)
+        outside[free] = False
+        assert not P[:, outside].any() and np.allclose(np.linalg.norm(P, axis=1), 1.0, atol=1e-12)
+        X = P[:, free].T
+        res = np.linalg.norm(A @ X - (B @ X) * lam, axis=0) / np.maximum(np.linalg.norm(B @ X, axis=0) * scale, 1e-300)
+        assert res.max() < 1e-8

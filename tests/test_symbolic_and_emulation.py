@@ -355,3 +355,38 @@ def test_edge_meshes_single_tet_and_fan(emu, pf):
                 A = planes_to_csc(vals[nm], pm, S, 4 * pts.shape[0])
                 parity.check_pattern(A, None, ops[nm])
                 assert parity.scaled_error(A, ops[nm]) < parity.VALUE_TOL
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_random_delaunay_meshes_both_layouts(emu, seed):
+    """Unstructured meshes with irregular valences (up to ~60 elements per node: many pieces per diagonal block) and a
+    material interface, random tile parameters: the two item layouts give bitwise the same planes and match the oracle."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.random((int(rng.integers(150, 450)), 3)) * np.array([2.0, 0.5, 0.3])
+    tets = Delaunay(pts).simplices.astype(np.int64)
+    X = pts[tets]
+    det = np.linalg.det(np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0], X[:, 3] - X[:, 0]], 1))
+    tets[det < 0] = tets[det < 0][:, [0, 2, 1, 3]]                        # the reference's orientation convention
+    tets = tets[np.abs(det) > 1e-6 * np.abs(det).max()]                   # drop slivers
+    used = np.unique(tets)
+    remap = -np.ones(pts.shape[0], dtype=np.int64)
+    remap[used] = np.arange(used.size)
+    pts, tets = pts[used], remap[tets]
+    left = pts[tets].mean(axis=1)[:, 0] < 1.0
+    mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.)}
+    conn, mat_id, rows = orc.element_table({1: tets[left], 2: tets[~left]}, mats)
+    kw = dict(items_per_cta=int(rng.choice([64, 256, 512])), elem_budget=int(rng.choice([160, 310, 620])), max_chunk=int(rng.choice([3, 6, 8])))
+    vals = {}
+    for pf in (False, True):
+        S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=pf, **kw)
+        vals[pf], bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.2, 0.1)
+        assert bad.min() == 2 ** 31 - 1
+    for nm in "MKD":
+        assert np.array_equal(vals[False][nm], vals[True][nm]), nm
+    ops = orc.assemble(pts, conn, rows, mat_id, 0.2, 0.1)
+    for nm, pm in (("K", layout.plane_map_K()), ("D", layout.plane_map_D(0.2, 0.1)), ("M", layout.plane_map_M())):
+        A = planes_to_csc(vals[True][nm], pm, S, 4 * pts.shape[0])
+        ref = orc.drop_component_zeros_M(ops[nm]) if nm == "M" else ops[nm]
+        parity.check_pattern(A, None, ref)
+        assert parity.scaled_error(A, ref) < parity.VALUE_TOL, nm

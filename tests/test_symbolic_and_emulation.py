@@ -390,3 +390,15 @@ def test_random_delaunay_meshes_both_layouts(emu, seed):
         ref = orc.drop_component_zeros_M(ops[nm]) if nm == "M" else ops[nm]
         parity.check_pattern(A, None, ref)
         assert parity.scaled_error(A, ref) < parity.VALUE_TOL, nm
+
+
+def test_schedule_fits_the_kernels_shared_memory():
+    """build_schedule shrinks tiles until the largest one fits the dynamic shared memory of assemble_kernel (the launch would
+    be refused otherwise); the default tiles measured on the B200 (ncu: 111.9 KB for the fused launch) are reproduced."""
+    from thermoelasticity_fem_b200.symbolic import MAX_SMEM_BYTES
+    pts, tets, tris, nodes = kuhn_box(14, 14, 14, 1., 1., 1., n_layers=1)
+    conn = torch.from_numpy(tets[1])
+    S = build_schedule(conn, pts.shape[0])
+    assert 90_000 < S.smem_bytes() < 120_000 and S.smem_bytes(with_D=False) < S.smem_bytes()
+    big = build_schedule(conn, pts.shape[0], items_per_cta=4000, elem_budget=5000)
+    assert big.smem_bytes() <= MAX_SMEM_BYTES and big.max_cta_nodes <= 256 and big.n_cta < S.n_cta

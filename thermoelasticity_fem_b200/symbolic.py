@@ -41,6 +41,7 @@ ELEM_BUDGET_PER_CTA = 620    # bound on the sum of node degrees per tile (>= sta
 MAX_CHUNK = 8                # lists longer than 2 * MAX_CHUNK are split into chunks of <= MAX_CHUNK
 ITEM_SORT_WINDOW = 1         # > 1: items ordered longest-first inside windows of this many consecutive items (measured:
                              # helps the K-only launch by <= 12 %, scatters the 29 plane stores of M + D + K: off)
+MAX_SMEM_BYTES = 220 * 1024  # dynamic shared memory limit of assemble_kernel (csrc/tefem_assemble.cu)
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
 # True: the pieces of split blocks come first in a tile's item list and every block has one item in block order behind
@@ -94,6 +95,21 @@ class Schedule:
         return np.array([self.max_cta_items, self.max_cta_elems, self.max_cta_inc, self.max_cta_slots, self.max_cta_split,
                          self.max_cta_nodes, int(self.pieces_first)], dtype=np.int32)
 
+    def smem_bytes(self, with_D=True, with_K=True):
+        """Dynamic shared memory one CTA of assemble_kernel needs for the largest tile (mirrors launch_assemble_pf /
+        stage_layout of csrc/tefem_assemble.cu): element records + parked pieces + two prefetch stages + barriers + tables.
+        The fused M + D + K launch (default arguments) is the largest instantiation."""
+        def up16(b):
+            return (b + 15) & ~15
+        rec = 17 if with_D else 13
+        live = (13 if (with_K or with_D) else 0) + 1 + (4 if with_D else 0)
+        slot = live | 1
+        rec_doubles = (self.max_cta_elems * rec + 15) & ~15
+        part_doubles = (self.max_cta_slots * slot + 15) & ~15
+        stage = (64 + up16(24 * ((self.max_cta_nodes + 1) & ~1)) + up16(4 * (self.max_cta_elems + 3)) + 2 * up16(4 * (self.max_cta_items + 3))
+                 + 2 * up16(4 * (self.max_cta_split + 3)) + up16(2 * (self.max_cta_inc + 7)))
+        return 8 * (rec_doubles + part_doubles) + 2 * stage + 16 + 20 * 8
+
     def schedule_bytes(self):
         """Bytes of slot-map / schedule data one assembly launch reads (cta_xyz is counted by DeviceMesh)."""
         return sum(t.numel() * t.element_size() for t in
@@ -145,20 +161,24 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     tile_cost: what `items_per_cta` bounds - 'items' (all work items of the tile's rows; default of the inline layout)
     or 'blocks' (its blocks = the threads of the block-order pass; default of the pieces-first layout).
 
-    A tile must not reference more than 256 nodes / 4096 elements (byte / 12-bit local numbers); meshes whose
-    node numbering has little locality (e.g. the Gmsh numbering of data/sandwich.msh) get smaller tiles."""
+    A tile must not reference more than 256 nodes / 4096 elements (byte / 12-bit local numbers) and must fit the
+    kernel's shared memory (Schedule.smem_bytes); meshes whose node numbering has little locality (e.g. the Gmsh
+    numbering of data/sandwich.msh), very high valences or oversized requests get smaller tiles."""
     pieces_first = PIECES_FIRST if pieces_first is None else bool(pieces_first)
     if tile_cost is None:
         tile_cost = 'blocks' if pieces_first else 'items'
     assert tile_cost in ('items', 'blocks')
     for _ in range(12):
         try:
-            return _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id,
-                                   ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
-                                   pieces_first, tile_cost)
+            S = _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id,
+                                ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
+                                pieces_first, tile_cost)
+            if S.smem_bytes() <= MAX_SMEM_BYTES:            # the kernel would refuse the launch: smaller tiles
+                return S
         except _TileTooLarge:
-            items_per_cta = max(16, (3 * items_per_cta) // 4)
-            elem_budget = max(32, (3 * elem_budget) // 4)
+            pass
+        items_per_cta = max(16, (3 * items_per_cta) // 4)
+        elem_budget = max(32, (3 * elem_budget) // 4)
     raise RuntimeError("could not build a tile schedule within the shared-memory index limits")
 
 

@@ -302,7 +302,8 @@ static int upload_quad() {
 // Threads per CTA: 256 (default; the 512-block tiles of symbolic.py are two passes).  The pieces-first kernel is also
 // instantiated for 128 and 64 threads - more, smaller CTAs per SM, i.e. more independent barrier domains (a third of the
 // stall samples of the 256-thread kernel wait at one of the three barriers of a tile, profiles/README.md) - selected
-// with the environment variable TEFEM_ASM_THREADS (measurement knob; pair it with items_per_cta = 2 x threads).
+// with the environment variable TEFEM_ASM_THREADS (measurement knob, read at every launch; pair it with items_per_cta =
+// 2 x threads).
 // 512 threads per SM in every case, so that no instantiation is capped below 128 registers.
 #ifndef ASM_THREADS_N
 #define ASM_THREADS_N 256
@@ -534,14 +535,10 @@ static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStre
     return TEFEM_OK;
 }
 
-// TEFEM_ASM_THREADS = 64 | 128 | 256 (read once per process)
+// TEFEM_ASM_THREADS = 64 | 128 | 256 (read at every launch, so that one process can compare the variants)
 static int asm_threads() {
-    static int nt = 0;
-    if (nt == 0) {
-        const char* e = getenv("TEFEM_ASM_THREADS");
-        nt = e ? atoi(e) : ASM_THREADS;
-    }
-    return nt;
+    const char* e = getenv("TEFEM_ASM_THREADS");
+    return (e && e[0]) ? atoi(e) : ASM_THREADS;
 }
 
 template <int OPS, int DUU>

@@ -130,6 +130,20 @@ int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int3
                    double* vals_M, double* vals_K, double* vals_D,
                    int32_t* bad_elem, void* stream);
 
+/* Bank-aware tile-local numbering of the staged elements of every tile (HOST function, all pointers are host pointers;
+ * no reference counterpart - part of the symbolic phase).  The record of staged element e sits at rec[stride * e] in shared
+ * memory, so e mod 16 decides the banks its gathers hit; for every pair of elements that the lanes of one half-warp read in
+ * the same load the function counts at which class differences they collide, then exchanges the classes of two elements
+ * inside a block of 16 consecutive staged elements while that lowers the count (the numbering stays a bijection onto
+ * 0 .. n_elems - 1 and phase 1 of the kernel keeps its access pattern).
+ * strides: bit 0 = kernels without D (record stride 13), bit 1 = with D (stride 17).  h_new_local[o_elems + old number] <- new
+ * number; h_n_slots[c] <- n_elems of tile c; h_cost (optional, [2]) <- pairwise collision count before / after.
+ * The caller permutes cta_elems / cta_conn8 and rewrites the element field of the incidence entries; lists, order and
+ * values are unchanged (bitwise).                                                                                  */
+int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta_hdr, const int32_t* h_item_inc,
+                                  const int32_t* h_item_meta, const uint16_t* h_inc, int strides, int n_sweeps,
+                                  int n_threads, int32_t* h_new_local, int32_t* h_n_slots, int64_t* h_cost);
+
 /* Synchronises the stream, reads bad_elem[2] and returns TEFEM_OK, TEFEM_ERR_NEG_JACOBIAN or
  * TEFEM_ERR_ZERO_JACOBIAN for the FIRST offending element in element order (the one the
  * reference's loop would have raised on); *h_elem receives its index.                          */

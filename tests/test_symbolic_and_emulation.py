@@ -298,9 +298,10 @@ def test_pieces_first_layout_is_bitwise_the_inline_layout(sandwich, emu, mesh_ki
         conn, mat_id, rows = orc.element_table(tets, mats)
         variants = [dict(), dict(items_per_cta=64, elem_budget=160, max_chunk=3), dict(items_per_cta=700, elem_budget=800, max_chunk=6)]
     for kw in variants:
-        S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=False, **kw)
+        S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=False,
+                            bank_opt=False, **kw)
         S1 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=True,
-                            tile_cost='items', **kw)
+                            tile_cost='items', bank_opt=False, **kw)
         check_pieces_first_invariants(S1, S0)
         S2 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=True, **kw)
         assert S2.n_cta <= S1.n_cta            # default tile cost of this layout: blocks per tile (the block-order pass)
@@ -402,3 +403,47 @@ def test_schedule_fits_the_kernels_shared_memory():
     assert 90_000 < S.smem_bytes() < 120_000 and S.smem_bytes(with_D=False) < S.smem_bytes()
     big = build_schedule(conn, pts.shape[0], items_per_cta=4000, elem_budget=5000)
     assert big.smem_bytes() <= MAX_SMEM_BYTES and big.max_cta_nodes <= 256 and big.n_cta < S.n_cta
+
+
+@pytest.mark.parametrize("pf", [True, False])
+def test_bank_aware_numbering_keeps_the_values_bitwise(emu, pf):
+    """symbolic.optimize_banks (native host routine tefem_schedule_bank_numbering): the staged elements of every tile are
+    renumbered inside blocks of 16, the incidence entries follow; the schedule still decodes to the mesh, the emulated
+    assembly is BITWISE unchanged, and the modelled shared-memory wavefronts of the incidence loop drop."""
+    from thermoelasticity_fem_b200.symbolic import optimize_banks
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import k1_model
+    pts, tets, tris, nodes = kuhn_box(9, 8, 7, jitter=0.15, seed=5)
+    mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+            3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    conn, mat_id, rows = orc.element_table(tets, mats)
+    S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=pf, bank_opt=False)
+    S2, (before, after) = optimize_banks(S, return_cost=True, n_threads=2)
+    assert S2.bank_optimized and not S.bank_optimized and after < 0.8 * before
+    H, H2 = S.cta_hdr.numpy().astype(np.int64), S2.cta_hdr.numpy().astype(np.int64)
+    assert np.array_equal(H, H2) and S2.max_cta_elems == S.max_cta_elems            # a bijection: no holes, same segment sizes
+    assert torch.equal(S.item_inc, S2.item_inc) and torch.equal(S.item_meta, S2.item_meta)
+    ce, ce2 = S.cta_elems.numpy(), S2.cta_elems.numpy()
+    cn8 = S2.cta_conn8.numpy().astype(np.int64) & 0xFFFFFFFF
+    inc, inc2 = S.inc.numpy().astype(np.int64) & 0xFFFF, S2.inc.numpy().astype(np.int64) & 0xFFFF
+    cnodes = S2.cta_nodes.numpy()
+    moved = 0
+    for c in range(S.n_cta):
+        n_el, n_inc, n_nd, o_el, o_inc, o_nd = H[c, 1], H[c, 2], H[c, 4], H[c, 6], H[c, 7], H[c, 9]
+        a, b = ce[o_el:o_el + n_el], ce2[o_el:o_el + n_el]
+        for b0 in range(0, n_el, 16):                                               # a permutation inside every block of 16
+            assert np.array_equal(np.sort(a[b0:b0 + 16]), np.sort(b[b0:b0 + 16]))
+        moved += int((a != b).sum())
+        loc = np.stack([(cn8[o_el:o_el + n_el] >> (8 * k)) & 0xff for k in range(4)], axis=1)
+        assert np.array_equal(cnodes[o_nd:o_nd + n_nd][loc], conn[b])               # byte connectivity follows the elements
+        w, w2 = inc[o_inc:o_inc + n_inc], inc2[o_inc:o_inc + n_inc]
+        assert np.array_equal(w & 15, w2 & 15) and np.array_equal(a[w >> 4], b[w2 >> 4])   # same (element, a, b), new local number
+    assert moved > 0
+    v1, bad1 = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.2, 0.1)
+    v2, bad2 = emu_assemble(emu, S2, pts, conn, mat_id, rows, "MKD", 0.2, 0.1)
+    for nm in "MKD":
+        assert np.array_equal(v1[nm], v2[nm]), nm
+    for with_d in (False, True):
+        r1, r2 = k1_model.model(S, 17 if with_d else 13, with_d, True), k1_model.model(S2, 17 if with_d else 13, with_d, True)
+        assert r2["wavefronts"] < 0.93 * r1["wavefronts"] and r2["ideal"] == r1["ideal"]
+    assert k1_model.model_phase1(S2)["wavefronts"] == k1_model.model_phase1(S)["wavefronts"]   # phase 1 is untouched

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "tefem_assemble": [P, c_int, c_int32, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
                        P, P, P, P, P],
     "tefem_check_jacobian": [P, P, P],
+    "tefem_schedule_bank_numbering": [c_int32, P, P, P, P, c_int, c_int, c_int, P, P, P],
     "tefem_planes_spmv": [P, P, c_int32, c_int64, P, P, P, c_double, c_double, P, P],
     "tefem_form_system": [P, P, c_int32, c_int64, P, c_double, P, c_int, c_double, P, c_double, P, P, P],
     "tefem_block_jacobi_scale": [P, P, c_int32, P, P, P],

@@ -11,7 +11,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libtefem_b200.so")
-SOURCES = ["tefem_core.cu", "tefem_assemble.cu", "tefem_system.cu", "tefem_krylov.cu", "tefem_precond.cu", "tefem_comm.cu"]
+SOURCES = ["tefem_core.cu", "tefem_assemble.cu", "tefem_schedule.cu", "tefem_system.cu", "tefem_krylov.cu", "tefem_precond.cu",
+           "tefem_comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

@@ -47,6 +47,9 @@ MAX_CTA_NODES = 256          # tile-local node numbers are bytes
 # True: the pieces of split blocks come first in a tile's item list and every block has one item in block order behind
 # them (see build_schedule); False: pieces inline + split lists.  TEFEM_PIECES_FIRST=0/1 overrides (A/B measurements).
 PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "1") == "1"
+# Bank-aware tile-local numbering of the staged elements (optimize_banks): off unless TEFEM_BANK_OPT=1 - the modelled gain
+# (tools/k1_model.py: -21 % / -14 % gather wavefronts) has not been measured on a GPU yet.
+BANK_OPT = os.environ.get("TEFEM_BANK_OPT", "0") == "1"
 HDR_STRIDE = 12
 H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)
 
@@ -82,6 +85,7 @@ class Schedule:
     split_block: torch.Tensor    # int32 [padded] tile-local block
     split_meta: torch.Tensor     # int32 [padded]
     pieces_first: bool = False   # item layout of the tiles (build_schedule)
+    bank_optimized: bool = False # staged elements renumbered per tile by optimize_banks
 
     def to(self, device):
         kw = {}
@@ -116,6 +120,64 @@ class Schedule:
                    (self.inc, self.cta_hdr, self.cta_conn8, self.item_inc, self.item_meta, self.split_block, self.split_meta))
 
 
+def optimize_banks(S: "Schedule", strides: int = 3, n_sweeps: int = 3, n_threads: int = 0, return_cost: bool = False,
+                   chunk: int = 1 << 26):
+    """Bank-aware tile-local numbering of the staged elements (native host routine tefem_schedule_bank_numbering,
+    csrc/tefem_schedule.cu): returns a Schedule whose cta_elems / cta_conn8 are permuted inside blocks of 16 staged elements
+    per tile and whose incidence entries carry the new local numbers.  Items, lists, summation order and therefore the
+    assembled values are unchanged (bitwise); only the shared-memory banks the kernel's gathers hit change.
+    strides: bit 0 = count the collisions of the kernels without D (record stride 13), bit 1 = with D (stride 17).
+    The search runs on the host (threads over tiles) on copies of the schedule arrays; the permutation is applied on the
+    device the schedule lives on, in chunks of `chunk` entries."""
+    import ctypes
+
+    from . import _lib
+    lib = _lib.load()
+    dev = S.cta_hdr.device
+    n_cta = S.n_cta
+    if n_cta == 0:
+        return (S, (0, 0)) if return_cost else S
+    hdr = S.cta_hdr.cpu().contiguous()
+    item_inc, item_meta, inc_h = S.item_inc.cpu().contiguous(), S.item_meta.cpu().contiguous(), S.inc.cpu().contiguous()
+    new_local = torch.zeros(S.cta_elems.numel(), dtype=torch.int32)
+    n_slots = torch.zeros(n_cta, dtype=torch.int32)
+    cost = (ctypes.c_int64 * 2)()
+    p = _lib.ptr
+    _lib.check(lib.tefem_schedule_bank_numbering(n_cta, p(hdr), p(item_inc), p(item_meta), p(inc_h), int(strides), int(n_sweeps),
+                                                 int(n_threads), p(new_local), p(n_slots), cost))
+    del item_inc, item_meta, inc_h
+    assert torch.equal(n_slots, hdr[:, H_NELEMS])                    # a bijection: the segment sizes do not change
+    H = S.cta_hdr.to(torch.int64)
+    n_el, o_el, n_inc, o_inc = (H[:, k].contiguous() for k in (H_NELEMS, H_OELEMS, H_NINC, H_OINC))
+    new_local = new_local.to(dev)
+    # ---- staged element arrays: entry q of tile t moves to o_el[t] + new_local[q]
+    new_elems, new_conn8 = S.cta_elems.clone(), S.cta_conn8.clone()
+    n_staged = int(S.cta_elems.numel())
+    for s0 in range(0, n_staged, chunk):
+        q = torch.arange(s0, min(s0 + chunk, n_staged), dtype=torch.int64, device=dev)
+        t = torch.searchsorted(o_el, q, right=True) - 1
+        valid = (q - o_el[t]) < n_el[t]
+        q, t = q[valid], t[valid]
+        dest = o_el[t] + new_local[q].to(torch.int64)
+        new_elems[dest] = S.cta_elems[q]
+        new_conn8[dest] = S.cta_conn8[q]
+    # ---- incidence entries: element field -> new local number
+    new_inc = S.inc.clone()
+    n_ent = int(S.inc.numel())
+    for s0 in range(0, n_ent, chunk):
+        q = torch.arange(s0, min(s0 + chunk, n_ent), dtype=torch.int64, device=dev)
+        t = torch.searchsorted(o_inc, q, right=True) - 1
+        valid = (q - o_inc[t]) < n_inc[t]
+        q, t = q[valid], t[valid]
+        w = S.inc[q].to(torch.int64) & 0xFFFF
+        w = (new_local[o_el[t] + (w >> 4)].to(torch.int64) << 4) | (w & 15)
+        new_inc[q] = torch.where(w >= 32768, w - 65536, w).to(torch.int16)
+    kw = dict(S.__dict__)
+    kw.update(cta_elems=new_elems, cta_conn8=new_conn8, inc=new_inc, bank_optimized=True)
+    out = Schedule(**kw)
+    return (out, (int(cost[0]), int(cost[1]))) if return_cost else out
+
+
 def _excl_cumsum(x):
     return torch.cumsum(x, 0) - x
 
@@ -145,7 +207,8 @@ class _TileTooLarge(Exception):
 def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                    items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA,
                    max_chunk: int = MAX_CHUNK, mat_id: torch.Tensor = None,
-                   item_sort_window: int = None, pieces_first: bool = None, tile_cost: str = None) -> Schedule:
+                   item_sort_window: int = None, pieces_first: bool = None, tile_cost: str = None,
+                   bank_opt: bool = None) -> Schedule:
     """conn: integer tensor [E, 4] in the reference's element order; node numbers < n_nodes.
     n_rows: only rows of nodes < n_rows are assembled (row-partitioned multi-GPU: owned nodes
     are numbered first); default all.
@@ -158,6 +221,8 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     pieces, synchronises, then the block items: warps hold lists of similar length (the diagonal chunks no longer
     sit between the short off-diagonal lists) and EVERY block is stored by the thread at its block-order position
     (no scattered stores of the combined blocks).  Same chunks, same summation order: bitwise the same values.
+    bank_opt: renumber the staged elements of every tile so that the kernel's shared-memory gathers hit fewer bank conflicts
+    (optimize_banks; default BANK_OPT).
     tile_cost: what `items_per_cta` bounds - 'items' (all work items of the tile's rows; default of the inline layout)
     or 'blocks' (its blocks = the threads of the block-order pass; default of the pieces-first layout).
 
@@ -174,7 +239,7 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                                 ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
                                 pieces_first, tile_cost)
             if S.smem_bytes() <= MAX_SMEM_BYTES:            # the kernel would refuse the launch: smaller tiles
-                return S
+                return optimize_banks(S) if (BANK_OPT if bank_opt is None else bank_opt) else S
         except _TileTooLarge:
             pass
         items_per_cta = max(16, (3 * items_per_cta) // 4)

@@ -1,10 +1,13 @@
 """A/B of K1 item layouts on the GPU box: inline (split lists) vs pieces-first, same mesh, same chunks.
 Checks that the planes are BITWISE identical (same chunks => same summation order) and times both.
-usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first" ...]   (first variant = reference)
+usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first[,bank_opt]" ...]   (first variant = reference;
+bank_opt = 1: bank-aware numbering of the staged elements, symbolic.optimize_banks; 2 / 3: optimised for the kernels with D /
+without D only)
 Threads per CTA are a per-process knob of the library: TEFEM_ASM_THREADS=64|128 python tools/asm_ab.py 100 128,160,8,1 256,310,8,1
 (pair with items = 2 x threads; build variants: TEFEM_LIB=/path/to/lib.so)."""
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -13,11 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from thermoelasticity_fem_b200 import LinearThermoElastic  # noqa: E402
 from thermoelasticity_fem_b200.device import DeviceMesh  # noqa: E402
-from thermoelasticity_fem_b200.symbolic import build_schedule  # noqa: E402
+from thermoelasticity_fem_b200.symbolic import build_schedule, optimize_banks  # noqa: E402
 from thermoelasticity_fem_b200.synthetic import kuhn_box  # noqa: E402
 
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-variants = sys.argv[2:] or ["256,310,8,0", "256,310,8,1", "272,330,8,1", "256,310,6,1", "512,620,8,1"]
+variants = sys.argv[2:] or ["512,620,8,1", "512,620,8,1,1", "512,620,8,1,2", "512,620,8,1,3", "256,310,8,0"]
 pts, tets, tris, nodes = kuhn_box(cells, cells, cells, 1.0, 1.0, 1.0, n_layers=1, index_dtype=np.int32)
 conn = tets[1]
 mat = LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.)
@@ -26,11 +29,20 @@ E, N = conn.shape[0], pts.shape[0]
 conn_d = torch.from_numpy(conn).cuda()
 ref = {}
 for v in variants:
-    items, budget, chunk, pf = [int(x) for x in v.split(",")]
-    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk, pieces_first=bool(pf))
+    f = [int(x) for x in v.split(",")]
+    items, budget, chunk, pf = f[:4]
+    bank = f[4] if len(f) > 4 else 0
+    t_sym = time.perf_counter()
+    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk, pieces_first=bool(pf), bank_opt=False)
+    t_sym = time.perf_counter() - t_sym
+    t_bank = time.perf_counter()
+    if bank:
+        S = optimize_banks(S, strides={1: 3, 2: 2, 3: 1}[bank])
+    t_bank = time.perf_counter() - t_bank
     dm = DeviceMesh(pts, conn, np.zeros(E, dtype=np.int32), table, schedule=S)
     P = S.n_blocks
-    line = f"{v:14s} n_cta={S.n_cta} items={S.n_items} max_items={S.max_cta_items} max_el={S.max_cta_elems} slots={S.max_cta_slots} |"
+    line = (f"{v:16s} n_cta={S.n_cta} items={S.n_items} max_items={S.max_cta_items} max_el={S.max_cta_elems} slots={S.max_cta_slots} "
+            f"symbolic {t_sym:.2f}s bank {t_bank:.2f}s |")
     for ops, nnz in (("K", 13), ("MKD", 29)):
         out = dm.assemble(ops, 0.2, 0.2)
         for _ in range(3):

@@ -34,7 +34,7 @@ def main():
                        ["-c", os.path.join(B.CSRC, "tefem_assemble.cu"), "-o", obj], check=True)
         subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-shared", "-o", lib, obj] + others + ["-ldl"], check=True)
         libs[name] = os.path.relpath(lib, ROOT)
-    runs = ["echo == default; python tools/asm_ab.py 100 512,620,8,1",
+    runs = ["echo == default and bank-aware numberings; python tools/asm_ab.py 100 512,620,8,1 512,620,8,1,1 512,620,8,1,2 512,620,8,1,3",
             "echo == 128 threads; TEFEM_ASM_THREADS=128 python tools/asm_ab.py 100 256,310,8,1 384,465,8,1",
             "echo == 64 threads; TEFEM_ASM_THREADS=64 python tools/asm_ab.py 100 128,160,8,1 192,235,8,1 256,310,8,1"]
     for name, lib in libs.items():

@@ -23,14 +23,46 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace tefem {
 
 namespace {
 
-enum { H_NITEMS = 0, H_NELEMS = 1, H_OITEMS = 5, H_OELEMS = 6, H_OINC = 7, H_NPIECE = 11, HDR_STRIDE = 12 };
+enum { H_NITEMS = 0, H_NELEMS = 1, H_NINC = 2, H_OITEMS = 5, H_OELEMS = 6, H_OINC = 7, H_NPIECE = 11, HDR_STRIDE = 12 };
+
+// Tiles with the same items and incidence entries (structured meshes repeat a few hundred tile patterns) share one search:
+// FNV-1a over the tile's item and incidence segments; a hit is verified byte by byte before its numbering is copied.
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+struct TileKey {
+    const int32_t* hdr;
+    const int32_t* item_inc;
+    const int32_t* item_meta;
+    const uint16_t* inc;
+    uint64_t hash() const {
+        uint64_t h = 1469598103934665603ull;
+        const int32_t dims[4] = {hdr[H_NITEMS], hdr[H_NELEMS], hdr[H_NINC], hdr[H_NPIECE]};
+        h = fnv1a(h, dims, sizeof(dims));
+        h = fnv1a(h, item_inc + hdr[H_OITEMS], sizeof(int32_t) * (size_t)hdr[H_NITEMS]);
+        h = fnv1a(h, item_meta + hdr[H_OITEMS], sizeof(int32_t) * (size_t)hdr[H_NITEMS]);
+        return fnv1a(h, inc + hdr[H_OINC], sizeof(uint16_t) * (size_t)hdr[H_NINC]);
+    }
+    bool same(const TileKey& o) const {
+        return hdr[H_NITEMS] == o.hdr[H_NITEMS] && hdr[H_NELEMS] == o.hdr[H_NELEMS] && hdr[H_NINC] == o.hdr[H_NINC] &&
+               hdr[H_NPIECE] == o.hdr[H_NPIECE] &&
+               memcmp(item_inc + hdr[H_OITEMS], o.item_inc + o.hdr[H_OITEMS], sizeof(int32_t) * (size_t)hdr[H_NITEMS]) == 0 &&
+               memcmp(item_meta + hdr[H_OITEMS], o.item_meta + o.hdr[H_OITEMS], sizeof(int32_t) * (size_t)hdr[H_NITEMS]) == 0 &&
+               memcmp(inc + hdr[H_OINC], o.inc + o.hdr[H_OINC], sizeof(uint16_t) * (size_t)hdr[H_NINC]) == 0;
+    }
+};
 
 struct PairW {
     int32_t other;
@@ -214,16 +246,41 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
     if (n_threads <= 0) n_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 64u);
     n_threads = std::min(n_threads, std::max(1, n_cta));
     std::atomic<int32_t> next{0};
-    std::atomic<int64_t> before{0}, after{0};
+    std::atomic<int64_t> before{0}, after{0}, searched{0};
+    struct Done { int32_t tile; int64_t cb, ca; };
+    std::unordered_map<uint64_t, Done> done;       // hash -> a finished tile with that content
+    std::mutex done_mutex;
     auto worker = [&]() {
         for (;;) {
             const int32_t c = next.fetch_add(1);
             if (c >= n_cta) break;
             const int32_t* hdr = h_cta_hdr + (size_t)HDR_STRIDE * c;
+            const TileKey key = {hdr, h_item_inc, h_item_meta, h_inc};
+            const uint64_t h = key.hash();
+            Done rep = {-1, 0, 0};
+            {
+                std::lock_guard<std::mutex> lock(done_mutex);
+                auto it = done.find(h);
+                if (it != done.end()) rep = it->second;
+            }
+            if (rep.tile >= 0) {
+                const int32_t* rhdr = h_cta_hdr + (size_t)HDR_STRIDE * rep.tile;
+                const TileKey rkey = {rhdr, h_item_inc, h_item_meta, h_inc};
+                if (key.same(rkey)) {   // the finished tile's numbering is read-only from now on
+                    memcpy(h_new_local + hdr[H_OELEMS], h_new_local + rhdr[H_OELEMS], sizeof(int32_t) * (size_t)hdr[H_NELEMS]);
+                    h_n_slots[c] = hdr[H_NELEMS];
+                    before.fetch_add(rep.cb);
+                    after.fetch_add(rep.ca);
+                    continue;
+                }
+            }
             int64_t cb = 0, ca = 0;
             h_n_slots[c] = optimise_tile(hdr, h_item_inc, h_item_meta, h_inc, strides, n_sweeps, h_new_local + hdr[H_OELEMS], &cb, &ca);
             before.fetch_add(cb);
             after.fetch_add(ca);
+            searched.fetch_add(1);
+            std::lock_guard<std::mutex> lock(done_mutex);
+            done.emplace(h, Done{c, cb, ca});
         }
     };
     std::vector<std::thread> pool;
@@ -231,5 +288,8 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
     worker();
     for (std::thread& t : pool) t.join();
     if (h_cost) { h_cost[0] = before.load(); h_cost[1] = after.load(); }
+    if (getenv("TEFEM_SCHEDULE_VERBOSE"))
+        fprintf(stderr, "[tefem schedule] bank numbering: %lld of %d tiles searched, the others share a pattern\n",
+                (long long)searched.load(), (int)n_cta);
     return TEFEM_OK;
 }

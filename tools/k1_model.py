@@ -7,7 +7,8 @@ loaded of the 16 eight-byte banks (equal addresses are a broadcast).  Output: wa
 lane fill, and the conflict-free bound - the quantities profiles/README.md compares with ncu's
 l1tex__data_pipe_lsu_wavefronts_mem_shared.
 
-usage: python tools/k1_model.py [cells] [variant ...]   variant = items,budget,chunk[,pieces_first]
+usage: python tools/k1_model.py [cells] [variant ...]   variant = items,budget,chunk[,pieces_first[,bank_opt]]
+(bank_opt: 0 = staged order, 1 = symbolic.optimize_banks for both record strides, 2 = stride 17 only, 3 = stride 13 only)
 """
 import os
 import sys
@@ -130,7 +131,10 @@ if __name__ == "__main__":
         kw = dict(items_per_cta=f[0], elem_budget=f[1], max_chunk=f[2])
         if len(f) > 3:
             kw["pieces_first"] = bool(f[3])
-        S = build_schedule(conn, N, **kw)
+        S = build_schedule(conn, N, bank_opt=False, **kw)
+        if len(f) > 4 and f[4]:
+            from thermoelasticity_fem_b200.symbolic import optimize_banks
+            S = optimize_banks(S, strides={1: 3, 2: 2, 3: 1}[f[4]])
         staged = int(S.cta_hdr[:, 1].sum())
         tiles = range(S.n_cta // 2, min(S.n_cta, S.n_cta // 2 + 40))
         for rs in (13, 17):

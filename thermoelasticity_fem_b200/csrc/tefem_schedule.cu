@@ -103,7 +103,7 @@ void add_pair(std::vector<PairW>& list, int16_t& slot, int32_t other, const int*
 
 // One tile: returns the new local number of every staged element in new_local[0 .. n_el) and the number of record slots.
 int optimise_tile(const int32_t* hdr, const int32_t* item_inc, const int32_t* item_meta, const uint16_t* inc, int strides,
-                  int n_sweeps, int32_t* new_local, int64_t* cost_before, int64_t* cost_after) {
+                  int n_sweeps, int block_size, int32_t* new_local, int64_t* cost_before, int64_t* cost_after) {
     const int n_items = hdr[H_NITEMS], n_el = hdr[H_NELEMS], n_piece = hdr[H_NPIECE];
     const int32_t* it_inc = item_inc + hdr[H_OITEMS];
     const int32_t* it_meta = item_meta + hdr[H_OITEMS];
@@ -173,7 +173,8 @@ int optimise_tile(const int32_t* hdr, const int32_t* item_inc, const int32_t* it
     // phase 1 cost what they cost before (an unconstrained re-numbering would scatter the elements a half-warp stages:
     // modelled +2.4 wavefronts per element in phase 1, half of the gain).
     T.cls.resize(n_el);
-    for (int i = 0; i < n_el; ++i) T.cls[i] = i & 15;
+    std::vector<int32_t> pos(n_el);                        // new local number of staged element i
+    for (int i = 0; i < n_el; ++i) { pos[i] = i; T.cls[i] = i & 15; }
     auto total_cost = [&]() {
         int64_t c = 0;
         for (int i = 0; i < n_el; ++i)
@@ -185,17 +186,20 @@ int optimise_tile(const int32_t* hdr, const int32_t* item_inc, const int32_t* it
         return slot ? T.nbr[i][slot - 1].w : nullptr;
     };
     if (cost_before) *cost_before = total_cost();
+    const int BS = block_size;                             // 16: phase 1 untouched; 32 / 64: its half-warps exchange neighbours
+    std::vector<int64_t> C((size_t)BS * 16);
     for (int sweep = 0; sweep < n_sweeps; ++sweep) {
         int swaps = 0;
-        for (int b0 = 0; b0 < n_el; b0 += 16) {
-            const int nb = std::min(16, n_el - b0);
-            for (int round = 0; round < 8; ++round) {
-                int64_t C[16][16];   // C[m][r]: collisions of member m if it were in class r (others fixed)
+        for (int b0 = 0; b0 < n_el; b0 += BS) {
+            const int nb = std::min(BS, n_el - b0);
+            for (int round = 0; round < 8 * (BS / 16); ++round) {
+                // C[m][r]: collisions of member m if it were in class r (others fixed)
                 for (int m = 0; m < nb; ++m) {
-                    for (int r = 0; r < 16; ++r) C[m][r] = 0;
+                    int64_t* c = &C[(size_t)m * 16];
+                    for (int r = 0; r < 16; ++r) c[r] = 0;
                     for (const PairW& p : T.nbr[b0 + m]) {
                         const int rf = T.cls[p.other];
-                        for (int d = 0; d < 16; ++d) C[m][(d + rf) & 15] += p.w[d];
+                        for (int d = 0; d < 16; ++d) c[(d + rf) & 15] += p.w[d];
                     }
                 }
                 int64_t best = 0;
@@ -203,7 +207,8 @@ int optimise_tile(const int32_t* hdr, const int32_t* item_inc, const int32_t* it
                 for (int x = 0; x < nb; ++x)
                     for (int y = x + 1; y < nb; ++y) {
                         const int i = b0 + x, j = b0 + y, ri = T.cls[i], rj = T.cls[j];
-                        int64_t delta = C[x][rj] - C[x][ri] + C[y][ri] - C[y][rj];
+                        if (ri == rj) continue;
+                        int64_t delta = C[(size_t)x * 16 + rj] - C[(size_t)x * 16 + ri] + C[(size_t)y * 16 + ri] - C[(size_t)y * 16 + rj];
                         const int32_t* w = mutual(i, j);
                         if (w) {
                             // C[x][rj] assumed j stays in rj (difference 0), C[y][ri] likewise; after the swap the pair sits at
@@ -214,15 +219,15 @@ int optimise_tile(const int32_t* hdr, const int32_t* item_inc, const int32_t* it
                     }
                 if (bi < 0) break;
                 std::swap(T.cls[bi], T.cls[bj]);
+                std::swap(pos[bi], pos[bj]);
                 swaps += 1;
             }
         }
         if (swaps == 0) break;
     }
     if (cost_after) *cost_after = total_cost();
-    // ---- new local number: block base + class (a permutation inside every block of 16; a last partial block keeps classes
-    // below its size because only its own members' classes are exchanged)
-    for (int i = 0; i < n_el; ++i) new_local[i] = (i & ~15) + T.cls[i];
+    // ---- new local numbers: a permutation of the positions inside every block
+    for (int i = 0; i < n_el; ++i) new_local[i] = pos[i];
     return n_el;
 }
 
@@ -243,6 +248,9 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
                                              int n_threads, int32_t* h_new_local, int32_t* h_n_slots, int64_t* h_cost) {
     TEFEM_REQUIRE(h_cta_hdr && h_item_inc && h_item_meta && h_inc && h_new_local && h_n_slots, "null pointer");
     TEFEM_REQUIRE(n_cta >= 0 && (strides & 3) != 0 && n_sweeps >= 0, "arguments");
+    int block_size = 16;   // TEFEM_BANK_BLOCK = 16 | 32 | 64 (measurement knob: elements exchanged between the half-warps of phase 1)
+    if (const char* e = getenv("TEFEM_BANK_BLOCK")) block_size = atoi(e);
+    TEFEM_REQUIRE(block_size == 16 || block_size == 32 || block_size == 64, "TEFEM_BANK_BLOCK must be 16, 32 or 64");
     if (n_threads <= 0) n_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 64u);
     n_threads = std::min(n_threads, std::max(1, n_cta));
     std::atomic<int32_t> next{0};
@@ -275,7 +283,7 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
                 }
             }
             int64_t cb = 0, ca = 0;
-            h_n_slots[c] = optimise_tile(hdr, h_item_inc, h_item_meta, h_inc, strides, n_sweeps, h_new_local + hdr[H_OELEMS], &cb, &ca);
+            h_n_slots[c] = optimise_tile(hdr, h_item_inc, h_item_meta, h_inc, strides, n_sweeps, block_size, h_new_local + hdr[H_OELEMS], &cb, &ca);
             before.fetch_add(cb);
             after.fetch_add(ca);
             searched.fetch_add(1);

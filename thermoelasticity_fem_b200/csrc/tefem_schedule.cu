@@ -258,10 +258,12 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
     struct Done { int32_t tile; int64_t cb, ca; };
     std::unordered_map<uint64_t, Done> done;       // hash -> a finished tile with that content
     std::mutex done_mutex;
+    std::atomic<int> failed{0};
     auto worker = [&]() {
+        try {
         for (;;) {
             const int32_t c = next.fetch_add(1);
-            if (c >= n_cta) break;
+            if (c >= n_cta || failed.load()) break;
             const int32_t* hdr = h_cta_hdr + (size_t)HDR_STRIDE * c;
             const TileKey key = {hdr, h_item_inc, h_item_meta, h_inc};
             const uint64_t h = key.hash();
@@ -290,11 +292,24 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
             std::lock_guard<std::mutex> lock(done_mutex);
             done.emplace(h, Done{c, cb, ca});
         }
+        } catch (...) {   // out of memory in a worker: report, the caller keeps the staged order
+            failed.store(1);
+        }
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+    for (int t = 1; t < n_threads; ++t) {
+        try {
+            pool.emplace_back(worker);
+        } catch (...) {   // thread limit of the container: go on with the threads that started
+            break;
+        }
+    }
     worker();
     for (std::thread& t : pool) t.join();
+    if (failed.load()) {
+        set_error("bank numbering: a worker failed (out of memory?)");
+        return TEFEM_ERR_INVALID;
+    }
     if (h_cost) { h_cost[0] = before.load(); h_cost[1] = after.load(); }
     if (getenv("TEFEM_SCHEDULE_VERBOSE"))
         fprintf(stderr, "[tefem schedule] bank numbering: %lld of %d tiles searched, the others share a pattern\n",

@@ -241,7 +241,14 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                                 ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
                                 pieces_first, tile_cost)
             if S.smem_bytes() <= MAX_SMEM_BYTES:            # the kernel would refuse the launch: smaller tiles
-                return optimize_banks(S) if (BANK_OPT if bank_opt is None else bank_opt) else S
+                if not (BANK_OPT if bank_opt is None else bank_opt):
+                    return S
+                try:
+                    return optimize_banks(S)
+                except Exception as exc:                    # an optimisation, not a requirement: keep the staged order
+                    import warnings
+                    warnings.warn(f"bank-aware numbering skipped: {exc}")
+                    return S
         except _TileTooLarge:
             pass
         items_per_cta = max(16, (3 * items_per_cta) // 4)

@@ -155,8 +155,8 @@ def test_sandwich_schedule_and_emulated_assembly(sandwich, emu, aM, aK):
     S = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id))
     assert S.n_blocks == 39985
     if aM == 0.2:
-        S_inline = S if not S.pieces_first else build_schedule(torch.from_numpy(conn), pts.shape[0],
-                                                               mat_id=torch.from_numpy(mat_id), pieces_first=False)
+        S_inline = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=False,
+                                  pitch=False)       # the invariants below describe the packed lists (block_inc)
         check_schedule_invariants(S_inline, conn, pts.shape[0], mat_id=mat_id)
     vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", aM, aK)
     assert bad[0] == 2 ** 31 - 1 and bad[1] == 2 ** 31 - 1
@@ -192,7 +192,9 @@ def test_kuhn_multimaterial_and_bad_jacobian(emu):
         S = build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items, elem_budget=max(160, items),
                            max_chunk=chunk, mat_id=torch.from_numpy(mat_id), pieces_first=pf)
         if not pf:
-            check_schedule_invariants(S, conn, pts.shape[0], chunk, mat_id=mat_id)
+            check_schedule_invariants(build_schedule(torch.from_numpy(conn), pts.shape[0], items_per_cta=items,
+                                                     elem_budget=max(160, items), max_chunk=chunk, mat_id=torch.from_numpy(mat_id),
+                                                     pieces_first=False, pitch=False), conn, pts.shape[0], chunk, mat_id=mat_id)
         vals, bad = emu_assemble(emu, S, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
         ops = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)
         A = planes_to_csc(vals["K"], layout.plane_map_K(), S, 4 * pts.shape[0])
@@ -299,9 +301,9 @@ def test_pieces_first_layout_is_bitwise_the_inline_layout(sandwich, emu, mesh_ki
         variants = [dict(), dict(items_per_cta=64, elem_budget=160, max_chunk=3), dict(items_per_cta=700, elem_budget=800, max_chunk=6)]
     for kw in variants:
         S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=False,
-                            bank_opt=False, **kw)
+                            bank_opt=False, pitch=False, **kw)
         S1 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=True,
-                            tile_cost='items', bank_opt=False, **kw)
+                            tile_cost='items', bank_opt=False, pitch=False, **kw)
         check_pieces_first_invariants(S1, S0)
         S2 = build_schedule(torch.from_numpy(conn), pts.shape[0], mat_id=torch.from_numpy(mat_id), pieces_first=True, **kw)
         assert S2.n_cta <= S1.n_cta            # default tile cost of this layout: blocks per tile (the block-order pass)
@@ -447,3 +449,47 @@ def test_bank_aware_numbering_keeps_the_values_bitwise(emu, pf):
         r1, r2 = k1_model.model(S, 17 if with_d else 13, with_d, True), k1_model.model(S2, 17 if with_d else 13, with_d, True)
         assert r2["wavefronts"] < 0.93 * r1["wavefronts"] and r2["ideal"] == r1["ideal"]
     assert k1_model.model_phase1(S2)["wavefronts"] == k1_model.model_phase1(S)["wavefronts"]   # phase 1 is untouched
+
+
+
+@pytest.mark.parametrize("pf", [True, False])
+def test_fixed_pitch_lists_keep_the_values_bitwise(emu, pf):
+    """symbolic.pitch_lists: every list is moved to a multiple of the pitch (6 entries for blocks, 10 for pieces), entry by
+    entry unchanged; the emulated assembly is bitwise the same and the start words of 32 consecutive items hit 32 different
+    four-byte banks."""
+    pts, tets, tris, nodes = kuhn_box(8, 7, 7, jitter=0.1, seed=6)
+    mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+            3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    conn, mat_id, rows = orc.element_table(tets, mats)
+    common = dict(mat_id=torch.from_numpy(mat_id), pieces_first=pf, bank_opt=False)
+    S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], pitch=False, **common)
+    S1 = build_schedule(torch.from_numpy(conn), pts.shape[0], pitch=True, **common)
+    assert S1.lists_pitched and not S0.lists_pitched and S1.max_cta_inc > S0.max_cta_inc and S1.smem_bytes() <= 220 * 1024
+    H0, H1 = S0.cta_hdr.numpy().astype(np.int64), S1.cta_hdr.numpy().astype(np.int64)
+    keep = [c for c in range(12) if c not in (2, 7)]                    # everything but n_inc / o_inc
+    assert np.array_equal(H0[:, keep], H1[:, keep]) and torch.equal(S0.item_meta, S1.item_meta)
+    i0, i1 = S0.item_inc.numpy().astype(np.int64) & 0xFFFFFFFF, S1.item_inc.numpy().astype(np.int64) & 0xFFFFFFFF
+    assert np.array_equal(i0 >> 16, i1 >> 16)
+    inc0, inc1 = S0.inc.numpy(), S1.inc.numpy()
+    meta = S0.item_meta.numpy().astype(np.int64) & 0xFFFFFFFF
+    for c in range(S0.n_cta):
+        n_it, o_it, n_piece = H0[c, 0], H0[c, 5], H0[c, 11]
+        assert H1[c, 7] % 8 == 0 and H1[c, 2] <= S1.max_cta_inc
+        for k in range(n_it):
+            ln = meta[o_it + k] & 0xff
+            if pf and k >= n_piece and ((meta[o_it + k] >> 8) & 0xffff) != 0:
+                continue                                                 # combine item: no list
+            a, b = H0[c, 7] + (i0[o_it + k] & 0xffff), H1[c, 7] + (i1[o_it + k] & 0xffff)
+            assert np.array_equal(inc0[a:a + ln], inc1[b:b + ln])
+            base = 0 if k < n_piece else (i1[o_it + n_piece] & 0xffff)       # the block pass starts behind the pieces' slots
+            assert ((i1[o_it + k] & 0xffff) - base) % (10 if k < n_piece else 6) == 0 and (i1[o_it + k] & 0xffff) + ln <= H1[c, 2]
+        lo = n_piece if pf else 0
+        sl = slice(o_it + lo, o_it + min(n_it, lo + 32))                   # the first warp of the block pass
+        starts, lens = i1[sl] & 0xffff, meta[sl] & 0xff
+        gathers = ~(((meta[sl] >> 8) & 0xffff) != 0) if pf else np.ones(lens.size, dtype=bool)     # combine items load nothing
+        if np.all(lens[gathers] <= 6):                                     # one slot each: consecutive multiples of 3 words
+            assert np.unique((starts[gathers] >> 1) % 32).size == int(gathers.sum())
+    v0, _ = emu_assemble(emu, S0, pts, conn, mat_id, rows, "MKD", 0.2, 0.1)
+    v1, _ = emu_assemble(emu, S1, pts, conn, mat_id, rows, "MKD", 0.2, 0.1)
+    for nm in "MKD":
+        assert np.array_equal(v0[nm], v1[nm]), nm

@@ -52,6 +52,9 @@ PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "1") == "1"
 # -22 % / -15 % gather wavefronts; it was built after the round's GPU budget was spent, so the first measurement is the
 # round-end bench.  TEFEM_BANK_OPT=0 restores the numbering the committed ncu captures were taken with.
 BANK_OPT = os.environ.get("TEFEM_BANK_OPT", "1") == "1"
+# Fixed-pitch placement of the incidence lists (pitch_lists): same status - values untouched, kernel untouched, modelled
+# 1.7 -> 0.7 wavefronts per element for the 2-byte entry loads.  TEFEM_PITCH_LISTS=0 keeps the packed lists.
+PITCH_LISTS = os.environ.get("TEFEM_PITCH_LISTS", "1") == "1"
 HDR_STRIDE = 12
 H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)
 
@@ -88,6 +91,7 @@ class Schedule:
     split_meta: torch.Tensor     # int32 [padded]
     pieces_first: bool = False   # item layout of the tiles (build_schedule)
     bank_optimized: bool = False # staged elements renumbered per tile by optimize_banks
+    lists_pitched: bool = False  # incidence lists re-placed at a fixed pitch by pitch_lists (block_inc is then stale)
 
     def to(self, device):
         kw = {}
@@ -120,6 +124,63 @@ class Schedule:
         """Bytes of slot-map / schedule data one assembly launch reads (cta_xyz is counted by DeviceMesh)."""
         return sum(t.numel() * t.element_size() for t in
                    (self.inc, self.cta_hdr, self.cta_conn8, self.item_inc, self.item_meta, self.split_block, self.split_meta))
+
+
+def pitch_lists(S: "Schedule", pitch_blocks: int = 6, pitch_pieces: int = 10) -> "Schedule":
+    """Re-places the incidence lists of every tile at a fixed pitch: item k of a pass starts at entry pitch * (slots before it),
+    a list longer than the pitch takes several slots.  The kernel reads its entries as 2-byte shared-memory loads,
+    lane l at inc[start_l + step]: with the lists packed back to back the 32 start words of a warp fall into ~12 of the 32
+    four-byte banks (ncu: 1.8 wavefronts per element for these loads, 0.8 conflict-free); with a pitch of 3 (blocks: 6
+    entries) or 5 (pieces: 10 entries) words - both odd, hence invertible modulo 32 - the start words of 32 consecutive items
+    hit 32 different banks at every step.  Costs ~20 % more incidence entries per tile (2 bytes each); items, lists, their
+    order and the values are unchanged - only item_inc's start field, the incidence array and its segment sizes change."""
+    dev = S.cta_hdr.device
+    n_cta = S.n_cta
+    if n_cta == 0 or S.lists_pitched:
+        return S
+    i64 = dict(dtype=torch.int64, device=dev)
+    H = S.cta_hdr.to(torch.int64)
+    n_it, o_it, n_inc, o_inc, n_piece = (H[:, k].contiguous() for k in (H_NITEMS, H_OITEMS, H_NINC, H_OINC, H_NPIECE))
+    tot_items = int(n_it.sum().item())
+    tile_of_item = torch.repeat_interleave(torch.arange(n_cta, **i64), n_it)
+    rank = torch.arange(tot_items, **i64) - (torch.cumsum(n_it, 0) - n_it)[tile_of_item]      # item index inside its tile
+    pos = o_it[tile_of_item] + rank                                                          # position in the padded item arrays
+    inc_word = S.item_inc[pos].to(torch.int64) & 0xFFFFFFFF
+    meta = S.item_meta[pos].to(torch.int64) & 0xFFFFFFFF
+    start = inc_word & 0xFFFF
+    length = meta & 0xFF
+    is_piece = rank < n_piece[tile_of_item]
+    if S.pieces_first:                                   # combine items (block pass, slot field set) carry a piece count, no list
+        length = torch.where(~is_piece & (((meta >> 8) & 0xFFFF) != 0), torch.zeros_like(length), length)
+    pitch = torch.where(is_piece, torch.full_like(length, pitch_pieces), torch.full_like(length, pitch_blocks))
+    take = torch.div(length + pitch - 1, pitch, rounding_mode='floor') * pitch
+    csum = torch.cumsum(take, 0) - take
+    tile_first = (torch.cumsum(n_it, 0) - n_it).clamp(max=max(tot_items - 1, 0))
+    new_start = csum - csum[tile_first][tile_of_item]
+    new_n_inc = torch.zeros(n_cta, **i64).index_add_(0, tile_of_item, take)
+    if int(new_n_inc.max().item()) >= 65536:
+        return S                                         # start offsets are 16-bit: keep the packed lists
+    padded = torch.div(new_n_inc + 7, 8, rounding_mode='floor') * 8
+    new_o_inc = torch.cumsum(padded, 0) - padded
+    # ---- move the entries: entry k of item i goes from o_inc + start + k to new_o_inc + new_start + k
+    tot_ent = int(length.sum().item())
+    item_of_ent = torch.repeat_interleave(torch.arange(tot_items, **i64), length)
+    k = torch.arange(tot_ent, **i64) - (torch.cumsum(length, 0) - length)[item_of_ent]
+    t_ent = tile_of_item[item_of_ent]
+    src = o_inc[t_ent] + start[item_of_ent] + k
+    dst = new_o_inc[t_ent] + new_start[item_of_ent] + k
+    new_inc = torch.zeros(int(padded.sum().item()) + 8, dtype=S.inc.dtype, device=dev)
+    new_inc[dst] = S.inc[src]
+    new_item_inc = S.item_inc.clone()
+    w = (inc_word & ~0xFFFF) | new_start
+    new_item_inc[pos] = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(S.item_inc.dtype)
+    new_hdr = S.cta_hdr.clone()
+    new_hdr[:, H_NINC] = new_n_inc.to(new_hdr.dtype)
+    new_hdr[:, H_OINC] = new_o_inc.to(new_hdr.dtype)
+    assert int(new_o_inc[-1].item()) + int(padded[-1].item()) < 2 ** 31
+    kw = dict(S.__dict__)
+    kw.update(cta_hdr=new_hdr, item_inc=new_item_inc, inc=new_inc, max_cta_inc=int(new_n_inc.max().item()), lists_pitched=True)
+    return Schedule(**kw)
 
 
 def optimize_banks(S: "Schedule", strides: int = 3, n_sweeps: int = 3, n_threads: int = 0, return_cost: bool = False,
@@ -210,7 +271,7 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                    items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA,
                    max_chunk: int = MAX_CHUNK, mat_id: torch.Tensor = None,
                    item_sort_window: int = None, pieces_first: bool = None, tile_cost: str = None,
-                   bank_opt: bool = None) -> Schedule:
+                   bank_opt: bool = None, pitch: bool = None) -> Schedule:
     """conn: integer tensor [E, 4] in the reference's element order; node numbers < n_nodes.
     n_rows: only rows of nodes < n_rows are assembled (row-partitioned multi-GPU: owned nodes
     are numbered first); default all.
@@ -223,6 +284,7 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     pieces, synchronises, then the block items: warps hold lists of similar length (the diagonal chunks no longer
     sit between the short off-diagonal lists) and EVERY block is stored by the thread at its block-order position
     (no scattered stores of the combined blocks).  Same chunks, same summation order: bitwise the same values.
+    pitch: re-place the incidence lists at a fixed pitch (pitch_lists; default PITCH_LISTS).
     bank_opt: renumber the staged elements of every tile so that the kernel's shared-memory gathers hit fewer bank conflicts
     (optimize_banks; default BANK_OPT).
     tile_cost: what `items_per_cta` bounds - 'items' (all work items of the tile's rows; default of the inline layout)
@@ -241,6 +303,8 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                                 ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
                                 pieces_first, tile_cost)
             if S.smem_bytes() <= MAX_SMEM_BYTES:            # the kernel would refuse the launch: smaller tiles
+                if (PITCH_LISTS if pitch is None else pitch):
+                    S = pitch_lists(S)
                 if not (BANK_OPT if bank_opt is None else bank_opt):
                     return S
                 try:

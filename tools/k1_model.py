@@ -7,8 +7,9 @@ loaded of the 16 eight-byte banks (equal addresses are a broadcast).  Output: wa
 lane fill, and the conflict-free bound - the quantities profiles/README.md compares with ncu's
 l1tex__data_pipe_lsu_wavefronts_mem_shared.
 
-usage: python tools/k1_model.py [cells] [variant ...]   variant = items,budget,chunk[,pieces_first[,bank_opt]]
-(bank_opt: 0 = staged order, 1 = symbolic.optimize_banks for both record strides, 2 = stride 17 only, 3 = stride 13 only)
+usage: python tools/k1_model.py [cells] [variant ...]   variant = items,budget,chunk[,pieces_first[,bank_opt[,pitch]]]
+(bank_opt: 0 = staged order, 1 = symbolic.optimize_banks for both record strides, 2 = stride 17 only, 3 = stride 13 only;
+pitch: 1 = symbolic.pitch_lists, 0 = lists packed back to back)
 """
 import os
 import sys
@@ -97,6 +98,46 @@ def model(S, rec_stride=13, with_d=False, skip_equal_ab=False, tiles=None):
     return dict(wavefronts=tot_w, ideal=tot_ideal / 16.0, lane_steps=lane_steps, warp_steps=warp_steps, blocks=n_blocks)
 
 
+def model_entry_loads(S, tiles=None):
+    """Shared-memory wavefronts of the 2-byte incidence-entry loads (lane l reads inc[start_l + step]; 32 lanes, 32
+    four-byte banks, equal words are a broadcast)."""
+    H = S.cta_hdr.numpy().astype(np.int64)
+    ii = S.item_inc.numpy().astype(np.int64) & 0xFFFFFFFF
+    im = S.item_meta.numpy().astype(np.int64) & 0xFFFFFFFF
+    tot = 0
+    for c in (range(S.n_cta) if tiles is None else tiles):
+        n_it, o_it, n_piece = H[c, 0], H[c, 5], H[c, 11]
+        start = ii[o_it:o_it + n_it] & 0xffff
+        ln = im[o_it:o_it + n_it] & 0xff
+        if n_piece > 0:
+            slot = (im[o_it:o_it + n_it] >> 8) & 0xffff
+            combine = np.zeros(n_it, dtype=bool)
+            combine[n_piece:] = slot[n_piece:] != 0
+            ln = np.where(combine, 0, ln)
+        for lo, hi in ([(0, n_piece), (n_piece, n_it)] if n_piece > 0 else [(0, n_it)]):
+            n = hi - lo
+            if n <= 0:
+                continue
+            npad = -(-n // 32) * 32
+            st = np.zeros(npad, dtype=np.int64)
+            le = np.zeros(npad, dtype=np.int64)
+            st[:n], le[:n] = start[lo:hi], ln[lo:hi]
+            st, le = st.reshape(-1, 32), le.reshape(-1, 32)
+            wmax = le.max(axis=1)
+            for k in range(int(wmax.max())):
+                aw = wmax > k
+                act = (le > k) & aw[:, None]
+                word = np.where(act, (st + k) >> 1, -1 - np.arange(32)[None, :])[aw]
+                srt = np.sort(word, axis=1)
+                first = np.ones_like(srt, dtype=bool)
+                first[:, 1:] = srt[:, 1:] != srt[:, :-1]
+                bank = np.where(first & (srt >= 0), srt % 32, 32)
+                load = np.zeros((srt.shape[0], 33), dtype=np.int64)
+                np.add.at(load, (np.repeat(np.arange(srt.shape[0]), 32), bank.reshape(-1)), 1)
+                tot += int(load[:, :32].max(axis=1).sum())
+    return tot
+
+
 def model_phase1(S, rec_stride=13, tiles=None):
     """Shared-memory wavefronts of phase 1 (thread le -> staged element le): 12 coordinate loads gathered by tile-local
     node (xyz[3 * node + c]) and rec_stride record stores at le * rec_stride + k."""
@@ -131,12 +172,15 @@ if __name__ == "__main__":
         kw = dict(items_per_cta=f[0], elem_budget=f[1], max_chunk=f[2])
         if len(f) > 3:
             kw["pieces_first"] = bool(f[3])
-        S = build_schedule(conn, N, bank_opt=False, **kw)
+        S = build_schedule(conn, N, bank_opt=False, pitch=bool(f[5]) if len(f) > 5 else False, **kw)
         if len(f) > 4 and f[4]:
             from thermoelasticity_fem_b200.symbolic import optimize_banks
             S = optimize_banks(S, strides={1: 3, 2: 2, 3: 1}[f[4]])
         staged = int(S.cta_hdr[:, 1].sum())
         tiles = range(S.n_cta // 2, min(S.n_cta, S.n_cta // 2 + 40))
+        nb_t = sum(int((S.cta_hdr[c + 1, 10] if c + 1 < S.n_cta else S.n_blocks) - S.cta_hdr[c, 10]) for c in tiles)
+        print(f"{v:14s} incidence-entry loads: {model_entry_loads(S, tiles) / (nb_t / 2.5):.2f} wavefronts/elem "
+              f"(max entries per tile {S.max_cta_inc})", flush=True)
         for rs in (13, 17):
             r1 = model_phase1(S, rs, tiles)
             nb = sum(int((S.cta_hdr[c + 1, 10] if c + 1 < S.n_cta else S.n_blocks) - S.cta_hdr[c, 10]) for c in tiles)

@@ -463,7 +463,8 @@ def test_fixed_pitch_lists_keep_the_values_bitwise(emu, pf):
     conn, mat_id, rows = orc.element_table(tets, mats)
     common = dict(mat_id=torch.from_numpy(mat_id), pieces_first=pf, bank_opt=False)
     S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], pitch=False, **common)
-    S1 = build_schedule(torch.from_numpy(conn), pts.shape[0], pitch=True, **common)
+    from thermoelasticity_fem_b200.symbolic import pitch_lists
+    S1 = pitch_lists(S0, keep_occupancy=False)
     assert S1.lists_pitched and not S0.lists_pitched and S1.max_cta_inc > S0.max_cta_inc and S1.smem_bytes() <= 220 * 1024
     H0, H1 = S0.cta_hdr.numpy().astype(np.int64), S1.cta_hdr.numpy().astype(np.int64)
     keep = [c for c in range(12) if c not in (2, 7)]                    # everything but n_inc / o_inc

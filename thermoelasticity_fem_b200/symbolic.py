@@ -52,9 +52,13 @@ PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "1") == "1"
 # -22 % / -15 % gather wavefronts; it was built after the round's GPU budget was spent, so the first measurement is the
 # round-end bench.  TEFEM_BANK_OPT=0 restores the numbering the committed ncu captures were taken with.
 BANK_OPT = os.environ.get("TEFEM_BANK_OPT", "1") == "1"
-# Fixed-pitch placement of the incidence lists (pitch_lists): same status - values untouched, kernel untouched, modelled
-# 1.7 -> 0.7 wavefronts per element for the 2-byte entry loads.  TEFEM_PITCH_LISTS=0 keeps the packed lists.
-PITCH_LISTS = os.environ.get("TEFEM_PITCH_LISTS", "1") == "1"
+# Fixed-pitch placement of the incidence lists (pitch_lists): values untouched, kernel untouched, modelled 1.7 -> 0.7
+# wavefronts per element for the 2-byte entry loads - but ~20 % more entries per tile, and the default tiles leave only
+# 7.8 KB of shared memory before the fused M + D + K launch drops from two CTAs per SM to one (2 x (111.9 + 1) KB of 228 KB):
+# with the lists pitched the margin shrinks to < 1 KB.  OFF by default (TEFEM_PITCH_LISTS=1 enables); when enabled it is
+# skipped for schedules where it would cost a CTA per SM.
+PITCH_LISTS = os.environ.get("TEFEM_PITCH_LISTS", "0") == "1"
+SM_SMEM_BYTES = 228 * 1024     # shared memory of a B200 SM; every resident CTA reserves 1 KB of it
 HDR_STRIDE = 12
 H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)
 
@@ -126,14 +130,15 @@ class Schedule:
                    (self.inc, self.cta_hdr, self.cta_conn8, self.item_inc, self.item_meta, self.split_block, self.split_meta))
 
 
-def pitch_lists(S: "Schedule", pitch_blocks: int = 6, pitch_pieces: int = 10) -> "Schedule":
+def pitch_lists(S: "Schedule", pitch_blocks: int = 6, pitch_pieces: int = 10, keep_occupancy: bool = True) -> "Schedule":
     """Re-places the incidence lists of every tile at a fixed pitch: item k of a pass starts at entry pitch * (slots before it),
     a list longer than the pitch takes several slots.  The kernel reads its entries as 2-byte shared-memory loads,
     lane l at inc[start_l + step]: with the lists packed back to back the 32 start words of a warp fall into ~12 of the 32
     four-byte banks (ncu: 1.8 wavefronts per element for these loads, 0.8 conflict-free); with a pitch of 3 (blocks: 6
     entries) or 5 (pieces: 10 entries) words - both odd, hence invertible modulo 32 - the start words of 32 consecutive items
     hit 32 different banks at every step.  Costs ~20 % more incidence entries per tile (2 bytes each); items, lists, their
-    order and the values are unchanged - only item_inc's start field, the incidence array and its segment sizes change."""
+    order and the values are unchanged - only item_inc's start field, the incidence array and its segment sizes change.
+    keep_occupancy: return S unchanged when the larger segments would reduce the CTAs per SM of the fused launch."""
     dev = S.cta_hdr.device
     n_cta = S.n_cta
     if n_cta == 0 or S.lists_pitched:
@@ -180,7 +185,13 @@ def pitch_lists(S: "Schedule", pitch_blocks: int = 6, pitch_pieces: int = 10) ->
     assert int(new_o_inc[-1].item()) + int(padded[-1].item()) < 2 ** 31
     kw = dict(S.__dict__)
     kw.update(cta_hdr=new_hdr, item_inc=new_item_inc, inc=new_inc, max_cta_inc=int(new_n_inc.max().item()), lists_pitched=True)
-    return Schedule(**kw)
+    out = Schedule(**kw)
+
+    def ctas_per_sm(sched, margin):
+        return (SM_SMEM_BYTES - margin) // (sched.smem_bytes() + 1024)
+    if keep_occupancy and ctas_per_sm(out, 2048) < ctas_per_sm(S, 0):
+        return S                                         # the longer incidence segments would cost a resident CTA per SM
+    return out
 
 
 def optimize_banks(S: "Schedule", strides: int = 3, n_sweeps: int = 3, n_threads: int = 0, return_cost: bool = False,

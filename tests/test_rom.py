@@ -311,7 +311,8 @@ class _ScipyDeviceMesh:
             for c in range(4):
                 if plane_map[r, c] >= 0:
                     out[comp == r] += (vals.A[comp == r, :][:, comp == c] @ xv[comp == c])
-        y.copy_(torch.from_numpy(beta_y * y.numpy() + alpha * out))
+        base = 0.0 if beta_y == 0.0 else beta_y * y.numpy()     # like the kernel: y is not read when beta_y == 0 (may be uninitialised)
+        y.copy_(torch.from_numpy(base + alpha * out))
         return y
 
 

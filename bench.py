@@ -179,7 +179,7 @@ def run_tefem(args):
                     "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / hbm_peak}
         del out
     dm.check_jacobian()
-    asm["schedule"] = {"tiles": int(S.n_cta), "blocks_per_tile": int(S.max_cta_items - S.max_cta_slots) if S.pieces_first else int(S.max_cta_items),
+    asm["schedule"] = {"tiles": int(S.n_cta), "max_items_per_tile": int(S.max_cta_items), "max_pieces_per_tile": int(S.max_cta_slots),
                        "pieces_first": bool(S.pieces_first), "bank_aware_numbering": bool(S.bank_optimized),
                        "lists_pitched": bool(S.lists_pitched), "smem_bytes_per_cta": int(S.smem_bytes())}
 

@@ -130,6 +130,10 @@ int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int3
                    double* vals_M, double* vals_K, double* vals_D,
                    int32_t* bad_elem, void* stream);
 
+/* Threads per CTA of the pieces-first assembly kernel: 64, 128 or 256 (default; measurement knob - more, smaller CTAs per
+ * SM need tiles of 2 x threads items).  Host-side setting of the calling process; no reference counterpart.      */
+int tefem_assemble_set_threads(int threads);
+
 /* Bank-aware tile-local numbering of the staged elements of every tile (HOST function, all pointers are host pointers;
  * no reference counterpart - part of the symbolic phase).  The record of staged element e sits at rec[stride * e] in shared
  * memory, so e mod 16 decides the banks its gathers hit; for every pair of elements that the lanes of one half-warp read in
@@ -200,13 +204,22 @@ int tefem_solver_profile(tefem_solver* s, int enable, double* h_spmv_ms, int64_t
  * x vectors have n_rows owned node rows followed by n_halo halo node rows;
  * send: for each neighbour k, the owned node rows send_idx[send_ptr[k] .. send_ptr[k+1]) go to
  * rank h_nbr[k]; recv: halo rows [recv_ptr[k], recv_ptr[k+1]) (relative to n_rows) arrive from it.
- * n_interior_rows: rows [0, n_int) that reference no halo column are listed first in row_order
- * (so the interior product overlaps the exchange); row_order may be NULL (identity).            */
+ * PEER-MEMORY HALO (default; the communicator has vector slots, tefem_comm_vec_alloc): the SpMV input vectors of
+ * the solver live in the slots; before an SpMV a push kernel stores the boundary values straight into the halo
+ * tails of the neighbours' copies (remote stores over NVLink) and raises a flag, and the SpMV - ONE launch over
+ * all rows - waits for its neighbours' flags: no packing, no NCCL call, no second launch.  send_dst[k] /
+ * send_dpos[k] (device arrays, one per send entry): destination rank and node position in THAT rank's local
+ * vector (its n_rows + halo offset).  boundary_rows / interior_rows may be NULL.
+ * NCCL HALO (communicator without vector slots; kept as the measured alternative): pack kernel + grouped
+ * ncclSend/ncclRecv on a second stream overlapped with the interior rows, boundary rows in a second launch;
+ * needs the interior / boundary row lists, send_dst / send_dpos may be NULL.                                   */
 int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int32_t* h_nbr,
-                          const int32_t* h_send_ptr, const int32_t* send_idx,
-                          const int32_t* h_recv_ptr,
+                          const int32_t* h_send_ptr, const int32_t* send_idx, const int32_t* send_dst,
+                          const int32_t* send_dpos, const int32_t* h_recv_ptr,
                           const int32_t* boundary_rows, int32_t n_boundary_rows,
                           const int32_t* interior_rows, int32_t n_interior_rows);
+/* number of peer-memory vector slots a solver needs (tefem_comm_vec_alloc) */
+int tefem_solver_peer_slots(void);
 
 /* Aggregation-based coarse correction, used as the right preconditioner of tefem_bicgstab on top of the block-Jacobi
  * scaling: z = omega r + P1 M1(P1^T r) on the scaled system, with a replicated level 1 (one V-cycle with damped
@@ -237,6 +250,9 @@ int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, con
                          const float* inv2, double* work, void* comm);
 int tefem_precond_destroy(tefem_precond* pc);
 int tefem_precond_apply(tefem_precond* pc, const double* r, double* z, void* stream);
+/* Multi-GPU: agg_ranks[n_agg] (uint8 device array, bit r set iff rank r owns fine nodes of the aggregate) restricts the
+ * in-kernel all-reduce of the restricted residual to the ranks that contribute (the others hold exact zeros).      */
+int tefem_precond_set_agg_ranks(tefem_precond* pc, const uint8_t* agg_ranks);
 /* Attach (or detach with NULL) a preconditioner to the Krylov driver. */
 int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc);
 
@@ -293,7 +309,18 @@ int tefem_comm_allreduce_sum(tefem_comm* c, double* buf, int n, void* stream);
  * peer wait (call after a stream synchronisation; tefem_bicgstab does).                                          */
 int tefem_comm_shm_alloc(tefem_comm* c, int64_t big_cap_doubles, char* h_handle);
 int tefem_comm_shm_open(tefem_comm* c, const char* h_handles);
+/* A time-out marks the communicator failed: later waits return at once and tefem_comm_check keeps reporting it until
+ * tefem_comm_reset_error (after the ranks have been resynchronised).  tefem_comm_set_timeout: seconds a peer wait may
+ * spin (default 30).                                                                                               */
 int tefem_comm_check(tefem_comm* c);
+int tefem_comm_reset_error(tefem_comm* c);
+int tefem_comm_set_timeout(tefem_comm* c, double seconds);
+/* Peer-mapped vector slots: n_slots vectors of slot_doubles doubles (identical on all ranks; slot_doubles >= the
+ * largest 4 * (n_rows + n_halo) over the ranks), allocated by the library with cudaMalloc because they must be
+ * shareable over CUDA IPC - the one exception to "the caller owns every buffer".  Same handle exchange as above.
+ * Create them BEFORE tefem_solver_create: a solver of a communicator with slots keeps its SpMV input vectors there. */
+int tefem_comm_vec_alloc(tefem_comm* c, int n_slots, int64_t slot_doubles, char* h_handle);
+int tefem_comm_vec_open(tefem_comm* c, const char* h_handles);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,19 @@ def _worker(rank, world, port, result_dir):
         for k, recv in recv_bufs:
             x.reshape(-1, 4)[lp.n_own + lp.recv_ptr[k]: lp.n_own + lp.recv_ptr[k + 1]] = recv.numpy()
         assert np.array_equal(x, xg[dof_loc])                           # halo values are the owners' values
+        # peer-memory halo (distributed.halo_destinations): entry k of my send list lands at node dpos[k] of rank dst[k]
+        # - emulate the remote stores: every rank publishes (destination rank, position, global node id) and each rank
+        # checks that what lands in its halo tail is the node it expects there, and that the tail is covered exactly once
+        from thermoelasticity_fem_b200.distributed import halo_destinations
+        dst, dpos = halo_destinations(lp)
+        sent = [None] * world
+        dist.all_gather_object(sent, (dst, dpos, lp.local_nodes[lp.send_idx]))
+        landed = np.full(lp.n_local, -1, dtype=np.int64)
+        for d_, p_, g_ in sent:
+            mine_ = d_ == rank
+            assert np.all(landed[p_[mine_]] == -1)
+            landed[p_[mine_]] = g_[mine_]
+        assert np.all(landed[:lp.n_own] == -1) and np.array_equal(landed[lp.n_own:], lp.local_nodes[lp.n_own:])
         y = K_loc @ x
         y_ref = (Kg @ xg)[4 * lo:4 * hi]
         assert np.max(np.abs(y - y_ref)) <= 1e-13 * np.abs(y_ref).max()

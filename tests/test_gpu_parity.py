@@ -470,43 +470,24 @@ def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
     assert abs(np.abs(solver.X[3::4]).max() - float(g["maxTheta"])) < 1e-6 * float(g["maxTheta"])
 
 
-# ---- measurement knobs that are built and cross-compiled but were not yet run on a GPU when the round's budget ended: opt-in ----
-_EXPERIMENTAL = __import__("os").environ.get("TEFEM_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not _EXPERIMENTAL, reason="set TEFEM_EXPERIMENTAL=1 (unmeasured kernel variants)")
-@pytest.mark.parametrize("threads,items", [(128, 256), (64, 128)])
+# ---- measurement knobs of K1 -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("threads,items", [(256, 512), (128, 256), (64, 128)])
 def test_assembly_thread_count_variants_are_bitwise_the_default(threads, items):
-    """TEFEM_ASM_THREADS is read once per process: the variant runs in a subprocess and its planes must equal the default's."""
-    import os
-    import subprocess
-    import sys
-    import tempfile
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = f"""
-import sys, numpy as np, torch
-sys.path.insert(0, {root!r})
-from thermoelasticity_fem_b200 import LinearThermoElastic
-from thermoelasticity_fem_b200.device import DeviceMesh
-from thermoelasticity_fem_b200.symbolic import build_schedule
-from thermoelasticity_fem_b200.synthetic import kuhn_box
-pts, tets, tris, nodes = kuhn_box(24, 20, 18, 1., 1., 1., n_layers=1, index_dtype=np.int32)
-conn = tets[1]
-table = np.array([LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.).table_row()])
-S = build_schedule(torch.from_numpy(conn).cuda(), pts.shape[0], items_per_cta=int(sys.argv[2]), elem_budget=int(1.21 * int(sys.argv[2])))
-dm = DeviceMesh(pts, conn, np.zeros(conn.shape[0], dtype=np.int32), table, schedule=S)
-out = dm.assemble("MKD", 0.2, 0.2)
-np.savez(sys.argv[1], **{{k: v.cpu().numpy() for k, v in out.items()}})
-"""
-    with tempfile.TemporaryDirectory() as tmp:
-        paths = {}
-        for tag, env_threads in (("default", None), ("variant", threads)):
-            env = dict(os.environ)
-            env.pop("TEFEM_ASM_THREADS", None)
-            if env_threads is not None:
-                env["TEFEM_ASM_THREADS"] = str(env_threads)
-            paths[tag] = os.path.join(tmp, tag + ".npz")
-            subprocess.run([sys.executable, "-c", code, paths[tag], str(items if env_threads else 512)], check=True, env=env, timeout=300)
-        a, b = np.load(paths["default"]), np.load(paths["variant"])
-        for k in a.files:
-            assert np.array_equal(a[k], b[k]), k
+    """The tile-synchronous instantiations of K1 (256 / 128 / 64 threads per CTA, tefem_assemble_set_threads) must produce
+    the planes of the default - the dynamic-chunk kernel - bit for bit."""
+    import torch
+    from thermoelasticity_fem_b200 import LinearThermoElastic
+    from thermoelasticity_fem_b200.device import DeviceMesh
+    from thermoelasticity_fem_b200.symbolic import build_schedule
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(24, 20, 18, 1., 1., 1., n_layers=1, index_dtype=np.int32)
+    conn = tets[1]
+    table = np.array([LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.).table_row()])
+    outs = {}
+    for tag, nt, it in (("default", 0, 512), ("variant", threads, items)):
+        S = build_schedule(torch.from_numpy(conn).cuda(), pts.shape[0], items_per_cta=it, elem_budget=int(1.21 * it))
+        dm = DeviceMesh(pts, conn, np.zeros(conn.shape[0], dtype=np.int32), table, schedule=S)
+        dm.asm_threads = nt
+        outs[tag] = {k: v.cpu().numpy() for k, v in dm.assemble("MKD", 0.2, 0.2).items()}
+    for k in outs["default"]:
+        assert np.array_equal(outs["default"][k], outs["variant"][k]), k

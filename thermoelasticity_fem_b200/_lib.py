@@ -27,6 +27,7 @@ _SIGNATURES = {
     "tefem_element_matrices": [P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P],
     "tefem_assemble": [P, c_int, c_int32, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
                        P, P, P, P, P],
+    "tefem_assemble_set_threads": [c_int],
     "tefem_check_jacobian": [P, P, P],
     "tefem_schedule_bank_numbering": [c_int32, P, P, P, P, c_int, c_int, c_int, P, P, P],
     "tefem_planes_spmv": [P, P, c_int32, c_int64, P, P, P, c_double, c_double, P, P],
@@ -43,7 +44,8 @@ _SIGNATURES = {
                              P, P, P],
     "tefem_precond_destroy": [P],
     "tefem_precond_apply": [P, P, P, P],
-    "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, c_int32, P, c_int32],
+    "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, P, P, c_int32, P, c_int32],
+    "tefem_precond_set_agg_ranks": [P, P],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
     "tefem_newmark_correct": [c_int64, P, P, P, P, c_double, c_double, c_double, P, P],
@@ -56,6 +58,11 @@ _SIGNATURES = {
     "tefem_comm_shm_alloc": [P, c_int64, P],
     "tefem_comm_shm_open": [P, P],
     "tefem_comm_check": [P],
+    "tefem_comm_reset_error": [P],
+    "tefem_comm_set_timeout": [P, c_double],
+    "tefem_comm_vec_alloc": [P, c_int, c_int64, P],
+    "tefem_comm_vec_open": [P, P],
+    "tefem_solver_peer_slots": [],
 }
 _RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32]), "tefem_launch_count": (c_int64, []),
              "tefem_precond_work_doubles": (c_int64, [c_int32, c_int32])}

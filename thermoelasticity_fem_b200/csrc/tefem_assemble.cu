@@ -137,7 +137,7 @@ TEFEM_HD void store_block(const AssembleArgs& A, int32_t p, const typename AsmTr
 // constants applied once.
 template <int OPS, int DUU>
 TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta, const double* recs, const uint16_t* inc_s,
-                          double W4, const QuadS& S, const double* NN, typename AsmTraits<OPS, DUU>::Acc& acc) {
+                          double W4, const QuadS& S, const QuadNN& NN, typename AsmTraits<OPS, DUU>::Acc& acc) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Geom g;
     g.clear();
@@ -154,7 +154,7 @@ TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta
 // consecutive addresses of every plane) or park the values of a piece of a split block in its shared-memory slot.
 template <int OPS, int DUU>
 TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_word, int32_t meta, const double* recs,
-                           const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const double* NN) {
+                           const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const QuadNN& NN) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Acc acc;
     gather_item<OPS, DUU>(A, inc_word, meta, recs, inc_s, W4, S, NN, acc);
@@ -169,7 +169,7 @@ TEFEM_HD void process_item(const AssembleArgs& A, int32_t block0, uint32_t inc_w
 // at its block-order position: the plane stores of a warp are contiguous.
 template <int OPS, int DUU>
 TEFEM_HD void process_pf_item(const AssembleArgs& A, int32_t p, uint32_t inc_word, int32_t meta, const double* recs,
-                              const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const double* NN) {
+                              const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const QuadNN& NN) {
     typedef AsmTraits<OPS, DUU> T;
     typename T::Acc acc;
     const int slot = meta_slot(meta);
@@ -196,7 +196,7 @@ TEFEM_HD void combine_split(const AssembleArgs& A, int32_t p, int32_t meta, cons
 }
 
 // Dense element matrices of one element (parity path; elements.py:220-286).
-TEFEM_HD void element_dense(const double* rec, const double* mat, double W4, const QuadS& S, const double* NN, int kinds,
+TEFEM_HD void element_dense(const double* rec, const double* mat, double W4, const QuadS& S, const QuadNN& NN, int kinds,
                             double* Muu, double* Dtu, double* Dtt, double* Kuu, double* Kut, double* Ktt) {
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
@@ -261,6 +261,12 @@ const QuadTables& quad_tables() {
     return q;
 }
 
+// The select form of the table look-ups (tefem_element.cuh) must return the table entries bit for bit.
+static bool quad_select_checked() {
+    static const bool ok = quad_select_exact(quad_tables().S, quad_tables().NN);
+    return ok;
+}
+
 struct TileDims {
     int n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes;
     int pieces_first;   // item layout of every tile: 0 = inline (split lists), 1 = pieces first + one item per block
@@ -287,6 +293,7 @@ namespace tefem {
 __constant__ QuadTables c_quad;
 
 static int upload_quad() {
+    TEFEM_REQUIRE(quad_select_checked(), "quadrature tables do not have the value structure the select form assumes");
     static bool done = false;   // per process; constant memory is per device context of this module
     static int dev_done = -1;
     int dev = 0;
@@ -302,8 +309,7 @@ static int upload_quad() {
 // Threads per CTA: 256 (default; the 512-block tiles of symbolic.py are two passes).  The pieces-first kernel is also
 // instantiated for 128 and 64 threads - more, smaller CTAs per SM, i.e. more independent barrier domains (a third of the
 // stall samples of the 256-thread kernel wait at one of the three barriers of a tile, profiles/README.md) - selected
-// with the environment variable TEFEM_ASM_THREADS (measurement knob, read at every launch; pair it with items_per_cta =
-// 2 x threads).
+// with tefem_assemble_set_threads (measurement knob; pair it with items_per_cta = 2 x threads).
 // 512 threads per SM in every case, so that no instantiation is capped below 128 registers.
 #ifndef ASM_THREADS_N
 #define ASM_THREADS_N 256
@@ -395,14 +401,16 @@ __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(c
     const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
     char* stage0 = reinterpret_cast<char*>(partials + part_doubles);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
-    double* tabS_s = reinterpret_cast<double*>(bars + 2);
-    double* tabNN = tabS_s + 4;
-    if (threadIdx.x < 4) tabS_s[threadIdx.x] = c_quad.S[threadIdx.x];
-    if (threadIdx.x < 16) tabNN[threadIdx.x] = c_quad.NN[threadIdx.x];
-#ifdef ASM_S_SELECT
-    const QuadS tabS = make_quad_s(c_quad.S);
+#ifdef ASM_TAB_SELECT
+    const QuadS tabS = make_quad_s(c_quad.S);        // selected by compares, no shared-memory tables (tefem_element.cuh)
+    const QuadNN tabNN = make_quad_nn(c_quad.NN);
 #else
+    double* tabS_s = reinterpret_cast<double*>(bars + 2);
+    double* tabNN_s = tabS_s + 4;
+    if (threadIdx.x < 4) tabS_s[threadIdx.x] = c_quad.S[threadIdx.x];
+    if (threadIdx.x < 16) tabNN_s[threadIdx.x] = c_quad.NN[threadIdx.x];
     const QuadS tabS = make_quad_s(tabS_s);
+    const QuadNN tabNN = make_quad_nn(tabNN_s);
 #endif
     typedef AsmTraits<OPS, DUU> T;
     const int G = gridDim.x;
@@ -489,6 +497,174 @@ __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(c
     }
 }
 
+// ---- K1, dynamic form (default for the pieces-first layout) ----------------------------------------------------------
+// ncu of the tile-synchronous kernel above (profiles/r2a_*): the shared-memory pipe that bounds it is busy only 65 - 68 %
+// of the cycles and 32 % of the stall samples sit at the three CTA barriers of a tile - the phases of a tile do not
+// fill the 256 threads evenly (480 elements, 78 pieces, 445 blocks) and every warp waits for the slowest one three
+// times per tile, with only two CTAs per SM to cover for each other.
+// Here ONE persistent CTA of 16 warps owns the SM and there is no CTA-wide barrier in the tile loop.  The work of a
+// tile is cut into CHUNKS of 32 consecutive entries (32 staged elements of phase 1, 32 pieces, 32 blocks in block
+// order: a warp still stores 32 consecutive blocks of every plane) that the warps GRAB from shared-memory counters;
+// dependencies are counters too: a warp starts the gathers of tile k when all phase-1 chunks of k are done and reads the
+// parked pieces when all piece chunks are done.  A warp that finds no chunk left in tile k LEAVES it and moves on to
+// phase 1 of tile k + 1 while others still gather for k: the phases of consecutive tiles overlap and the pipe stays
+// busy.  Records, partial sums and the TMA stage are double-buffered; the LAST warp to leave tile k (every chunk of k
+// is finished then, and no warp will look at its stage again) issues the prefetch of tile k + 2 into the buffers of
+// k, so no warp can run more than one tile ahead of the slowest one and the mbarrier phase a warp waits for is never
+// ambiguous.  All counters are monotonic (never reset): a warp visits every tile of its CTA in order and keeps the
+// running chunk totals per buffer parity in registers, so a grab is a bounded compare-and-swap and "phase complete" is
+// `done >= total`; counts of tiles k and k + 2 cannot mix because k + 2 starts only after every warp has left k.
+// Same items, same per-item summation order as the tile-synchronous kernel: the planes are BITWISE identical.
+constexpr int DYN_THREADS = 512;
+enum { C_P1_NEXT = 0, C_P1_DONE, C_PC_NEXT, C_PC_DONE, C_BL_NEXT, C_LEFT, C_PER_PARITY = 8 };
+
+__device__ __forceinline__ unsigned ld_shared_volatile(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// lane 0 takes the next chunk number below `limit` (bounded: the counter never passes the tile's total); -1 when none
+__device__ __forceinline__ int chunk_grab(unsigned* ctr, unsigned limit, int lane) {
+    int id = -1;
+    if (lane == 0) {
+        unsigned old = ld_shared_volatile(ctr);
+        while ((int)(old - limit) < 0) {
+            const unsigned seen = atomicCAS(ctr, old, old + 1);
+            if (seen == old) { id = (int)old; break; }
+            old = seen;
+        }
+    }
+    return __shfl_sync(0xffffffffu, id, 0);
+}
+// every lane's shared-memory writes of the chunk are ordered before the count; returns the count before this chunk
+__device__ __forceinline__ unsigned chunk_done(unsigned* ctr, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(ctr, 1u);
+    return __shfl_sync(0xffffffffu, old, 0);
+}
+__device__ __forceinline__ void chunk_wait(const unsigned* ctr, unsigned total, int lane) {
+    if (lane == 0) {
+        while ((int)(ld_shared_volatile(ctr) - total) < 0) __nanosleep(32);
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+
+// One lane: issue the bulk copies of tile t into stage buffer `st` (header read from global memory here).
+__device__ __forceinline__ void prefetch_tile_now(const AssembleArgs& A, int t, char* st, const StageLayout& L, uint64_t* bar) {
+    const int4* hg = reinterpret_cast<const int4*>(A.cta_hdr) + 3 * (size_t)t;
+    prefetch_tile(A, t, __ldg(hg), __ldg(hg + 1), __ldg(hg + 2), st, L, bar);
+}
+
+template <int OPS, int DUU>
+__global__ void __launch_bounds__(DYN_THREADS, 1) assemble_dyn_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
+                                                                      int part_doubles) {
+    extern __shared__ __align__(128) double smem[];
+    typedef AsmTraits<OPS, DUU> T;
+    const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
+    double* recs0 = smem;                                   // [2][rec_doubles]
+    double* parts0 = recs0 + 2 * (size_t)rec_doubles;       // [2][part_doubles]
+    char* stage0 = reinterpret_cast<char*>(parts0 + 2 * (size_t)part_doubles);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
+    unsigned* ctr0 = reinterpret_cast<unsigned*>(bars + 2); // [2][C_PER_PARITY]
+#ifdef ASM_TAB_SELECT
+    const QuadS tabS = make_quad_s(c_quad.S);
+    const QuadNN tabNN = make_quad_nn(c_quad.NN);
+#else
+    double* tabS_s = reinterpret_cast<double*>(ctr0 + 2 * C_PER_PARITY);
+    double* tabNN_s = tabS_s + 4;
+    if (threadIdx.x < 4) tabS_s[threadIdx.x] = c_quad.S[threadIdx.x];
+    if (threadIdx.x < 16) tabNN_s[threadIdx.x] = c_quad.NN[threadIdx.x];
+    const QuadS tabS = make_quad_s(tabS_s);
+    const QuadNN tabNN = make_quad_nn(tabNN_s);
+#endif
+    const int G = gridDim.x, lane = threadIdx.x & 31;
+    const int K = (A.n_cta - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA: blockIdx.x, blockIdx.x + G, ...
+    if (threadIdx.x < 2 * C_PER_PARITY) ctr0[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (K > 0) prefetch_tile_now(A, blockIdx.x, stage0, L, &bars[0]);
+        if (K > 1) prefetch_tile_now(A, blockIdx.x + G, stage0 + L.bytes, L, &bars[1]);
+    }
+    const double W4 = c_quad.W4;
+    // chunk totals of the tiles this warp has passed, per buffer parity (cur = parity of tile k)
+    unsigned p1_cur = 0, p1_oth = 0, pc_cur = 0, pc_oth = 0, bl_cur = 0, bl_oth = 0;
+    for (int k = 0; k < K; ++k) {
+        const int b = k & 1;
+        char* st = stage0 + (size_t)b * L.bytes;
+        double* recs = recs0 + (size_t)b * rec_doubles;
+        double* partials = parts0 + (size_t)b * part_doubles;
+        unsigned* c = ctr0 + b * C_PER_PARITY;
+        const uint32_t parity = (uint32_t)(k >> 1) & 1u;
+        while (!mbar_try_wait(&bars[b], parity)) {}
+        const int32_t* hdr = reinterpret_cast<const int32_t*>(st + L.hdr);
+        const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], o_elems = hdr[H_OELEMS], n_piece = hdr[H_NPIECE];
+        const int32_t block0 = hdr[H_BLOCK0];
+        const double* xyz = reinterpret_cast<const double*>(st + L.xyz);
+        const uint32_t* conn8 = reinterpret_cast<const uint32_t*>(st + L.conn8);
+        const int32_t* it_inc = reinterpret_cast<const int32_t*>(st + L.it_inc);
+        const int32_t* it_meta = reinterpret_cast<const int32_t*>(st + L.it_meta);
+        const uint16_t* inc_s = reinterpret_cast<const uint16_t*>(st + L.inc);
+        const unsigned p1_tot = p1_cur + (unsigned)((n_elems + 31) >> 5);
+        const unsigned pc_tot = pc_cur + (unsigned)((n_piece + 31) >> 5);
+        const unsigned bl_tot = bl_cur + (unsigned)((n_items - n_piece + 31) >> 5);
+        // phase 1: geometry records, 32 staged elements per chunk
+        for (;;) {
+            const int id = chunk_grab(c + C_P1_NEXT, p1_tot, lane);
+            if (id < 0) break;
+            const int le = (int)((unsigned)id - p1_cur) * 32 + lane;
+            if (le < n_elems) {
+                const double det = stage_element_local<T::WANT_D>(xyz, conn8[le], recs + (size_t)le * T::REC);
+                if (!(det > 0.0)) {  // error path only: elements.py:207-210
+                    const int32_t e = A.cta_elems[o_elems + le];
+                    if (det < 0.0) atomicMin(A.bad_elem, e);
+                    else atomicMin(A.bad_elem + 1, e);
+                }
+            }
+            chunk_done(c + C_P1_DONE, lane);
+        }
+        chunk_wait(c + C_P1_DONE, p1_tot, lane);
+        // phase 2a: pieces of split blocks park their values
+        for (;;) {
+            const int id = chunk_grab(c + C_PC_NEXT, pc_tot, lane);
+            if (id < 0) break;
+            const int it = (int)((unsigned)id - pc_cur) * 32 + lane;
+            if (it < n_piece)
+                process_pf_item<OPS, DUU>(A, -1, (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, W4, tabS, tabNN);
+            chunk_done(c + C_PC_DONE, lane);
+        }
+        // phase 2b: one lane per block, 32 consecutive blocks per chunk
+        for (;;) {
+            const int id = chunk_grab(c + C_BL_NEXT, bl_tot, lane);
+            if (id < 0) break;
+            const int q = (int)((unsigned)id - bl_cur) * 32 + lane;     // block of the tile
+            const int it = n_piece + q;
+            const bool live = it < n_items;
+            const int32_t meta = live ? it_meta[it] : 0;
+            if (__any_sync(0xffffffffu, live && meta_slot(meta) >= 0)) chunk_wait(c + C_PC_DONE, pc_tot, lane);   // combine items
+            if (live)
+                process_pf_item<OPS, DUU>(A, block0 + q, (uint32_t)it_inc[it], meta, recs, inc_s, partials, W4, tabS, tabNN);
+        }
+        // leave tile k; the last of the CTA's warps to do so frees its buffers for tile k + 2
+        const unsigned left = chunk_done(c + C_LEFT, lane);
+        if (left + 1u == (unsigned)(DYN_THREADS / 32) * (unsigned)((k >> 1) + 1) && k + 2 < K && lane == 0) {
+            fence_proxy_async();
+            prefetch_tile_now(A, (int)blockIdx.x + (k + 2) * G, st, L, &bars[b]);
+        }
+        // next tile: swap the parities
+        const unsigned t1 = p1_oth, t2 = pc_oth, t3 = bl_oth;
+        p1_oth = p1_tot; pc_oth = pc_tot; bl_oth = bl_tot;
+        p1_cur = t1; pc_cur = t2; bl_cur = t3;
+    }
+}
+
 __global__ void __launch_bounds__(128) element_matrices_kernel(
     const double* __restrict__ coords, const int32_t* __restrict__ conn, const int32_t* __restrict__ mat_id,
     const double* __restrict__ mat_table, const int64_t* __restrict__ elem_idx, int64_t n, int kinds,
@@ -504,7 +680,7 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
         if (det < 0.0) atomicMin(bad_elem, (int32_t)e);
         else atomicMin(bad_elem + 1, (int32_t)e);
     }
-    element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], c_quad.W4, make_quad_s(c_quad.S), c_quad.NN, kinds,
+    element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], c_quad.W4, make_quad_s(c_quad.S), make_quad_nn(c_quad.NN), kinds,
                   Muu ? Muu + t * 144 : nullptr, Dtu ? Dtu + t * 48 : nullptr, Dtt ? Dtt + t * 16 : nullptr,
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
@@ -535,18 +711,49 @@ static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStre
     return TEFEM_OK;
 }
 
-// TEFEM_ASM_THREADS = 64 | 128 | 256 (read at every launch, so that one process can compare the variants)
-static int asm_threads() {
-    const char* e = getenv("TEFEM_ASM_THREADS");
-    return (e && e[0]) ? atoi(e) : ASM_THREADS;
+template <int OPS, int DUU>
+static int launch_assemble_dyn(const AssembleArgs& A, const TileDims& d, cudaStream_t st, bool* fits) {
+    const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
+    const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
+    const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
+    const size_t smem = 2 * ((size_t)rec_doubles + part_doubles) * sizeof(double) + 2 * (size_t)L.bytes + 16 +
+                        2 * C_PER_PARITY * sizeof(unsigned) + 20 * sizeof(double);
+    *fits = smem <= 227 * 1024;
+    if (!*fits) return TEFEM_OK;                  // the caller falls back to the tile-synchronous kernel
+    static int sm_count = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_dyn_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int dev = 0;
+        TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
+        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    int grid = sm_count;                          // one persistent CTA per SM
+    if (grid > d.n_cta) grid = d.n_cta;
+    assemble_dyn_kernel<OPS, DUU><<<grid, DYN_THREADS, smem, st>>>(A, d, rec_doubles, part_doubles);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
 }
+
+// Kernel form of the pieces-first layout: 0 = dynamic chunks (one 512-thread CTA per SM, default), or the threads per
+// CTA of the tile-synchronous kernel: 64 | 128 | 256.  Set with tefem_assemble_set_threads (measurement knob; the
+// environment is not consulted on the launch path).
+static int g_asm_threads = 0;
+static int asm_threads() { return g_asm_threads; }
 
 template <int OPS, int DUU>
 static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
-    const int nt = asm_threads();
+    int nt = asm_threads();
     if (!d.pieces_first) {
-        TEFEM_REQUIRE(nt == ASM_THREADS, "TEFEM_ASM_THREADS applies to the pieces-first item layout only");
+        TEFEM_REQUIRE(nt == 0 || nt == ASM_THREADS, "tefem_assemble_set_threads applies to the pieces-first item layout only");
         return launch_assemble_pf<OPS, DUU, false, ASM_THREADS>(A, d, st);
+    }
+    if (nt == 0) {
+        bool fits = false;
+        const int rc = launch_assemble_dyn<OPS, DUU>(A, d, st, &fits);
+        if (rc || fits) return rc;
+        nt = ASM_THREADS;                         // tiles too large for the double buffers: tile-synchronous kernel
     }
     switch (nt) {
         case ASM_THREADS: return launch_assemble_pf<OPS, DUU, true, ASM_THREADS>(A, d, st);
@@ -556,7 +763,7 @@ static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_
 #endif
         default: break;
     }
-    set_error("TEFEM_ASM_THREADS must be 64, 128 or 256");
+    set_error("kernel form of the assembly must be 0, 64, 128 or 256 (tefem_assemble_set_threads)");
     return TEFEM_ERR_INVALID;
 }
 
@@ -636,6 +843,13 @@ extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta,
     }
 }
 
+extern "C" int tefem_assemble_set_threads(int threads) {
+    TEFEM_REQUIRE(threads == 0 || threads == 64 || threads == 128 || threads == 256,
+                  "0 (dynamic chunks) or 64 / 128 / 256 threads per CTA of the tile-synchronous kernel");
+    g_asm_threads = threads;
+    return TEFEM_OK;
+}
+
 extern "C" int tefem_check_jacobian(const int32_t* bad_elem, int32_t* h_elem, void* stream) {
     int32_t h[2];
     TEFEM_CUDA_CHECK(cudaMemcpyAsync(h, bad_elem, sizeof(h), cudaMemcpyDeviceToHost, as_stream(stream)));
@@ -690,17 +904,17 @@ static int emu_run(const AssembleArgs& A, const TileDims& d, int n_mat) {
             if (d.pieces_first) {
                 if (it < n_piece) {   // piece k parks in slot k
                     if (slot != it || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
-                    process_pf_item<OPS, DUU>(A, -1, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), q.NN);
+                    process_pf_item<OPS, DUU>(A, -1, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
                 } else {              // block items: all pieces were processed before (the kernel synchronises)
                     const int b = it - n_piece;
                     if ((int)(iw >> 16) != b) return TEFEM_ERR_INVALID;
                     if (slot < 0 ? s + meta_len(meta) > h[H_NINC] : slot + meta_len(meta) > n_piece) return TEFEM_ERR_INVALID;
-                    process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), q.NN);
+                    process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
                 }
                 continue;
             }
             if (slot >= d.max_slots || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
-            process_item<OPS, DUU>(A, h[H_BLOCK0], iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), q.NN);
+            process_item<OPS, DUU>(A, h[H_BLOCK0], iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
         }
         for (int k = 0; k < h[H_NSPLIT]; ++k) {
             const int32_t sm = A.split_meta[h[H_OSPLIT] + k];
@@ -753,7 +967,7 @@ extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* c
             int32_t* slot = bad_elem + (det < 0.0 ? 0 : 1);
             if (e < *slot) *slot = (int32_t)e;
         }
-        element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], q.W4, make_quad_s(q.S), q.NN, kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
+        element_dense(rec, mat_table + MAT_STRIDE * mat_id[e], q.W4, make_quad_s(q.S), make_quad_nn(q.NN), kinds, Muu ? Muu + e * 144 : nullptr, Dtu ? Dtu + e * 48 : nullptr,
                       Dtt ? Dtt + e * 16 : nullptr, Kuu ? Kuu + e * 144 : nullptr, Kut ? Kut + e * 48 : nullptr,
                       Ktt ? Ktt + e * 16 : nullptr);
     }

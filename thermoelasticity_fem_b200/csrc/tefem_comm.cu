@@ -73,8 +73,14 @@ struct tefem_comm {
     char* shm_local = nullptr;
     char* shm_base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t shm_cap = 0;
-    uint32_t epoch[2] = {0, 0};
+    uint32_t epoch[PEER_N_CHANNELS] = {0, 0, 0};
     int* d_err = nullptr;
+    long long timeout = PEER_TIMEOUT_DEFAULT;
+    // peer-mapped vector slots (SpMV inputs whose halo tails the neighbours write directly, tefem_krylov.cu)
+    char* vec_local = nullptr;
+    char* vec_base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_slots = 0;
+    int64_t slot_doubles = 0;
 };
 
 extern "C" int tefem_comm_unique_id(const char* h_nccl_lib_path, char* h_id) {
@@ -108,9 +114,12 @@ extern "C" int tefem_comm_create(tefem_comm** out, const char* h_nccl_lib_path, 
 
 extern "C" int tefem_comm_destroy(tefem_comm* c) {
     if (!c) return TEFEM_OK;
-    for (int r = 0; r < c->n_ranks && r < PEER_MAX_RANKS; ++r)
+    for (int r = 0; r < c->n_ranks && r < PEER_MAX_RANKS; ++r) {
         if (r != c->rank && c->shm_base[r]) cudaIpcCloseMemHandle(c->shm_base[r]);
+        if (r != c->rank && c->vec_base[r]) cudaIpcCloseMemHandle(c->vec_base[r]);
+    }
     if (c->shm_local) cudaFree(c->shm_local);
+    if (c->vec_local) cudaFree(c->vec_local);
     if (c->d_err) cudaFree(c->d_err);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     delete c;
@@ -170,6 +179,57 @@ extern "C" int tefem_comm_shm_open(tefem_comm* c, const char* h_handles) {
     return TEFEM_OK;
 }
 
+// ---- peer-mapped vector slots ----------------------------------------------------------------------
+// Every rank allocates n_slots vectors of slot_doubles doubles (the same sizes on all ranks, so that slot k of rank q
+// sits at vec_base[q] + k * slot_doubles) and maps the allocations of the others with CUDA IPC.  The Krylov driver
+// keeps its SpMV input vectors there: a neighbour writes the halo tail of my vector with plain remote stores.
+extern "C" int tefem_comm_vec_alloc(tefem_comm* c, int n_slots, int64_t slot_doubles, char* h_handle) {
+    TEFEM_REQUIRE(c && h_handle && n_slots > 0 && slot_doubles > 0, "arguments");
+    TEFEM_REQUIRE(c->n_ranks <= PEER_MAX_RANKS, "peer-memory vectors support up to 8 ranks (one node)");
+    TEFEM_REQUIRE(!c->vec_local, "peer-memory vectors already allocated");
+    const int64_t slot = (slot_doubles + 15) / 16 * 16;
+    const size_t bytes = (size_t)n_slots * (size_t)slot * sizeof(double);
+    TEFEM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->vec_local), bytes));
+    TEFEM_CUDA_CHECK(cudaMemset(c->vec_local, 0, bytes));
+    TEFEM_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    TEFEM_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->vec_local));
+    memcpy(h_handle, &h, sizeof(h));
+    c->n_slots = n_slots;
+    c->slot_doubles = slot;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_comm_vec_open(tefem_comm* c, const char* h_handles) {
+    TEFEM_REQUIRE(c && h_handles && c->vec_local, "allocate the local vectors first");
+    for (int r = 0; r < c->n_ranks; ++r) {
+        if (r == c->rank) { c->vec_base[r] = c->vec_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_handles + 64 * (size_t)r, sizeof(h));
+        void* p = nullptr;
+        TEFEM_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->vec_base[r] = reinterpret_cast<char*>(p);
+    }
+    return TEFEM_OK;
+}
+
+bool tefem_comm_has_vectors(const tefem_comm* c) {
+    return c && c->vec_local && c->vec_base[c->n_ranks - 1] != nullptr && c->vec_base[0] != nullptr;
+}
+int tefem_comm_n_slots(const tefem_comm* c) { return c ? c->n_slots : 0; }
+int64_t tefem_comm_slot_doubles(const tefem_comm* c) { return c ? c->slot_doubles : 0; }
+double* tefem_comm_slot(const tefem_comm* c, int rank, int slot) {
+    return reinterpret_cast<double*>(c->vec_base[rank]) + (int64_t)slot * c->slot_doubles;
+}
+int tefem_comm_rank(const tefem_comm* c) { return c ? c->rank : 0; }
+int tefem_comm_world(const tefem_comm* c) { return c ? c->n_ranks : 1; }
+
+extern "C" int tefem_comm_set_timeout(tefem_comm* c, double seconds) {
+    TEFEM_REQUIRE(c && seconds > 0.0, "arguments");
+    c->timeout = (long long)(seconds * 1.9e9);          // cycles of the SM clock at its nominal maximum
+    return TEFEM_OK;
+}
+
 bool tefem_comm_has_peer(const tefem_comm* c) { return c && c->shm_base[c->n_ranks - 1] != nullptr && c->shm_base[0] != nullptr; }
 int64_t tefem_comm_peer_cap(const tefem_comm* c) { return c ? c->shm_cap : 0; }
 
@@ -179,17 +239,26 @@ PeerCtx tefem_comm_peer_ctx(tefem_comm* c, int channel) {
     ctx.epoch = ++c->epoch[channel];
     for (int r = 0; r < c->n_ranks; ++r) ctx.base[r] = c->shm_base[r];
     ctx.err = c->d_err;
+    ctx.timeout = c->timeout;
     return ctx;
 }
 
-// Call after a stream synchronisation: reports a time-out recorded by a peer wait.
+// Call after a stream synchronisation: reports a time-out recorded by a peer wait.  The flag stays set (every later
+// solve on this communicator fails fast instead of computing with partial sums) until tefem_comm_reset_error.
 extern "C" int tefem_comm_check(tefem_comm* c) {
     if (!c || !c->d_err) return TEFEM_OK;
     int e = 0;
     TEFEM_CUDA_CHECK(cudaMemcpy(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (e) {
-        set_error("peer-memory reduction timed out waiting for another rank");
+        set_error("peer-memory exchange timed out waiting for another rank (communicator marked failed; "
+                  "tefem_comm_reset_error after all ranks have been resynchronised)");
         return TEFEM_ERR_NCCL;
     }
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_comm_reset_error(tefem_comm* c) {
+    TEFEM_REQUIRE(c, "null communicator");
+    if (c->d_err) TEFEM_CUDA_CHECK(cudaMemset(c->d_err, 0, sizeof(int)));
     return TEFEM_OK;
 }

@@ -10,6 +10,14 @@ bool tefem_comm_has_peer(const tefem_comm* c);
 int64_t tefem_comm_peer_cap(const tefem_comm* c);
 tefem::PeerCtx tefem_comm_peer_ctx(tefem_comm* c, int channel);      // next epoch of that channel
 
+// Peer-mapped vector slots (tefem_comm_vec_alloc / _open): slot k of rank q
+bool tefem_comm_has_vectors(const tefem_comm* c);
+int tefem_comm_n_slots(const tefem_comm* c);
+int64_t tefem_comm_slot_doubles(const tefem_comm* c);
+double* tefem_comm_slot(const tefem_comm* c, int rank, int slot);
+int tefem_comm_rank(const tefem_comm* c);
+int tefem_comm_world(const tefem_comm* c);
+
 // Packed point-to-point exchange with the neighbouring row blocks: for neighbour k, the doubles
 // send[4*send_ptr[k] .. 4*send_ptr[k+1]) go to rank nbr[k] and recv[4*recv_ptr[k] .. 4*recv_ptr[k+1])
 // arrive from it, all inside one ncclGroupStart/End.

@@ -74,27 +74,68 @@ TEFEM_HD double rec_gt(const double* rec, int c, int b) {
     return b == 0 ? rec[REC_GT0 + c] : rec[REC_G + 3 * (c + 1) + (b - 1)];
 }
 
-// S_a = sum_g w N_a(g) of the four local nodes.  Default: an indexed load from the table (shared memory in K1: one
-// conflict-free wavefront per half-warp on the pipe that bounds the kernel, profiles/README.md).  -DASM_S_SELECT
-// (measurement variant, same values): the four values are held by value and selected with compares; ptxas re-reads them
-// from the constant bank inside the loop (LDCU / LDC), whether that beats the shared-memory load is not measured yet.
+// Quadrature tables S_a = sum_g w N_a(g) and NN_ab = sum_g w N_a(g) N_b(g) as seen by the incidence loop.
+// Default (ASM_TAB_SELECT, K1 is bound by the shared-memory pipe, profiles/README.md): the tables take only 2 and 5
+// BITWISE distinct values (S: a == 0 or not; NN: (0,0), a == b >= 1, a != b both >= 1, {0, 1|2}, {0, 3} - the last two
+// differ in the last bit because the reference sums the Gauss points in a fixed order), so the entry is selected with
+// compares on the local node numbers from values held in registers / the constant bank: no shared-memory load.
+// -DASM_TAB_LOAD restores the indexed loads (one wavefront per half-warp and table; the round-1 kernel).
+// Both forms return the table entries themselves: the assembled values are bitwise identical.
+#ifndef ASM_TAB_LOAD
+#define ASM_TAB_SELECT 1
+#endif
 struct QuadS {
-#ifdef ASM_S_SELECT
-    double s0, s1, s2, s3;
-    TEFEM_HD double at(int a) const { return a == 0 ? s0 : (a == 1 ? s1 : (a == 2 ? s2 : s3)); }
+#ifdef ASM_TAB_SELECT
+    double s0, s1;
+    TEFEM_HD double at(int a) const { return a == 0 ? s0 : s1; }
 #else
     const double* s;
     TEFEM_HD double at(int a) const { return s[a]; }
 #endif
 };
+struct QuadNN {
+#ifdef ASM_TAB_SELECT
+    double v00, vdd, vod, v0x, v03;
+    TEFEM_HD double at(int a, int b) const {
+        const double diag = a == 0 ? v00 : vdd;
+        const double with0 = (a | b) == 3 ? v03 : v0x;      // one of a, b is 0 here: a | b is the other one
+        const double off = (a == 0 || b == 0) ? with0 : vod;
+        return a == b ? diag : off;
+    }
+#else
+    const double* nn;
+    TEFEM_HD double at(int a, int b) const { return nn[4 * a + b]; }
+#endif
+};
+// True when the select form reproduces every entry of the tables bit for bit (checked once on the host before the
+// first launch; the tables are built in the reference's operation order, tefem_assemble.cu make_quad_tables).
 TEFEM_HD QuadS make_quad_s(const double* S) {
     QuadS q;
-#ifdef ASM_S_SELECT
-    q.s0 = S[0]; q.s1 = S[1]; q.s2 = S[2]; q.s3 = S[3];
+#ifdef ASM_TAB_SELECT
+    q.s0 = S[0]; q.s1 = S[1];
 #else
     q.s = S;
 #endif
     return q;
+}
+TEFEM_HD QuadNN make_quad_nn(const double* NN) {
+    QuadNN q;
+#ifdef ASM_TAB_SELECT
+    q.v00 = NN[0]; q.vdd = NN[5]; q.vod = NN[6]; q.v0x = NN[1]; q.v03 = NN[3];
+#else
+    q.nn = NN;
+#endif
+    return q;
+}
+inline bool quad_select_exact(const double* S, const double* NN) {
+    const QuadS s = make_quad_s(S);
+    const QuadNN n = make_quad_nn(NN);
+    for (int a = 0; a < 4; ++a) {
+        if (s.at(a) != S[a]) return false;
+        for (int b = 0; b < 4; ++b)
+            if (n.at(a, b) != NN[4 * a + b]) return false;
+    }
+    return true;
 }
 
 // Values of one node-pair block.  WITH_K/... select which parts are live so that the compiler drops the dead
@@ -163,7 +204,7 @@ struct GeomAcc {
 // acc += geometric contribution of block (a, b) of the element whose record is `rec`.
 template <bool WITH_K, bool WITH_M, bool WITH_D>
 TEFEM_HD void block_accumulate(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, const double* __restrict__ rec, int a, int b,
-                               double W4, const QuadS& S, const double* __restrict__ NN) {
+                               double W4, const QuadS& S, const QuadNN& NN) {
     const double det = rec[REC_DET];
     double ds = 0.0;
     if (WITH_K || WITH_D) ds = det * S.at(a);
@@ -182,7 +223,7 @@ TEFEM_HD void block_accumulate(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, const doubl
         acc.q[1] += ds * gb1;
         acc.q[2] += ds * gb2;
     }
-    if (WITH_M || WITH_D) acc.nn += det * NN[4 * a + b];
+    if (WITH_M || WITH_D) acc.nn += det * NN.at(a, b);
     if (WITH_D) {
         acc.r[0] += ds * rec_gt(rec, 0, b);
         acc.r[1] += ds * rec_gt(rec, 1, b);

@@ -47,7 +47,8 @@ constexpr int NSCAL = 24;
 enum { SC_RHO = 0, SC_ALPHA, SC_OMEGA, SC_BETA, SC_RR, SC_BB, SC_RHV, SC_THR_U = 7, SC_PKT = 8 /* 8 packet slots 8..15 */,
        SC_THR_T = 16, SC_BNORM2 = 17 };
 // device int block
-enum { IN_STOP = 0, IN_STOP_ITER = 1, IN_ITERS = 2, IN_REASON = 3 };   // reason: 1 converged, 2 breakdown
+enum { IN_STOP = 0, IN_STOP_ITER = 1, IN_ITERS = 2, IN_REASON = 3,   // reason: 1 converged, 2 breakdown
+       IN_TICKET = 8 };                                                  // CTA ticket of push_halo_kernel
 
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
@@ -129,19 +130,96 @@ __device__ __forceinline__ void spmv_store_partials(const double (&d)[5], double
     }
 }
 
-template <int DOTS, int UNROLL>
+// Flags of one halo exchange (peer-memory halo, tefem_peer.cuh; resolved on the host so that the kernels index nothing
+// dynamically): `mine[q]` = the flag neighbour q raises in THIS rank's region when its boundary values have landed in my
+// vector; `theirs[q]` = the flag I raise in neighbour q's region.  Slab partitions have <= 2 neighbours.
+struct HaloFlags {
+    int n = 0;
+    uint32_t epoch = 0;
+    long long timeout = PEER_TIMEOUT_DEFAULT;
+    int* err = nullptr;
+    const uint32_t* mine[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t* theirs[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+// Threads 0 .. n-1 of the CTA wait for one neighbour flag each (bounded; a time-out marks the communicator failed and
+// later waits return at once), then the CTA synchronises: every thread may read the halo tail afterwards.
+__device__ __forceinline__ void halo_wait(const HaloFlags& hf) {
+#pragma unroll
+    for (int q = 0; q < PEER_MAX_RANKS; ++q) {
+        if (q < hf.n && (int)threadIdx.x == q) {
+            const uint32_t* f = hf.mine[q];
+            if ((int32_t)(ld_acquire_sys(f) - hf.epoch) < 0 && !*reinterpret_cast<volatile int*>(hf.err)) {
+                const long long t0 = clock64();
+                while ((int32_t)(ld_acquire_sys(f) - hf.epoch) < 0) {
+                    if (clock64() - t0 > hf.timeout) { *hf.err = 1; break; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// HALO: multi-GPU form.  The halo tail of x (rows n_rows ..) is written by the neighbouring ranks' push_halo_kernel
+// straight into this rank's peer-mapped vector (remote stores over NVLink); the kernel only has to wait for their
+// "pushed" flags of this exchange (an acquire at system scope, which also drops stale L1 lines) before it reads x -
+// no packing, no NCCL call, no second launch for the boundary rows.
+template <int DOTS, int UNROLL, bool HALO>
 __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_kernel(const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ colidx,
                                                             const int32_t* __restrict__ rows, int32_t n_rows,
                                                             const double* __restrict__ sys, const double* __restrict__ x,
                                                             double* __restrict__ y, const double* __restrict__ w,
                                                             const double* __restrict__ sd, double* __restrict__ partials,
-                                                            const int* __restrict__ ictl) {
+                                                            const int* __restrict__ ictl, const HaloFlags hf) {
     __shared__ double red[8 * 32];
     double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
+    if (HALO && active) halo_wait(hf);
     if (active) spmv_rows<DOTS, UNROLL>(rowptr, colidx, rows, n_rows, sys, x, y, w, sd, d);
     spmv_store_partials<DOTS>(d, red, partials);
+}
+
+// Halo push: entry k sends the 4 values of owned node idx[k] to node dpos[k] of rank dst[k]'s copy of the SAME vector
+// slot (all ranks lay their slots out identically, tefem_comm_vec_alloc) with one 256-bit remote store.  The CTA that
+// takes the last ticket - every other CTA's stores are then visible system-wide - raises this rank's flag of the
+// exchange on the neighbours.  The consumer is the neighbour's next SpMV (or pull_halo_kernel).
+struct HaloSlots {
+    double* base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+__global__ void __launch_bounds__(256) push_halo_kernel(int64_t n, const int32_t* __restrict__ idx,
+                                                        const int32_t* __restrict__ dst, const int32_t* __restrict__ dpos,
+                                                        const double* __restrict__ x, const HaloSlots slots,
+                                                        const HaloFlags hf, const int* ictl, int* ticket) {
+    if (ictl && ictl[IN_STOP]) return;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        double a, b, c, d;
+        ld256_x(x + 4 * (int64_t)idx[k], a, b, c, d);
+        double* o = slots.base[dst[k]] + 4 * (int64_t)dpos[k];
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        if (t == (int)gridDim.x - 1) {
+            *ticket = 0;
+            __threadfence_system();
+#pragma unroll
+            for (int q = 0; q < PEER_MAX_RANKS; ++q)
+                if (q < hf.n) st_release_sys(hf.theirs[q], hf.epoch);
+        }
+    }
+}
+
+// Consumer of a push outside the SpMV (tefem_solver_halo_exchange): waits for the neighbours' flags and copies the halo
+// tail of the slot into the caller's vector.
+__global__ void __launch_bounds__(256) pull_halo_kernel(int64_t n_tail, const double* __restrict__ slot_tail,
+                                                        double* __restrict__ x_tail, const HaloFlags hf) {
+    halo_wait(hf);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_tail; k += (int64_t)gridDim.x * blockDim.x)
+        x_tail[k] = ld_volatile_f64(slot_tail + k);
 }
 
 // r = b - y ; rhat = r ; p = r ; partials (r.r_u, r.r_t, b.b_u, b.b_t, x.x_u, x.x_t)
@@ -301,17 +379,19 @@ __global__ void __launch_bounds__(256) update_s_kernel(int64_t n, const double* 
 
 // x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v)
 // (ph = N p, sh = N s: the right-preconditioned directions; ph == p, sh == s without a preconditioner)
+// (p / ph and s / sh name the SAME buffers when there is no preconditioner: no __restrict__ on them)
 __global__ void __launch_bounds__(256) update_xrp_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
-                                                         double* __restrict__ p, const double* __restrict__ s,
+                                                         double* p, const double* s,
                                                          const double* __restrict__ t, const double* __restrict__ v,
-                                                         const double* __restrict__ ph, const double* __restrict__ sh,
+                                                         const double* ph, const double* sh,
                                                          const double* __restrict__ sc, const int* __restrict__ ictl,
                                                          int iter) {
     if (ictl[IN_STOP] && ictl[IN_STOP_ITER] != iter) return;
     const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA], beta = sc[SC_BETA];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const double pv = p[k], sv = s[k];
-        x[k] += alpha * ph[k] + omega * sh[k];
+        const double phv = ph[k], shv = sh[k];
+        x[k] += alpha * phv + omega * shv;
         const double rv = sv - omega * t[k];
         r[k] = rv;
         p[k] = rv + beta * (pv - omega * v[k]);
@@ -487,6 +567,13 @@ struct tefem_solver {
     int n_nbr = 0;
     std::vector<int32_t> nbr, send_ptr, recv_ptr;
     const int32_t* send_idx = nullptr;
+    // peer-memory halo (default): destination rank / node position of every send entry; the SpMV input vectors live in
+    // the communicator's peer-mapped slots
+    const int32_t* send_dst = nullptr;
+    const int32_t* send_dpos = nullptr;
+    bool peer_halo = false;
+    double *xs = nullptr, *xa = nullptr;       // staging slots: restart / true-residual SpMV input, generic exchange
+    // NCCL halo (measurement alternative: communicator without vector slots): interior / boundary row split
     const int32_t* boundary_rows = nullptr;
     int32_t n_boundary_rows = 0;
     const int32_t* interior_rows = nullptr;
@@ -505,6 +592,9 @@ struct tefem_solver {
     double cat_ms[4] = {0.0, 0.0, 0.0, 0.0};
     long long cat_count[4] = {0, 0, 0, 0};
 };
+
+enum { SLOT_P = 0, SLOT_S = 1, SLOT_PH = 2, SLOT_SH = 3, SLOT_XS = 4, SLOT_XA = 5, SLOT_COUNT = 6 };
+extern "C" int tefem_solver_peer_slots() { return SLOT_COUNT; }
 
 enum { PROF_SPMV = 0, PROF_PRECOND = 1, PROF_REDUCE = 2, PROF_UPDATE = 3 };
 static int prof_begin(tefem_solver* s, cudaStream_t st, int cat = PROF_SPMV) {
@@ -569,6 +659,20 @@ extern "C" int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n
     s->ictl = reinterpret_cast<int*>(w); w += align16(16);
     s->sendbuf = w;
     s->comm = reinterpret_cast<tefem_comm*>(comm);
+    if (s->comm && tefem_comm_has_vectors(s->comm)) {
+        // SpMV inputs (p, s, their preconditioned images, two staging vectors) in the peer-mapped slots: the
+        // neighbours write the halo tails directly
+        TEFEM_REQUIRE(tefem_comm_n_slots(s->comm) >= SLOT_COUNT && tefem_comm_slot_doubles(s->comm) >= nl,
+                      "peer-memory vector slots too few / too small (tefem_comm_vec_alloc)");
+        const int me = tefem_comm_rank(s->comm);
+        s->p = tefem_comm_slot(s->comm, me, SLOT_P);
+        s->s = tefem_comm_slot(s->comm, me, SLOT_S);
+        s->ph = tefem_comm_slot(s->comm, me, SLOT_PH);
+        s->sh = tefem_comm_slot(s->comm, me, SLOT_SH);
+        s->xs = tefem_comm_slot(s->comm, me, SLOT_XS);
+        s->xa = tefem_comm_slot(s->comm, me, SLOT_XA);
+        s->peer_halo = true;
+    }
     TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_ictl, 4 * sizeof(int)));
     TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_sc, NSCAL * sizeof(double)));
     if (s->comm) {
@@ -613,20 +717,29 @@ extern "C" int tefem_solver_destroy(tefem_solver* s) {
     return TEFEM_OK;
 }
 
+// Halo description of a row-partitioned solve.  h_nbr / h_send_ptr / h_recv_ptr: neighbour ranks (ascending), the
+// segments of send_idx (owned nodes whose values neighbour k needs, ascending global id) and of the halo tail.
+// Peer-memory halo (the communicator has vector slots): send_dst[k] / send_dpos[k] = destination rank and node position
+// in that rank's local vector of send entry k (device arrays; the position is n_own + halo offset THERE);
+// boundary_rows / interior_rows may be NULL.  NCCL halo (no vector slots): send_dst / send_dpos may be NULL and the
+// interior / boundary row lists are required (the exchange overlaps the interior rows).
 extern "C" int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int32_t* h_nbr,
-                                     const int32_t* h_send_ptr, const int32_t* send_idx, const int32_t* h_recv_ptr,
+                                     const int32_t* h_send_ptr, const int32_t* send_idx, const int32_t* send_dst,
+                                     const int32_t* send_dpos, const int32_t* h_recv_ptr,
                                      const int32_t* boundary_rows, int32_t n_boundary_rows,
                                      const int32_t* interior_rows, int32_t n_interior_rows) {
     TEFEM_REQUIRE(s, "null solver");
     TEFEM_REQUIRE(n_halo == s->n_halo, "n_halo differs from tefem_solver_create");
+    TEFEM_REQUIRE(n_nbr >= 0 && n_nbr <= PEER_MAX_RANKS, "0 .. 8 neighbour ranks");
     TEFEM_REQUIRE(n_nbr == 0 || (h_nbr && h_send_ptr && h_recv_ptr && send_idx), "null halo arrays");
-    TEFEM_REQUIRE(n_boundary_rows + n_interior_rows == s->n_rows, "interior + boundary rows must cover the owned rows");
+    if (s->peer_halo) TEFEM_REQUIRE(n_nbr == 0 || (send_dst && send_dpos), "the peer-memory halo needs send_dst / send_dpos");
+    else TEFEM_REQUIRE(n_boundary_rows + n_interior_rows == s->n_rows, "interior + boundary rows must cover the owned rows");
     s->n_nbr = n_nbr;
     s->nbr.assign(h_nbr, h_nbr + n_nbr);
     s->send_ptr.assign(h_send_ptr, h_send_ptr + n_nbr + 1);
     s->recv_ptr.assign(h_recv_ptr, h_recv_ptr + n_nbr + 1);
     TEFEM_REQUIRE(n_nbr == 0 || s->send_ptr[n_nbr] <= s->n_rows, "send list larger than the owned rows");
-    s->send_idx = send_idx;
+    s->send_idx = send_idx; s->send_dst = send_dst; s->send_dpos = send_dpos;
     s->boundary_rows = boundary_rows; s->n_boundary_rows = n_boundary_rows;
     s->interior_rows = interior_rows; s->n_interior_rows = n_interior_rows;
     return TEFEM_OK;
@@ -658,12 +771,12 @@ static const SpmvCfg& spmv_cfg() {
     return cfg;
 }
 
-template <int DOTS, int UNROLL>
+template <int DOTS, int UNROLL, bool HALO>
 static int spmv_resident_ctas(int threads, int* out) {
     static int cached_threads = 0, cached = 0;
     if (cached_threads != threads) {
         int occ = 0, dev = 0, sms = 0;
-        TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_kernel<DOTS, UNROLL>, threads, 0));
+        TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_kernel<DOTS, UNROLL, HALO>, threads, 0));
         TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
         TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         cached = (occ < 1 ? 1 : occ) * sms;
@@ -673,13 +786,19 @@ static int spmv_resident_ctas(int threads, int* out) {
     return TEFEM_OK;
 }
 
-template <int DOTS, int UNROLL>
+// Optional halo wait of an SpMV launch (peer-memory halo)
+struct SpmvHalo {
+    bool on = false;
+    HaloFlags hf;
+};
+
+template <int DOTS, int UNROLL, bool HALO>
 static int launch_spmv_u(const SpmvCfg& c, const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
                          const double* sys, const double* x, double* y, const double* w, const double* sd, double* partials,
-                         const int* ictl, int* n_cta_out, cudaStream_t st) {
+                         const int* ictl, int* n_cta_out, const SpmvHalo& h, cudaStream_t st) {
     // one resident wave of grid-striding CTAs (no tail), capped by the partial-sum buffers
     int resident = 0;
-    int rc = spmv_resident_ctas<DOTS, UNROLL>(c.threads, &resident);
+    int rc = spmv_resident_ctas<DOTS, UNROLL, HALO>(c.threads, &resident);
     if (rc) return rc;
     if (c.ctas_per_sm > 0 && resident > 148 * c.ctas_per_sm) resident = 148 * c.ctas_per_sm;
     if (resident > MAX_PARTIAL_CTAS) resident = MAX_PARTIAL_CTAS;
@@ -687,7 +806,8 @@ static int launch_spmv_u(const SpmvCfg& c, const int32_t* rowptr, const int32_t*
     if (g64 > resident) g64 = resident;
     const int g = g64 < 1 ? 1 : (int)g64;
     if (n_cta_out) *n_cta_out = g;
-    spmv_kernel<DOTS, UNROLL><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, sd ? sd : x, partials, ictl);
+    spmv_kernel<DOTS, UNROLL, HALO><<<g, c.threads, 0, st>>>(rowptr, colidx, rows, n_rows, sys, x, y, w, sd ? sd : x, partials, ictl,
+                                                            h.hf);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
@@ -695,16 +815,55 @@ static int launch_spmv_u(const SpmvCfg& c, const int32_t* rowptr, const int32_t*
 template <int DOTS>
 static int launch_spmv(const int32_t* rowptr, const int32_t* colidx, const int32_t* rows, int32_t n_rows,
                        const double* sys, const double* x, double* y, const double* w, const double* sd, double* partials,
-                       const int* ictl, int* n_cta_out, cudaStream_t st) {
+                       const int* ictl, int* n_cta_out, cudaStream_t st, const SpmvHalo& h = SpmvHalo()) {
     const SpmvCfg& c = spmv_cfg();
-    if (c.unroll == 4) return launch_spmv_u<DOTS, 4>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, st);
-    if (c.unroll == 1) return launch_spmv_u<DOTS, 1>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, st);
-    return launch_spmv_u<DOTS, 2>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, st);
+    if (h.on) {   // multi-GPU: the tuned configuration only
+        return launch_spmv_u<DOTS, 2, true>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, h, st);
+    }
+    if (c.unroll == 4) return launch_spmv_u<DOTS, 4, false>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, h, st);
+    if (c.unroll == 1) return launch_spmv_u<DOTS, 1, false>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, h, st);
+    return launch_spmv_u<DOTS, 2, false>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, h, st);
+}
+
+// Peer-memory halo, producer side: push the boundary values of slot vector x (one of this rank's slots) into the same
+// slot of the neighbours and raise the flags of a new exchange, whose context is returned for the consumer.
+static int push_halo(tefem_solver* s, const double* x, const int* ictl, SpmvHalo* h, cudaStream_t st) {
+    const int me = tefem_comm_rank(s->comm);
+    const int64_t off = x - tefem_comm_slot(s->comm, me, 0);
+    TEFEM_REQUIRE(off >= 0 && off % tefem_comm_slot_doubles(s->comm) == 0 &&
+                      off / tefem_comm_slot_doubles(s->comm) < tefem_comm_n_slots(s->comm),
+                  "the SpMV input of a multi-GPU solve must be a peer-memory vector slot");
+    const int slot = (int)(off / tefem_comm_slot_doubles(s->comm));
+    h->on = true;
+    const PeerCtx pc = tefem_comm_peer_ctx(s->comm, PEER_CH_HALO);      // next epoch of the halo channel
+    h->hf.n = s->n_nbr; h->hf.epoch = pc.epoch; h->hf.timeout = pc.timeout; h->hf.err = pc.err;
+    for (int k = 0; k < s->n_nbr; ++k) {
+        h->hf.mine[k] = peer_flag(pc, pc.rank, s->nbr[k]);
+        h->hf.theirs[k] = peer_flag(pc, s->nbr[k], pc.rank);
+    }
+    HaloSlots hs;
+    for (int r = 0; r < tefem_comm_world(s->comm); ++r) hs.base[r] = tefem_comm_slot(s->comm, r, slot);
+    const int64_t n_send = s->send_ptr[s->n_nbr];
+    const unsigned g = (unsigned)(n_send > 0 ? ceil_div(n_send, 256) : 1);
+    push_halo_kernel<<<g, 256, 0, st>>>(n_send, s->send_idx, s->send_dst, s->send_dpos, x, hs, h->hf, ictl,
+                                        s->ictl + IN_TICKET);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
 }
 
 // Exchange the halo part of x (owned rows listed in send_idx go out, halo rows come in).
 static int halo_exchange(tefem_solver* s, double* x, const int* ictl, cudaStream_t st) {
     if (!s->comm || s->n_nbr == 0) return TEFEM_OK;
+    if (s->peer_halo) {   // stage through slot XA: owned part in, push, wait, halo tail out
+        TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->xa, x, sizeof(double) * (size_t)s->n_own, cudaMemcpyDeviceToDevice, st));
+        SpmvHalo h;
+        int rc = push_halo(s, s->xa, nullptr, &h, st);
+        if (rc) return rc;
+        const int64_t n_tail = s->n_loc - s->n_own;
+        pull_halo_kernel<<<grid_for(n_tail, 256), 256, 0, st>>>(n_tail, s->xa + s->n_own, x + s->n_own, h.hf);
+        TEFEM_LAUNCH_CHECK();
+        return TEFEM_OK;
+    }
     const int64_t n_send = s->send_ptr[s->n_nbr];
     if (n_send > 0) {
         pack_halo_kernel<<<(unsigned)ceil_div(4 * n_send, 256), 256, 0, st>>>(n_send, s->send_idx, x, s->sendbuf, ictl);
@@ -714,7 +873,9 @@ static int halo_exchange(tefem_solver* s, double* x, const int* ictl, cudaStream
                                         s->recv_ptr.data(), x + s->n_own, st);
 }
 
-// y = A x with the halo exchange of x overlapped with the interior rows; DOTS partials packed.
+// y = A x with the halo of x.  Peer-memory halo (default): push kernel + ONE SpMV launch over all rows in natural
+// order that waits for the neighbours' flags.  NCCL halo (communicator without vector slots): pack + send/recv on a
+// second stream overlapped with the interior rows, boundary rows after the halo event.  DOTS partials packed.
 template <int DOTS>
 static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys, double* x,
                      double* y, const double* w, const double* sd, const int* ictl, int* n_part_ctas, cudaStream_t st) {
@@ -725,9 +886,17 @@ static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* coli
         if (rc0) return rc0;
         return prof_end(s, st);
     }
-    // comm stream: pack + send/recv ; main stream: interior rows ; then boundary rows
     int rc = prof_begin(s, st);
     if (rc) return rc;
+    if (s->peer_halo) {
+        SpmvHalo h;
+        rc = push_halo(s, x, ictl, &h, st);
+        if (rc) return rc;
+        rc = launch_spmv<DOTS>(rowptr, colidx, nullptr, s->n_rows, sys, x, y, w, sd, s->partials, ictl, n_part_ctas, st, h);
+        if (rc) return rc;
+        return prof_end(s, st);
+    }
+    // comm stream: pack + send/recv ; main stream: interior rows ; then boundary rows
     TEFEM_CUDA_CHECK(cudaEventRecord(s->ev_ready, st));
     TEFEM_CUDA_CHECK(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
     rc = halo_exchange(s, x, ictl, s->comm_stream);
@@ -817,7 +986,12 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
     for (;;) {
         // ---- (re)start: r = b - A x, rhat = p = r
         int npc = 0;
-        int rc = dist_spmv<0>(s, rowptr, colidx, sys, x, s->t, nullptr, nullptr, nullptr, &npc, st);
+        double* xin = x;
+        if (s->peer_halo && s->n_nbr > 0) {   // the operator input must be a peer-memory slot: stage the owned part of x
+            TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->xs, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            xin = s->xs;
+        }
+        int rc = dist_spmv<0>(s, rowptr, colidx, sys, xin, s->t, nullptr, nullptr, nullptr, &npc, st);
         if (rc) return rc;
         init_residual_kernel<<<vgrid, 256, 0, st>>>(n, b, s->t, x, s->r, s->rhat, s->p, s->partials);
         TEFEM_LAUNCH_CHECK();

@@ -20,12 +20,13 @@ namespace tefem {
 
 constexpr int PEER_MAX_RANKS = 8;
 constexpr int PEER_SMALL = 16;                       // doubles per small packet
-constexpr int64_t PEER_FLAG_BYTES = 1024;            // 2 channels x 2 parities x 8 ranks x 4 B, padded
+constexpr int64_t PEER_FLAG_BYTES = 1024;            // 3 channels x 2 parities x 8 ranks x 4 B, padded
 constexpr int64_t PEER_SMALL_BYTES = 2 * PEER_SMALL * 8;
 constexpr int64_t PEER_BIG_OFFSET = 2048;
-constexpr long long PEER_TIMEOUT = 4000000000LL;     // ~2 s at 1.9 GHz
+constexpr long long PEER_TIMEOUT_DEFAULT = 60000000000LL;     // ~30 s at 1.9 GHz (tefem_comm_set_timeout overrides it)
 
-enum { PEER_CH_DOTS = 0, PEER_CH_COARSE = 1 };
+// channels: dot-product packets, restricted residual of the coarse correction, halo values of the SpMV input
+enum { PEER_CH_DOTS = 0, PEER_CH_COARSE = 1, PEER_CH_HALO = 2, PEER_N_CHANNELS = 3 };
 
 struct PeerCtx {
     int world = 1, rank = 0;
@@ -34,12 +35,17 @@ struct PeerCtx {
     int64_t cap = 0;                                 // doubles per parity of the big buffer
     char* base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int* err = nullptr;                              // device int: set to 1 on a wait time-out
+    long long timeout = PEER_TIMEOUT_DEFAULT;        // cycles a wait may spin before it gives up
 };
 
+// flag[channel][parity][source rank] in `owner`'s region (host + device)
 #ifdef __CUDACC__
-__device__ __forceinline__ uint32_t* peer_flag(const PeerCtx& c, int owner, int src) {
+__host__ __device__
+#endif
+inline uint32_t* peer_flag(const PeerCtx& c, int owner, int src) {
     return reinterpret_cast<uint32_t*>(c.base[owner]) + ((c.channel * 2 + (int)(c.epoch & 1u)) * PEER_MAX_RANKS + src);
 }
+#ifdef __CUDACC__
 __device__ __forceinline__ double* peer_small(const PeerCtx& c, int owner) {
     return reinterpret_cast<double*>(c.base[owner] + PEER_FLAG_BYTES) + (c.epoch & 1u) * PEER_SMALL;
 }
@@ -68,15 +74,20 @@ __device__ __forceinline__ void ld_volatile_v2(const double* p, double& a, doubl
 __device__ __forceinline__ void peer_signal(const PeerCtx& c, int t) {
     if (t < c.world) st_release_sys(peer_flag(c, t, c.rank), c.epoch);
 }
-// Thread `t` (< world) waits for rank t's flag in the local region.
-__device__ __forceinline__ void peer_wait(const PeerCtx& c, int t) {
-    if (t < c.world) {
-        const uint32_t* f = peer_flag(c, c.rank, t);
-        const long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(f) - c.epoch) < 0) {
-            if (clock64() - t0 > PEER_TIMEOUT) { *c.err = 1; break; }
-        }
+// Thread `t` (< world) waits for rank t's flag in the local region.  A wait that expires records the error and every
+// later wait on this communicator returns at once (the host reports it after its next synchronisation and the
+// communicator stays marked until tefem_comm_reset_error): a lost rank costs ONE time-out, not one per kernel.
+__device__ __forceinline__ void peer_wait_flag(const PeerCtx& c, int src) {
+    const uint32_t* f = peer_flag(c, c.rank, src);
+    if ((int32_t)(ld_acquire_sys(f) - c.epoch) >= 0) return;
+    if (*reinterpret_cast<volatile int*>(c.err)) return;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - c.epoch) < 0) {
+        if (clock64() - t0 > c.timeout) { *c.err = 1; break; }
     }
+}
+__device__ __forceinline__ void peer_wait(const PeerCtx& c, int t) {
+    if (t < c.world) peer_wait_flag(c, t);
 }
 #endif
 

@@ -102,10 +102,13 @@ __global__ void __launch_bounds__(256) coarse_start_kernel(int64_t n, const doub
 
 // Multi-GPU form of coarse_start_kernel, fused with the all-reduce of the restricted residual over NVLink peer
 // memory (tefem_peer.cuh): every rank's restriction kernel wrote its partial P1^T r into its own peer buffer; this
-// kernel raises the flags, waits for all ranks, adds the partial vectors of all ranks in rank order (bitwise
-// identical on every rank: level 1 and 2 stay consistent replicas) and applies D1^-1 and the first damped-Jacobi
-// step.  One thread per aggregate (8 doubles, four 128-bit volatile loads per rank).
+// kernel raises the flags, waits for all ranks, adds the partial vectors in rank order (bitwise identical on every
+// rank: level 1 and 2 stay consistent replicas) and applies D1^-1 and the first damped-Jacobi step.
+// agg_ranks[i] (optional): bit r set iff rank r owns fine nodes of aggregate i - only those ranks' partial sums are
+// read (the others are exact zeros), i.e. 1 - 2 remote reads per aggregate for a slab partition instead of world:
+// 6 x fewer bytes over NVLink at 8 GPUs.  One thread per aggregate (8 doubles, four 128-bit volatile loads per rank).
 __global__ void __launch_bounds__(128) peer_coarse_start_kernel(const PeerCtx pc, int32_t n_agg,
+                                                                const uint8_t* __restrict__ agg_ranks,
                                                                 const double* __restrict__ dinv, double wc,
                                                                 double* __restrict__ bc, double* __restrict__ xc) {
     if (blockIdx.x == 0) {
@@ -116,15 +119,16 @@ __global__ void __launch_bounds__(128) peer_coarse_start_kernel(const PeerCtx pc
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_agg) return;
+    const unsigned mask = agg_ranks ? (unsigned)agg_ranks[i] : 0xffu;
     double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int r = 0; r < pc.world; ++r) {
+        if (!((mask >> r) & 1u)) continue;
         const double* src = peer_big(pc, r) + 8 * i;
+        double v[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double a, b;
-            ld_volatile_v2(src + 2 * q, a, b);
-            s[2 * q] += a; s[2 * q + 1] += b;
-        }
+        for (int q = 0; q < 4; ++q) ld_volatile_v2(src + 2 * q, v[2 * q], v[2 * q + 1]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[q] += v[q];
     }
     const double* D = dinv + 64 * i;
 #pragma unroll
@@ -140,38 +144,55 @@ __global__ void __launch_bounds__(128) peer_coarse_start_kernel(const PeerCtx pc
 // out = c0 * xin + c1 * (b - A x) for a 4x4-block CSR matrix A in SINGLE precision (b == nullptr: 0; xin is read
 // only when c0 != 0): the level-1 operator, and the transfer operators P2^T / P2 between levels 1 and 2.  It only
 // shapes the preconditioner (a fixed linear operator either way), the Krylov vectors and the fine operator stay
-// fp64; half the bytes keep the whole level in L2.  4 threads per coarse node, one 128-bit load per block row.
+// fp64; half the bytes keep the whole level in L2.
+// COARSE_LANES (8) lanes share one block row: lane l multiplies the blocks s + l, s + l + 8, ... (four 128-bit loads of
+// the block, one 256-bit load of x_j) and a fixed shuffle tree adds the 4 row sums; lanes 0 .. 3 store.  The level-1
+// rows hold ~54 blocks: with one thread per scalar row (round 1) a sweep was a 27-trip dependent loop on 110 k threads,
+// i.e. latency bound at ~1/3 of the L2 bandwidth; 8 lanes per row give 7 independent trips on 220 k threads.  The sum
+// order is fixed (lane-strided partial sums, then the tree), so every rank computes bitwise the same coarse vectors.
+constexpr int COARSE_LANES = 8;
 __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restrict__ rowptr,
                                                           const int32_t* __restrict__ colidx, int32_t n_rows,
                                                           const float* __restrict__ sys, const double* __restrict__ x,
                                                           const double* __restrict__ b, const double* xin,
                                                           double c0, double c1, double* out) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= 4 * (int64_t)n_rows) return;
-    const int32_t i = (int32_t)(tid >> 2);
-    const int r = (int)(tid & 3);
-    const int32_t s = rowptr[i], t = rowptr[i + 1];
-    double acc0 = 0.0, acc1 = 0.0;
-    int32_t p = s;
-    for (; p + 2 <= t; p += 2) {
-        const int32_t j0 = colidx[p], j1 = colidx[p + 1];
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sys + 16 * (int64_t)p + 4 * r));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(sys + 16 * (int64_t)(p + 1) + 4 * r));
-        const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0);
-        const double2 u1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0 + 2);
-        const double2 w0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j1);
-        const double2 w1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j1 + 2);
-        acc0 += (double)a0.x * u0.x + (double)a0.y * u0.y + (double)a0.z * u1.x + (double)a0.w * u1.y;
-        acc1 += (double)a1.x * w0.x + (double)a1.y * w0.y + (double)a1.z * w1.x + (double)a1.w * w1.y;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t i = (int32_t)(gid / COARSE_LANES);
+    const int l = (int)(gid % COARSE_LANES);
+    const bool live = i < n_rows;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (live) {
+        const int32_t s = rowptr[i], t = rowptr[i + 1];
+        for (int32_t p = s + l; p < t; p += COARSE_LANES) {
+            const int32_t j = colidx[p];
+            const float4* blk = reinterpret_cast<const float4*>(sys + 16 * (int64_t)p);
+            const float4 r0 = __ldg(blk), r1 = __ldg(blk + 1), r2 = __ldg(blk + 2), r3 = __ldg(blk + 3);
+            const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j);
+            const double2 u1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j + 2);
+            a0 += (double)r0.x * u0.x + (double)r0.y * u0.y + (double)r0.z * u1.x + (double)r0.w * u1.y;
+            a1 += (double)r1.x * u0.x + (double)r1.y * u0.y + (double)r1.z * u1.x + (double)r1.w * u1.y;
+            a2 += (double)r2.x * u0.x + (double)r2.y * u0.y + (double)r2.z * u1.x + (double)r2.w * u1.y;
+            a3 += (double)r3.x * u0.x + (double)r3.y * u0.y + (double)r3.z * u1.x + (double)r3.w * u1.y;
+        }
     }
-    if (p < t) {
-        const int32_t j0 = colidx[p];
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sys + 16 * (int64_t)p + 4 * r));
-        const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0);
-        const double2 u1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j0 + 2);
-        acc0 += (double)a0.x * u0.x + (double)a0.y * u0.y + (double)a0.z * u1.x + (double)a0.w * u1.y;
+    // all 32 lanes of the warp take part in the shuffles (rows never straddle a warp: 8 divides 32)
+#pragma unroll
+    for (int off = COARSE_LANES / 2; off > 0; off >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, off, COARSE_LANES);
+        a1 += __shfl_down_sync(0xffffffffu, a1, off, COARSE_LANES);
+        a2 += __shfl_down_sync(0xffffffffu, a2, off, COARSE_LANES);
+        a3 += __shfl_down_sync(0xffffffffu, a3, off, COARSE_LANES);
     }
-    out[tid] = (c0 != 0.0 ? c0 * xin[tid] : 0.0) + c1 * ((b ? b[tid] : 0.0) - (acc0 + acc1));
+    // lane r < 4 keeps row r: a_r of lane 0 is fetched by lane r
+    const double s1 = __shfl_sync(0xffffffffu, a1, 0, COARSE_LANES);
+    const double s2 = __shfl_sync(0xffffffffu, a2, 0, COARSE_LANES);
+    const double s3 = __shfl_sync(0xffffffffu, a3, 0, COARSE_LANES);
+    const double s0 = __shfl_sync(0xffffffffu, a0, 0, COARSE_LANES);
+    if (live && l < 4) {
+        const double acc = l == 0 ? s0 : (l == 1 ? s1 : (l == 2 ? s2 : s3));
+        const int64_t k = 4 * (int64_t)i + l;
+        out[k] = (c0 != 0.0 ? c0 * xin[k] : 0.0) + c1 * ((b ? b[k] : 0.0) - acc);
+    }
 }
 
 // y = M x for a dense row-major n x n single-precision matrix; one CTA of 128 threads per row, fixed reduction tree.
@@ -203,6 +224,7 @@ struct tefem_precond {
     int n_pre = 1, n_post = 1;                   // damped-Jacobi sweeps on level 1 before / after the level-2 correction
     double *rc = nullptr, *bc = nullptr, *xc = nullptr, *tc = nullptr, *r2 = nullptr, *x2 = nullptr;
     tefem_comm* comm = nullptr;
+    const uint8_t* agg_ranks = nullptr;          // multi-GPU: which ranks contribute to an aggregate's restricted residual
     // TEFEM_PROFILE_PRECOND=1 (diagnostics, stderr at destroy): device time of the three parts of an application -
     // restriction + all-reduce over the ranks + first sweep (includes waiting for the slowest rank), the level-1 / level-2
     // cycle (replicated work), the prolongation.  Synchronises the stream after every application: not for timed runs.
@@ -258,6 +280,12 @@ extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t
     return TEFEM_OK;
 }
 
+extern "C" int tefem_precond_set_agg_ranks(tefem_precond* p, const uint8_t* agg_ranks) {
+    TEFEM_REQUIRE(p, "null preconditioner");
+    p->agg_ranks = agg_ranks;
+    return TEFEM_OK;
+}
+
 extern "C" int tefem_precond_destroy(tefem_precond* p) {
     if (p && p->profile) {
         if (p->n_apply > 0)
@@ -275,7 +303,9 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
     TEFEM_REQUIRE(p && r && z, "null pointer");
     const int64_t n1 = 8 * (int64_t)p->n1;                    // scalar size of level 1
     const int32_t np1 = 2 * p->n1, np2 = 2 * p->n2;           // pseudo nodes (4-DOF block rows) of levels 1 and 2
-    const unsigned g1 = (unsigned)ceil_div(n1, 256), g2 = (unsigned)ceil_div(4 * (int64_t)np2, 256);
+    const unsigned g1 = (unsigned)ceil_div(n1, 256);                                           // one thread per scalar of level 1
+    const unsigned gs1 = (unsigned)ceil_div((int64_t)COARSE_LANES * np1, 256);                 // coarse_spmv: 8 lanes per block row
+    const unsigned gs2 = (unsigned)ceil_div((int64_t)COARSE_LANES * np2, 256);
     const unsigned gr = (unsigned)ceil_div(32 * (int64_t)p->n1, 256);
     if (p->profile) cudaEventRecord(p->ev[0], st);
     // level 0 -> 1: rc = P1^T r, summed over the ranks (levels 1 and 2 are replicated): the restriction writes
@@ -287,7 +317,8 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
         double* mine = reinterpret_cast<double*>(pc.base[pc.rank] + PEER_BIG_OFFSET) + (int64_t)(pc.epoch & 1u) * pc.cap;
         restrict_kernel<<<gr, 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, mine);
         TEFEM_LAUNCH_CHECK();
-        peer_coarse_start_kernel<<<(unsigned)ceil_div((int64_t)p->n1, 128), 128, 0, st>>>(pc, p->n1, p->dinv1, p->omega_c, p->bc, p->xc);
+        peer_coarse_start_kernel<<<(unsigned)ceil_div((int64_t)p->n1, 128), 128, 0, st>>>(pc, p->n1, p->agg_ranks, p->dinv1, p->omega_c,
+                                                                                          p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();
     } else {
         restrict_kernel<<<gr, 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, p->rc);
@@ -301,20 +332,20 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
     // into the other buffer: x' = x + wc (bc - A1^ x).
     double *cur = p->xc, *alt = p->rc;
     for (int k = 1; k < p->n_pre; ++k) {
-        coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
+        coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
         TEFEM_LAUNCH_CHECK();
         double* t = cur; cur = alt; alt = t;
     }
-    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, nullptr, 0.0, 1.0, p->tc);
+    coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, nullptr, 0.0, 1.0, p->tc);
     TEFEM_LAUNCH_CHECK();                                                                       // tc = bc - A1^ x
-    coarse_spmv_kernel<<<g2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, p->r2);
+    coarse_spmv_kernel<<<gs2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, p->r2);
     TEFEM_LAUNCH_CHECK();                                                                       // r2 = P2^T tc
     dense_matvec_kernel<<<(unsigned)(4 * np2), 128, 0, st>>>(4 * np2, p->inv2, p->r2, p->x2);
     TEFEM_LAUNCH_CHECK();                                                                       // x2 = A2^-1 r2
-    coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, cur);
+    coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, cur);
     TEFEM_LAUNCH_CHECK();                                                                       // x += P2 x2
     for (int k = 0; k < p->n_post; ++k) {
-        coarse_spmv_kernel<<<g1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
+        coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
         TEFEM_LAUNCH_CHECK();
         double* t = cur; cur = alt; alt = t;
     }

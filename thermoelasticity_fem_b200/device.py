@@ -46,6 +46,9 @@ class DeviceMesh:
         self.cta_xyz = self.coords[S.cta_nodes.long()].contiguous()
         self._h_max = S.h_max()
         self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
+        # kernel form of K1: 0 = dynamic chunks, one 512-thread CTA per SM (default); 64 | 128 | 256 = threads per CTA of
+        # the tile-synchronous kernel (measurement knob, pair with tiles of 2 x threads blocks)
+        self.asm_threads = 0
 
     # ---- K1 -------------------------------------------------------------------------------------
     def alloc_planes(self, which, alpha_M=0., alpha_K=0.):
@@ -63,6 +66,7 @@ class DeviceMesh:
         mask = sum({"M": _lib.OP_M, "K": _lib.OP_K, "D": _lib.OP_D}[nm] for nm in set(ops))
         self.bad_elem.fill_(_lib.INT32_MAX)
         p = _lib.ptr
+        _lib.check(self.lib.tefem_assemble_set_threads(int(self.asm_threads)))
         _lib.check(self.lib.tefem_assemble(
             p(self.mat_table), self.n_mat, S.n_cta, p(self._h_max), p(S.cta_hdr), p(S.cta_elems),
             p(S.cta_conn8), p(self.cta_xyz), p(S.item_inc), p(S.item_meta), p(S.split_block), p(S.split_meta),
@@ -176,15 +180,19 @@ class KrylovSolver:
         self.n_halo = n_halo
         self._keep = []
 
-    def set_halo(self, nbr, send_ptr, send_idx, recv_ptr, boundary_rows, interior_rows):
+    def set_halo(self, nbr, send_ptr, send_idx, recv_ptr, boundary_rows=None, interior_rows=None, send_dst=None,
+                 send_dpos=None):
+        """Peer-memory halo (communicator with vector slots): send_dst / send_dpos = destination rank and node position
+        there of every send entry (int32 device tensors); NCCL halo: the boundary / interior row lists."""
         nbr = np.ascontiguousarray(nbr, dtype=np.int32)
         send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int32)
         recv_ptr = np.ascontiguousarray(recv_ptr, dtype=np.int32)
-        self._keep = [send_idx, boundary_rows, interior_rows]
+        self._keep = [send_idx, boundary_rows, interior_rows, send_dst, send_dpos]
         p = _lib.ptr
         _lib.check(self.lib.tefem_solver_set_halo(
-            self.handle, self.n_halo, len(nbr), p(nbr), p(send_ptr), p(send_idx), p(recv_ptr),
-            p(boundary_rows), int(boundary_rows.numel()), p(interior_rows), int(interior_rows.numel())))
+            self.handle, self.n_halo, len(nbr), p(nbr), p(send_ptr), p(send_idx), p(send_dst), p(send_dpos), p(recv_ptr),
+            p(boundary_rows), int(boundary_rows.numel()) if boundary_rows is not None else 0,
+            p(interior_rows), int(interior_rows.numel()) if interior_rows is not None else 0))
 
     def bicgstab(self, sys, b, x, rtol=1e-10, max_iter=20000, check_every=16):
         """Solves sys x = b (both already block-Jacobi scaled); x holds the initial guess and the result.

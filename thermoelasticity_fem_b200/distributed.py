@@ -56,6 +56,31 @@ class Comm:
         _lib.check(self.lib.tefem_comm_create(ctypes.byref(self.handle), path, raw, self.world, self.rank))
 
         self.peer_cap = -1
+        self.slot_doubles = 0
+
+    def setup_vectors(self, n_local_nodes):
+        """Allocate and exchange the peer-mapped vector slots of the solver (include/tefem.h, tefem_comm_vec_alloc):
+        once per communicator, BEFORE the KrylovSolver is created.  Every rank passes its own local node count (owned +
+        halo); the slots are sized for the largest."""
+        import torch.distributed as dist
+        need = ((4 * int(n_local_nodes) + 15) // 16) * 16
+        t = torch.tensor([need], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        need = int(t.item())
+        if self.slot_doubles:
+            if need > self.slot_doubles:
+                raise RuntimeError("peer-memory vector slots already allocated with a smaller size")
+            return
+        raw = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.tefem_comm_vec_alloc(self.handle, int(self.lib.tefem_solver_peer_slots()), need, raw))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(raw.raw))
+        _lib.check(self.lib.tefem_comm_vec_open(self.handle, ctypes.create_string_buffer(b"".join(handles), 64 * self.world)))
+        dist.barrier()
+        self.slot_doubles = need
+
+    def set_timeout(self, seconds):
+        _lib.check(self.lib.tefem_comm_set_timeout(self.handle, float(seconds)))
 
     def setup_peer(self, big_cap_doubles=0):
         """Allocate and exchange the peer-memory region of the in-kernel reductions (include/tefem.h,
@@ -112,6 +137,27 @@ def dirichlet_node_data(tri_groups_global, dict_dirichlet_U, dict_dirichlet_thet
     return dofs, np.array([fill[d] for d in dofs]), np.array([lift[d] for d in dofs])
 
 
+def halo_destinations(lp: LocalProblem):
+    """Per send entry of `lp`: destination rank and node position in THAT rank's local vector (its n_own + the offset of
+    this rank's segment in its halo tail).  Collective: every rank publishes (n_own, neighbours, halo offsets)."""
+    import torch.distributed as dist
+    mine = (int(lp.n_own), [int(q) for q in lp.nbr], [int(v) for v in lp.recv_ptr])
+    table = [None] * lp.world
+    dist.all_gather_object(table, mine)
+    n_send = int(lp.send_ptr[-1])
+    dst = np.zeros(n_send, dtype=np.int32)
+    dpos = np.zeros(n_send, dtype=np.int32)
+    for k, q in enumerate(lp.nbr):
+        n_own_q, nbr_q, recv_ptr_q = table[int(q)]
+        j = nbr_q.index(lp.rank)                         # my segment in q's halo tail
+        s0, s1 = int(lp.send_ptr[k]), int(lp.send_ptr[k + 1])
+        if recv_ptr_q[j + 1] - recv_ptr_q[j] != s1 - s0:
+            raise RuntimeError(f"halo mismatch between ranks {lp.rank} and {q}")
+        dst[s0:s1] = q
+        dpos[s0:s1] = n_own_q + recv_ptr_q[j] + np.arange(s1 - s0)
+    return dst, dpos
+
+
 def surface_node_weights(coords_of, tri_global):
     """Lumped nodal weights area/3 with the reference's 'area' 0.5*|X12.X13| (model.py:153), summed per GLOBAL node
     in triangle order.  coords_of(ids) -> [n, 3]."""
@@ -131,7 +177,11 @@ class DistributedTransient:
 
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
                  alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=16,
-                 comm=None, precond="multilevel"):
+                 comm=None, precond="multilevel", halo="peer"):
+        """halo: 'peer' (default) - boundary values are stored straight into the neighbours' vectors over NVLink and the
+        SpMV waits for flags; 'nccl' - packed ncclSend / ncclRecv overlapped with the interior rows (measured alternative)."""
+        assert halo in ("peer", "nccl")
+        self.halo = halo
         self.lp, self.comm = lp, comm
         self.alpha_M, self.alpha_K = alpha_M, alpha_K
         self.gamma, self.beta = gamma, beta
@@ -177,6 +227,8 @@ class DistributedTransient:
         d_layout = layout.n_planes(layout.plane_map_D(self.alpha_M, self.alpha_K))
         self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
         self.dinv = dm.block_jacobi_scale(self.sys)
+        if self.comm is not None and self.halo == "peer":
+            self.comm.setup_vectors(lp.n_local)          # before the solver: it keeps its SpMV inputs in the slots
         self.krylov = KrylovSolver(dm, lp.n_halo, self.comm)
         if self.comm is not None and self.precond_kind != "multilevel":
             self.comm.setup_peer(0)
@@ -185,10 +237,19 @@ class DistributedTransient:
             from .multilevel import TwoLevelPreconditioner
             self.precond = TwoLevelPreconditioner(dm, self.sys, comm=self.comm)
             self.krylov.set_precond(self.precond)
-        i32 = torch.int32
-        self.krylov.set_halo(lp.nbr, lp.send_ptr, torch.from_numpy(lp.send_idx.astype(np.int32)).to(dev), lp.recv_ptr,
-                             torch.from_numpy(lp.boundary_rows.astype(np.int32)).to(dev),
-                             torch.from_numpy(lp.interior_rows.astype(np.int32)).to(dev))
+        send_idx = torch.from_numpy(lp.send_idx.astype(np.int32)).to(dev)
+        if self.comm is not None and self.halo == "peer":
+            dst, dpos = halo_destinations(lp)
+            self.krylov.set_halo(lp.nbr, lp.send_ptr, send_idx, lp.recv_ptr,
+                                 send_dst=torch.from_numpy(dst).to(dev), send_dpos=torch.from_numpy(dpos).to(dev))
+        else:
+            self.krylov.set_halo(lp.nbr, lp.send_ptr, send_idx, lp.recv_ptr,
+                                 torch.from_numpy(lp.boundary_rows.astype(np.int32)).to(dev),
+                                 torch.from_numpy(lp.interior_rows.astype(np.int32)).to(dev))
+        if self.comm is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier()                               # every rank is set up before the first in-kernel wait
         n_loc = 4 * lp.n_local
         z = lambda: torch.zeros(n_loc, dtype=torch.float64, device=dev)
         self._x, self._v, self._a, self._a_new, self._w1, self._w2, self._rhs, self._b = (z() for _ in range(8))

@@ -285,8 +285,21 @@ class TwoLevelPreconditioner:
         self.agg2 = agg2
         self.n1, self.n2, self.h, self.H1 = n1, n2, h, H1
         self.factor1, self.omega, self.omega_c, self.n_pre, self.n_post = factor1, omega, omega_c, n_pre, n_post
+        self.agg_ranks = None
         if comm is not None:
             comm.setup_peer(8 * n1)               # the restricted residual is all-reduced through peer memory
+            # which ranks own fine nodes of an aggregate: only their partial sums are read over NVLink
+            dist = _dist()
+            mine = ((agg_ptr[1:] - agg_ptr[:-1]) > 0).to(torch.int32)
+            if dist is not None:
+                parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+                dist.all_gather(parts, mine)
+            else:
+                parts = [mine]
+            bits = torch.zeros(n1, dtype=torch.int32, device=dev)
+            for r, m in enumerate(parts):
+                bits |= m << r
+            self.agg_ranks = bits.to(torch.uint8).contiguous()
         self.work = torch.zeros(int(lib.tefem_precond_work_doubles(n1, n2)), **f64)
         self.handle = ctypes.c_void_p()
         self.lib = lib
@@ -296,6 +309,8 @@ class TwoLevelPreconditioner:
             int(n_post), n2,
             p(self.r2_rowptr), p(self.r2_colidx), p(self.r2_vals), p(self.p2_rowptr), p(self.p2_colidx), p(self.p2_vals),
             p(self.inv2), p(self.work), comm.handle if comm is not None else None))
+        if self.agg_ranks is not None:
+            _lib.check(lib.tefem_precond_set_agg_ranks(self.handle, p(self.agg_ranks)))
 
     def apply(self, r, z):
         _lib.check(self.lib.tefem_precond_apply(self.handle, _lib.ptr(r), _lib.ptr(z), _lib.stream_ptr()))

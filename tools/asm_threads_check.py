@@ -22,9 +22,9 @@ E = conn.shape[0]
 conn_d = torch.from_numpy(conn).cuda()
 ref = None
 for threads, items in ((256, 512), (128, 256), (64, 128), (128, 384), (64, 192)):
-    os.environ["TEFEM_ASM_THREADS"] = str(threads)
     S = build_schedule(conn_d, pts.shape[0], items_per_cta=items, elem_budget=int(1.21 * items))
     dm = DeviceMesh(pts, conn, np.zeros(E, dtype=np.int32), table, schedule=S)
+    dm.asm_threads = threads
     line = f"threads {threads:3d} tile {items:3d}:"
     for ops in ("K", "MKD"):
         out = dm.assemble(ops, 0.2, 0.2)
@@ -42,4 +42,3 @@ for threads, items in ((256, 512), (128, 256), (64, 128), (128, 384), (64, 192))
             else:
                 line += " bitwise=" + ("YES" if all(torch.equal(ref[k], out[k]) for k in out) else "NO")
     print(line, flush=True)
-os.environ.pop("TEFEM_ASM_THREADS", None)

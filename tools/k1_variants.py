@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from thermoelasticity_fem_b200 import build as B  # noqa: E402
 
 VARIANTS = {
-    "sselect": ["-DASM_S_SELECT"],                       # S_a by compares on values held in (uniform) registers
+    "tabload": ["-DASM_TAB_LOAD"],                       # round-1 form: S_a / NN_ab loaded from shared-memory tables
     "persm768": ["-DASM_THREADS_PER_SM=768"],            # register cap 85: three 256-thread CTAs per SM where shared memory allows
 }
 

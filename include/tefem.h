@@ -173,11 +173,13 @@ int tefem_form_system(const int32_t* rowptr, const int32_t* colidx, int32_t n_ro
                       double* sys, void* stream);
 
 /* Block-Jacobi setup (kernel K5): inverts the 4x4 diagonal block of every node row (partial
- * pivoting) into dinv[N,16] and left-scales the system in place, sys <- blockdiag(dinv) * sys,
- * so that the Krylov iteration needs no separate preconditioner application.
- * diag_idx[N] = position of the diagonal block of each row.                                    */
+ * pivoting) into dinv[N,16] and, when scale != 0, left-scales the system in place,
+ * sys <- blockdiag(dinv) * sys, so that BiCGSTAB needs no separate preconditioner application
+ * (scale = 0 keeps sys: tefem_cg applies dinv symmetrically).
+ * diag_idx[N] = position of the diagonal block of each row; singular: one int32 of caller-owned
+ * device memory (scratch; the library allocates nothing).  Synchronises the stream.            */
 int tefem_block_jacobi_scale(const int32_t* rowptr, const int32_t* diag_idx, int32_t n_rows,
-                             double* sys, double* dinv, void* stream);
+                             double* sys, double* dinv, int32_t* singular, int scale, void* stream);
 
 /* z[4N] = blockdiag(dinv) * r   (applies the same scaling to a right-hand side); entries of the
  * constrained DOFs (dir_mask != 0, may be NULL) are set to 0 (their unknown is eliminated).      */
@@ -264,12 +266,26 @@ int tefem_solver_halo_exchange(tefem_solver* s, double* x, void* stream);
  * Solves sys x = b where sys and b have ALREADY been scaled by tefem_block_jacobi_scale/apply.
  * Stops when, for each field f in {u rows, theta rows}, ||(b - sys x)_f|| <= rtol * ||b_f|| (a field with
  * b_f = 0 is measured against ||x_f||): the TRUE residual is re-evaluated before returning and
- * recursive-residual drift triggers a restart from the current x; when two restarts in a row cannot
- * improve the true residual (the eps*cond floor) the solve returns OK if it is within 100*rtol.  x holds the initial guess
- * on entry.  h_info[4] = {iterations, restarts, final relative residual, ||b||}.                */
+ * recursive-residual drift triggers a restart from the current x.  When two restarts in a row cannot
+ * improve the true residual (the eps*cond floor of working precision) the solve stops: it returns OK only
+ * if the residual is within floor_factor * rtol (floor_factor >= 1; 1 = never accept above rtol) and then
+ * raises h_info[4], otherwise TEFEM_ERR_NO_CONVERGE.  x holds the initial guess on entry.
+ * h_info[6] = {iterations, restarts, final relative residual, ||b||, floor flag (1: stalled and accepted
+ * above rtol), stall count}.                                                                    */
 int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx,
                    const double* sys, const double* b, double* x,
-                   double rtol, int max_iter, int check_every, double* h_info, void* stream);
+                   double rtol, int max_iter, int check_every, double floor_factor, double* h_info,
+                   void* stream);
+
+/* Block-Jacobi-preconditioned CG for a SYMMETRIC POSITIVE DEFINITE system in the same block layout (sys UNSCALED,
+ * dinv from tefem_block_jacobi_scale(.., scale = 0)).  Used by the staged steady-state solve: the reference's K has
+ * no theta -> u block (model.py:94-103), so spsolve(K_ff, F_f) (solvers.py:26) is K_tt theta = F_t followed by
+ * K_uu u = F_u - K_ut theta, each SPD once the other field's DOFs are eliminated (identity rows).  One SpMV per
+ * iteration, a persistent cooperative kernel per batch of check_every iterations.  Same stopping rule (per field,
+ * on dinv * residual, true residual verified) and h_info as tefem_bicgstab.  Single GPU.          */
+int tefem_cg(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys,
+             const double* dinv, const double* b, double* x, double rtol, int max_iter, int check_every,
+             double floor_factor, double* h_info, void* stream);
 
 /* Fused Newmark kernels (kernel K7), solvers.py:167-178.
  * predictor: w1 = v + (1-gamma) dt a ; w2 = x + dt v + 0.5 dt^2 (1-2 beta) a   (zero on constrained DOFs)

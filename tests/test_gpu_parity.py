@@ -235,6 +235,8 @@ def test_steady_state_sandwich(sandwich_mesh1, sandwich):
                   dict_heat_flux={6: -25.}, dict_heat_source=None)
     solver = LinearSteadyState(model)
     solver.solve()
+    # default on the reference's own mesh: the staged solve (K_tt then K_uu, CG); it must reach rtol, not the stall floor
+    assert solver.solve_info["method"] == "staged-cg" and not solver.solve_info["floor"], solver.solve_info
     for k in ("free_dofs", "free_dofs_U", "free_dofs_theta"):
         assert np.array_equal(getattr(model, k), g[k]), k
     assert np.max(np.abs(model.vec_F - g["F"])) <= 1e-13 * np.abs(g["F"]).max()
@@ -279,6 +281,7 @@ def test_transient_sandwich_first_steps(sandwich_mesh2, sandwich):
     states = {}
     for i in range(1, n_steps + 1):
         info = solver.step(i)
+        assert not info["floor"] and info["relres"] <= 1e-10, info          # reached rtol, not the stall floor
         states[i] = tuple(t.cpu().numpy().copy() for t in (solver._x, solver._v, solver._a))
     m = orc.Material(*MAT2)
     ref = orc.transient(pts, groups, {1: m, 2: m, 3: m}, dU, dT, dict(surface={5: arr}), 0.2, 0.2, t_end, n_t,
@@ -422,8 +425,19 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
         xc = xc + pc.omega_c * (bc - A1 @ xc)
     z_host = pc.omega * r + P1 @ xc
     z = torch.empty(4 * n, dtype=torch.float64, device="cuda")
-    pc.apply(torch.from_numpy(r).cuda(), z)
+    pc.apply(torch.from_numpy(r).cuda(), z)                                       # one cooperative kernel (default)
     assert np.abs(z.cpu().numpy() - z_host).max() <= 1e-11 * np.abs(z_host).max()
+    # the same application as separate launches (measurement alternative, TEFEM_PRECOND_FUSED=0 at creation)
+    import os
+    os.environ["TEFEM_PRECOND_FUSED"] = "0"
+    try:
+        pc2 = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10)
+    finally:
+        del os.environ["TEFEM_PRECOND_FUSED"]
+    z2 = torch.empty_like(z)
+    pc2.apply(torch.from_numpy(r).cuda(), z2)
+    assert np.abs(z2.cpu().numpy() - z_host).max() <= 1e-11 * np.abs(z_host).max()
+    assert np.abs((z2 - z).cpu().numpy()).max() <= 1e-12 * np.abs(z_host).max()
 
 
 def test_steady_state_multilevel_matches_block_jacobi_and_oracle():
@@ -432,14 +446,25 @@ def test_steady_state_multilevel_matches_block_jacobi_and_oracle():
     pts, groups, mesh, model, dU, dT, loads = _kuhn_steady_model(30, 10, 8)
     sols, its = {}, {}
     for kind in ("block_jacobi", "multilevel"):
-        solver = LinearSteadyState(model, precond=kind)
+        solver = LinearSteadyState(model, precond=kind, solver="coupled")
         solver.solve()
+        assert not solver.solve_info["floor"], solver.solve_info
         sols[kind], its[kind] = solver.X.copy(), solver.solve_info["iterations"]
+    # staged solve: K_tt theta = F_t, then K_uu u = F_u - K_ut theta, both with CG (tefem_cg)
+    solver = LinearSteadyState(model, solver="staged")
+    solver.solve()
+    info_s = solver.solve_info
+    assert info_s["method"] == "staged-cg" and not info_s["floor"], info_s
+    sols["staged"] = solver.X.copy()
     X, info = orc.steady_state(pts, groups, {k: orc.Material(*v) for k, v in KUHN_MATS.items()}, dU, dT, loads)
     for kind in sols:
         eu, et = parity.field_errors(sols[kind], X)
         assert eu < parity.SOLUTION_TOL and et < parity.SOLUTION_TOL, (kind, eu, et)
     assert its["multilevel"] < its["block_jacobi"], its
+    # CG spends one SpMV per iteration, BiCGSTAB two: the staged solve must need fewer SpMVs than the coupled one
+    print("iterations: coupled block-Jacobi BiCGSTAB", its["block_jacobi"], "| staged CG theta + u",
+          info_s["stages"]["theta"]["iterations"], "+", info_s["stages"]["u"]["iterations"])
+    assert info_s["iterations"] < 2 * its["block_jacobi"], (info_s, its)
 
 
 def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
@@ -458,6 +483,7 @@ def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
     solver = LinearTransient(model, np.zeros(3 * N), np.zeros(3 * N), np.zeros(N), np.zeros(N), t_end, n_t, 0.5, 0.25,
                              progress=False)
     solver.solve()
+    assert not any(i["floor"] for i in solver.solve_info)                    # every one of the 999 solves reached rtol
     assert solver.X.shape == (4 * N, n_t) and solver.U.shape == (3 * N, n_t) and solver.T.shape == (N, n_t)
     assert solver.dt == float(g["dt"])
     for col, step in enumerate(g["steps"]):
@@ -471,10 +497,10 @@ def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
 
 
 # ---- measurement knobs of K1 -------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("threads,items", [(256, 512), (128, 256), (64, 128)])
+@pytest.mark.parametrize("threads,items", [(0, 512), (128, 256), (64, 128)])
 def test_assembly_thread_count_variants_are_bitwise_the_default(threads, items):
-    """The tile-synchronous instantiations of K1 (256 / 128 / 64 threads per CTA, tefem_assemble_set_threads) must produce
-    the planes of the default - the dynamic-chunk kernel - bit for bit."""
+    """The other kernel forms of K1 (dynamic chunks = 0; 128 / 64 threads per CTA; tefem_assemble_set_threads) must produce
+    the planes of the default (tile-synchronous, 256 threads) bit for bit."""
     import torch
     from thermoelasticity_fem_b200 import LinearThermoElastic
     from thermoelasticity_fem_b200.device import DeviceMesh
@@ -484,7 +510,7 @@ def test_assembly_thread_count_variants_are_bitwise_the_default(threads, items):
     conn = tets[1]
     table = np.array([LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.).table_row()])
     outs = {}
-    for tag, nt, it in (("default", 0, 512), ("variant", threads, items)):
+    for tag, nt, it in (("default", 256, 512), ("variant", threads, items)):
         S = build_schedule(torch.from_numpy(conn).cuda(), pts.shape[0], items_per_cta=it, elem_budget=int(1.21 * it))
         dm = DeviceMesh(pts, conn, np.zeros(conn.shape[0], dtype=np.int32), table, schedule=S)
         dm.asm_threads = nt

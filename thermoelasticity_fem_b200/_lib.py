@@ -32,7 +32,7 @@ _SIGNATURES = {
     "tefem_schedule_bank_numbering": [c_int32, P, P, P, P, c_int, c_int, c_int, P, P, P],
     "tefem_planes_spmv": [P, P, c_int32, c_int64, P, P, P, c_double, c_double, P, P],
     "tefem_form_system": [P, P, c_int32, c_int64, P, c_double, P, c_int, c_double, P, c_double, P, P, P],
-    "tefem_block_jacobi_scale": [P, P, c_int32, P, P, P],
+    "tefem_block_jacobi_scale": [P, P, c_int32, P, P, P, c_int, P],
     "tefem_block_jacobi_apply": [P, c_int32, P, P, P, P],
     "tefem_spmv": [P, P, c_int32, P, P, P, P],
     "tefem_solver_create": [P, c_int32, c_int32, P, P],
@@ -46,7 +46,8 @@ _SIGNATURES = {
     "tefem_precond_apply": [P, P, P, P],
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_precond_set_agg_ranks": [P, P],
-    "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, P, P],
+    "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
+    "tefem_cg": [P, P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
     "tefem_newmark_correct": [c_int64, P, P, P, P, c_double, c_double, c_double, P, P],
     "tefem_load_axpy": [c_int64, P, P, P, P, P],

@@ -508,14 +508,15 @@ __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(c
 // dependencies are counters too: a warp starts the gathers of tile k when all phase-1 chunks of k are done and reads the
 // parked pieces when all piece chunks are done.  A warp that finds no chunk left in tile k LEAVES it and moves on to
 // phase 1 of tile k + 1 while others still gather for k: the phases of consecutive tiles overlap and the pipe stays
-// busy.  Records, partial sums and the TMA stage are double-buffered; the LAST warp to leave tile k (every chunk of k
-// is finished then, and no warp will look at its stage again) issues the prefetch of tile k + 2 into the buffers of
-// k, so no warp can run more than one tile ahead of the slowest one and the mbarrier phase a warp waits for is never
-// ambiguous.  All counters are monotonic (never reset): a warp visits every tile of its CTA in order and keeps the
+// busy.  Records and partial sums are double-buffered, the TMA stage triple-buffered; the LAST warp to leave tile k
+// (every chunk of k is finished then, and no warp will look at its stage again) issues the prefetch of tile k + 3 into
+// the stage of k, so no warp can run more than two tiles ahead of the slowest one and the mbarrier phase a warp waits
+// for is never ambiguous; phase 1 of tile k additionally waits until every warp has left tile k - 2 (its records).  All counters are monotonic (never reset): a warp visits every tile of its CTA in order and keeps the
 // running chunk totals per buffer parity in registers, so a grab is a bounded compare-and-swap and "phase complete" is
 // `done >= total`; counts of tiles k and k + 2 cannot mix because k + 2 starts only after every warp has left k.
 // Same items, same per-item summation order as the tile-synchronous kernel: the planes are BITWISE identical.
 constexpr int DYN_THREADS = 512;
+constexpr int DYN_STAGES = 3;          // TMA stages: the prefetch of a tile is issued two tiles before it is consumed
 enum { C_P1_NEXT = 0, C_P1_DONE, C_PC_NEXT, C_PC_DONE, C_BL_NEXT, C_LEFT, C_PER_PARITY = 8 };
 
 __device__ __forceinline__ unsigned ld_shared_volatile(const unsigned* p) {
@@ -546,7 +547,7 @@ __device__ __forceinline__ unsigned chunk_done(unsigned* ctr, int lane) {
 }
 __device__ __forceinline__ void chunk_wait(const unsigned* ctr, unsigned total, int lane) {
     if (lane == 0) {
-        while ((int)(ld_shared_volatile(ctr) - total) < 0) __nanosleep(32);
+        while ((int)(ld_shared_volatile(ctr) - total) < 0) {}
     }
     __syncwarp();
     __threadfence_block();
@@ -566,9 +567,9 @@ __global__ void __launch_bounds__(DYN_THREADS, 1) assemble_dyn_kernel(const Asse
     const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
     double* recs0 = smem;                                   // [2][rec_doubles]
     double* parts0 = recs0 + 2 * (size_t)rec_doubles;       // [2][part_doubles]
-    char* stage0 = reinterpret_cast<char*>(parts0 + 2 * (size_t)part_doubles);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
-    unsigned* ctr0 = reinterpret_cast<unsigned*>(bars + 2); // [2][C_PER_PARITY]
+    char* stage0 = reinterpret_cast<char*>(parts0 + 2 * (size_t)part_doubles);   // [DYN_STAGES][L.bytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + DYN_STAGES * (size_t)L.bytes);
+    unsigned* ctr0 = reinterpret_cast<unsigned*>(bars + 4); // [2][C_PER_PARITY]
 #ifdef ASM_TAB_SELECT
     const QuadS tabS = make_quad_s(c_quad.S);
     const QuadNN tabNN = make_quad_nn(c_quad.NN);
@@ -584,26 +585,30 @@ __global__ void __launch_bounds__(DYN_THREADS, 1) assemble_dyn_kernel(const Asse
     const int K = (A.n_cta - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA: blockIdx.x, blockIdx.x + G, ...
     if (threadIdx.x < 2 * C_PER_PARITY) ctr0[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+#pragma unroll
+        for (int q = 0; q < DYN_STAGES; ++q) mbar_init(&bars[q], 1);
         fence_proxy_async();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (K > 0) prefetch_tile_now(A, blockIdx.x, stage0, L, &bars[0]);
-        if (K > 1) prefetch_tile_now(A, blockIdx.x + G, stage0 + L.bytes, L, &bars[1]);
+#pragma unroll
+        for (int q = 0; q < DYN_STAGES; ++q)
+            if (q < K) prefetch_tile_now(A, blockIdx.x + q * G, stage0 + (size_t)q * L.bytes, L, &bars[q]);
     }
     const double W4 = c_quad.W4;
     // chunk totals of the tiles this warp has passed, per buffer parity (cur = parity of tile k)
     unsigned p1_cur = 0, p1_oth = 0, pc_cur = 0, pc_oth = 0, bl_cur = 0, bl_oth = 0;
+    int sidx = 0;                 // k % DYN_STAGES
+    uint32_t sphase = 0;          // (k / DYN_STAGES) & 1
     for (int k = 0; k < K; ++k) {
         const int b = k & 1;
-        char* st = stage0 + (size_t)b * L.bytes;
+        char* st = stage0 + (size_t)sidx * L.bytes;
         double* recs = recs0 + (size_t)b * rec_doubles;
         double* partials = parts0 + (size_t)b * part_doubles;
         unsigned* c = ctr0 + b * C_PER_PARITY;
-        const uint32_t parity = (uint32_t)(k >> 1) & 1u;
-        while (!mbar_try_wait(&bars[b], parity)) {}
+        while (!mbar_try_wait(&bars[sidx], sphase)) {}
+        // the records / partial sums of parity b were last used by tile k - 2: every warp must have left it
+        chunk_wait(c + C_LEFT, (unsigned)(DYN_THREADS / 32) * (unsigned)(k >> 1), lane);
         const int32_t* hdr = reinterpret_cast<const int32_t*>(st + L.hdr);
         const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], o_elems = hdr[H_OELEMS], n_piece = hdr[H_NPIECE];
         const int32_t block0 = hdr[H_BLOCK0];
@@ -652,12 +657,14 @@ __global__ void __launch_bounds__(DYN_THREADS, 1) assemble_dyn_kernel(const Asse
             if (live)
                 process_pf_item<OPS, DUU>(A, block0 + q, (uint32_t)it_inc[it], meta, recs, inc_s, partials, W4, tabS, tabNN);
         }
-        // leave tile k; the last of the CTA's warps to do so frees its buffers for tile k + 2
+        // leave tile k; the last of the CTA's warps to do so frees its STAGE for tile k + DYN_STAGES (the prefetch runs
+        // DYN_STAGES - 1 tiles ahead of the consumers; records and partial sums are double-buffered, see the wait above)
         const unsigned left = chunk_done(c + C_LEFT, lane);
-        if (left + 1u == (unsigned)(DYN_THREADS / 32) * (unsigned)((k >> 1) + 1) && k + 2 < K && lane == 0) {
+        if (left + 1u == (unsigned)(DYN_THREADS / 32) * (unsigned)((k >> 1) + 1) && k + DYN_STAGES < K && lane == 0) {
             fence_proxy_async();
-            prefetch_tile_now(A, (int)blockIdx.x + (k + 2) * G, st, L, &bars[b]);
+            prefetch_tile_now(A, (int)blockIdx.x + (k + DYN_STAGES) * G, st, L, &bars[sidx]);
         }
+        if (++sidx == DYN_STAGES) { sidx = 0; sphase ^= 1u; }
         // next tile: swap the parities
         const unsigned t1 = p1_oth, t2 = pc_oth, t3 = bl_oth;
         p1_oth = p1_tot; pc_oth = pc_tot; bl_oth = bl_tot;
@@ -716,7 +723,7 @@ static int launch_assemble_dyn(const AssembleArgs& A, const TileDims& d, cudaStr
     const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
     const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
     const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
-    const size_t smem = 2 * ((size_t)rec_doubles + part_doubles) * sizeof(double) + 2 * (size_t)L.bytes + 16 +
+    const size_t smem = 2 * ((size_t)rec_doubles + part_doubles) * sizeof(double) + DYN_STAGES * (size_t)L.bytes + 32 +
                         2 * C_PER_PARITY * sizeof(unsigned) + 20 * sizeof(double);
     *fits = smem <= 227 * 1024;
     if (!*fits) return TEFEM_OK;                  // the caller falls back to the tile-synchronous kernel
@@ -736,10 +743,10 @@ static int launch_assemble_dyn(const AssembleArgs& A, const TileDims& d, cudaStr
     return TEFEM_OK;
 }
 
-// Kernel form of the pieces-first layout: 0 = dynamic chunks (one 512-thread CTA per SM, default), or the threads per
-// CTA of the tile-synchronous kernel: 64 | 128 | 256.  Set with tefem_assemble_set_threads (measurement knob; the
-// environment is not consulted on the launch path).
-static int g_asm_threads = 0;
+// Kernel form of the pieces-first layout: the threads per CTA of the tile-synchronous kernel, 256 (default) | 128 | 64,
+// or 0 = dynamic chunks (one 512-thread CTA per SM; measured slower than the default, profiles/README.md).  Set with
+// tefem_assemble_set_threads (measurement knob; the environment is not consulted on the launch path).
+static int g_asm_threads = ASM_THREADS;
 static int asm_threads() { return g_asm_threads; }
 
 template <int OPS, int DUU>

@@ -485,6 +485,152 @@ __global__ void __launch_bounds__(SPMV_THREADS, 2) coop_bicgstab_kernel(const Co
     }
 }
 
+// ---- preconditioned CG for the SPD field systems of the staged steady-state solve ---------------------------------
+// K of the reference has no theta -> u block (model.py:94-103: uu <- Kuu, ut <- Kut, tt <- Ktt), so
+// spsolve(K_ff, F_f) (solvers.py:26) is a block back-substitution: K_tt theta = F_t, then K_uu u = F_u - K_ut theta,
+// two SYMMETRIC POSITIVE DEFINITE solves.  CG needs one SpMV and one preconditioner application per iteration
+// (BiCGSTAB: two of each) and cannot break down.  Preconditioner: the inverse 4x4 diagonal node blocks (block
+// Jacobi per node, applied symmetrically as z = D^-1 r: the operator itself stays unscaled and symmetric).
+// Convergence is judged like in tefem_bicgstab, per field on the block-Jacobi-scaled residual z = D^-1 r:
+// |z_f| <= rtol |D^-1 b|_f, and verified with the true residual before returning.
+// One persistent cooperative kernel runs a batch of iterations (3 grid.sync() per iteration); every CTA reduces
+// the per-CTA partials itself in the same fixed order, so all CTAs hold identical scalars and stop together.
+enum { CG_RZ = 0, CG_BB_U, CG_BB_T, CG_RR, CG_ALPHA, CG_BETA, CG_PKT = 8 };
+
+struct CgArgs {
+    const int32_t* rowptr; const int32_t* colidx; const double* sys; const double* dinv;
+    int32_t n_rows;
+    const double* b;
+    double *x, *r, *z, *p, *q, *partials, *sc;
+    int* ictl;
+    int mode;          // 0: (re)start - r = b - A x, z = D^-1 r, p = z, scalars; 1: iterate [it0, it1)
+    int it0, it1;
+    double rtol2;
+};
+
+// z_row = sum_c dinv[i][row][c] r[4 i + c] for the scalar row `k` of this lane; the four lanes of a node exchange
+// their r values with shuffles (all 32 lanes of the warp call this together).
+__device__ __forceinline__ double quad_block_apply(const double* __restrict__ dinv, int64_t k, bool live, double rv) {
+    const int lane = threadIdx.x & 31, q0 = lane & ~3;
+    const double r0 = __shfl_sync(0xffffffffu, rv, q0), r1 = __shfl_sync(0xffffffffu, rv, q0 + 1);
+    const double r2 = __shfl_sync(0xffffffffu, rv, q0 + 2), r3 = __shfl_sync(0xffffffffu, rv, q0 + 3);
+    if (!live) return 0.0;
+    double d0, d1, d2, d3;
+    ld256(dinv + 4 * k, d0, d1, d2, d3);          // row (k & 3) of block (k >> 2): dinv[16 i + 4 r + c] = dinv[4 k + c]
+    return d0 * r0 + d1 * r1 + d2 * r2 + d3 * r3;
+}
+
+__global__ void __launch_bounds__(SPMV_THREADS, 2) coop_cg_kernel(const CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[8 * 32];
+    __shared__ double sc[NSCAL];
+    __shared__ int ictl[4];
+    if (threadIdx.x < NSCAL) sc[threadIdx.x] = a.sc[threadIdx.x];
+    if (threadIdx.x < 4) ictl[threadIdx.x] = a.ictl[threadIdx.x];
+    __syncthreads();
+    const int64_t n = 4 * (int64_t)a.n_rows;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t w0 = t0 - (threadIdx.x & 31);                       // first scalar row of this warp's trip
+    const bool th = (threadIdx.x & 3) == 3;                           // a thread always owns the same row type
+    double* part = a.partials;
+    if (a.mode == 0) {
+        {   // q = A x
+            double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            spmv_rows<0, 2>(a.rowptr, a.colidx, nullptr, a.n_rows, a.sys, a.x, a.q, nullptr, nullptr, d);
+        }
+        grid.sync();
+        double rz = 0.0, zz = 0.0, bb = 0.0;
+        for (int64_t w = w0; w < n; w += stride) {
+            const int64_t k = w + (threadIdx.x & 31);
+            const bool live = k < n;
+            const double bv = live ? a.b[k] : 0.0;
+            const double rv = live ? bv - a.q[k] : 0.0;
+            const double zv = quad_block_apply(a.dinv, k, live, rv);
+            const double sb = quad_block_apply(a.dinv, k, live, bv);
+            if (live) { a.r[k] = rv; a.z[k] = zv; a.p[k] = zv; }
+            rz += rv * zv; zz += zv * zv; bb += sb * sb;
+        }
+        double v[5] = {rz, th ? 0.0 : zz, th ? zz : 0.0, th ? 0.0 : bb, th ? bb : 0.0};
+        block_reduce_sum<5>(v, red);
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) part[(size_t)blockIdx.x * 5 + j] = v[j];
+        grid.sync();
+        coop_reduce<5>(part, gridDim.x, red, sc + CG_PKT);
+        if (threadIdx.x == 0) {
+            const double bb_u = sc[CG_PKT + 3], bb_t = sc[CG_PKT + 4];
+            sc[CG_RZ] = sc[CG_PKT]; sc[CG_BB_U] = bb_u; sc[CG_BB_T] = bb_t;
+            sc[SC_BNORM2] = bb_u + bb_t;
+            sc[CG_RR] = field_measure(sc[CG_PKT + 1], sc[CG_PKT + 2], bb_u, bb_t);
+            ictl[IN_STOP] = 0; ictl[IN_STOP_ITER] = -1; ictl[IN_REASON] = 0;
+            if (sc[CG_RR] <= a.rtol2) { ictl[IN_STOP] = 1; ictl[IN_REASON] = 1; }
+        }
+        __syncthreads();
+    } else {
+        for (int it = a.it0; it < a.it1; ++it) {
+            if (ictl[IN_STOP]) break;                       // identical in every CTA
+            {   // q = A p, (p . q)
+                double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                spmv_rows<1, 2>(a.rowptr, a.colidx, nullptr, a.n_rows, a.sys, a.p, a.q, a.p, nullptr, d);
+                spmv_store_partials<1>(d, red, part);
+            }
+            grid.sync();
+            coop_reduce<1>(part, gridDim.x, red, sc + CG_PKT);
+            if (threadIdx.x == 0) {
+                const double pq = sc[CG_PKT];
+                if (!(pq > 0.0) || !isfinite(pq)) { ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = -2; ictl[IN_REASON] = 2; }
+                else sc[CG_ALPHA] = sc[CG_RZ] / pq;
+            }
+            __syncthreads();
+            if (ictl[IN_STOP]) break;
+            {   // x += alpha p ; r -= alpha q ; z = D^-1 r ; (r . z), |z|^2 per field
+                const double alpha = sc[CG_ALPHA];
+                double rz = 0.0, zz = 0.0;
+                for (int64_t w = w0; w < n; w += stride) {
+                    const int64_t k = w + (threadIdx.x & 31);
+                    const bool live = k < n;
+                    double rv = 0.0;
+                    if (live) {
+                        a.x[k] += alpha * a.p[k];
+                        rv = a.r[k] - alpha * a.q[k];
+                        a.r[k] = rv;
+                    }
+                    const double zv = quad_block_apply(a.dinv, k, live, rv);
+                    if (live) a.z[k] = zv;
+                    rz += rv * zv; zz += zv * zv;
+                }
+                double v[3] = {rz, th ? 0.0 : zz, th ? zz : 0.0};
+                block_reduce_sum<3>(v, red);
+                if (threadIdx.x == 0)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) part[(size_t)(gridDim.x + blockIdx.x) * 3 + j] = v[j];
+            }
+            grid.sync();
+            coop_reduce<3>(part + (size_t)gridDim.x * 3, gridDim.x, red, sc + CG_PKT);
+            if (threadIdx.x == 0) {
+                const double rz_new = sc[CG_PKT];
+                ictl[IN_ITERS] += 1;
+                sc[CG_RR] = field_measure(sc[CG_PKT + 1], sc[CG_PKT + 2], sc[CG_BB_U], sc[CG_BB_T]);
+                if (sc[CG_RR] <= a.rtol2) { ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = it; ictl[IN_REASON] = 1; }
+                else if (!(rz_new > 0.0) || !isfinite(rz_new)) { ictl[IN_STOP] = 1; ictl[IN_STOP_ITER] = it; ictl[IN_REASON] = 2; }
+                else { sc[CG_BETA] = rz_new / sc[CG_RZ]; sc[CG_RZ] = rz_new; }
+            }
+            __syncthreads();
+            if (ictl[IN_STOP]) break;
+            {   // p = z + beta p
+                const double beta = sc[CG_BETA];
+                for (int64_t k = t0; k < n; k += stride) a.p[k] = a.z[k] + beta * a.p[k];
+            }
+            grid.sync();
+        }
+    }
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x < NSCAL) a.sc[threadIdx.x] = sc[threadIdx.x];
+        if (threadIdx.x < 4) a.ictl[threadIdx.x] = ictl[threadIdx.x];
+    }
+}
+
 // send[k*4 + c] = x[4*idx[k] + c]
 __global__ void __launch_bounds__(256) pack_halo_kernel(int64_t n_nodes, const int32_t* __restrict__ idx,
                                                         const double* __restrict__ x, double* __restrict__ send,
@@ -968,11 +1114,11 @@ static int coop_grid(int32_t n_rows) {
 }
 
 extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys,
-                              const double* b, double* x, double rtol, int max_iter, int check_every, double* h_info,
-                              void* stream) {
+                              const double* b, double* x, double rtol, int max_iter, int check_every, double floor_factor,
+                              double* h_info, void* stream) {
     TEFEM_REQUIRE(s && rowptr && colidx && sys && b && x, "null pointer");
     TEFEM_REQUIRE((((uintptr_t)sys) & 127) == 0 && (((uintptr_t)x) & 31) == 0, "sys / x alignment");
-    TEFEM_REQUIRE(rtol > 0 && max_iter > 0, "rtol / max_iter");
+    TEFEM_REQUIRE(rtol > 0 && max_iter > 0 && floor_factor >= 1.0, "rtol / max_iter / floor_factor");
     if (check_every < 1) check_every = 1;
     cudaStream_t st = as_stream(stream);
     const int64_t n = s->n_own;
@@ -980,6 +1126,7 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
     const double rtol2 = rtol * rtol;
     const int max_restarts = 20;
     int total_iters = 0, restarts = 0, stalls = 0;
+    bool floor_hit = false;
     double relres = -1.0, bnorm = 0.0, prev_relres = INFINITY;
     int status = TEFEM_ERR_NO_CONVERGE;
     TEFEM_CUDA_CHECK(cudaMemsetAsync(s->ictl, 0, 16 * sizeof(int), st));
@@ -1012,8 +1159,8 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         // that fail to improve it mean that floor has been reached
         if (restarts > 0 && relres > 0.5 * prev_relres) ++stalls; else stalls = 0;
         prev_relres = relres;
-        if (stalls >= 2) {
-            if (relres <= 100.0 * rtol) status = TEFEM_OK;
+        if (stalls >= 2) {      // accepted only within floor_factor * rtol, and reported (h_info[4])
+            if (relres <= floor_factor * rtol) { status = TEFEM_OK; floor_hit = relres > rtol; }
             break;
         }
         if (total_iters >= max_iter || restarts > max_restarts) break;
@@ -1097,10 +1244,102 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         h_info[1] = (double)restarts;
         h_info[2] = relres;
         h_info[3] = bnorm;
+        h_info[4] = floor_hit ? 1.0 : 0.0;
+        h_info[5] = (double)stalls;
     }
     if (status == TEFEM_ERR_NO_CONVERGE)
-        set_error("BiCGSTAB did not converge: %d iterations, %d restarts, relative residual %.3e (rtol %.3e)",
-                  total_iters, restarts, relres, rtol);
+        set_error("BiCGSTAB did not converge: %d iterations, %d restarts, relative residual %.3e (rtol %.3e)%s",
+                  total_iters, restarts, relres, rtol,
+                  stalls >= 2 ? "; the true residual stalled (eps * cond floor of working precision)" : "");
+    return status;
+}
+
+// Preconditioned CG (coop_cg_kernel): same host protocol as tefem_bicgstab - (re)start with the true residual, batches
+// of check_every iterations, true-residual verification, stall detection.
+extern "C" int tefem_cg(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys, const double* dinv,
+                        const double* b, double* x, double rtol, int max_iter, int check_every, double floor_factor,
+                        double* h_info, void* stream) {
+    TEFEM_REQUIRE(s && rowptr && colidx && sys && dinv && b && x, "null pointer");
+    TEFEM_REQUIRE((((uintptr_t)sys) & 127) == 0 && (((uintptr_t)x) & 31) == 0 && (((uintptr_t)dinv) & 31) == 0, "sys / x / dinv alignment");
+    TEFEM_REQUIRE(rtol > 0 && max_iter > 0 && floor_factor >= 1.0, "rtol / max_iter / floor_factor");
+    TEFEM_REQUIRE(!s->comm, "tefem_cg is a single-GPU solver");
+    if (check_every < 1) check_every = 1;
+    cudaStream_t st = as_stream(stream);
+    const int64_t n = s->n_own;
+    static int resident = -1;
+    if (resident < 0) {
+        int dev = 0, sms = 0, per_sm = 0, coop_ok = 0;
+        TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
+        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
+        TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_cg_kernel, SPMV_THREADS, 0));
+        TEFEM_REQUIRE(coop_ok && per_sm > 0, "cooperative launch unavailable");
+        resident = sms * per_sm;
+        if (resident > MAX_PARTIAL_CTAS) resident = MAX_PARTIAL_CTAS;
+    }
+    int64_t g64 = ceil_div(n, SPMV_THREADS);
+    if (g64 > resident) g64 = resident;
+    const dim3 grid((unsigned)(g64 < 1 ? 1 : g64)), block(SPMV_THREADS);
+    const double rtol2 = rtol * rtol;
+    const int max_restarts = 20;
+    int total_iters = 0, restarts = 0, stalls = 0;
+    bool floor_hit = false;
+    double relres = -1.0, bnorm = 0.0, prev_relres = INFINITY;
+    int status = TEFEM_ERR_NO_CONVERGE;
+    TEFEM_CUDA_CHECK(cudaMemsetAsync(s->ictl, 0, 16 * sizeof(int), st));
+    TEFEM_CUDA_CHECK(cudaMemsetAsync(s->sc, 0, NSCAL * sizeof(double), st));
+    CgArgs ca = {rowptr, colidx, sys, dinv, s->n_rows, b, x, s->r, s->rhat, s->p, s->v, s->partials, s->sc, s->ictl, 0, 0, 0, rtol2};
+    for (;;) {
+        ca.mode = 0;
+        void* kargs[] = {&ca};
+        TEFEM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)coop_cg_kernel, grid, block, kargs, 0, st));
+        count_launch();
+        TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_sc, s->sc, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, st));
+        TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
+        bnorm = sqrt(s->h_sc[SC_BNORM2]);
+        relres = sqrt(s->h_sc[CG_RR]);
+        if (bnorm == 0.0) {
+            TEFEM_CUDA_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
+            relres = 0.0; status = TEFEM_OK; break;
+        }
+        if (!isfinite(relres)) { set_error("non-finite residual in CG"); status = TEFEM_ERR_BREAKDOWN; break; }
+        if (s->h_ictl[IN_STOP] && s->h_ictl[IN_REASON] == 1) { status = TEFEM_OK; break; }
+        if (restarts > 0 && relres > 0.5 * prev_relres) ++stalls; else stalls = 0;
+        prev_relres = relres;
+        if (stalls >= 2) {
+            if (relres <= floor_factor * rtol) { status = TEFEM_OK; floor_hit = relres > rtol; }
+            break;
+        }
+        if (total_iters >= max_iter || restarts > max_restarts) break;
+        bool stopped = false;
+        int it = 0;
+        while (!stopped && total_iters + it < max_iter) {
+            int it1 = it + check_every;
+            if (total_iters + it1 > max_iter) it1 = max_iter - total_iters;
+            ca.mode = 1; ca.it0 = it; ca.it1 = it1;
+            void* ka[] = {&ca};
+            TEFEM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)coop_cg_kernel, grid, block, ka, 0, st));
+            count_launch();
+            it = it1;
+            TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
+            stopped = s->h_ictl[IN_STOP] != 0;
+        }
+        total_iters = s->h_ictl[IN_ITERS];
+        ++restarts;
+    }
+    if (h_info) {
+        h_info[0] = (double)total_iters;
+        h_info[1] = (double)restarts;
+        h_info[2] = relres;
+        h_info[3] = bnorm;
+        h_info[4] = floor_hit ? 1.0 : 0.0;
+        h_info[5] = (double)stalls;
+    }
+    if (status == TEFEM_ERR_NO_CONVERGE)
+        set_error("CG did not converge: %d iterations, %d restarts, relative residual %.3e (rtol %.3e)", total_iters, restarts,
+                  relres, rtol);
     return status;
 }
 

@@ -241,22 +241,21 @@ extern "C" int tefem_form_system(const int32_t* rowptr, const int32_t* colidx, i
 }
 
 extern "C" int tefem_block_jacobi_scale(const int32_t* rowptr, const int32_t* diag_idx, int32_t n_rows, double* sys,
-                                        double* dinv, void* stream) {
-    TEFEM_REQUIRE(rowptr && diag_idx && sys && dinv, "null pointer");
+                                        double* dinv, int32_t* singular, int scale, void* stream) {
+    TEFEM_REQUIRE(rowptr && diag_idx && sys && dinv && singular, "null pointer");
     if (n_rows == 0) return TEFEM_OK;
     cudaStream_t st = as_stream(stream);
-    int32_t* d_sing = nullptr;
-    TEFEM_CUDA_CHECK(cudaMallocAsync(&d_sing, sizeof(int32_t), st));
     const int32_t big = INT32_MAX;
-    TEFEM_CUDA_CHECK(cudaMemcpyAsync(d_sing, &big, sizeof(big), cudaMemcpyHostToDevice, st));
-    block_invert_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, st>>>(diag_idx, n_rows, sys, dinv, d_sing);
+    TEFEM_CUDA_CHECK(cudaMemcpyAsync(singular, &big, sizeof(big), cudaMemcpyHostToDevice, st));
+    block_invert_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, st>>>(diag_idx, n_rows, sys, dinv, singular);
     TEFEM_LAUNCH_CHECK();
-    block_scale_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, st>>>(rowptr, n_rows, dinv, sys);
-    TEFEM_LAUNCH_CHECK();
+    if (scale) {
+        block_scale_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, st>>>(rowptr, n_rows, dinv, sys);
+        TEFEM_LAUNCH_CHECK();
+    }
     int32_t h_sing = INT32_MAX;
-    TEFEM_CUDA_CHECK(cudaMemcpyAsync(&h_sing, d_sing, sizeof(h_sing), cudaMemcpyDeviceToHost, st));
+    TEFEM_CUDA_CHECK(cudaMemcpyAsync(&h_sing, singular, sizeof(h_sing), cudaMemcpyDeviceToHost, st));
     TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
-    TEFEM_CUDA_CHECK(cudaFreeAsync(d_sing, st));
     if (h_sing != INT32_MAX) {
         set_error("singular 4x4 diagonal block at node row %d", h_sing);
         return TEFEM_ERR_BREAKDOWN;

@@ -46,9 +46,9 @@ class DeviceMesh:
         self.cta_xyz = self.coords[S.cta_nodes.long()].contiguous()
         self._h_max = S.h_max()
         self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
-        # kernel form of K1: 0 = dynamic chunks, one 512-thread CTA per SM (default); 64 | 128 | 256 = threads per CTA of
-        # the tile-synchronous kernel (measurement knob, pair with tiles of 2 x threads blocks)
-        self.asm_threads = 0
+        # kernel form of K1: 256 (default) | 128 | 64 = threads per CTA of the tile-synchronous kernel (pair with tiles of
+        # 2 x threads blocks); 0 = dynamic chunks, one 512-thread CTA per SM (measured slower, profiles/README.md)
+        self.asm_threads = 256
 
     # ---- K1 -------------------------------------------------------------------------------------
     def alloc_planes(self, which, alpha_M=0., alpha_K=0.):
@@ -144,12 +144,15 @@ class DeviceMesh:
             p(dir_mask), p(sys), _lib.stream_ptr()))
         return sys
 
-    def block_jacobi_scale(self, sys):
+    def block_jacobi_scale(self, sys, scale=True):
+        """Inverse 4x4 diagonal blocks dinv [n_rows, 16]; scale=True also left-scales sys in place (BiCGSTAB path),
+        scale=False keeps sys (the symmetric CG path applies dinv itself)."""
         S = self.schedule
         dinv = torch.empty((S.n_rows, 16), dtype=torch.float64, device=self.device)
+        singular = torch.empty(1, dtype=torch.int32, device=self.device)        # scratch the library needs: caller-owned
         p = _lib.ptr
-        _lib.check(self.lib.tefem_block_jacobi_scale(p(S.rowptr), p(S.diag_idx), S.n_rows, p(sys), p(dinv),
-                                                     _lib.stream_ptr()))
+        _lib.check(self.lib.tefem_block_jacobi_scale(p(S.rowptr), p(S.diag_idx), S.n_rows, p(sys), p(dinv), p(singular),
+                                                     int(bool(scale)), _lib.stream_ptr()))
         return dinv
 
     def block_jacobi_apply(self, dinv, r, z, dir_mask=None):
@@ -194,15 +197,34 @@ class KrylovSolver:
             p(boundary_rows), int(boundary_rows.numel()) if boundary_rows is not None else 0,
             p(interior_rows), int(interior_rows.numel()) if interior_rows is not None else 0))
 
-    def bicgstab(self, sys, b, x, rtol=1e-10, max_iter=20000, check_every=16):
+    @staticmethod
+    def _info(info, method):
+        return dict(iterations=int(info[0]), restarts=int(info[1]), relres=float(info[2]), bnorm=float(info[3]),
+                    floor=bool(info[4]), stalls=int(info[5]), method=method)
+
+    def bicgstab(self, sys, b, x, rtol=1e-10, max_iter=20000, check_every=16, floor_factor=1.0):
         """Solves sys x = b (both already block-Jacobi scaled); x holds the initial guess and the result.
-        Returns dict(iterations, restarts, relres, bnorm).  Raises ConvergenceError when rtol is not met."""
+        Returns dict(iterations, restarts, relres, bnorm, floor, stalls).  Raises ConvergenceError when rtol is not met;
+        floor_factor > 1 accepts a solve whose TRUE residual stalled (the eps * cond floor of fp64) within
+        floor_factor * rtol and reports it as info['floor'] = True (default 1: never accept above rtol)."""
         S = self.dmesh.schedule
-        info = (ctypes.c_double * 4)()
+        info = (ctypes.c_double * 6)()
         p = _lib.ptr
         rc = self.lib.tefem_bicgstab(self.handle, p(S.rowptr), p(S.colidx), p(sys), p(b), p(x), float(rtol),
-                                     int(max_iter), int(check_every), info, _lib.stream_ptr())
-        self.last_info = dict(iterations=int(info[0]), restarts=int(info[1]), relres=float(info[2]), bnorm=float(info[3]))
+                                     int(max_iter), int(check_every), float(floor_factor), info, _lib.stream_ptr())
+        self.last_info = self._info(info, "bicgstab")
+        _lib.check(rc)
+        return self.last_info
+
+    def cg(self, sys, dinv, b, x, rtol=1e-10, max_iter=20000, check_every=16, floor_factor=1.0):
+        """Block-Jacobi-preconditioned CG on the UNSCALED symmetric positive definite system `sys` (dinv from
+        block_jacobi_scale(sys, scale=False)); same stopping rule, info and exceptions as bicgstab."""
+        S = self.dmesh.schedule
+        info = (ctypes.c_double * 6)()
+        p = _lib.ptr
+        rc = self.lib.tefem_cg(self.handle, p(S.rowptr), p(S.colidx), p(sys), p(dinv), p(b), p(x), float(rtol),
+                               int(max_iter), int(check_every), float(floor_factor), info, _lib.stream_ptr())
+        self.last_info = self._info(info, "cg")
         _lib.check(rc)
         return self.last_info
 

@@ -177,11 +177,12 @@ class DistributedTransient:
 
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
                  alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=16,
-                 comm=None, precond="multilevel", halo="peer"):
+                 comm=None, precond="multilevel", halo="peer", floor_factor=1.0):
         """halo: 'peer' (default) - boundary values are stored straight into the neighbours' vectors over NVLink and the
         SpMV waits for flags; 'nccl' - packed ncclSend / ncclRecv overlapped with the interior rows (measured alternative)."""
         assert halo in ("peer", "nccl")
         self.halo = halo
+        self.floor_factor = floor_factor
         self.lp, self.comm = lp, comm
         self.alpha_M, self.alpha_K = alpha_M, alpha_K
         self.gamma, self.beta = gamma, beta
@@ -274,7 +275,8 @@ class DistributedTransient:
         dm.planes_spmv(self.planes["K"], self._mapK, self._w2, rhs, alpha=-1.0, beta_y=1.0)
         dm.block_jacobi_apply(self.dinv, rhs, self._b, self.dir_mask)
         self._guess.guess(self._a, self._a_new)
-        info = self.krylov.bicgstab(self.sys, self._b, self._a_new, self.rtol, self.max_iter, self.check_every)
+        info = self.krylov.bicgstab(self.sys, self._b, self._a_new, self.rtol, self.max_iter, self.check_every,
+                                    self.floor_factor)
         self._guess.push(self._a)
         # x, v, a are advanced on the halo nodes as well (same arithmetic as on their owner): they need a_new there
         _lib.check(lib.tefem_solver_halo_exchange(self.krylov.handle, _lib.ptr(self._a_new), _lib.stream_ptr()))

@@ -22,20 +22,24 @@ import torch
 from . import _lib
 
 
-def _dist():
+def _dist(distributed=True):
+    """torch.distributed when this set-up is a collective over the ranks (`distributed`: the caller's solve has a
+    communicator - a single-GPU model built inside a multi-rank job must NOT enter collectives)."""
+    if not distributed:
+        return None
     import torch.distributed as dist
     return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
 
 
-def _allreduce(t, op):
-    dist = _dist()
+def _allreduce(t, op, distributed=True):
+    dist = _dist(distributed)
     if dist is not None:
         dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return t
 
 
-def _gather_objects(obj):
-    dist = _dist()
+def _gather_objects(obj, distributed=True):
+    dist = _dist(distributed)
     if dist is None:
         return [obj]
     out = [None] * dist.get_world_size()
@@ -43,9 +47,9 @@ def _gather_objects(obj):
     return out
 
 
-def _gather_cat(t):
+def _gather_cat(t, distributed=True):
     """Concatenation over the ranks of a tensor whose first dimension differs per rank (padded all_gather)."""
-    dist = _dist()
+    dist = _dist(distributed)
     if dist is None:
         return t
     world = dist.get_world_size()
@@ -67,26 +71,26 @@ def _grid_keys(xyz, lo, H, dims):
     return (ijk[:, 0] * dims[1] + ijk[:, 1]) * dims[2] + ijk[:, 2]
 
 
-def build_aggregation(xyz, n_own, factor1):
+def build_aggregation(xyz, n_own, factor1, distributed=True):
     """Geometric aggregation of the nodes: cubes of edge factor1 * h on a grid anchored at the GLOBAL bounding box
     (h = mean node spacing).  xyz: [n_local, 3] coordinates (owned nodes first).  Returns a dict with the sorted
     global aggregate keys `uniq`, the grid `dims1`, the aggregate of every local node `agg`, the owned nodes grouped
     by aggregate (`agg_ptr`, `order`), the aggregate centres `centres` [n1, 3] (mean of the member nodes over all
-    ranks) and the offsets `off` [n_local, 3] of the local nodes from their centre.  Collective when
-    torch.distributed is initialised."""
+    ranks) and the offsets `off` [n_local, 3] of the local nodes from their centre.  Collective over the default
+    torch.distributed group when `distributed` (a row-partitioned solve); purely local otherwise."""
     dev = xyz.device
     f64 = dict(dtype=torch.float64, device=dev)
     own = xyz[:n_own]
-    lo = _allreduce(own.min(dim=0).values.clone(), "MIN")
-    hi = _allreduce(own.max(dim=0).values.clone(), "MAX")
-    n_glob = int(_allreduce(torch.tensor([float(n_own)], **f64), "SUM").item())
+    lo = _allreduce(own.min(dim=0).values.clone(), "MIN", distributed)
+    hi = _allreduce(own.max(dim=0).values.clone(), "MAX", distributed)
+    n_glob = int(_allreduce(torch.tensor([float(n_own)], **f64), "SUM", distributed).item())
     ext = (hi - lo).clamp(min=1e-300)
     h = float(ext.prod().item() / max(n_glob, 1)) ** (1.0 / 3.0)
     H1 = factor1 * h
     dims1 = torch.ceil(ext / H1 + 1e-9).to(torch.int64).clamp(min=1)
     key = _grid_keys(xyz, lo, H1, dims1)                                   # all local nodes (owned + halo)
     uniq_local = torch.unique(key[:n_own]).cpu().numpy()
-    uniq = np.unique(np.concatenate(_gather_objects(uniq_local)))          # same on every rank
+    uniq = np.unique(np.concatenate(_gather_objects(uniq_local, distributed)))          # same on every rank
     n1 = int(uniq.shape[0])
     agg = torch.searchsorted(torch.from_numpy(uniq).to(dev), key)          # aggregate of every local node
     node_agg = agg[:n_own]
@@ -95,7 +99,7 @@ def build_aggregation(xyz, n_own, factor1):
     torch.cumsum(torch.bincount(node_agg, minlength=n1), 0, out=agg_ptr[1:])
     sums = torch.zeros((n1, 4), **f64)
     sums.index_add_(0, node_agg, torch.cat([own, torch.ones((n_own, 1), **f64)], dim=1))
-    _allreduce(sums, "SUM")
+    _allreduce(sums, "SUM", distributed)
     centres = sums[:, :3] / sums[:, 3:4]
     off = xyz - centres[agg]
     return dict(h=h, H1=H1, dims1=dims1, uniq=uniq, n1=n1, agg=agg, node_agg=node_agg, order=order, agg_ptr=agg_ptr,
@@ -111,7 +115,7 @@ def rotation_blocks(d):
     return R
 
 
-def galerkin_level1(agg, off, block_row, colidx, sys, n1, chunk=1 << 22):
+def galerkin_level1(agg, off, block_row, colidx, sys, n1, chunk=1 << 22, distributed=True):
     """A1 = P1^T A P1 for the rigid-body prolongation P1 = [I4 | R(d_i)] of every node: the 4x4 blocks A_ij of the
     fine rows of this rank contribute the 8x8 block [[A, A R_j], [R_i^T A, R_i^T A R_j]] to the aggregate pair
     (agg i, agg j); the partial operators of all ranks are gathered and summed (level 1 is replicated).
@@ -137,8 +141,8 @@ def galerkin_level1(agg, off, block_row, colidx, sys, n1, chunk=1 << 22):
         part.index_add_(0, inv[s:e], B)
         del A, Ri, Rj, B, RtA
     del inv
-    if _dist() is not None:
-        keys, vals = _gather_cat(uk), _gather_cat(part)
+    if _dist(distributed) is not None:
+        keys, vals = _gather_cat(uk, distributed), _gather_cat(part, distributed)
         uk, inv = torch.unique(keys, return_inverse=True)
         part = torch.zeros((uk.numel(), 8, 8), **f64).index_add_(0, inv, vals)
         del keys, vals, inv
@@ -254,10 +258,11 @@ class TwoLevelPreconditioner:
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = torch.int32
         p = _lib.ptr
-        A = build_aggregation(dm.coords, n_own, factor1)
+        distributed = comm is not None
+        A = build_aggregation(dm.coords, n_own, factor1, distributed=distributed)
         n1, uniq, dims1, h, H1 = A["n1"], A["uniq"], A["dims1"], A["h"], A["H1"]
         node_agg, order, agg_ptr = A["node_agg"], A["order"], A["agg_ptr"]
-        row1, col1, blocks = galerkin_level1(A["agg"], A["off"], S.block_row, S.colidx, sys, n1)
+        row1, col1, blocks = galerkin_level1(A["agg"], A["off"], S.block_row, S.colidx, sys, n1, distributed=distributed)
         rowptr1, Dinv, scaled = scale_level1(row1, col1, blocks, n1)
         del blocks
         rp, ci, vals = pseudo_node_csr(rowptr1, col1, scaled)
@@ -289,7 +294,7 @@ class TwoLevelPreconditioner:
         if comm is not None:
             comm.setup_peer(8 * n1)               # the restricted residual is all-reduced through peer memory
             # which ranks own fine nodes of an aggregate: only their partial sums are read over NVLink
-            dist = _dist()
+            dist = _dist(True)
             mine = ((agg_ptr[1:] - agg_ptr[:-1]) > 0).to(torch.int32)
             if dist is not None:
                 parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]

@@ -59,12 +59,19 @@ def reduced_newmark(Mr, Dr, Kr, forces, q_init, v_init, dt, gamma, beta, n_t, st
 
 
 class _SystemSolve:
-    """Shared by both solvers: forms the eliminated, block-Jacobi-scaled system and solves with it."""
+    """Shared by both solvers: forms the eliminated system and solves with it - BiCGSTAB on the block-Jacobi-scaled
+    system (method='bicgstab', any operator), or block-Jacobi-preconditioned CG on the unscaled system (method='cg',
+    symmetric positive definite operators: the field systems of the staged steady-state solve)."""
 
-    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="auto", dir_mask=None):
+    def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="auto", dir_mask=None, method="bicgstab",
+                 floor_factor=1.0):
         """dir_mask (uint8 [4N], default: the model's Dirichlet DOFs): DOFs eliminated from the system (identity rows
-        and columns); the reduced-order bases pass the complement of one field's free DOFs (rom.py)."""
+        and columns); the reduced-order bases pass the complement of one field's free DOFs (rom.py).
+        floor_factor: see KrylovSolver.bicgstab (1 = a solve that stalls above rtol raises)."""
+        if method not in ("bicgstab", "cg"):
+            raise ValueError("method must be 'bicgstab' or 'cg'")
         self.model = model
+        self.method, self.floor_factor = method, floor_factor
         self.dm = model.mesh.device_mesh()
         self.dir_mask = model._dir_mask if dir_mask is None else dir_mask
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
@@ -72,8 +79,12 @@ class _SystemSolve:
         planes = {k: v for k, v in model._planes.items()
                   if (k == "M" and cM != 0.) or (k == "D" and cD != 0.) or (k == "K" and cK != 0.)}
         self.sys = self.dm.form_system(planes, cM, cD, cK, d_layout, self.dir_mask)
-        self.dinv = self.dm.block_jacobi_scale(self.sys)
+        self.dinv = self.dm.block_jacobi_scale(self.sys, scale=(method == "bicgstab"))
         self.krylov = KrylovSolver(self.dm)
+        if method == "cg":
+            if precond not in ("auto", "block_jacobi"):
+                raise ValueError("method='cg' runs with the block-Jacobi preconditioner")
+            precond = "block_jacobi"
         # right preconditioner on top of the block-Jacobi scaling: aggregation coarse correction (multilevel.py);
         # precond="block_jacobi" keeps the scaling alone
         self.precond = None
@@ -90,18 +101,35 @@ class _SystemSolve:
 
     def solve(self, rhs, x):
         """x <- solution of A_ff x_f = rhs_f (constrained entries of x stay 0)."""
-        self.dm.block_jacobi_apply(self.dinv, rhs, self.b, self.dir_mask)
-        info = self.krylov.bicgstab(self.sys, self.b, x, self.rtol, self.max_iter, self.check_every)
+        if self.method == "cg":
+            self.b.copy_(rhs)
+            self.b.masked_fill_(self.dir_mask.bool(), 0.0)
+            info = self.krylov.cg(self.sys, self.dinv, self.b, x, self.rtol, self.max_iter, self.check_every, self.floor_factor)
+        else:
+            self.dm.block_jacobi_apply(self.dinv, rhs, self.b, self.dir_mask)
+            info = self.krylov.bicgstab(self.sys, self.b, x, self.rtol, self.max_iter, self.check_every, self.floor_factor)
         self.info.append(info)
         return info
 
 
 class LinearSteadyState:
-    """Steady-state solver for linear thermoelasticity (reference solvers.py:8-66)."""
+    """Steady-state solver for linear thermoelasticity (reference solvers.py:8-66).
 
-    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="auto"):
+    solver: how spsolve(K_ff, F_f) (solvers.py:26) is replaced.
+      'staged'  - K has no theta -> u block (model.py:94-103: uu <- Kuu, ut <- Kut, tt <- Ktt), so the solve is a block
+                  back-substitution: K_tt theta = F_t, then K_uu u = F_u - K_ut theta, two SYMMETRIC POSITIVE DEFINITE
+                  systems solved with block-Jacobi-preconditioned CG (one SpMV per iteration, no breakdown);
+      'coupled' - preconditioned BiCGSTAB on the whole non-symmetric operator (the transient solver's path; with the
+                  aggregation coarse correction on large meshes);
+      'auto'    - 'staged' below MULTILEVEL_MIN_NODES nodes (where block-Jacobi is the preconditioner anyway), 'coupled'
+                  above (the coarse correction needs 20 x fewer iterations there)."""
+
+    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="auto", solver="auto", floor_factor=1.0):
+        if solver not in ("auto", "staged", "coupled"):
+            raise ValueError("solver must be 'auto', 'staged' or 'coupled'")
         self.model = model
         self.rtol, self.max_iter, self.check_every, self.precond = rtol, max_iter, check_every, precond
+        self.solver, self.floor_factor = solver, floor_factor
         self.X = None
         self.U = None
         self.T = None
@@ -119,9 +147,16 @@ class LinearSteadyState:
         m.apply_dirichlet_F()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every, self.precond)
-        x = torch.zeros(m.mesh.n_dofs, dtype=torch.float64, device=ss.dm.device)
-        self.solve_info = ss.solve(m.rhs_device(), x)
+        solver = self.solver
+        if solver == "auto":
+            solver = "staged" if (m.mesh.n_nodes < MULTILEVEL_MIN_NODES and self.precond in ("auto", "block_jacobi")) else "coupled"
+        if solver == "staged":
+            x = self._solve_staged(m)
+        else:
+            ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every, self.precond,
+                              floor_factor=self.floor_factor)
+            x = torch.zeros(m.mesh.n_dofs, dtype=torch.float64, device=ss.dm.device)
+            self.solve_info = ss.solve(m.rhs_device(), x)
         x.masked_fill_(m._dir_mask.bool(), 0.0)   # eliminated unknowns (a coarse correction may leave round-off there)
         x += m._g_fill                       # prescribed values on the constrained DOFs (solvers.py:27-49)
         torch.cuda.synchronize()
@@ -131,6 +166,33 @@ class LinearSteadyState:
         self.U, theta = _deinterleave(self.X, m.mesh.n_nodes)
         self.T = theta + m.mesh.reference_temperature()       # solvers.py:51-66
         self.timings = dict(assemble_s=t1 - t0, solve_s=t2 - t1, post_s=time.perf_counter() - t2)
+
+
+    def _solve_staged(self, m):
+        """theta from K_tt, then u from K_uu with the coupling moved to the right-hand side; each system keeps the uniform
+        4-DOF-per-node layout with the other field's DOFs as identity rows (like the reduced-order bases, rom.py)."""
+        dm = m.mesh.device_mesh()
+        n = m.mesh.n_dofs
+        is_t = (torch.arange(n, device=dm.device) % 4) == 3
+        dirm = m._dir_mask.bool()
+        rhs = m.rhs_device()
+        kw = dict(precond="block_jacobi", method="cg", floor_factor=self.floor_factor)
+        ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every,
+                          dir_mask=(dirm | ~is_t).to(torch.uint8), **kw)
+        x = torch.zeros(n, dtype=torch.float64, device=dm.device)
+        info_t = ss.solve(rhs, x)                                        # K_tt theta = F_t
+        del ss
+        rhs_u = rhs.clone()
+        dm.planes_spmv(m._planes["K"], layout.plane_map_K(), x, rhs_u, alpha=-1.0, beta_y=1.0)    # F_u - K_ut theta
+        ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every,
+                          dir_mask=(dirm | is_t).to(torch.uint8), **kw)
+        xu = torch.zeros_like(x)
+        info_u = ss.solve(rhs_u, xu)                                     # K_uu u = F_u - K_ut theta
+        x += xu
+        self.solve_info = dict(method="staged-cg", iterations=info_t["iterations"] + info_u["iterations"],
+                               restarts=info_t["restarts"] + info_u["restarts"], relres=max(info_t["relres"], info_u["relres"]),
+                               bnorm=info_u["bnorm"], floor=info_t["floor"] or info_u["floor"], stages=dict(theta=info_t, u=info_u))
+        return x
 
 
 class LinearTransient:
@@ -146,7 +208,7 @@ class LinearTransient:
                  t_end, n_t,
                  gamma=0.5, beta=0.25,
                  rtol=1e-10, max_iter=50000, check_every=32, history='full', warm_start=True, guess_order=0,
-                 on_step=None, progress=True, precond="auto"):
+                 on_step=None, progress=True, precond="auto", floor_factor=1.0):
         self.model = model
         self.gamma = gamma
         self.beta = beta
@@ -163,6 +225,7 @@ class LinearTransient:
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
         self.history, self.warm_start, self.on_step, self.progress = history, warm_start, on_step, progress
         self.precond = precond
+        self.floor_factor = floor_factor
         # initial guess of each solve: 0 (warm_start=False) or the previous accelerations extrapolated in time
         # with a polynomial of degree guess_order (0 = previous acceleration, 1 = linear, 2 = quadratic).
         # Measured on the B200 (sandwich mesh, 100^3 and 190^3 boxes): the iteration count of BiCGSTAB, with and without
@@ -216,7 +279,7 @@ class LinearTransient:
         self._x0_full, self._v0_full = x0, v0
         dt = self.dt
         self._ss = _SystemSolve(m, 1.0, self.gamma * dt, self.beta * dt ** 2, self.rtol, self.max_iter, self.check_every,
-                                self.precond)
+                                self.precond, floor_factor=self.floor_factor)
         self._w1 = torch.empty_like(self._x)
         self._w2 = torch.empty_like(self._x)
         self._rhs = torch.empty_like(self._x)

@@ -3,8 +3,8 @@ Checks that the planes are BITWISE identical (same chunks => same summation orde
 usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first[,bank_opt]" ...]   (first variant = reference;
 bank_opt = 1: bank-aware numbering of the staged elements, symbolic.optimize_banks; 2 / 3: optimised for the kernels with D /
 without D only)
-Kernel form (tool-level switch TEFEM_ASM_THREADS -> DeviceMesh.asm_threads): 0 = dynamic chunks (default), 64 | 128 | 256 = threads
-per CTA of the tile-synchronous kernel (pair with items = 2 x threads); build variants: TEFEM_LIB=/path/to/lib.so."""
+Kernel form (tool-level switch TEFEM_ASM_THREADS -> DeviceMesh.asm_threads): 256 (default) | 128 | 64 = threads per CTA of the tile-synchronous
+kernel, 0 = dynamic chunks (pair with items = 2 x threads); build variants: TEFEM_LIB=/path/to/lib.so."""
 import os
 import sys
 import time
@@ -40,7 +40,7 @@ for v in variants:
         S = optimize_banks(S, strides={1: 3, 2: 2, 3: 1}[bank])
     t_bank = time.perf_counter() - t_bank
     dm = DeviceMesh(pts, conn, np.zeros(E, dtype=np.int32), table, schedule=S)
-    dm.asm_threads = int(os.environ.get("TEFEM_ASM_THREADS", "0"))      # tool-level switch (the library has a setter)
+    dm.asm_threads = int(os.environ.get("TEFEM_ASM_THREADS", "256"))      # tool-level switch (the library has a setter)
     P = S.n_blocks
     line = (f"{v:16s} n_cta={S.n_cta} items={S.n_items} max_items={S.max_cta_items} max_el={S.max_cta_elems} slots={S.max_cta_slots} "
             f"symbolic {t_sym:.2f}s bank {t_bank:.2f}s |")

@@ -10,7 +10,14 @@ right-hand side (2 plane SpMVs), BiCGSTAB solve on the block-Jacobi-scaled syste
 correction as right preconditioner (two 4x4-block SpMVs + two preconditioner passes per iteration), corrector.
 Assembly of M, D, K (kernel K1) is timed separately on the same mesh and reported under "assembly".
 
-One JSON line is printed by rank 0; see DESIGN.md for the definition of every key.
+One JSON line is printed by rank 0; see DESIGN.md for the definition of every key.  Besides the contract's keys:
+  prepare_s        everything before the time loop on this mesh (assembly, Dirichlet elimination, block-Jacobi scaling,
+                   preconditioner set-up, halo set-up), max over ranks;  rhs_planes_spmv: bandwidth of the two plane SpMVs
+                   of the Newmark right-hand side;
+  parity_vs_1gpu   (N > 1) the row-partitioned solve against the single-GPU solve of a small box, in this very run;
+  same_config      (N = 1) GPU arm and the reference's CPU implementation on the SAME mesh and steps, both measured:
+                   BASELINE config 2 (examples/example_transient_2.py on data/sandwich.msh);
+  cpu_baseline     the reference's algorithm on a bounded sample, SCALED to the 28 M-DOF metric ("modelled": true).
 """
 import argparse
 import json
@@ -183,9 +190,30 @@ def run_tefem(args):
                        "pieces_first": bool(S.pieces_first), "bank_aware_numbering": bool(S.bank_optimized),
                        "lists_pitched": bool(S.lists_pitched), "smem_bytes_per_cta": int(S.smem_bytes())}
 
-    # ---- transient steps
+    # ---- everything before the time loop (assembly again, elimination, scaling, preconditioner, halo set-up)
+    barrier()
+    t0 = time.perf_counter()
     solver.prepare()
+    barrier()
+    prepare_s = max_over_ranks(time.perf_counter() - t0)
     kry = solver._ss.krylov
+    # ---- the two plane SpMVs of the Newmark right-hand side (D and K in plane storage, once per step)
+    planes = solver.planes if world > 1 else model._planes
+    rhs_spmv = {}
+    xin, yout = solver._w1, solver._rhs
+    for nm, pmap in (("D", solver._mapD), ("K", solver._mapK)):
+        dm.planes_spmv(planes[nm], pmap, xin, yout, alpha=-1.0, beta_y=1.0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dm.planes_spmv(planes[nm], pmap, xin, yout, alpha=-1.0, beta_y=1.0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+        nbytes = 8 * int(planes[nm].shape[0]) * P_loc + 4 * P_loc + 4 * (N_own + 1) + 3 * 8 * 4 * N_own
+        rhs_spmv[nm] = {"ms": ms, "planes": int(planes[nm].shape[0]), "algorithmic_bytes": nbytes,
+                        "achieved_gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm_peak}
     for i in range(1, args.warmup + 1):
         solver.step(i)
     barrier()
@@ -222,7 +250,7 @@ def run_tefem(args):
     spmv_avg_ms = max_over_ranks(spmv_ms / max(spmv_count, 1))
     spmv_gbs = spmv_bytes / spmv_avg_ms / 1e6
     traffic = None      # DRAM bytes per launch from the committed ncu --set full capture of this very command
-    tpath = os.path.join(ROOT, "profiles", "r1_spmv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_spmv_traffic.json")      # ncu --set full of the CURRENT kernel (profiles/README.md)
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
@@ -239,8 +267,11 @@ def run_tefem(args):
     if args.e2e_steps > 0:
         n_loc = 4 * dm.n_nodes if world == 1 else solver._x.numel()
         host = [torch.empty(n_loc, dtype=torch.float64).pin_memory() for _ in range(3)]
-        load_host = torch.from_numpy(surface_load()).pin_memory()
-        coef_dev = torch.empty(3, dtype=torch.float64, device="cuda")
+        # H2D: the step's load amplitudes (4 doubles per load term) live in pinned host memory and are copied to the device
+        # every step; the load kernel reads them from there (tefem_load_axpy_dev) - no amplitude travels as a kernel argument
+        n_terms = solver.n_load_terms()
+        coef_host = torch.zeros((max(n_terms, 1), 4), dtype=torch.float64).pin_memory()
+        coef_dev = torch.zeros((max(n_terms, 1), 4), dtype=torch.float64, device="cuda")
         first = args.warmup + args.steps + 1
         # the state of step i is snapshotted on the device (3 vector copies) and read back to pinned host memory on
         # a second stream while step i + 1 runs; every read-back completes inside the timed region
@@ -251,8 +282,10 @@ def run_tefem(args):
         barrier()
         t0 = time.perf_counter()
         for k, i in enumerate(range(first, first + args.e2e_steps)):
-            coef_dev.copy_(load_host[:, i], non_blocking=True)            # H2D: this step's load amplitudes
-            solver.step(i)
+            if n_terms:                                                    # (a rank may own no loaded node)
+                coef_host[:n_terms].copy_(torch.as_tensor(solver.load_coefficients(i), dtype=torch.float64).reshape(-1, 4))
+            coef_dev.copy_(coef_host, non_blocking=True)                   # H2D: this step's load amplitudes
+            solver.step(i, coef_dev=coef_dev)
             if k:
                 main.wait_event(ev_copied)                                 # previous read-back has left the staging copy
             for sdev, d in zip(stage, (solver._x, solver._v, solver._a)):
@@ -266,15 +299,22 @@ def run_tefem(args):
         torch.cuda.synchronize()
         barrier()
         dt_e2e = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": args.e2e_steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 24,
+        e2e = {"value": args.e2e_steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": int(sum_over_ranks(32 * n_terms)),
                "d2h_bytes_per_step": int(sum_over_ranks(3 * 8 * n_loc)), "steps": args.e2e_steps,
-               "note": "read-back of step i overlapped with step i + 1 (device snapshot + copy stream)"}
+               "note": "H2D = the step's load amplitudes from pinned memory (read by the load kernel on the device); "
+                       "read-back of step i overlapped with step i + 1 (device snapshot + copy stream)"}
+
+    # ---- N > 1: the partitioned solve against the single-GPU solve of a small box, in this run
+    parity = None
+    if world > 1 and args.parity_cells > 0:
+        parity = parity_vs_single_gpu(args.parity_cells, rank, world)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     cpu = cpu_baseline(n_dofs_total, budget_s=args.cpu_budget) if (world == 1 and args.cpu_budget > 0) else None
+    same = same_config_sandwich(args.same_config_steps) if (world == 1 and args.same_config_steps > 0) else None
     n_free = int(n_dofs_total - (len(model.dirichlet_dofs_U) + len(model.dirichlet_dofs_theta))) if world == 1 else None
     line = {
         "metric": "transient steps/s (implicit Newmark step of the coupled thermoelastic model, 28M DOF box)",
@@ -291,12 +331,149 @@ def run_tefem(args):
                    "dof_iterations_per_s": n_dofs_total * float(np.sum(iters)) / (ms_total * 1e-3),
                    "ms_per_iteration": ms_total / max(float(np.sum(iters)), 1.0),
                    "relres": [inf["relres"] for inf in infos], "restarts": [inf["restarts"] for inf in infos]},
-        "assembly": asm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "setup_s": t_setup,
+        "assembly": asm, "roofline": roofline, "cpu_baseline": cpu, "same_config": same, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup, "prepare_s": prepare_s,
+        "rhs_planes_spmv": rhs_spmv, "parity_vs_1gpu": parity,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_vs_single_gpu(cells, rank, world, steps=2):
+    """The row-partitioned transient solve of a cells^3 box on `world` GPUs against the single-GPU solve of the same box
+    (computed by rank 0 while the others wait): largest relative difference per field of x, v, a after `steps` steps."""
+    import torch
+    import torch.distributed as dist
+    mesh, model, solver = build_case(cells, rank, world)
+    solver.prepare()
+    infos = [solver.step(i) for i in range(1, steps + 1)]
+    lp = solver.lp
+    sizes = [int(4 * (lp.bounds[r + 1] - lp.bounds[r])) for r in range(world)]
+    full = []
+    for t in solver.owned_state():
+        pad = torch.zeros(max(sizes), dtype=torch.float64, device="cuda")
+        pad[:t.numel()] = t
+        out = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(out, pad)
+        full.append(torch.cat([o[:s_] for o, s_ in zip(out, sizes)]).cpu().numpy())
+    res = None
+    if rank == 0:
+        _, _, ref = build_case(cells, 0, 1)
+        ref.prepare()
+        ref_infos = [ref.step(i) for i in range(1, steps + 1)]
+        want = [(ref._x + ref.model._g_fill).cpu().numpy(), ref._v.cpu().numpy(), ref._a.cpu().numpy()]
+        worst = {}
+        for name, got, w in zip(("x", "v", "a"), full, want):
+            idx = np.arange(w.size)
+            for fld, m in (("u", idx % 4 != 3), ("theta", idx % 4 == 3)):
+                worst[f"{name}_{fld}"] = float(np.linalg.norm(got[m] - w[m]) / max(np.linalg.norm(w[m]), 1e-300))
+        res = {"cells": cells, "n_dofs": int(want[0].size), "steps": steps, "rel_diff": worst, "max_rel_diff": max(worst.values()),
+               "ok": bool(max(worst.values()) < 1e-7), "tolerance": 1e-7,
+               "iterations": {"partitioned": [i["iterations"] for i in infos], "single_gpu": [i["iterations"] for i in ref_infos]}}
+        del ref
+    del solver
+    torch.cuda.synchronize()
+    dist.barrier()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# same mesh, same steps, both measured: BASELINE config 2 (examples/example_transient_2.py on data/sandwich.msh)
+# ---------------------------------------------------------------------------------------------------
+def _sandwich_config2(ns, n_steps, mesh_path=None, blocks=None):
+    """Model + LinearTransient of example_transient_2.py truncated to n_steps steps (same dt = 1800 / 999) for the package
+    `ns` (the reference's modules, or this repo's)."""
+    dt = T_END / (N_T - 1)
+    n_t = n_steps + 1
+    vec_t = np.linspace(0., dt * n_steps, n_t)
+    mesh = ns.Mesh()
+    if blocks is not None:
+        mesh.from_blocks(*blocks)
+    else:
+        mesh.load_mesh(mesh_path)
+    mat = ns.LinearThermoElastic(**MAT2)
+    mesh.set_materials({1: mat, 2: mat, 3: mat})
+    mesh.make_elements()
+    arr = np.zeros((3, n_t))
+    arr[0, :] = np.sin(2 * np.pi * vec_t / 900.) * -1e9
+    model = ns.Model(mesh, dict_dirichlet_U=DU, dict_dirichlet_theta=DT, dict_surface_forces={5: arr},
+                     alpha_M=ALPHA_M, alpha_K=ALPHA_K)
+    n = mesh.n_nodes
+    return model, (model, np.zeros(3 * n), np.zeros(3 * n), np.zeros(n), np.zeros(n), dt * n_steps, n_t, 0.5, 0.25)
+
+
+def same_config_sandwich(ref_steps=5, gpu_steps=200):
+    """BASELINE config 2 on BOTH arms, measured in this run: the unmodified reference (its own classes, byte code under
+    oracle/_ref or the sources when present; SuperLU re-factorised every step, one core) and this repo through the same
+    public API.  Both are timed over the bodies of their time loops (the reference's through the iterator it wraps its loop
+    in, solvers.py:163); set-up (assembly, DOF maps) is reported beside each."""
+    import types
+    import torch
+    import thermoelasticity_fem_b200 as te
+    from oracle import reference_shim as rs
+    out = {"workload": "BASELINE config 2: examples/example_transient_2.py on data/sandwich.msh (3 119 nodes, 13 712 tets, "
+                       "12 476 DOF), dt = 1800/999 s, Rayleigh 0.2 / 0.2", "metric": "transient steps/s", "same_config": True}
+    # ---- GPU arm
+    g = np.load(rs.SANDWICH_NPZ)
+    blocks = [(str(g[f"b{i}_type"]), int(g[f"b{i}_tag"]), g[f"b{i}_conn"].astype(np.int64)) for i in range(int(g["n_blocks"]))]
+    ns_gpu = types.SimpleNamespace(Mesh=te.Mesh, LinearThermoElastic=te.LinearThermoElastic, Model=te.Model)
+    model, targs = _sandwich_config2(ns_gpu, gpu_steps, blocks=(g["points"], blocks))
+    solver = te.LinearTransient(*targs, progress=False, history='last')
+    t0 = time.perf_counter()
+    solver.prepare()
+    torch.cuda.synchronize()
+    t_prep = time.perf_counter() - t0
+    for i in range(1, 4):
+        solver.step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    its = [solver.step(i)["iterations"] for i in range(4, gpu_steps + 1)]
+    torch.cuda.synchronize()
+    dt_gpu = time.perf_counter() - t0
+    out["gpu"] = {"steps_per_s": (gpu_steps - 3) / dt_gpu, "steps_timed": gpu_steps - 3, "prepare_s": t_prep,
+                  "iterations_per_step": float(np.mean(its))}
+    del solver, model
+    out["reference"] = same_config_reference(ref_steps)
+    if "steps_per_s" in out["reference"]:
+        out["ratio_measured"] = out["gpu"]["steps_per_s"] / out["reference"]["steps_per_s"]
+    return out
+
+
+def same_config_reference(ref_steps=5):
+    """The unmodified reference on BASELINE config 2, timed on the host cores (see same_config_sandwich)."""
+    import types
+    from oracle import reference_shim as rs
+    if not rs.available():
+        return {"unavailable": "neither /root/reference nor oracle/_ref byte code present"}
+    ref = rs.load_reference()
+    ns_ref = types.SimpleNamespace(Mesh=ref.mesh.Mesh, LinearThermoElastic=ref.materials.LinearThermoElastic, Model=ref.model.Model)
+    # the reference wraps its time loop in tqdm (solvers.py:163): substituting a timing iterator for the progress bar gives
+    # the start time of every loop body without touching the reference's code
+    stamps = []
+
+    def timed(iterable, *a, **k):
+        for item in iterable:
+            stamps.append(time.perf_counter())
+            yield item
+        stamps.append(time.perf_counter())
+
+    _, rargs = _sandwich_config2(ns_ref, ref_steps, mesh_path=rs.sandwich_path())
+    rsolver = ref.solvers.LinearTransient(*rargs)
+    saved = ref.solvers.tqdm
+    ref.solvers.tqdm = timed
+    try:
+        t0 = time.perf_counter()
+        rsolver.solve()
+        t_total = time.perf_counter() - t0
+    finally:
+        ref.solvers.tqdm = saved
+    per_step = (stamps[-1] - stamps[0]) / ref_steps
+    return {"steps_per_s": 1.0 / per_step, "s_per_step": per_step, "steps_timed": ref_steps, "cores": 1,
+            "kind": "reference", "source": "sources" if rs.sources_available() else "byte code (oracle/_ref)",
+            "what_is_timed": "the bodies of the reference's own time loop (solvers.py:163-186: assemble_F, apply_dirichlet_F, "
+                             "2 SpMV, spsolve re-factorised, updates), via the iterator it wraps the loop in",
+            "solve_call_s_incl_assembly_and_postprocessing": t_total, "host_cpu_count": os.cpu_count()}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -373,7 +550,7 @@ def cpu_baseline(n_dofs_full, budget_s=20.0, cells=16):
         n += 1
     dt = time.perf_counter() - t1
     raw = n / dt
-    return {"value": raw * case.n_dofs / n_dofs_full, "unit": "steps/s", "cores": 1, "kind": "port",
+    return {"value": raw * case.n_dofs / n_dofs_full, "unit": "steps/s", "cores": 1, "kind": "port", "modelled": True,
             "sample": f"oracle port of the reference step (F, lifting, 2 SpMV, scipy spsolve re-factorised every step) on a "
                       f"{cells}^3-cell Kuhn box = {case.n_dofs} DOF ({n} steps timed, {raw:.4f} steps/s there); "
                       f"assembly port = per-element Python loop",
@@ -382,8 +559,11 @@ def cpu_baseline(n_dofs_full, budget_s=20.0, cells=16):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and is
-    not present on the GPU box) on the host cores, same metric / unit, each step a bounded sample of the workload."""
+    """--impl reference: the reference's CPU algorithm on the host cores, same metric / unit.  The reference cannot run
+    the 28 M-DOF workload at all (dense n_dofs^2 assembly, model.py:88), so `value` is MODELLED ("modelled": true): the
+    oracle port of its step on a bounded sample box, scaled linearly in the DOF count.  The MEASURED like-for-like figure is
+    in "same_config": the unmodified reference (oracle/_ref byte code, or its sources) on BASELINE config 2, the mesh it
+    ships - bench.py's own arm reports the GPU side of the same block."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -410,11 +590,16 @@ def run_reference(args):
                                    "transient (config-2 material/BCs/load/Rayleigh), BiCGSTAB rtol 1e-10 per field, "
                                "block-Jacobi scaling + 3-level aggregation preconditioner",
                        "cells": args.cells, "n_tets": E_total, "n_dofs": n_dofs_total},
-            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
+            "modelled": True,
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 1, "kind": "port", "modelled": True, "sample": sample,
                              "sample_value": raw, "sample_n_dofs": case.n_dofs, "scaled_to": SCALING_RULE,
                              "host_cpu_count": os.cpu_count()},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.same_config_steps > 0:
+        line["same_config"] = {"workload": "BASELINE config 2: examples/example_transient_2.py on data/sandwich.msh (12 476 DOF)",
+                               "metric": "transient steps/s", "same_config": True,
+                               "reference": same_config_reference(args.same_config_steps)}
     print(json.dumps(line))
 
 
@@ -428,6 +613,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline (0 = skip)")
     ap.add_argument("--ref-cells", type=int, default=16)
+    ap.add_argument("--parity-cells", type=int, default=24, help="N > 1: box for the partitioned-vs-single-GPU check (0 = skip)")
+    ap.add_argument("--same-config-steps", type=int, default=5,
+                    help="N = 1: reference steps of BASELINE config 2 timed beside the GPU arm (0 = skip; ~25 s of CPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -255,6 +255,9 @@ int tefem_precond_apply(tefem_precond* pc, const double* r, double* z, void* str
 /* Multi-GPU: agg_ranks[n_agg] (uint8 device array, bit r set iff rank r owns fine nodes of the aggregate) restricts the
  * in-kernel all-reduce of the restricted residual to the ranks that contribute (the others hold exact zeros).      */
 int tefem_precond_set_agg_ranks(tefem_precond* pc, const uint8_t* agg_ranks);
+/* Level-1 operator in HALF precision (same block layout as sys1, 16 halves per block, 32-byte aligned; NULL detaches):
+ * the six level-1 sweeps of an application then read half the bytes.  Preconditioner data only.                     */
+int tefem_precond_set_level1_half(tefem_precond* pc, const void* sys1_half);
 /* Attach (or detach with NULL) a preconditioner to the Krylov driver. */
 int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc);
 
@@ -307,6 +310,10 @@ int tefem_lincomb3(int64_t n, double c0, const double* x0, double c1, const doub
  * time-dependent amplitude (model.py:120-286: area/3 and volume/4 lumping).  node[] unique.     */
 int tefem_load_axpy(int64_t n_entries, const int32_t* node, const double* w, const double* h_coef,
                     double* F, void* stream);
+/* Same, with the four amplitudes in DEVICE memory (d_coef[4]): the end-to-end path copies the step's amplitudes from
+ * pinned host memory instead of passing them as kernel arguments.                                                  */
+int tefem_load_axpy_dev(int64_t n_entries, const int32_t* node, const double* w, const double* d_coef,
+                        double* F, void* stream);
 
 /* ---- multi-GPU communicator (NCCL over NVLink), one process per GPU ------------------------- */
 typedef struct tefem_comm tefem_comm;

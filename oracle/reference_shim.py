@@ -26,12 +26,34 @@ import numpy as np
 REFERENCE_ROOT = os.environ.get("TEFEM_REFERENCE_ROOT", "/root/reference")
 REFERENCE_SRC = os.path.join(REFERENCE_ROOT, "src")
 SANDWICH_MSH = os.path.join(REFERENCE_ROOT, "data", "sandwich.msh")
+# byte code of the unmodified reference built by oracle/build_ref.py (travels to the GPU box; git-ignored)
+REFERENCE_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+# the reference's data/sandwich.msh as arrays (committed fixture): what `meshio.read` returns for a path ending in .npz
+SANDWICH_NPZ = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "sandwich_mesh.npz")
 
 _GMSH_TYPE = {15: ("vertex", 1), 1: ("line", 2), 2: ("triangle", 3), 4: ("tetra", 4)}
 
 
-def available():
+def sources_available():
     return os.path.isdir(os.path.join(REFERENCE_SRC, "thermoelasticity_fem"))
+
+
+def bytecode_available():
+    d = os.path.join(REFERENCE_PYC, "thermoelasticity_fem")
+    ver = os.path.join(d, "PYTHON_VERSION")
+    if not (os.path.exists(os.path.join(d, "solvers.pyc")) and os.path.exists(ver)):
+        return False
+    with open(ver) as fh:                         # byte code is specific to the minor version of the interpreter
+        return fh.read().split(".")[:2] == sys.version.split()[0].split(".")[:2]
+
+
+def available():
+    return sources_available() or bytecode_available()
+
+
+def sandwich_path():
+    """What to pass to the reference's Mesh.load_mesh: its own data/sandwich.msh, or the committed array copy."""
+    return SANDWICH_MSH if os.path.exists(SANDWICH_MSH) else SANDWICH_NPZ
 
 
 class _CellBlock:
@@ -99,8 +121,14 @@ def parse_gmsh41(path):
     return pts, blocks
 
 
+def _read_npz_blocks(path):
+    g = np.load(path)
+    blocks = [(str(g[f"b{i}_type"]), int(g[f"b{i}_tag"]), g[f"b{i}_conn"].astype(np.int64)) for i in range(int(g["n_blocks"]))]
+    return g["points"], blocks
+
+
 def _meshio_read(path):
-    pts, blocks = parse_gmsh41(path)
+    pts, blocks = _read_npz_blocks(path) if str(path).endswith(".npz") else parse_gmsh41(path)
     cells = [_CellBlock(t, c) for t, _, c in blocks]
     cd = {"gmsh:physical": [np.full(c.shape[0], p, dtype=np.int64) for _, p, c in blocks]}
     return _MeshioMesh(pts, cells, cd)
@@ -125,10 +153,11 @@ def _install_stand_ins():
 def load_reference():
     """Returns the reference's modules (elements, materials, mesh, model, solvers) as a namespace."""
     if not available():
-        raise RuntimeError("reference sources not present at %s" % REFERENCE_SRC)
+        raise RuntimeError("reference not present: neither sources at %s nor byte code at %s" % (REFERENCE_SRC, REFERENCE_PYC))
     _install_stand_ins()
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    where = REFERENCE_SRC if sources_available() else REFERENCE_PYC
+    if where not in sys.path:
+        sys.path.insert(0, where)
     import importlib
     ns = types.SimpleNamespace()
     for name in ("elements", "materials", "mesh", "model", "solvers"):

@@ -404,9 +404,9 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
     G = (D1inv @ (P1.T @ A @ P1)).tocsr()
     Gd, A1d = G.toarray(), A1.toarray()
     off_diag = ~np.kron(np.eye(n1, dtype=bool), np.ones((8, 8), dtype=bool))
-    assert np.abs(Gd - A1d)[off_diag].max() <= 2e-7 * np.abs(Gd).max()          # stored in single precision
+    assert np.abs(Gd - A1d)[off_diag].max() <= 1e-3 * np.abs(Gd).max()          # level 1 is stored in half precision
     blk = np.abs(A1d[~off_diag].reshape(n1, 8, 8) - np.eye(8)).max()
-    assert blk <= 1e-6                                                           # scaled diagonal blocks = identity
+    assert blk <= 1e-3                                                           # scaled diagonal blocks = identity (half precision)
     P2 = bsr(pc.p2_rowptr, pc.p2_colidx, pc.p2_vals, (8 * n1, 8 * n2))
     R2 = bsr(pc.r2_rowptr, pc.r2_colidx, pc.r2_vals, (8 * n2, 8 * n1))
     assert abs(R2 - P2.T).max() == 0.0
@@ -425,19 +425,14 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
         xc = xc + pc.omega_c * (bc - A1 @ xc)
     z_host = pc.omega * r + P1 @ xc
     z = torch.empty(4 * n, dtype=torch.float64, device="cuda")
-    pc.apply(torch.from_numpy(r).cuda(), z)                                       # one cooperative kernel (default)
+    pc.apply(torch.from_numpy(r).cuda(), z)                                       # separate launches (default)
     assert np.abs(z.cpu().numpy() - z_host).max() <= 1e-11 * np.abs(z_host).max()
-    # the same application as separate launches (measurement alternative, TEFEM_PRECOND_FUSED=0 at creation)
-    import os
-    os.environ["TEFEM_PRECOND_FUSED"] = "0"
-    try:
-        pc2 = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10)
-    finally:
-        del os.environ["TEFEM_PRECOND_FUSED"]
+    # the same with the level-1 operator kept in single precision
+    pc2 = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10, level1_dtype="fp32")
+    assert pc.level1_dtype == "fp16" and pc2.level1_dtype == "fp32"
     z2 = torch.empty_like(z)
     pc2.apply(torch.from_numpy(r).cuda(), z2)
-    assert np.abs(z2.cpu().numpy() - z_host).max() <= 1e-11 * np.abs(z_host).max()
-    assert np.abs((z2 - z).cpu().numpy()).max() <= 1e-12 * np.abs(z_host).max()
+    assert np.abs((z2 - z).cpu().numpy()).max() <= 5e-3 * np.abs(z_host).max()      # half-precision storage: ~5e-4 relative
 
 
 def test_steady_state_multilevel_matches_block_jacobi_and_oracle():
@@ -497,10 +492,9 @@ def test_transient_sandwich_full_run_vs_reference_states(sandwich_mesh2):
 
 
 # ---- measurement knobs of K1 -------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("threads,items", [(0, 512), (128, 256), (64, 128)])
+@pytest.mark.parametrize("threads,items", [(128, 256), (64, 128)])
 def test_assembly_thread_count_variants_are_bitwise_the_default(threads, items):
-    """The other kernel forms of K1 (dynamic chunks = 0; 128 / 64 threads per CTA; tefem_assemble_set_threads) must produce
-    the planes of the default (tile-synchronous, 256 threads) bit for bit."""
+    """The 128- and 64-thread instantiations of K1 (tefem_assemble_set_threads) must produce the default's planes bit for bit."""
     import torch
     from thermoelasticity_fem_b200 import LinearThermoElastic
     from thermoelasticity_fem_b200.device import DeviceMesh
@@ -517,3 +511,22 @@ def test_assembly_thread_count_variants_are_bitwise_the_default(threads, items):
         outs[tag] = {k: v.cpu().numpy() for k, v in dm.assemble("MKD", 0.2, 0.2).items()}
     for k in outs["default"]:
         assert np.array_equal(outs["default"][k], outs["variant"][k]), k
+
+
+def test_clear_full_matrices_keeps_the_reduced_operators_usable():
+    """reference sequence apply_dirichlet_matrices(); clear_full_matrices() (model.py:288-302): mat_K reads None, mat_K_f_f and
+    every later solve keep working (the planes back both views)."""
+    from thermoelasticity_fem_b200 import LinearSteadyState
+    pts, groups, mesh, model, dU, dT, loads = _kuhn_steady_model(8, 4, 3)
+    model.create_free_dofs_lists()
+    model.assemble_K()
+    model.assemble_F()
+    model.apply_dirichlet_matrices()
+    nnz = model.mat_K_f_f.nnz
+    model.clear_full_matrices()
+    assert model.mat_K is None and model.mat_M is None
+    assert model.mat_K_f_f is not None and model.mat_K_f_f.nnz == nnz
+    model.apply_dirichlet_F()
+    assert model.lift_vector() is not None
+    model.assemble_K()                       # re-assembly restores the full view
+    assert model.mat_K is not None

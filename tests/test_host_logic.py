@@ -192,3 +192,9 @@ def test_preconditioner_hierarchy_host_logic():
     for a in range(n2):
         cells = ijk[agg2 == a]
         assert np.all(cells.max(axis=0) - cells.min(axis=0) < f2)
+
+
+def test_plots_module_exports_the_names_the_reference_examples_import():
+    """reference examples import these at module top level (example_steadystate.py:13, example_UQ_1.py): the names must exist."""
+    from thermoelasticity_fem_b200.plots import (animate_U_T, plot_U_T, plot_dofU_vs_t, plot_dofU_vs_t_random,  # noqa: F401
+                                                  plot_nodeT_vs_t, plot_nodeT_vs_t_random)

@@ -46,11 +46,13 @@ _SIGNATURES = {
     "tefem_precond_apply": [P, P, P, P],
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_precond_set_agg_ranks": [P, P],
+    "tefem_precond_set_level1_half": [P, P],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_cg": [P, P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
     "tefem_newmark_correct": [c_int64, P, P, P, P, c_double, c_double, c_double, P, P],
     "tefem_load_axpy": [c_int64, P, P, P, P, P],
+    "tefem_load_axpy_dev": [c_int64, P, P, P, P, P],
     "tefem_lincomb3": [c_int64, c_double, P, c_double, P, c_double, P, P, P],
     "tefem_comm_unique_id": [c_char_p, P],
     "tefem_comm_create": [P, c_char_p, P, c_int, c_int],

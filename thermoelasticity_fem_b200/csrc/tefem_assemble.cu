@@ -497,181 +497,6 @@ __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(c
     }
 }
 
-// ---- K1, dynamic form (default for the pieces-first layout) ----------------------------------------------------------
-// ncu of the tile-synchronous kernel above (profiles/r2a_*): the shared-memory pipe that bounds it is busy only 65 - 68 %
-// of the cycles and 32 % of the stall samples sit at the three CTA barriers of a tile - the phases of a tile do not
-// fill the 256 threads evenly (480 elements, 78 pieces, 445 blocks) and every warp waits for the slowest one three
-// times per tile, with only two CTAs per SM to cover for each other.
-// Here ONE persistent CTA of 16 warps owns the SM and there is no CTA-wide barrier in the tile loop.  The work of a
-// tile is cut into CHUNKS of 32 consecutive entries (32 staged elements of phase 1, 32 pieces, 32 blocks in block
-// order: a warp still stores 32 consecutive blocks of every plane) that the warps GRAB from shared-memory counters;
-// dependencies are counters too: a warp starts the gathers of tile k when all phase-1 chunks of k are done and reads the
-// parked pieces when all piece chunks are done.  A warp that finds no chunk left in tile k LEAVES it and moves on to
-// phase 1 of tile k + 1 while others still gather for k: the phases of consecutive tiles overlap and the pipe stays
-// busy.  Records and partial sums are double-buffered, the TMA stage triple-buffered; the LAST warp to leave tile k
-// (every chunk of k is finished then, and no warp will look at its stage again) issues the prefetch of tile k + 3 into
-// the stage of k, so no warp can run more than two tiles ahead of the slowest one and the mbarrier phase a warp waits
-// for is never ambiguous; phase 1 of tile k additionally waits until every warp has left tile k - 2 (its records).  All counters are monotonic (never reset): a warp visits every tile of its CTA in order and keeps the
-// running chunk totals per buffer parity in registers, so a grab is a bounded compare-and-swap and "phase complete" is
-// `done >= total`; counts of tiles k and k + 2 cannot mix because k + 2 starts only after every warp has left k.
-// Same items, same per-item summation order as the tile-synchronous kernel: the planes are BITWISE identical.
-constexpr int DYN_THREADS = 512;
-constexpr int DYN_STAGES = 3;          // TMA stages: the prefetch of a tile is issued two tiles before it is consumed
-enum { C_P1_NEXT = 0, C_P1_DONE, C_PC_NEXT, C_PC_DONE, C_BL_NEXT, C_LEFT, C_PER_PARITY = 8 };
-
-__device__ __forceinline__ unsigned ld_shared_volatile(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-// lane 0 takes the next chunk number below `limit` (bounded: the counter never passes the tile's total); -1 when none
-__device__ __forceinline__ int chunk_grab(unsigned* ctr, unsigned limit, int lane) {
-    int id = -1;
-    if (lane == 0) {
-        unsigned old = ld_shared_volatile(ctr);
-        while ((int)(old - limit) < 0) {
-            const unsigned seen = atomicCAS(ctr, old, old + 1);
-            if (seen == old) { id = (int)old; break; }
-            old = seen;
-        }
-    }
-    return __shfl_sync(0xffffffffu, id, 0);
-}
-// every lane's shared-memory writes of the chunk are ordered before the count; returns the count before this chunk
-__device__ __forceinline__ unsigned chunk_done(unsigned* ctr, int lane) {
-    __threadfence_block();
-    __syncwarp();
-    unsigned old = 0;
-    if (lane == 0) old = atomicAdd(ctr, 1u);
-    return __shfl_sync(0xffffffffu, old, 0);
-}
-__device__ __forceinline__ void chunk_wait(const unsigned* ctr, unsigned total, int lane) {
-    if (lane == 0) {
-        while ((int)(ld_shared_volatile(ctr) - total) < 0) {}
-    }
-    __syncwarp();
-    __threadfence_block();
-}
-
-// One lane: issue the bulk copies of tile t into stage buffer `st` (header read from global memory here).
-__device__ __forceinline__ void prefetch_tile_now(const AssembleArgs& A, int t, char* st, const StageLayout& L, uint64_t* bar) {
-    const int4* hg = reinterpret_cast<const int4*>(A.cta_hdr) + 3 * (size_t)t;
-    prefetch_tile(A, t, __ldg(hg), __ldg(hg + 1), __ldg(hg + 2), st, L, bar);
-}
-
-template <int OPS, int DUU>
-__global__ void __launch_bounds__(DYN_THREADS, 1) assemble_dyn_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
-                                                                      int part_doubles) {
-    extern __shared__ __align__(128) double smem[];
-    typedef AsmTraits<OPS, DUU> T;
-    const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
-    double* recs0 = smem;                                   // [2][rec_doubles]
-    double* parts0 = recs0 + 2 * (size_t)rec_doubles;       // [2][part_doubles]
-    char* stage0 = reinterpret_cast<char*>(parts0 + 2 * (size_t)part_doubles);   // [DYN_STAGES][L.bytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + DYN_STAGES * (size_t)L.bytes);
-    unsigned* ctr0 = reinterpret_cast<unsigned*>(bars + 4); // [2][C_PER_PARITY]
-#ifdef ASM_TAB_SELECT
-    const QuadS tabS = make_quad_s(c_quad.S);
-    const QuadNN tabNN = make_quad_nn(c_quad.NN);
-#else
-    double* tabS_s = reinterpret_cast<double*>(ctr0 + 2 * C_PER_PARITY);
-    double* tabNN_s = tabS_s + 4;
-    if (threadIdx.x < 4) tabS_s[threadIdx.x] = c_quad.S[threadIdx.x];
-    if (threadIdx.x < 16) tabNN_s[threadIdx.x] = c_quad.NN[threadIdx.x];
-    const QuadS tabS = make_quad_s(tabS_s);
-    const QuadNN tabNN = make_quad_nn(tabNN_s);
-#endif
-    const int G = gridDim.x, lane = threadIdx.x & 31;
-    const int K = (A.n_cta - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA: blockIdx.x, blockIdx.x + G, ...
-    if (threadIdx.x < 2 * C_PER_PARITY) ctr0[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < DYN_STAGES; ++q) mbar_init(&bars[q], 1);
-        fence_proxy_async();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < DYN_STAGES; ++q)
-            if (q < K) prefetch_tile_now(A, blockIdx.x + q * G, stage0 + (size_t)q * L.bytes, L, &bars[q]);
-    }
-    const double W4 = c_quad.W4;
-    // chunk totals of the tiles this warp has passed, per buffer parity (cur = parity of tile k)
-    unsigned p1_cur = 0, p1_oth = 0, pc_cur = 0, pc_oth = 0, bl_cur = 0, bl_oth = 0;
-    int sidx = 0;                 // k % DYN_STAGES
-    uint32_t sphase = 0;          // (k / DYN_STAGES) & 1
-    for (int k = 0; k < K; ++k) {
-        const int b = k & 1;
-        char* st = stage0 + (size_t)sidx * L.bytes;
-        double* recs = recs0 + (size_t)b * rec_doubles;
-        double* partials = parts0 + (size_t)b * part_doubles;
-        unsigned* c = ctr0 + b * C_PER_PARITY;
-        while (!mbar_try_wait(&bars[sidx], sphase)) {}
-        // the records / partial sums of parity b were last used by tile k - 2: every warp must have left it
-        chunk_wait(c + C_LEFT, (unsigned)(DYN_THREADS / 32) * (unsigned)(k >> 1), lane);
-        const int32_t* hdr = reinterpret_cast<const int32_t*>(st + L.hdr);
-        const int n_items = hdr[H_NITEMS], n_elems = hdr[H_NELEMS], o_elems = hdr[H_OELEMS], n_piece = hdr[H_NPIECE];
-        const int32_t block0 = hdr[H_BLOCK0];
-        const double* xyz = reinterpret_cast<const double*>(st + L.xyz);
-        const uint32_t* conn8 = reinterpret_cast<const uint32_t*>(st + L.conn8);
-        const int32_t* it_inc = reinterpret_cast<const int32_t*>(st + L.it_inc);
-        const int32_t* it_meta = reinterpret_cast<const int32_t*>(st + L.it_meta);
-        const uint16_t* inc_s = reinterpret_cast<const uint16_t*>(st + L.inc);
-        const unsigned p1_tot = p1_cur + (unsigned)((n_elems + 31) >> 5);
-        const unsigned pc_tot = pc_cur + (unsigned)((n_piece + 31) >> 5);
-        const unsigned bl_tot = bl_cur + (unsigned)((n_items - n_piece + 31) >> 5);
-        // phase 1: geometry records, 32 staged elements per chunk
-        for (;;) {
-            const int id = chunk_grab(c + C_P1_NEXT, p1_tot, lane);
-            if (id < 0) break;
-            const int le = (int)((unsigned)id - p1_cur) * 32 + lane;
-            if (le < n_elems) {
-                const double det = stage_element_local<T::WANT_D>(xyz, conn8[le], recs + (size_t)le * T::REC);
-                if (!(det > 0.0)) {  // error path only: elements.py:207-210
-                    const int32_t e = A.cta_elems[o_elems + le];
-                    if (det < 0.0) atomicMin(A.bad_elem, e);
-                    else atomicMin(A.bad_elem + 1, e);
-                }
-            }
-            chunk_done(c + C_P1_DONE, lane);
-        }
-        chunk_wait(c + C_P1_DONE, p1_tot, lane);
-        // phase 2a: pieces of split blocks park their values
-        for (;;) {
-            const int id = chunk_grab(c + C_PC_NEXT, pc_tot, lane);
-            if (id < 0) break;
-            const int it = (int)((unsigned)id - pc_cur) * 32 + lane;
-            if (it < n_piece)
-                process_pf_item<OPS, DUU>(A, -1, (uint32_t)it_inc[it], it_meta[it], recs, inc_s, partials, W4, tabS, tabNN);
-            chunk_done(c + C_PC_DONE, lane);
-        }
-        // phase 2b: one lane per block, 32 consecutive blocks per chunk
-        for (;;) {
-            const int id = chunk_grab(c + C_BL_NEXT, bl_tot, lane);
-            if (id < 0) break;
-            const int q = (int)((unsigned)id - bl_cur) * 32 + lane;     // block of the tile
-            const int it = n_piece + q;
-            const bool live = it < n_items;
-            const int32_t meta = live ? it_meta[it] : 0;
-            if (__any_sync(0xffffffffu, live && meta_slot(meta) >= 0)) chunk_wait(c + C_PC_DONE, pc_tot, lane);   // combine items
-            if (live)
-                process_pf_item<OPS, DUU>(A, block0 + q, (uint32_t)it_inc[it], meta, recs, inc_s, partials, W4, tabS, tabNN);
-        }
-        // leave tile k; the last of the CTA's warps to do so frees its STAGE for tile k + DYN_STAGES (the prefetch runs
-        // DYN_STAGES - 1 tiles ahead of the consumers; records and partial sums are double-buffered, see the wait above)
-        const unsigned left = chunk_done(c + C_LEFT, lane);
-        if (left + 1u == (unsigned)(DYN_THREADS / 32) * (unsigned)((k >> 1) + 1) && k + DYN_STAGES < K && lane == 0) {
-            fence_proxy_async();
-            prefetch_tile_now(A, (int)blockIdx.x + (k + DYN_STAGES) * G, st, L, &bars[sidx]);
-        }
-        if (++sidx == DYN_STAGES) { sidx = 0; sphase ^= 1u; }
-        // next tile: swap the parities
-        const unsigned t1 = p1_oth, t2 = pc_oth, t3 = bl_oth;
-        p1_oth = p1_tot; pc_oth = pc_tot; bl_oth = bl_tot;
-        p1_cur = t1; pc_cur = t2; bl_cur = t3;
-    }
-}
-
 __global__ void __launch_bounds__(128) element_matrices_kernel(
     const double* __restrict__ coords, const int32_t* __restrict__ conn, const int32_t* __restrict__ mat_id,
     const double* __restrict__ mat_table, const int64_t* __restrict__ elem_idx, int64_t n, int kinds,
@@ -718,49 +543,21 @@ static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStre
     return TEFEM_OK;
 }
 
-template <int OPS, int DUU>
-static int launch_assemble_dyn(const AssembleArgs& A, const TileDims& d, cudaStream_t st, bool* fits) {
-    const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
-    const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
-    const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
-    const size_t smem = 2 * ((size_t)rec_doubles + part_doubles) * sizeof(double) + DYN_STAGES * (size_t)L.bytes + 32 +
-                        2 * C_PER_PARITY * sizeof(unsigned) + 20 * sizeof(double);
-    *fits = smem <= 227 * 1024;
-    if (!*fits) return TEFEM_OK;                  // the caller falls back to the tile-synchronous kernel
-    static int sm_count = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_dyn_kernel<OPS, DUU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        int dev = 0;
-        TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
-        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
-    int grid = sm_count;                          // one persistent CTA per SM
-    if (grid > d.n_cta) grid = d.n_cta;
-    assemble_dyn_kernel<OPS, DUU><<<grid, DYN_THREADS, smem, st>>>(A, d, rec_doubles, part_doubles);
-    TEFEM_LAUNCH_CHECK();
-    return TEFEM_OK;
-}
-
-// Kernel form of the pieces-first layout: the threads per CTA of the tile-synchronous kernel, 256 (default) | 128 | 64,
-// or 0 = dynamic chunks (one 512-thread CTA per SM; measured slower than the default, profiles/README.md).  Set with
-// tefem_assemble_set_threads (measurement knob; the environment is not consulted on the launch path).
+// Threads per CTA of the pieces-first kernel: 256 (default) | 128 | 64, set with tefem_assemble_set_threads (measurement
+// knob; the environment is not consulted on the launch path).  A fourth form - ONE persistent 512-thread CTA per SM
+// whose warps grab 32-entry chunks from shared-memory counters, no CTA barrier, records double-buffered, TMA
+// triple-buffered - was built and measured in round 2 (bitwise equal planes; K 1.39 - 1.52 ms, M + D + K 1.66 - 1.75 ms
+// against 0.83 / 1.28 ms on the 100^3 box) and removed: all 16 warps then sit in the dependency chain of the SAME tile,
+// and what hides the latencies of a tile is other, independent tiles in flight (profiles/README.md).
 static int g_asm_threads = ASM_THREADS;
 static int asm_threads() { return g_asm_threads; }
 
 template <int OPS, int DUU>
 static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
-    int nt = asm_threads();
+    const int nt = asm_threads();
     if (!d.pieces_first) {
-        TEFEM_REQUIRE(nt == 0 || nt == ASM_THREADS, "tefem_assemble_set_threads applies to the pieces-first item layout only");
+        TEFEM_REQUIRE(nt == ASM_THREADS, "tefem_assemble_set_threads applies to the pieces-first item layout only");
         return launch_assemble_pf<OPS, DUU, false, ASM_THREADS>(A, d, st);
-    }
-    if (nt == 0) {
-        bool fits = false;
-        const int rc = launch_assemble_dyn<OPS, DUU>(A, d, st, &fits);
-        if (rc || fits) return rc;
-        nt = ASM_THREADS;                         // tiles too large for the double buffers: tile-synchronous kernel
     }
     switch (nt) {
         case ASM_THREADS: return launch_assemble_pf<OPS, DUU, true, ASM_THREADS>(A, d, st);
@@ -770,7 +567,7 @@ static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_
 #endif
         default: break;
     }
-    set_error("kernel form of the assembly must be 0, 64, 128 or 256 (tefem_assemble_set_threads)");
+    set_error("threads per CTA of the assembly kernel must be 64, 128 or 256 (tefem_assemble_set_threads)");
     return TEFEM_ERR_INVALID;
 }
 
@@ -851,8 +648,7 @@ extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta,
 }
 
 extern "C" int tefem_assemble_set_threads(int threads) {
-    TEFEM_REQUIRE(threads == 0 || threads == 64 || threads == 128 || threads == 256,
-                  "0 (dynamic chunks) or 64 / 128 / 256 threads per CTA of the tile-synchronous kernel");
+    TEFEM_REQUIRE(threads == 64 || threads == 128 || threads == 256, "threads per CTA must be 64, 128 or 256");
     g_asm_threads = threads;
     return TEFEM_OK;
 }

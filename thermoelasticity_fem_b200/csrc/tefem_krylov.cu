@@ -693,6 +693,20 @@ __global__ void __launch_bounds__(256) load_axpy_kernel(int64_t n, const int32_t
     if (c3 != 0.0) f[3] += wk * c3;
 }
 
+// same with the four amplitudes read from device memory (end-to-end path: the step's amplitudes arrive by an H2D copy)
+__global__ void __launch_bounds__(256) load_axpy_dev_kernel(int64_t n, const int32_t* __restrict__ node,
+                                                            const double* __restrict__ w, const double* __restrict__ coef,
+                                                            double* __restrict__ F) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double wk = w[k], c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3];
+    double* f = F + 4 * (int64_t)node[k];
+    if (c0 != 0.0) f[0] += wk * c0;
+    if (c1 != 0.0) f[1] += wk * c1;
+    if (c2 != 0.0) f[2] += wk * c2;
+    if (c3 != 0.0) f[3] += wk * c3;
+}
+
 }  // namespace tefem
 
 using namespace tefem;
@@ -1371,6 +1385,15 @@ extern "C" int tefem_load_axpy(int64_t n_entries, const int32_t* node, const dou
     if (n_entries == 0) return TEFEM_OK;
     load_axpy_kernel<<<(unsigned)ceil_div(n_entries, 256), 256, 0, as_stream(stream)>>>(n_entries, node, w, h_coef[0],
                                                                                          h_coef[1], h_coef[2], h_coef[3], F);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_load_axpy_dev(int64_t n_entries, const int32_t* node, const double* w, const double* d_coef, double* F,
+                                   void* stream) {
+    TEFEM_REQUIRE(node && w && d_coef && F, "null pointer");
+    if (n_entries == 0) return TEFEM_OK;
+    load_axpy_dev_kernel<<<(unsigned)ceil_div(n_entries, 256), 256, 0, as_stream(stream)>>>(n_entries, node, w, d_coef, F);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }

@@ -28,10 +28,8 @@
 #include "tefem_comm.h"
 #include "tefem_precond.h"
 
-#include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
-
-namespace cg = cooperative_groups;
 
 namespace tefem {
 
@@ -154,9 +152,31 @@ __global__ void __launch_bounds__(128) peer_coarse_start_kernel(const PeerCtx pc
 // i.e. latency bound at ~1/3 of the L2 bandwidth; 8 lanes per row give 7 independent trips on 220 k threads.  The sum
 // order is fixed (lane-strided partial sums, then the tree), so every rank computes bitwise the same coarse vectors.
 constexpr int COARSE_LANES = 8;
+
+// One 4x4 block (row-major) of a coarse operator as 16 floats: stored in single precision (transfer operators), or in
+// HALF precision (the level-1 operator A1^ = D1^-1 A1: unit diagonal blocks, off-diagonal entries of magnitude <~ 1, so
+// the 11-bit mantissa perturbs the preconditioner by ~5e-4 relative - measured: no change of the BiCGSTAB iteration
+// counts at 150^3, profiles/README.md - and halves the bytes of the six level-1 sweeps of an application: the 190^3
+// level then fits the L2 next to the vectors).
+__device__ __forceinline__ void load_block16(const float* __restrict__ sys, int64_t p, float4& r0, float4& r1, float4& r2, float4& r3) {
+    const float4* blk = reinterpret_cast<const float4*>(sys + 16 * p);
+    r0 = __ldg(blk); r1 = __ldg(blk + 1); r2 = __ldg(blk + 2); r3 = __ldg(blk + 3);
+}
+__device__ __forceinline__ void load_block16(const __half* __restrict__ sys, int64_t p, float4& r0, float4& r1, float4& r2, float4& r3) {
+    const uint4* blk = reinterpret_cast<const uint4*>(sys + 16 * p);
+    const uint4 lo = __ldg(blk), hi = __ldg(blk + 1);
+    const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
+    const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&lo.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&lo.w));
+    const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+    const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&hi.z)), b3 = __half22float2(*reinterpret_cast<const __half2*>(&hi.w));
+    r0 = make_float4(a0.x, a0.y, a1.x, a1.y); r1 = make_float4(a2.x, a2.y, a3.x, a3.y);
+    r2 = make_float4(b0.x, b0.y, b1.x, b1.y); r3 = make_float4(b2.x, b2.y, b3.x, b3.y);
+}
+
+template <typename VT>
 __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restrict__ rowptr,
                                                           const int32_t* __restrict__ colidx, int32_t n_rows,
-                                                          const float* __restrict__ sys, const double* __restrict__ x,
+                                                          const VT* __restrict__ sys, const double* __restrict__ x,
                                                           const double* __restrict__ b, const double* xin,
                                                           double c0, double c1, double* out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,8 +188,8 @@ __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restr
         const int32_t s = rowptr[i], t = rowptr[i + 1];
         for (int32_t p = s + l; p < t; p += COARSE_LANES) {
             const int32_t j = colidx[p];
-            const float4* blk = reinterpret_cast<const float4*>(sys + 16 * (int64_t)p);
-            const float4 r0 = __ldg(blk), r1 = __ldg(blk + 1), r2 = __ldg(blk + 2), r3 = __ldg(blk + 3);
+            float4 r0, r1, r2, r3;
+            load_block16(sys, (int64_t)p, r0, r1, r2, r3);
             const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j);
             const double2 u1 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j + 2);
             a0 += (double)r0.x * u0.x + (double)r0.y * u0.y + (double)r0.z * u1.x + (double)r0.w * u1.y;
@@ -209,191 +229,10 @@ __global__ void __launch_bounds__(128) dense_matvec_kernel(int32_t n, const floa
     if (threadIdx.x == 0) y[blockIdx.x] = a[0];
 }
 
-// ---- one application of the preconditioner as ONE persistent cooperative kernel ------------------------------------
-// The separate kernels above cost ~10 us each on the B200 whatever their size (12 dependent launches of 2 - 8 us
-// kernels: 0.12 ms per application, which does not shrink with the row partition - 25 % of an iteration at 8 GPUs).
-// Here the whole application - restriction, all-reduce over the ranks through peer memory, D1^-1 + first sweep, the
-// level-1 sweeps, the level-2 correction, the post-smoothing and the prolongation - runs in one cooperative launch
-// whose phases are separated by grid.sync().  Same arithmetic per row as the kernels above (the dense level-2 product
-// sums a row with one warp instead of one CTA: a fixed order again, identical on every rank).
-struct PcFused {
-    int32_t n_rows, n1, n2;
-    const int32_t *agg_ptr, *agg_nodes, *node_agg;
-    const float4* node_off;
-    double omega, omega_c;
-    int n_pre, n_post;
-    const int32_t *rowptr1, *colidx1;
-    const float* sys1;
-    const double* dinv1;
-    const int32_t *r2_rowptr, *r2_colidx, *p2_rowptr, *p2_colidx;
-    const float *r2_vals, *p2_vals, *inv2;
-    double *rc, *bc, *xc, *tc, *r2, *x2;
-    const double* r;
-    double* z;
-    int multi;                       // 1: restricted residual summed over the ranks (pc, agg_ranks)
-    const uint8_t* agg_ranks;
-};
-
-// coarse_spmv_kernel's row product for the whole grid: groups of COARSE_LANES lanes stride over the block rows with a
-// uniform trip count (every lane of a warp reaches the shuffles)
-__device__ __forceinline__ void coarse_spmv_dev(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                                int32_t n_rows, const float* __restrict__ sys, const double* x,
-                                                const double* b, const double* xin, double c0, double c1, double* out) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int32_t grp = (int32_t)(gid / COARSE_LANES), n_grp = (int32_t)(((int64_t)gridDim.x * blockDim.x) / COARSE_LANES);
-    const int l = (int)(gid % COARSE_LANES);
-    for (int32_t base = 0; base < n_rows; base += n_grp) {
-        const int32_t i = base + grp;
-        const bool live = i < n_rows;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        if (live) {
-            const int32_t s = rowptr[i], t = rowptr[i + 1];
-            for (int32_t p = s + l; p < t; p += COARSE_LANES) {
-                const int32_t j = colidx[p];
-                const float4* blk = reinterpret_cast<const float4*>(sys + 16 * (int64_t)p);
-                const float4 r0 = __ldg(blk), r1 = __ldg(blk + 1), r2 = __ldg(blk + 2), r3 = __ldg(blk + 3);
-                const double2 u0 = __ldcg(reinterpret_cast<const double2*>(x + 4 * (int64_t)j));
-                const double2 u1 = __ldcg(reinterpret_cast<const double2*>(x + 4 * (int64_t)j + 2));
-                a0 += (double)r0.x * u0.x + (double)r0.y * u0.y + (double)r0.z * u1.x + (double)r0.w * u1.y;
-                a1 += (double)r1.x * u0.x + (double)r1.y * u0.y + (double)r1.z * u1.x + (double)r1.w * u1.y;
-                a2 += (double)r2.x * u0.x + (double)r2.y * u0.y + (double)r2.z * u1.x + (double)r2.w * u1.y;
-                a3 += (double)r3.x * u0.x + (double)r3.y * u0.y + (double)r3.z * u1.x + (double)r3.w * u1.y;
-            }
-        }
-#pragma unroll
-        for (int off = COARSE_LANES / 2; off > 0; off >>= 1) {
-            a0 += __shfl_down_sync(0xffffffffu, a0, off, COARSE_LANES);
-            a1 += __shfl_down_sync(0xffffffffu, a1, off, COARSE_LANES);
-            a2 += __shfl_down_sync(0xffffffffu, a2, off, COARSE_LANES);
-            a3 += __shfl_down_sync(0xffffffffu, a3, off, COARSE_LANES);
-        }
-        const double s1 = __shfl_sync(0xffffffffu, a1, 0, COARSE_LANES);
-        const double s2 = __shfl_sync(0xffffffffu, a2, 0, COARSE_LANES);
-        const double s3 = __shfl_sync(0xffffffffu, a3, 0, COARSE_LANES);
-        const double s0 = __shfl_sync(0xffffffffu, a0, 0, COARSE_LANES);
-        if (live && l < 4) {
-            const double acc = l == 0 ? s0 : (l == 1 ? s1 : (l == 2 ? s2 : s3));
-            const int64_t k = 4 * (int64_t)i + l;
-            out[k] = (c0 != 0.0 ? c0 * __ldcg(xin + k) : 0.0) + c1 * ((b ? __ldcg(b + k) : 0.0) - acc);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 2) precond_fused_kernel(const PcFused a, const PeerCtx pc) {
-    cg::grid_group grid = cg::this_grid();
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_thr = (int64_t)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = tid >> 5, n_warp = n_thr >> 5;
-    // ---- restriction rc = P1^T r (one warp per aggregate; multi-GPU: into this rank's peer buffer)
-    double* rc_out = a.multi ? peer_big(pc, pc.rank) : a.rc;
-    for (int64_t I = warp; I < a.n1; I += n_warp) {
-        const int32_t s = a.agg_ptr[I], t = a.agg_ptr[I + 1];
-        double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int32_t k = s + lane; k < t; k += 32) {
-            const int32_t i = a.agg_nodes[k];
-            const double* rv = a.r + 4 * (int64_t)i;
-            const float4 d = a.node_off[i];
-            const double v0 = rv[0], v1 = rv[1], v2 = rv[2];
-            v[0] += v0; v[1] += v1; v[2] += v2; v[3] += rv[3];
-            v[4] += (double)d.y * v2 - (double)d.z * v1;
-            v[5] += (double)d.z * v0 - (double)d.x * v2;
-            v[6] += (double)d.x * v1 - (double)d.y * v0;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-            for (int k = 0; k < 7; ++k) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
-        if (lane == 0) {
-            double* o = rc_out + 8 * I;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) o[k] = v[k];
-            o[7] = 0.0;
-        }
-    }
-    grid.sync();
-    if (a.multi) {   // all-reduce over the ranks: flags, then masked reads of the contributing ranks' partial sums
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            peer_signal(pc, threadIdx.x);
-        }
-        peer_wait(pc, threadIdx.x);
-        __syncthreads();
-    }
-    // ---- bc = D1^-1 rc ; xc = omega_c bc (first damped-Jacobi sweep from 0); one thread per aggregate
-    for (int64_t I = tid; I < a.n1; I += n_thr) {
-        double s8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (a.multi) {
-            const unsigned mask = a.agg_ranks ? (unsigned)a.agg_ranks[I] : 0xffu;
-            for (int r = 0; r < pc.world; ++r) {
-                if (!((mask >> r) & 1u)) continue;
-                const double* src = peer_big(pc, r) + 8 * I;
-                double v[8];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) ld_volatile_v2(src + 2 * q, v[2 * q], v[2 * q + 1]);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) s8[q] += v[q];
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s8[q] = __ldcg(a.rc + 8 * I + q);
-        }
-        const double* D = a.dinv1 + 64 * I;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            double b = 0.0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) b += D[8 * k + c] * s8[c];
-            a.bc[8 * I + k] = b;
-            a.xc[8 * I + k] = a.omega_c * b;
-        }
-    }
-    grid.sync();
-    // ---- level-1 V-cycle (tefem_precond_apply_stream has the same sequence as separate launches)
-    const int32_t np1 = 2 * a.n1, np2 = 2 * a.n2;
-    double *cur = a.xc, *alt = a.rc;
-    for (int k = 1; k < a.n_pre; ++k) {
-        coarse_spmv_dev(a.rowptr1, a.colidx1, np1, a.sys1, cur, a.bc, cur, 1.0, a.omega_c, alt);
-        grid.sync();
-        double* t = cur; cur = alt; alt = t;
-    }
-    coarse_spmv_dev(a.rowptr1, a.colidx1, np1, a.sys1, cur, a.bc, nullptr, 0.0, 1.0, a.tc);              // tc = bc - A1^ x
-    grid.sync();
-    coarse_spmv_dev(a.r2_rowptr, a.r2_colidx, np2, a.r2_vals, a.tc, nullptr, nullptr, 0.0, -1.0, a.r2);  // r2 = P2^T tc
-    grid.sync();
-    {   // x2 = A2^-1 r2: one warp per row of the dense fp32 inverse
-        const int32_t n = 4 * np2;
-        for (int64_t row = warp; row < n; row += n_warp) {
-            const float* m = a.inv2 + row * n;
-            double acc = 0.0;
-            for (int32_t k = lane; k < n; k += 32) acc += (double)__ldg(m + k) * __ldcg(a.r2 + k);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-            if (lane == 0) a.x2[row] = acc;
-        }
-    }
-    grid.sync();
-    coarse_spmv_dev(a.p2_rowptr, a.p2_colidx, np1, a.p2_vals, a.x2, nullptr, cur, 1.0, -1.0, cur);        // x += P2 x2
-    grid.sync();
-    for (int k = 0; k < a.n_post; ++k) {
-        coarse_spmv_dev(a.rowptr1, a.colidx1, np1, a.sys1, cur, a.bc, cur, 1.0, a.omega_c, alt);
-        grid.sync();
-        double* t = cur; cur = alt; alt = t;
-    }
-    // ---- prolongation z_i = omega r_i + (t_I + w_I x d_i, theta_I)
-    for (int64_t i = tid; i < a.n_rows; i += n_thr) {
-        double r0, r1, r2, r3;
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(a.r + 4 * i));
-        const double* c = cur + 8 * (int64_t)a.node_agg[i];
-        const double2 c01 = __ldcg(reinterpret_cast<const double2*>(c)), c23 = __ldcg(reinterpret_cast<const double2*>(c + 2));
-        const double2 w01 = __ldcg(reinterpret_cast<const double2*>(c + 4)), w23 = __ldcg(reinterpret_cast<const double2*>(c + 6));
-        const float4 d = a.node_off[i];
-        r0 = a.omega * r0 + c01.x + (w01.y * (double)d.z - w23.x * (double)d.y);
-        r1 = a.omega * r1 + c01.y + (w23.x * (double)d.x - w01.x * (double)d.z);
-        r2 = a.omega * r2 + c23.x + (w01.x * (double)d.y - w01.y * (double)d.x);
-        r3 = a.omega * r3 + c23.y;
-        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a.z + 4 * i), "d"(r0), "d"(r1), "d"(r2), "d"(r3) : "memory");
-    }
-}
+// (A fused form - restriction, all-reduce, V-cycle and prolongation in ONE persistent cooperative kernel with grid.sync()
+// between the phases - was built and measured in round 2: 0.32 ms per application against 0.19 ms for the separate
+// launches at 150^3 on one GPU, 0.26 against 0.15 ms on two: a grid-wide barrier costs as much as a kernel boundary here
+// and the fine-level passes lose their occupancy.  Removed; numbers in profiles/README.md.)
 
 }  // namespace tefem
 
@@ -414,8 +253,7 @@ struct tefem_precond {
     double *rc = nullptr, *bc = nullptr, *xc = nullptr, *tc = nullptr, *r2 = nullptr, *x2 = nullptr;
     tefem_comm* comm = nullptr;
     const uint8_t* agg_ranks = nullptr;          // multi-GPU: which ranks contribute to an aggregate's restricted residual
-    bool fused = true;                           // one cooperative kernel per application (TEFEM_PRECOND_FUSED=0: separate launches)
-    int fused_grid = 0;
+    const __half* sys1h = nullptr;               // level-1 operator in half precision (tefem_precond_set_level1_half)
     // TEFEM_PROFILE_PRECOND=1 (diagnostics, stderr at destroy): device time of the three parts of an application -
     // restriction + all-reduce over the ranks + first sweep (includes waiting for the slowest rank), the level-1 / level-2
     // cycle (replicated work), the prolongation.  Synchronises the stream after every application: not for timed runs.
@@ -460,26 +298,21 @@ extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t
     p->rc = w; w += a1; p->bc = w; w += a1; p->xc = w; w += a1; p->tc = w; w += a1;
     p->r2 = w; w += a2; p->x2 = w;
     p->comm = reinterpret_cast<tefem_comm*>(comm);
-    const char* fe = getenv("TEFEM_PRECOND_FUSED");      // measurement switch, read once per preconditioner
-    if (fe && fe[0] == '0') p->fused = false;
-    if (p->fused) {
-        int dev = 0, sms = 0, per_sm = 0, coop_ok = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, precond_fused_kernel, 256, 0) != cudaSuccess || !coop_ok || per_sm < 1)
-            p->fused = false;
-        else
-            p->fused_grid = sms * (per_sm > 2 ? 2 : per_sm);
-    }
     const char* pe = getenv("TEFEM_PROFILE_PRECOND");
     if (pe && pe[0] == '1') {
-        p->fused = false;                        // the per-part timers need the separate launches
         p->profile = true;
         for (int k = 0; k < 4; ++k) {
             if (cudaEventCreate(&p->ev[k]) != cudaSuccess) { p->profile = false; break; }
         }
     }
     *out = p;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_precond_set_level1_half(tefem_precond* p, const void* sys1_half) {
+    TEFEM_REQUIRE(p, "null preconditioner");
+    TEFEM_REQUIRE((((uintptr_t)sys1_half) & 31) == 0, "the half-precision blocks must be 32-byte aligned");
+    p->sys1h = reinterpret_cast<const __half*>(sys1_half);
     return TEFEM_OK;
 }
 
@@ -504,28 +337,6 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
 
 int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cudaStream_t st) {
     TEFEM_REQUIRE(p && r && z, "null pointer");
-    if (p->fused) {
-        PcFused a;
-        a.n_rows = p->n_rows; a.n1 = p->n1; a.n2 = p->n2;
-        a.agg_ptr = p->agg_ptr; a.agg_nodes = p->agg_nodes; a.node_agg = p->node_agg; a.node_off = p->node_off;
-        a.omega = p->omega; a.omega_c = p->omega_c; a.n_pre = p->n_pre; a.n_post = p->n_post;
-        a.rowptr1 = p->rowptr1; a.colidx1 = p->colidx1; a.sys1 = p->sys1; a.dinv1 = p->dinv1;
-        a.r2_rowptr = p->r2_rowptr; a.r2_colidx = p->r2_colidx; a.p2_rowptr = p->p2_rowptr; a.p2_colidx = p->p2_colidx;
-        a.r2_vals = p->r2_vals; a.p2_vals = p->p2_vals; a.inv2 = p->inv2;
-        a.rc = p->rc; a.bc = p->bc; a.xc = p->xc; a.tc = p->tc; a.r2 = p->r2; a.x2 = p->x2;
-        a.r = r; a.z = z;
-        a.multi = p->comm ? 1 : 0; a.agg_ranks = p->agg_ranks;
-        PeerCtx pc;
-        if (p->comm) {
-            TEFEM_REQUIRE(tefem_comm_has_peer(p->comm) && tefem_comm_peer_cap(p->comm) >= 8 * (int64_t)p->n1,
-                          "the peer-memory region must hold 8 * n_agg doubles (tefem_comm_shm_alloc)");
-            pc = tefem_comm_peer_ctx(p->comm, PEER_CH_COARSE);
-        }
-        void* kargs[] = {&a, &pc};
-        TEFEM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)precond_fused_kernel, dim3((unsigned)p->fused_grid), dim3(256), kargs, 0, st));
-        count_launch();
-        return TEFEM_OK;
-    }
     const int64_t n1 = 8 * (int64_t)p->n1;                    // scalar size of level 1
     const int32_t np1 = 2 * p->n1, np2 = 2 * p->n2;           // pseudo nodes (4-DOF block rows) of levels 1 and 2
     const unsigned g1 = (unsigned)ceil_div(n1, 256);                                           // one thread per scalar of level 1
@@ -552,28 +363,35 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
         TEFEM_LAUNCH_CHECK();
     }
     if (p->profile) cudaEventRecord(p->ev[1], st);
+    // the level-1 operator: half precision when attached, else single
+#define LEVEL1_SPMV(X, B, XIN, C0, C1, OUT)                                                                                         \
+    do {                                                                                                                            \
+        if (p->sys1h) coarse_spmv_kernel<__half><<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1h, X, B, XIN, C0, C1, OUT); \
+        else coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, X, B, XIN, C0, C1, OUT);           \
+    } while (0)
     // level 1 V-cycle on A1^ = D1^-1 A1 (bc = D1^-1 rc, x = wc bc so far = the first damped-Jacobi sweep from 0):
     // further pre-smoothing sweeps, correction from level 2, post-smoothing.  A sweep reads all of x, so it writes
     // into the other buffer: x' = x + wc (bc - A1^ x).
     double *cur = p->xc, *alt = p->rc;
     for (int k = 1; k < p->n_pre; ++k) {
-        coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
+        LEVEL1_SPMV(cur, p->bc, cur, 1.0, p->omega_c, alt);
         TEFEM_LAUNCH_CHECK();
         double* t = cur; cur = alt; alt = t;
     }
-    coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, nullptr, 0.0, 1.0, p->tc);
+    LEVEL1_SPMV(cur, p->bc, nullptr, 0.0, 1.0, p->tc);
     TEFEM_LAUNCH_CHECK();                                                                       // tc = bc - A1^ x
-    coarse_spmv_kernel<<<gs2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, p->r2);
+    coarse_spmv_kernel<float><<<gs2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, p->r2);
     TEFEM_LAUNCH_CHECK();                                                                       // r2 = P2^T tc
     dense_matvec_kernel<<<(unsigned)(4 * np2), 128, 0, st>>>(4 * np2, p->inv2, p->r2, p->x2);
     TEFEM_LAUNCH_CHECK();                                                                       // x2 = A2^-1 r2
-    coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, cur);
+    coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, cur);
     TEFEM_LAUNCH_CHECK();                                                                       // x += P2 x2
     for (int k = 0; k < p->n_post; ++k) {
-        coarse_spmv_kernel<<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, cur, p->bc, cur, 1.0, p->omega_c, alt);
+        LEVEL1_SPMV(cur, p->bc, cur, 1.0, p->omega_c, alt);
         TEFEM_LAUNCH_CHECK();
         double* t = cur; cur = alt; alt = t;
     }
+#undef LEVEL1_SPMV
     if (p->profile) cudaEventRecord(p->ev[2], st);
     // level 1 -> 0
     if (p->n_rows > 0) {

@@ -46,9 +46,7 @@ class DeviceMesh:
         self.cta_xyz = self.coords[S.cta_nodes.long()].contiguous()
         self._h_max = S.h_max()
         self.bad_elem = torch.full((2,), _lib.INT32_MAX, dtype=torch.int32, device=dev)
-        # kernel form of K1: 256 (default) | 128 | 64 = threads per CTA of the tile-synchronous kernel (pair with tiles of
-        # 2 x threads blocks); 0 = dynamic chunks, one 512-thread CTA per SM (measured slower, profiles/README.md)
-        self.asm_threads = 256
+        self.asm_threads = 256          # threads per CTA of K1 (64 | 128 | 256: measurement knob, pair with tiles of 2 x threads blocks)
 
     # ---- K1 -------------------------------------------------------------------------------------
     def alloc_planes(self, which, alpha_M=0., alpha_K=0.):
@@ -265,6 +263,10 @@ def newmark_correct(lib, x, v, a, a_new, dt, gamma, beta, dir_mask):
 
 
 def load_axpy(lib, node, w, coef, F):
+    """F[4 node + c] += w * coef[c]; coef: 4 host numbers (kernel arguments) or a device tensor of 4 doubles."""
+    if hasattr(coef, "data_ptr"):
+        _lib.check(lib.tefem_load_axpy_dev(node.numel(), _lib.ptr(node), _lib.ptr(w), _lib.ptr(coef), _lib.ptr(F), _lib.stream_ptr()))
+        return
     c = (ctypes.c_double * 4)(*[float(v) for v in coef])
     _lib.check(lib.tefem_load_axpy(node.numel(), _lib.ptr(node), _lib.ptr(w), c, _lib.ptr(F), _lib.stream_ptr()))
 

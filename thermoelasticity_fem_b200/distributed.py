@@ -177,7 +177,7 @@ class DistributedTransient:
 
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
                  alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=16,
-                 comm=None, precond="multilevel", halo="peer", floor_factor=1.0):
+                 comm=None, precond="multilevel", halo="peer", floor_factor=1.0, mat_table=None):
         """halo: 'peer' (default) - boundary values are stored straight into the neighbours' vectors over NVLink and the
         SpMV waits for flags; 'nccl' - packed ncclSend / ncclRecv overlapped with the interior rows (measured alternative)."""
         assert halo in ("peer", "nccl")
@@ -189,8 +189,9 @@ class DistributedTransient:
         self.t_end, self.n_t = t_end, n_t
         self.dt = t_end / (n_t - 1)
         self.rtol, self.max_iter, self.check_every, self.precond_kind = rtol, max_iter, check_every, precond
-        table = np.array([m.table_row() for m in materials])
+        table = np.asarray(mat_table) if mat_table is not None else np.array([m.table_row() for m in materials])
         self.dm = DeviceMesh(coords_local, lp.conn, mat_id_local, table, n_rows=lp.n_own)
+        self.initial_state = None        # optional (x0, v0): local [4 n_local] arrays, free DOFs only are used
         self.n_halo = lp.n_halo
         self.lib = self.dm.lib
         dev = self.dm.device
@@ -221,12 +222,18 @@ class DistributedTransient:
                                    torch.from_numpy(np.asarray(w)[own]).to(dev), coef_fn))
         self.solve_info = []
 
-    def prepare(self):
+    def prepare(self, steady=False):
+        """Assembly, Dirichlet elimination, block-Jacobi scaling, solver / preconditioner / halo set-up.
+        steady=False: the Newmark operator M + gamma dt D + beta dt^2 K (solvers.py:159-161); True: K alone (solvers.py:26)."""
         lp, dm, dev = self.lp, self.dm, self.dm.device
         dt = self.dt
-        self.planes = dm.assemble("MKD", self.alpha_M, self.alpha_K)
         d_layout = layout.n_planes(layout.plane_map_D(self.alpha_M, self.alpha_K))
-        self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
+        if steady:
+            self.planes = dm.assemble("K", self.alpha_M, self.alpha_K)
+            self.sys = dm.form_system(self.planes, 0.0, 0.0, 1.0, d_layout, self.dir_mask)
+        else:
+            self.planes = dm.assemble("MKD", self.alpha_M, self.alpha_K)
+            self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
         self.dinv = dm.block_jacobi_scale(self.sys)
         if self.comm is not None and self.halo == "peer":
             self.comm.setup_vectors(lp.n_local)          # before the solver: it keeps its SpMV inputs in the slots
@@ -254,6 +261,10 @@ class DistributedTransient:
         n_loc = 4 * lp.n_local
         z = lambda: torch.zeros(n_loc, dtype=torch.float64, device=dev)
         self._x, self._v, self._a, self._a_new, self._w1, self._w2, self._rhs, self._b = (z() for _ in range(8))
+        if self.initial_state is not None:      # solvers.py:155-157: only the free DOFs are advanced
+            free = ~self._mask_host
+            self._x.copy_(torch.from_numpy(np.asarray(self.initial_state[0]) * free))
+            self._v.copy_(torch.from_numpy(np.asarray(self.initial_state[1]) * free))
         self._mapD = layout.plane_map_D(self.alpha_M, self.alpha_K)
         self._mapK = layout.plane_map_K()
         self._guess = GuessExtrapolator(self.lib, self._x, order=0)
@@ -262,12 +273,19 @@ class DistributedTransient:
             self._lift = z()
             dm.planes_spmv(self.planes["K"], self._mapK, self.g_lift, self._lift)
 
-    def step(self, i):
+    def n_load_terms(self):
+        return len(self.loads)
+
+    def load_coefficients(self, i):
+        return np.array([coef_fn(i) for _, _, coef_fn in self.loads], dtype=np.float64).reshape(-1, 4)
+
+    def step(self, i, coef_dev=None):
+        """coef_dev (optional, device [n_terms, 4]): this step's load amplitudes already on the device (end-to-end path)."""
         dm, lib = self.dm, self.lib
         rhs = self._rhs
         rhs.zero_()
-        for node, w, coef_fn in self.loads:
-            load_axpy(lib, node, w, coef_fn(i), rhs)
+        for k, (node, w, coef_fn) in enumerate(self.loads):
+            load_axpy(lib, node, w, coef_fn(i) if coef_dev is None else coef_dev[k], rhs)
         if self._lift is not None:
             rhs -= self._lift
         newmark_predict(lib, self._x, self._v, self._a, self.dt, self.gamma, self.beta, self.dir_mask, self._w1, self._w2)
@@ -281,6 +299,23 @@ class DistributedTransient:
         # x, v, a are advanced on the halo nodes as well (same arithmetic as on their owner): they need a_new there
         _lib.check(lib.tefem_solver_halo_exchange(self.krylov.handle, _lib.ptr(self._a_new), _lib.stream_ptr()))
         newmark_correct(lib, self._x, self._v, self._a, self._a_new, self.dt, self.gamma, self.beta, self.dir_mask)
+        self.solve_info.append(info)
+        return info
+
+    def solve_steady(self, idx_t=None):
+        """K_ff x_f = F_f - K_fd x_d on the partitioned mesh (reference solvers.py:19-49); call prepare(steady=True) first.
+        Returns the solver info; the solution (prescribed values included) is owned_state()[0]."""
+        dm, lib = self.dm, self.lib
+        rhs = self._rhs
+        rhs.zero_()
+        for node, w, coef_fn in self.loads:
+            load_axpy(lib, node, w, coef_fn(idx_t), rhs)
+        if self._lift is not None:
+            rhs -= self._lift
+        dm.block_jacobi_apply(self.dinv, rhs, self._b, self.dir_mask)
+        self._x.zero_()
+        info = self.krylov.bicgstab(self.sys, self._b, self._x, self.rtol, self.max_iter, self.check_every, self.floor_factor)
+        self._x.masked_fill_(self.dir_mask.bool(), 0.0)
         self.solve_info.append(info)
         return info
 

@@ -61,6 +61,7 @@ class Model:
         self._export = {}            # name -> cached scipy export
         self._override = {}          # attributes explicitly assigned by the user
         self._reduced = set()
+        self._cleared = set()        # operators whose full-matrix view was cleared while the reduced view stays alive
         self._F = None               # device [4N]
         self._rhs = None             # device [4N]: (F - lift) on free DOFs, 0 on constrained DOFs
         self._bc_dev = None          # (dir_mask uint8 [4N], g_fill [4N], g_lift [4N]) on the device, uploaded lazily
@@ -143,6 +144,7 @@ class Model:
         dm = self.mesh.device_mesh()
         for nm in ops:
             self._planes.pop(nm, None)
+            self._cleared.discard(nm)
             self._export.pop("mat_" + nm, None)
             self._override.pop("mat_" + nm, None)
         out = dm.assemble(ops, self.alpha_M, self.alpha_K)
@@ -332,7 +334,7 @@ class Model:
         key = "mat_" + nm
         if key in self._override:
             return self._override[key]
-        if nm not in self._planes:
+        if nm not in self._planes or nm in self._cleared:
             return None
         if key not in self._export:
             self._export[key] = self.mesh.device_mesh().export_csc(self._planes[nm], self.plane_map(nm), drop_zeros=True)
@@ -342,10 +344,16 @@ class Model:
         key = "mat_" + nm
         self._export.pop(key, None)
         if value is None:
-            self._planes.pop(nm, None)
+            # reference: clear_full_matrices() after apply_dirichlet_matrices() frees the full matrices but the reduced
+            # ones stay usable (model.py:288-302).  Here the planes back BOTH views: once reduced, they are kept (only the
+            # full-matrix view reads None); otherwise they are freed.
             self._override.pop(key, None)
-            if nm == "K":
-                self._lift = None
+            if nm in self._reduced:
+                self._cleared.add(nm)
+            else:
+                self._planes.pop(nm, None)
+                if nm == "K":
+                    self._lift = None
         else:
             self._override[key] = value
 
@@ -402,6 +410,10 @@ class Model:
             raise RuntimeError("create_free_dofs_lists() must be called first")            # model.py:342,354
         prob = FieldEigenProblem(self, field, **kw)
         lam, Phi, info = prob.smallest(int(n_q), tol=tol)
+        if not info.get("converged", False):
+            # scipy's eigs raises ArpackNoConvergence in the reference (model.py:346-347): do not hand an unconverged
+            # basis to the reduced-order model silently
+            raise RuntimeError(f"reduced-order basis for '{field}' did not converge to tol={tol:g}: {info}")
         return lam, Phi, info
 
     def compute_ROB_u(self, n_q_u, tol=1e-9, **kw):

@@ -244,7 +244,9 @@ class TwoLevelPreconditioner:
     """Owns the device arrays of one preconditioner and its C handle (attach with KrylovSolver.set_precond)."""
 
     def __init__(self, dm, sys, comm=None, factor1=8.0, factor2=3.0, omega=1.0, omega_c=0.7, n_pre=3, n_post=3,
-                 dense_limit=200):
+                 dense_limit=200, level1_dtype="fp16"):
+        """level1_dtype: storage of the scaled level-1 operator for the sweeps - 'fp16' (default; falls back to 'fp32' when
+        an entry would overflow half precision) or 'fp32'.  Preconditioner data only."""
         import os
         import scipy.sparse as sp
         if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c[,n_pre,n_post]"
@@ -268,6 +270,14 @@ class TwoLevelPreconditioner:
         rp, ci, vals = pseudo_node_csr(rowptr1, col1, scaled)
         self.rowptr1, self.colidx1 = rp.to(i32), ci.to(i32)
         self.sys1 = vals.to(torch.float32).contiguous()
+        if level1_dtype not in ("fp16", "fp32"):
+            raise ValueError("level1_dtype must be 'fp16' or 'fp32'")
+        self.sys1_half = None
+        if level1_dtype == "fp16" and float(self.sys1.abs().max().item()) < 6.0e4:
+            self.sys1_half = self.sys1.to(torch.float16).contiguous()
+            # level 2 is built from (and consistent with) the operator the sweeps really use
+            self.sys1 = self.sys1_half.to(torch.float32)
+        self.level1_dtype = "fp16" if self.sys1_half is not None else "fp32"
         self.dinv1 = Dinv.reshape(n1, 64).contiguous()
         self.node_off = torch.zeros((n_own, 4), dtype=torch.float32, device=dev)
         self.node_off[:, :3] = A["off"][:n_own].to(torch.float32)
@@ -316,6 +326,8 @@ class TwoLevelPreconditioner:
             p(self.inv2), p(self.work), comm.handle if comm is not None else None))
         if self.agg_ranks is not None:
             _lib.check(lib.tefem_precond_set_agg_ranks(self.handle, p(self.agg_ranks)))
+        if self.sys1_half is not None:
+            _lib.check(lib.tefem_precond_set_level1_half(self.handle, p(self.sys1_half)))
 
     def apply(self, r, z):
         _lib.check(self.lib.tefem_precond_apply(self.handle, _lib.ptr(r), _lib.ptr(z), _lib.stream_ptr()))

@@ -35,11 +35,21 @@ def animate_U_T(*args, **kwargs):
     raise NotImplementedError("animation is outside the B200 hot path (reference plots.py:26-75)")
 
 
-def plot_U_vs_t(*args, **kwargs):
+def plot_dofU_vs_t(*args, **kwargs):
     _need()
-    raise NotImplementedError("outside the B200 hot path (reference plots.py)")
+    raise NotImplementedError("outside the B200 hot path (reference plots.py:77-89)")
 
 
-plot_T_vs_t = plot_U_vs_t
-plot_U_vs_t_random = plot_U_vs_t
-plot_T_vs_t_random = plot_U_vs_t
+def plot_nodeT_vs_t(*args, **kwargs):
+    _need()
+    raise NotImplementedError("outside the B200 hot path (reference plots.py:91-103)")
+
+
+def plot_dofU_vs_t_random(*args, **kwargs):
+    _need()
+    raise NotImplementedError("outside the B200 hot path (reference plots.py:105-136)")
+
+
+def plot_nodeT_vs_t_random(*args, **kwargs):
+    _need()
+    raise NotImplementedError("outside the B200 hot path (reference plots.py:138-169)")

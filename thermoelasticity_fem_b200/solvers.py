@@ -124,10 +124,14 @@ class LinearSteadyState:
       'auto'    - 'staged' below MULTILEVEL_MIN_NODES nodes (where block-Jacobi is the preconditioner anyway), 'coupled'
                   above (the coarse correction needs 20 x fewer iterations there)."""
 
-    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="auto", solver="auto", floor_factor=1.0):
+    def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="auto", solver="auto", floor_factor=1.0,
+                 comm=None):
+        """comm: None (one GPU) | 'auto' | distributed.Comm - row-partitioned solve on the GPUs of the torch.distributed job
+        (dist_api.py; the coupled BiCGSTAB path); every rank receives the full X, U, T."""
         if solver not in ("auto", "staged", "coupled"):
             raise ValueError("solver must be 'auto', 'staged' or 'coupled'")
         self.model = model
+        self.comm = comm
         self.rtol, self.max_iter, self.check_every, self.precond = rtol, max_iter, check_every, precond
         self.solver, self.floor_factor = solver, floor_factor
         self.X = None
@@ -137,7 +141,29 @@ class LinearSteadyState:
         self.solve_info = None
         self.timings = {}
 
+    def _solve_distributed(self):
+        from . import dist_api
+        m = self.model
+        t0 = time.perf_counter()
+        comm = dist_api.make_comm(self.comm)
+        m.create_free_dofs_lists()
+        zeros = np.zeros(m.mesh.n_dofs)
+        pm, ds = dist_api.distributed_transient(m, zeros, zeros, 1.0, 2, 0.5, 0.25, comm, self.rtol, self.max_iter,
+                                                self.check_every, self.precond, self.floor_factor, MULTILEVEL_MIN_NODES)
+        ds.prepare(steady=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        self.solve_info = ds.solve_steady()
+        self.X = pm.gather(ds.owned_state()[0])
+        t2 = time.perf_counter()
+        self.U, theta = _deinterleave(self.X, m.mesh.n_nodes)
+        self.T = theta + m.mesh.reference_temperature()
+        self.timings = dict(assemble_s=t1 - t0, solve_s=t2 - t1, post_s=time.perf_counter() - t2)
+        self._distributed = (pm, ds)
+
     def solve(self):
+        if self.comm is not None:
+            return self._solve_distributed()
         m = self.model
         t0 = time.perf_counter()
         m.create_free_dofs_lists()
@@ -208,7 +234,7 @@ class LinearTransient:
                  t_end, n_t,
                  gamma=0.5, beta=0.25,
                  rtol=1e-10, max_iter=50000, check_every=32, history='full', warm_start=True, guess_order=0,
-                 on_step=None, progress=True, precond="auto", floor_factor=1.0):
+                 on_step=None, progress=True, precond="auto", floor_factor=1.0, comm=None):
         self.model = model
         self.gamma = gamma
         self.beta = beta
@@ -226,6 +252,9 @@ class LinearTransient:
         self.history, self.warm_start, self.on_step, self.progress = history, warm_start, on_step, progress
         self.precond = precond
         self.floor_factor = floor_factor
+        # comm: None (one GPU) | 'auto' | distributed.Comm - row-partitioned solve on the GPUs of the torch.distributed
+        # job (dist_api.py); every rank receives the kept histories
+        self.comm = comm
         # initial guess of each solve: 0 (warm_start=False) or the previous accelerations extrapolated in time
         # with a polynomial of degree guess_order (0 = previous acceleration, 1 = linear, 2 = quadratic).
         # Measured on the B200 (sandwich mesh, 100^3 and 190^3 boxes): the iteration count of BiCGSTAB, with and without
@@ -290,13 +319,22 @@ class LinearTransient:
         self._mapK = layout.plane_map_K()
         self._lib = _lib.load()
 
-    def step(self, i):
-        """One time step (solvers.py:164-186) entirely on the device."""
+    def n_load_terms(self):
+        return len(self.model.load_terms(idx_t=1))
+
+    def load_coefficients(self, i):
+        """[n_terms, 4] amplitudes of the load terms at step i (host): what an end-to-end caller copies to the device."""
+        return np.array([coef for _, _, coef in self.model.load_terms(idx_t=i)], dtype=np.float64).reshape(-1, 4)
+
+    def step(self, i, coef_dev=None):
+        """One time step (solvers.py:164-186) entirely on the device.  coef_dev (optional, device [n_terms, 4]): the load
+        amplitudes of this step already copied to the device (end-to-end path); default: taken from the model's host arrays
+        and passed as kernel arguments."""
         m, dm = self.model, self._ss.dm
         rhs = self._rhs
         rhs.zero_()
-        for node, w, coef in m.load_terms(idx_t=i):                        # F(i), model.py:120-286
-            load_axpy(self._lib, node, w, coef, rhs)
+        for k, (node, w, coef) in enumerate(m.load_terms(idx_t=i)):        # F(i), model.py:120-286
+            load_axpy(self._lib, node, w, coef if coef_dev is None else coef_dev[k], rhs)
         if self._lift is not None:                                         # F_f -= K_fd x_d, model.py:326-339
             rhs -= self._lift
         newmark_predict(self._lib, self._x, self._v, self._a, self.dt, self.gamma, self.beta, m._dir_mask,
@@ -312,7 +350,53 @@ class LinearTransient:
         newmark_correct(self._lib, self._x, self._v, self._a, self._a_new, self.dt, self.gamma, self.beta, m._dir_mask)
         return info
 
+    def _solve_distributed(self):
+        from . import dist_api
+        m = self.model
+        t0 = time.perf_counter()
+        comm = dist_api.make_comm(self.comm)
+        m.create_free_dofs_lists()
+        n, n_t, n_nodes = m.mesh.n_dofs, self.n_t, m.mesh.n_nodes
+
+        def interleave(u3, th):
+            X = np.zeros(n)
+            X[::4], X[1::4], X[2::4], X[3::4] = np.asarray(u3)[::3], np.asarray(u3)[1::3], np.asarray(u3)[2::3], th
+            return X
+
+        x0, v0 = interleave(self.initial_U, self.initial_theta), interleave(self.initial_Udot, self.initial_thetadot)
+        pm, ds = dist_api.distributed_transient(m, x0, v0, self.t_end, n_t, self.gamma, self.beta, comm, self.rtol,
+                                                self.max_iter, self.check_every, self.precond, self.floor_factor,
+                                                MULTILEVEL_MIN_NODES)
+        ds.prepare()
+        keep_every = 1 if self.history == 'full' else (None if self.history == 'last' else int(self.history))
+        cols = list(range(0, n_t, keep_every)) if keep_every is not None else [n_t - 1]
+        col_of = {s_: k for k, s_ in enumerate(cols)}
+        self.kept_steps = np.array(cols)
+        self.X, self.Xdot, self.Xdotdot = (np.zeros((n, len(cols))) for _ in range(3))
+        if 0 in col_of:
+            self.X[:, 0], self.Xdot[:, 0] = x0, v0
+            self.X[m._mask_host, 0] = m._g_fill_host[m._mask_host]
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        it = range(1, n_t)
+        for i in (_tqdm(it) if (self.progress and comm.rank == 0) else it):
+            self.solve_info.append(ds.step(i))
+            if i in col_of:
+                k = col_of[i]
+                xo, vo, ao = ds.owned_state()
+                self.X[:, k], self.Xdot[:, k], self.Xdotdot[:, k] = pm.gather(xo), pm.gather(vo), pm.gather(ao)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        self.U, theta = _deinterleave(self.X, n_nodes)
+        self.Udot, self.Tdot = _deinterleave(self.Xdot, n_nodes)
+        self.Udotdot, self.Tdotdot = _deinterleave(self.Xdotdot, n_nodes)
+        self.T = theta + m.mesh.reference_temperature()[:, None]
+        self.timings = dict(prepare_s=t1 - t0, loop_s=t2 - t1, steps=n_t - 1, post_s=time.perf_counter() - t2)
+        self._distributed = (pm, ds)
+
     def solve(self):
+        if self.comm is not None:
+            return self._solve_distributed()
         m = self.model
         t0 = time.perf_counter()
         self.prepare()

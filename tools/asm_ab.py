@@ -3,8 +3,7 @@ Checks that the planes are BITWISE identical (same chunks => same summation orde
 usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first[,bank_opt]" ...]   (first variant = reference;
 bank_opt = 1: bank-aware numbering of the staged elements, symbolic.optimize_banks; 2 / 3: optimised for the kernels with D /
 without D only)
-Kernel form (tool-level switch TEFEM_ASM_THREADS -> DeviceMesh.asm_threads): 256 (default) | 128 | 64 = threads per CTA of the tile-synchronous
-kernel, 0 = dynamic chunks (pair with items = 2 x threads); build variants: TEFEM_LIB=/path/to/lib.so."""
+Kernel form (tool-level switch TEFEM_ASM_THREADS -> DeviceMesh.asm_threads): 256 (default) | 128 | 64 = threads per CTA (pair with items = 2 x threads); build variants: TEFEM_LIB=/path/to/lib.so."""
 import os
 import sys
 import time

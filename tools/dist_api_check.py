@@ -1,0 +1,118 @@
+"""Multi-GPU parity through the PUBLIC API (run under torchrun on >= 2 GPUs): LinearTransient(..., comm='auto') and
+LinearSteadyState(..., comm='auto') against the single-GPU solve of the same Model, on
+  (1) data/sandwich.msh (Gmsh numbering: partitioned by a coordinate sort) with BASELINE config 2 / config 1, and
+  (2) a jittered Kuhn box with three materials, non-zero Dirichlet values and every load kind.
+Prints 'DIST_API_CHECK OK' on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 tools/dist_api_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from thermoelasticity_fem_b200 import LinearSteadyState, LinearThermoElastic, LinearTransient, Mesh, Model  # noqa: E402
+from thermoelasticity_fem_b200.synthetic import kuhn_box  # noqa: E402
+
+MAT1 = dict(rho=2300, Y=64e9, nu=0.1, k=1., c=750., alpha=4e-6, T0=20.)
+MAT2 = dict(rho=2300, Y=64e9, nu=0.1, k=1., c=1., alpha=4e-6, T0=20.)
+
+
+def sandwich_mesh(mat):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sandwich_mesh.npz"))
+    blocks = [(str(g[f"b{i}_type"]), int(g[f"b{i}_tag"]), g[f"b{i}_conn"].astype(np.int64)) for i in range(int(g["n_blocks"]))]
+    mesh = Mesh()
+    mesh.from_blocks(g["points"], blocks)
+    m = LinearThermoElastic(**mat)
+    mesh.set_materials({1: m, 2: m, 3: m})
+    mesh.make_elements()
+    return mesh
+
+
+def kuhn_model():
+    pts, tets, tris, nodes = kuhn_box(12, 5, 4, jitter=0.2, seed=0)
+    props = {1: (2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: (7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
+             3: (2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    mesh.set_materials({k: LinearThermoElastic(*v) for k, v in props.items()})
+    mesh.make_elements()
+    n_t = 5
+    t = np.linspace(0., 1., n_t)
+    surf = np.zeros((3, n_t)); surf[1] = 1e5 * np.sin(3 * t); surf[2] = -1e6 * t
+    kw = dict(dict_dirichlet_U={4: [('x', 0.), ('y', 1e-4), ('z', 0.)], 5: [('x', 2e-4)]}, dict_dirichlet_theta={4: 3.0, 6: -1.5},
+              dict_surface_forces={7: surf}, dict_volume_forces={2: np.array([0., 0., -7800 * 9.81])},
+              dict_nodal_forces={8: np.array([10., 0., 0.])} if 8 in nodes else None,
+              dict_heat_flux={7: -25. * (1 + t)}, dict_heat_source={1: 1e3}, alpha_M=0.3, alpha_K=0.05)
+    return mesh, kw, n_t
+
+
+def field_err(a, b):
+    idx = np.arange(a.shape[0])
+    out = []
+    for m in (idx % 4 != 3, idx % 4 == 3):
+        out.append(float(np.linalg.norm(a[m] - b[m]) / max(np.linalg.norm(b[m]), 1e-300)))
+    return out
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    ok = True
+    results = []
+    # ---- (1a) config 2 on the sandwich mesh, 5 steps
+    n_steps, dt = 5, 1800.0 / 999
+    n_t = n_steps + 1
+    vec_t = np.linspace(0., dt * n_steps, n_t)
+    arr = np.zeros((3, n_t)); arr[0] = np.sin(2 * np.pi * vec_t / 900.) * -1e9
+    mk = lambda: Model(sandwich_mesh(MAT2), dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]},
+                       dict_dirichlet_theta={4: 0., 5: 0.}, dict_surface_forces={5: arr}, alpha_M=0.2, alpha_K=0.2)
+    model = mk()
+    N = model.mesh.n_nodes
+    z3, z1 = np.zeros(3 * N), np.zeros(N)
+    sd = LinearTransient(model, z3, z3, z1, z1, dt * n_steps, n_t, 0.5, 0.25, progress=False, comm='auto')
+    sd.solve()
+    # ---- (1b) config 1 steady
+    mk1 = lambda: Model(sandwich_mesh(MAT1), dict_dirichlet_U={4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('x', 0.), ('y', 0.), ('z', 0.)]},
+                        dict_dirichlet_theta={4: 0., 5: 0.}, dict_surface_forces={7: np.array([0., 0., -1e9])}, dict_heat_flux={6: -25.})
+    ss = LinearSteadyState(mk1(), comm='auto')
+    ss.solve()
+    # ---- (2) three materials, non-zero Dirichlet values, every load kind
+    mesh, kw, n_t2 = kuhn_model()
+    mk2 = lambda: Model(mesh, **kw)
+    N2 = mesh.n_nodes
+    rng = np.random.default_rng(3)
+    u0, th0 = 1e-5 * rng.standard_normal(3 * N2), rng.standard_normal(N2)
+    s2 = LinearTransient(mk2(), u0, np.zeros(3 * N2), th0, np.zeros(N2), 1.0, n_t2, 0.5, 0.25, progress=False, comm='auto')
+    s2.solve()
+    if rank == 0:
+        ref = LinearTransient(mk(), z3, z3, z1, z1, dt * n_steps, n_t, 0.5, 0.25, progress=False)
+        ref.solve()
+        for name, a, b in (("X", sd.X[:, -1], ref.X[:, -1]), ("Xdot", sd.Xdot[:, -1], ref.Xdot[:, -1]), ("Xdotdot", sd.Xdotdot[:, -1], ref.Xdotdot[:, -1])):
+            results.append(("sandwich transient " + name, field_err(a, b)))
+        results.append(("sandwich transient T", [float(np.abs(sd.T - ref.T).max() / np.abs(ref.T).max()), 0.0]))
+        r1 = LinearSteadyState(mk1(), solver="coupled")
+        r1.solve()
+        results.append(("sandwich steady X", field_err(ss.X, r1.X)))
+        r2 = LinearTransient(mk2(), u0, np.zeros(3 * N2), th0, np.zeros(N2), 1.0, n_t2, 0.5, 0.25, progress=False)
+        r2.solve()
+        for k in (1, n_t2 - 1):
+            results.append((f"kuhn 3 materials X step {k}", field_err(s2.X[:, k], r2.X[:, k])))
+        results.append(("kuhn 3 materials Xdotdot last", field_err(s2.Xdotdot[:, -1], r2.Xdotdot[:, -1])))
+        for name, errs in results:
+            print(f"{name}: rel diff u {errs[0]:.3e} theta {errs[1]:.3e}")
+            ok = ok and max(errs) < 1e-7
+        print("iterations partitioned", [i["iterations"] for i in sd.solve_info], "single", [i["iterations"] for i in ref.solve_info])
+        print("DIST_API_CHECK OK" if ok else "DIST_API_CHECK FAILED")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,7 @@ DU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]}       # e
 DT = {4: 0., 5: 0.}
 ALPHA_M = ALPHA_K = 0.2
 RTOL = 1e-10
+HALO = "peer"        # --halo nccl: the NCCL send/recv halo exchange (measured alternative to the peer-memory halo)
 
 
 def surface_load():
@@ -111,7 +112,7 @@ def build_case(cells, rank=0, world=1):
     if world > 1:
         from thermoelasticity_fem_b200.distributed import build_distributed_case
         return build_distributed_case(cells, rank, world, MAT2, DU, DT, surface_load(), ALPHA_M, ALPHA_K,
-                                      T_END, N_T, RTOL)
+                                      T_END, N_T, RTOL, halo=HALO)
     pts, tets, tris, nodes = kuhn_box(cells, cells, cells, 1.0, 1.0, 1.0, n_layers=1, index_dtype=np.int32)
     mesh = Mesh().from_arrays(pts, tets, tris, nodes)
     mesh.set_materials({1: LinearThermoElastic(**MAT2)})
@@ -616,7 +617,11 @@ def main():
     ap.add_argument("--parity-cells", type=int, default=24, help="N > 1: box for the partitioned-vs-single-GPU check (0 = skip)")
     ap.add_argument("--same-config-steps", type=int, default=5,
                     help="N = 1: reference steps of BASELINE config 2 timed beside the GPU arm (0 = skip; ~25 s of CPU)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo of the SpMV - direct stores into the neighbours' vectors (default) or NCCL send/recv")
     args = ap.parse_args()
+    global HALO
+    HALO = args.halo
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -5,7 +5,8 @@ imports anything under oracle/).
 
 The reference (rcapillon/thermoelasticity_fem) is pure Python and lives under /root/reference, which does not exist on
 the GPU box.  Like a C reference that is compiled where its sources lie into ``oracle/_ref/*.so``, this script compiles the
-reference's modules WHERE THEY LIE into sourceless byte code ``oracle/_ref/thermoelasticity_fem/<module>.pyc`` (outputs only;
+reference's modules WHERE THEY LIE into sourceless byte code ``oracle/_ref/thermoelasticity_fem/<module>.bc`` (the .pyc format
+under another extension: snapshot tools commonly drop ``*.pyc``; outputs only;
 ``oracle/_ref/`` is git-ignored - no reference source enters the repository or its history - but it is not gpurun-ignored, so
 the built files ship with the snapshot like the CUDA library).  ``oracle/reference_shim.load_reference()`` imports the sources
 when /root/reference is present and this byte code otherwise.
@@ -30,7 +31,7 @@ def build(reference_root=None, quiet=True):
     os.makedirs(OUT, exist_ok=True)
     for name in MODULES:
         py = os.path.join(src, name + ".py")
-        pyc = os.path.join(OUT, name + ".pyc")
+        pyc = os.path.join(OUT, name + ".bc")
         if not os.path.exists(pyc) or os.path.getmtime(pyc) < os.path.getmtime(py):
             py_compile.compile(py, cfile=pyc, dfile=f"<reference>/src/thermoelasticity_fem/{name}.py", doraise=True,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

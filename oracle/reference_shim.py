@@ -41,7 +41,7 @@ def sources_available():
 def bytecode_available():
     d = os.path.join(REFERENCE_PYC, "thermoelasticity_fem")
     ver = os.path.join(d, "PYTHON_VERSION")
-    if not (os.path.exists(os.path.join(d, "solvers.pyc")) and os.path.exists(ver)):
+    if not (os.path.exists(os.path.join(d, "solvers.bc")) and os.path.exists(ver)):
         return False
     with open(ver) as fh:                         # byte code is specific to the minor version of the interpreter
         return fh.read().split(".")[:2] == sys.version.split()[0].split(".")[:2]
@@ -155,11 +155,30 @@ def load_reference():
     if not available():
         raise RuntimeError("reference not present: neither sources at %s nor byte code at %s" % (REFERENCE_SRC, REFERENCE_PYC))
     _install_stand_ins()
-    where = REFERENCE_SRC if sources_available() else REFERENCE_PYC
-    if where not in sys.path:
-        sys.path.insert(0, where)
     import importlib
     ns = types.SimpleNamespace()
+    if sources_available():
+        if REFERENCE_SRC not in sys.path:
+            sys.path.insert(0, REFERENCE_SRC)
+    elif "thermoelasticity_fem" not in sys.modules:
+        # byte code built by oracle/build_ref.py: <module>.bc files in the .pyc format, imported with sourceless loaders
+        import importlib.machinery
+        import importlib.util
+        d = os.path.join(REFERENCE_PYC, "thermoelasticity_fem")
+
+        def load(fullname, fname, is_pkg):
+            path = os.path.join(d, fname)
+            loader = importlib.machinery.SourcelessFileLoader(fullname, path)
+            spec = importlib.util.spec_from_file_location(fullname, path, loader=loader,
+                                                          submodule_search_locations=[d] if is_pkg else None)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[fullname] = mod
+            loader.exec_module(mod)
+            return mod
+
+        pkg = load("thermoelasticity_fem", "__init__.bc", True)
+        for name in ("elements", "materials", "mesh", "model", "solvers"):     # dependency order of the reference's imports
+            setattr(pkg, name, load("thermoelasticity_fem." + name, name + ".bc", False))
     for name in ("elements", "materials", "mesh", "model", "solvers"):
         setattr(ns, name, importlib.import_module("thermoelasticity_fem." + name))
     return ns

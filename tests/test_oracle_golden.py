@@ -148,3 +148,33 @@ def test_sandwich_steady(sandwich):
     T0 = orc.reference_temperature(pts.shape[0], groups["tet"], {1: m, 2: m, 3: m})
     assert np.array_equal(g["X_raw_spsolve"][3::4] + T0, g["T"])
     assert np.abs(g["U"]).max() == 0.2111117771259024
+
+
+def test_shipped_reference_bytecode_reproduces_the_golden_fixtures():
+    """oracle/_ref (byte code of the unmodified reference built by oracle/build_ref.py, what bench.py's CPU arms time on the
+    GPU box) is pinned to the committed fixtures: its element matrices on data/sandwich.msh are BIT-identical to those the
+    reference sources produced (tests/golden/sandwich_elements.npz).  Runs in a subprocess that cannot see /root/reference."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "thermoelasticity_fem", "solvers.bc")):
+        pytest.skip("oracle/_ref not built (run __graft_entry__.build() where /root/reference is present)")
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from oracle import reference_shim as rs
+assert not rs.sources_available() and rs.bytecode_available()
+ref = rs.load_reference()
+mesh = ref.mesh.Mesh(); mesh.load_mesh(rs.sandwich_path())
+mat = ref.materials.LinearThermoElastic(rho=2300, Y=64e9, nu=0.1, k=1., c=750., alpha=4e-6, T0=20.)
+mesh.set_materials({{1: mat, 2: mat, 3: mat}}); mesh.make_elements()
+g = np.load({os.path.join(root, "tests", "golden", "sandwich_elements.npz")!r})
+for k, e in enumerate(g["subset"][:60]):
+    for nm in ("Muu", "Dtu", "Dtt", "Kuu", "Kut", "Ktt"):
+        assert np.array_equal(getattr(mesh.elements[int(e)], "compute_mat_" + nm + "_e")(), g[nm][k]), (nm, int(e))
+print("BYTECODE_PINNED")
+"""
+    env = dict(os.environ, TEFEM_REFERENCE_ROOT="/nonexistent")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "BYTECODE_PINNED" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]

@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(128) peer_coarse_start_kernel(const PeerCtx pc
 // only when c0 != 0): the level-1 operator, and the transfer operators P2^T / P2 between levels 1 and 2.  It only
 // shapes the preconditioner (a fixed linear operator either way), the Krylov vectors and the fine operator stay
 // fp64; half the bytes keep the whole level in L2.
-// COARSE_LANES (8) lanes share one block row: lane l multiplies the blocks s + l, s + l + 8, ... (four 128-bit loads of
-// the block, one 256-bit load of x_j) and a fixed shuffle tree adds the 4 row sums; lanes 0 .. 3 store.  The level-1
-// rows hold ~54 blocks: with one thread per scalar row (round 1) a sweep was a 27-trip dependent loop on 110 k threads,
-// i.e. latency bound at ~1/3 of the L2 bandwidth; 8 lanes per row give 7 independent trips on 220 k threads.  The sum
-// order is fixed (lane-strided partial sums, then the tree), so every rank computes bitwise the same coarse vectors.
-constexpr int COARSE_LANES = 8;
+// COARSE_LANES (16) lanes share one block row: lane l multiplies the blocks s + l, s + l + 16, ...; the column index of
+// the NEXT trip is loaded one trip ahead, so that a trip costs ONE memory latency (block and x_j loads issue together)
+// instead of two, at full occupancy (few registers); a fixed shuffle tree adds the 4 row sums and lanes 0 .. 3 store.
+// These kernels are latency bound, not bandwidth bound: with one thread per scalar row (round 1) a sweep was a 27-trip
+// chain of dependent loads, with 8 lanes per row (first version of round 2) still 7 trips of two latencies each: ~10 us
+// per launch whether the operator came from L2 or from HBM (profiles/README.md).  The sum order is fixed (lane-strided
+// partial sums, then the tree), so every rank computes bitwise the same coarse vectors.
+constexpr int COARSE_LANES = 16;
 
 // One 4x4 block (row-major) of a coarse operator as 16 floats: stored in single precision (transfer operators), or in
 // HALF precision (the level-1 operator A1^ = D1^-1 A1: unit diagonal blocks, off-diagonal entries of magnitude <~ 1, so
@@ -186,8 +188,11 @@ __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restr
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (live) {
         const int32_t s = rowptr[i], t = rowptr[i + 1];
-        for (int32_t p = s + l; p < t; p += COARSE_LANES) {
-            const int32_t j = colidx[p];
+        int32_t p = s + l;
+        int32_t j = p < t ? colidx[p] : 0;
+        while (p < t) {
+            const int32_t pn = p + COARSE_LANES;
+            const int32_t jn = pn < t ? colidx[pn] : 0;            // next trip's column: in flight during this trip
             float4 r0, r1, r2, r3;
             load_block16(sys, (int64_t)p, r0, r1, r2, r3);
             const double2 u0 = *reinterpret_cast<const double2*>(x + 4 * (int64_t)j);
@@ -196,9 +201,10 @@ __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restr
             a1 += (double)r1.x * u0.x + (double)r1.y * u0.y + (double)r1.z * u1.x + (double)r1.w * u1.y;
             a2 += (double)r2.x * u0.x + (double)r2.y * u0.y + (double)r2.z * u1.x + (double)r2.w * u1.y;
             a3 += (double)r3.x * u0.x + (double)r3.y * u0.y + (double)r3.z * u1.x + (double)r3.w * u1.y;
+            p = pn; j = jn;
         }
     }
-    // all 32 lanes of the warp take part in the shuffles (rows never straddle a warp: 8 divides 32)
+    // all 32 lanes of the warp take part in the shuffles (rows never straddle a warp: 16 divides 32)
 #pragma unroll
     for (int off = COARSE_LANES / 2; off > 0; off >>= 1) {
         a0 += __shfl_down_sync(0xffffffffu, a0, off, COARSE_LANES);
@@ -340,7 +346,7 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
     const int64_t n1 = 8 * (int64_t)p->n1;                    // scalar size of level 1
     const int32_t np1 = 2 * p->n1, np2 = 2 * p->n2;           // pseudo nodes (4-DOF block rows) of levels 1 and 2
     const unsigned g1 = (unsigned)ceil_div(n1, 256);                                           // one thread per scalar of level 1
-    const unsigned gs1 = (unsigned)ceil_div((int64_t)COARSE_LANES * np1, 256);                 // coarse_spmv: 8 lanes per block row
+    const unsigned gs1 = (unsigned)ceil_div((int64_t)COARSE_LANES * np1, 256);                 // coarse_spmv: 16 lanes per block row
     const unsigned gs2 = (unsigned)ceil_div((int64_t)COARSE_LANES * np2, 256);
     const unsigned gr = (unsigned)ceil_div(32 * (int64_t)p->n1, 256);
     if (p->profile) cudaEventRecord(p->ev[0], st);

@@ -334,7 +334,8 @@ class _MeshShim:
         return self._dm
 
 
-def build_distributed_case(cells, rank, world, mat_kwargs, dU, dT, surface_arr, alpha_M, alpha_K, t_end, n_t, rtol):
+def build_distributed_case(cells, rank, world, mat_kwargs, dU, dT, surface_arr, alpha_M, alpha_K, t_end, n_t, rtol,
+                           halo="peer"):
     """BASELINE config 4 on `world` GPUs: unit box of cells^3 Kuhn cells, x-slabs of node planes, every rank
     generates only the cells that touch its planes.  Returns (mesh shim, model shim, solver) for bench.py."""
     from .synthetic import kuhn_face_tris, kuhn_node_coords, kuhn_slab_tets
@@ -353,7 +354,7 @@ def build_distributed_case(cells, rank, world, mat_kwargs, dU, dT, surface_arr, 
     comm = Comm() if world > 1 else None
     solver = DistributedTransient(lp, coords, np.zeros(lp.conn.shape[0], dtype=np.int32),
                                   [LinearThermoElastic(**mat_kwargs)], dirichlet, loads, alpha_M, alpha_K,
-                                  t_end, n_t, rtol=rtol, comm=comm)
+                                  t_end, n_t, rtol=rtol, comm=comm, halo=halo)
     solver._ss = type("S", (), {})()          # bench.py reads solver._ss.krylov after prepare()
     orig_prepare = solver.prepare
 

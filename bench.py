@@ -217,6 +217,19 @@ def run_tefem(args):
                         "achieved_gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm_peak}
     for i in range(1, args.warmup + 1):
         solver.step(i)
+    # device time of the Krylov solve inside every step (events around the driver call): step = solve + everything else
+    # (load vector, predictor, right-hand side, scaling, halo of the new acceleration, corrector, host bookkeeping)
+    solve_events = []
+    orig_bicgstab = kry.bicgstab
+
+    def timed_bicgstab(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_bicgstab(*a, **k)
+        e1.record()
+        solve_events.append((e0, e1))
+        return out
+    kry.bicgstab = timed_bicgstab
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -233,6 +246,8 @@ def run_tefem(args):
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = lib.tefem_launch_count() - launches0
+    kry.bicgstab = orig_bicgstab
+    solve_ms = max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in solve_events) / max(len(solve_events), 1))
     spmv_ms, spmv_count = kry.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     iters = [inf["iterations"] for inf in infos]
@@ -327,10 +342,14 @@ def run_tefem(args):
                                "block-Jacobi scaling + 3-level aggregation preconditioner",
                    "cells": args.cells, "n_tets": E_total, "n_dofs": n_dofs_total, "n_free_dofs": n_free,
                    "partition": "single GPU" if world == 1 else f"x-slabs of node rows over {world} GPUs",
+                   "halo": None if world == 1 else ("peer memory: boundary values stored into the neighbours' vectors over NVLink, "
+                                                    "flags, one SpMV launch" if HALO == "peer" else "NCCL send/recv, overlapped with the interior rows"),
                    "l2_policy": "operands larger than L2 (system matrix %.1f GB per GPU)" % (8 * 16 * P_loc / 1e9)},
         "solver": {"preconditioner": precond_desc, "iterations_per_step": float(np.mean(iters)), "iterations": iters,
                    "dof_iterations_per_s": n_dofs_total * float(np.sum(iters)) / (ms_total * 1e-3),
                    "ms_per_iteration": ms_total / max(float(np.sum(iters)), 1.0),
+                   "solve_ms_per_step": solve_ms, "other_ms_per_step": ms_total / args.steps - solve_ms,
+                   "solve_ms_per_iteration": solve_ms * args.steps / max(float(np.sum(iters)), 1.0),
                    "relres": [inf["relres"] for inf in infos], "restarts": [inf["restarts"] for inf in infos]},
         "assembly": asm, "roofline": roofline, "cpu_baseline": cpu, "same_config": same, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup, "prepare_s": prepare_s,

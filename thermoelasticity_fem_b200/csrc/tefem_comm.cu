@@ -221,6 +221,12 @@ int64_t tefem_comm_slot_doubles(const tefem_comm* c) { return c ? c->slot_double
 double* tefem_comm_slot(const tefem_comm* c, int rank, int slot) {
     return reinterpret_cast<double*>(c->vec_base[rank]) + (int64_t)slot * c->slot_doubles;
 }
+const int* tefem_comm_err_ptr(const tefem_comm* c) { return c ? c->d_err : nullptr; }
+int tefem_comm_report_timeout() {
+    set_error("peer-memory exchange timed out waiting for another rank (communicator marked failed; "
+              "tefem_comm_reset_error after all ranks have been resynchronised)");
+    return TEFEM_ERR_NCCL;
+}
 int tefem_comm_rank(const tefem_comm* c) { return c ? c->rank : 0; }
 int tefem_comm_world(const tefem_comm* c) { return c ? c->n_ranks : 1; }
 

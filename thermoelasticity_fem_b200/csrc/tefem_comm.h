@@ -16,6 +16,10 @@ int tefem_comm_n_slots(const tefem_comm* c);
 int64_t tefem_comm_slot_doubles(const tefem_comm* c);
 double* tefem_comm_slot(const tefem_comm* c, int rank, int slot);
 int tefem_comm_rank(const tefem_comm* c);
+// device flag a timed-out peer wait raises (read it with the solver's own asynchronous copies instead of the blocking
+// tefem_comm_check), and the error a raised flag maps to
+const int* tefem_comm_err_ptr(const tefem_comm* c);
+int tefem_comm_report_timeout();
 int tefem_comm_world(const tefem_comm* c);
 
 // Packed point-to-point exchange with the neighbouring row blocks: for neighbour k, the doubles

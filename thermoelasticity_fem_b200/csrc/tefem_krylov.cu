@@ -748,6 +748,7 @@ struct tefem_solver {
     size_t ev_used = 0;
     double spmv_ms = 0.0;
     long long spmv_count = 0;
+    int last_iters = 0;           // iterations of the previous solve: where the host starts polling the stop flag
     bool profile_all = false;     // TEFEM_PROFILE_ALL=1: also time the other parts of an iteration (diagnostics, stderr)
     double cat_ms[4] = {0.0, 0.0, 0.0, 0.0};
     long long cat_count[4] = {0, 0, 0, 0};
@@ -833,7 +834,8 @@ extern "C" int tefem_solver_create(tefem_solver** out, int32_t n_rows, int32_t n
         s->xa = tefem_comm_slot(s->comm, me, SLOT_XA);
         s->peer_halo = true;
     }
-    TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_ictl, 4 * sizeof(int)));
+    TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_ictl, 8 * sizeof(int)));     // [0..3] control block, [4] peer time-out flag
+    s->h_ictl[4] = 0;
     TEFEM_CUDA_CHECK(cudaMallocHost(&s->h_sc, NSCAL * sizeof(double)));
     if (s->comm) {
         TEFEM_CUDA_CHECK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
@@ -1184,8 +1186,15 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         const bool coop = !s->comm && !s->pc && !s->profile && s->n_rows <= COOP_MAX_ROWS && coop_grid(s->n_rows) > 0;
         if (s->profile) s->ev_used = 0;          // drop the (re)start SpMV from the timing
         int iters_seen = total_iters;
+        // Polling schedule: the launches queued behind a raised stop flag are no-ops, but each still costs ~2 us, and every
+        // poll drains the launch pipeline.  Consecutive solves of a time loop need nearly the same number of iterations,
+        // so the first poll of a (re)start is placed a few iterations before the previous solve's count and the following
+        // ones come at short intervals; without history (or after a restart) the regular check_every applies.
+        const int fine_every = check_every < 4 ? check_every : 4;
+        int first_poll = check_every;
+        if (restarts == 0 && s->last_iters > 2 * check_every) first_poll = s->last_iters - fine_every;
         while (!stopped && total_iters + it < max_iter) {
-            const int batch_end = it + check_every;
+            const int batch_end = it == 0 ? first_poll : it + (first_poll > check_every ? fine_every : check_every);
             if (coop) {   // one cooperative launch runs the whole batch (small systems)
                 int it1 = batch_end;
                 if (total_iters + it1 > max_iter) it1 = max_iter - total_iters;
@@ -1236,8 +1245,10 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
                 prof_end(s, st, PROF_UPDATE);
             }
             TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl, s->ictl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            if (s->comm && tefem_comm_err_ptr(s->comm))     // the peer time-out flag rides on the same synchronisation
+                TEFEM_CUDA_CHECK(cudaMemcpyAsync(s->h_ictl + 4, tefem_comm_err_ptr(s->comm), sizeof(int), cudaMemcpyDeviceToHost, st));
             TEFEM_CUDA_CHECK(cudaStreamSynchronize(st));
-            if (s->comm) { rc = tefem_comm_check(s->comm); if (rc) return rc; }
+            if (s->comm && s->h_ictl[4]) return tefem_comm_report_timeout();
             if (s->profile) {
                 const int done_now = s->h_ictl[IN_ITERS] - iters_seen;      // iterations that really ran in this batch
                 rc = prof_harvest(s, 2 * (size_t)(done_now > 0 ? done_now : 0));
@@ -1253,6 +1264,7 @@ extern "C" int tefem_bicgstab(tefem_solver* s, const int32_t* rowptr, const int3
         }
         ++restarts;
     }
+    s->last_iters = (status == TEFEM_OK && restarts <= 1) ? total_iters : 0;
     if (h_info) {
         h_info[0] = (double)total_iters;
         h_info[1] = (double)restarts;

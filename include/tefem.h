@@ -258,6 +258,9 @@ int tefem_precond_set_agg_ranks(tefem_precond* pc, const uint8_t* agg_ranks);
 /* Level-1 operator in HALF precision (same block layout as sys1, 16 halves per block, 32-byte aligned; NULL detaches):
  * the six level-1 sweeps of an application then read half the bytes.  Preconditioner data only.                     */
 int tefem_precond_set_level1_half(tefem_precond* pc, const void* sys1_half);
+/* Level-1 cycle: overlapped != 0 (default): the last pre-smoothing sweep and the level-2 correction are formed from the
+ * same residual (one level-1 product less per application); 0: classic V-cycle (all pre-sweeps, then the residual).  */
+int tefem_precond_set_cycle(tefem_precond* pc, int overlapped);
 /* Attach (or detach with NULL) a preconditioner to the Krylov driver. */
 int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc);
 

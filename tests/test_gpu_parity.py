@@ -417,16 +417,32 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
     rng = np.random.default_rng(5)
     r = rng.standard_normal(4 * n)
     bc = D1inv @ (P1.T @ r)
-    xc = pc.omega_c * bc
-    for _ in range(pc.n_pre - 1):
-        xc = xc + pc.omega_c * (bc - A1 @ xc)
-    xc = xc + P2 @ (inv2 @ (P2.T @ (bc - A1 @ xc)))
-    for _ in range(pc.n_post):
-        xc = xc + pc.omega_c * (bc - A1 @ xc)
-    z_host = pc.omega * r + P1 @ xc
+
+    def cycle_host(kind):
+        xc = pc.omega_c * bc
+        if kind == "classic":
+            for _ in range(pc.n_pre - 1):
+                xc = xc + pc.omega_c * (bc - A1 @ xc)
+            xc = xc + P2 @ (inv2 @ (P2.T @ (bc - A1 @ xc)))
+        else:      # overlapped: the last pre-smoothing sweep and the level-2 correction share one residual
+            for _ in range(pc.n_pre - 2):
+                xc = xc + pc.omega_c * (bc - A1 @ xc)
+            t = bc - A1 @ xc
+            xc = xc + pc.omega_c * t + P2 @ (inv2 @ (P2.T @ t))
+        for _ in range(pc.n_post):
+            xc = xc + pc.omega_c * (bc - A1 @ xc)
+        return pc.omega * r + P1 @ xc
+
+    assert pc.cycle == "overlapped"
+    z_host = cycle_host("overlapped")
     z = torch.empty(4 * n, dtype=torch.float64, device="cuda")
-    pc.apply(torch.from_numpy(r).cuda(), z)                                       # separate launches (default)
+    pc.apply(torch.from_numpy(r).cuda(), z)
     assert np.abs(z.cpu().numpy() - z_host).max() <= 1e-11 * np.abs(z_host).max()
+    pc3 = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10, cycle="classic")
+    z3 = torch.empty_like(z)
+    pc3.apply(torch.from_numpy(r).cuda(), z3)
+    zc = cycle_host("classic")
+    assert np.abs(z3.cpu().numpy() - zc).max() <= 1e-11 * np.abs(zc).max()
     # the same with the level-1 operator kept in single precision
     pc2 = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10, level1_dtype="fp32")
     assert pc.level1_dtype == "fp16" and pc2.level1_dtype == "fp32"

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_precond_set_agg_ranks": [P, P],
     "tefem_precond_set_level1_half": [P, P],
+    "tefem_precond_set_cycle": [P, c_int],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_cg": [P, P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) peer_coarse_start_kernel(const PeerCtx pc
     }
 }
 
-// out = c0 * xin + c1 * (b - A x) for a 4x4-block CSR matrix A in SINGLE precision (b == nullptr: 0; xin is read
+// out = c0 * xin + c1 * (cb * b - A x) for a 4x4-block CSR matrix A in SINGLE precision (b == nullptr: 0; xin is read
 // only when c0 != 0): the level-1 operator, and the transfer operators P2^T / P2 between levels 1 and 2.  It only
 // shapes the preconditioner (a fixed linear operator either way), the Krylov vectors and the fine operator stay
 // fp64; half the bytes keep the whole level in L2.
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restr
                                                           const int32_t* __restrict__ colidx, int32_t n_rows,
                                                           const VT* __restrict__ sys, const double* __restrict__ x,
                                                           const double* __restrict__ b, const double* xin,
-                                                          double c0, double c1, double* out) {
+                                                          double c0, double c1, double cb, double* out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int32_t i = (int32_t)(gid / COARSE_LANES);
     const int l = (int)(gid % COARSE_LANES);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) coarse_spmv_kernel(const int32_t* __restr
     if (live && l < 4) {
         const double acc = l == 0 ? s0 : (l == 1 ? s1 : (l == 2 ? s2 : s3));
         const int64_t k = 4 * (int64_t)i + l;
-        out[k] = (c0 != 0.0 ? c0 * xin[k] : 0.0) + c1 * ((b ? b[k] : 0.0) - acc);
+        out[k] = (c0 != 0.0 ? c0 * xin[k] : 0.0) + c1 * ((b ? cb * b[k] : 0.0) - acc);
     }
 }
 
@@ -260,6 +260,7 @@ struct tefem_precond {
     tefem_comm* comm = nullptr;
     const uint8_t* agg_ranks = nullptr;          // multi-GPU: which ranks contribute to an aggregate's restricted residual
     const __half* sys1h = nullptr;               // level-1 operator in half precision (tefem_precond_set_level1_half)
+    bool overlap = true;                         // last pre-smoothing sweep and level-2 correction from one residual
     // TEFEM_PROFILE_PRECOND=1 (diagnostics, stderr at destroy): device time of the three parts of an application -
     // restriction + all-reduce over the ranks + first sweep (includes waiting for the slowest rank), the level-1 / level-2
     // cycle (replicated work), the prolongation.  Synchronises the stream after every application: not for timed runs.
@@ -322,6 +323,12 @@ extern "C" int tefem_precond_set_level1_half(tefem_precond* p, const void* sys1_
     return TEFEM_OK;
 }
 
+extern "C" int tefem_precond_set_cycle(tefem_precond* p, int overlapped) {
+    TEFEM_REQUIRE(p, "null preconditioner");
+    p->overlap = overlapped != 0;
+    return TEFEM_OK;
+}
+
 extern "C" int tefem_precond_set_agg_ranks(tefem_precond* p, const uint8_t* agg_ranks) {
     TEFEM_REQUIRE(p, "null preconditioner");
     p->agg_ranks = agg_ranks;
@@ -372,26 +379,35 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
     // the level-1 operator: half precision when attached, else single
 #define LEVEL1_SPMV(X, B, XIN, C0, C1, OUT)                                                                                         \
     do {                                                                                                                            \
-        if (p->sys1h) coarse_spmv_kernel<__half><<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1h, X, B, XIN, C0, C1, OUT); \
-        else coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, X, B, XIN, C0, C1, OUT);           \
+        if (p->sys1h) coarse_spmv_kernel<__half><<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1h, X, B, XIN, C0, C1, 1.0, OUT); \
+        else coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->rowptr1, p->colidx1, np1, p->sys1, X, B, XIN, C0, C1, 1.0, OUT);           \
     } while (0)
     // level 1 V-cycle on A1^ = D1^-1 A1 (bc = D1^-1 rc, x = wc bc so far = the first damped-Jacobi sweep from 0):
     // further pre-smoothing sweeps, correction from level 2, post-smoothing.  A sweep reads all of x, so it writes
     // into the other buffer: x' = x + wc (bc - A1^ x).
+    //   classic cycle:  n_pre - 1 sweeps, residual t = bc - A1^ x, x += P2 A2^-1 P2^T t
+    //   overlapped (default, n_pre >= 2): n_pre - 2 sweeps, residual t = bc - A1^ x, then the LAST pre-smoothing sweep and
+    //     the level-2 correction are both formed from that one residual: x += wc t + P2 A2^-1 P2^T t - one level-1 product
+    //     less per application, still a fixed linear operator; BiCGSTAB iterations on the scipy prototype of config 4's
+    //     operator: 92 -> 92 (24^3 box), 111 -> 101 (48^3) (profiles/README.md)
     double *cur = p->xc, *alt = p->rc;
-    for (int k = 1; k < p->n_pre; ++k) {
+    const bool overlap = p->overlap && p->n_pre >= 2;
+    for (int k = 1; k < p->n_pre - (overlap ? 1 : 0); ++k) {
         LEVEL1_SPMV(cur, p->bc, cur, 1.0, p->omega_c, alt);
         TEFEM_LAUNCH_CHECK();
         double* t = cur; cur = alt; alt = t;
     }
     LEVEL1_SPMV(cur, p->bc, nullptr, 0.0, 1.0, p->tc);
     TEFEM_LAUNCH_CHECK();                                                                       // tc = bc - A1^ x
-    coarse_spmv_kernel<float><<<gs2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, p->r2);
+    coarse_spmv_kernel<float><<<gs2, 256, 0, st>>>(p->r2_rowptr, p->r2_colidx, np2, p->r2_vals, p->tc, nullptr, nullptr, 0.0, -1.0, 1.0, p->r2);
     TEFEM_LAUNCH_CHECK();                                                                       // r2 = P2^T tc
     dense_matvec_kernel<<<(unsigned)(4 * np2), 128, 0, st>>>(4 * np2, p->inv2, p->r2, p->x2);
     TEFEM_LAUNCH_CHECK();                                                                       // x2 = A2^-1 r2
-    coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, cur);
-    TEFEM_LAUNCH_CHECK();                                                                       // x += P2 x2
+    if (overlap)   // x += wc tc + P2 x2  ( = x - ( -wc tc - P2 x2 ) )
+        coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, p->tc, cur, 1.0, -1.0, -p->omega_c, cur);
+    else           // x += P2 x2
+        coarse_spmv_kernel<float><<<gs1, 256, 0, st>>>(p->p2_rowptr, p->p2_colidx, np1, p->p2_vals, p->x2, nullptr, cur, 1.0, -1.0, 1.0, cur);
+    TEFEM_LAUNCH_CHECK();
     for (int k = 0; k < p->n_post; ++k) {
         LEVEL1_SPMV(cur, p->bc, cur, 1.0, p->omega_c, alt);
         TEFEM_LAUNCH_CHECK();

@@ -244,9 +244,14 @@ class TwoLevelPreconditioner:
     """Owns the device arrays of one preconditioner and its C handle (attach with KrylovSolver.set_precond)."""
 
     def __init__(self, dm, sys, comm=None, factor1=8.0, factor2=3.0, omega=1.0, omega_c=0.7, n_pre=3, n_post=3,
-                 dense_limit=200, level1_dtype="fp16"):
+                 dense_limit=200, level1_dtype="fp16", cycle="overlapped"):
         """level1_dtype: storage of the scaled level-1 operator for the sweeps - 'fp16' (default; falls back to 'fp32' when
-        an entry would overflow half precision) or 'fp32'.  Preconditioner data only."""
+        an entry would overflow half precision) or 'fp32'.  Preconditioner data only.
+        cycle: 'overlapped' (default) - the last pre-smoothing sweep and the level-2 correction use one residual (one
+        level-1 product less per application) - or 'classic'."""
+        if cycle not in ("overlapped", "classic"):
+            raise ValueError("cycle must be 'overlapped' or 'classic'")
+        self.cycle = cycle
         import os
         import scipy.sparse as sp
         if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c[,n_pre,n_post]"
@@ -254,6 +259,8 @@ class TwoLevelPreconditioner:
             factor1, factor2, omega, omega_c = v[:4]
             if len(v) >= 6:
                 n_pre, n_post = int(v[4]), int(v[5])
+            if len(v) >= 7:
+                cycle = "overlapped" if v[6] else "classic"
         lib, dev = dm.lib, dm.device
         S = dm.schedule
         n_own = S.n_rows
@@ -328,6 +335,8 @@ class TwoLevelPreconditioner:
             _lib.check(lib.tefem_precond_set_agg_ranks(self.handle, p(self.agg_ranks)))
         if self.sys1_half is not None:
             _lib.check(lib.tefem_precond_set_level1_half(self.handle, p(self.sys1_half)))
+        self.cycle = cycle
+        _lib.check(lib.tefem_precond_set_cycle(self.handle, int(cycle == "overlapped")))
 
     def apply(self, r, z):
         _lib.check(self.lib.tefem_precond_apply(self.handle, _lib.ptr(r), _lib.ptr(z), _lib.stream_ptr()))

@@ -40,6 +40,7 @@ DU = {4: [('x', 0.), ('y', 0.), ('z', 0.)], 5: [('y', 0.), ('z', 0.)]}       # e
 DT = {4: 0., 5: 0.}
 ALPHA_M = ALPHA_K = 0.2
 RTOL = 1e-10
+ML_OPTIONS = None    # --ml "n_pre=3,n_post=2,cycle=classic,...": keyword arguments of multilevel.TwoLevelPreconditioner (experiments)
 HALO = "peer"        # --halo nccl: the NCCL send/recv halo exchange (measured alternative to the peer-memory halo)
 
 
@@ -112,7 +113,7 @@ def build_case(cells, rank=0, world=1):
     if world > 1:
         from thermoelasticity_fem_b200.distributed import build_distributed_case
         return build_distributed_case(cells, rank, world, MAT2, DU, DT, surface_load(), ALPHA_M, ALPHA_K,
-                                      T_END, N_T, RTOL, halo=HALO)
+                                      T_END, N_T, RTOL, halo=HALO, precond_options=ML_OPTIONS)
     pts, tets, tris, nodes = kuhn_box(cells, cells, cells, 1.0, 1.0, 1.0, n_layers=1, index_dtype=np.int32)
     mesh = Mesh().from_arrays(pts, tets, tris, nodes)
     mesh.set_materials({1: LinearThermoElastic(**MAT2)})
@@ -121,7 +122,7 @@ def build_case(cells, rank=0, world=1):
                   alpha_M=ALPHA_M, alpha_K=ALPHA_K)
     n = mesh.n_nodes
     solver = LinearTransient(model, np.zeros(3 * n), np.zeros(3 * n), np.zeros(n), np.zeros(n), T_END, N_T, 0.5, 0.25,
-                             rtol=RTOL, history='last', progress=False, check_every=16)
+                             rtol=RTOL, history='last', progress=False, check_every=16, precond_options=ML_OPTIONS)
     return mesh, model, solver
 
 
@@ -255,7 +256,8 @@ def run_tefem(args):
     pc = pc if hasattr(pc, "n1") else None
     precond_desc = "block-Jacobi scaling only" if pc is None else (
         f"block-Jacobi scaling + additive aggregation correction with rigid-body coarse spaces: level 1 = {pc.n1} "
-        f"aggregates (cubes of {pc.factor1:g} h, Galerkin, {pc.n_pre}+{pc.n_post} damped-Jacobi sweeps {pc.omega_c:g}), "
+        f"aggregates (cubes of {pc.factor1:g} h, Galerkin, operator stored in {pc.level1_dtype}, {pc.n_pre}+{pc.n_post} damped-Jacobi "
+        f"sweeps {pc.omega_c:g}, {pc.cycle} cycle), "
         f"level 2 = {pc.n2} aggregates (dense inverse), fine weight {pc.omega:g}")
     ms_per_step = ms_total / args.steps
     steps_per_s = 1e3 / ms_per_step
@@ -638,9 +640,15 @@ def main():
                     help="N = 1: reference steps of BASELINE config 2 timed beside the GPU arm (0 = skip; ~25 s of CPU)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo of the SpMV - direct stores into the neighbours' vectors (default) or NCCL send/recv")
+    ap.add_argument("--ml", default="", help="experiments: keyword arguments of the preconditioner, e.g. n_pre=3,n_post=2,cycle=classic")
     args = ap.parse_args()
-    global HALO
+    global HALO, ML_OPTIONS
     HALO = args.halo
+    if args.ml:
+        ML_OPTIONS = {}
+        for kv in args.ml.split(","):
+            k, v = kv.split("=")
+            ML_OPTIONS[k] = v if k in ("cycle", "level1_dtype") else (int(v) if k in ("n_pre", "n_post", "dense_limit") else float(v))
     if args.impl == "reference":
         run_reference(args)
     else:

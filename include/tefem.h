@@ -189,6 +189,9 @@ int tefem_block_jacobi_apply(const double* dinv, int32_t n_rows, const double* r
 /* y = sys * x on the 4x4 block format (kernel K3), 4 threads per node row.                     */
 int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows,
                const double* sys, const double* x, double* y, void* stream);
+/* Launch configuration of the SpMV (threads per CTA, resident CTAs per SM of the grid-stride grid, blocks per trip);
+ * default 256, 8, 2 (tuned at config B).  Measurement knob, host-side setting of the calling process.              */
+int tefem_spmv_set_config(int threads, int ctas_per_sm, int unroll);
 
 /* Opaque Krylov solver handle (kernel K4/K6 driver).  Work vectors are provided by the caller:
  * work must hold tefem_solver_work_doubles(n_rows, n_halo) doubles, 128-byte aligned.                                    */

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "tefem_block_jacobi_scale": [P, P, c_int32, P, P, P, c_int, P],
     "tefem_block_jacobi_apply": [P, c_int32, P, P, P, P],
     "tefem_spmv": [P, P, c_int32, P, P, P, P],
+    "tefem_spmv_set_config": [c_int, c_int, c_int],
     "tefem_solver_create": [P, c_int32, c_int32, P, P],
     "tefem_solver_destroy": [P],
     "tefem_solver_profile": [P, c_int, P, P],

@@ -915,23 +915,13 @@ static int grid_for(int64_t n_threads, int per_cta) {
 }
 
 // Launch configuration of the SpMV (threads per CTA, CTAs per SM of the grid-stride grid, blocks per trip):
-// tuned on the B200 at config B (profiles/README.md); TEFEM_SPMV_CFG="threads,ctas_per_sm,unroll" overrides it
-// for experiments.
+// tuned on the B200 at config B (profiles/README.md); tefem_spmv_set_config(threads, ctas_per_sm, unroll) overrides it
+// for experiments (single-GPU launches; the multi-GPU path uses the tuned configuration).
 struct SpmvCfg {
     int threads = 256, ctas_per_sm = 8, unroll = 2;
 };
-static const SpmvCfg& spmv_cfg() {
-    static SpmvCfg cfg = [] {
-        SpmvCfg c;
-        const char* e = getenv("TEFEM_SPMV_CFG");
-        if (e) sscanf(e, "%d,%d,%d", &c.threads, &c.ctas_per_sm, &c.unroll);
-        if (c.threads < 32 || c.threads > 256 || (c.threads & 31)) c.threads = 256;
-        if (c.ctas_per_sm < 1 || c.ctas_per_sm > 8) c.ctas_per_sm = 8;   // partial buffers hold 148 * 8 CTAs
-        if (c.unroll != 1 && c.unroll != 2 && c.unroll != 4) c.unroll = 2;
-        return c;
-    }();
-    return cfg;
-}
+static SpmvCfg g_spmv_cfg;
+static const SpmvCfg& spmv_cfg() { return g_spmv_cfg; }
 
 template <int DOTS, int UNROLL, bool HALO>
 static int spmv_resident_ctas(int threads, int* out) {
@@ -1100,6 +1090,14 @@ extern "C" int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc) {
 extern "C" int tefem_solver_halo_exchange(tefem_solver* s, double* x, void* stream) {
     TEFEM_REQUIRE(s && x, "null pointer");
     return halo_exchange(s, x, nullptr, as_stream(stream));
+}
+
+extern "C" int tefem_spmv_set_config(int threads, int ctas_per_sm, int unroll) {
+    TEFEM_REQUIRE(threads >= 32 && threads <= 256 && (threads & 31) == 0, "threads per CTA: a multiple of 32 in 32 .. 256");
+    TEFEM_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, "1 .. 8 CTAs per SM (the partial-sum buffers hold 148 * 8)");
+    TEFEM_REQUIRE(unroll == 1 || unroll == 2 || unroll == 4, "blocks per trip: 1, 2 or 4");
+    g_spmv_cfg.threads = threads; g_spmv_cfg.ctas_per_sm = ctas_per_sm; g_spmv_cfg.unroll = unroll;
+    return TEFEM_OK;
 }
 
 extern "C" int tefem_spmv(const int32_t* rowptr, const int32_t* colidx, int32_t n_rows, const double* sys,

@@ -248,9 +248,7 @@ extern "C" int tefem_schedule_bank_numbering(int32_t n_cta, const int32_t* h_cta
                                              int n_threads, int32_t* h_new_local, int32_t* h_n_slots, int64_t* h_cost) {
     TEFEM_REQUIRE(h_cta_hdr && h_item_inc && h_item_meta && h_inc && h_new_local && h_n_slots, "null pointer");
     TEFEM_REQUIRE(n_cta >= 0 && (strides & 3) != 0 && n_sweeps >= 0, "arguments");
-    int block_size = 16;   // TEFEM_BANK_BLOCK = 16 | 32 | 64 (measurement knob: elements exchanged between the half-warps of phase 1)
-    if (const char* e = getenv("TEFEM_BANK_BLOCK")) block_size = atoi(e);
-    TEFEM_REQUIRE(block_size == 16 || block_size == 32 || block_size == 64, "TEFEM_BANK_BLOCK must be 16, 32 or 64");
+    const int block_size = 16;   // classes are exchanged inside blocks of 16 staged elements: phase 1 keeps its half-warp sets
     if (n_threads <= 0) n_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 64u);
     n_threads = std::min(n_threads, std::max(1, n_cta));
     std::atomic<int32_t> next{0};

@@ -97,13 +97,14 @@ def make_comm(comm):
 
 
 def distributed_transient(model, x0_full, v0_full, t_end, n_t, gamma, beta, comm, rtol, max_iter, check_every, precond,
-                          floor_factor, min_nodes_multilevel):
+                          floor_factor, min_nodes_multilevel, precond_options=None):
     """(PartitionedModel, DistributedTransient) for a Model; x0_full / v0_full: [4N] initial state, reference numbering."""
     pm = PartitionedModel(model, comm.rank, comm.world)
     if precond == "auto":
         precond = "multilevel" if model.mesh.n_nodes >= min_nodes_multilevel else "block_jacobi"
     solver = DistributedTransient(pm.lp, pm.coords_local, pm.mat_id_local, None, pm.dirichlet, pm.loads(), model.alpha_M,
                                   model.alpha_K, t_end, n_t, gamma, beta, rtol=rtol, max_iter=max_iter, check_every=check_every,
-                                  comm=comm, precond=precond, floor_factor=floor_factor, mat_table=pm.mat_table)
+                                  comm=comm, precond=precond, floor_factor=floor_factor, mat_table=pm.mat_table,
+                                  precond_options=precond_options)
     solver.initial_state = (pm.to_local(x0_full), pm.to_local(v0_full))
     return pm, solver

@@ -177,12 +177,13 @@ class DistributedTransient:
 
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
                  alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=16,
-                 comm=None, precond="multilevel", halo="peer", floor_factor=1.0, mat_table=None):
+                 comm=None, precond="multilevel", halo="peer", floor_factor=1.0, mat_table=None, precond_options=None):
         """halo: 'peer' (default) - boundary values are stored straight into the neighbours' vectors over NVLink and the
         SpMV waits for flags; 'nccl' - packed ncclSend / ncclRecv overlapped with the interior rows (measured alternative)."""
         assert halo in ("peer", "nccl")
         self.halo = halo
         self.floor_factor = floor_factor
+        self.precond_options = precond_options or {}
         self.lp, self.comm = lp, comm
         self.alpha_M, self.alpha_K = alpha_M, alpha_K
         self.gamma, self.beta = gamma, beta
@@ -243,7 +244,7 @@ class DistributedTransient:
         self.precond = None
         if self.precond_kind == "multilevel":
             from .multilevel import TwoLevelPreconditioner
-            self.precond = TwoLevelPreconditioner(dm, self.sys, comm=self.comm)
+            self.precond = TwoLevelPreconditioner(dm, self.sys, comm=self.comm, **self.precond_options)
             self.krylov.set_precond(self.precond)
         send_idx = torch.from_numpy(lp.send_idx.astype(np.int32)).to(dev)
         if self.comm is not None and self.halo == "peer":
@@ -335,7 +336,7 @@ class _MeshShim:
 
 
 def build_distributed_case(cells, rank, world, mat_kwargs, dU, dT, surface_arr, alpha_M, alpha_K, t_end, n_t, rtol,
-                           halo="peer"):
+                           halo="peer", precond_options=None):
     """BASELINE config 4 on `world` GPUs: unit box of cells^3 Kuhn cells, x-slabs of node planes, every rank
     generates only the cells that touch its planes.  Returns (mesh shim, model shim, solver) for bench.py."""
     from .synthetic import kuhn_face_tris, kuhn_node_coords, kuhn_slab_tets
@@ -354,7 +355,7 @@ def build_distributed_case(cells, rank, world, mat_kwargs, dU, dT, surface_arr, 
     comm = Comm() if world > 1 else None
     solver = DistributedTransient(lp, coords, np.zeros(lp.conn.shape[0], dtype=np.int32),
                                   [LinearThermoElastic(**mat_kwargs)], dirichlet, loads, alpha_M, alpha_K,
-                                  t_end, n_t, rtol=rtol, comm=comm, halo=halo)
+                                  t_end, n_t, rtol=rtol, comm=comm, halo=halo, precond_options=precond_options)
     solver._ss = type("S", (), {})()          # bench.py reads solver._ss.krylov after prepare()
     orig_prepare = solver.prepare
 

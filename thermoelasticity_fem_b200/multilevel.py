@@ -252,15 +252,7 @@ class TwoLevelPreconditioner:
         if cycle not in ("overlapped", "classic"):
             raise ValueError("cycle must be 'overlapped' or 'classic'")
         self.cycle = cycle
-        import os
         import scipy.sparse as sp
-        if "TEFEM_ML" in os.environ:          # experiments: "factor1,factor2,omega,omega_c[,n_pre,n_post]"
-            v = [float(x) for x in os.environ["TEFEM_ML"].split(",")]
-            factor1, factor2, omega, omega_c = v[:4]
-            if len(v) >= 6:
-                n_pre, n_post = int(v[4]), int(v[5])
-            if len(v) >= 7:
-                cycle = "overlapped" if v[6] else "classic"
         lib, dev = dm.lib, dm.device
         S = dm.schedule
         n_own = S.n_rows

@@ -64,7 +64,7 @@ class _SystemSolve:
     symmetric positive definite operators: the field systems of the staged steady-state solve)."""
 
     def __init__(self, model, cM, cD, cK, rtol, max_iter, check_every, precond="auto", dir_mask=None, method="bicgstab",
-                 floor_factor=1.0):
+                 floor_factor=1.0, precond_options=None):
         """dir_mask (uint8 [4N], default: the model's Dirichlet DOFs): DOFs eliminated from the system (identity rows
         and columns); the reduced-order bases pass the complement of one field's free DOFs (rom.py).
         floor_factor: see KrylovSolver.bicgstab (1 = a solve that stalls above rtol raises)."""
@@ -92,7 +92,7 @@ class _SystemSolve:
             precond = "multilevel" if self.dm.n_nodes >= MULTILEVEL_MIN_NODES else "block_jacobi"
         if precond == "multilevel":
             from .multilevel import TwoLevelPreconditioner
-            self.precond = TwoLevelPreconditioner(self.dm, self.sys)
+            self.precond = TwoLevelPreconditioner(self.dm, self.sys, **(precond_options or {}))
             self.krylov.set_precond(self.precond)
         elif precond != "block_jacobi":
             raise ValueError("precond must be 'auto', 'multilevel' or 'block_jacobi'")
@@ -125,13 +125,14 @@ class LinearSteadyState:
                   above (the coarse correction needs 20 x fewer iterations there)."""
 
     def __init__(self, model, rtol=1e-10, max_iter=50000, check_every=32, precond="auto", solver="auto", floor_factor=1.0,
-                 comm=None):
+                 comm=None, precond_options=None):
         """comm: None (one GPU) | 'auto' | distributed.Comm - row-partitioned solve on the GPUs of the torch.distributed job
         (dist_api.py; the coupled BiCGSTAB path); every rank receives the full X, U, T."""
         if solver not in ("auto", "staged", "coupled"):
             raise ValueError("solver must be 'auto', 'staged' or 'coupled'")
         self.model = model
         self.comm = comm
+        self.precond_options = precond_options      # keyword arguments of multilevel.TwoLevelPreconditioner (experiments)
         self.rtol, self.max_iter, self.check_every, self.precond = rtol, max_iter, check_every, precond
         self.solver, self.floor_factor = solver, floor_factor
         self.X = None
@@ -149,7 +150,8 @@ class LinearSteadyState:
         m.create_free_dofs_lists()
         zeros = np.zeros(m.mesh.n_dofs)
         pm, ds = dist_api.distributed_transient(m, zeros, zeros, 1.0, 2, 0.5, 0.25, comm, self.rtol, self.max_iter,
-                                                self.check_every, self.precond, self.floor_factor, MULTILEVEL_MIN_NODES)
+                                                self.check_every, self.precond, self.floor_factor, MULTILEVEL_MIN_NODES,
+                                                self.precond_options)
         ds.prepare(steady=True)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -180,7 +182,7 @@ class LinearSteadyState:
             x = self._solve_staged(m)
         else:
             ss = _SystemSolve(m, 0., 0., 1., self.rtol, self.max_iter, self.check_every, self.precond,
-                              floor_factor=self.floor_factor)
+                              floor_factor=self.floor_factor, precond_options=self.precond_options)
             x = torch.zeros(m.mesh.n_dofs, dtype=torch.float64, device=ss.dm.device)
             self.solve_info = ss.solve(m.rhs_device(), x)
         x.masked_fill_(m._dir_mask.bool(), 0.0)   # eliminated unknowns (a coarse correction may leave round-off there)
@@ -234,7 +236,7 @@ class LinearTransient:
                  t_end, n_t,
                  gamma=0.5, beta=0.25,
                  rtol=1e-10, max_iter=50000, check_every=32, history='full', warm_start=True, guess_order=0,
-                 on_step=None, progress=True, precond="auto", floor_factor=1.0, comm=None):
+                 on_step=None, progress=True, precond="auto", floor_factor=1.0, comm=None, precond_options=None):
         self.model = model
         self.gamma = gamma
         self.beta = beta
@@ -251,6 +253,7 @@ class LinearTransient:
         self.rtol, self.max_iter, self.check_every = rtol, max_iter, check_every
         self.history, self.warm_start, self.on_step, self.progress = history, warm_start, on_step, progress
         self.precond = precond
+        self.precond_options = precond_options      # keyword arguments of multilevel.TwoLevelPreconditioner (experiments)
         self.floor_factor = floor_factor
         # comm: None (one GPU) | 'auto' | distributed.Comm - row-partitioned solve on the GPUs of the torch.distributed
         # job (dist_api.py); every rank receives the kept histories
@@ -308,7 +311,7 @@ class LinearTransient:
         self._x0_full, self._v0_full = x0, v0
         dt = self.dt
         self._ss = _SystemSolve(m, 1.0, self.gamma * dt, self.beta * dt ** 2, self.rtol, self.max_iter, self.check_every,
-                                self.precond, floor_factor=self.floor_factor)
+                                self.precond, floor_factor=self.floor_factor, precond_options=self.precond_options)
         self._w1 = torch.empty_like(self._x)
         self._w2 = torch.empty_like(self._x)
         self._rhs = torch.empty_like(self._x)
@@ -366,7 +369,7 @@ class LinearTransient:
         x0, v0 = interleave(self.initial_U, self.initial_theta), interleave(self.initial_Udot, self.initial_thetadot)
         pm, ds = dist_api.distributed_transient(m, x0, v0, self.t_end, n_t, self.gamma, self.beta, comm, self.rtol,
                                                 self.max_iter, self.check_every, self.precond, self.floor_factor,
-                                                MULTILEVEL_MIN_NODES)
+                                                MULTILEVEL_MIN_NODES, self.precond_options)
         ds.prepare()
         keep_every = 1 if self.history == 'full' else (None if self.history == 'last' else int(self.history))
         cols = list(range(0, n_t, keep_every)) if keep_every is not None else [n_t - 1]

@@ -45,19 +45,20 @@ MAX_SMEM_BYTES = 220 * 1024  # dynamic shared memory limit of assemble_kernel (c
 MAX_CTA_ELEMS = 4096         # 12 bits of the packed incidence entry
 MAX_CTA_NODES = 256          # tile-local node numbers are bytes
 # True: the pieces of split blocks come first in a tile's item list and every block has one item in block order behind
-# them (see build_schedule); False: pieces inline + split lists.  TEFEM_PIECES_FIRST=0/1 overrides (A/B measurements).
-PIECES_FIRST = os.environ.get("TEFEM_PIECES_FIRST", "1") == "1"
+# them (see build_schedule); False: pieces inline + split lists (build_schedule(pieces_first=...) for A/B measurements).
+PIECES_FIRST = True
 # Bank-aware tile-local numbering of the staged elements (optimize_banks).  On by default: it cannot change a value (the
 # kernel and the lists are untouched, CPU emulation: bitwise) and the CPU model that reproduces ncu's wavefront counts predicts
-# -22 % / -15 % gather wavefronts; it was built after the round's GPU budget was spent, so the first measurement is the
-# round-end bench.  TEFEM_BANK_OPT=0 restores the numbering the committed ncu captures were taken with.
-BANK_OPT = os.environ.get("TEFEM_BANK_OPT", "1") == "1"
+# -22 % / -15 % gather wavefronts; measured under ncu in round 2: -16 % / -15 % of all shared-memory wavefronts
+# (profiles/README.md).  build_schedule(bank_opt=False) keeps the staged order.
+BANK_OPT = True
 # Fixed-pitch placement of the incidence lists (pitch_lists): values untouched, kernel untouched, modelled 1.7 -> 0.7
 # wavefronts per element for the 2-byte entry loads - but ~20 % more entries per tile, and the default tiles leave only
 # 7.8 KB of shared memory before the fused M + D + K launch drops from two CTAs per SM to one (2 x (111.9 + 1) KB of 228 KB):
-# with the lists pitched the margin shrinks to < 1 KB.  OFF by default (TEFEM_PITCH_LISTS=1 enables); when enabled it is
-# skipped for schedules where it would cost a CTA per SM.
-PITCH_LISTS = os.environ.get("TEFEM_PITCH_LISTS", "0") == "1"
+# with the lists pitched the margin shrinks to < 1 KB.  OFF by default (build_schedule(pitch=True) enables; measured in
+# round 2 with 448-block tiles: slower, profiles/README.md); when enabled it is skipped for schedules where it would cost
+# a CTA per SM.
+PITCH_LISTS = False
 SM_SMEM_BYTES = 228 * 1024     # shared memory of a B200 SM; every resident CTA reserves 1 KB of it
 HDR_STRIDE = 12
 H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)

@@ -5,7 +5,8 @@ A/Bs them (tools/asm_ab.py checks every pieces-first run bitwise against the fir
     /usr/local/graft/bin/gpurun --timeout 300 -- '<printed command>'
 
 Variants: name -> extra nvcc flags (see csrc/tefem_assemble.cu, csrc/tefem_element.cuh).  Run-time knobs need no build:
-TEFEM_ASM_THREADS=64|128 (threads per CTA of the pieces-first kernel), TEFEM_PIECES_FIRST=0|1 (default item layout).
+tools/asm_ab.py reads TEFEM_ASM_THREADS=64|128 (-> DeviceMesh.asm_threads) and takes the item layout / bank numbering / pitch
+as fields of its variant strings.
 """
 import os
 import subprocess

@@ -258,7 +258,9 @@ def run_tefem(args):
         f"block-Jacobi scaling + additive aggregation correction with rigid-body coarse spaces: level 1 = {pc.n1} "
         f"aggregates (cubes of {pc.factor1:g} h, Galerkin, operator stored in {pc.level1_dtype}, {pc.n_pre}+{pc.n_post} damped-Jacobi "
         f"sweeps {pc.omega_c:g}, {pc.cycle} cycle), "
-        f"level 2 = {pc.n2} aggregates (dense inverse), fine weight {pc.omega:g}")
+        f"level 2 = {pc.n2} aggregates (dense inverse), fine weight {pc.omega:g}; coarse cycle: "
+        + ("one persistent kernel per application, rows of levels 1 and 2 partitioned over the ranks, coarse vectors exchanged "
+           "through peer memory" if pc.coarse == "persistent" else "separate launches on replicated levels"))
     ms_per_step = ms_total / args.steps
     steps_per_s = 1e3 / ms_per_step
 
@@ -344,8 +346,11 @@ def run_tefem(args):
                                "block-Jacobi scaling + 3-level aggregation preconditioner",
                    "cells": args.cells, "n_tets": E_total, "n_dofs": n_dofs_total, "n_free_dofs": n_free,
                    "partition": "single GPU" if world == 1 else f"x-slabs of node rows over {world} GPUs",
-                   "halo": None if world == 1 else ("peer memory: boundary values stored into the neighbours' vectors over NVLink, "
-                                                    "flags, one SpMV launch" if HALO == "peer" else "NCCL send/recv, overlapped with the interior rows"),
+                   "halo": None if world == 1 else {
+                       "peer": "fused: ONE SpMV kernel stores its boundary values into the neighbours' vectors over NVLink, multiplies "
+                               "the interior rows, waits for the neighbours' flags, multiplies the boundary rows",
+                       "peer-push": "peer memory: separate push launch, the SpMV waits for the flags before its first row",
+                       "nccl": "NCCL send/recv, overlapped with the interior rows"}[HALO],
                    "l2_policy": "operands larger than L2 (system matrix %.1f GB per GPU)" % (8 * 16 * P_loc / 1e9)},
         "solver": {"preconditioner": precond_desc, "iterations_per_step": float(np.mean(iters)), "iterations": iters,
                    "dof_iterations_per_s": n_dofs_total * float(np.sum(iters)) / (ms_total * 1e-3),
@@ -638,7 +643,7 @@ def main():
     ap.add_argument("--parity-cells", type=int, default=24, help="N > 1: box for the partitioned-vs-single-GPU check (0 = skip)")
     ap.add_argument("--same-config-steps", type=int, default=5,
                     help="N = 1: reference steps of BASELINE config 2 timed beside the GPU arm (0 = skip; ~25 s of CPU)")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--halo", default="peer", choices=["peer", "peer-push", "nccl"],
                     help="N > 1: halo of the SpMV - direct stores into the neighbours' vectors (default) or NCCL send/recv")
     ap.add_argument("--ml", default="", help="experiments: keyword arguments of the preconditioner, e.g. n_pre=3,n_post=2,cycle=classic")
     args = ap.parse_args()
@@ -648,7 +653,7 @@ def main():
         ML_OPTIONS = {}
         for kv in args.ml.split(","):
             k, v = kv.split("=")
-            ML_OPTIONS[k] = v if k in ("cycle", "level1_dtype") else (int(v) if k in ("n_pre", "n_post", "dense_limit") else float(v))
+            ML_OPTIONS[k] = v if k in ("cycle", "level1_dtype", "coarse") else (int(v) if k in ("n_pre", "n_post", "dense_limit") else float(v))
     if args.impl == "reference":
         run_reference(args)
     else:

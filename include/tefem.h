@@ -223,6 +223,11 @@ int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr, const int3
                           const int32_t* send_dpos, const int32_t* h_recv_ptr,
                           const int32_t* boundary_rows, int32_t n_boundary_rows,
                           const int32_t* interior_rows, int32_t n_interior_rows);
+/* Peer-memory halo: rows [lo, hi) have no halo column (for row blocks in node order the interior is one contiguous
+ * range; lo == hi when unknown).  fused != 0 (default): the SpMV is ONE kernel that stores this rank's boundary values
+ * into the neighbours' vectors, multiplies the interior rows, waits for the neighbours' flags and multiplies the
+ * boundary rows; 0: separate push launch, the SpMV waits before its first row (comparison).                          */
+int tefem_solver_set_interior_range(tefem_solver* s, int32_t lo, int32_t hi, int fused);
 /* number of peer-memory vector slots a solver needs (tefem_comm_vec_alloc) */
 int tefem_solver_peer_slots(void);
 
@@ -264,6 +269,23 @@ int tefem_precond_set_level1_half(tefem_precond* pc, const void* sys1_half);
 /* Level-1 cycle: overlapped != 0 (default): the last pre-smoothing sweep and the level-2 correction are formed from the
  * same residual (one level-1 product less per application); 0: classic V-cycle (all pre-sweeps, then the residual).  */
 int tefem_precond_set_cycle(tefem_precond* pc, int overlapped);
+/* Coarse cycle of an application.  mode 0: separate launches on levels replicated on every rank (~10 dependent small
+ * kernels per application whatever the number of GPUs).  mode 1: ONE persistent cooperative kernel; the rows of levels 1
+ * and 2 are PARTITIONED over the ranks, every coarse vector has one replica per rank in the peer-memory region in a
+ * self-validating layout (16 bytes per value: two 8-byte units {32 data bits, 32-bit tag}), the rank that owns a row
+ * computes it and stores it into all replicas (remote stores over NVLink), and a consumer retries its load until the tags
+ * match: no barrier inside the kernel (csrc/tefem_precond.cu, coarse_cycle_kernel).  cycle_work: ZEROED, 128-byte
+ * aligned buffer of tefem_precond_cycle_doubles(...) doubles owned by the caller (mode 1; NULL for mode 0).  With a
+ * communicator its region must have been allocated with big_cap_doubles >= tefem_precond_peer_doubles(...); without one
+ * the same kernel runs on cycle_work alone.  Call after set_cycle / set_level1_half.                                  */
+int tefem_precond_set_coarse_mode(tefem_precond* pc, int mode, double* cycle_work);
+int64_t tefem_precond_peer_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post);
+/* Persistent cycle on several GPUs: x_mask[n_agg] / t_mask[n_agg] (uint8 device arrays, bit q) = rank q reads the level-1
+ * iterates / the residual t of the aggregate; the owner stores a row only into those replicas (NULL: into all).  Row
+ * ownership: aggregate i belongs to rank q with n_agg q / world <= i < n_agg (q + 1) / world (integer division), level-2
+ * aggregate J likewise with n_agg2; the owner of J computes rows 8 J .. 8 J + 7 of P2^T t and of the dense product.  */
+int tefem_precond_set_cycle_masks(tefem_precond* pc, const uint8_t* x_mask, const uint8_t* t_mask);
+int64_t tefem_precond_cycle_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post);
 /* Attach (or detach with NULL) a preconditioner to the Krylov driver. */
 int tefem_solver_set_precond(tefem_solver* s, tefem_precond* pc);
 

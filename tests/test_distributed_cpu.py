@@ -196,3 +196,112 @@ def test_dirichlet_and_load_restriction_to_local_nodes():
         b = localize(conn, np.arange(conn.shape[0]), bounds, rank)
         assert np.array_equal(a.conn, b.conn) and np.array_equal(a.elem_ids, b.elem_ids)
         assert np.array_equal(a.local_nodes, b.local_nodes) and np.array_equal(a.send_idx, b.send_idx)
+
+
+def test_longest_interior_range():
+    from thermoelasticity_fem_b200.distributed import longest_interior_range
+    assert longest_interior_range(np.array([0, 1, 2, 97, 98, 99]), 100) == (3, 97)
+    assert longest_interior_range(np.array([], dtype=np.int64), 10) == (0, 10)
+    assert longest_interior_range(np.array([5]), 10) == (0, 5)
+    lo, hi = longest_interior_range(np.arange(10), 10)
+    assert lo == hi
+    assert longest_interior_range(np.array([0, 1, 2, 3]), 10) == (4, 10)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_cycle_masks_cover_every_read_of_the_row_partitioned_coarse_cycle(world):
+    """Emulation of the data movement of csrc/tefem_precond.cu coarse_cycle_kernel: every rank keeps replicas of the coarse
+    vectors that start as NaN; the owner of a row stores it only into the replicas named by the masks of
+    multilevel.cycle_masks; every rank then computes its own rows from ITS replicas.  No NaN may be read and the result
+    must equal the cycle computed in one piece (overlapped form, 3 + 3 sweeps, level 2, prolongation reads)."""
+    import scipy.sparse as sp
+    from thermoelasticity_fem_b200.multilevel import cycle_masks, row_owner
+    rng = np.random.default_rng(7 + world)
+    g = 5                                                    # 5 x 5 x 5 aggregates, 27-point coupling
+    n1 = g ** 3
+    ijk = np.stack(np.meshgrid(np.arange(g), np.arange(g), np.arange(g), indexing="ij"), axis=-1).reshape(-1, 3)
+    near = np.abs(ijk[:, None, :] - ijk[None, :, :]).max(axis=2) <= 1
+    pat = sp.csr_array(np.kron(near, np.ones((2, 2))))       # pseudo-node pattern, 2 per aggregate
+    rowptr1 = torch.from_numpy(pat.indptr.astype(np.int32))
+    colidx1 = torch.from_numpy(pat.indices.astype(np.int32))
+    A = sp.bsr_array((0.05 * rng.standard_normal((pat.nnz, 4, 4)), pat.indices, pat.indptr), shape=(8 * n1, 8 * n1)).tocsr()
+    A = A + sp.identity(8 * n1, format="csr")
+    agg2 = ((ijk[:, 0] // 3) * 2 + ijk[:, 1] // 3) * 2 + ijk[:, 2] // 3
+    n2 = int(agg2.max()) + 1
+    P2 = sp.csr_array((np.ones(8 * n1), (np.arange(8 * n1), 8 * np.repeat(agg2, 8) + np.tile(np.arange(8), n1))), shape=(8 * n1, 8 * n2))
+    inv2 = np.linalg.inv((P2.T @ A @ P2).toarray())
+    # fine nodes: slabs along x that do NOT line up with the coarse row partition
+    fine_rank_of_agg = [set(int(q) for q in rng.integers(0, world, size=2)) for _ in range(n1)]
+    agg_ranks = torch.tensor([sum(1 << q for q in s) for s in fine_rank_of_agg], dtype=torch.uint8)
+    x_mask, t_mask = cycle_masks(rowptr1, colidx1, n1, agg2, n2, agg_ranks, world)
+    xm, tm = x_mask.numpy(), t_mask.numpy()
+    own1, own2 = row_owner(n1, world).numpy(), row_owner(n2, world).numpy()
+    wc = 0.7
+    bc = rng.standard_normal(8 * n1)
+    # one-piece cycle
+    x = wc * bc
+    x = x + wc * (bc - A @ x)
+    t = bc - A @ x
+    x = x + wc * t + P2 @ (inv2 @ (P2.T @ t))
+    for _ in range(3):
+        x = x + wc * (bc - A @ x)
+    # partitioned emulation
+    rows_of = [np.flatnonzero(np.repeat(own1, 8) == q) for q in range(world)]
+    rows2_of = [np.flatnonzero(np.repeat(own2, 8) == q) for q in range(world)]
+
+    def publish(values_by_rank, mask, n):
+        reps = [np.full(8 * n, np.nan) for _ in range(world)]
+        for q in range(world):
+            for dst in range(world):
+                sel = rows_of[q] if n == n1 else rows2_of[q]
+                if mask is not None:
+                    sel = sel[((mask[sel // 8] >> dst) & 1).astype(bool)]
+                reps[dst][sel] = values_by_rank[q][sel]
+        return reps
+
+    def full(vals_rows):                                      # rank q computed only its rows
+        out = [np.zeros(8 * n1) for _ in range(world)]
+        for q in range(world):
+            out[q][rows_of[q]] = vals_rows[q]
+        return out
+
+    def sweep(reps, extra=None):
+        outs = []
+        for q in range(world):
+            r = rows_of[q]
+            Ax = A[r] @ np.where(np.isnan(reps[q]), np.nan, reps[q])     # NaN propagates if an unsent value is read
+            cols = np.unique(A[r].indices)
+            assert not np.isnan(reps[q][cols]).any(), "a level-1 row reads a value that was not sent to its rank"
+            outs.append(Ax)
+        return outs
+
+    X = publish(full([wc * bc[rows_of[q]] for q in range(world)]), xm, n1)
+    Ax = sweep(X)
+    X = publish(full([X[q][rows_of[q]] + wc * (bc[rows_of[q]] - Ax[q]) for q in range(world)]), xm, n1)
+    Ax = sweep(X)
+    T = publish(full([bc[rows_of[q]] - Ax[q] for q in range(world)]), tm, n1)
+    r2_rows = []
+    for q in range(world):
+        r = rows2_of[q]
+        cols = np.unique(P2.T.tocsr()[r].indices)
+        assert not np.isnan(T[q][cols]).any(), "P2^T reads a residual row that was not sent to the level-2 owner"
+        r2_rows.append(P2.T.tocsr()[r] @ T[q])
+    r2 = np.zeros(8 * n2)
+    for q in range(world):
+        r2[rows2_of[q]] = r2_rows[q]                          # r2 and x2 go to every rank
+    x2 = inv2 @ r2
+    new = []
+    for q in range(world):
+        r = rows_of[q]
+        assert not np.isnan(T[q][r]).any() and not np.isnan(X[q][r]).any()
+        new.append(X[q][r] + wc * T[q][r] + P2[r] @ x2)
+    X = publish(full(new), xm, n1)
+    for _ in range(3):
+        Ax = sweep(X)
+        X = publish(full([X[q][rows_of[q]] + wc * (bc[rows_of[q]] - Ax[q]) for q in range(world)]), xm, n1)
+    for q in range(world):
+        r = rows_of[q]
+        assert np.abs(X[q][r] - x[r]).max() <= 1e-12 * np.abs(x).max()
+        need = np.flatnonzero(np.repeat(np.array([q in s for s in fine_rank_of_agg]), 8))     # prolongation reads
+        assert not np.isnan(X[q][need]).any(), "the prolongation reads a coarse value that was not sent to its rank"
+        assert np.abs(X[q][need] - x[need]).max() <= 1e-12 * np.abs(x).max()

@@ -456,6 +456,17 @@ def test_aggregation_preconditioner_apply_matches_host_restatement():
     pc3.apply(torch.from_numpy(r).cuda(), z3)
     zc = cycle_host("classic")
     assert np.abs(z3.cpu().numpy() - zc).max() <= 1e-11 * np.abs(zc).max()
+    # the persistent row-partitioned dataflow kernel of the coarse cycle (the multi-GPU default) on one GPU
+    for kind, zref, zdev in (("overlapped", z_host, z), ("classic", zc, z3)):
+        pcp = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10, cycle=kind, coarse="persistent")
+        assert pcp.coarse == "persistent" and pc.coarse == "launches"
+        zp = torch.empty_like(z)
+        for _ in range(3):                 # repeated applications: barrier counters and epochs advance
+            zp.zero_()
+            pcp.apply(torch.from_numpy(r).cuda(), zp)
+            torch.cuda.synchronize()
+            assert np.abs(zp.cpu().numpy() - zref).max() <= 1e-11 * np.abs(zref).max()
+        assert np.abs((zp - zdev).cpu().numpy()).max() <= 1e-11 * np.abs(zref).max()
     # the same with the level-1 operator kept in single precision
     pc2 = TwoLevelPreconditioner(ss.dm, ss.sys, factor1=2.0, factor2=0.0, dense_limit=10, level1_dtype="fp32")
     assert pc.level1_dtype == "fp16" and pc2.level1_dtype == "fp32"

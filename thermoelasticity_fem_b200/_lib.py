@@ -41,6 +41,7 @@ _SIGNATURES = {
     "tefem_solver_profile": [P, c_int, P, P],
     "tefem_solver_halo_exchange": [P, P, P],
     "tefem_solver_set_precond": [P, P],
+    "tefem_solver_set_interior_range": [P, c_int32, c_int32, c_int],
     "tefem_precond_create": [P, c_int32, c_int32, P, P, P, P, c_double, P, P, P, P, c_double, c_int, c_int, c_int32, P, P, P, P, P, P,
                              P, P, P],
     "tefem_precond_destroy": [P],
@@ -49,6 +50,8 @@ _SIGNATURES = {
     "tefem_precond_set_agg_ranks": [P, P],
     "tefem_precond_set_level1_half": [P, P],
     "tefem_precond_set_cycle": [P, c_int],
+    "tefem_precond_set_coarse_mode": [P, c_int, P],
+    "tefem_precond_set_cycle_masks": [P, P, P],
     "tefem_bicgstab": [P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_cg": [P, P, P, P, P, P, P, c_double, c_int, c_int, c_double, P, P],
     "tefem_newmark_predict": [c_int64, P, P, P, c_double, c_double, c_double, P, P, P, P],
@@ -70,7 +73,9 @@ _SIGNATURES = {
     "tefem_solver_peer_slots": [],
 }
 _RESTYPES = {"tefem_solver_work_doubles": (c_int64, [c_int32, c_int32]), "tefem_launch_count": (c_int64, []),
-             "tefem_precond_work_doubles": (c_int64, [c_int32, c_int32])}
+             "tefem_precond_work_doubles": (c_int64, [c_int32, c_int32]),
+             "tefem_precond_peer_doubles": (c_int64, [c_int32, c_int32, c_int, c_int]),
+             "tefem_precond_cycle_doubles": (c_int64, [c_int32, c_int32, c_int, c_int])}
 
 _lib = None
 

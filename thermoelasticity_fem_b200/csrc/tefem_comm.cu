@@ -73,7 +73,7 @@ struct tefem_comm {
     char* shm_local = nullptr;
     char* shm_base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t shm_cap = 0;
-    uint32_t epoch[PEER_N_CHANNELS] = {0, 0, 0};
+    uint32_t epoch[PEER_N_CHANNELS] = {0, 0, 0, 0};
     int* d_err = nullptr;
     long long timeout = PEER_TIMEOUT_DEFAULT;
     // peer-mapped vector slots (SpMV inputs whose halo tails the neighbours write directly, tefem_krylov.cu)

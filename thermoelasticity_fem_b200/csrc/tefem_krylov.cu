@@ -64,14 +64,19 @@ __device__ __forceinline__ void ld256_x(const double* p, double& a, double& b, d
 // split by field (u rows r < 3, theta rows r == 3).
 // rows: optional list of node rows (interior / boundary split), else rows [0, n_rows).
 // The grid-stride row loop of the SpMV; d[] receives this thread's dot-product contributions.
-template <int DOTS, int UNROLL>
+__device__ __forceinline__ void ld256_cg(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// XCG: x is read through L2 only (rows whose columns another GPU writes WHILE the kernel runs: spmv_fused_halo_kernel)
+template <int DOTS, int UNROLL, bool XCG = false>
 __device__ __forceinline__ void spmv_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                           const int32_t* __restrict__ rows, int32_t n_rows, const double* __restrict__ sys,
                                           const double* __restrict__ x, double* __restrict__ y,
-                                          const double* __restrict__ w, const double* __restrict__ sd, double (&d)[5]) {
+                                          const double* __restrict__ w, const double* __restrict__ sd, double (&d)[5],
+                                          int32_t row0 = 0) {
     const int64_t n = 4 * (int64_t)n_rows;
     for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t i = rows ? rows[tid >> 2] : (int32_t)(tid >> 2);
+        const int32_t i = rows ? rows[tid >> 2] : row0 + (int32_t)(tid >> 2);
         const int r = (int)(tid & 3);
         const int32_t s = rowptr[i], t = rowptr[i + 1];
         double acc0 = 0.0, acc1 = 0.0;
@@ -85,7 +90,10 @@ __device__ __forceinline__ void spmv_rows(const int32_t* __restrict__ rowptr, co
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) ld256(sys + 16 * (int64_t)(p + u) + 4 * r, a[u][0], a[u][1], a[u][2], a[u][3]);
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) ld256_x(x + 4 * (int64_t)j[u], v[u][0], v[u][1], v[u][2], v[u][3]);
+            for (int u = 0; u < UNROLL; ++u) {
+                if (XCG) ld256_cg(x + 4 * (int64_t)j[u], v[u][0], v[u][1], v[u][2], v[u][3]);
+                else ld256_x(x + 4 * (int64_t)j[u], v[u][0], v[u][1], v[u][2], v[u][3]);
+            }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const double c = a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2] + a[u][3] * v[u][3];
@@ -95,7 +103,8 @@ __device__ __forceinline__ void spmv_rows(const int32_t* __restrict__ rowptr, co
         for (; p < t; ++p) {
             double a0, a1, a2, a3, x0, x1, x2, x3;
             ld256(sys + 16 * (int64_t)p + 4 * r, a0, a1, a2, a3);
-            ld256_x(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
+            if (XCG) ld256_cg(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
+            else ld256_x(x + 4 * (int64_t)colidx[p], x0, x1, x2, x3);
             acc0 += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
         }
         const double yv = acc0 + acc1;
@@ -211,6 +220,57 @@ __global__ void __launch_bounds__(256) push_halo_kernel(int64_t n, const int32_t
                 if (q < hf.n) st_release_sys(hf.theirs[q], hf.epoch);
         }
     }
+}
+
+// SpMV FUSED WITH ITS HALO EXCHANGE (default multi-GPU form): one kernel is producer and consumer.  The first CTAs store
+// this rank's boundary values of x into the neighbours' copies of the vector (as push_halo_kernel) and the one that takes
+// the last ticket raises the flags; then every CTA multiplies the INTERIOR rows [lo, hi) - rows without halo columns, a
+// contiguous range for row blocks in node order - and only then waits for the neighbours' flags and multiplies the
+// boundary rows [0, lo) and [hi, n_rows): the NVLink transfer and the skew between the ranks hide behind the interior rows,
+// and the separate push launch is gone.
+struct HaloPush {
+    int64_t n = 0;
+    const int32_t *idx = nullptr, *dst = nullptr, *dpos = nullptr;
+    HaloSlots slots;
+    int* ticket = nullptr;
+    int n_ctas = 0;              // CTAs that push (and take a ticket)
+    int32_t lo = 0, hi = 0;      // interior rows
+};
+template <int DOTS, int UNROLL>
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_MIN_CTAS) spmv_fused_halo_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t n_rows, const double* __restrict__ sys,
+    const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ w, const double* __restrict__ sd,
+    double* __restrict__ partials, const int* __restrict__ ictl, const HaloFlags hf, const HaloPush hp) {
+    __shared__ double red[8 * 32];
+    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const bool active = (ictl == nullptr) || (ictl[IN_STOP] == 0);
+    if (active) {
+        if ((int)blockIdx.x < hp.n_ctas) {
+            for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < hp.n; k += (int64_t)hp.n_ctas * blockDim.x) {
+                double a, b, c, e;
+                ld256_x(x + 4 * (int64_t)hp.idx[k], a, b, c, e);
+                double* o = hp.slots.base[hp.dst[k]] + 4 * (int64_t)hp.dpos[k];
+                asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(a), "d"(b), "d"(c), "d"(e) : "memory");
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int t = atomicAdd(hp.ticket, 1);
+                if (t == hp.n_ctas - 1) {
+                    *hp.ticket = 0;
+                    __threadfence_system();
+#pragma unroll
+                    for (int q = 0; q < PEER_MAX_RANKS; ++q)
+                        if (q < hf.n) st_release_sys(hf.theirs[q], hf.epoch);
+                }
+            }
+        }
+        spmv_rows<DOTS, UNROLL>(rowptr, colidx, nullptr, hp.hi - hp.lo, sys, x, y, w, sd, d, hp.lo);
+        halo_wait(hf);
+        spmv_rows<DOTS, UNROLL, true>(rowptr, colidx, nullptr, hp.lo, sys, x, y, w, sd, d, 0);
+        spmv_rows<DOTS, UNROLL, true>(rowptr, colidx, nullptr, n_rows - hp.hi, sys, x, y, w, sd, d, hp.hi);
+    }
+    spmv_store_partials<DOTS>(d, red, partials);
 }
 
 // Consumer of a push outside the SpMV (tefem_solver_halo_exchange): waits for the neighbours' flags and copies the halo
@@ -738,6 +798,8 @@ struct tefem_solver {
     int32_t n_boundary_rows = 0;
     const int32_t* interior_rows = nullptr;
     int32_t n_interior_rows = 0;
+    bool fused_halo = true;                  // peer halo: the SpMV kernel pushes the boundary values itself
+    int32_t interior_lo = 0, interior_hi = 0;   // rows [lo, hi) have no halo column (tefem_solver_set_interior_range)
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
     // optional SpMV timing (bench.py roofline): event pairs around every SpMV launch, harvested at the
@@ -907,6 +969,15 @@ extern "C" int tefem_solver_set_halo(tefem_solver* s, int32_t n_halo, int n_nbr,
     return TEFEM_OK;
 }
 
+// Peer-memory halo: rows [lo, hi) have no halo column (a contiguous interior range; lo == hi: none known) - the fused
+// SpMV multiplies them before it waits for the neighbours.  fused = 0 restores the separate push launch (comparison).
+extern "C" int tefem_solver_set_interior_range(tefem_solver* s, int32_t lo, int32_t hi, int fused) {
+    TEFEM_REQUIRE(s && lo >= 0 && lo <= hi && hi <= s->n_rows, "0 <= lo <= hi <= n_rows");
+    s->interior_lo = lo; s->interior_hi = hi;
+    s->fused_halo = fused != 0;
+    return TEFEM_OK;
+}
+
 static int grid_for(int64_t n_threads, int per_cta) {
     int64_t g = ceil_div(n_threads, per_cta);
     if (g > MAX_PARTIAL_CTAS) g = MAX_PARTIAL_CTAS;
@@ -977,9 +1048,8 @@ static int launch_spmv(const int32_t* rowptr, const int32_t* colidx, const int32
     return launch_spmv_u<DOTS, 2, false>(c, rowptr, colidx, rows, n_rows, sys, x, y, w, sd, partials, ictl, n_cta_out, h, st);
 }
 
-// Peer-memory halo, producer side: push the boundary values of slot vector x (one of this rank's slots) into the same
-// slot of the neighbours and raise the flags of a new exchange, whose context is returned for the consumer.
-static int push_halo(tefem_solver* s, const double* x, const int* ictl, SpmvHalo* h, cudaStream_t st) {
+// Flags and slot addresses of the next halo exchange of slot vector x.
+static int halo_context(tefem_solver* s, const double* x, SpmvHalo* h, HaloSlots* hs) {
     const int me = tefem_comm_rank(s->comm);
     const int64_t off = x - tefem_comm_slot(s->comm, me, 0);
     TEFEM_REQUIRE(off >= 0 && off % tefem_comm_slot_doubles(s->comm) == 0 &&
@@ -993,12 +1063,53 @@ static int push_halo(tefem_solver* s, const double* x, const int* ictl, SpmvHalo
         h->hf.mine[k] = peer_flag(pc, pc.rank, s->nbr[k]);
         h->hf.theirs[k] = peer_flag(pc, s->nbr[k], pc.rank);
     }
+    for (int r = 0; r < tefem_comm_world(s->comm); ++r) hs->base[r] = tefem_comm_slot(s->comm, r, slot);
+    return TEFEM_OK;
+}
+
+// Peer-memory halo, fused form: ONE launch pushes this rank's boundary values, multiplies the interior rows, waits for the
+// neighbours and multiplies the boundary rows (spmv_fused_halo_kernel).
+template <int DOTS>
+static int launch_spmv_fused(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys, const double* x,
+                             double* y, const double* w, const double* sd, const int* ictl, int* n_cta_out, cudaStream_t st);
+
+// Peer-memory halo, producer side: push the boundary values of slot vector x (one of this rank's slots) into the same
+// slot of the neighbours and raise the flags of a new exchange, whose context is returned for the consumer.
+static int push_halo(tefem_solver* s, const double* x, const int* ictl, SpmvHalo* h, cudaStream_t st) {
     HaloSlots hs;
-    for (int r = 0; r < tefem_comm_world(s->comm); ++r) hs.base[r] = tefem_comm_slot(s->comm, r, slot);
+    int rc = halo_context(s, x, h, &hs);
+    if (rc) return rc;
     const int64_t n_send = s->send_ptr[s->n_nbr];
     const unsigned g = (unsigned)(n_send > 0 ? ceil_div(n_send, 256) : 1);
     push_halo_kernel<<<g, 256, 0, st>>>(n_send, s->send_idx, s->send_dst, s->send_dpos, x, hs, h->hf, ictl,
                                         s->ictl + IN_TICKET);
+    TEFEM_LAUNCH_CHECK();
+    return TEFEM_OK;
+}
+
+template <int DOTS>
+static int launch_spmv_fused(tefem_solver* s, const int32_t* rowptr, const int32_t* colidx, const double* sys, const double* x,
+                             double* y, const double* w, const double* sd, const int* ictl, int* n_cta_out, cudaStream_t st) {
+    SpmvHalo h;
+    HaloPush hp;
+    int rc = halo_context(s, x, &h, &hp.slots);
+    if (rc) return rc;
+    int resident = 0;
+    rc = spmv_resident_ctas<DOTS, 2, true>(SPMV_THREADS, &resident);     // same register budget as the HALO instantiation
+    if (rc) return rc;
+    if (resident > MAX_PARTIAL_CTAS) resident = MAX_PARTIAL_CTAS;
+    int64_t g64 = ceil_div(4 * (int64_t)s->n_rows, SPMV_THREADS);
+    if (g64 > resident) g64 = resident;
+    const int g = g64 < 1 ? 1 : (int)g64;
+    if (n_cta_out) *n_cta_out = g;
+    hp.n = s->send_ptr[s->n_nbr];
+    hp.idx = s->send_idx; hp.dst = s->send_dst; hp.dpos = s->send_dpos;
+    hp.ticket = s->ictl + IN_TICKET;
+    int64_t pc = ceil_div(hp.n > 0 ? hp.n : 1, SPMV_THREADS);
+    hp.n_ctas = (int)(pc > g ? g : pc);                                  // >= 1: an empty send list still raises the flags
+    hp.lo = s->interior_lo; hp.hi = s->interior_hi;
+    spmv_fused_halo_kernel<DOTS, 2><<<g, SPMV_THREADS, 0, st>>>(rowptr, colidx, s->n_rows, sys, x, y, w, sd ? sd : x, s->partials, ictl,
+                                                                h.hf, hp);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
@@ -1040,6 +1151,11 @@ static int dist_spmv(tefem_solver* s, const int32_t* rowptr, const int32_t* coli
     }
     int rc = prof_begin(s, st);
     if (rc) return rc;
+    if (s->peer_halo && s->fused_halo) {
+        rc = launch_spmv_fused<DOTS>(s, rowptr, colidx, sys, x, y, w, sd, ictl, n_part_ctas, st);
+        if (rc) return rc;
+        return prof_end(s, st);
+    }
     if (s->peer_halo) {
         SpmvHalo h;
         rc = push_halo(s, x, ictl, &h, st);

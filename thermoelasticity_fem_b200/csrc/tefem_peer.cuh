@@ -20,13 +20,13 @@ namespace tefem {
 
 constexpr int PEER_MAX_RANKS = 8;
 constexpr int PEER_SMALL = 16;                       // doubles per small packet
-constexpr int64_t PEER_FLAG_BYTES = 1024;            // 3 channels x 2 parities x 8 ranks x 4 B, padded
+constexpr int64_t PEER_FLAG_BYTES = 1024;            // 4 channels x 2 parities x 8 ranks x 4 B, padded
 constexpr int64_t PEER_SMALL_BYTES = 2 * PEER_SMALL * 8;
 constexpr int64_t PEER_BIG_OFFSET = 2048;
 constexpr long long PEER_TIMEOUT_DEFAULT = 60000000000LL;     // ~30 s at 1.9 GHz (tefem_comm_set_timeout overrides it)
 
 // channels: dot-product packets, restricted residual of the coarse correction, halo values of the SpMV input
-enum { PEER_CH_DOTS = 0, PEER_CH_COARSE = 1, PEER_CH_HALO = 2, PEER_N_CHANNELS = 3 };
+enum { PEER_CH_DOTS = 0, PEER_CH_COARSE = 1, PEER_CH_HALO = 2, PEER_CH_CYCLE = 3, PEER_N_CHANNELS = 4 };
 
 struct PeerCtx {
     int world = 1, rank = 0;

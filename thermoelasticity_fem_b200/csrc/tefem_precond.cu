@@ -34,16 +34,26 @@
 namespace tefem {
 
 // rc[8I + 0..3] = sum_i r_i ; rc[8I + 4..6] = sum_i d_i x r_u,i ; rc[8I + 7] = 0 over the nodes i of aggregate I
-// (d_i = offset from the aggregate's centre, single precision); one warp per aggregate, fixed shuffle tree.
-__global__ void __launch_bounds__(256) restrict_kernel(int32_t n_agg, const int32_t* __restrict__ agg_ptr,
-                                                       const int32_t* __restrict__ agg_nodes,
-                                                       const float4* __restrict__ node_off,
-                                                       const double* __restrict__ r, double* __restrict__ rc) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n_agg) return;
-    const int32_t s = agg_ptr[warp], t = agg_ptr[warp + 1];
+// (d_i = offset from the aggregate's centre, single precision).  One CTA of 128 threads per aggregate (a cube of 8 h has
+// ~500 nodes: four trips of dependent loads instead of the sixteen of a single warp, which made this pass latency bound:
+// 24 us for 0.9 M nodes on one of eight GPUs); thread-strided partial sums, fixed shuffle tree, the four warp sums added
+// in warp order.  An aggregate without local nodes (most of them in a multi-GPU solve) writes zeros and leaves.
+constexpr int RESTRICT_THREADS = 128;
+__global__ void __launch_bounds__(RESTRICT_THREADS) restrict_kernel(int32_t n_agg, const int32_t* __restrict__ agg_ptr,
+                                                                    const int32_t* __restrict__ agg_nodes,
+                                                                    const float4* __restrict__ node_off,
+                                                                    const double* __restrict__ r, double* __restrict__ rc) {
+    __shared__ double part[RESTRICT_THREADS / 32][8];
+    const int agg = (int)blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (agg >= n_agg) return;
+    const int32_t s = agg_ptr[agg], t = agg_ptr[agg + 1];
+    double* o = rc + 8 * (int64_t)agg;
+    if (s == t) {
+        if (threadIdx.x < 8) o[threadIdx.x] = 0.0;
+        return;
+    }
     double a[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int32_t k = s + lane; k < t; k += 32) {
+    for (int32_t k = s + (int32_t)threadIdx.x; k < t; k += RESTRICT_THREADS) {
         const int32_t i = agg_nodes[k];
         const double* v = r + 4 * (int64_t)i;
         const float4 d = node_off[i];
@@ -58,9 +68,16 @@ __global__ void __launch_bounds__(256) restrict_kernel(int32_t n_agg, const int3
 #pragma unroll
         for (int k = 0; k < 7; ++k) a[k] += __shfl_down_sync(0xffffffffu, a[k], off);
     if (lane == 0) {
-        double* o = rc + 8 * (int64_t)warp;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) o[k] = a[k];
+        for (int k = 0; k < 7; ++k) part[warp][k] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double v = part[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < RESTRICT_THREADS / 32; ++w) v += part[w][threadIdx.x];
+        o[threadIdx.x] = v;
+    } else if (threadIdx.x == 7) {
         o[7] = 0.0;
     }
 }
@@ -240,6 +257,359 @@ __global__ void __launch_bounds__(128) dense_matvec_kernel(int32_t n, const floa
 // launches at 150^3 on one GPU, 0.26 against 0.15 ms on two: a grid-wide barrier costs as much as a kernel boundary here
 // and the fine-level passes lose their occupancy.  Removed; numbers in profiles/README.md.)
 
+// ---- ROW-PARTITIONED coarse cycle: one persistent DATAFLOW kernel per application, vectors exchanged over peer memory ----
+//
+// The replicated cycle above is ~10 dependent launches of ~10 - 14 us each on EVERY rank, whatever the number of GPUs: at
+// 8 GPUs it was 29 % of a BiCGSTAB iteration and the first limit of strong scaling (profiles/README.md).  Here the rows of
+// levels 1 and 2 are PARTITIONED: rank q owns the aggregates [n1 q / world, n1 (q + 1) / world) (both pseudo nodes) and
+// the scalar rows [n q / world, ..) of the dense level-2 inverse.  Every coarse vector of the cycle has its own buffer
+// (one per phase: nothing is overwritten inside an application) with one REPLICA per rank in the peer-mapped region, in a
+// SELF-VALIDATING layout: a double is stored as the 16 bytes {low word, tag, high word, tag} (two 8-byte units, each
+// written atomically), where tag = 32 * application + vector number.  The rank that owns a row computes it - lane mapping
+// and summation order of coarse_spmv_kernel - and stores it into all replicas (256-bit stores, remote ones over NVLink);
+// a consumer loads the 16 bytes and simply retries until both tags match.  There is NO barrier and NO fence inside the
+// kernel: a phase starts on a row as soon as the values that row reads have arrived, so the latency of an application is
+// its dependency chain (one NVLink store + one L2 read per level-1 product), not ten grid-wide synchronisations.
+// (First version of this kernel: flag barriers over all CTAs of all ranks between the phases - a system fence after remote
+// stores, a ticket, a flag store, a poll: ~12 us per phase, SLOWER than the separate launches; profiles/README.md.)
+// A value has exactly one producer, so the replicas are bitwise identical and so are the stop decisions of the ranks.
+// Waits are bounded like every peer wait.  All CTAs must be co-resident (consumers spin on producers of the same grid):
+// grid <= the occupancy limit of the device.  Before the first phase the kernel exchanges one flag per rank pair:
+// every rank's restriction has finished and no rank still reads the buffers of the previous application.
+// world == 1 runs the same kernel on local buffers.
+constexpr int CYC_THREADS = 256;
+constexpr int CYC_MAX_X = 24;            // vector numbers: level-1 iterates 0 .. CYC_MAX_X - 1, then t, x2, bc, r2
+enum { CYC_V_T = 24, CYC_V_X2 = 25, CYC_V_BC = 26, CYC_V_R2 = 27 };
+
+struct CycleArgs {
+    const int32_t *rowptr1, *colidx1;
+    const void* sys1;                    // float or __half blocks (template parameter)
+    const double* dinv1;
+    const uint8_t* agg_ranks;
+    const int32_t *r2_rowptr, *r2_colidx, *p2_rowptr, *p2_colidx;
+    const float *r2_vals, *p2_vals, *inv2;
+    int32_t n1, n2, a0, a1;              // own aggregates [a0, a1)
+    double wc;
+    int n_pre, n_post, overlap;
+    int world, rank;
+    const double* rc[PEER_MAX_RANKS];    // the ranks' partial restricted residuals (world == 1: the local one)
+    uint4* X[PEER_MAX_RANKS];            // tagged vectors of rank r: iterate k at k * vec_units, t at m, x2 at m + 1, r2 after x2 (m = n_iterates)
+    uint4* bc;                           // local tagged vector: D1^-1 rc on the own rows
+    const uint8_t *x_mask, *t_mask;      // per aggregate: the ranks that read its level-1 iterates / its residual t (null: all)
+    int32_t j0, j1;                      // own level-2 aggregates: rows of P2^T and of the dense inverse
+    int64_t a2_units;                    // 16-byte units of a level-2 vector
+    int64_t vec_units;                   // 16-byte units between consecutive vectors
+    int n_iterates;
+    uint32_t* flags[PEER_MAX_RANKS];     // flags[r][src]: rank src's start flag in rank r's region
+    uint32_t tag_base;                   // 32 * application
+    int* err;
+    long long timeout;
+    unsigned long long* stamps;          // diagnostics (TEFEM_PROFILE_PRECOND=1): globaltimer of CTA 0 after each phase, or null
+};
+
+__device__ __forceinline__ void cyc_stamp(const CycleArgs& a, int k) {
+    if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.stamps[k] = t;
+    }
+}
+
+// ---- tagged ("LL") doubles: {lo, tag, hi, tag} ----
+__device__ __forceinline__ unsigned long long ll_pack(uint32_t w, uint32_t tag) { return (unsigned long long)w | ((unsigned long long)tag << 32); }
+__device__ __forceinline__ void ll_store1(uint4* p, uint32_t tag, double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(ll_pack((uint32_t)b, tag)), "l"(ll_pack((uint32_t)(b >> 32), tag)) : "memory");
+}
+__device__ __forceinline__ void ll_store4(uint4* p, uint32_t tag, double v0, double v1, double v2, double v3) {
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0), b1 = (unsigned long long)__double_as_longlong(v1);
+    const unsigned long long b2 = (unsigned long long)__double_as_longlong(v2), b3 = (unsigned long long)__double_as_longlong(v3);
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(ll_pack((uint32_t)b0, tag)), "l"(ll_pack((uint32_t)(b0 >> 32), tag)),
+                 "l"(ll_pack((uint32_t)b1, tag)), "l"(ll_pack((uint32_t)(b1 >> 32), tag)) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p + 2), "l"(ll_pack((uint32_t)b2, tag)), "l"(ll_pack((uint32_t)(b2 >> 32), tag)),
+                 "l"(ll_pack((uint32_t)b3, tag)), "l"(ll_pack((uint32_t)(b3 >> 32), tag)) : "memory");
+}
+__device__ __forceinline__ uint4 ll_ld(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// two consecutive values with ONE 256-bit load (p 32-byte aligned)
+__device__ __forceinline__ void ll_ld2(const uint4* p, uint4& v0, uint4& v1) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+    v0 = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+    v1 = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+}
+__device__ __forceinline__ double ll_value(const uint4& v) { return __hiloint2double((int)v.z, (int)v.x); }
+template <int N>
+__device__ __forceinline__ bool ll_try(const uint4* p, uint32_t tag, uint4 (&v)[N]) {
+    bool ok = true;
+    if (N == 1) {
+        v[0] = ll_ld(p);
+    } else {
+#pragma unroll
+        for (int k = 0; k + 1 < N; k += 2) ll_ld2(p + k, v[k], v[k + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) ok = ok && v[k].y == tag && v[k].w == tag;
+    return ok;
+}
+// Spin until the tags of N (1 or even; p 32-byte aligned for N > 1) consecutive values match.  Bounded: a time-out marks
+// the communicator failed and later waits give up at once.  (A __nanosleep(40) between retries cost ~1 us per wait:
+// measured slower, profiles/README.md.)
+template <int N>
+__device__ __forceinline__ void ll_load(const uint4* p, uint32_t tag, double (&out)[N], int* err, long long timeout) {
+    static_assert(N == 1 || (N & 1) == 0, "1 or an even number of values");
+    uint4 v[N];
+    if (!ll_try<N>(p, tag, v)) {
+        const long long t0 = clock64();
+        for (;;) {
+            if (ll_try<N>(p, tag, v)) break;
+            if (*reinterpret_cast<volatile int*>(err)) break;
+            if (clock64() - t0 > timeout) { *err = 1; break; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = ll_value(v[k]);
+}
+
+// A tagged vector as the kernel sees it: the local replica to read, and (for outputs) the unit offset inside every rank's region.
+struct CycVec {
+    const uint4* rd;      // local replica
+    int64_t off;          // offset (units) from CycleArgs::X[r]; < 0: local-only vector, written through `wr`
+    uint4* wr;
+    uint32_t tag;
+};
+
+// out = c0 * xin + c1 * (cb * b - A x) on the block rows [r0, r1) of a 4x4-block CSR operator, stored into the n_dst
+// replicas of out.  One WARP per block row; lane l multiplies the blocks s + l, s + l + 32, ... - two trips (64 blocks, a
+// whole level-1 row) are in flight together, so a row costs one chain row pointer -> column indices -> {blocks, x} whatever
+// its length; the lanes that store first fetch xin and b (available before x); fixed shuffle tree; lane q < n_dst writes the
+// row's four values into replica q.  (The sum order differs from coarse_spmv_kernel's 16-lane mapping in the last bits: the
+// replicas of the ranks are identical by construction - one producer per value - not identical to the single-GPU cycle.)
+constexpr int CYC_LANES = 32;
+
+template <typename VT>
+__device__ __forceinline__ void cyc_block_fma(const VT* __restrict__ sys, int32_t p, const double (&u)[4], double& a0, double& a1,
+                                              double& a2, double& a3) {
+    float4 q0, q1, q2, q3;
+    load_block16(sys, (int64_t)p, q0, q1, q2, q3);
+    a0 += (double)q0.x * u[0] + (double)q0.y * u[1] + (double)q0.z * u[2] + (double)q0.w * u[3];
+    a1 += (double)q1.x * u[0] + (double)q1.y * u[1] + (double)q1.z * u[2] + (double)q1.w * u[3];
+    a2 += (double)q2.x * u[0] + (double)q2.y * u[1] + (double)q2.z * u[2] + (double)q2.w * u[3];
+    a3 += (double)q3.x * u[0] + (double)q3.y * u[1] + (double)q3.z * u[2] + (double)q3.w * u[3];
+}
+
+template <typename VT>
+__device__ __forceinline__ void cyc_rows(const CycleArgs& a, uint4* const* reps, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ colidx, const VT* __restrict__ sys, int32_t r0, int32_t r1,
+                                         const CycVec& x, const CycVec* b, const CycVec* xin, double c0, double c1, double cb,
+                                         const CycVec& out, int n_dst, const uint8_t* __restrict__ dst_mask) {
+    const int32_t gid = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int32_t group = gid / CYC_LANES, n_groups = (int32_t)(gridDim.x * blockDim.x) / CYC_LANES;
+    const int l = gid % CYC_LANES;
+    for (int32_t base = r0; base < r1; base += n_groups) {          // uniform trip count: all lanes reach the shuffles
+        const int32_t i = base + group;
+        const bool live = i < r1;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double o[4] = {0.0, 0.0, 0.0, 0.0}, bb[4] = {0.0, 0.0, 0.0, 0.0};
+        bool writes = false;
+        if (live) {
+            const int32_t s = rowptr[i], t = rowptr[i + 1];
+            for (int32_t p = s + l; p < t; p += 2 * CYC_LANES) {
+                const int32_t p2 = p + CYC_LANES;
+                const bool two = p2 < t;
+                const int32_t j = colidx[p], j2 = two ? colidx[p2] : 0;
+                double u[4], u2[4];
+                ll_load<4>(x.rd + 4 * (int64_t)j, x.tag, u, a.err, a.timeout);
+                if (two) ll_load<4>(x.rd + 4 * (int64_t)j2, x.tag, u2, a.err, a.timeout);
+                cyc_block_fma<VT>(sys, p, u, a0, a1, a2, a3);
+                if (two) cyc_block_fma<VT>(sys, p2, u2, a0, a1, a2, a3);
+            }
+            // lane q stores into replica q when rank q reads this row (dst_mask per aggregate = pair of block rows)
+            writes = l < n_dst && (!dst_mask || ((dst_mask[i >> 1] >> l) & 1));
+            if (writes) {
+                const int64_t k = 4 * (int64_t)i;
+                if (xin) {
+                    ll_load<4>(xin->rd + k, xin->tag, o, a.err, a.timeout);
+                    o[0] *= c0; o[1] *= c0; o[2] *= c0; o[3] *= c0;
+                }
+                if (b) {
+                    ll_load<4>(b->rd + k, b->tag, bb, a.err, a.timeout);
+                    bb[0] *= cb; bb[1] *= cb; bb[2] *= cb; bb[3] *= cb;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = CYC_LANES / 2; off > 0; off >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, off);
+            a1 += __shfl_down_sync(0xffffffffu, a1, off);
+            a2 += __shfl_down_sync(0xffffffffu, a2, off);
+            a3 += __shfl_down_sync(0xffffffffu, a3, off);
+        }
+        const double s0 = __shfl_sync(0xffffffffu, a0, 0);
+        const double s1 = __shfl_sync(0xffffffffu, a1, 0);
+        const double s2 = __shfl_sync(0xffffffffu, a2, 0);
+        const double s3 = __shfl_sync(0xffffffffu, a3, 0);
+        if (writes) {
+            const int64_t k = 4 * (int64_t)i;
+            uint4* dst = out.off >= 0 ? reps[l] + out.off + k : out.wr + k;
+            ll_store4(dst, out.tag, o[0] + c1 * (bb[0] - s0), o[1] + c1 * (bb[1] - s1), o[2] + c1 * (bb[2] - s2), o[3] + c1 * (bb[3] - s3));
+        }
+    }
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const CycleArgs a) {
+    extern __shared__ double s_r2[];                     // 8 n2 doubles: P2^T t, staged once per CTA for the dense product
+    __shared__ uint4* reps[PEER_MAX_RANKS];
+    const int tid = (int)threadIdx.x;
+    const VT* sys1 = reinterpret_cast<const VT*>(a.sys1);
+    const int me = a.rank;
+    if (tid < PEER_MAX_RANKS) reps[tid] = a.X[tid];
+    // every rank's restriction has finished (its partial sums are visible) and none is still reading a vector of the
+    // previous application (whose buffers this one overwrites)
+    if (a.world > 1) {
+        if (blockIdx.x == 0 && tid < a.world) {
+            __threadfence_system();
+            st_release_sys(a.flags[tid] + a.rank, a.tag_base);
+        }
+        if (tid < a.world) {
+            const uint32_t* f = a.flags[a.rank] + tid;
+            if ((int32_t)(ld_acquire_sys(f) - a.tag_base) < 0 && !*reinterpret_cast<volatile int*>(a.err)) {
+                const long long t0 = clock64();
+                while ((int32_t)(ld_acquire_sys(f) - a.tag_base) < 0) {
+                    if (clock64() - t0 > a.timeout) { *a.err = 1; break; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int stamp = 0;
+    cyc_stamp(a, stamp++);
+    const uint32_t T = a.tag_base + 1u;                  // tag of vector v: T + v
+    const int64_t U = a.vec_units;
+    const uint4* mine = a.X[me];
+    CycVec vbc = {a.bc, -1, a.bc, T + CYC_V_BC};
+    const int64_t off_r2 = (int64_t)(a.n_iterates + 1) * U + a.a2_units;
+    CycVec vr2 = {mine + off_r2, off_r2, nullptr, T + CYC_V_R2};
+    CycVec vt = {mine + (int64_t)a.n_iterates * U, (int64_t)a.n_iterates * U, nullptr, T + CYC_V_T};
+    CycVec vx2 = {mine + (int64_t)(a.n_iterates + 1) * U, (int64_t)(a.n_iterates + 1) * U, nullptr, T + CYC_V_X2};
+    int it = 0;                                          // current level-1 iterate
+    auto iterate = [&](int k) { CycVec v = {mine + (int64_t)k * U, (int64_t)k * U, nullptr, T + (uint32_t)k}; return v; };
+    // phase 0: bc = D1^-1 sum_ranks rc (rank order; only the ranks that own nodes of the aggregate), x_0 = wc bc.
+    // 8 lanes per own aggregate, lane k = row k of the 8x8 block.
+    {
+        const int32_t gid = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+        const int32_t n_groups = (int32_t)(gridDim.x * blockDim.x) >> 3;
+        const int k = gid & 7;
+        for (int32_t i = a.a0 + (gid >> 3); i < a.a1; i += n_groups) {
+            const unsigned mask = (a.world > 1 && a.agg_ranks) ? (unsigned)a.agg_ranks[i] : 0xffu;
+            double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int r = 0; r < a.world; ++r) {
+                if (!((mask >> r) & 1u)) continue;
+                const double* src = a.rc[r] + 8 * (int64_t)i;
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ld_volatile_v2(src + 2 * q, v[2 * q], v[2 * q + 1]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s[q] += v[q];
+            }
+            const double* D = a.dinv1 + 64 * (int64_t)i + 8 * k;
+            double b = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) b += D[c] * s[c];
+            ll_store1(a.bc + 8 * (int64_t)i + k, vbc.tag, b);
+            const double x = a.wc * b;
+            const unsigned xm = a.x_mask ? (unsigned)a.x_mask[i] : 0xffu;
+            for (int r = 0; r < a.world; ++r)
+                if ((xm >> r) & 1u) ll_store1(a.X[r] + 8 * (int64_t)i + k, T, x);
+        }
+    }
+    cyc_stamp(a, stamp++);
+    const int32_t r0 = 2 * a.a0, r1 = 2 * a.a1;           // own pseudo nodes (block rows) of level 1
+    const bool overlap = a.overlap && a.n_pre >= 2;
+    for (int k = 1; k < a.n_pre - (overlap ? 1 : 0); ++k) {                          // x' = x + wc (bc - A1^ x)
+        const CycVec x = iterate(it), xn = iterate(it + 1);
+        cyc_rows<VT>(a, reps, a.rowptr1, a.colidx1, sys1, r0, r1, x, &vbc, &x, 1.0, a.wc, 1.0, xn, a.world, a.x_mask);
+        ++it;
+        cyc_stamp(a, stamp++);
+    }
+    {   // t = bc - A1^ x
+        const CycVec x = iterate(it);
+        cyc_rows<VT>(a, reps, a.rowptr1, a.colidx1, sys1, r0, r1, x, &vbc, nullptr, 0.0, 1.0, 1.0, vt, a.world, a.t_mask);
+    }
+    cyc_stamp(a, stamp++);
+    // r2 = P2^T t on the own level-2 aggregates (their children's t rows were sent here), stored into every replica
+    cyc_rows<float>(a, reps, a.r2_rowptr, a.r2_colidx, a.r2_vals, 2 * a.j0, 2 * a.j1, vt, nullptr, nullptr, 0.0, -1.0, 1.0, vr2, a.world, nullptr);
+    cyc_stamp(a, stamp++);
+    {   // x2 = A2^-1 r2 on the own rows of the dense inverse: r2 staged in shared memory, one warp per row, lane-strided
+        // sums + shuffle tree
+        const int n = 8 * a.n2;
+        const int32_t warp = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+        const int lane = tid & 31;
+        const int32_t q0 = 8 * a.j0, q1 = 8 * a.j1;                                          // own rows of the dense inverse
+        const bool any_row = q0 + (int32_t)((blockIdx.x * blockDim.x) >> 5) < q1;           // uniform over the CTA
+        if (any_row) {
+            for (int c = tid; c < n; c += CYC_THREADS) {
+                double v[1];
+                ll_load<1>(vr2.rd + c, vr2.tag, v, a.err, a.timeout);
+                s_r2[c] = v[0];
+            }
+            __syncthreads();
+            for (int32_t row = q0 + warp; row < q1; row += n_warps) {
+                const float4* m = reinterpret_cast<const float4*>(a.inv2 + (int64_t)row * n);
+                double acc = 0.0;
+#pragma unroll 4
+                for (int c = lane; c < n / 4; c += 32) {
+                    const float4 v = __ldg(m + c);
+                    const double2 u0 = *reinterpret_cast<const double2*>(s_r2 + 4 * c), u1 = *reinterpret_cast<const double2*>(s_r2 + 4 * c + 2);
+                    acc += (double)v.x * u0.x + (double)v.y * u0.y + (double)v.z * u1.x + (double)v.w * u1.y;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+                acc = __shfl_sync(0xffffffffu, acc, 0);
+                if (lane < a.world) ll_store1(a.X[lane] + vx2.off + row, vx2.tag, acc);
+            }
+        }
+    }
+    cyc_stamp(a, stamp++);
+    {   // x' = x + P2 x2 (+ wc t: the last pre-smoothing sweep of the overlapped cycle)
+        const CycVec x = iterate(it), xn = iterate(it + 1);
+        cyc_rows<float>(a, reps, a.p2_rowptr, a.p2_colidx, a.p2_vals, r0, r1, vx2, overlap ? &vt : nullptr, &x, 1.0, -1.0,
+                        overlap ? -a.wc : 1.0, xn, a.world, a.x_mask);
+        ++it;
+    }
+    cyc_stamp(a, stamp++);
+    for (int k = 0; k < a.n_post; ++k) {
+        const CycVec x = iterate(it), xn = iterate(it + 1);
+        cyc_rows<VT>(a, reps, a.rowptr1, a.colidx1, sys1, r0, r1, x, &vbc, &x, 1.0, a.wc, 1.0, xn, a.world, a.x_mask);
+        ++it;
+        cyc_stamp(a, stamp++);
+    }
+}
+
+// Prolongation that reads the tagged final iterate of the persistent cycle: rows owned by other ranks may still be on
+// their way when this kernel starts (their producers are other GPUs' cycle kernels, which never wait for this kernel).
+__global__ void __launch_bounds__(256) prolong_combine_ll_kernel(int64_t n_nodes, const int32_t* __restrict__ node_agg,
+                                                                 const float4* __restrict__ node_off, double omega,
+                                                                 const double* __restrict__ r, const uint4* xc, uint32_t tag,
+                                                                 double* __restrict__ z, int* err, long long timeout) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double r0, r1, r2, r3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(r + 4 * i));
+    double c[8];
+    ll_load<8>(xc + 8 * (int64_t)node_agg[i], tag, c, err, timeout);
+    const float4 d = node_off[i];
+    r0 = omega * r0 + c[0] + (c[5] * (double)d.z - c[6] * (double)d.y);
+    r1 = omega * r1 + c[1] + (c[6] * (double)d.x - c[4] * (double)d.z);
+    r2 = omega * r2 + c[2] + (c[4] * (double)d.y - c[5] * (double)d.x);
+    r3 = omega * r3 + c[3];
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(z + 4 * i), "d"(r0), "d"(r1), "d"(r2), "d"(r3) : "memory");
+}
+
 }  // namespace tefem
 
 using namespace tefem;
@@ -261,6 +631,13 @@ struct tefem_precond {
     const uint8_t* agg_ranks = nullptr;          // multi-GPU: which ranks contribute to an aggregate's restricted residual
     const __half* sys1h = nullptr;               // level-1 operator in half precision (tefem_precond_set_level1_half)
     bool overlap = true;                         // last pre-smoothing sweep and level-2 correction from one residual
+    // row-partitioned persistent coarse cycle (coarse_cycle_kernel; tefem_precond_set_coarse_mode)
+    bool persistent = false;
+    int cyc_grid = 0;                            // CTAs of the persistent kernel (<= co-resident limit)
+    uint4* cyc_local = nullptr;                  // caller's zeroed buffer of tagged vectors (tefem_precond_cycle_doubles)
+    const uint8_t *x_mask = nullptr, *t_mask = nullptr;      // tefem_precond_set_cycle_masks
+    int* d_err_local = nullptr;                  // time-out flag of the tagged loads without a communicator
+    uint32_t local_epoch = 0;
     // TEFEM_PROFILE_PRECOND=1 (diagnostics, stderr at destroy): device time of the three parts of an application -
     // restriction + all-reduce over the ranks + first sweep (includes waiting for the slowest rank), the level-1 / level-2
     // cycle (replicated work), the prolongation.  Synchronises the stream after every application: not for timed runs.
@@ -268,12 +645,35 @@ struct tefem_precond {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double part_ms[3] = {0.0, 0.0, 0.0};
     int64_t n_apply = 0;
+    double stamp_us[32] = {0.0};                 // persistent cycle: time of CTA 0 between its phase stamps
+    int n_stamps = 0;
 };
 
 static int64_t pc_align(int64_t n) { return (n + 15) / 16 * 16; }
 
 extern "C" int64_t tefem_precond_work_doubles(int32_t n_agg, int32_t n_agg2) {
-    return 4 * pc_align(8 * (int64_t)n_agg) + 2 * pc_align(8 * (int64_t)n_agg2);
+    return 4 * pc_align(8 * (int64_t)n_agg) + 2 * pc_align(8 * (int64_t)n_agg2) + 16;
+}
+
+// Level-1 iterates of one application of the persistent cycle (each has its own buffer): x_0, the pre-smoothing sweeps, the
+// level-2 update, the post-smoothing sweeps.
+static int cycle_iterates(int n_pre, int n_post, bool overlap) {
+    return 2 + ((overlap && n_pre >= 2) ? n_pre - 2 : n_pre - 1) + n_post;
+}
+// 16-byte units of the tagged vectors every rank's region holds: the iterates (for any cycle form), t, x2
+static int64_t cycle_shared_units(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
+    return (int64_t)(cycle_iterates(n_pre, n_post, false) + 1) * pc_align(8 * (int64_t)n_agg) + 2 * pc_align(8 * (int64_t)n_agg2);
+}
+
+// Capacity (doubles per parity) of the peer-memory region the row-partitioned coarse cycle needs (tefem_comm_shm_alloc):
+// the partial restricted residual, then the tagged vectors (16 bytes per value).
+extern "C" int64_t tefem_precond_peer_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
+    return pc_align(8 * (int64_t)n_agg) + 2 * cycle_shared_units(n_agg, n_agg2, n_pre, n_post);
+}
+// Doubles of the caller's ZEROED, 128-byte aligned buffer for tefem_precond_set_coarse_mode(mode 1): the local tagged vectors
+// (bc, r2) and - used without a communicator - the shared ones.
+extern "C" int64_t tefem_precond_cycle_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
+    return 2 * (pc_align(8 * (int64_t)n_agg) + cycle_shared_units(n_agg, n_agg2, n_pre, n_post)) + 16;
 }
 
 extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, const int32_t* agg_ptr,
@@ -303,7 +703,8 @@ extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t
     const int64_t a1 = pc_align(8 * (int64_t)n_agg), a2 = pc_align(8 * (int64_t)n_agg2);
     double* w = work;
     p->rc = w; w += a1; p->bc = w; w += a1; p->xc = w; w += a1; p->tc = w; w += a1;
-    p->r2 = w; w += a2; p->x2 = w;
+    p->r2 = w; w += a2; p->x2 = w; w += a2;
+    p->d_err_local = reinterpret_cast<int*>(w);                      // the caller zeroed `work`
     p->comm = reinterpret_cast<tefem_comm*>(comm);
     const char* pe = getenv("TEFEM_PROFILE_PRECOND");
     if (pe && pe[0] == '1') {
@@ -329,6 +730,59 @@ extern "C" int tefem_precond_set_cycle(tefem_precond* p, int overlapped) {
     return TEFEM_OK;
 }
 
+// mode 0: the coarse cycle as separate launches on replicated levels; 1: row-partitioned persistent dataflow kernel
+// (coarse_cycle_kernel).  cycle_work: zeroed buffer of tefem_precond_cycle_doubles doubles (mode 1).  With a communicator
+// the peer region must hold tefem_precond_peer_doubles per parity.
+template <typename VT>
+static int cycle_configure(tefem_precond* p, size_t smem, int* per_sm) {
+    if (smem > 48 * 1024)
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(coarse_cycle_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, coarse_cycle_kernel<VT>, CYC_THREADS, smem));
+    (void)p;
+    return TEFEM_OK;
+}
+
+extern "C" int tefem_precond_set_coarse_mode(tefem_precond* p, int mode, double* cycle_work) {
+    TEFEM_REQUIRE(p && (mode == 0 || mode == 1), "mode 0 (launches) or 1 (persistent)");
+    if (mode == 1) {
+        TEFEM_REQUIRE(cycle_work && (((uintptr_t)cycle_work) & 127) == 0, "cycle_work: zeroed, 128-byte aligned buffer");
+        TEFEM_REQUIRE(cycle_iterates(p->n_pre, p->n_post, p->overlap) <= CYC_MAX_X, "too many sweeps for the persistent coarse cycle");
+        const size_t smem = sizeof(double) * 8 * (size_t)p->n2;
+        TEFEM_REQUIRE(smem <= 96 * 1024, "level 2 too large for the persistent coarse cycle (8 n_agg2 doubles of shared memory)");
+        if (p->comm)
+            TEFEM_REQUIRE(tefem_comm_has_peer(p->comm) &&
+                              tefem_comm_peer_cap(p->comm) >= tefem_precond_peer_doubles(p->n1, p->n2, p->n_pre, p->n_post),
+                          "the peer-memory region must hold tefem_precond_peer_doubles(...) doubles per parity");
+        int dev = 0, sms = 0, per_sm = 0;
+        TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
+        TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int rc = p->sys1h ? cycle_configure<__half>(p, smem, &per_sm) : cycle_configure<float>(p, smem, &per_sm);
+        if (rc) return rc;
+        TEFEM_REQUIRE(per_sm >= 1, "the coarse-cycle kernel does not fit on an SM");
+        const int world = p->comm ? tefem_comm_world(p->comm) : 1;
+        // one pass over the own block rows of level 1 (one warp each) when the co-resident limit allows
+        const int64_t own_rows = 2 * ceil_div((int64_t)p->n1, world);
+        int64_t g = ceil_div(own_rows * CYC_LANES, CYC_THREADS);
+        if (g < 64) g = 64;
+        if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
+        p->cyc_grid = (int)g;
+        p->cyc_local = reinterpret_cast<uint4*>(cycle_work);
+    }
+    p->persistent = mode == 1;
+    return TEFEM_OK;
+}
+
+// Persistent cycle on several GPUs: x_mask[i] / t_mask[i] (uint8 device arrays over the aggregates, bit q) = rank q reads
+// the level-1 iterates / the residual t of aggregate i: the owner stores a row only into those replicas (without the
+// masks every row goes to every rank: 7 x the NVLink traffic of a slab partition).  The owner's own bit must be set.
+// Ownership: aggregate i belongs to rank q with n_agg q / world <= i < n_agg (q + 1) / world (integer division), level-2
+// aggregate J likewise with n_agg2.
+extern "C" int tefem_precond_set_cycle_masks(tefem_precond* p, const uint8_t* x_mask, const uint8_t* t_mask) {
+    TEFEM_REQUIRE(p, "null preconditioner");
+    p->x_mask = x_mask; p->t_mask = t_mask;
+    return TEFEM_OK;
+}
+
 extern "C" int tefem_precond_set_agg_ranks(tefem_precond* p, const uint8_t* agg_ranks) {
     TEFEM_REQUIRE(p, "null preconditioner");
     p->agg_ranks = agg_ranks;
@@ -341,6 +795,11 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
             fprintf(stderr, "[tefem precond profile] %lld applications: restrict + all-reduce + first sweep %.4f ms, level-1/2 cycle %.4f ms, "
                             "prolongation %.4f ms per application\n", (long long)p->n_apply, p->part_ms[0] / p->n_apply,
                     p->part_ms[1] / p->n_apply, p->part_ms[2] / p->n_apply);
+        if (p->n_apply > 0 && p->n_stamps > 0) {
+            fprintf(stderr, "[tefem precond profile] persistent cycle, CTA 0, us per phase (phase 0, sweeps.., t, r2, x2, update, post..):");
+            for (int k = 1; k < p->n_stamps; ++k) fprintf(stderr, " %.2f", p->stamp_us[k] / p->n_apply);
+            fprintf(stderr, "\n");
+        }
         for (int k = 0; k < 4; ++k)
             if (p->ev[k]) cudaEventDestroy(p->ev[k]);
     }
@@ -348,14 +807,97 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
     return TEFEM_OK;
 }
 
+// One application with the row-partitioned persistent coarse cycle: restriction, coarse_cycle_kernel, prolongation.
+static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaStream_t st) {
+    const int64_t a1 = pc_align(8 * (int64_t)p->n1), a2 = pc_align(8 * (int64_t)p->n2);
+    const unsigned gr = (unsigned)p->n1;                                                        // restriction: one CTA per aggregate
+    CycleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rowptr1 = p->rowptr1; a.colidx1 = p->colidx1;
+    a.sys1 = p->sys1h ? (const void*)p->sys1h : (const void*)p->sys1;
+    a.dinv1 = p->dinv1; a.agg_ranks = p->agg_ranks;
+    a.r2_rowptr = p->r2_rowptr; a.r2_colidx = p->r2_colidx; a.r2_vals = p->r2_vals;
+    a.p2_rowptr = p->p2_rowptr; a.p2_colidx = p->p2_colidx; a.p2_vals = p->p2_vals; a.inv2 = p->inv2;
+    a.n1 = p->n1; a.n2 = p->n2;
+    a.wc = p->omega_c; a.n_pre = p->n_pre; a.n_post = p->n_post; a.overlap = p->overlap ? 1 : 0;
+    a.bc = p->cyc_local;
+    a.vec_units = a1; a.a2_units = a2;
+    a.x_mask = p->x_mask; a.t_mask = p->t_mask;
+    a.n_iterates = cycle_iterates(p->n_pre, p->n_post, p->overlap);
+    double* rc_mine = p->rc;
+    if (p->comm) {
+        const PeerCtx pc = tefem_comm_peer_ctx(p->comm, PEER_CH_CYCLE);
+        a.world = pc.world; a.rank = pc.rank;
+        a.tag_base = pc.epoch * 32u;
+        a.err = pc.err; a.timeout = pc.timeout;
+        for (int q = 0; q < pc.world; ++q) {
+            double* big = reinterpret_cast<double*>(pc.base[q] + PEER_BIG_OFFSET);
+            a.rc[q] = big + (int64_t)(pc.epoch & 1u) * pc.cap;
+            a.X[q] = reinterpret_cast<uint4*>(big + a1);
+            a.flags[q] = reinterpret_cast<uint32_t*>(pc.base[q]) + (PEER_CH_CYCLE * 2) * PEER_MAX_RANKS;
+        }
+        rc_mine = const_cast<double*>(a.rc[pc.rank]);
+    } else {
+        a.world = 1; a.rank = 0;
+        a.tag_base = (++p->local_epoch) * 32u;
+        a.err = p->d_err_local;                                   // local producers cannot be lost
+        a.timeout = PEER_TIMEOUT_DEFAULT;
+        a.rc[0] = p->rc;
+        a.X[0] = p->cyc_local + a1;
+    }
+    // diagnostics: the 16 spare doubles at the end of cycle_work hold the phase stamps of CTA 0
+    unsigned long long* d_stamps = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<double*>(p->cyc_local) + tefem_precond_cycle_doubles(p->n1, p->n2, p->n_pre, p->n_post) - 16);
+    a.stamps = p->profile ? d_stamps : nullptr;
+    a.a0 = (int32_t)((int64_t)p->n1 * a.rank / a.world); a.a1 = (int32_t)((int64_t)p->n1 * (a.rank + 1) / a.world);
+    a.j0 = (int32_t)((int64_t)p->n2 * a.rank / a.world); a.j1 = (int32_t)((int64_t)p->n2 * (a.rank + 1) / a.world);
+    if (p->profile) cudaEventRecord(p->ev[0], st);
+    restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, rc_mine);
+    TEFEM_LAUNCH_CHECK();
+    if (p->profile) cudaEventRecord(p->ev[1], st);
+    void* kargs[] = {&a};
+    const void* fn = p->sys1h ? (const void*)coarse_cycle_kernel<__half> : (const void*)coarse_cycle_kernel<float>;
+    // A plain launch (a cooperative one costs more): the grid is within the co-resident limit of the device, and a CTA that
+    // waits for a producer of the same grid can only be delayed - not blocked - by independent work of other streams.
+    TEFEM_CUDA_CHECK(cudaLaunchKernel(fn, dim3((unsigned)p->cyc_grid), dim3(CYC_THREADS), kargs, sizeof(double) * 8 * (size_t)p->n2, st));
+    count_launch();
+    TEFEM_CUDA_CHECK(cudaGetLastError());
+    const uint4* cur = a.X[a.rank] + (int64_t)(a.n_iterates - 1) * a.vec_units;           // the last iterate, tagged
+    const uint32_t cur_tag = a.tag_base + 1u + (uint32_t)(a.n_iterates - 1);
+    if (p->profile) cudaEventRecord(p->ev[2], st);
+    if (p->n_rows > 0) {
+        prolong_combine_ll_kernel<<<(unsigned)ceil_div((int64_t)p->n_rows, 256), 256, 0, st>>>(
+            p->n_rows, p->node_agg, p->node_off, p->omega, r, cur, cur_tag, z, a.err, a.timeout);
+        TEFEM_LAUNCH_CHECK();
+    }
+    if (p->profile) {
+        cudaEventRecord(p->ev[3], st);
+        if (cudaEventSynchronize(p->ev[3]) == cudaSuccess) {
+            for (int k = 0; k < 3; ++k) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]) == cudaSuccess) p->part_ms[k] += ms;
+            }
+            p->n_apply += 1;
+            unsigned long long h[16];
+            const int ns = 5 + a.n_iterates - 1 < 16 ? 5 + a.n_iterates - 1 : 16;    // start, phase 0, sweeps, t, r2, x2, update, post
+            if (cudaMemcpy(h, d_stamps, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                for (int k = 1; k < ns; ++k) p->stamp_us[k] += 1e-3 * (double)(h[k] - h[k - 1]);
+                p->n_stamps = ns;
+            }
+        }
+    }
+    return TEFEM_OK;
+}
+
 int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cudaStream_t st) {
     TEFEM_REQUIRE(p && r && z, "null pointer");
+    if (p->persistent) return apply_persistent(p, r, z, st);
     const int64_t n1 = 8 * (int64_t)p->n1;                    // scalar size of level 1
     const int32_t np1 = 2 * p->n1, np2 = 2 * p->n2;           // pseudo nodes (4-DOF block rows) of levels 1 and 2
     const unsigned g1 = (unsigned)ceil_div(n1, 256);                                           // one thread per scalar of level 1
     const unsigned gs1 = (unsigned)ceil_div((int64_t)COARSE_LANES * np1, 256);                 // coarse_spmv: 16 lanes per block row
     const unsigned gs2 = (unsigned)ceil_div((int64_t)COARSE_LANES * np2, 256);
-    const unsigned gr = (unsigned)ceil_div(32 * (int64_t)p->n1, 256);
+    const unsigned gr = (unsigned)p->n1;                                                        // restriction: one CTA per aggregate
     if (p->profile) cudaEventRecord(p->ev[0], st);
     // level 0 -> 1: rc = P1^T r, summed over the ranks (levels 1 and 2 are replicated): the restriction writes
     // into this rank's peer buffer and the next kernel does all-reduce + D1^-1 + first smoothing step in one
@@ -364,13 +906,13 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
                       "the peer-memory region must hold 8 * n_agg doubles (tefem_comm_shm_alloc)");
         const PeerCtx pc = tefem_comm_peer_ctx(p->comm, PEER_CH_COARSE);
         double* mine = reinterpret_cast<double*>(pc.base[pc.rank] + PEER_BIG_OFFSET) + (int64_t)(pc.epoch & 1u) * pc.cap;
-        restrict_kernel<<<gr, 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, mine);
+        restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, mine);
         TEFEM_LAUNCH_CHECK();
         peer_coarse_start_kernel<<<(unsigned)ceil_div((int64_t)p->n1, 128), 128, 0, st>>>(pc, p->n1, p->agg_ranks, p->dinv1, p->omega_c,
                                                                                           p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();
     } else {
-        restrict_kernel<<<gr, 256, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, p->rc);
+        restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, p->rc);
         TEFEM_LAUNCH_CHECK();
         coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();

@@ -195,6 +195,10 @@ class KrylovSolver:
             p(boundary_rows), int(boundary_rows.numel()) if boundary_rows is not None else 0,
             p(interior_rows), int(interior_rows.numel()) if interior_rows is not None else 0))
 
+    def set_interior_range(self, lo, hi, fused=True):
+        """Rows [lo, hi) have no halo column; fused: the SpMV kernel does its own halo exchange (include/tefem.h)."""
+        _lib.check(self.lib.tefem_solver_set_interior_range(self.handle, int(lo), int(hi), int(bool(fused))))
+
     @staticmethod
     def _info(info, method):
         return dict(iterations=int(info[0]), restarts=int(info[1]), relres=float(info[2]), bnorm=float(info[3]),

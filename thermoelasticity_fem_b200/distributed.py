@@ -137,6 +137,16 @@ def dirichlet_node_data(tri_groups_global, dict_dirichlet_U, dict_dirichlet_thet
     return dofs, np.array([fill[d] for d in dofs]), np.array([lift[d] for d in dofs])
 
 
+def longest_interior_range(boundary_rows, n_own):
+    """[lo, hi): the longest run of owned rows without a halo column (row blocks in node order: everything between the
+    interface layers)."""
+    b = np.unique(np.asarray(boundary_rows, dtype=np.int64))
+    edges = np.concatenate([[-1], b, [n_own]])
+    gaps = edges[1:] - edges[:-1] - 1
+    k = int(np.argmax(gaps))
+    return int(edges[k] + 1), int(edges[k] + 1 + gaps[k])
+
+
 def halo_destinations(lp: LocalProblem):
     """Per send entry of `lp`: destination rank and node position in THAT rank's local vector (its n_own + the offset of
     this rank's segment in its halo tail).  Collective: every rank publishes (n_own, neighbours, halo offsets)."""
@@ -178,9 +188,11 @@ class DistributedTransient:
     def __init__(self, lp: LocalProblem, coords_local, mat_id_local, materials, dirichlet, loads,
                  alpha_M, alpha_K, t_end, n_t, gamma=0.5, beta=0.25, rtol=1e-10, max_iter=50000, check_every=16,
                  comm=None, precond="multilevel", halo="peer", floor_factor=1.0, mat_table=None, precond_options=None):
-        """halo: 'peer' (default) - boundary values are stored straight into the neighbours' vectors over NVLink and the
-        SpMV waits for flags; 'nccl' - packed ncclSend / ncclRecv overlapped with the interior rows (measured alternative)."""
-        assert halo in ("peer", "nccl")
+        """halo: 'peer' (default) - the SpMV is ONE kernel that stores this rank's boundary values straight into the neighbours'
+        vectors over NVLink, multiplies the interior rows, waits for the neighbours' flags and multiplies the boundary rows;
+        'peer-push' - the same stores from a separate push launch, the SpMV waits before its first row; 'nccl' - packed
+        ncclSend / ncclRecv overlapped with the interior rows (both measured alternatives)."""
+        assert halo in ("peer", "peer-push", "nccl")
         self.halo = halo
         self.floor_factor = floor_factor
         self.precond_options = precond_options or {}
@@ -236,7 +248,7 @@ class DistributedTransient:
             self.planes = dm.assemble("MKD", self.alpha_M, self.alpha_K)
             self.sys = dm.form_system(self.planes, 1.0, self.gamma * dt, self.beta * dt ** 2, d_layout, self.dir_mask)
         self.dinv = dm.block_jacobi_scale(self.sys)
-        if self.comm is not None and self.halo == "peer":
+        if self.comm is not None and self.halo != "nccl":
             self.comm.setup_vectors(lp.n_local)          # before the solver: it keeps its SpMV inputs in the slots
         self.krylov = KrylovSolver(dm, lp.n_halo, self.comm)
         if self.comm is not None and self.precond_kind != "multilevel":
@@ -247,10 +259,12 @@ class DistributedTransient:
             self.precond = TwoLevelPreconditioner(dm, self.sys, comm=self.comm, **self.precond_options)
             self.krylov.set_precond(self.precond)
         send_idx = torch.from_numpy(lp.send_idx.astype(np.int32)).to(dev)
-        if self.comm is not None and self.halo == "peer":
+        if self.comm is not None and self.halo != "nccl":
             dst, dpos = halo_destinations(lp)
             self.krylov.set_halo(lp.nbr, lp.send_ptr, send_idx, lp.recv_ptr,
                                  send_dst=torch.from_numpy(dst).to(dev), send_dpos=torch.from_numpy(dpos).to(dev))
+            lo, hi = longest_interior_range(lp.boundary_rows, lp.n_own)
+            self.krylov.set_interior_range(lo, hi, fused=self.halo == "peer")
         else:
             self.krylov.set_halo(lp.nbr, lp.send_ptr, send_idx, lp.recv_ptr,
                                  torch.from_numpy(lp.boundary_rows.astype(np.int32)).to(dev),

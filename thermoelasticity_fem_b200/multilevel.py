@@ -240,15 +240,52 @@ def _bsr_arrays(M, dev):
             torch.from_numpy(np.ascontiguousarray(B.data.reshape(-1, 16)).astype(np.float32)).to(dev))
 
 
+def row_owner(n, world, device=None):
+    """Owner rank of each of n rows split as the library does: rank q owns [n q // world, n (q + 1) // world)."""
+    bounds = torch.tensor([n * q // world for q in range(world + 1)], dtype=torch.int64, device=device)
+    return torch.searchsorted(bounds, torch.arange(n, dtype=torch.int64, device=device), right=True) - 1
+
+
+def cycle_masks(rowptr1, colidx1, n1, agg2, n2, agg_ranks, world):
+    """Destination masks of the row-partitioned coarse cycle (include/tefem.h, tefem_precond_set_cycle_masks), uint8 over the
+    aggregates, bit q = rank q reads the row: the level-1 iterates of aggregate i are read by its owner, by the owners of the
+    rows that have a block in column i, and by the ranks that own fine nodes of i (prolongation); its residual t by its owner
+    and by the owner of its level-2 aggregate.  The same on every rank (built from replicated data)."""
+    dev = rowptr1.device
+    own1 = row_owner(n1, world, dev)
+    cnt = (rowptr1[1:] - rowptr1[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(2 * n1, dtype=torch.int64, device=dev), cnt)
+    reader = own1[rows >> 1]                                   # rank that multiplies this block
+    cagg = colidx1.long() >> 1
+    x_mask = (torch.ones(n1, dtype=torch.int32, device=dev) << own1.to(torch.int32))
+    for q in range(world):
+        hit = torch.zeros(n1, dtype=torch.bool, device=dev)
+        hit[cagg[reader == q]] = True
+        x_mask |= hit.to(torch.int32) << q
+    if agg_ranks is not None:
+        x_mask |= agg_ranks.to(torch.int32)
+    own2 = row_owner(n2, world, dev)
+    a2 = torch.as_tensor(np.asarray(agg2), dtype=torch.int64, device=dev)
+    t_mask = (torch.ones(n1, dtype=torch.int32, device=dev) << own1.to(torch.int32)) | \
+             (torch.ones(n1, dtype=torch.int32, device=dev) << own2[a2].to(torch.int32))
+    return x_mask.to(torch.uint8).contiguous(), t_mask.to(torch.uint8).contiguous()
+
+
 class TwoLevelPreconditioner:
     """Owns the device arrays of one preconditioner and its C handle (attach with KrylovSolver.set_precond)."""
 
     def __init__(self, dm, sys, comm=None, factor1=8.0, factor2=3.0, omega=1.0, omega_c=0.7, n_pre=3, n_post=3,
-                 dense_limit=200, level1_dtype="fp16", cycle="overlapped"):
+                 dense_limit=200, level1_dtype="fp16", cycle="overlapped", coarse="auto"):
         """level1_dtype: storage of the scaled level-1 operator for the sweeps - 'fp16' (default; falls back to 'fp32' when
         an entry would overflow half precision) or 'fp32'.  Preconditioner data only.
         cycle: 'overlapped' (default) - the last pre-smoothing sweep and the level-2 correction use one residual (one
-        level-1 product less per application) - or 'classic'."""
+        level-1 product less per application) - or 'classic'.
+        coarse: how the level-1 / level-2 cycle runs - 'launches' (separate kernels on levels replicated on every rank),
+        'persistent' (one cooperative kernel per application; rows of levels 1 and 2 partitioned over the ranks, coarse
+        vectors exchanged through peer memory) or 'auto' (persistent with a communicator, launches on one GPU)."""
+        if coarse not in ("auto", "launches", "persistent"):
+            raise ValueError("coarse must be 'auto', 'launches' or 'persistent'")
+        self.coarse = ("persistent" if comm is not None else "launches") if coarse == "auto" else coarse
         if cycle not in ("overlapped", "classic"):
             raise ValueError("cycle must be 'overlapped' or 'classic'")
         self.cycle = cycle
@@ -301,7 +338,9 @@ class TwoLevelPreconditioner:
         self.factor1, self.omega, self.omega_c, self.n_pre, self.n_post = factor1, omega, omega_c, n_pre, n_post
         self.agg_ranks = None
         if comm is not None:
-            comm.setup_peer(8 * n1)               # the restricted residual is all-reduced through peer memory
+            # the restricted residual is all-reduced through peer memory; the row-partitioned cycle also keeps its coarse
+            # vectors there (one replica per rank)
+            comm.setup_peer(int(lib.tefem_precond_peer_doubles(n1, n2, int(n_pre), int(n_post))) if self.coarse == "persistent" else 8 * n1)
             # which ranks own fine nodes of an aggregate: only their partial sums are read over NVLink
             dist = _dist(True)
             mine = ((agg_ptr[1:] - agg_ptr[:-1]) > 0).to(torch.int32)
@@ -329,6 +368,15 @@ class TwoLevelPreconditioner:
             _lib.check(lib.tefem_precond_set_level1_half(self.handle, p(self.sys1_half)))
         self.cycle = cycle
         _lib.check(lib.tefem_precond_set_cycle(self.handle, int(cycle == "overlapped")))
+        self.cycle_work = None
+        if self.coarse == "persistent":       # tagged coarse vectors of the persistent cycle (zero = no tag yet)
+            self.cycle_work = torch.zeros(int(lib.tefem_precond_cycle_doubles(n1, n2, int(n_pre), int(n_post))), **f64)
+        _lib.check(lib.tefem_precond_set_coarse_mode(self.handle, int(self.coarse == "persistent"),
+                                                     p(self.cycle_work) if self.cycle_work is not None else None))
+        self.x_mask = self.t_mask = None
+        if self.coarse == "persistent" and comm is not None:
+            self.x_mask, self.t_mask = cycle_masks(self.rowptr1, self.colidx1, n1, agg2, n2, self.agg_ranks, comm.world)
+            _lib.check(lib.tefem_precond_set_cycle_masks(self.handle, p(self.x_mask), p(self.t_mask)))
 
     def apply(self, r, z):
         _lib.check(self.lib.tefem_precond_apply(self.handle, _lib.ptr(r), _lib.ptr(z), _lib.stream_ptr()))

@@ -30,6 +30,8 @@
 
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <vector>
 
 namespace tefem {
 
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(128) dense_matvec_kernel(int32_t n, const floa
 // every rank's restriction has finished and no rank still reads the buffers of the previous application.
 // world == 1 runs the same kernel on local buffers.
 constexpr int CYC_THREADS = 256;
+constexpr int CYC_GATHER_CTAS = 4;       // CTAs that copy r2 out of its tagged replica for everybody else (no polling storm)
 constexpr int CYC_MAX_X = 24;            // vector numbers: level-1 iterates 0 .. CYC_MAX_X - 1, then t, x2, bc, r2
 enum { CYC_V_T = 24, CYC_V_X2 = 25, CYC_V_BC = 26, CYC_V_R2 = 27 };
 
@@ -297,6 +300,9 @@ struct CycleArgs {
     uint4* bc;                           // local tagged vector: D1^-1 rc on the own rows
     const uint8_t *x_mask, *t_mask;      // per aggregate: the ranks that read its level-1 iterates / its residual t (null: all)
     int32_t j0, j1;                      // own level-2 aggregates: rows of P2^T and of the dense inverse
+    double* r2_plain;                    // local: r2 gathered from its tagged replica by the first CYC_GATHER_CTAS CTAs
+    unsigned long long* gathered;        // local counter of finished gather CTAs (never reset)
+    unsigned long long gathered_target;  // its value when this application's r2 is complete
     int64_t a2_units;                    // 16-byte units of a level-2 vector
     int64_t vec_units;                   // 16-byte units between consecutive vectors
     int n_iterates;
@@ -305,14 +311,30 @@ struct CycleArgs {
     int* err;
     long long timeout;
     unsigned long long* stamps;          // diagnostics (TEFEM_PROFILE_PRECOND=1): globaltimer of CTA 0 after each phase, or null
+    unsigned long long* all_stamps;      // diagnostics: [n_cta][16] stamps of every CTA, or null
 };
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void cyc_stamp(const CycleArgs& a, int k) {
-    if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.stamps && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        a.stamps[k] = t;
+        if (blockIdx.x == 0) a.stamps[k] = t;
+        if (a.all_stamps) a.all_stamps[16 * (size_t)blockIdx.x + k] = t;      // diagnostics: every CTA's time line
     }
+}
+
+// L2 prefetch of [p, p + bytes) by the whole grid (128-byte lines): the operators of this rank's rows were evicted by the
+// fine-level SpMV since the last application; fetched at kernel start they are L2 hits when their phase comes.
+__device__ __forceinline__ void cyc_prefetch(const void* p, int64_t bytes) {
+    const char* c = reinterpret_cast<const char*>(p);
+    for (int64_t o = 128 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); o < bytes; o += 128 * (int64_t)gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(c + o));
 }
 
 // ---- tagged ("LL") doubles: {lo, tag, hi, tag} ----
@@ -324,9 +346,10 @@ __device__ __forceinline__ void ll_store1(uint4* p, uint32_t tag, double v) {
 __device__ __forceinline__ void ll_store4(uint4* p, uint32_t tag, double v0, double v1, double v2, double v3) {
     const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0), b1 = (unsigned long long)__double_as_longlong(v1);
     const unsigned long long b2 = (unsigned long long)__double_as_longlong(v2), b3 = (unsigned long long)__double_as_longlong(v3);
-    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(ll_pack((uint32_t)b0, tag)), "l"(ll_pack((uint32_t)(b0 >> 32), tag)),
+    // volatile (strong) stores: a weak store to peer memory may wait in a write-combining stage for microseconds
+    asm volatile("st.volatile.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(ll_pack((uint32_t)b0, tag)), "l"(ll_pack((uint32_t)(b0 >> 32), tag)),
                  "l"(ll_pack((uint32_t)b1, tag)), "l"(ll_pack((uint32_t)(b1 >> 32), tag)) : "memory");
-    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p + 2), "l"(ll_pack((uint32_t)b2, tag)), "l"(ll_pack((uint32_t)(b2 >> 32), tag)),
+    asm volatile("st.volatile.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p + 2), "l"(ll_pack((uint32_t)b2, tag)), "l"(ll_pack((uint32_t)(b2 >> 32), tag)),
                  "l"(ll_pack((uint32_t)b3, tag)), "l"(ll_pack((uint32_t)(b3 >> 32), tag)) : "memory");
 }
 __device__ __forceinline__ uint4 ll_ld(const uint4* p) {
@@ -401,6 +424,30 @@ __device__ __forceinline__ void cyc_block_fma(const VT* __restrict__ sys, int32_
     a3 += (double)q3.x * u[0] + (double)q3.y * u[1] + (double)q3.z * u[2] + (double)q3.w * u[3];
 }
 
+// Raw (unchecked) loads of 4 tagged values and the check / retry that follows: a batch of independent loads is ISSUED before
+// the first tag is looked at, so that the batch costs one memory latency (a check is a branch on the loaded data: checking
+// between the loads would serialise them).
+__device__ __forceinline__ void ll_issue4(const uint4* p, uint4 (&v)[4]) { ll_ld2(p, v[0], v[1]); ll_ld2(p + 2, v[2], v[3]); }
+__device__ __forceinline__ bool ll_ok4(const uint4 (&v)[4], uint32_t tag) {
+    return v[0].y == tag && v[0].w == tag && v[1].y == tag && v[1].w == tag && v[2].y == tag && v[2].w == tag && v[3].y == tag && v[3].w == tag;
+}
+__device__ __forceinline__ void ll_finish4(const uint4* p, uint32_t tag, uint4 (&v)[4], double (&out)[4], int* err, long long timeout) {
+    if (!ll_ok4(v, tag)) {
+        const long long t0 = clock64();
+        for (;;) {
+            ll_issue4(p, v);
+            if (ll_ok4(v, tag)) break;
+            if (*reinterpret_cast<volatile int*>(err)) break;
+            if (clock64() - t0 > timeout) { *err = 1; break; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = ll_value(v[k]);
+}
+
+// (Measured and dropped: issuing the blocks and both x loads of a trip, and xin with b, as batches before the first tag check
+// - fewer dependent latencies on paper, but 200 - 400 bytes of spills at the 80 registers that three CTAs per SM allow, and
+// the stragglers of the post-smoothing sweeps got slower: 90 against 75 us per application, profiles/README.md.)
 template <typename VT>
 __device__ __forceinline__ void cyc_rows(const CycleArgs& a, uint4* const* reps, const int32_t* __restrict__ rowptr,
                                          const int32_t* __restrict__ colidx, const VT* __restrict__ sys, int32_t r0, int32_t r1,
@@ -468,6 +515,8 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
     const VT* sys1 = reinterpret_cast<const VT*>(a.sys1);
     const int me = a.rank;
     if (tid < PEER_MAX_RANKS) reps[tid] = a.X[tid];
+    int stamp = 0;
+    cyc_stamp(a, stamp++);                               // kernel entry
     // every rank's restriction has finished (its partial sums are visible) and none is still reading a vector of the
     // previous application (whose buffers this one overwrites)
     if (a.world > 1) {
@@ -486,8 +535,17 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
         }
     }
     __syncthreads();
-    int stamp = 0;
-    cyc_stamp(a, stamp++);
+    {   // operators of the own rows -> L2 (level 1, dense level-2 rows, transfer operators)
+        const int32_t b0 = a.rowptr1[2 * a.a0], b1 = a.rowptr1[2 * a.a1];
+        cyc_prefetch(reinterpret_cast<const char*>(a.sys1) + (int64_t)b0 * 16 * sizeof(VT), (int64_t)(b1 - b0) * 16 * sizeof(VT));
+        cyc_prefetch(a.colidx1 + b0, (int64_t)(b1 - b0) * 4);
+        cyc_prefetch(a.inv2 + (int64_t)8 * a.j0 * 8 * a.n2, (int64_t)8 * (a.j1 - a.j0) * 8 * a.n2 * 4);
+        const int32_t c0 = a.r2_rowptr[2 * a.j0], c1 = a.r2_rowptr[2 * a.j1];
+        cyc_prefetch(a.r2_vals + (int64_t)c0 * 16, (int64_t)(c1 - c0) * 64);
+        const int32_t d0 = a.p2_rowptr[2 * a.a0], d1 = a.p2_rowptr[2 * a.a1];
+        cyc_prefetch(a.p2_vals + (int64_t)d0 * 16, (int64_t)(d1 - d0) * 64);
+    }
+    cyc_stamp(a, stamp++);                               // start flags exchanged
     const uint32_t T = a.tag_base + 1u;                  // tag of vector v: T + v
     const int64_t U = a.vec_units;
     const uint4* mine = a.X[me];
@@ -544,33 +602,86 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
     // r2 = P2^T t on the own level-2 aggregates (their children's t rows were sent here), stored into every replica
     cyc_rows<float>(a, reps, a.r2_rowptr, a.r2_colidx, a.r2_vals, 2 * a.j0, 2 * a.j1, vt, nullptr, nullptr, 0.0, -1.0, 1.0, vr2, a.world, nullptr);
     cyc_stamp(a, stamp++);
-    {   // x2 = A2^-1 r2 on the own rows of the dense inverse: r2 staged in shared memory, one warp per row, lane-strided
-        // sums + shuffle tree
-        const int n = 8 * a.n2;
-        const int32_t warp = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
-        const int lane = tid & 31;
-        const int32_t q0 = 8 * a.j0, q1 = 8 * a.j1;                                          // own rows of the dense inverse
-        const bool any_row = q0 + (int32_t)((blockIdx.x * blockDim.x) >> 5) < q1;           // uniform over the CTA
-        if (any_row) {
-            for (int c = tid; c < n; c += CYC_THREADS) {
-                double v[1];
-                ll_load<1>(vr2.rd + c, vr2.tag, v, a.err, a.timeout);
-                s_r2[c] = v[0];
+    {   // x2 = A2^-1 r2 on the own rows of the dense inverse: one CTA per row with all the row's loads in flight at once (the
+        // first row is loaded BEFORE the wait for r2, which is staged in shared memory); thread-strided sums, fixed tree
+        __shared__ double wsum[CYC_THREADS / 32];
+        const int n = 8 * a.n2, n4 = n / 4;
+        const int32_t q0 = 8 * a.j0, q1 = 8 * a.j1;
+        const int lane = tid & 31, warp = tid >> 5;
+        if ((int)blockIdx.x < CYC_GATHER_CTAS) {   // gather: tagged replica -> plain local array, then one counter tick per CTA
+            // thread -> 4 consecutive values (one block row of r2), all its rows issued before the first check
+            for (int c = 4 * ((int)blockIdx.x * CYC_THREADS + tid); c < n; c += 4 * CYC_GATHER_CTAS * CYC_THREADS) {
+                uint4 v[4];
+                double d[4];
+                ll_issue4(vr2.rd + c, v);
+                ll_finish4(vr2.rd + c, vr2.tag, v, d, a.err, a.timeout);
+                a.r2_plain[c] = d[0]; a.r2_plain[c + 1] = d[1]; a.r2_plain[c + 2] = d[2]; a.r2_plain[c + 3] = d[3];
             }
             __syncthreads();
-            for (int32_t row = q0 + warp; row < q1; row += n_warps) {
-                const float4* m = reinterpret_cast<const float4*>(a.inv2 + (int64_t)row * n);
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(a.gathered, 1ULL);
+            }
+        }
+        int32_t row = q0 + (int32_t)blockIdx.x;
+        if (row < q1) {                                                                      // uniform over the CTA
+            constexpr int PRE = 4;                                                           // float4 per thread held in registers
+            float4 m[PRE];
+            const float4* mrow = reinterpret_cast<const float4*>(a.inv2 + (int64_t)row * n);
+#pragma unroll
+            for (int u = 0; u < PRE; ++u) m[u] = (tid + u * CYC_THREADS < n4) ? __ldg(mrow + tid + u * CYC_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // r2: every CTA polling all 8 n2 tagged values (hundreds of CTAs x 64 KB per retry) starved the few warps that
+            // still produce them; the gather CTAs above copied it to a plain array - wait for their counter, read it once
+            if (tid == 0) {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu_u64(a.gathered) < a.gathered_target) {
+                    if (*reinterpret_cast<volatile int*>(a.err)) break;
+                    if (clock64() - t0 > a.timeout) { *a.err = 1; break; }
+                }
+            }
+            __syncthreads();
+            for (int c0 = tid; c0 < n; c0 += 8 * CYC_THREADS) {           // eight loads in flight per thread, then the stores
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (c0 + u * CYC_THREADS < n) ? __ldcg(a.r2_plain + c0 + u * CYC_THREADS) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c0 + u * CYC_THREADS < n) s_r2[c0 + u * CYC_THREADS] = v[u];
+            }
+            __syncthreads();
+            for (; row < q1; row += (int32_t)gridDim.x) {
                 double acc = 0.0;
-#pragma unroll 4
-                for (int c = lane; c < n / 4; c += 32) {
-                    const float4 v = __ldg(m + c);
+#pragma unroll
+                for (int u = 0; u < PRE; ++u) {
+                    const int c = tid + u * CYC_THREADS;
+                    if (c < n4) {
+                        const double2 u0 = *reinterpret_cast<const double2*>(s_r2 + 4 * c), u1 = *reinterpret_cast<const double2*>(s_r2 + 4 * c + 2);
+                        acc += (double)m[u].x * u0.x + (double)m[u].y * u0.y + (double)m[u].z * u1.x + (double)m[u].w * u1.y;
+                    }
+                }
+                mrow = reinterpret_cast<const float4*>(a.inv2 + (int64_t)row * n);
+                for (int c = tid + PRE * CYC_THREADS; c < n4; c += CYC_THREADS) {                // rows longer than PRE * 4 * 256 values
+                    const float4 v = __ldg(mrow + c);
                     const double2 u0 = *reinterpret_cast<const double2*>(s_r2 + 4 * c), u1 = *reinterpret_cast<const double2*>(s_r2 + 4 * c + 2);
                     acc += (double)v.x * u0.x + (double)v.y * u0.y + (double)v.z * u1.x + (double)v.w * u1.y;
                 }
+                const int32_t next = row + (int32_t)gridDim.x;
+                if (next < q1) {                                                             // the next row's loads fly during the reduction
+                    const float4* mn = reinterpret_cast<const float4*>(a.inv2 + (int64_t)next * n);
+#pragma unroll
+                    for (int u = 0; u < PRE; ++u) m[u] = (tid + u * CYC_THREADS < n4) ? __ldg(mn + tid + u * CYC_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-                acc = __shfl_sync(0xffffffffu, acc, 0);
-                if (lane < a.world) ll_store1(a.X[lane] + vx2.off + row, vx2.tag, acc);
+                if (lane == 0) wsum[warp] = acc;
+                __syncthreads();
+                if (tid < a.world) {
+                    double t = wsum[0];
+#pragma unroll
+                    for (int w = 1; w < CYC_THREADS / 32; ++w) t += wsum[w];
+                    ll_store1(a.X[tid] + vx2.off + row, vx2.tag, t);
+                }
+                __syncthreads();
             }
         }
     }
@@ -638,6 +749,7 @@ struct tefem_precond {
     const uint8_t *x_mask = nullptr, *t_mask = nullptr;      // tefem_precond_set_cycle_masks
     int* d_err_local = nullptr;                  // time-out flag of the tagged loads without a communicator
     uint32_t local_epoch = 0;
+    unsigned long long gather_total = 0;         // ticks of the r2 gather counter so far
     // TEFEM_PROFILE_PRECOND=1 (diagnostics, stderr at destroy): device time of the three parts of an application -
     // restriction + all-reduce over the ranks + first sweep (includes waiting for the slowest rank), the level-1 / level-2
     // cycle (replicated work), the prolongation.  Synchronises the stream after every application: not for timed runs.
@@ -647,6 +759,8 @@ struct tefem_precond {
     int64_t n_apply = 0;
     double stamp_us[32] = {0.0};                 // persistent cycle: time of CTA 0 between its phase stamps
     int n_stamps = 0;
+    unsigned long long* d_all_stamps = nullptr;  // diagnostics only (allocated when TEFEM_PROFILE_PRECOND=1)
+    double phase_end_us[3][16] = {{0.0}};        // per phase: min / median / max over the CTAs of the time since the kernel's first stamp
 };
 
 static int64_t pc_align(int64_t n) { return (n + 15) / 16 * 16; }
@@ -673,7 +787,7 @@ extern "C" int64_t tefem_precond_peer_doubles(int32_t n_agg, int32_t n_agg2, int
 // Doubles of the caller's ZEROED, 128-byte aligned buffer for tefem_precond_set_coarse_mode(mode 1): the local tagged vectors
 // (bc, r2) and - used without a communicator - the shared ones.
 extern "C" int64_t tefem_precond_cycle_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
-    return 2 * (pc_align(8 * (int64_t)n_agg) + cycle_shared_units(n_agg, n_agg2, n_pre, n_post)) + 16;
+    return 2 * (pc_align(8 * (int64_t)n_agg) + cycle_shared_units(n_agg, n_agg2, n_pre, n_post)) + pc_align(8 * (int64_t)n_agg2) + 32;
 }
 
 extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, const int32_t* agg_ptr,
@@ -796,10 +910,19 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
                             "prolongation %.4f ms per application\n", (long long)p->n_apply, p->part_ms[0] / p->n_apply,
                     p->part_ms[1] / p->n_apply, p->part_ms[2] / p->n_apply);
         if (p->n_apply > 0 && p->n_stamps > 0) {
-            fprintf(stderr, "[tefem precond profile] persistent cycle, CTA 0, us per phase (phase 0, sweeps.., t, r2, x2, update, post..):");
+            fprintf(stderr, "[tefem precond profile] persistent cycle, CTA 0, us per phase (start flags, phase 0, sweeps.., t, r2, x2, update, post..):");
             for (int k = 1; k < p->n_stamps; ++k) fprintf(stderr, " %.2f", p->stamp_us[k] / p->n_apply);
             fprintf(stderr, "\n");
+            if (p->d_all_stamps) {
+                const char* nm[3] = {"first", "median", "last"};
+                for (int q = 0; q < 3; ++q) {
+                    fprintf(stderr, "[tefem precond profile] end of phase over all CTAs, us since the first CTA started (%s CTA):", nm[q]);
+                    for (int k = 0; k < p->n_stamps; ++k) fprintf(stderr, " %.2f", p->phase_end_us[q][k] / p->n_apply);
+                    fprintf(stderr, "\n");
+                }
+            }
         }
+        if (p->d_all_stamps) cudaFree(p->d_all_stamps);
         for (int k = 0; k < 4; ++k)
             if (p->ev[k]) cudaEventDestroy(p->ev[k]);
     }
@@ -845,10 +968,19 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
         a.rc[0] = p->rc;
         a.X[0] = p->cyc_local + a1;
     }
-    // diagnostics: the 16 spare doubles at the end of cycle_work hold the phase stamps of CTA 0
-    unsigned long long* d_stamps = reinterpret_cast<unsigned long long*>(
-        reinterpret_cast<double*>(p->cyc_local) + tefem_precond_cycle_doubles(p->n1, p->n2, p->n_pre, p->n_post) - 16);
+    // tail of cycle_work: r2 as a plain vector, then 32 words: the phase stamps of CTA 0 (diagnostics) and the gather counter
+    double* tail = reinterpret_cast<double*>(p->cyc_local) + tefem_precond_cycle_doubles(p->n1, p->n2, p->n_pre, p->n_post) - 32;
+    unsigned long long* d_stamps = reinterpret_cast<unsigned long long*>(tail);
     a.stamps = p->profile ? d_stamps : nullptr;
+    if (p->profile && !p->d_all_stamps) {
+        if (cudaMalloc(reinterpret_cast<void**>(&p->d_all_stamps), sizeof(unsigned long long) * 16 * (size_t)p->cyc_grid) != cudaSuccess)
+            p->d_all_stamps = nullptr;
+    }
+    a.all_stamps = p->profile ? p->d_all_stamps : nullptr;
+    a.r2_plain = tail - a2;
+    a.gathered = reinterpret_cast<unsigned long long*>(tail + 16);
+    p->gather_total += CYC_GATHER_CTAS;
+    a.gathered_target = p->gather_total;
     a.a0 = (int32_t)((int64_t)p->n1 * a.rank / a.world); a.a1 = (int32_t)((int64_t)p->n1 * (a.rank + 1) / a.world);
     a.j0 = (int32_t)((int64_t)p->n2 * a.rank / a.world); a.j1 = (int32_t)((int64_t)p->n2 * (a.rank + 1) / a.world);
     if (p->profile) cudaEventRecord(p->ev[0], st);
@@ -879,10 +1011,23 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
             }
             p->n_apply += 1;
             unsigned long long h[16];
-            const int ns = 5 + a.n_iterates - 1 < 16 ? 5 + a.n_iterates - 1 : 16;    // start, phase 0, sweeps, t, r2, x2, update, post
+            const int ns = 6 + a.n_iterates - 1 < 16 ? 6 + a.n_iterates - 1 : 16;    // entry, start flags, phase 0, sweeps, t, r2, x2, update, post
             if (cudaMemcpy(h, d_stamps, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
                 for (int k = 1; k < ns; ++k) p->stamp_us[k] += 1e-3 * (double)(h[k] - h[k - 1]);
                 p->n_stamps = ns;
+            }
+            if (p->d_all_stamps) {
+                std::vector<unsigned long long> all(16 * (size_t)p->cyc_grid);
+                if (cudaMemcpy(all.data(), p->d_all_stamps, sizeof(unsigned long long) * all.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                    unsigned long long t0 = ~0ULL;
+                    for (int c = 0; c < p->cyc_grid; ++c) t0 = all[16 * (size_t)c] < t0 ? all[16 * (size_t)c] : t0;
+                    std::vector<double> v((size_t)p->cyc_grid);
+                    for (int k = 0; k < ns; ++k) {
+                        for (int c = 0; c < p->cyc_grid; ++c) v[(size_t)c] = 1e-3 * (double)(all[16 * (size_t)c + k] - t0);
+                        std::sort(v.begin(), v.end());
+                        p->phase_end_us[0][k] += v.front(); p->phase_end_us[1][k] += v[v.size() / 2]; p->phase_end_us[2][k] += v.back();
+                    }
+                }
             }
         }
     }

@@ -263,6 +263,9 @@ int tefem_precond_apply(tefem_precond* pc, const double* r, double* z, void* str
 /* Multi-GPU: agg_ranks[n_agg] (uint8 device array, bit r set iff rank r owns fine nodes of the aggregate) restricts the
  * in-kernel all-reduce of the restricted residual to the ranks that contribute (the others hold exact zeros).      */
 int tefem_precond_set_agg_ranks(tefem_precond* pc, const uint8_t* agg_ranks);
+/* Multi-GPU, after set_agg_ranks: agg_list[n] (int32 device array) = the aggregates with fine nodes on THIS rank; the
+ * restriction then launches one CTA per listed aggregate instead of one per aggregate of the whole mesh.           */
+int tefem_precond_set_agg_list(tefem_precond* pc, const int32_t* agg_list, int32_t n);
 /* Level-1 operator in HALF precision (same block layout as sys1, 16 halves per block, 32-byte aligned; NULL detaches):
  * the six level-1 sweeps of an application then read half the bytes.  Preconditioner data only.                     */
 int tefem_precond_set_level1_half(tefem_precond* pc, const void* sys1_half);

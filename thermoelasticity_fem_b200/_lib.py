@@ -48,6 +48,7 @@ _SIGNATURES = {
     "tefem_precond_apply": [P, P, P, P],
     "tefem_solver_set_halo": [P, c_int32, c_int, P, P, P, P, P, P, P, c_int32, P, c_int32],
     "tefem_precond_set_agg_ranks": [P, P],
+    "tefem_precond_set_agg_list": [P, P, c_int32],
     "tefem_precond_set_level1_half": [P, P],
     "tefem_precond_set_cycle": [P, c_int],
     "tefem_precond_set_coarse_mode": [P, c_int, P],

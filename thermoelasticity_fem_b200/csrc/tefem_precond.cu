@@ -41,17 +41,47 @@ namespace tefem {
 // 24 us for 0.9 M nodes on one of eight GPUs); thread-strided partial sums, fixed shuffle tree, the four warp sums added
 // in warp order.  An aggregate without local nodes (most of them in a multi-GPU solve) writes zeros and leaves.
 constexpr int RESTRICT_THREADS = 128;
-__global__ void __launch_bounds__(RESTRICT_THREADS) restrict_kernel(int32_t n_agg, const int32_t* __restrict__ agg_ptr,
+// agg_list (optional): the aggregates with local nodes - one CTA each instead of one per aggregate of the whole mesh (on one
+// of eight GPUs 7 of 8 CTAs found an empty aggregate: ~7 us of launch waves).  Only together with agg_ranks: nobody reads
+// the partial sums of a rank without nodes in the aggregate.
+// Persistent coarse cycle on several GPUs (push.world > 1): the partial sums go straight to the rank that OWNS the aggregate
+// in the cycle (aggregate i -> rank floor(((i + 1) world - 1) / n_agg)), as tagged values (tefem "LL" layout, below) in slot
+// [this rank] of the owner's partial-sum area - a remote store over NVLink.  The owner's cycle kernel waits for the tags: no
+// flag exchange and no remote read opens the cycle.
+struct RestrictPush {
+    int world = 0, rank = 0;
+    uint4* base[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // partial-sum areas
+    int64_t slot_units = 0;                      // 16-byte units per source-rank slot
+    uint32_t tag = 0;
+};
+__device__ __forceinline__ void ll_store1_early(uint4* p, uint32_t tag, double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = (unsigned long long)(uint32_t)b | ((unsigned long long)tag << 32);
+    const unsigned long long hi = (unsigned long long)(uint32_t)(b >> 32) | ((unsigned long long)tag << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__global__ void __launch_bounds__(RESTRICT_THREADS) restrict_kernel(int32_t n_agg, int32_t n_agg_total, const int32_t* __restrict__ agg_list,
+                                                                    const int32_t* __restrict__ agg_ptr,
                                                                     const int32_t* __restrict__ agg_nodes,
                                                                     const float4* __restrict__ node_off,
-                                                                    const double* __restrict__ r, double* __restrict__ rc) {
+                                                                    const double* __restrict__ r, double* __restrict__ rc,
+                                                                    const RestrictPush push) {
     __shared__ double part[RESTRICT_THREADS / 32][8];
-    const int agg = (int)blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (agg >= n_agg) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= n_agg) return;
+    const int agg = agg_list ? agg_list[blockIdx.x] : (int)blockIdx.x;
     const int32_t s = agg_ptr[agg], t = agg_ptr[agg + 1];
+    uint4* dst = nullptr;
+    if (push.world > 1) {
+        const int owner = (int)((((int64_t)agg + 1) * push.world - 1) / n_agg_total);
+        dst = push.base[owner] + (int64_t)push.rank * push.slot_units + 8 * (int64_t)agg;
+    }
     double* o = rc + 8 * (int64_t)agg;
     if (s == t) {
-        if (threadIdx.x < 8) o[threadIdx.x] = 0.0;
+        if (threadIdx.x < 8) {
+            if (dst) ll_store1_early(dst + threadIdx.x, push.tag, 0.0);
+            else o[threadIdx.x] = 0.0;
+        }
         return;
     }
     double a[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -74,13 +104,15 @@ __global__ void __launch_bounds__(RESTRICT_THREADS) restrict_kernel(int32_t n_ag
         for (int k = 0; k < 7; ++k) part[warp][k] = a[k];
     }
     __syncthreads();
-    if (threadIdx.x < 7) {
-        double v = part[0][threadIdx.x];
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        if (threadIdx.x < 7) {
+            v = part[0][threadIdx.x];
 #pragma unroll
-        for (int w = 1; w < RESTRICT_THREADS / 32; ++w) v += part[w][threadIdx.x];
-        o[threadIdx.x] = v;
-    } else if (threadIdx.x == 7) {
-        o[7] = 0.0;
+            for (int w = 1; w < RESTRICT_THREADS / 32; ++w) v += part[w][threadIdx.x];
+        }
+        if (dst) ll_store1_early(dst + threadIdx.x, push.tag, v);
+        else o[threadIdx.x] = v;
     }
 }
 
@@ -282,7 +314,7 @@ __global__ void __launch_bounds__(128) dense_matvec_kernel(int32_t n, const floa
 constexpr int CYC_THREADS = 256;
 constexpr int CYC_GATHER_CTAS = 4;       // CTAs that copy r2 out of its tagged replica for everybody else (no polling storm)
 constexpr int CYC_MAX_X = 24;            // vector numbers: level-1 iterates 0 .. CYC_MAX_X - 1, then t, x2, bc, r2
-enum { CYC_V_T = 24, CYC_V_X2 = 25, CYC_V_BC = 26, CYC_V_R2 = 27 };
+enum { CYC_V_T = 24, CYC_V_X2 = 25, CYC_V_BC = 26, CYC_V_R2 = 27, CYC_V_RC = 28 };
 
 struct CycleArgs {
     const int32_t *rowptr1, *colidx1;
@@ -295,11 +327,13 @@ struct CycleArgs {
     double wc;
     int n_pre, n_post, overlap;
     int world, rank;
-    const double* rc[PEER_MAX_RANKS];    // the ranks' partial restricted residuals (world == 1: the local one)
+    const double* rc[PEER_MAX_RANKS];    // world == 1: rc[0] = the restricted residual (plain doubles)
+    int64_t part_off;                    // world > 1: offset (units, from X[r]) of the tagged partial sums, slot q = rank q's
     uint4* X[PEER_MAX_RANKS];            // tagged vectors of rank r: iterate k at k * vec_units, t at m, x2 at m + 1, r2 after x2 (m = n_iterates)
     uint4* bc;                           // local tagged vector: D1^-1 rc on the own rows
     const uint8_t *x_mask, *t_mask;      // per aggregate: the ranks that read its level-1 iterates / its residual t (null: all)
     int32_t j0, j1;                      // own level-2 aggregates: rows of P2^T and of the dense inverse
+    double* xc_plain;                    // local: the final iterate as plain doubles (aggregates with local fine nodes)
     double* r2_plain;                    // local: r2 gathered from its tagged replica by the first CYC_GATHER_CTAS CTAs
     unsigned long long* gathered;        // local counter of finished gather CTAs (never reset)
     unsigned long long gathered_target;  // its value when this application's r2 is complete
@@ -517,23 +551,8 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
     if (tid < PEER_MAX_RANKS) reps[tid] = a.X[tid];
     int stamp = 0;
     cyc_stamp(a, stamp++);                               // kernel entry
-    // every rank's restriction has finished (its partial sums are visible) and none is still reading a vector of the
-    // previous application (whose buffers this one overwrites)
-    if (a.world > 1) {
-        if (blockIdx.x == 0 && tid < a.world) {
-            __threadfence_system();
-            st_release_sys(a.flags[tid] + a.rank, a.tag_base);
-        }
-        if (tid < a.world) {
-            const uint32_t* f = a.flags[a.rank] + tid;
-            if ((int32_t)(ld_acquire_sys(f) - a.tag_base) < 0 && !*reinterpret_cast<volatile int*>(a.err)) {
-                const long long t0 = clock64();
-                while ((int32_t)(ld_acquire_sys(f) - a.tag_base) < 0) {
-                    if (clock64() - t0 > a.timeout) { *a.err = 1; break; }
-                }
-            }
-        }
-    }
+    // No start synchronisation: the partial sums of the restriction arrive as tagged values (phase 0 waits for them), and
+    // the tagged vectors of consecutive applications live in two alternating areas (apply_persistent).
     __syncthreads();
     {   // operators of the own rows -> L2 (level 1, dense level-2 rows, transfer operators)
         const int32_t b0 = a.rowptr1[2 * a.a0], b1 = a.rowptr1[2 * a.a1];
@@ -567,10 +586,14 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
             double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             for (int r = 0; r < a.world; ++r) {
                 if (!((mask >> r) & 1u)) continue;
-                const double* src = a.rc[r] + 8 * (int64_t)i;
                 double v[8];
+                if (a.world > 1) {      // tagged partial sums of rank r, pushed into this rank's area by its restriction
+                    ll_load<8>(mine + a.part_off + (int64_t)r * U + 8 * (int64_t)i, T + CYC_V_RC, v, a.err, a.timeout);
+                } else {
+                    const double* src = a.rc[0] + 8 * (int64_t)i;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ld_volatile_v2(src + 2 * q, v[2 * q], v[2 * q + 1]);
+                    for (int q = 0; q < 4; ++q) ld_volatile_v2(src + 2 * q, v[2 * q], v[2 * q + 1]);
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) s[q] += v[q];
             }
@@ -699,26 +722,17 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
         ++it;
         cyc_stamp(a, stamp++);
     }
-}
-
-// Prolongation that reads the tagged final iterate of the persistent cycle: rows owned by other ranks may still be on
-// their way when this kernel starts (their producers are other GPUs' cycle kernels, which never wait for this kernel).
-__global__ void __launch_bounds__(256) prolong_combine_ll_kernel(int64_t n_nodes, const int32_t* __restrict__ node_agg,
-                                                                 const float4* __restrict__ node_off, double omega,
-                                                                 const double* __restrict__ r, const uint4* xc, uint32_t tag,
-                                                                 double* __restrict__ z, int* err, long long timeout) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    double r0, r1, r2, r3;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r0), "=d"(r1), "=d"(r2), "=d"(r3) : "l"(r + 4 * i));
-    double c[8];
-    ll_load<8>(xc + 8 * (int64_t)node_agg[i], tag, c, err, timeout);
-    const float4 d = node_off[i];
-    r0 = omega * r0 + c[0] + (c[5] * (double)d.z - c[6] * (double)d.y);
-    r1 = omega * r1 + c[1] + (c[6] * (double)d.x - c[4] * (double)d.z);
-    r2 = omega * r2 + c[2] + (c[4] * (double)d.y - c[5] * (double)d.x);
-    r3 = omega * r3 + c[3];
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(z + 4 * i), "d"(r0), "d"(r1), "d"(r2), "d"(r3) : "memory");
+    {   // the final iterate of the aggregates with local fine nodes as PLAIN doubles: the prolongation reads the 8 values of an
+        // aggregate once per node (~500 times) - from L1 when they are plain, 128 bytes of L2 traffic per node when tagged
+        const CycVec x = iterate(it);
+        const int64_t n = 8 * (int64_t)a.n1;
+        for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+            if (a.world > 1 && a.agg_ranks && !((a.agg_ranks[c >> 3] >> me) & 1)) continue;
+            double v[1];
+            ll_load<1>(x.rd + c, x.tag, v, a.err, a.timeout);
+            a.xc_plain[c] = v[0];
+        }
+    }
 }
 
 }  // namespace tefem
@@ -747,6 +761,9 @@ struct tefem_precond {
     int cyc_grid = 0;                            // CTAs of the persistent kernel (<= co-resident limit)
     uint4* cyc_local = nullptr;                  // caller's zeroed buffer of tagged vectors (tefem_precond_cycle_doubles)
     const uint8_t *x_mask = nullptr, *t_mask = nullptr;      // tefem_precond_set_cycle_masks
+    const int32_t* agg_list = nullptr;           // aggregates with local nodes (tefem_precond_set_agg_ranks), or null: all
+    int32_t n_agg_list = 0;
+    double* xc_plain = nullptr;                  // persistent cycle: the final iterate as plain doubles for the prolongation
     int* d_err_local = nullptr;                  // time-out flag of the tagged loads without a communicator
     uint32_t local_epoch = 0;
     unsigned long long gather_total = 0;         // ticks of the r2 gather counter so far
@@ -778,16 +795,20 @@ static int cycle_iterates(int n_pre, int n_post, bool overlap) {
 static int64_t cycle_shared_units(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
     return (int64_t)(cycle_iterates(n_pre, n_post, false) + 1) * pc_align(8 * (int64_t)n_agg) + 2 * pc_align(8 * (int64_t)n_agg2);
 }
+// ... and, with a communicator, one slot of tagged partial restricted residuals per source rank
+static int64_t cycle_peer_units(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
+    return cycle_shared_units(n_agg, n_agg2, n_pre, n_post) + (int64_t)PEER_MAX_RANKS * pc_align(8 * (int64_t)n_agg);
+}
 
 // Capacity (doubles per parity) of the peer-memory region the row-partitioned coarse cycle needs (tefem_comm_shm_alloc):
 // the partial restricted residual, then the tagged vectors (16 bytes per value).
 extern "C" int64_t tefem_precond_peer_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
-    return pc_align(8 * (int64_t)n_agg) + 2 * cycle_shared_units(n_agg, n_agg2, n_pre, n_post);
+    return pc_align(8 * (int64_t)n_agg) + 4 * cycle_peer_units(n_agg, n_agg2, n_pre, n_post);       // two application parities
 }
 // Doubles of the caller's ZEROED, 128-byte aligned buffer for tefem_precond_set_coarse_mode(mode 1): the local tagged vectors
 // (bc, r2) and - used without a communicator - the shared ones.
 extern "C" int64_t tefem_precond_cycle_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post) {
-    return 2 * (pc_align(8 * (int64_t)n_agg) + cycle_shared_units(n_agg, n_agg2, n_pre, n_post)) + pc_align(8 * (int64_t)n_agg2) + 32;
+    return 2 * (pc_align(8 * (int64_t)n_agg) + 2 * cycle_shared_units(n_agg, n_agg2, n_pre, n_post)) + pc_align(8 * (int64_t)n_agg2) + 32;
 }
 
 extern "C" int tefem_precond_create(tefem_precond** out, int32_t n_rows, int32_t n_agg, const int32_t* agg_ptr,
@@ -903,6 +924,16 @@ extern "C" int tefem_precond_set_agg_ranks(tefem_precond* p, const uint8_t* agg_
     return TEFEM_OK;
 }
 
+// Multi-GPU: the aggregates that have fine nodes on this rank (device array of n indices): the restriction launches one
+// CTA per listed aggregate.  Requires agg_ranks (partial sums of unlisted aggregates are never written nor read).
+extern "C" int tefem_precond_set_agg_list(tefem_precond* p, const int32_t* agg_list, int32_t n) {
+    TEFEM_REQUIRE(p && n >= 0 && (n == 0 || agg_list), "arguments");
+    TEFEM_REQUIRE(p->agg_ranks, "set agg_ranks first");
+    p->agg_list = n > 0 ? agg_list : nullptr;
+    p->n_agg_list = n;
+    return TEFEM_OK;
+}
+
 extern "C" int tefem_precond_destroy(tefem_precond* p) {
     if (p && p->profile) {
         if (p->n_apply > 0)
@@ -933,7 +964,8 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
 // One application with the row-partitioned persistent coarse cycle: restriction, coarse_cycle_kernel, prolongation.
 static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaStream_t st) {
     const int64_t a1 = pc_align(8 * (int64_t)p->n1), a2 = pc_align(8 * (int64_t)p->n2);
-    const unsigned gr = (unsigned)p->n1;                                                        // restriction: one CTA per aggregate
+    const int32_t n_restrict = p->agg_list ? p->n_agg_list : p->n1;                             // restriction: one CTA per (local) aggregate
+    const unsigned gr = (unsigned)(n_restrict > 0 ? n_restrict : 1);
     CycleArgs a;
     memset(&a, 0, sizeof(a));
     a.rowptr1 = p->rowptr1; a.colidx1 = p->colidx1;
@@ -945,6 +977,7 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
     a.wc = p->omega_c; a.n_pre = p->n_pre; a.n_post = p->n_post; a.overlap = p->overlap ? 1 : 0;
     a.bc = p->cyc_local;
     a.vec_units = a1; a.a2_units = a2;
+    a.part_off = cycle_shared_units(p->n1, p->n2, p->n_pre, p->n_post);
     a.x_mask = p->x_mask; a.t_mask = p->t_mask;
     a.n_iterates = cycle_iterates(p->n_pre, p->n_post, p->overlap);
     double* rc_mine = p->rc;
@@ -955,18 +988,19 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
         a.err = pc.err; a.timeout = pc.timeout;
         for (int q = 0; q < pc.world; ++q) {
             double* big = reinterpret_cast<double*>(pc.base[q] + PEER_BIG_OFFSET);
-            a.rc[q] = big + (int64_t)(pc.epoch & 1u) * pc.cap;
-            a.X[q] = reinterpret_cast<uint4*>(big + a1);
+            // the tagged vectors of consecutive applications alternate between two areas: a rank can run ahead of another by
+            // less than one application (the dense level-2 product needs P2^T t of every rank), so an area is rewritten only
+            // after all its readers have left the application that used it
+            a.X[q] = reinterpret_cast<uint4*>(big + a1) + (int64_t)(pc.epoch & 1u) * cycle_peer_units(p->n1, p->n2, p->n_pre, p->n_post);
             a.flags[q] = reinterpret_cast<uint32_t*>(pc.base[q]) + (PEER_CH_CYCLE * 2) * PEER_MAX_RANKS;
         }
-        rc_mine = const_cast<double*>(a.rc[pc.rank]);
     } else {
         a.world = 1; a.rank = 0;
         a.tag_base = (++p->local_epoch) * 32u;
         a.err = p->d_err_local;                                   // local producers cannot be lost
         a.timeout = PEER_TIMEOUT_DEFAULT;
         a.rc[0] = p->rc;
-        a.X[0] = p->cyc_local + a1;
+        a.X[0] = p->cyc_local + a1 + (int64_t)(p->local_epoch & 1u) * cycle_shared_units(p->n1, p->n2, p->n_pre, p->n_post);
     }
     // tail of cycle_work: r2 as a plain vector, then 32 words: the phase stamps of CTA 0 (diagnostics) and the gather counter
     double* tail = reinterpret_cast<double*>(p->cyc_local) + tefem_precond_cycle_doubles(p->n1, p->n2, p->n_pre, p->n_post) - 32;
@@ -978,13 +1012,19 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
     }
     a.all_stamps = p->profile ? p->d_all_stamps : nullptr;
     a.r2_plain = tail - a2;
+    a.xc_plain = p->xc;
     a.gathered = reinterpret_cast<unsigned long long*>(tail + 16);
     p->gather_total += CYC_GATHER_CTAS;
     a.gathered_target = p->gather_total;
     a.a0 = (int32_t)((int64_t)p->n1 * a.rank / a.world); a.a1 = (int32_t)((int64_t)p->n1 * (a.rank + 1) / a.world);
     a.j0 = (int32_t)((int64_t)p->n2 * a.rank / a.world); a.j1 = (int32_t)((int64_t)p->n2 * (a.rank + 1) / a.world);
     if (p->profile) cudaEventRecord(p->ev[0], st);
-    restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, rc_mine);
+    RestrictPush push;
+    if (p->comm) {      // partial sums go to the owner of the aggregate as tagged values
+        push.world = a.world; push.rank = a.rank; push.slot_units = a.vec_units; push.tag = a.tag_base + 1u + CYC_V_RC;
+        for (int q = 0; q < a.world; ++q) push.base[q] = a.X[q] + a.part_off;
+    }
+    restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(n_restrict, p->n1, p->agg_list, p->agg_ptr, p->agg_nodes, p->node_off, r, rc_mine, push);
     TEFEM_LAUNCH_CHECK();
     if (p->profile) cudaEventRecord(p->ev[1], st);
     void* kargs[] = {&a};
@@ -994,12 +1034,10 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
     TEFEM_CUDA_CHECK(cudaLaunchKernel(fn, dim3((unsigned)p->cyc_grid), dim3(CYC_THREADS), kargs, sizeof(double) * 8 * (size_t)p->n2, st));
     count_launch();
     TEFEM_CUDA_CHECK(cudaGetLastError());
-    const uint4* cur = a.X[a.rank] + (int64_t)(a.n_iterates - 1) * a.vec_units;           // the last iterate, tagged
-    const uint32_t cur_tag = a.tag_base + 1u + (uint32_t)(a.n_iterates - 1);
     if (p->profile) cudaEventRecord(p->ev[2], st);
     if (p->n_rows > 0) {
-        prolong_combine_ll_kernel<<<(unsigned)ceil_div((int64_t)p->n_rows, 256), 256, 0, st>>>(
-            p->n_rows, p->node_agg, p->node_off, p->omega, r, cur, cur_tag, z, a.err, a.timeout);
+        prolong_combine_kernel<<<(unsigned)ceil_div((int64_t)p->n_rows, 256), 256, 0, st>>>(p->n_rows, p->node_agg, p->node_off,
+                                                                                            p->omega, r, p->xc, z);
         TEFEM_LAUNCH_CHECK();
     }
     if (p->profile) {
@@ -1042,7 +1080,8 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
     const unsigned g1 = (unsigned)ceil_div(n1, 256);                                           // one thread per scalar of level 1
     const unsigned gs1 = (unsigned)ceil_div((int64_t)COARSE_LANES * np1, 256);                 // coarse_spmv: 16 lanes per block row
     const unsigned gs2 = (unsigned)ceil_div((int64_t)COARSE_LANES * np2, 256);
-    const unsigned gr = (unsigned)p->n1;                                                        // restriction: one CTA per aggregate
+    const int32_t n_restrict = p->agg_list ? p->n_agg_list : p->n1;                             // restriction: one CTA per (local) aggregate
+    const unsigned gr = (unsigned)(n_restrict > 0 ? n_restrict : 1);
     if (p->profile) cudaEventRecord(p->ev[0], st);
     // level 0 -> 1: rc = P1^T r, summed over the ranks (levels 1 and 2 are replicated): the restriction writes
     // into this rank's peer buffer and the next kernel does all-reduce + D1^-1 + first smoothing step in one
@@ -1051,13 +1090,13 @@ int tefem_precond_apply_stream(tefem_precond* p, const double* r, double* z, cud
                       "the peer-memory region must hold 8 * n_agg doubles (tefem_comm_shm_alloc)");
         const PeerCtx pc = tefem_comm_peer_ctx(p->comm, PEER_CH_COARSE);
         double* mine = reinterpret_cast<double*>(pc.base[pc.rank] + PEER_BIG_OFFSET) + (int64_t)(pc.epoch & 1u) * pc.cap;
-        restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, mine);
+        restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(n_restrict, p->n1, p->agg_list, p->agg_ptr, p->agg_nodes, p->node_off, r, mine, RestrictPush());
         TEFEM_LAUNCH_CHECK();
         peer_coarse_start_kernel<<<(unsigned)ceil_div((int64_t)p->n1, 128), 128, 0, st>>>(pc, p->n1, p->agg_ranks, p->dinv1, p->omega_c,
                                                                                           p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();
     } else {
-        restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(p->n1, p->agg_ptr, p->agg_nodes, p->node_off, r, p->rc);
+        restrict_kernel<<<gr, RESTRICT_THREADS, 0, st>>>(n_restrict, p->n1, p->agg_list, p->agg_ptr, p->agg_nodes, p->node_off, r, p->rc, RestrictPush());
         TEFEM_LAUNCH_CHECK();
         coarse_start_kernel<<<g1, 256, 0, st>>>(n1, p->dinv1, p->rc, p->omega_c, p->bc, p->xc);
         TEFEM_LAUNCH_CHECK();

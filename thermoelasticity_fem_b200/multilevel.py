@@ -286,6 +286,7 @@ class TwoLevelPreconditioner:
         if coarse not in ("auto", "launches", "persistent"):
             raise ValueError("coarse must be 'auto', 'launches' or 'persistent'")
         self.coarse = ("persistent" if comm is not None else "launches") if coarse == "auto" else coarse
+        self._coarse_auto = coarse == "auto"
         if cycle not in ("overlapped", "classic"):
             raise ValueError("cycle must be 'overlapped' or 'classic'")
         self.cycle = cycle
@@ -319,6 +320,8 @@ class TwoLevelPreconditioner:
         self.node_off[:, :3] = A["off"][:n_own].to(torch.float32)
         # ---- level 2 (host, a few hundred aggregates): transfer operators and dense inverse of P2^T A1^ P2
         agg2, n2, factor2 = build_level2(uniq, dims1, factor2, dense_limit)
+        if self._coarse_auto and self.coarse == "persistent" and 64 * n2 > 96 * 1024:
+            self.coarse = "launches"      # the persistent kernel stages P2^T t (8 n2 doubles) in shared memory
         self.factor2 = factor2
         P2 = transfer_level2(A["centres"].cpu().numpy(), agg2, n2)
         A1 = sp.bsr_array((self.sys1.double().cpu().numpy().reshape(-1, 4, 4), self.colidx1.cpu().numpy(),
@@ -364,6 +367,10 @@ class TwoLevelPreconditioner:
             p(self.inv2), p(self.work), comm.handle if comm is not None else None))
         if self.agg_ranks is not None:
             _lib.check(lib.tefem_precond_set_agg_ranks(self.handle, p(self.agg_ranks)))
+            # the aggregates with fine nodes on this rank: the restriction runs one CTA per listed aggregate
+            self.agg_list = torch.nonzero((self.agg_ptr[1:] - self.agg_ptr[:-1]) > 0).reshape(-1).to(i32).contiguous()
+            if 0 < int(self.agg_list.numel()) < n1:
+                _lib.check(lib.tefem_precond_set_agg_list(self.handle, p(self.agg_list), int(self.agg_list.numel())))
         if self.sys1_half is not None:
             _lib.check(lib.tefem_precond_set_level1_half(self.handle, p(self.sys1_half)))
         self.cycle = cycle

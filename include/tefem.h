@@ -273,14 +273,16 @@ int tefem_precond_set_level1_half(tefem_precond* pc, const void* sys1_half);
  * same residual (one level-1 product less per application); 0: classic V-cycle (all pre-sweeps, then the residual).  */
 int tefem_precond_set_cycle(tefem_precond* pc, int overlapped);
 /* Coarse cycle of an application.  mode 0: separate launches on levels replicated on every rank (~10 dependent small
- * kernels per application whatever the number of GPUs).  mode 1: ONE persistent cooperative kernel; the rows of levels 1
- * and 2 are PARTITIONED over the ranks, every coarse vector has one replica per rank in the peer-memory region in a
- * self-validating layout (16 bytes per value: two 8-byte units {32 data bits, 32-bit tag}), the rank that owns a row
- * computes it and stores it into all replicas (remote stores over NVLink), and a consumer retries its load until the tags
- * match: no barrier inside the kernel (csrc/tefem_precond.cu, coarse_cycle_kernel).  cycle_work: ZEROED, 128-byte
- * aligned buffer of tefem_precond_cycle_doubles(...) doubles owned by the caller (mode 1; NULL for mode 0).  With a
- * communicator its region must have been allocated with big_cap_doubles >= tefem_precond_peer_doubles(...); without one
- * the same kernel runs on cycle_work alone.  Call after set_cycle / set_level1_half.                                  */
+ * kernels per application whatever the number of GPUs).  mode 1: ONE persistent kernel (plain launch, grid within the
+ * co-resident limit); the rows of levels 1 and 2 are PARTITIONED over the ranks, every coarse vector has one replica per
+ * rank in the peer-memory region in a self-validating layout (16 bytes per value: two 8-byte units {32 data bits, 32-bit
+ * tag}), the rank that owns a row computes it and stores it into the replicas of the ranks that read it (remote stores
+ * over NVLink, tefem_precond_set_cycle_masks), the restriction pushes its partial sums the same way to the owner of the
+ * aggregate, and a consumer retries its load until the tags match: no barrier, fence or flag (csrc/tefem_precond.cu,
+ * coarse_cycle_kernel).  cycle_work: ZEROED, 128-byte aligned buffer of tefem_precond_cycle_doubles(...) doubles owned
+ * by the caller (mode 1; NULL for mode 0).  With a communicator its ZEROED region must have been allocated with
+ * big_cap_doubles >= tefem_precond_peer_doubles(...) and every rank must apply the preconditioner the same number of
+ * times; without one the same kernel runs on cycle_work alone.  Call after set_cycle / set_level1_half.              */
 int tefem_precond_set_coarse_mode(tefem_precond* pc, int mode, double* cycle_work);
 int64_t tefem_precond_peer_doubles(int32_t n_agg, int32_t n_agg2, int n_pre, int n_post);
 /* Persistent cycle on several GPUs: x_mask[n_agg] / t_mask[n_agg] (uint8 device arrays, bit q) = rank q reads the level-1

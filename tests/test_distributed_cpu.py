@@ -305,3 +305,19 @@ def test_cycle_masks_cover_every_read_of_the_row_partitioned_coarse_cycle(world)
         need = np.flatnonzero(np.repeat(np.array([q in s for s in fine_rank_of_agg]), 8))     # prolongation reads
         assert not np.isnan(X[q][need]).any(), "the prolongation reads a coarse value that was not sent to its rank"
         assert np.abs(X[q][need] - x[need]).max() <= 1e-12 * np.abs(x).max()
+
+
+def test_row_owner_matches_the_kernel_side_formula():
+    """multilevel.row_owner (destination masks, Python) and the owner the restriction kernel computes for an aggregate
+    (csrc/tefem_precond.cu restrict_kernel: ((i + 1) world - 1) / n, integer division) must agree, and both must describe
+    the contiguous ranges [n q / world, n (q + 1) / world) that apply_persistent hands to the cycle kernel."""
+    from thermoelasticity_fem_b200.multilevel import row_owner
+    for n in (1, 2, 7, 8, 27, 125, 511, 3375, 13824):
+        for world in (1, 2, 3, 4, 8):
+            if n < world:
+                continue
+            own = row_owner(n, world).tolist()
+            assert own == [((i + 1) * world - 1) // n for i in range(n)]
+            for q in range(world):
+                lo, hi = n * q // world, n * (q + 1) // world
+                assert all(o == q for o in own[lo:hi]) and own.count(q) == hi - lo

@@ -21,9 +21,11 @@
 //     as small block-CSR matrices) and a DENSE inverse (a few hundred aggregates), and a post-smoothing step;
 //   * the fine level needs NO extra SpMV: per application one restriction pass and one prolongation pass over
 //     the fine vector, the level-1 work is ~1/100 of a fine SpMV.
-// Every step is a fixed linear operator (fixed sweeps, no inner Krylov), so BiCGSTAB stays valid.  In the
-// multi-GPU case level 1 and 2 are replicated on every rank: the restricted residual (8 * n_agg doubles) is
-// summed over the ranks through NVLink peer memory inside the kernel that starts the V-cycle.
+// Every step is a fixed linear operator (fixed sweeps, no inner Krylov), so BiCGSTAB stays valid.  On several GPUs the
+// coarse cycle runs either on levels replicated on every rank (separate launches; the restricted residual, 8 * n_agg
+// doubles, is summed over the ranks through NVLink peer memory inside the kernel that starts the V-cycle) or - the
+// default - with the rows of levels 1 and 2 partitioned over the ranks in one persistent dataflow kernel
+// (coarse_cycle_kernel below).
 #include "tefem_common.cuh"
 #include "tefem_comm.h"
 #include "tefem_precond.h"
@@ -296,21 +298,25 @@ __global__ void __launch_bounds__(128) dense_matvec_kernel(int32_t n, const floa
 // The replicated cycle above is ~10 dependent launches of ~10 - 14 us each on EVERY rank, whatever the number of GPUs: at
 // 8 GPUs it was 29 % of a BiCGSTAB iteration and the first limit of strong scaling (profiles/README.md).  Here the rows of
 // levels 1 and 2 are PARTITIONED: rank q owns the aggregates [n1 q / world, n1 (q + 1) / world) (both pseudo nodes) and
-// the scalar rows [n q / world, ..) of the dense level-2 inverse.  Every coarse vector of the cycle has its own buffer
-// (one per phase: nothing is overwritten inside an application) with one REPLICA per rank in the peer-mapped region, in a
-// SELF-VALIDATING layout: a double is stored as the 16 bytes {low word, tag, high word, tag} (two 8-byte units, each
-// written atomically), where tag = 32 * application + vector number.  The rank that owns a row computes it - lane mapping
-// and summation order of coarse_spmv_kernel - and stores it into all replicas (256-bit stores, remote ones over NVLink);
-// a consumer loads the 16 bytes and simply retries until both tags match.  There is NO barrier and NO fence inside the
-// kernel: a phase starts on a row as soon as the values that row reads have arrived, so the latency of an application is
-// its dependency chain (one NVLink store + one L2 read per level-1 product), not ten grid-wide synchronisations.
-// (First version of this kernel: flag barriers over all CTAs of all ranks between the phases - a system fence after remote
-// stores, a ticket, a flag store, a poll: ~12 us per phase, SLOWER than the separate launches; profiles/README.md.)
+// the level-2 aggregates [n2 q / world, ..): their rows of P2^T and of the dense level-2 inverse.  Every coarse vector of
+// the cycle has its own buffer (one per phase: nothing is overwritten inside an application) with one REPLICA per rank in
+// the peer-mapped region, in a SELF-VALIDATING layout: a double is stored as the 16 bytes {low word, tag, high word, tag}
+// (two 8-byte units, each written atomically), where tag = 32 * application + vector number.  The rank that owns a row
+// computes it and stores it (strong 256-bit stores, remote ones over NVLink) into the replicas of the ranks that read it
+// (destination masks, tefem_precond_set_cycle_masks); a consumer loads the 16 bytes and simply retries until both tags
+// match.  There is NO barrier, NO fence and NO flag: the restriction kernel pushes its partial sums as tagged values to the
+// owner of the aggregate, and a phase starts on a row as soon as the values that row reads have arrived, so the latency of
+// an application is its dependency chain (per level-1 product one NVLink store-to-visible latency plus the row's L2
+// reads), not ten synchronisations.  The tagged vectors of consecutive applications alternate between two areas: a rank
+// runs ahead of another by less than one application (the dense level-2 product needs P2^T t of EVERY rank), so an area
+// is rewritten only after its readers have left the application that used it.
+// Versions that were measured and dropped (profiles/README.md): flag barriers over all CTAs of all ranks between the
+// phases (system fence after remote stores + ticket + flag + poll: ~12 us per phase, slower than the launches); weak
+// stores for the tagged values (they waited microseconds in a write-combining stage); a start-flag exchange; a
+// __nanosleep back-off in the retry loop; batched loads in the level-1 rows.
 // A value has exactly one producer, so the replicas are bitwise identical and so are the stop decisions of the ranks.
 // Waits are bounded like every peer wait.  All CTAs must be co-resident (consumers spin on producers of the same grid):
-// grid <= the occupancy limit of the device.  Before the first phase the kernel exchanges one flag per rank pair:
-// every rank's restriction has finished and no rank still reads the buffers of the previous application.
-// world == 1 runs the same kernel on local buffers.
+// grid <= the occupancy limit of the device.  world == 1 runs the same kernel on local buffers.
 constexpr int CYC_THREADS = 256;
 constexpr int CYC_GATHER_CTAS = 4;       // CTAs that copy r2 out of its tagged replica for everybody else (no polling storm)
 constexpr int CYC_MAX_X = 24;            // vector numbers: level-1 iterates 0 .. CYC_MAX_X - 1, then t, x2, bc, r2
@@ -340,7 +346,6 @@ struct CycleArgs {
     int64_t a2_units;                    // 16-byte units of a level-2 vector
     int64_t vec_units;                   // 16-byte units between consecutive vectors
     int n_iterates;
-    uint32_t* flags[PEER_MAX_RANKS];     // flags[r][src]: rank src's start flag in rank r's region
     uint32_t tag_base;                   // 32 * application
     int* err;
     long long timeout;
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__(CYC_THREADS, 3) coarse_cycle_kernel(const Cycl
         const int32_t d0 = a.p2_rowptr[2 * a.a0], d1 = a.p2_rowptr[2 * a.a1];
         cyc_prefetch(a.p2_vals + (int64_t)d0 * 16, (int64_t)(d1 - d0) * 64);
     }
-    cyc_stamp(a, stamp++);                               // start flags exchanged
+    cyc_stamp(a, stamp++);                               // operator prefetches issued
     const uint32_t T = a.tag_base + 1u;                  // tag of vector v: T + v
     const int64_t U = a.vec_units;
     const uint4* mine = a.X[me];
@@ -941,7 +946,7 @@ extern "C" int tefem_precond_destroy(tefem_precond* p) {
                             "prolongation %.4f ms per application\n", (long long)p->n_apply, p->part_ms[0] / p->n_apply,
                     p->part_ms[1] / p->n_apply, p->part_ms[2] / p->n_apply);
         if (p->n_apply > 0 && p->n_stamps > 0) {
-            fprintf(stderr, "[tefem precond profile] persistent cycle, CTA 0, us per phase (start flags, phase 0, sweeps.., t, r2, x2, update, post..):");
+            fprintf(stderr, "[tefem precond profile] persistent cycle, CTA 0, us per phase (prefetch, phase 0, sweeps.., t, r2, x2, update, post..):");
             for (int k = 1; k < p->n_stamps; ++k) fprintf(stderr, " %.2f", p->stamp_us[k] / p->n_apply);
             fprintf(stderr, "\n");
             if (p->d_all_stamps) {
@@ -992,7 +997,6 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
             // less than one application (the dense level-2 product needs P2^T t of every rank), so an area is rewritten only
             // after all its readers have left the application that used it
             a.X[q] = reinterpret_cast<uint4*>(big + a1) + (int64_t)(pc.epoch & 1u) * cycle_peer_units(p->n1, p->n2, p->n_pre, p->n_post);
-            a.flags[q] = reinterpret_cast<uint32_t*>(pc.base[q]) + (PEER_CH_CYCLE * 2) * PEER_MAX_RANKS;
         }
     } else {
         a.world = 1; a.rank = 0;
@@ -1049,7 +1053,7 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
             }
             p->n_apply += 1;
             unsigned long long h[16];
-            const int ns = 6 + a.n_iterates - 1 < 16 ? 6 + a.n_iterates - 1 : 16;    // entry, start flags, phase 0, sweeps, t, r2, x2, update, post
+            const int ns = 6 + a.n_iterates - 1 < 16 ? 6 + a.n_iterates - 1 : 16;    // entry, prefetch, phase 0, sweeps, t, r2, x2, update, post
             if (cudaMemcpy(h, d_stamps, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
                 for (int k = 1; k < ns; ++k) p->stamp_us[k] += 1e-3 * (double)(h[k] - h[k - 1]);
                 p->n_stamps = ns;

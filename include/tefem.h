@@ -129,17 +129,6 @@ int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int3
                    int64_t n_blocks, int ops, double alpha_M, double alpha_K,
                    double* vals_M, double* vals_K, double* vals_D,
                    int32_t* bad_elem, void* stream);
-/* Opt-in MIRROR layout of the pieces-first schedule (symbolic.mirror_schedule; round 2): the geometric sums of block (j, i)
- * are the transposes of those of block (i, j), so the item of a plain block (i, j), j > i, column j owned, also writes
- * block item_mirror[item] = (j, i) from the same shared-memory gathers (-1: no mirror) and the lower blocks have no item:
- * half the gathers of the off-diagonal blocks, which bound this kernel.  item_mirror: int32, laid out like item_inc
- * (16-byte aligned tile segments); h_max[6] = 1; no split lists.  Every block is still written exactly once, no atomics;
- * the values equal the direct layout's up to the rounding of one product order (<= 1e-15 relative).                    */
-int tefem_assemble_mirror(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
-                          const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
-                          const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
-                          const int32_t* item_mirror, const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M,
-                          double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem, void* stream);
 
 /* Threads per CTA of the pieces-first assembly kernel: 64, 128 or 256 (default; measurement knob - more, smaller CTAs per
  * SM need tiles of 2 x threads items).  Host-side setting of the calling process; no reference counterpart.      */

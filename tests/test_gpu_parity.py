@@ -128,47 +128,6 @@ def test_assembly_sandwich_vs_reference(sandwich_mesh2, sandwich):
         assert np.array_equal(model2._planes[nm].cpu().numpy(), model._planes[nm].cpu().numpy()), nm
 
 
-def test_mirror_layout_matches_direct_layout_on_the_gpu(sandwich):
-    """Opt-in mirror layout of K1 (symbolic.mirror_schedule, tefem_assemble_mirror): one thread produces block (i, j) and its
-    mirror (j, i).  Planes against the direct layout (<= 1e-14 of the plane's largest entry: one product order differs),
-    bitwise reproducible, on a three-material jittered box, the reference's mesh and a row-restricted schedule."""
-    import torch
-    from oracle import tefem_oracle as orc
-    from thermoelasticity_fem_b200.device import DeviceMesh
-    from thermoelasticity_fem_b200.symbolic import build_schedule
-    from thermoelasticity_fem_b200.synthetic import kuhn_box
-    cases = []
-    pts, tets, tris, nodes = kuhn_box(9, 6, 5, jitter=0.2, seed=2)
-    mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
-            3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
-    conn, mat_id, rows = orc.element_table(tets, mats)
-    cases.append((pts, conn, mat_id, rows, None, dict(items_per_cta=128, elem_budget=240)))
-    cases.append((pts, conn, mat_id, rows, (2 * pts.shape[0]) // 3, {}))
-    spts, blocks, groups = sandwich
-    m = orc.Material(*MAT2)
-    sconn, smat, srows = orc.element_table(groups["tet"], {1: m, 2: m, 3: m})
-    cases.append((spts, sconn, smat, srows, None, {}))
-    for pts, conn, mat_id, rows, n_rows, kw in cases:
-        conn_t = torch.from_numpy(conn).cuda()
-        planes = {}
-        for mirror in (False, True):
-            S = build_schedule(conn_t, pts.shape[0], n_rows, mat_id=torch.from_numpy(mat_id).cuda(), mirror=mirror, **kw)
-            assert S.mirrored == mirror
-            dm = DeviceMesh(pts, conn, mat_id, rows, n_rows=n_rows, schedule=S)
-            out = dm.assemble("MKD", 0.2, 0.3)
-            outK = dm.assemble("K", 0., 0.)
-            again = dm.assemble("MKD", 0.2, 0.3)
-            for nm in "MKD":
-                assert torch.equal(out[nm], again[nm]), nm                         # bitwise reproducible
-            assert torch.equal(out["K"], outK["K"])                                # fused launch == single-operator launch
-            planes[mirror] = {nm: out[nm].cpu().numpy() for nm in "MKD"}
-        for nm in "MKD":
-            a, b = planes[False][nm], planes[True][nm]
-            assert np.isfinite(b).all()
-            scale = np.abs(a).max(axis=1, keepdims=True) + 1e-300
-            assert (np.abs(a - b) / scale).max() < 1e-14, nm
-
-
 def test_assembly_kuhn_variants():
     from thermoelasticity_fem_b200 import Model
     g = golden("kuhn_small.npz")

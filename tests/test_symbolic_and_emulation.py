@@ -58,19 +58,11 @@ def emu_assemble(emu, S, pts, conn, mat_id, rows, ops, aM, aK):
     cta_xyz = np.ascontiguousarray(pts[a["cta_nodes"]])
     h_max = S.h_max()
     mask = sum({"M": 1, "K": 2, "D": 4}[c] for c in ops)
-    if S.mirrored:
-        mir = S.item_mirror.numpy()
-        rc = emu.tefem_emu_assemble_mirror(ptr(rows), ctypes.c_int(rows.shape[0]), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]),
-                                           ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_xyz), ptr(a["item_inc"]),
-                                           ptr(a["item_meta"]), ptr(mir), ptr(a["inc"]),
-                                           ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
-                                           ptr(vM), ptr(vK), ptr(vD), ptr(bad))
-    else:
-        rc = emu.tefem_emu_assemble(ptr(rows), ctypes.c_int(rows.shape[0]), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]),
-                                    ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_xyz), ptr(a["item_inc"]),
-                                    ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]), ptr(a["inc"]),
-                                    ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
-                                    ptr(vM), ptr(vK), ptr(vD), ptr(bad))
+    rc = emu.tefem_emu_assemble(ptr(rows), ctypes.c_int(rows.shape[0]), ctypes.c_int32(S.n_cta), ptr(h_max), ptr(a["cta_hdr"]),
+                                ptr(a["cta_elems"]), ptr(a["cta_conn8"]), ptr(cta_xyz), ptr(a["item_inc"]),
+                                ptr(a["item_meta"]), ptr(a["split_block"]), ptr(a["split_meta"]), ptr(a["inc"]),
+                                ctypes.c_int64(P), mask, ctypes.c_double(aM), ctypes.c_double(aK),
+                                ptr(vM), ptr(vK), ptr(vD), ptr(bad))
     assert rc == 0
     for nm, v in (("M", vM), ("K", vK), ("D", vD)):
         if nm in ops and bad.min() == 2 ** 31 - 1:                               # (a bad Jacobian yields inf / nan values)
@@ -502,61 +494,3 @@ def test_fixed_pitch_lists_keep_the_values_bitwise(emu, pf):
     v1, _ = emu_assemble(emu, S1, pts, conn, mat_id, rows, "MKD", 0.2, 0.1)
     for nm in "MKD":
         assert np.array_equal(v0[nm], v1[nm]), nm
-
-
-@pytest.mark.parametrize("case", ["kuhn3", "sandwich", "rows"])
-def test_mirror_layout_matches_the_direct_layout(emu, case, request):
-    """Mirror layout (symbolic.mirror_schedule + process_mirror_item): one item produces block (i, j) and its mirror (j, i).
-    Every block is written exactly once (the emulation starts from NaN planes), the values equal the direct layout's up to
-    the rounding of one product order, the kept items and their lists are untouched; three materials with interface blocks
-    (kept direct on both sides), the reference's mesh, and a row-restricted schedule (halo columns keep direct items)."""
-    n_rows = None
-    if case == "kuhn3":
-        pts, tets, tris, nodes = kuhn_box(6, 4, 4, jitter=0.2, seed=2)
-        mats = {1: orc.Material(2300, 64e9, 0.1, 1., 750., 4e-6, 20.), 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.),
-                3: orc.Material(2700, 70e9, 0.33, 200., 900., 2.3e-5, 30.)}
-        conn, mat_id, rows = orc.element_table(tets, mats)
-    elif case == "sandwich":
-        pts, blocks, groups = request.getfixturevalue("sandwich")
-        m = orc.Material(*MAT2)
-        conn, mat_id, rows = orc.element_table(groups["tet"], {1: m, 2: orc.Material(7800, 210e9, 0.3, 45., 460., 1.2e-5, 25.), 3: m})
-    else:
-        pts, tets, tris, nodes = kuhn_box(7, 4, 3)
-        conn, mat_id, rows = orc.element_table(tets, {k: orc.Material(*MAT2) for k in tets})
-        n_rows = (2 * pts.shape[0]) // 3
-    kw = dict(items_per_cta=96, elem_budget=200, max_chunk=6, mat_id=torch.from_numpy(mat_id), n_rows=n_rows)
-    S0 = build_schedule(torch.from_numpy(conn), pts.shape[0], **kw)
-    S1 = build_schedule(torch.from_numpy(conn), pts.shape[0], mirror=True, **kw)
-    assert S1.mirrored and not S0.mirrored and S1.n_blocks == S0.n_blocks and S1.n_cta == S0.n_cta
-    assert S1.n_items < S0.n_items and S1.smem_bytes() <= 220 * 1024
-    mir = S1.item_mirror.numpy()
-    H = S1.cta_hdr.numpy().astype(np.int64)
-    br, bc = S1.block_row.numpy().astype(np.int64), S1.colidx.numpy().astype(np.int64)
-    n_mirrored = 0
-    for c in range(S1.n_cta):
-        n_it, o_it, p0, n_pc = H[c, 0], H[c, 5], H[c, 10], H[c, 11]
-        iw = S1.item_inc.numpy()[o_it:o_it + n_it].astype(np.int64) & 0xffffffff
-        m = mir[o_it:o_it + n_it]
-        assert (m[:n_pc] == -1).all()
-        g = p0 + (iw[n_pc:] >> 16)
-        assert (np.diff(g) > 0).all()                                              # block items stay in block order
-        has = m[n_pc:] >= 0
-        n_mirrored += int(has.sum())
-        assert (bc[g[has]] > br[g[has]]).all() and (bc[g[has]] < S1.n_rows).all()
-        assert (br[m[n_pc:][has]] == bc[g[has]]).all() and (bc[m[n_pc:][has]] == br[g[has]]).all()
-    assert n_mirrored == S0.n_items - S1.n_items and n_mirrored > 0
-    for ops, aM, aK in (("MKD", 0.1, 0.4), ("K", 0., 0.), ("MD", 0.3, 0.)):
-        v0, _ = emu_assemble(emu, S0, pts, conn, mat_id, rows, ops, aM, aK)
-        v1, _ = emu_assemble(emu, S1, pts, conn, mat_id, rows, ops, aM, aK)           # asserts: no block left unwritten
-        for nm in ops:
-            scale = np.abs(v0[nm]).max(axis=1, keepdims=True) + 1e-300
-            assert (np.abs(v1[nm] - v0[nm]) / scale).max() < 1e-14, (case, ops, nm)
-    if case == "rows":
-        return
-    ops_ref = orc.assemble(pts, conn, rows, mat_id, 0.1, 0.4)
-    v1, _ = emu_assemble(emu, S1, pts, conn, mat_id, rows, "MKD", 0.1, 0.4)
-    A = planes_to_csc(v1["K"], layout.plane_map_K(), S1, 4 * pts.shape[0])
-    parity.check_pattern(A, None, ops_ref["K"])
-    assert parity.scaled_error(A, ops_ref["K"]) < parity.VALUE_TOL
-    D = planes_to_csc(v1["D"], layout.plane_map_D(0.1, 0.4), S1, 4 * pts.shape[0])
-    assert parity.scaled_error(D, ops_ref["D"]) < parity.VALUE_TOL

@@ -27,8 +27,6 @@ _SIGNATURES = {
     "tefem_element_matrices": [P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P],
     "tefem_assemble": [P, c_int, c_int32, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
                        P, P, P, P, P],
-    "tefem_assemble_mirror": [P, c_int, c_int32, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_double, c_double,
-                              P, P, P, P, P],
     "tefem_assemble_set_threads": [c_int],
     "tefem_check_jacobian": [P, P, P],
     "tefem_schedule_bank_numbering": [c_int32, P, P, P, P, c_int, c_int, c_int, P, P, P],

@@ -48,7 +48,6 @@ struct AssembleArgs {
     const int32_t* item_meta;  // length | (partial slot + 1) << 8 | material << 24   (slot + 1 == 0: the block's only item)
     const int32_t* split_block;  // tile-local block with several items
     const int32_t* split_meta;   // first partial slot | n_items << 16
-    const int32_t* item_mirror;  // mirror layout: global block (j, i) the item of block (i, j) also writes, or -1; else null
     const uint16_t* inc;
     int32_t n_cta;
     int64_t n_blocks;
@@ -149,51 +148,6 @@ TEFEM_HD void gather_item(const AssembleArgs& A, uint32_t inc_word, int32_t meta
         block_accumulate<T::NEED_K, T::NEED_M, T::WANT_D>(g, recs + (size_t)(w >> 4) * T::REC, (w >> 2) & 3, w & 3, W4, S, NN);
     }
     block_finalize<T::NEED_K, T::NEED_M, T::WANT_D>(g, A.mat_table + MAT_STRIDE * meta_mat(meta), acc);
-}
-
-// Mirror layout: the sums of a plain block item and of its mirror from one pass over the list.
-template <int OPS, int DUU>
-TEFEM_HD void gather_item_mirror(const AssembleArgs& A, uint32_t inc_word, int32_t meta, const double* recs, const uint16_t* inc_s,
-                                 double W4, const QuadS& S, const QuadNN& NN, typename AsmTraits<OPS, DUU>::Acc& acc,
-                                 typename AsmTraits<OPS, DUU>::Acc& acc_m) {
-    typedef AsmTraits<OPS, DUU> T;
-    typename T::Geom g;
-    MirrorAcc<T::NEED_K, T::WANT_D> m;
-    g.clear();
-    m.clear();
-    const uint32_t s = inc_word & 0xffffu, t = s + (uint32_t)meta_len(meta);
-#pragma unroll 2
-    for (uint32_t k = s; k < t; ++k) {
-        const uint32_t w = inc_s[k];
-        block_accumulate_mirror<T::NEED_K, T::NEED_M, T::WANT_D>(g, m, recs + (size_t)(w >> 4) * T::REC, (w >> 2) & 3, w & 3, W4, S, NN);
-    }
-    const double* mat = A.mat_table + MAT_STRIDE * meta_mat(meta);
-    block_finalize<T::NEED_K, T::NEED_M, T::WANT_D>(g, mat, acc);
-    block_finalize_mirror<T::NEED_K, T::NEED_M, T::WANT_D>(g, m, mat, acc_m);
-}
-
-// Mirror layout, block pass: item of block p (plain: its list, and the mirror block `mir` >= 0 from the same gathers; combine:
-// the parked pieces).  Lower blocks (j, i), j < i, of owned columns have no item: their values come from the item of (i, j).
-template <int OPS, int DUU>
-TEFEM_HD void process_mirror_item(const AssembleArgs& A, int32_t p, int32_t mir, uint32_t inc_word, int32_t meta, const double* recs,
-                                  const uint16_t* inc_s, double* slots, double W4, const QuadS& S, const QuadNN& NN) {
-    typedef AsmTraits<OPS, DUU> T;
-    typename T::Acc acc;
-    const int slot = meta_slot(meta);
-    if (slot < 0) {
-        if (mir >= 0) {
-            typename T::Acc acc_m;
-            gather_item_mirror<OPS, DUU>(A, inc_word, meta, recs, inc_s, W4, S, NN, acc, acc_m);
-            store_block<OPS, DUU>(A, mir, acc_m);
-        } else {
-            gather_item<OPS, DUU>(A, inc_word, meta, recs, inc_s, W4, S, NN, acc);
-        }
-    } else {
-        acc.clear();
-        const int n = meta_len(meta);
-        for (int c = 0; c < n; ++c) acc.add_from(slots + (size_t)(slot + c) * T::SLOT);
-    }
-    store_block<OPS, DUU>(A, p, acc);
 }
 
 // One work item of the inline layout: either write the block (items are in block order: consecutive threads write
@@ -316,7 +270,6 @@ static bool quad_select_checked() {
 struct TileDims {
     int n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes;
     int pieces_first;   // item layout of every tile: 0 = inline (split lists), 1 = pieces first + one item per block
-    int mirror;         // pieces-first layout whose block items also write their mirror block (item_mirror)
 };
 
 }  // namespace tefem
@@ -394,10 +347,9 @@ __host__ __device__ inline uint32_t up16(uint32_t bytes) { return (bytes + 15u) 
 
 // Shared-memory layout of one prefetch stage (byte offsets, all multiples of 16).
 struct StageLayout {
-    uint32_t hdr, xyz, conn8, it_inc, it_meta, it_mir, sp_block, sp_meta, inc, bytes;
+    uint32_t hdr, xyz, conn8, it_inc, it_meta, sp_block, sp_meta, inc, bytes;
 };
-__host__ __device__ inline StageLayout stage_layout(int max_items, int max_elems, int max_inc, int max_split, int max_nodes,
-                                                    bool mirror = false) {
+__host__ __device__ inline StageLayout stage_layout(int max_items, int max_elems, int max_inc, int max_split, int max_nodes) {
     StageLayout L;
     uint32_t o = 0;
     L.hdr = o; o += 64;
@@ -405,7 +357,6 @@ __host__ __device__ inline StageLayout stage_layout(int max_items, int max_elems
     L.conn8 = o; o += up16(4u * (uint32_t)(max_elems + 3));
     L.it_inc = o; o += up16(4u * (uint32_t)(max_items + 3));
     L.it_meta = o; o += up16(4u * (uint32_t)(max_items + 3));
-    L.it_mir = o; if (mirror) o += up16(4u * (uint32_t)(max_items + 3));
     L.sp_block = o; o += up16(4u * (uint32_t)(max_split + 3));
     L.sp_meta = o; o += up16(4u * (uint32_t)(max_split + 3));
     L.inc = o; o += up16(2u * (uint32_t)(max_inc + 7));
@@ -422,7 +373,7 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
     const int o_items = h1.y, o_elems = h1.z, o_inc = h1.w, o_split = h2.x, o_nodes = h2.y;
     const uint32_t b_items = up16(4u * n_items), b_elems = up16(4u * n_elems), b_inc = up16(2u * n_inc);
     const uint32_t b_split = up16(4u * n_split), b_xyz = up16(24u * n_nodes);
-    const uint32_t total = 48u + b_xyz + b_elems + (A.item_mirror ? 3u : 2u) * b_items + 2u * b_split + b_inc;
+    const uint32_t total = 48u + b_xyz + b_elems + 2u * b_items + 2u * b_split + b_inc;
     mbar_expect_tx(bar, total);
     bulk_g2s(st + L.hdr, hg, 48u, bar);
     if (b_xyz) bulk_g2s(st + L.xyz, A.cta_xyz + 3 * (size_t)o_nodes, b_xyz, bar);
@@ -430,7 +381,6 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
     if (b_items) {
         bulk_g2s(st + L.it_inc, A.item_inc + o_items, b_items, bar);
         bulk_g2s(st + L.it_meta, A.item_meta + o_items, b_items, bar);
-        if (A.item_mirror) bulk_g2s(st + L.it_mir, A.item_mirror + o_items, b_items, bar);
     }
     if (b_split) {
         bulk_g2s(st + L.sp_block, A.split_block + o_split, b_split, bar);
@@ -442,13 +392,13 @@ __device__ __forceinline__ void prefetch_tile(const AssembleArgs& A, int t, cons
 // Shared memory: [element records][partial-sum slots][stage 0][stage 1][2 mbarriers][S, NN tables].
 // The quadrature tables are indexed by the per-incidence local node numbers: from shared memory (20 distinct
 // banks, broadcast) instead of constant memory, where a warp's divergent indices would be serialised.
-template <int OPS, int DUU, bool PF, int NT, bool MIR = false>
+template <int OPS, int DUU, bool PF, int NT>
 __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(const AssembleArgs A, const TileDims D, int rec_doubles,
                                                                   int part_doubles) {
     extern __shared__ __align__(128) double smem[];
     double* recs = smem;
     double* partials = recs + rec_doubles;
-    const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes, MIR);
+    const StageLayout L = stage_layout(D.max_items, D.max_elems, D.max_inc, D.max_split, D.max_nodes);
     char* stage0 = reinterpret_cast<char*>(partials + part_doubles);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);
 #ifdef ASM_TAB_SELECT
@@ -524,17 +474,9 @@ __global__ void __launch_bounds__(NT, ASM_THREADS_PER_SM / NT) assemble_kernel(c
 #pragma unroll 1
             for (int ph = (n_piece > 0 ? 0 : 1); ph < 2; ++ph) {
                 const int lo = ph ? n_piece : 0, hi = ph ? n_items : n_piece;
-                for (int it = lo + threadIdx.x; it < hi; it += NT) {
-                    if (MIR && ph) {   // mirror layout: the item names its block; lower blocks have no item
-                        const int32_t* it_mir = reinterpret_cast<const int32_t*>(st + L.it_mir);
-                        const uint32_t iw = (uint32_t)it_inc[it];
-                        process_mirror_item<OPS, DUU>(A, block0 + (int32_t)(iw >> 16), it_mir[it], iw, it_meta[it], recs, inc_s,
-                                                      partials, W4, tabS, tabNN);
-                    } else {
-                        process_pf_item<OPS, DUU>(A, ph ? block0 + (it - lo) : -1, (uint32_t)it_inc[it], it_meta[it], recs, inc_s,
-                                                  partials, W4, tabS, tabNN);
-                    }
-                }
+                for (int it = lo + threadIdx.x; it < hi; it += NT)
+                    process_pf_item<OPS, DUU>(A, ph ? block0 + (it - lo) : -1, (uint32_t)it_inc[it], it_meta[it], recs, inc_s,
+                                              partials, W4, tabS, tabNN);
                 if (ph == 0) __syncthreads();
             }
         } else {
@@ -575,28 +517,28 @@ __global__ void __launch_bounds__(128) element_matrices_kernel(
                   Kuu ? Kuu + t * 144 : nullptr, Kut ? Kut + t * 48 : nullptr, Ktt ? Ktt + t * 16 : nullptr);
 }
 
-template <int OPS, int DUU, bool PF, int NT, bool MIR = false>
+template <int OPS, int DUU, bool PF, int NT>
 static int launch_assemble_pf(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
     const int rec_doubles = (d.max_elems * AsmTraits<OPS, DUU>::REC + 15) & ~15;   // keep what follows 128-byte aligned
     const int part_doubles = (d.max_slots * AsmTraits<OPS, DUU>::SLOT + 15) & ~15;
-    const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes, MIR);
+    const StageLayout L = stage_layout(d.max_items, d.max_elems, d.max_inc, d.max_split, d.max_nodes);
     const size_t smem = ((size_t)rec_doubles + part_doubles) * sizeof(double) + 2 * (size_t)L.bytes + 16 + 20 * sizeof(double);
     TEFEM_REQUIRE(smem <= 220 * 1024, "tile exceeds shared memory");
     static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU, PF, NT, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TEFEM_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel<OPS, DUU, PF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         int dev = 0;
         TEFEM_CUDA_CHECK(cudaGetDevice(&dev));
         TEFEM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
     int per_sm = 0;
-    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU, PF, NT, MIR>, NT, smem));
+    TEFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_kernel<OPS, DUU, PF, NT>, NT, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count * per_sm;
     if (grid > d.n_cta) grid = d.n_cta;
-    assemble_kernel<OPS, DUU, PF, NT, MIR><<<grid, NT, smem, st>>>(A, d, rec_doubles, part_doubles);
+    assemble_kernel<OPS, DUU, PF, NT><<<grid, NT, smem, st>>>(A, d, rec_doubles, part_doubles);
     TEFEM_LAUNCH_CHECK();
     return TEFEM_OK;
 }
@@ -613,10 +555,6 @@ static int asm_threads() { return g_asm_threads; }
 template <int OPS, int DUU>
 static int launch_assemble(const AssembleArgs& A, const TileDims& d, cudaStream_t st) {
     const int nt = asm_threads();
-    if (d.mirror) {
-        TEFEM_REQUIRE(nt == ASM_THREADS && d.pieces_first, "the mirror layout is a pieces-first layout for the default thread count");
-        return launch_assemble_pf<OPS, DUU, true, ASM_THREADS, true>(A, d, st);
-    }
     if (!d.pieces_first) {
         TEFEM_REQUIRE(nt == ASM_THREADS, "tefem_assemble_set_threads applies to the pieces-first item layout only");
         return launch_assemble_pf<OPS, DUU, false, ASM_THREADS>(A, d, st);
@@ -660,15 +598,14 @@ extern "C" int tefem_element_matrices(const double* coords, const int32_t* conn,
     return TEFEM_OK;
 }
 
-static int assemble_impl(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
-                         const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
-                         const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta, const int32_t* item_mirror,
-                         const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
-                         int ops, double alpha_M,
-                         double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem,
-                         void* stream) {
+extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
+                              const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
+                              const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
+                              const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
+                              int ops, double alpha_M,
+                              double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem,
+                              void* stream) {
     TEFEM_REQUIRE(mat_table && bad_elem && h_max, "null input");
-    TEFEM_REQUIRE(!item_mirror || ((((uintptr_t)item_mirror) & 15) == 0 && h_max[6] == 1), "item_mirror: 16-byte aligned, pieces-first layout");
     TEFEM_REQUIRE(cta_hdr && cta_elems && cta_conn8 && cta_xyz && item_inc && item_meta && inc, "null schedule");
     const int max_items = h_max[0], max_elems = h_max[1], max_inc = h_max[2], max_slots = h_max[3], max_split = h_max[4],
               max_nodes = h_max[5], pieces_first = h_max[6];
@@ -694,11 +631,10 @@ static int assemble_impl(const double* mat_table, int n_mat, int32_t n_cta, cons
     A.mat_table = mat_table;
     A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_xyz = cta_xyz;
     A.item_inc = item_inc; A.item_meta = item_meta; A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
-    A.item_mirror = item_mirror;
     A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
-    const TileDims d = {n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes, pieces_first, item_mirror ? 1 : 0};
+    const TileDims d = {n_cta, max_items, max_elems, max_inc, max_slots, max_split, max_nodes, pieces_first};
     cudaStream_t st = as_stream(stream);
     switch (ops) {
         case 1: return dispatch_duu<1>(A, duu, d, st);
@@ -709,30 +645,6 @@ static int assemble_impl(const double* mat_table, int n_mat, int32_t n_cta, cons
         case 6: return dispatch_duu<6>(A, duu, d, st);
         default: return dispatch_duu<7>(A, duu, d, st);
     }
-}
-
-extern "C" int tefem_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
-                              const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
-                              const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
-                              const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
-                              int ops, double alpha_M,
-                              double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem,
-                              void* stream) {
-    return assemble_impl(mat_table, n_mat, n_cta, h_max, cta_hdr, cta_elems, cta_conn8, cta_xyz, item_inc, item_meta, nullptr,
-                         split_block, split_meta, inc, n_blocks, ops, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem, stream);
-}
-
-// Mirror layout (symbolic.mirror_schedule): item_mirror[item] = global block (j, i) that the item of the plain block (i, j),
-// j > i, also writes (-1: none); the lower blocks of owned columns have no item of their own.
-extern "C" int tefem_assemble_mirror(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max,
-                                     const int32_t* cta_hdr, const int32_t* cta_elems, const int32_t* cta_conn8,
-                                     const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
-                                     const int32_t* item_mirror, const uint16_t* inc, int64_t n_blocks, int ops, double alpha_M,
-                                     double alpha_K, double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem,
-                                     void* stream) {
-    TEFEM_REQUIRE(item_mirror, "null item_mirror");
-    return assemble_impl(mat_table, n_mat, n_cta, h_max, cta_hdr, cta_elems, cta_conn8, cta_xyz, item_inc, item_meta, item_mirror,
-                         nullptr, nullptr, inc, n_blocks, ops, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem, stream);
 }
 
 extern "C" int tefem_assemble_set_threads(int threads) {
@@ -797,16 +709,10 @@ static int emu_run(const AssembleArgs& A, const TileDims& d, int n_mat) {
                     if (slot != it || s + meta_len(meta) > h[H_NINC]) return TEFEM_ERR_INVALID;
                     process_pf_item<OPS, DUU>(A, -1, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
                 } else {              // block items: all pieces were processed before (the kernel synchronises)
-                    const int b = d.mirror ? (int)(iw >> 16) : it - n_piece;
+                    const int b = it - n_piece;
                     if ((int)(iw >> 16) != b) return TEFEM_ERR_INVALID;
                     if (slot < 0 ? s + meta_len(meta) > h[H_NINC] : slot + meta_len(meta) > n_piece) return TEFEM_ERR_INVALID;
-                    if (d.mirror) {
-                        const int32_t mir = A.item_mirror[h[H_OITEMS] + it];
-                        if (mir < -1 || mir >= A.n_blocks || (mir >= 0 && slot >= 0)) return TEFEM_ERR_INVALID;
-                        process_mirror_item<OPS, DUU>(A, h[H_BLOCK0] + b, mir, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
-                    } else {
-                        process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
-                    }
+                    process_pf_item<OPS, DUU>(A, h[H_BLOCK0] + b, iw, meta, recs.data(), inc_s, partials.data(), q.W4, make_quad_s(q.S), make_quad_nn(q.NN));
                 }
                 continue;
             }
@@ -822,21 +728,20 @@ static int emu_run(const AssembleArgs& A, const TileDims& d, int n_mat) {
     return TEFEM_OK;
 }
 
-static int emu_assemble_impl(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
-                             const int32_t* cta_elems, const int32_t* cta_conn8,
-                             const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta, const int32_t* item_mirror,
-                             const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
-                             int ops, double alpha_M, double alpha_K,
-                             double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
+extern "C" int tefem_emu_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
+                                  const int32_t* cta_elems, const int32_t* cta_conn8,
+                                  const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
+                                  const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
+                                  int ops, double alpha_M, double alpha_K,
+                                  double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
     AssembleArgs A;
     memset(&A, 0, sizeof(A));
-    A.item_mirror = item_mirror;
     A.mat_table = mat_table;
     A.cta_hdr = cta_hdr; A.cta_elems = cta_elems; A.cta_conn8 = cta_conn8; A.cta_xyz = cta_xyz;
     A.item_inc = item_inc; A.item_meta = item_meta; A.split_block = split_block; A.split_meta = split_meta; A.inc = inc;
     A.n_cta = n_cta; A.n_blocks = n_blocks; A.alpha_M = alpha_M; A.alpha_K = alpha_K;
     A.vals_M = vals_M; A.vals_K = vals_K; A.vals_D = vals_D; A.bad_elem = bad_elem;
-    const TileDims d = {n_cta, h_max[0], h_max[1], h_max[2], h_max[3], h_max[4], h_max[5], h_max[6], item_mirror ? 1 : 0};
+    const TileDims d = {n_cta, h_max[0], h_max[1], h_max[2], h_max[3], h_max[4], h_max[5], h_max[6]};
     const int duu = (alpha_K != 0.0) ? 2 : (alpha_M != 0.0 ? 1 : 0);
 #define TEFEM_EMU_CASE(O)                                                     \
     case O:                                                                   \
@@ -849,27 +754,6 @@ static int emu_assemble_impl(const double* mat_table, int n_mat, int32_t n_cta, 
         default: return TEFEM_ERR_INVALID;
     }
 #undef TEFEM_EMU_CASE
-}
-
-extern "C" int tefem_emu_assemble(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
-                                  const int32_t* cta_elems, const int32_t* cta_conn8,
-                                  const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
-                                  const int32_t* split_block, const int32_t* split_meta, const uint16_t* inc, int64_t n_blocks,
-                                  int ops, double alpha_M, double alpha_K,
-                                  double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
-    return emu_assemble_impl(mat_table, n_mat, n_cta, h_max, cta_hdr, cta_elems, cta_conn8, cta_xyz, item_inc, item_meta, nullptr,
-                             split_block, split_meta, inc, n_blocks, ops, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
-}
-
-extern "C" int tefem_emu_assemble_mirror(const double* mat_table, int n_mat, int32_t n_cta, const int32_t* h_max, const int32_t* cta_hdr,
-                                         const int32_t* cta_elems, const int32_t* cta_conn8,
-                                         const double* cta_xyz, const int32_t* item_inc, const int32_t* item_meta,
-                                         const int32_t* item_mirror, const uint16_t* inc, int64_t n_blocks,
-                                         int ops, double alpha_M, double alpha_K,
-                                         double* vals_M, double* vals_K, double* vals_D, int32_t* bad_elem) {
-    if (!item_mirror) return TEFEM_ERR_INVALID;
-    return emu_assemble_impl(mat_table, n_mat, n_cta, h_max, cta_hdr, cta_elems, cta_conn8, cta_xyz, item_inc, item_meta, item_mirror,
-                             nullptr, nullptr, inc, n_blocks, ops, alpha_M, alpha_K, vals_M, vals_K, vals_D, bad_elem);
 }
 
 extern "C" int tefem_emu_element_matrices(const double* coords, const int32_t* conn, const int32_t* mat_id,

@@ -231,69 +231,6 @@ TEFEM_HD void block_accumulate(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, const doubl
     }
 }
 
-// MIRROR form (round 2, opt-in schedule): the thread that sums block (i, j) also produces block (j, i) from the SAME gathers.
-// The geometric sums of the mirror are the transposes: P'[x][y] = P[y][x] and nn' = nn (NN is bitwise symmetric: N_a * N_b
-// commutes), and only the coupling sums need their own accumulators: q'[x] = sum det S_b G[x][a], r'[c] = sum det S_b GT[c][a].
-// The values are those of the direct sum up to the rounding of one product order ((W det g_a) g_b against (W det g_b) g_a).
-template <bool WITH_K, bool WITH_D>
-struct MirrorAcc {
-    double q[WITH_K ? 3 : 1];
-    double r[WITH_D ? 3 : 1];
-    TEFEM_HD void clear() {
-        for (int i = 0; i < (WITH_K ? 3 : 1); ++i) q[i] = 0.0;
-        for (int i = 0; i < (WITH_D ? 3 : 1); ++i) r[i] = 0.0;
-    }
-};
-
-template <bool WITH_K, bool WITH_M, bool WITH_D>
-TEFEM_HD void block_accumulate_mirror(GeomAcc<WITH_K, WITH_M, WITH_D>& acc, MirrorAcc<WITH_K, WITH_D>& mir,
-                                      const double* __restrict__ rec, int a, int b, double W4, const QuadS& S, const QuadNN& NN) {
-    const double det = rec[REC_DET];
-    double dsa = 0.0, dsb = 0.0;
-    if (WITH_K || WITH_D) { dsa = det * S.at(a); dsb = det * S.at(b); }
-    if (WITH_K) {
-        const double ga0 = rec[REC_G + 3 * a], ga1 = rec[REC_G + 3 * a + 1], ga2 = rec[REC_G + 3 * a + 2];
-        const double gb0 = rec[REC_G + 3 * b], gb1 = rec[REC_G + 3 * b + 1], gb2 = rec[REC_G + 3 * b + 2];
-        const double wd = W4 * det;
-        const double w0 = wd * ga0, w1 = wd * ga1, w2 = wd * ga2;
-        acc.P[0] += w0 * gb0; acc.P[1] += w0 * gb1; acc.P[2] += w0 * gb2;
-        acc.P[3] += w1 * gb0; acc.P[4] += w1 * gb1; acc.P[5] += w1 * gb2;
-        acc.P[6] += w2 * gb0; acc.P[7] += w2 * gb1; acc.P[8] += w2 * gb2;
-        acc.q[0] += dsa * gb0; acc.q[1] += dsa * gb1; acc.q[2] += dsa * gb2;
-        mir.q[0] += dsb * ga0; mir.q[1] += dsb * ga1; mir.q[2] += dsb * ga2;
-    }
-    if (WITH_M || WITH_D) acc.nn += det * NN.at(a, b);
-    if (WITH_D) {
-        acc.r[0] += dsa * rec_gt(rec, 0, b); acc.r[1] += dsa * rec_gt(rec, 1, b); acc.r[2] += dsa * rec_gt(rec, 2, b);
-        mir.r[0] += dsb * rec_gt(rec, 0, a); mir.r[1] += dsb * rec_gt(rec, 1, a); mir.r[2] += dsb * rec_gt(rec, 2, a);
-    }
-}
-
-// Values of the mirror block (j, i) from the sums of block (i, j).
-template <bool WITH_K, bool WITH_M, bool WITH_D>
-TEFEM_HD void block_finalize_mirror(const GeomAcc<WITH_K, WITH_M, WITH_D>& g, const MirrorAcc<WITH_K, WITH_D>& mir,
-                                    const double* __restrict__ mat, BlockAcc<WITH_K, WITH_M, WITH_D>& out) {
-    out.clear();
-    if (WITH_K) {
-        const double lam = mat[MAT_LAM], mu = mat[MAT_MU];
-        const double md = mu * (g.P[0] + g.P[4] + g.P[8]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                out.kuu[3 * i + j] = lam * g.P[3 * j + i] + mu * g.P[3 * i + j] + (i == j ? md : 0.0);
-        const double nb = -mat[MAT_BETA];
-        out.kut[0] = nb * mir.q[0]; out.kut[1] = nb * mir.q[1]; out.kut[2] = nb * mir.q[2];
-        out.ktt = mat[MAT_K] * (g.P[0] + g.P[4] + g.P[8]);
-    }
-    if (WITH_M || WITH_D) out.m = mat[MAT_RHO] * g.nn;
-    if (WITH_D) {
-        const double nbt = -(mat[MAT_BETA] * mat[MAT_T0]);
-        out.dtu[0] = nbt * mir.r[0]; out.dtu[1] = nbt * mir.r[1]; out.dtu[2] = nbt * mir.r[2];
-        out.dtt = mat[MAT_RHO] * mat[MAT_C] * g.nn;
-    }
-}
-
 // The block values of a material-uniform item: out = material constants x geometric sums
 // (Kuu/Kut/Ktt elements.py:254-286, Muu :220-229, Dtu :231-241, Dtt :243-252).
 template <bool WITH_K, bool WITH_M, bool WITH_D>

@@ -65,16 +65,6 @@ class DeviceMesh:
         self.bad_elem.fill_(_lib.INT32_MAX)
         p = _lib.ptr
         _lib.check(self.lib.tefem_assemble_set_threads(int(self.asm_threads)))
-        if S.mirrored:      # opt-in mirror layout (symbolic.mirror_schedule): block items also write their mirror block
-            _lib.check(self.lib.tefem_assemble_mirror(
-                p(self.mat_table), self.n_mat, S.n_cta, p(self._h_max), p(S.cta_hdr), p(S.cta_elems),
-                p(S.cta_conn8), p(self.cta_xyz), p(S.item_inc), p(S.item_meta), p(S.item_mirror),
-                p(S.inc), S.n_blocks, mask, float(alpha_M), float(alpha_K),
-                p(out.get("M")) if "M" in ops else None, p(out.get("K")) if "K" in ops else None,
-                p(out.get("D")) if "D" in ops else None, p(self.bad_elem), _lib.stream_ptr()))
-            if check:
-                self.check_jacobian()
-            return out
         _lib.check(self.lib.tefem_assemble(
             p(self.mat_table), self.n_mat, S.n_cta, p(self._h_max), p(S.cta_hdr), p(S.cta_elems),
             p(S.cta_conn8), p(self.cta_xyz), p(S.item_inc), p(S.item_meta), p(S.split_block), p(S.split_meta),

@@ -59,9 +59,6 @@ BANK_OPT = True
 # round 2 with 448-block tiles: slower, profiles/README.md); when enabled it is skipped for schedules where it would cost
 # a CTA per SM.
 PITCH_LISTS = False
-# Mirror layout (mirror_schedule): one thread produces block (i, j) and its mirror (j, i) from one pass over the incidence list.
-# Opt-in (build_schedule(mirror=True)) until it has been measured against the direct layout on the B200.
-MIRROR = False
 SM_SMEM_BYTES = 228 * 1024     # shared memory of a B200 SM; every resident CTA reserves 1 KB of it
 HDR_STRIDE = 12
 H_NITEMS, H_NELEMS, H_NINC, H_NSPLIT, H_NNODES, H_OITEMS, H_OELEMS, H_OINC, H_OSPLIT, H_ONODES, H_BLOCK0, H_NPIECE = range(12)
@@ -100,8 +97,6 @@ class Schedule:
     pieces_first: bool = False   # item layout of the tiles (build_schedule)
     bank_optimized: bool = False # staged elements renumbered per tile by optimize_banks
     lists_pitched: bool = False  # incidence lists re-placed at a fixed pitch by pitch_lists (block_inc is then stale)
-    item_mirror: torch.Tensor = None   # int32 [padded like item_inc]: mirror layout (mirror_schedule), else None
-    mirrored: bool = False       # block items also write their mirror block; lower blocks of owned columns have no item
 
     def to(self, device):
         kw = {}
@@ -126,16 +121,14 @@ class Schedule:
         slot = live | 1
         rec_doubles = (self.max_cta_elems * rec + 15) & ~15
         part_doubles = (self.max_cta_slots * slot + 15) & ~15
-        stage = (64 + up16(24 * ((self.max_cta_nodes + 1) & ~1)) + up16(4 * (self.max_cta_elems + 3))
-                 + (3 if self.mirrored else 2) * up16(4 * (self.max_cta_items + 3))
+        stage = (64 + up16(24 * ((self.max_cta_nodes + 1) & ~1)) + up16(4 * (self.max_cta_elems + 3)) + 2 * up16(4 * (self.max_cta_items + 3))
                  + 2 * up16(4 * (self.max_cta_split + 3)) + up16(2 * (self.max_cta_inc + 7)))
         return 8 * (rec_doubles + part_doubles) + 2 * stage + 16 + 20 * 8
 
     def schedule_bytes(self):
         """Bytes of slot-map / schedule data one assembly launch reads (cta_xyz is counted by DeviceMesh)."""
         return sum(t.numel() * t.element_size() for t in
-                   (self.inc, self.cta_hdr, self.cta_conn8, self.item_inc, self.item_meta, self.split_block, self.split_meta)
-                   + ((self.item_mirror,) if self.item_mirror is not None else ()))
+                   (self.inc, self.cta_hdr, self.cta_conn8, self.item_inc, self.item_meta, self.split_block, self.split_meta))
 
 
 def pitch_lists(S: "Schedule", pitch_blocks: int = 6, pitch_pieces: int = 10, keep_occupancy: bool = True) -> "Schedule":
@@ -260,71 +253,6 @@ def optimize_banks(S: "Schedule", strides: int = 3, n_sweeps: int = 3, n_threads
     return (out, (int(cost[0]), int(cost[1]))) if return_cost else out
 
 
-def mirror_schedule(S: "Schedule") -> "Schedule":
-    """Mirror layout of a pieces-first schedule (opt-in, build_schedule(mirror=True)): the geometric sums of block (j, i) are
-    the transposes of those of block (i, j) (tefem_element.cuh, block_accumulate_mirror), so ONE thread can produce both from
-    one pass over the incidence list - half the shared-memory gathers of the off-diagonal blocks, which bound kernel K1
-    (profiles/README.md).  For every PLAIN block item (i, j) with j > i and column j owned, item_mirror names the global
-    block (j, i) it also writes; the item of (j, i) is removed.  Kept as they are: the pieces and combine items of split
-    blocks (diagonal chunks, material interfaces: both sides of an interface block stay direct) and the blocks of halo
-    columns (their mirror row is another rank's).  Every block is still written exactly once; the mirror stores are
-    scattered 8-byte stores (the direct ones stay in block order).  Values: those of the direct sum up to the rounding of one
-    product order.  The incidence lists of the removed items stay in the tile segments (unused)."""
-    assert S.pieces_first and not S.lists_pitched and not S.mirrored
-    dev = S.cta_hdr.device
-    i64 = dict(dtype=torch.int64, device=dev)
-    n_cta, P, N = S.n_cta, S.n_blocks, S.n_nodes
-    hdr = S.cta_hdr.to(torch.int64)
-    n_it, n_pc, o_it, blk0 = hdr[:, H_NITEMS], hdr[:, H_NPIECE], hdr[:, H_OITEMS], hdr[:, H_BLOCK0]
-    ptr = _ptr_from_counts(n_it, n_cta, dev)
-    total = int(ptr[-1].item())
-    tile = torch.repeat_interleave(torch.arange(n_cta, **i64), n_it)
-    rank = torch.arange(total, **i64) - ptr[tile]
-    pos = o_it[tile] + rank
-    iw = S.item_inc[pos].to(torch.int64) & 0xffffffff
-    meta = S.item_meta[pos].to(torch.int64) & 0xffffffff
-    is_piece = rank < n_pc[tile]
-    g = (blk0[tile] + (iw >> 16)).clamp(0, max(P - 1, 0))                       # global block of a block item
-    plain = (~is_piece) & (((meta >> 8) & 0xffff) == 0)
-    row, col = S.block_row.to(torch.int64)[g], S.colidx.to(torch.int64)[g]
-    lower = plain & (col < row)                                               # col < row < n_rows: an owned column
-    upper = plain & (col > row) & (col < S.n_rows)
-    keys = S.block_row.to(torch.int64) * N + S.colidx.to(torch.int64)         # ascending: blocks are in (row, col) order
-    mir = torch.full((total,), -1, **i64)
-    want = col[upper] * N + row[upper]
-    m = torch.searchsorted(keys, want)
-    assert bool((keys[m.clamp(max=max(P - 1, 0))] == want).all()), "the block pattern must be structurally symmetric"
-    plain_blk = torch.zeros(P, dtype=torch.bool, device=dev)
-    plain_blk[g[plain]] = True
-    assert bool(plain_blk[m].all()), "the mirror of a plain block must be plain (same elements, same materials)"
-    mir[upper] = m
-    # every removed item must be the mirror of exactly one kept item
-    covered = torch.zeros(P, dtype=torch.bool, device=dev)
-    covered[m] = True
-    assert bool(covered[g[lower]].all()) and int(covered.sum().item()) == int(lower.sum().item())
-    keep = ~lower
-    tile_k = tile[keep]
-    new_cnt = torch.bincount(tile_k, minlength=n_cta)
-    new_ptr = _ptr_from_counts(new_cnt, n_cta, dev)
-
-    def repack(values, fill):
-        out, pptr, _ = _pad_segments(values[keep], tile_k, new_ptr, n_cta, 4, fill)
-        return out, pptr
-    item_inc_p, item_pptr = repack(S.item_inc[pos].to(torch.int64), 0)
-    item_meta_p, _ = repack(S.item_meta[pos].to(torch.int64), 0)
-    item_block_p, _ = repack(S.item_block[pos].to(torch.int64), 0)
-    item_mir_p, _ = repack(mir, -1)
-    new_hdr = hdr.clone()
-    new_hdr[:, H_NITEMS] = new_cnt
-    new_hdr[:, H_OITEMS] = item_pptr[:-1]
-    kw = dict(S.__dict__)
-    i32 = torch.int32
-    kw.update(cta_hdr=new_hdr.to(i32).contiguous(), item_inc=item_inc_p.to(i32), item_meta=item_meta_p.to(i32),
-              item_block=item_block_p.to(i32), item_mirror=item_mir_p.to(i32), n_items=int(new_cnt.sum().item()),
-              max_cta_items=int(new_cnt.max().item()) if n_cta else 0, mirrored=True)
-    return Schedule(**kw)
-
-
 def _excl_cumsum(x):
     return torch.cumsum(x, 0) - x
 
@@ -355,7 +283,7 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
                    items_per_cta: int = ITEMS_PER_CTA, elem_budget: int = ELEM_BUDGET_PER_CTA,
                    max_chunk: int = MAX_CHUNK, mat_id: torch.Tensor = None,
                    item_sort_window: int = None, pieces_first: bool = None, tile_cost: str = None,
-                   bank_opt: bool = None, pitch: bool = None, mirror: bool = None) -> Schedule:
+                   bank_opt: bool = None, pitch: bool = None) -> Schedule:
     """conn: integer tensor [E, 4] in the reference's element order; node numbers < n_nodes.
     n_rows: only rows of nodes < n_rows are assembled (row-partitioned multi-GPU: owned nodes
     are numbered first); default all.
@@ -371,7 +299,6 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     pitch: re-place the incidence lists at a fixed pitch (pitch_lists; default PITCH_LISTS).
     bank_opt: renumber the staged elements of every tile so that the kernel's shared-memory gathers hit fewer bank conflicts
     (optimize_banks; default BANK_OPT).
-    mirror: mirror layout (mirror_schedule; pieces-first only, opt-in): one thread produces block (i, j) and its mirror (j, i).
     tile_cost: what `items_per_cta` bounds - 'items' (all work items of the tile's rows; default of the inline layout)
     or 'blocks' (its blocks = the threads of the block-order pass; default of the pieces-first layout).
 
@@ -379,7 +306,6 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
     kernel's shared memory (Schedule.smem_bytes); meshes whose node numbering has little locality (e.g. the Gmsh
     numbering of data/sandwich.msh), very high valences or oversized requests get smaller tiles."""
     pieces_first = PIECES_FIRST if pieces_first is None else bool(pieces_first)
-    mirror = (MIRROR and pieces_first and not (PITCH_LISTS if pitch is None else pitch)) if mirror is None else bool(mirror)
     if tile_cost is None:
         tile_cost = 'blocks' if pieces_first else 'items'
     assert tile_cost in ('items', 'blocks')
@@ -388,11 +314,8 @@ def build_schedule(conn: torch.Tensor, n_nodes: int, n_rows: int = None,
             S = _build_schedule(conn, n_nodes, n_rows, items_per_cta, elem_budget, max_chunk, mat_id,
                                 ITEM_SORT_WINDOW if item_sort_window is None else item_sort_window,
                                 pieces_first, tile_cost)
-            if mirror:
-                assert pieces_first, "the mirror layout is a pieces-first layout"
-                S = mirror_schedule(S)
             if S.smem_bytes() <= MAX_SMEM_BYTES:            # the kernel would refuse the launch: smaller tiles
-                if (PITCH_LISTS if pitch is None else pitch) and not mirror:
+                if (PITCH_LISTS if pitch is None else pitch):
                     S = pitch_lists(S)
                 if not (BANK_OPT if bank_opt is None else bank_opt):
                     return S

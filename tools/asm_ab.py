@@ -1,7 +1,6 @@
 """A/B of K1 item layouts on the GPU box: inline (split lists) vs pieces-first, same mesh, same chunks.
 Checks that the planes are BITWISE identical (same chunks => same summation order) and times both.
-usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first[,bank_opt[,pitch[,mirror]]]" ...]   (first variant = reference;
-mirror = 1: mirror layout, symbolic.mirror_schedule - not bitwise equal to the direct layouts, maxrel ~1e-16;
+usage: python tools/asm_ab.py [cells] ["items,budget,chunk,pieces_first[,bank_opt[,pitch]]" ...]   (first variant = reference;
 bank_opt = 1: bank-aware numbering of the staged elements, symbolic.optimize_banks; 2 / 3: optimised for the kernels with D /
 without D only)
 Kernel form (tool-level switch TEFEM_ASM_THREADS -> DeviceMesh.asm_threads): 256 (default) | 128 | 64 = threads per CTA (pair with items = 2 x threads); build variants: TEFEM_LIB=/path/to/lib.so."""
@@ -33,10 +32,8 @@ for v in variants:
     items, budget, chunk, pf = f[:4]
     bank = f[4] if len(f) > 4 else 0
     pitch = bool(f[5]) if len(f) > 5 else False
-    mirror = bool(f[6]) if len(f) > 6 else False
     t_sym = time.perf_counter()
-    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk, pieces_first=bool(pf), bank_opt=False, pitch=pitch,
-                       mirror=mirror)
+    S = build_schedule(conn_d, N, items_per_cta=items, elem_budget=budget, max_chunk=chunk, pieces_first=bool(pf), bank_opt=False, pitch=pitch)
     t_sym = time.perf_counter() - t_sym
     t_bank = time.perf_counter()
     if bank:

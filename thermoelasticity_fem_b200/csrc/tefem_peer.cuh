@@ -25,7 +25,8 @@ constexpr int64_t PEER_SMALL_BYTES = 2 * PEER_SMALL * 8;
 constexpr int64_t PEER_BIG_OFFSET = 2048;
 constexpr long long PEER_TIMEOUT_DEFAULT = 60000000000LL;     // ~30 s at 1.9 GHz (tefem_comm_set_timeout overrides it)
 
-// channels: dot-product packets, restricted residual of the coarse correction, halo values of the SpMV input
+// channels: dot-product packets, restricted residual of the coarse correction (replicated cycle), halo values of the SpMV
+// input, and the application counter of the row-partitioned coarse cycle (its tags; that channel uses no flags)
 enum { PEER_CH_DOTS = 0, PEER_CH_COARSE = 1, PEER_CH_HALO = 2, PEER_CH_CYCLE = 3, PEER_N_CHANNELS = 4 };
 
 struct PeerCtx {

@@ -986,6 +986,7 @@ static int apply_persistent(tefem_precond* p, const double* r, double* z, cudaSt
     a.x_mask = p->x_mask; a.t_mask = p->t_mask;
     a.n_iterates = cycle_iterates(p->n_pre, p->n_post, p->overlap);
     double* rc_mine = p->rc;
+    a.rc[0] = p->rc;                                              // read by phase 0 when world == 1 (with or without a communicator)
     if (p->comm) {
         const PeerCtx pc = tefem_comm_peer_ctx(p->comm, PEER_CH_CYCLE);
         a.world = pc.world; a.rank = pc.rank;

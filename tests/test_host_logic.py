@@ -198,3 +198,20 @@ def test_plots_module_exports_the_names_the_reference_examples_import():
     """reference examples import these at module top level (example_steadystate.py:13, example_UQ_1.py): the names must exist."""
     from thermoelasticity_fem_b200.plots import (animate_U_T, plot_U_T, plot_dofU_vs_t, plot_dofU_vs_t_random,  # noqa: F401
                                                   plot_nodeT_vs_t, plot_nodeT_vs_t_random)
+
+
+def test_persistent_cycle_buffer_sizes_are_consistent():
+    """Host-only size functions of the row-partitioned coarse cycle (include/tefem.h): the peer region holds the plain partial
+    residual plus TWO areas of tagged vectors (16 bytes per value = 2 doubles) with a slot of partial sums per rank; the local
+    buffer holds bc, two areas without the partial slots, the plain r2 and 32 words of counters / stamps."""
+    from thermoelasticity_fem_b200 import _lib
+    lib = _lib.load()
+    al = lambda n: (n + 15) // 16 * 16
+    for n1, n2, n_pre, n_post in ((27, 27, 3, 3), (3375, 125, 3, 3), (13824, 512, 3, 3), (13824, 512, 1, 0), (500, 64, 8, 8)):
+        a1, a2 = al(8 * n1), al(8 * n2)
+        iterates = 2 + (n_pre - 1) + n_post                       # sized for the classic cycle (one iterate more than the overlapped one)
+        shared = (iterates + 1) * a1 + 2 * a2                     # iterates, t, then x2 and r2
+        peer_area = shared + 8 * a1                               # + one slot of tagged partial sums per rank (<= 8)
+        assert lib.tefem_precond_peer_doubles(n1, n2, n_pre, n_post) == a1 + 2 * 2 * peer_area
+        assert lib.tefem_precond_cycle_doubles(n1, n2, n_pre, n_post) == 2 * (a1 + 2 * shared) + a2 + 32
+        assert lib.tefem_precond_work_doubles(n1, n2) == 4 * a1 + 2 * a2 + 16

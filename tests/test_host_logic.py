@@ -215,3 +215,57 @@ def test_persistent_cycle_buffer_sizes_are_consistent():
         assert lib.tefem_precond_peer_doubles(n1, n2, n_pre, n_post) == a1 + 2 * 2 * peer_area
         assert lib.tefem_precond_cycle_doubles(n1, n2, n_pre, n_post) == 2 * (a1 + 2 * shared) + a2 + 32
         assert lib.tefem_precond_work_doubles(n1, n2) == 4 * a1 + 2 * a2 + 16
+
+
+def test_vtu_export_round_trip(tmp_path):
+    """Binary export for plotting (thermoelasticity_fem_b200/vtk.py): what the reference hands to
+    pyvista in plot_U_T / animate_U_T (plots.py:6-75), written as raw-appended VTK XML and read back."""
+    from thermoelasticity_fem_b200 import Mesh
+    from thermoelasticity_fem_b200 import vtk, plots
+    from thermoelasticity_fem_b200.synthetic import kuhn_box
+    pts, tets, tris, nodes = kuhn_box(3, 2, 2, jitter=0.1, seed=4)
+    mesh = Mesh().from_arrays(pts, tets, tris, nodes)
+    n = mesh.n_nodes
+    rng = np.random.default_rng(0)
+    T, U = rng.standard_normal(n), rng.standard_normal(3 * n)
+    f = plots.export_U_T(mesh, T, U, str(tmp_path / "state.vtu"))
+    head = open(f, "rb").read(200).decode("ascii", "replace")
+    assert head.startswith('<?xml version="1.0"?>') and 'type="UnstructuredGrid"' in head and 'header_type="UInt64"' in head
+    back = vtk.read_vtu(f)
+    assert np.array_equal(back["points"], mesh.table_nodes) and np.array_equal(back["tets"], mesh.all_tets())
+    assert np.array_equal(back["point_data"]["T"], T) and np.array_equal(back["point_data"]["U"], U.reshape(n, 3))
+    tags = np.concatenate([np.full(len(t), k, dtype=np.int32) for k, t in mesh.dict_tet_groups.items()])
+    assert np.array_equal(back["cell_data"]["tag"], tags)
+    # time series: every second frame + the ParaView index
+    n_t = 5
+    vec_t = np.linspace(0., 2., n_t)
+    Th, Uh = rng.standard_normal((n, n_t)), rng.standard_normal((3 * n, n_t))
+    files = plots.export_animation(mesh, Th, Uh, vec_t, str(tmp_path / "run"), step=2)
+    assert [os.path.basename(p) for p in files] == ["run_0000.vtu", "run_0001.vtu", "run_0002.vtu", "run.pvd"]
+    assert np.array_equal(vtk.read_vtu(files[1])["point_data"]["T"], Th[:, 2])
+    assert np.array_equal(vtk.read_vtu(files[2])["point_data"]["U"], Uh[:, 4].reshape(n, 3))
+    pvd = open(files[-1]).read()
+    assert pvd.count("<DataSet") == 3 and 'timestep="1"' in pvd and 'file="run_0002.vtu"' in pvd
+    with pytest.raises(ValueError):
+        vtk.write_vtu(str(tmp_path / "bad.vtu"), pts, mesh.all_tets(), {"T": T[:-1]})
+    with pytest.raises(ValueError):
+        plots.export_animation(mesh, Th, Uh[:, :-1], vec_t, str(tmp_path / "bad"))
+
+
+def test_confidence_bounds_match_the_reference_loops():
+    """plots.confidence_bounds against the reference's per-row loops (plots.py:117-125), restated."""
+    from thermoelasticity_fem_b200 import plots
+    rng = np.random.default_rng(1)
+    samples = rng.standard_normal((7, 40))
+    for level in (0.95, 0.9, 0.5, 1.0):
+        lo, hi = plots.confidence_bounds(samples, level)
+        n_rej = int(np.floor((1 - level) * samples.shape[1] / 2))
+        for i in range(samples.shape[0]):
+            o = np.sort(samples[i, :])
+            assert lo[i] == o[n_rej] and hi[i] == o[-(n_rej + 1)]
+    # the plotting functions themselves need optional packages: a clear ImportError when those are missing, never at import
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="matplotlib"):
+            plots.plot_dofU_vs_t(0, np.arange(3.), np.zeros((2, 3)))

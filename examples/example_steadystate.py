@@ -13,6 +13,7 @@ from thermoelasticity_fem_b200.materials import LinearThermoElastic
 from thermoelasticity_fem_b200.mesh import Mesh
 from thermoelasticity_fem_b200.model import Model
 from thermoelasticity_fem_b200.solvers import LinearSteadyState
+from thermoelasticity_fem_b200.plots import export_U_T
 
 from _mesh_fixture import sandwich_msh_path
 
@@ -38,6 +39,11 @@ if __name__ == '__main__':
 
     solver = LinearSteadyState(model)
     solver.solve()
+
+    # The reference ends with plot_U_T(solver.model.mesh, solver.T, solver.U, save_path='./steadystate.png') (pyvista).
+    # The same data as a binary VTK file that ParaView / pyvista open (no optional package needed):
+    if len(sys.argv) > 1:
+        print('wrote', export_U_T(solver.model.mesh, solver.T, solver.U, sys.argv[1]))
 
     print(f'max|U| = {np.abs(solver.U).max():.16g}   T in [{solver.T.min():.16g}, {solver.T.max():.16g}]')
     print(f'BiCGSTAB: {solver.solve_info}   timings: {solver.timings}')
